@@ -1,0 +1,736 @@
+// Implicit-GEMM convolutions on the 5th-generation tensor cores (tcgen05.mma, accumulators in
+// TMEM, operands staged by TMA into SWIZZLE_128B shared memory).
+//
+//  igemm_nt_kernel : forward and data-gradient.   D[pixel][cout] = sum_k A[pixel][k] * B[cout][k]
+//      A tile = 128 output pixels (TH x TW rectangle of one image) x 64 input channels, loaded by
+//      ONE 4-D TMA box per filter tap from the NHWC activation (the tap is a coordinate offset;
+//      out-of-bounds rows/columns are zero-filled by TMA, which implements the padding).
+//      Stride-2 convolutions read through per-parity views of the input (base + parity offset,
+//      doubled W/H strides) so that every tap is still a dense box.
+//  igemm_tn_kernel : weight-gradient.   D[(tap,cin)][cout] = sum_pixels X[pixel+tap][cin] * dY[pixel][cout]
+//      both operands are "MN-major" (the reduction index = pixel is the slow smem dimension).
+//
+// Both kernels are persistent (grid = #SMs), warp-specialised: warp 0 = TMA producer,
+// warp 1 = MMA issuer (+ TMEM allocation), warps 2..5 = epilogue (one TMEM lane quadrant each).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ecgmm {
+
+struct Tap {
+  int16_t map;  // which activation tensor map
+  int16_t dh;   // row offset added to the tile origin
+  int16_t dw;   // column offset
+  int16_t id;   // filter tap index r*S+s (wgrad output addressing)
+  int32_t wk;   // K offset of this tap inside the weight matrix
+};
+
+constexpr int kMaxTaps = 16;
+constexpr int kATile = 128 * 128;  // 128 pixels x 64 bf16 = 16 KiB
+
+struct alignas(64) NtParams {
+  CUtensorMap a_maps[4];
+  CUtensorMap b_map;
+  Tap taps[kMaxTaps];
+  int ntaps;
+  int k_chunks;  // 64-wide K chunks per tap (= Cin/64 forward, Cout/64 dgrad)
+  int TH, TW, tw_shift;
+  int tiles_h, tiles_w, n_img, n_tiles_n, total_tiles;
+  int OH, OW;  // valid extent of the tile grid
+  __nv_bfloat16* out;
+  long long out_sN, out_sH, out_sW;  // element strides of the output pixel grid
+  int accumulate;
+};
+
+template <int BN, int STAGES>
+struct NtSmem {
+  static constexpr int kBTile = BN * 128;
+  static constexpr int kStage = kATile + kBTile;
+  static constexpr int kBarOff = STAGES * kStage;
+  static constexpr int kBytes = kBarOff + 256 + 1024;  // barriers + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1) igemm_nt_kernel(const __grid_constant__ NtParams p) {
+  using L = NtSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kATile;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_maps[i]);
+    tma_prefetch_desc(&p.b_map);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nkb = p.ntaps * p.k_chunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles_n;
+        int m = t / p.n_tiles_n;
+        const int twi = m % p.tiles_w;
+        m /= p.tiles_w;
+        const int thi = m % p.tiles_h;
+        const int img = m / p.tiles_h;
+        const int h0 = thi * p.TH, w0 = twi * p.TW;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int tap = kb / p.k_chunks;
+          const int kc = kb - tap * p.k_chunks;
+          const Tap tp = p.taps[tap];
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], L::kStage);
+          tma_load_4d(sA + stage * kATile, &p.a_maps[tp.map], &full[stage], kc * 64, w0 + tp.dw, h0 + tp.dh, img);
+          tma_load_2d(sB + stage * L::kBTile, &p.b_map, &full[stage], tp.wk + kc * 64, nt * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t a_desc = make_sw128_desc(sA_addr + stage * kATile, 0, 1024);
+          const uint64_t b_desc = make_sw128_desc(sB_addr + stage * L::kBTile, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 4 x (K = 16) per 64-wide chunk; +32 B inside the swizzle atom
+            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty[stage]);
+          if (kb == nkb - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    const int quad = warp & 3;
+    const int m_row = quad * 32 + lane;
+    const int hl = m_row >> p.tw_shift;
+    const int wl = m_row & (p.TW - 1);
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int nt = t % p.n_tiles_n;
+      int m = t / p.n_tiles_n;
+      const int twi = m % p.tiles_w;
+      m /= p.tiles_w;
+      const int thi = m % p.tiles_h;
+      const int img = m / p.tiles_h;
+      const int oh = thi * p.TH + hl, ow = twi * p.TW + wl;
+      const bool valid = (oh < p.OH) && (ow < p.OW);
+      __nv_bfloat16* dst = p.out + img * p.out_sN + oh * p.out_sH + ow * p.out_sW + nt * BN;
+
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c * 32, r);
+        tmem_ld_wait();
+        if (valid) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[q * 8 + j]);
+            if (p.accumulate) {
+              const uint4 old = d4[q];
+              const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 o = __bfloat1622float2(ob[j]);
+                f[2 * j] += o.x;
+                f[2 * j + 1] += o.y;
+              }
+            }
+            uint4 v;
+            __nv_bfloat162* vb = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) vb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            d4[q] = v;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+template <int BN, int STAGES>
+static int launch_nt_t(const NtParams& p, cudaStream_t s) {
+  using L = NtSmem<BN, STAGES>;
+  static bool configured = false;  // one host thread per process drives a GPU (header contract)
+  if (!configured) {
+    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::kBytes));
+    configured = true;
+  }
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  igemm_nt_kernel<BN, STAGES><<<grid, 192, L::kBytes, s>>>(p);
+  return check_launch("igemm_nt_kernel");
+}
+
+// n_gemm = GEMM N extent (Cout forward, Cin dgrad)
+static int launch_nt(NtParams& p, int n_gemm, cudaStream_t s) {
+  ECGMM_CHECK(n_gemm % 64 == 0, ECGMM_ERR_SHAPE, "GEMM N=%d must be a multiple of 64", n_gemm);
+  int bn = (n_gemm % 256 == 0) ? 256 : (n_gemm % 128 == 0 ? 128 : 64);
+  p.n_tiles_n = n_gemm / bn;
+  p.total_tiles = p.n_img * p.tiles_h * p.tiles_w * p.n_tiles_n;
+  if (p.total_tiles == 0) return ECGMM_OK;
+  if (bn == 256) return launch_nt_t<256, 4>(p, s);
+  if (bn == 128) return launch_nt_t<128, 6>(p, s);
+  return launch_nt_t<64, 6>(p, s);
+}
+
+static void set_tile_grid(NtParams& p, int n_img, int OH, int OW) {
+  pick_tile(OH, OW, 128, &p.TH, &p.TW);
+  p.tw_shift = 0;
+  while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
+  p.tiles_h = ceil_div(OH, p.TH);
+  p.tiles_w = ceil_div(OW, p.TW);
+  p.n_img = n_img;
+  p.OH = OH;
+  p.OW = OW;
+}
+
+static int check_conv_cfg(int Cin, int Cout, int R, int S, int stride, int padH, int padW) {
+  ECGMM_CHECK(Cin > 0 && Cout > 0 && Cin % 64 == 0 && Cout % 64 == 0, ECGMM_ERR_SHAPE,
+              "conv channels must be positive multiples of 64 (Cin=%d Cout=%d)", Cin, Cout);
+  ECGMM_CHECK((R == 1 || R == 3) && (S == 1 || S == 3) && R * S <= kMaxTaps, ECGMM_ERR_SHAPE,
+              "unsupported filter %dx%d", R, S);
+  ECGMM_CHECK(stride == 1 || stride == 2, ECGMM_ERR_SHAPE, "unsupported stride %d", stride);
+  ECGMM_CHECK(padH == R / 2 && padW == S / 2, ECGMM_ERR_SHAPE, "padding must be (R/2,S/2), got (%d,%d)", padH,
+              padW);
+  return ECGMM_OK;
+}
+
+// Activation views for a convolution input x[N][H][W][C] read with `stride`:
+// stride 1 -> map 0 is the plain tensor; stride 2 -> map (ph*2+pw) is the parity sub-lattice.
+static int make_input_maps(CUtensorMap* maps, bool* used, const __nv_bfloat16* x, int N, int H, int W, int C,
+                           int stride, int box_w, int box_h) {
+  const uint64_t e = sizeof(__nv_bfloat16);
+  if (stride == 1) {
+    used[0] = true;
+    return make_tmap_4d(&maps[0], x, C, W, H, N, (uint64_t)C * e, (uint64_t)W * C * e, (uint64_t)H * W * C * e, 64,
+                        box_w, box_h);
+  }
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      const int id = ph * 2 + pw;
+      if (!used[id]) continue;
+      const int Hp = (H - ph + 1) / 2, Wp = (W - pw + 1) / 2;
+      ECGMM_CHECK(Hp > 0 && Wp > 0, ECGMM_ERR_SHAPE, "empty parity view (H=%d W=%d)", H, W);
+      int rc = make_tmap_4d(&maps[id], x + ((size_t)ph * W + pw) * C, C, Wp, Hp, N, 2ull * C * e, 2ull * W * C * e,
+                            (uint64_t)H * W * C * e, 64, box_w, box_h);
+      if (rc) return rc;
+    }
+  return ECGMM_OK;
+}
+
+// floor division by 2 for possibly negative values
+static inline int fdiv2(int v) { return (v >= 0) ? v / 2 : -((-v + 1) / 2); }
+
+// Fill the forward tap table (also used by wgrad: same input addressing).
+static int build_fwd_taps(Tap* taps, bool* used, int R, int S, int stride, int padH, int padW, int k_per_tap) {
+  int n = 0;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      Tap t;
+      if (stride == 1) {
+        t.map = 0;
+        t.dh = r - padH;
+        t.dw = s - padW;
+      } else {
+        const int ph = (r - padH) & 1, pw = (s - padW) & 1;
+        t.map = ph * 2 + pw;
+        t.dh = fdiv2(r - padH - ph);
+        t.dw = fdiv2(s - padW - pw);
+      }
+      used[t.map] = true;
+      t.id = r * S + s;
+      t.wk = (r * S + s) * k_per_tap;
+      taps[n++] = t;
+    }
+  return n;
+}
+
+}  // namespace ecgmm
+
+using namespace ecgmm;
+
+extern "C" int ecgmm_conv2d_fwd(const ecgmm_bf16* x_, const ecgmm_bf16* w_, ecgmm_bf16* y_, int N, int H, int W,
+                                int Cin, int Cout, int R, int S, int stride, int padH, int padW, void* stream) {
+  ECGMM_CHECK(x_ && w_ && y_, ECGMM_ERR_ARG, "conv2d_fwd: null pointer");
+  int rc = check_conv_cfg(Cin, Cout, R, S, stride, padH, padW);
+  if (rc) return rc;
+  if (N == 0) return ECGMM_OK;
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(x_);
+  const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
+  NtParams p;
+  memset(&p, 0, sizeof(p));
+  set_tile_grid(p, N, Ho, Wo);
+  bool used[4] = {false, false, false, false};
+  p.ntaps = build_fwd_taps(p.taps, used, R, S, stride, padH, padW, Cin);
+  p.k_chunks = Cin / 64;
+  rc = make_input_maps(p.a_maps, used, x, N, H, W, Cin, stride, p.TW, p.TH);
+  if (rc) return rc;
+  for (int i = 1; i < 4; ++i)
+    if (!used[i]) p.a_maps[i] = p.a_maps[p.taps[0].map];
+  if (!used[0]) p.a_maps[0] = p.a_maps[p.taps[0].map];
+  const int bn = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  rc = make_tmap_2d(&p.b_map, w_, (uint64_t)R * S * Cin, Cout, (uint64_t)R * S * Cin * 2, 64, bn);
+  if (rc) return rc;
+  p.out = reinterpret_cast<__nv_bfloat16*>(y_);
+  p.out_sW = Cout;
+  p.out_sH = (long long)Wo * Cout;
+  p.out_sN = (long long)Ho * Wo * Cout;
+  p.accumulate = 0;
+  return launch_nt(p, Cout, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ecgmm_conv2d_dgrad(const ecgmm_bf16* dy_, const ecgmm_bf16* wt_, ecgmm_bf16* dx_, int N, int H,
+                                  int W, int Cin, int Cout, int R, int S, int stride, int padH, int padW,
+                                  int accumulate, void* stream) {
+  ECGMM_CHECK(dy_ && wt_ && dx_, ECGMM_ERR_ARG, "conv2d_dgrad: null pointer");
+  int rc = check_conv_cfg(Cin, Cout, R, S, stride, padH, padW);
+  if (rc) return rc;
+  if (N == 0) return ECGMM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(dy_);
+  __nv_bfloat16* dx = reinterpret_cast<__nv_bfloat16*>(dx_);
+  const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
+  const uint64_t e = 2;
+  const int bn = (Cin % 256 == 0) ? 256 : (Cin % 128 == 0 ? 128 : 64);
+
+  // Input positions of parity (ph,pw) only receive taps with (ph+padH-r) and (pw+padW-s) even.
+  const int nph = (stride == 2 && H > 1) ? 2 : 1, npw = (stride == 2 && W > 1) ? 2 : 1;
+  bool need_zero = false;
+  if (stride == 2 && !accumulate) {
+    for (int ph = 0; ph < nph; ++ph)
+      for (int pw = 0; pw < npw; ++pw) {
+        int cnt = 0;
+        for (int r = 0; r < R; ++r)
+          for (int s = 0; s < S; ++s)
+            if (((ph + padH - r) & 1) == 0 && ((pw + padW - s) & 1) == 0) ++cnt;
+        if (cnt == 0) need_zero = true;
+      }
+    if (need_zero) ECGMM_CUDA(cudaMemsetAsync(dx, 0, (size_t)N * H * W * Cin * e, st));
+  }
+
+  for (int ph = 0; ph < nph; ++ph)
+    for (int pw = 0; pw < npw; ++pw) {
+      NtParams p;
+      memset(&p, 0, sizeof(p));
+      int n = 0;
+      for (int r = 0; r < R; ++r)
+        for (int s = 0; s < S; ++s) {
+          Tap t;
+          t.map = 0;
+          t.id = r * S + s;
+          t.wk = (r * S + s) * Cout;
+          if (stride == 1) {
+            t.dh = padH - r;
+            t.dw = padW - s;
+          } else {
+            if (((ph + padH - r) & 1) || ((pw + padW - s) & 1)) continue;
+            t.dh = (ph + padH - r) / 2;
+            t.dw = (pw + padW - s) / 2;
+          }
+          p.taps[n++] = t;
+        }
+      if (n == 0) continue;
+      p.ntaps = n;
+      p.k_chunks = Cout / 64;
+      const int Hc = (stride == 1) ? H : (H - ph + 1) / 2, Wc = (stride == 1) ? W : (W - pw + 1) / 2;
+      if (Hc <= 0 || Wc <= 0) continue;
+      set_tile_grid(p, N, Hc, Wc);
+      rc = make_tmap_4d(&p.a_maps[0], dy, Cout, Wo, Ho, N, (uint64_t)Cout * e, (uint64_t)Wo * Cout * e,
+                        (uint64_t)Ho * Wo * Cout * e, 64, p.TW, p.TH);
+      if (rc) return rc;
+      for (int i = 1; i < 4; ++i) p.a_maps[i] = p.a_maps[0];
+      rc = make_tmap_2d(&p.b_map, wt_, (uint64_t)R * S * Cout, Cin, (uint64_t)R * S * Cout * 2, 64, bn);
+      if (rc) return rc;
+      p.out = dx + ((size_t)ph * W + pw) * Cin * (stride == 2 ? 1 : 0);
+      p.out_sW = (long long)stride * Cin;
+      p.out_sH = (long long)stride * W * Cin;
+      p.out_sN = (long long)H * W * Cin;
+      p.accumulate = accumulate;
+      rc = launch_nt(p, Cin, st);
+      if (rc) return rc;
+    }
+  return ECGMM_OK;
+}
+
+// =====================================================================================
+// Weight gradient
+// =====================================================================================
+namespace ecgmm {
+
+constexpr int kKPix = 32;          // output pixels (GEMM K) per pipeline stage
+constexpr int kBox = kKPix * 128;  // one TMA box: 32 pixel rows x 64 channels = 4 KiB
+
+struct alignas(64) TnParams {
+  CUtensorMap x_maps[4];
+  CUtensorMap dy_map;
+  Tap taps[kMaxTaps];
+  int ntaps;
+  int cin_chunks;  // Cin / 64
+  int n_atoms;     // ntaps * cin_chunks : 64-row pieces of the dW matrix
+  int n_slots;     // ceil(n_atoms / 2)  : 128-row accumulators
+  int slots_per_group, n_groups_m, n_tiles_n, ksplit;
+  int TH, TW, tiles_h, tiles_w, n_img, total_kblocks;
+  float* dw;
+  int Cin, Cout, RS;
+  int mode;  // 0: dw is OIHW [Cout][Cin][R][S];  1: ResNet stem (space-to-depth atoms -> [64][3][7][7])
+};
+
+template <int BN, int SMAX, int STAGES>
+struct TnSmem {
+  static constexpr int kNB = BN / 64;  // dY boxes per stage
+  static constexpr int kStage = (kNB + 2 * SMAX) * kBox;
+  static constexpr int kBarOff = STAGES * kStage;
+  static constexpr int kBytes = kBarOff + 256 + 1024;
+};
+
+template <int BN, int SMAX, int STAGES>
+__global__ void __launch_bounds__(192, 1) igemm_tn_kernel(const __grid_constant__ TnParams p) {
+  using L = TnSmem<BN, SMAX, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.x_maps[i]);
+    tma_prefetch_desc(&p.dy_map);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work decomposition: blockIdx -> (k-split id, slot group, N tile)
+  const int ks = blockIdx.x % p.ksplit;
+  const int g = blockIdx.x / p.ksplit;
+  const int gm = g % p.n_groups_m;
+  const int nt = g / p.n_groups_m;
+  const int s0 = gm * p.slots_per_group;
+  const int ns = min(p.slots_per_group, p.n_slots - s0);
+  const int per = (p.total_kblocks + p.ksplit - 1) / p.ksplit;
+  const int kb0 = ks * per;
+  const int kb1 = min(p.total_kblocks, kb0 + per);
+  const bool has_work = (kb0 < kb1) && (ns > 0);
+
+  if (has_work) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          int m = kb;
+          const int twi = m % p.tiles_w;
+          m /= p.tiles_w;
+          const int thi = m % p.tiles_h;
+          const int img = m / p.tiles_h;
+          const int h0 = thi * p.TH, w0 = twi * p.TW;
+          uint8_t* st = smem + stage * L::kStage;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], (L::kNB + 2 * ns) * kBox);
+#pragma unroll
+          for (int j = 0; j < L::kNB; ++j)
+            tma_load_4d(st + j * kBox, &p.dy_map, &full[stage], nt * BN + j * 64, w0, h0, img);
+          for (int i = 0; i < 2 * ns; ++i) {
+            int atom = 2 * s0 + i;
+            if (atom >= p.n_atoms) atom = p.n_atoms - 1;  // odd atom count: dummy second half
+            const int tap = atom / p.cin_chunks;
+            const int cc = atom - tap * p.cin_chunks;
+            const Tap tp = p.taps[tap];
+            tma_load_4d(st + (L::kNB + i) * kBox, &p.x_maps[tp.map], &full[stage], cc * 64, w0 + tp.dw, h0 + tp.dh,
+                        img);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+      const uint32_t s_addr = smem_u32(smem);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = s_addr + stage * L::kStage;
+          // MN-major operands: 64-wide atoms kBox bytes apart (LBO), 8 K-rows = 1024 B (SBO)
+          const uint64_t b_desc = make_sw128_desc(st, kBox, 1024);
+          for (int i = 0; i < ns; ++i) {
+            const uint64_t a_desc = make_sw128_desc(st + (L::kNB + 2 * i) * kBox, kBox, 1024);
+#pragma unroll
+            for (int k = 0; k < kKPix / 16; ++k)  // 16 K-rows = 2048 B further into the box
+              umma_bf16(tmem_base + i * BN, a_desc + k * 128, b_desc + k * 128, idesc, (kb > kb0) || (k > 0));
+          }
+          umma_commit(&empty[stage]);
+          if (kb == kb1 - 1) umma_commit(tfull);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    } else {
+      const int quad = warp & 3;
+      const int m_row = quad * 32 + lane;
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+      for (int i = 0; i < ns; ++i) {
+        const int atom = 2 * (s0 + i) + (m_row >> 6);
+        const bool row_ok = atom < p.n_atoms;
+        const int a_c = row_ok ? atom : 0;
+        const int tap = a_c / p.cin_chunks;
+        const int cc = a_c - tap * p.cin_chunks;
+        const int e = m_row & 63;
+        long long row_off = 0, col_stride = 0;
+        bool ok = row_ok;
+        if (p.mode == 0) {
+          const int cin = cc * 64 + e;
+          row_off = (long long)cin * p.RS + p.taps[tap].id;
+          col_stride = (long long)p.Cin * p.RS;
+        } else {
+          const int ra = p.taps[tap].id, sa = e >> 4, ch = e & 15;
+          const int dr = ch / 6, ds = (ch % 6) / 3, c = ch % 3;
+          const int r = 2 * ra + dr, s = 2 * sa + ds;
+          ok = ok && ch < 12 && r < 7 && s < 7;
+          row_off = ((long long)c * 7 + r) * 7 + s;
+          col_stride = 147;
+        }
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + i * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + c * 32, r);
+          tmem_ld_wait();
+          if (ok) {
+            float* dst = p.dw + row_off + (long long)(nt * BN + c * 32) * col_stride;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + j * col_stride, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int BN, int SMAX, int STAGES>
+static int launch_tn_t(TnParams& p, cudaStream_t s) {
+  using L = TnSmem<BN, SMAX, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    ECGMM_CUDA(cudaFuncSetAttribute(igemm_tn_kernel<BN, SMAX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::kBytes));
+    configured = true;
+  }
+  p.n_atoms = p.ntaps * p.cin_chunks;
+  p.n_slots = (p.n_atoms + 1) / 2;
+  p.n_groups_m = ceil_div(p.n_slots, SMAX);
+  p.slots_per_group = ceil_div(p.n_slots, p.n_groups_m);
+  p.n_tiles_n = p.Cout / BN;
+  const int groups = p.n_groups_m * p.n_tiles_n;
+  int ksplit = num_sms() / groups;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > p.total_kblocks) ksplit = p.total_kblocks;
+  p.ksplit = ksplit;
+  igemm_tn_kernel<BN, SMAX, STAGES><<<groups * ksplit, 192, L::kBytes, s>>>(p);
+  return check_launch("igemm_tn_kernel");
+}
+
+static int launch_tn(TnParams& p, cudaStream_t s) {
+  if (p.total_kblocks == 0) return ECGMM_OK;
+  if (p.Cout % 256 == 0) return launch_tn_t<256, 2, 6>(p, s);
+  if (p.Cout % 128 == 0) return launch_tn_t<128, 4, 4>(p, s);
+  return launch_tn_t<64, 5, 4>(p, s);
+}
+
+}  // namespace ecgmm
+
+extern "C" int ecgmm_conv2d_wgrad(const ecgmm_bf16* x_, const ecgmm_bf16* dy_, float* dw, int N, int H, int W,
+                                  int Cin, int Cout, int R, int S, int stride, int padH, int padW, void* stream) {
+  ECGMM_CHECK(x_ && dy_ && dw, ECGMM_ERR_ARG, "conv2d_wgrad: null pointer");
+  int rc = check_conv_cfg(Cin, Cout, R, S, stride, padH, padW);
+  if (rc) return rc;
+  if (N == 0) return ECGMM_OK;
+  const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
+  TnParams p;
+  memset(&p, 0, sizeof(p));
+  pick_tile(Ho, Wo, kKPix, &p.TH, &p.TW);
+  p.tiles_h = ceil_div(Ho, p.TH);
+  p.tiles_w = ceil_div(Wo, p.TW);
+  p.n_img = N;
+  p.total_kblocks = N * p.tiles_h * p.tiles_w;
+  bool used[4] = {false, false, false, false};
+  p.ntaps = build_fwd_taps(p.taps, used, R, S, stride, padH, padW, Cin);
+  p.cin_chunks = Cin / 64;
+  rc = make_input_maps(p.x_maps, used, reinterpret_cast<const __nv_bfloat16*>(x_), N, H, W, Cin, stride, p.TW, p.TH);
+  if (rc) return rc;
+  for (int i = 0; i < 4; ++i)
+    if (!used[i]) p.x_maps[i] = p.x_maps[p.taps[0].map];
+  rc = make_tmap_4d(&p.dy_map, dy_, Cout, Wo, Ho, N, (uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2,
+                    (uint64_t)Ho * Wo * Cout * 2, 64, p.TW, p.TH);
+  if (rc) return rc;
+  p.dw = dw;
+  p.Cin = Cin;
+  p.Cout = Cout;
+  p.RS = R * S;
+  p.mode = 0;
+  return launch_tn(p, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------- ResNet stem
+extern "C" void ecgmm_stem_s2d_dims(int H, int W, int* Hs, int* Ws) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  if (Hs) *Hs = Ho + 3;
+  if (Ws) *Ws = Wo + 3;
+}
+
+static int stem_input_map(CUtensorMap* m, const ecgmm_bf16* xs, int N, int H, int W, int box_w, int box_h) {
+  int Hs, Ws;
+  ecgmm_stem_s2d_dims(H, W, &Hs, &Ws);
+  const int Wo = Ws - 3;
+  // column b of the view = the 64 contiguous elements (4 pixels x 16 ch) starting at pixel b:
+  // consecutive columns overlap (stride 32 B), which turns the 4 horizontal taps into GEMM K.
+  return make_tmap_4d(m, xs, 64, Wo, Hs, N, 32, (uint64_t)Ws * 32, (uint64_t)Hs * Ws * 32, 64, box_w, box_h);
+}
+
+extern "C" int ecgmm_stem_conv_fwd(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, int N, int H,
+                                   int W, void* stream) {
+  ECGMM_CHECK(xs && w_s2d && y, ECGMM_ERR_ARG, "stem_conv_fwd: null pointer");
+  if (N == 0) return ECGMM_OK;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  NtParams p;
+  memset(&p, 0, sizeof(p));
+  set_tile_grid(p, N, Ho, Wo);
+  p.ntaps = 4;
+  for (int ra = 0; ra < 4; ++ra) p.taps[ra] = Tap{0, (int16_t)ra, 0, (int16_t)ra, ra * 64};
+  p.k_chunks = 1;
+  int rc = stem_input_map(&p.a_maps[0], xs, N, H, W, p.TW, p.TH);
+  if (rc) return rc;
+  for (int i = 1; i < 4; ++i) p.a_maps[i] = p.a_maps[0];
+  rc = make_tmap_2d(&p.b_map, w_s2d, 256, 64, 512, 64, 64);
+  if (rc) return rc;
+  p.out = reinterpret_cast<__nv_bfloat16*>(y);
+  p.out_sW = 64;
+  p.out_sH = (long long)Wo * 64;
+  p.out_sN = (long long)Ho * Wo * 64;
+  return launch_nt(p, 64, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ecgmm_stem_conv_wgrad(const ecgmm_bf16* xs, const ecgmm_bf16* dy, float* dw, int N, int H, int W,
+                                     void* stream) {
+  ECGMM_CHECK(xs && dy && dw, ECGMM_ERR_ARG, "stem_conv_wgrad: null pointer");
+  if (N == 0) return ECGMM_OK;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  TnParams p;
+  memset(&p, 0, sizeof(p));
+  pick_tile(Ho, Wo, kKPix, &p.TH, &p.TW);
+  p.tiles_h = ceil_div(Ho, p.TH);
+  p.tiles_w = ceil_div(Wo, p.TW);
+  p.n_img = N;
+  p.total_kblocks = N * p.tiles_h * p.tiles_w;
+  p.ntaps = 4;
+  for (int ra = 0; ra < 4; ++ra) p.taps[ra] = Tap{0, (int16_t)ra, 0, (int16_t)ra, ra * 64};
+  p.cin_chunks = 1;
+  int rc = stem_input_map(&p.x_maps[0], xs, N, H, W, p.TW, p.TH);
+  if (rc) return rc;
+  for (int i = 1; i < 4; ++i) p.x_maps[i] = p.x_maps[0];
+  rc = make_tmap_4d(&p.dy_map, dy, 64, Wo, Ho, N, 128, (uint64_t)Wo * 128, (uint64_t)Ho * Wo * 128, 64, p.TW, p.TH);
+  if (rc) return rc;
+  p.dw = dw;
+  p.Cin = 3;
+  p.Cout = 64;
+  p.RS = 49;
+  p.mode = 1;
+  return launch_tn(p, static_cast<cudaStream_t>(stream));
+}

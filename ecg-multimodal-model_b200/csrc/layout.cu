@@ -1,0 +1,163 @@
+// Layout / precision conversion kernels: NCHW fp32 <-> NHWC bf16, conv weight shadows,
+// and the space-to-depth staging of the ResNet stem input.
+#include "common.h"
+
+namespace ecgmm {
+
+// [N][C][P] fp32 -> [N][P][C] bf16 through a 32x32 shared-memory tile (P = H*W).
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int P) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* xn = x + (size_t)n * C * P;
+  __nv_bfloat16* yn = y + (size_t)n * C * P;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, pp = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && pp < P) ? xn[(size_t)c * P + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pp = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && pp < P) yn[(size_t)pp * C + c] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int P) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const __nv_bfloat16* xn = x + (size_t)n * C * P;
+  float* yn = y + (size_t)n * C * P;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pp = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && pp < P) ? __bfloat162float(xn[(size_t)pp * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, pp = p0 + threadIdx.x;
+    if (c < C && pp < P) yn[(size_t)c * P + pp] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void conv_weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w_fwd,
+                                        __nv_bfloat16* __restrict__ w_dgrad, int O, int I, int RS) {
+  const size_t total = (size_t)O * I * RS;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int t = idx % RS;
+    const int i = (idx / RS) % I;
+    const int o = idx / ((size_t)RS * I);
+    const __nv_bfloat16 v = __float2bfloat16(w[idx]);
+    if (w_fwd) w_fwd[((size_t)o * RS + t) * I + i] = v;
+    if (w_dgrad) w_dgrad[((size_t)i * RS + t) * O + o] = v;
+  }
+}
+
+// Stem weights [64][3][7][7] -> [64][ra(4)][sa(4)][ch16] with ch16 = (dr*2+ds)*3 + c,
+// r = 2*ra+dr, s = 2*sa+ds (taps with r == 7 or s == 7 and channels 12..15 are zero).
+__global__ void stem_weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ws) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 256) return;
+  const int ch = idx & 15, sa = (idx >> 4) & 3, ra = (idx >> 6) & 3, o = idx >> 8;
+  float v = 0.f;
+  if (ch < 12) {
+    const int dr = ch / 6, ds = (ch % 6) / 3, c = ch % 3;
+    const int r = 2 * ra + dr, s = 2 * sa + ds;
+    if (r < 7 && s < 7) v = w[((o * 3 + c) * 7 + r) * 7 + s];
+  }
+  ws[idx] = __float2bfloat16(v);
+}
+
+// xs[n][a][b][(dr*2+ds)*3+c] = x[n][c][2a+dr-3][2b+ds-3]  (zero outside the image, channels 12..15 zero)
+template <typename T>
+__global__ void stem_s2d_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ xs, int H, int W, int Hs,
+                                int Ws) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = blockIdx.y;
+  const int n = blockIdx.z;
+  if (b >= Ws) return;
+  const T* xn = x + (size_t)n * 3 * H * W;
+  __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+  for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+    for (int ds = 0; ds < 2; ++ds) {
+      const int ih = 2 * a + dr - 3, iw = 2 * b + ds - 3;
+      const bool in = (ih >= 0 && ih < H && iw >= 0 && iw < W);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float f = 0.f;
+        if (in) f = static_cast<float>(xn[((size_t)c * H + ih) * W + iw]);
+        v[(dr * 2 + ds) * 3 + c] = __float2bfloat16(f);
+      }
+    }
+#pragma unroll
+  for (int c = 12; c < 16; ++c) v[c] = __float2bfloat16(0.f);
+  uint4* dst = reinterpret_cast<uint4*>(xs + (((size_t)n * Hs + a) * Ws + b) * 16);
+  dst[0] = reinterpret_cast<const uint4*>(v)[0];
+  dst[1] = reinterpret_cast<const uint4*>(v)[1];
+}
+
+}  // namespace ecgmm
+
+using namespace ecgmm;
+
+extern "C" int ecgmm_nchw_f32_to_nhwc_bf16(const float* x, ecgmm_bf16* y, int N, int C, int H, int W,
+                                           void* stream) {
+  ECGMM_CHECK(x && y, ECGMM_ERR_ARG, "nchw_f32_to_nhwc_bf16: null pointer");
+  if (N == 0) return ECGMM_OK;
+  const int P = H * W;
+  dim3 grid(ceil_div(P, 32), ceil_div(C, 32), N), block(32, 8);
+  ECGMM_CHECK(grid.y <= 65535 && grid.z <= 65535, ECGMM_ERR_SHAPE, "layout grid too large");
+  nchw_to_nhwc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(y), C, P);
+  return check_launch("nchw_to_nhwc_kernel");
+}
+
+extern "C" int ecgmm_nhwc_bf16_to_nchw_f32(const ecgmm_bf16* x, float* y, int N, int C, int H, int W,
+                                           void* stream) {
+  ECGMM_CHECK(x && y, ECGMM_ERR_ARG, "nhwc_bf16_to_nchw_f32: null pointer");
+  if (N == 0) return ECGMM_OK;
+  const int P = H * W;
+  dim3 grid(ceil_div(P, 32), ceil_div(C, 32), N), block(32, 8);
+  ECGMM_CHECK(grid.y <= 65535 && grid.z <= 65535, ECGMM_ERR_SHAPE, "layout grid too large");
+  nhwc_to_nchw_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), y, C, P);
+  return check_launch("nhwc_to_nchw_kernel");
+}
+
+extern "C" int ecgmm_conv_weight_prep(const float* w, ecgmm_bf16* w_fwd, ecgmm_bf16* w_dgrad, int O, int I, int R,
+                                      int S, void* stream) {
+  ECGMM_CHECK(w && (w_fwd || w_dgrad), ECGMM_ERR_ARG, "conv_weight_prep: null pointer");
+  const size_t total = (size_t)O * I * R * S;
+  if (total == 0) return ECGMM_OK;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  conv_weight_prep_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(w_fwd), reinterpret_cast<__nv_bfloat16*>(w_dgrad), O, I, R * S);
+  return check_launch("conv_weight_prep_kernel");
+}
+
+extern "C" int ecgmm_stem_weight_prep(const float* w, ecgmm_bf16* w_s2d, void* stream) {
+  ECGMM_CHECK(w && w_s2d, ECGMM_ERR_ARG, "stem_weight_prep: null pointer");
+  stem_weight_prep_kernel<<<64, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(w_s2d));
+  return check_launch("stem_weight_prep_kernel");
+}
+
+extern "C" int ecgmm_stem_s2d(const void* x, int x_is_bf16, ecgmm_bf16* xs, int N, int H, int W, void* stream) {
+  ECGMM_CHECK(x && xs, ECGMM_ERR_ARG, "stem_s2d: null pointer");
+  if (N == 0) return ECGMM_OK;
+  int Hs, Ws;
+  ecgmm_stem_s2d_dims(H, W, &Hs, &Ws);
+  ECGMM_CHECK(Hs <= 65535 && N <= 65535, ECGMM_ERR_SHAPE, "stem_s2d: image too tall / batch too large");
+  dim3 grid(ceil_div(Ws, 128), Hs, N);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_is_bf16)
+    stem_s2d_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                        reinterpret_cast<__nv_bfloat16*>(xs), H, W, Hs, Ws);
+  else
+    stem_s2d_kernel<float><<<grid, 128, 0, st>>>(reinterpret_cast<const float*>(x),
+                                                 reinterpret_cast<__nv_bfloat16*>(xs), H, W, Hs, Ws);
+  return check_launch("stem_s2d_kernel");
+}

@@ -1,0 +1,87 @@
+"""ctypes binding of libecgmm.so (C ABI declared in include/ecgmm.h).
+
+The library is the only compute path of this package: if it is missing or the device is not
+sm_100 every operator raises -- there is no CPU or eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_int, c_void_p, c_float, c_double, c_longlong, c_char_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libecgmm.so")
+
+_p = c_void_p
+_i = c_int
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+SIGNATURES = {
+    "ecgmm_version": [],
+    "ecgmm_last_error": [],
+    "ecgmm_check_device": [],
+    "ecgmm_nchw_f32_to_nhwc_bf16": [_p, _p, _i, _i, _i, _i, _p],
+    "ecgmm_nhwc_bf16_to_nchw_f32": [_p, _p, _i, _i, _i, _i, _p],
+    "ecgmm_conv_weight_prep": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "ecgmm_stem_s2d_dims": [_i, _i, POINTER(c_int), POINTER(c_int)],
+    "ecgmm_stem_s2d": [_p, _i, _p, _i, _i, _i, _p],
+    "ecgmm_stem_weight_prep": [_p, _p, _p],
+    "ecgmm_stem_conv_fwd": [_p, _p, _p, _i, _i, _i, _p],
+    "ecgmm_stem_conv_wgrad": [_p, _p, _p, _i, _i, _i, _p],
+    "ecgmm_conv2d_fwd": [_p, _p, _p] + [_i] * 10 + [_p],
+    "ecgmm_conv2d_dgrad": [_p, _p, _p] + [_i] * 11 + [_p],
+    "ecgmm_conv2d_wgrad": [_p, _p, _p] + [_i] * 10 + [_p],
+}
+_RESTYPES = {"ecgmm_last_error": c_char_p, "ecgmm_stem_s2d_dims": None}
+
+
+class EcgmmError(RuntimeError):
+    """Raised when a libecgmm entry point returns a negative status."""
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen libecgmm.so and attach the prototypes; fails loudly when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C ecg-multimodal-model_b200/csrc`). There is no fallback path."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().ecgmm_last_error().decode("utf-8", "replace")
+
+
+def call(name: str, *args) -> None:
+    """Invoke an int-returning entry point and raise EcgmmError on failure."""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise EcgmmError(f"{name} failed with status {rc}: {last_error()}")
+
+
+def stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_device() -> None:
+    """Raise unless a CUDA device of compute capability 10.x is current."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise EcgmmError("ecgmm needs a CUDA device (sm_100); no CPU fallback exists")
+    call("ecgmm_check_device")
