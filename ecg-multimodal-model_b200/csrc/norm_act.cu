@@ -1,0 +1,695 @@
+// HBM-bound kernels around the convolutions: BatchNorm statistics / apply / backward (2-D and
+// 1-D), ReLU, residual add, squeeze-excite scaling, 3x3/s2 max-pool fused behind the stem
+// BatchNorm, global average pool.  Activations are channels-last bf16 [N][P][C] (P = H*W or L),
+// 8 channels (16 bytes) per thread; statistics and reductions are fp32 partials finalised in fp64.
+//
+// Reduction scheme (deterministic, no atomics): a grid of (SPLIT, N) CTAs each reduces a slab of
+// pixels of one sample for all C channels and writes one partial row [C]; a one-CTA-per-128-
+// channels finalize kernel folds the N*SPLIT rows.  Per-sample rows double as the squeeze
+// (mean over L) of the SE blocks of the 1-D ResNet.
+#include "common.h"
+#include "vec.cuh"
+
+namespace ecgmm {
+
+constexpr int kRedThreads = 256;
+
+// ------------------------------------------------------------------------------------------
+// forward statistics:  psum/psq [N][SPLIT][C] = sum / sum of squares over the slab
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRedThreads) chan_stats_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                  float* __restrict__ psum,
+                                                                  float* __restrict__ psq, int P, int C,
+                                                                  int rows_per_split) {
+  extern __shared__ float sred[];  // [rows][C] x 2
+  const int CG = C >> 3;
+  const int rows = kRedThreads / CG;
+  const int cg = threadIdx.x % CG, r = threadIdx.x / CG;
+  const int n = blockIdx.y, split = blockIdx.x;
+  const int p0 = split * rows_per_split;
+  const int p1 = min(P, p0 + rows_per_split);
+  const uint4* base = reinterpret_cast<const uint4*>(x + (size_t)n * P * C) + cg;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  int p = p0 + r;
+  for (; p + 3 * rows < p1; p += 4 * rows) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld_stream(base + (size_t)(p + u * rows) * CG);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        q[j] = fmaf(f[j], f[j], q[j]);
+      }
+    }
+  }
+  for (; p < p1; p += rows) {
+    float f[8];
+    unpack8(ld_stream(base + (size_t)p * CG), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += f[j];
+      q[j] = fmaf(f[j], f[j], q[j]);
+    }
+  }
+  float* ss = sred;
+  float* sq = sred + rows * C;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ss[r * C + cg * 8 + j] = s[j];
+    sq[r * C + cg * 8 + j] = q[j];
+  }
+  __syncthreads();
+  const size_t orow = ((size_t)n * gridDim.x + split) * C;
+  for (int c = threadIdx.x; c < C; c += kRedThreads) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < rows; ++i) {
+      a += ss[i * C + c];
+      b += sq[i * C + c];
+    }
+    psum[orow + c] = a;
+    psq[orow + c] = b;
+  }
+}
+
+// Fold the partial rows; emit mean / invstd (saved for backward), the affine (scale, shift) the
+// apply kernel uses, optional per-sample sums (SE squeeze) and the running-statistics update.
+//   conv_bias: the convolution in front has a bias that the conv kernel does NOT add; in
+//   training mode it only shifts the batch mean (and so running_mean), never the output.
+__global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int rows_total,
+                                   int split, int C, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps,
+                                   float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long long* __restrict__ num_batches,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   float* __restrict__ scale_out, float* __restrict__ shift_out,
+                                   float* __restrict__ nsum_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches) *num_batches += 1;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  if (nsum_out) {
+    const int N = rows_total / split;
+    for (int n = 0; n < N; ++n) {
+      float ns = 0.f;
+      for (int k = 0; k < split; ++k) {
+        const size_t i = ((size_t)n * split + k) * C + c;
+        ns += psum[i];
+        q += psq[i];
+      }
+      nsum_out[(size_t)n * C + c] = ns;
+      s += ns;
+    }
+  } else {
+    for (int i = 0; i < rows_total; ++i) {
+      s += psum[(size_t)i * C + c];
+      q += psq[(size_t)i * C + c];
+    }
+  }
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  mean_out[c] = (float)mean;
+  invstd_out[c] = invstd;
+  scale_out[c] = sc;
+  shift_out[c] = b - (float)mean * sc;
+  if (running_mean) {
+    const float bm = (float)mean + (conv_bias ? conv_bias[c] : 0.f);
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * bm;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// eval mode: (scale, shift) from the running statistics; the conv bias is folded into shift.
+__global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ conv_bias, const float* __restrict__ running_mean,
+                                      const float* __restrict__ running_var, float eps,
+                                      float* __restrict__ scale_out, float* __restrict__ shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = (gamma ? gamma[c] : 1.f) / sqrtf(running_var[c] + eps);
+  scale_out[c] = sc;
+  shift_out[c] = (beta ? beta[c] : 0.f) + ((conv_bias ? conv_bias[c] : 0.f) - running_mean[c]) * sc;
+}
+
+// ------------------------------------------------------------------------------------------
+// apply:  y = act((x*scale[c] + shift[c]) * se[n][c] + res)
+// ------------------------------------------------------------------------------------------
+template <bool SE, bool RES, bool RELU>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ x,
+                                                        const float* __restrict__ scale,
+                                                        const float* __restrict__ shift,
+                                                        const float* __restrict__ se,
+                                                        const __nv_bfloat16* __restrict__ res,
+                                                        __nv_bfloat16* __restrict__ y, int CG, size_t vec_per_sample,
+                                                        size_t total_vec) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += stride) {
+    const int cg = (int)(i % CG);
+    float f[8], sc[8], sh[8];
+    unpack8(ld_stream(reinterpret_cast<const uint4*>(x) + i), f);
+    load8f(scale + cg * 8, sc);
+    load8f(shift + cg * 8, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+    if (SE) {
+      const size_t n = i / vec_per_sample;
+      float g[8];
+      load8f(se + (n * CG + cg) * 8, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= g[j];
+    }
+    if (RES) {
+      float r[8];
+      unpack8(ld_stream(reinterpret_cast<const uint4*>(res) + i), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    }
+    if (RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    reinterpret_cast<uint4*>(y)[i] = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stem: y = maxpool3x3/s2/p1(relu(x*scale + shift)), arg = position of the maximum inside the
+// window (first maximum in row-major window order, torch's tie rule), 0..8
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ x,
+                                                               const float* __restrict__ scale,
+                                                               const float* __restrict__ shift,
+                                                               __nv_bfloat16* __restrict__ y,
+                                                               uint8_t* __restrict__ arg, int H, int W, int Ho,
+                                                               int Wo, int CG, size_t total_vec) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += stride) {
+    const int cg = (int)(i % CG);
+    size_t t = i / CG;
+    const int ow = (int)(t % Wo);
+    t /= Wo;
+    const int oh = (int)(t % Ho);
+    const size_t n = t / Ho;
+    float sc[8], sh[8], best[8];
+    int bi[8];
+    load8f(scale + cg * 8, sc);
+    load8f(shift + cg * 8, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      bi[j] = 0;
+    }
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int h = 2 * oh - 1 + dh;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const int w = 2 * ow - 1 + dw;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(reinterpret_cast<const uint4*>(x)[((n * H + h) * W + w) * CG + cg], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+          if (a > best[j]) {
+            best[j] = a;
+            bi[j] = dh * 3 + dw;
+          }
+        }
+      }
+    }
+    reinterpret_cast<uint4*>(y)[i] = pack8(best);
+    if (arg) {
+      uint2 a;
+      a.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      a.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      reinterpret_cast<uint2*>(arg)[i] = a;
+    }
+  }
+}
+
+// Gradient reaching the pre-pool activation at (h, w) for 8 channels: sum of the pooled
+// gradients of the (at most 4) windows whose recorded argmax is this pixel, gated by ReLU.
+__device__ __forceinline__ void pool_gather_dz(const __nv_bfloat16* __restrict__ dyp,
+                                               const uint8_t* __restrict__ arg, size_t n, int h, int w, int Ho,
+                                               int Wo, int CG, int cg, const float (&xv)[8], const float (&sc)[8],
+                                               const float (&sh)[8], float (&dz)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dz[j] = 0.f;
+  const int oh0 = h >> 1, oh1 = (h + 1) >> 1;  // equal when h is even
+  const int ow0 = w >> 1, ow1 = (w + 1) >> 1;
+  for (int oh = oh0; oh <= oh1; ++oh) {
+    if (oh >= Ho) continue;
+    const int dh = h - 2 * oh + 1;
+    for (int ow = ow0; ow <= ow1; ++ow) {
+      if (ow >= Wo) continue;
+      const int code = dh * 3 + (w - 2 * ow + 1);
+      const size_t o = ((n * Ho + oh) * Wo + ow) * CG + cg;
+      const uint2 a = reinterpret_cast<const uint2*>(arg)[o];
+      float g[8];
+      unpack8(reinterpret_cast<const uint4*>(dyp)[o], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int aj = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xff;
+        if (aj == code) dz[j] += g[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (fmaf(xv[j], sc[j], sh[j]) <= 0.f) dz[j] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward reductions:  p1/p2 [N][SPLIT][C] = sum dz, sum dz * xhat
+//   MODE 0: dz = dy     MODE 1: dz = dy * (y > 0)     MODE 2: stem (pool gather + relu gate)
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
+    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+    const uint8_t* __restrict__ arg, const float* __restrict__ mean, const float* __restrict__ invstd,
+    const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ p1,
+    float* __restrict__ p2, int P, int C, int rows_per_split, int H, int W, int Ho, int Wo) {
+  extern __shared__ float sred[];
+  const int CG = C >> 3;
+  const int rows = kRedThreads / CG;
+  const int cg = threadIdx.x % CG, r = threadIdx.x / CG;
+  const int n = blockIdx.y, split = blockIdx.x;
+  const int pa = split * rows_per_split;
+  const int pb = min(P, pa + rows_per_split);
+  float mu[8], is[8], sc[8], sh[8], s[8], q[8];
+  load8f(mean + cg * 8, mu);
+  load8f(invstd + cg * 8, is);
+  if (MODE == 2) {
+    load8f(scale + cg * 8, sc);
+    load8f(shift + cg * 8, sh);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  const size_t sbase = (size_t)n * P * CG + cg;
+  for (int p = pa + r; p < pb; p += rows) {
+    const size_t i = sbase + (size_t)p * CG;
+    float xv[8], dz[8];
+    unpack8(ld_stream(reinterpret_cast<const uint4*>(x) + i), xv);
+    if (MODE == 2) {
+      pool_gather_dz(dy, arg, n, p / W, p % W, Ho, Wo, CG, cg, xv, sc, sh, dz);
+    } else {
+      unpack8(ld_stream(reinterpret_cast<const uint4*>(dy) + i), dz);
+      if (MODE == 1) {
+        float yv[8];
+        unpack8(ld_stream(reinterpret_cast<const uint4*>(y) + i), yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (yv[j] <= 0.f) dz[j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += dz[j];
+      q[j] = fmaf(dz[j], (xv[j] - mu[j]) * is[j], q[j]);
+    }
+  }
+  float* ss = sred;
+  float* sq = sred + rows * C;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ss[r * C + cg * 8 + j] = s[j];
+    sq[r * C + cg * 8 + j] = q[j];
+  }
+  __syncthreads();
+  const size_t orow = ((size_t)n * gridDim.x + split) * C;
+  for (int c = threadIdx.x; c < C; c += kRedThreads) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < rows; ++i) {
+      a += ss[i * C + c];
+      b += sq[i * C + c];
+    }
+    p1[orow + c] = a;
+    p2[orow + c] = b;
+  }
+}
+
+// Fold the backward partials.  With du = dz*se[n][c] + q[n][c] (SE blocks; se = 1, q = 0
+// otherwise) the BatchNorm backward is   dx = A*se*dz + B*x + D + A*q   with per-channel
+//   A = gamma*invstd,  B = -gamma*invstd^2*m2,  D = -A*m1 + gamma*invstd^2*mean*m2,
+//   m1 = mean(du), m2 = mean(du*xhat);  dgamma = sum(du*xhat), dbeta = sum(du).
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int N, int split,
+                                       int C, double per_sample, const float* __restrict__ gamma,
+                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                       const float* __restrict__ se, const float* __restrict__ q,
+                                       const float* __restrict__ nsum, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ coefA,
+                                       float* __restrict__ coefB, float* __restrict__ coefD) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = mean[c], is = invstd[c];
+  double s1 = 0.0, s2 = 0.0;
+  for (int n = 0; n < N; ++n) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < split; ++k) {
+      const size_t i = ((size_t)n * split + k) * C + c;
+      a += p1[i];
+      b += p2[i];
+    }
+    if (se) {
+      const double g = se[(size_t)n * C + c], qq = q[(size_t)n * C + c];
+      const double sum_xhat = ((double)nsum[(size_t)n * C + c] - per_sample * mu) * is;
+      a = g * a + per_sample * qq;
+      b = g * b + qq * sum_xhat;
+    }
+    s1 += a;
+    s2 += b;
+  }
+  const double M = per_sample * N;
+  const double m1 = s1 / M, m2 = s2 / M;
+  const double g = gamma ? gamma[c] : 1.0;
+  if (dgamma) dgamma[c] = (float)s2;
+  if (dbeta) dbeta[c] = (float)s1;
+  const double A = g * is;
+  coefA[c] = (float)A;
+  coefB[c] = (float)(-g * is * is * m2);
+  coefD[c] = (float)(-A * m1 + g * is * is * mu * m2);
+}
+
+// dx = A*se*dz + B*x + D + A*q ;  optionally also stores dz (gradient of the residual branch).
+template <int MODE, bool SE>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+    const uint8_t* __restrict__ arg, const float* __restrict__ coefA, const float* __restrict__ coefB,
+    const float* __restrict__ coefD, const float* __restrict__ scale, const float* __restrict__ shift,
+    const float* __restrict__ se, const float* __restrict__ q, __nv_bfloat16* __restrict__ dx,
+    __nv_bfloat16* __restrict__ dz_out, int CG, size_t vec_per_sample, size_t total_vec, int H, int W, int Ho,
+    int Wo) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += stride) {
+    const int cg = (int)(i % CG);
+    const size_t n = i / vec_per_sample;
+    float xv[8], dz[8], A[8], B[8], D[8];
+    unpack8(ld_stream(reinterpret_cast<const uint4*>(x) + i), xv);
+    load8f(coefA + cg * 8, A);
+    load8f(coefB + cg * 8, B);
+    load8f(coefD + cg * 8, D);
+    if (MODE == 2) {
+      float sc[8], sh[8];
+      load8f(scale + cg * 8, sc);
+      load8f(shift + cg * 8, sh);
+      const size_t p = (i / CG) % ((size_t)H * W);
+      pool_gather_dz(dy, arg, n, (int)(p / W), (int)(p % W), Ho, Wo, CG, cg, xv, sc, sh, dz);
+    } else {
+      unpack8(ld_stream(reinterpret_cast<const uint4*>(dy) + i), dz);
+      if (MODE == 1) {
+        float yv[8];
+        unpack8(ld_stream(reinterpret_cast<const uint4*>(y) + i), yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (yv[j] <= 0.f) dz[j] = 0.f;
+      }
+    }
+    if (dz_out) reinterpret_cast<uint4*>(dz_out)[i] = pack8(dz);
+    float o[8];
+    if (SE) {
+      float g[8], qq[8];
+      load8f(se + (n * CG + cg) * 8, g);
+      load8f(q + (n * CG + cg) * 8, qq);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], fmaf(g[j], dz[j], qq[j]), fmaf(B[j], xv[j], D[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dz[j], fmaf(B[j], xv[j], D[j]));
+    }
+    reinterpret_cast<uint4*>(dx)[i] = pack8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// global average pool  [N][P][C] bf16 -> [N][C] fp32   and its backward (broadcast / P)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRedThreads) avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                   float* __restrict__ out, int P, int C) {
+  extern __shared__ float sred[];
+  const int CG = C >> 3;
+  const int rows = kRedThreads / CG;
+  const int cg = threadIdx.x % CG, r = threadIdx.x / CG;
+  const int n = blockIdx.x;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  const uint4* base = reinterpret_cast<const uint4*>(x + (size_t)n * P * C) + cg;
+  for (int p = r; p < P; p += rows) {
+    float f[8];
+    unpack8(ld_stream(base + (size_t)p * CG), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += f[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sred[r * C + cg * 8 + j] = s[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kRedThreads) {
+    float a = 0.f;
+    for (int i = 0; i < rows; ++i) a += sred[i * C + c];
+    out[(size_t)n * C + c] = a / (float)P;
+  }
+}
+
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dout,
+                                                           __nv_bfloat16* __restrict__ dx, int CG, float inv_p,
+                                                           size_t vec_per_sample, size_t total_vec) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += stride) {
+    const int cg = (int)(i % CG);
+    const size_t n = i / vec_per_sample;
+    float g[8];
+    load8f(dout + (n * CG + cg) * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= inv_p;
+    reinterpret_cast<uint4*>(dx)[i] = pack8(g);
+  }
+}
+
+static int stream_grid(size_t total_vec) {
+  size_t b = (total_vec + 255) / 256;
+  const size_t cap = (size_t)num_sms() * 8;
+  return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+static int check_c(int C, const char* who) {
+  ECGMM_CHECK(C >= 8 && C % 8 == 0 && C <= 2048 && (kRedThreads % (C >> 3) == 0 || (C >> 3) % kRedThreads == 0),
+              ECGMM_ERR_SHAPE, "%s: channel count %d must be 8 * a power of two <= 2048", who, C);
+  ECGMM_CHECK((C >> 3) <= kRedThreads, ECGMM_ERR_SHAPE, "%s: channel count %d too large", who, C);
+  return ECGMM_OK;
+}
+
+}  // namespace ecgmm
+
+using namespace ecgmm;
+typedef __nv_bfloat16 bf16;
+
+extern "C" int ecgmm_reduce_split(int N, int P, int C) {
+  if (N <= 0 || P <= 0 || C < 8) return 1;
+  const int rows = kRedThreads / (C >> 3) > 0 ? kRedThreads / (C >> 3) : 1;
+  const int want = ceil_div(num_sms() * 4, N);
+  int max_split = ceil_div(P, rows * 4);
+  if (max_split < 1) max_split = 1;
+  int s = want < 1 ? 1 : want;
+  if (s > max_split) s = max_split;
+  return s;
+}
+
+static inline int rows_per_split(int P, int split) { return ceil_div(P, split); }
+
+extern "C" int ecgmm_chan_stats(const ecgmm_bf16* x, float* psum, float* psq, int N, int P, int C, int split,
+                                void* stream) {
+  ECGMM_CHECK(x && psum && psq, ECGMM_ERR_ARG, "chan_stats: null pointer");
+  int rc = check_c(C, "chan_stats");
+  if (rc) return rc;
+  ECGMM_CHECK(split >= 1 && N <= 65535, ECGMM_ERR_SHAPE, "chan_stats: bad split %d / batch %d", split, N);
+  if (N == 0) return ECGMM_OK;
+  const int rows = kRedThreads / (C >> 3);
+  const size_t smem = (size_t)2 * rows * C * sizeof(float);
+  chan_stats_kernel<<<dim3(split, N), kRedThreads, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(x), psum, psq, P, C, rows_per_split(P, split));
+  return check_launch("chan_stats_kernel");
+}
+
+extern "C" int ecgmm_bn_finalize(const float* psum, const float* psq, int N, int split, int C, long long count,
+                                 const float* gamma, const float* beta, const float* conv_bias, float eps,
+                                 float momentum, float* running_mean, float* running_var, long long* num_batches,
+                                 float* mean, float* invstd, float* scale, float* shift, float* nsum,
+                                 void* stream) {
+  ECGMM_CHECK(psum && psq && mean && invstd && scale && shift, ECGMM_ERR_ARG, "bn_finalize: null pointer");
+  ECGMM_CHECK(count > 0, ECGMM_ERR_SHAPE, "bn_finalize: empty batch");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+      psum, psq, N * split, split, C, (double)count, gamma, beta, conv_bias, eps, momentum, running_mean,
+      running_var, num_batches, mean, invstd, scale, shift, nsum);
+  return check_launch("bn_finalize_kernel");
+}
+
+extern "C" int ecgmm_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* conv_bias,
+                                    const float* running_mean, const float* running_var, float eps, float* scale,
+                                    float* shift, void* stream) {
+  ECGMM_CHECK(running_mean && running_var && scale && shift, ECGMM_ERR_ARG, "bn_eval_coeffs: null pointer");
+  bn_eval_coeffs_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, conv_bias, running_mean,
+                                                                           running_var, eps, scale, shift);
+  return check_launch("bn_eval_coeffs_kernel");
+}
+
+extern "C" int ecgmm_bn_apply(const ecgmm_bf16* x_, const float* scale, const float* shift, const float* se,
+                              const ecgmm_bf16* res_, ecgmm_bf16* y_, int N, int P, int C, int relu,
+                              void* stream) {
+  ECGMM_CHECK(x_ && scale && shift && y_, ECGMM_ERR_ARG, "bn_apply: null pointer");
+  ECGMM_CHECK(C % 8 == 0, ECGMM_ERR_SHAPE, "bn_apply: C=%d not a multiple of 8", C);
+  const size_t vps = (size_t)P * (C >> 3), total = vps * N;
+  if (total == 0) return ECGMM_OK;
+  const bf16* x = reinterpret_cast<const bf16*>(x_);
+  const bf16* res = reinterpret_cast<const bf16*>(res_);
+  bf16* y = reinterpret_cast<bf16*>(y_);
+  const int g = stream_grid(total);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int CG = C >> 3;
+#define ECGMM_APPLY(SE_, RES_, RELU_) \
+  bn_apply_kernel<SE_, RES_, RELU_><<<g, 256, 0, st>>>(x, scale, shift, se, res, y, CG, vps, total)
+  const int key = (se ? 4 : 0) | (res ? 2 : 0) | (relu ? 1 : 0);
+  switch (key) {
+    case 0: ECGMM_APPLY(false, false, false); break;
+    case 1: ECGMM_APPLY(false, false, true); break;
+    case 2: ECGMM_APPLY(false, true, false); break;
+    case 3: ECGMM_APPLY(false, true, true); break;
+    case 4: ECGMM_APPLY(true, false, false); break;
+    case 5: ECGMM_APPLY(true, false, true); break;
+    case 6: ECGMM_APPLY(true, true, false); break;
+    default: ECGMM_APPLY(true, true, true); break;
+  }
+#undef ECGMM_APPLY
+  return check_launch("bn_apply_kernel");
+}
+
+extern "C" int ecgmm_bn_relu_maxpool(const ecgmm_bf16* x, const float* scale, const float* shift, ecgmm_bf16* y,
+                                     uint8_t* argmax, int N, int H, int W, int C, void* stream) {
+  ECGMM_CHECK(x && scale && shift && y, ECGMM_ERR_ARG, "bn_relu_maxpool: null pointer");
+  ECGMM_CHECK(C % 8 == 0, ECGMM_ERR_SHAPE, "bn_relu_maxpool: C=%d not a multiple of 8", C);
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const size_t total = (size_t)N * Ho * Wo * (C >> 3);
+  if (total == 0) return ECGMM_OK;
+  bn_relu_maxpool_kernel<<<stream_grid(total), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(x), scale, shift, reinterpret_cast<bf16*>(y), argmax, H, W, Ho, Wo, C >> 3,
+      total);
+  return check_launch("bn_relu_maxpool_kernel");
+}
+
+extern "C" int ecgmm_bn_bwd_reduce(const ecgmm_bf16* x, const ecgmm_bf16* dy, const ecgmm_bf16* y,
+                                   const uint8_t* argmax, const float* mean, const float* invstd,
+                                   const float* scale, const float* shift, float* p1, float* p2, int N, int H,
+                                   int W, int C, int split, int mode, void* stream) {
+  ECGMM_CHECK(x && dy && mean && invstd && p1 && p2, ECGMM_ERR_ARG, "bn_bwd_reduce: null pointer");
+  ECGMM_CHECK(mode >= 0 && mode <= 2, ECGMM_ERR_ARG, "bn_bwd_reduce: bad mode %d", mode);
+  ECGMM_CHECK(mode != 1 || y, ECGMM_ERR_ARG, "bn_bwd_reduce: mode 1 needs y");
+  ECGMM_CHECK(mode != 2 || (argmax && scale && shift), ECGMM_ERR_ARG, "bn_bwd_reduce: mode 2 needs argmax/scale/shift");
+  int rc = check_c(C, "bn_bwd_reduce");
+  if (rc) return rc;
+  ECGMM_CHECK(split >= 1 && N <= 65535, ECGMM_ERR_SHAPE, "bn_bwd_reduce: bad split %d / batch %d", split, N);
+  if (N == 0) return ECGMM_OK;
+  const int P = H * W;
+  const int rows = kRedThreads / (C >> 3);
+  const size_t smem = (size_t)2 * rows * C * sizeof(float);
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  dim3 grid(split, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bf16* xb = reinterpret_cast<const bf16*>(x);
+  const bf16* dyb = reinterpret_cast<const bf16*>(dy);
+  const bf16* yb = reinterpret_cast<const bf16*>(y);
+  const int rps = rows_per_split(P, split);
+  if (mode == 0)
+    bn_bwd_reduce_kernel<0><<<grid, kRedThreads, smem, st>>>(xb, dyb, yb, argmax, mean, invstd, scale, shift, p1, p2,
+                                                             P, C, rps, H, W, Ho, Wo);
+  else if (mode == 1)
+    bn_bwd_reduce_kernel<1><<<grid, kRedThreads, smem, st>>>(xb, dyb, yb, argmax, mean, invstd, scale, shift, p1, p2,
+                                                             P, C, rps, H, W, Ho, Wo);
+  else
+    bn_bwd_reduce_kernel<2><<<grid, kRedThreads, smem, st>>>(xb, dyb, yb, argmax, mean, invstd, scale, shift, p1, p2,
+                                                             P, C, rps, H, W, Ho, Wo);
+  return check_launch("bn_bwd_reduce_kernel");
+}
+
+extern "C" int ecgmm_bn_bwd_finalize(const float* p1, const float* p2, int N, int split, int C,
+                                     long long per_sample, const float* gamma, const float* mean,
+                                     const float* invstd, const float* se, const float* q, const float* nsum,
+                                     float* dgamma, float* dbeta, float* coefA, float* coefB, float* coefD,
+                                     void* stream) {
+  ECGMM_CHECK(p1 && p2 && mean && invstd && coefA && coefB && coefD, ECGMM_ERR_ARG, "bn_bwd_finalize: null pointer");
+  ECGMM_CHECK(!se || (q && nsum), ECGMM_ERR_ARG, "bn_bwd_finalize: SE mode needs q and nsum");
+  ECGMM_CHECK(N > 0 && per_sample > 0, ECGMM_ERR_SHAPE, "bn_bwd_finalize: empty batch");
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+      p1, p2, N, split, C, (double)per_sample, gamma, mean, invstd, se, q, nsum, dgamma, dbeta, coefA, coefB, coefD);
+  return check_launch("bn_bwd_finalize_kernel");
+}
+
+extern "C" int ecgmm_bn_bwd_apply(const ecgmm_bf16* x, const ecgmm_bf16* dy, const ecgmm_bf16* y,
+                                  const uint8_t* argmax, const float* coefA, const float* coefB, const float* coefD,
+                                  const float* scale, const float* shift, const float* se, const float* q,
+                                  ecgmm_bf16* dx, ecgmm_bf16* dz_out, int N, int H, int W, int C, int mode,
+                                  void* stream) {
+  ECGMM_CHECK(x && dy && coefA && coefB && coefD && dx, ECGMM_ERR_ARG, "bn_bwd_apply: null pointer");
+  ECGMM_CHECK(mode >= 0 && mode <= 2, ECGMM_ERR_ARG, "bn_bwd_apply: bad mode %d", mode);
+  ECGMM_CHECK(mode != 1 || y, ECGMM_ERR_ARG, "bn_bwd_apply: mode 1 needs y");
+  ECGMM_CHECK(mode != 2 || (argmax && scale && shift && !se), ECGMM_ERR_ARG, "bn_bwd_apply: bad mode-2 arguments");
+  ECGMM_CHECK(!se || q, ECGMM_ERR_ARG, "bn_bwd_apply: SE mode needs q");
+  ECGMM_CHECK(C % 8 == 0, ECGMM_ERR_SHAPE, "bn_bwd_apply: C=%d not a multiple of 8", C);
+  const size_t vps = (size_t)H * W * (C >> 3), total = vps * N;
+  if (total == 0) return ECGMM_OK;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int g = stream_grid(total);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bf16* xb = reinterpret_cast<const bf16*>(x);
+  const bf16* dyb = reinterpret_cast<const bf16*>(dy);
+  const bf16* yb = reinterpret_cast<const bf16*>(y);
+  bf16* dxb = reinterpret_cast<bf16*>(dx);
+  bf16* dzb = reinterpret_cast<bf16*>(dz_out);
+#define ECGMM_BWD(MODE_, SE_)                                                                                      \
+  bn_bwd_apply_kernel<MODE_, SE_><<<g, 256, 0, st>>>(xb, dyb, yb, argmax, coefA, coefB, coefD, scale, shift, se, q, \
+                                                     dxb, dzb, C >> 3, vps, total, H, W, Ho, Wo)
+  if (mode == 2)
+    ECGMM_BWD(2, false);
+  else if (mode == 1 && se)
+    ECGMM_BWD(1, true);
+  else if (mode == 1)
+    ECGMM_BWD(1, false);
+  else if (se)
+    ECGMM_BWD(0, true);
+  else
+    ECGMM_BWD(0, false);
+#undef ECGMM_BWD
+  return check_launch("bn_bwd_apply_kernel");
+}
+
+extern "C" int ecgmm_avgpool_fwd(const ecgmm_bf16* x, float* out, int N, int P, int C, void* stream) {
+  ECGMM_CHECK(x && out, ECGMM_ERR_ARG, "avgpool_fwd: null pointer");
+  int rc = check_c(C, "avgpool_fwd");
+  if (rc) return rc;
+  if (N == 0) return ECGMM_OK;
+  ECGMM_CHECK(P > 0, ECGMM_ERR_SHAPE, "avgpool_fwd: empty plane");
+  const int rows = kRedThreads / (C >> 3);
+  avgpool_fwd_kernel<<<N, kRedThreads, (size_t)rows * C * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(x), out, P, C);
+  return check_launch("avgpool_fwd_kernel");
+}
+
+extern "C" int ecgmm_avgpool_bwd(const float* dout, ecgmm_bf16* dx, int N, int P, int C, void* stream) {
+  ECGMM_CHECK(dout && dx, ECGMM_ERR_ARG, "avgpool_bwd: null pointer");
+  ECGMM_CHECK(C % 8 == 0, ECGMM_ERR_SHAPE, "avgpool_bwd: C=%d not a multiple of 8", C);
+  const size_t vps = (size_t)P * (C >> 3), total = vps * N;
+  if (total == 0) return ECGMM_OK;
+  avgpool_bwd_kernel<<<stream_grid(total), 256, 0, (cudaStream_t)stream>>>(dout, reinterpret_cast<bf16*>(dx), C >> 3,
+                                                                         1.f / (float)P, vps, total);
+  return check_launch("avgpool_bwd_kernel");
+}

@@ -1,0 +1,169 @@
+// Stem of the 1-D ResNet-SE: Conv1d(Cin in {1..16}, 64, k=7, s=2, p=3) over raw fp32 signals
+// [B][Cin][L] (reference: multimodal_paper_modal_balance.py:99-104, train_signal_12_af.py:184).
+// K = Cin*7 <= 112 is too small / misaligned for the tensor-core path, and the whole layer is
+// ~1 % of the signal branch traffic, so it is a shared-memory CUDA-core kernel.
+// Output is channels-last bf16 [B][Lo][64] WITHOUT the bias: in training the following BatchNorm
+// cancels it (it only shifts running_mean, handled by bn_finalize), in eval it is folded into
+// the BatchNorm shift.
+#include "common.h"
+#include "vec.cuh"
+
+namespace ecgmm {
+
+constexpr int kStemCo = 64;
+constexpr int kStemTile = 128;                 // output positions per CTA tile
+constexpr int kStemSpan = 2 * kStemTile + 5;   // input samples feeding one tile
+constexpr int kStemMaxCin = 16;
+
+__global__ void __launch_bounds__(256) signal_stem_fwd_kernel(const float* __restrict__ x,
+                                                               const float* __restrict__ w,
+                                                               __nv_bfloat16* __restrict__ y, int Cin, int L,
+                                                               int Lo) {
+  extern __shared__ float sm[];
+  float* xs = sm;                      // [Cin][kStemSpan]
+  float* ws = sm + Cin * kStemSpan;    // [Cin*7][64]
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * kStemTile;
+  const int K = Cin * 7;
+  for (int e = threadIdx.x; e < K * kStemCo; e += 256) {
+    const int o = e / K, k = e % K;
+    ws[k * kStemCo + o] = w[e];
+  }
+  const int i0 = 2 * p0 - 3;
+  for (int e = threadIdx.x; e < Cin * kStemSpan; e += 256) {
+    const int ci = e / kStemSpan, j = e % kStemSpan;
+    const int i = i0 + j;
+    xs[e] = (i >= 0 && i < L) ? x[((size_t)b * Cin + ci) * L + i] : 0.f;
+  }
+  __syncthreads();
+  const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int ci = 0; ci < Cin; ++ci) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      float wv[8];
+      load8f(ws + (ci * 7 + k) * kStemCo + cg * 8, wv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float xv = xs[ci * kStemSpan + 2 * (pl + 32 * i) + k];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv, wv[j], acc[i][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = p0 + pl + 32 * i;
+    if (p < Lo) reinterpret_cast<uint4*>(y + ((size_t)b * Lo + p) * kStemCo)[cg] = pack8(acc[i]);
+  }
+}
+
+// dW[o][ci][k] += sum_{b,p} dy[b][p][o] * x[b][ci][2p+k-3].  Each CTA walks (b, tile) pairs,
+// keeps its share of the 64*Cin*7 outputs in registers and flushes once with atomics.
+template <int NOUT>  // outputs per thread = ceil(64*Cin*7 / 256)
+__global__ void __launch_bounds__(256) signal_stem_wgrad_kernel(const float* __restrict__ x,
+                                                                 const __nv_bfloat16* __restrict__ dy,
+                                                                 float* __restrict__ dw, int B, int Cin, int L,
+                                                                 int Lo, int tiles_per_row) {
+  extern __shared__ float sm[];
+  float* xs = sm;                     // [Cin][kStemSpan]
+  float* ds = sm + Cin * kStemSpan;   // [kStemTile][64]
+  const int K = Cin * 7, total_out = K * kStemCo;
+  float acc[NOUT];
+#pragma unroll
+  for (int j = 0; j < NOUT; ++j) acc[j] = 0.f;
+  const int o = threadIdx.x & 63;
+  const int total_tiles = B * tiles_per_row;
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int b = t / tiles_per_row, p0 = (t % tiles_per_row) * kStemTile;
+    const int i0 = 2 * p0 - 3;
+    __syncthreads();
+    for (int e = threadIdx.x; e < Cin * kStemSpan; e += 256) {
+      const int ci = e / kStemSpan, j = e % kStemSpan;
+      const int i = i0 + j;
+      xs[e] = (i >= 0 && i < L) ? x[((size_t)b * Cin + ci) * L + i] : 0.f;
+    }
+    for (int e = threadIdx.x; e < kStemTile * 8; e += 256) {
+      const int pl = e >> 3, cg = e & 7;
+      float f[8];
+      if (p0 + pl < Lo) {
+        unpack8(reinterpret_cast<const uint4*>(dy + ((size_t)b * Lo + p0 + pl) * kStemCo)[cg], f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ds[pl * kStemCo + cg * 8 + j] = f[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) {
+      const int kk = (threadIdx.x >> 6) + 4 * j;  // (ci,k) index handled by this thread
+      if (kk < K) {
+        const float* xr = xs + (kk / 7) * kStemSpan + (kk % 7);
+        float a = acc[j];
+#pragma unroll 8
+        for (int p = 0; p < kStemTile; ++p) a = fmaf(ds[p * kStemCo + o], xr[2 * p], a);
+        acc[j] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NOUT; ++j) {
+    const int kk = (threadIdx.x >> 6) + 4 * j;
+    if (kk < K && o * K + kk < total_out) atomicAdd(dw + (size_t)o * K + kk, acc[j]);
+  }
+}
+
+}  // namespace ecgmm
+
+using namespace ecgmm;
+
+extern "C" int ecgmm_signal_stem_fwd(const float* x, const float* w, ecgmm_bf16* y, int B, int Cin, int L,
+                                     void* stream) {
+  ECGMM_CHECK(x && w && y, ECGMM_ERR_ARG, "signal_stem_fwd: null pointer");
+  ECGMM_CHECK(Cin >= 1 && Cin <= kStemMaxCin && L >= 1, ECGMM_ERR_SHAPE, "signal_stem_fwd: Cin=%d L=%d", Cin, L);
+  ECGMM_CHECK(B <= 65535, ECGMM_ERR_SHAPE, "signal_stem_fwd: batch %d too large", B);
+  if (B == 0) return ECGMM_OK;
+  const int Lo = (L - 1) / 2 + 1;
+  const size_t smem = ((size_t)Cin * kStemSpan + (size_t)Cin * 7 * kStemCo) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    ECGMM_CUDA(cudaFuncSetAttribute(signal_stem_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
+  }
+  signal_stem_fwd_kernel<<<dim3(ceil_div(Lo, kStemTile), B), 256, smem, (cudaStream_t)stream>>>(
+      x, w, reinterpret_cast<__nv_bfloat16*>(y), Cin, L, Lo);
+  return check_launch("signal_stem_fwd_kernel");
+}
+
+extern "C" int ecgmm_signal_stem_wgrad(const float* x, const ecgmm_bf16* dy, float* dw, int B, int Cin, int L,
+                                       void* stream) {
+  ECGMM_CHECK(x && dy && dw, ECGMM_ERR_ARG, "signal_stem_wgrad: null pointer");
+  ECGMM_CHECK(Cin >= 1 && Cin <= kStemMaxCin && L >= 1, ECGMM_ERR_SHAPE, "signal_stem_wgrad: Cin=%d L=%d", Cin, L);
+  if (B == 0) return ECGMM_OK;
+  const int Lo = (L - 1) / 2 + 1;
+  const int tiles = ceil_div(Lo, kStemTile);
+  const size_t smem = ((size_t)Cin * kStemSpan + (size_t)kStemTile * kStemCo) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    ECGMM_CUDA(cudaFuncSetAttribute(signal_stem_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    64 * 1024));
+    ECGMM_CUDA(cudaFuncSetAttribute(signal_stem_wgrad_kernel<28>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    64 * 1024));
+    configured = true;
+  }
+  int grid = B * tiles;
+  if (grid > num_sms() * 2) grid = num_sms() * 2;
+  const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cin == 1)
+    signal_stem_wgrad_kernel<2><<<grid, 256, smem, st>>>(x, dyb, dw, B, Cin, L, Lo, tiles);
+  else
+    signal_stem_wgrad_kernel<28><<<grid, 256, smem, st>>>(x, dyb, dw, B, Cin, L, Lo, tiles);
+  return check_launch("signal_stem_wgrad_kernel");
+}

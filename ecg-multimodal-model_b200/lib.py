@@ -7,13 +7,15 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_int, c_void_p, c_float, c_double, c_longlong, c_char_p, POINTER
+from ctypes import c_int, c_void_p, c_float, c_longlong, c_ulonglong, c_char_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libecgmm.so")
 
 _p = c_void_p
 _i = c_int
+_f = c_float
+_ll = c_longlong
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 SIGNATURES = {
@@ -31,6 +33,39 @@ SIGNATURES = {
     "ecgmm_conv2d_fwd": [_p, _p, _p] + [_i] * 10 + [_p],
     "ecgmm_conv2d_dgrad": [_p, _p, _p] + [_i] * 11 + [_p],
     "ecgmm_conv2d_wgrad": [_p, _p, _p] + [_i] * 10 + [_p],
+    # BatchNorm / ReLU / pooling
+    "ecgmm_reduce_split": [_i, _i, _i],
+    "ecgmm_chan_stats": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "ecgmm_bn_finalize": [_p, _p, _i, _i, _i, _ll, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "ecgmm_bn_eval_coeffs": [_i, _p, _p, _p, _p, _p, _f, _p, _p, _p],
+    "ecgmm_bn_apply": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "ecgmm_bn_relu_maxpool": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "ecgmm_bn_bwd_reduce": [_p] * 10 + [_i] * 6 + [_p],
+    "ecgmm_bn_bwd_finalize": [_p, _p, _i, _i, _i, _ll] + [_p] * 11 + [_p],
+    "ecgmm_bn_bwd_apply": [_p] * 13 + [_i] * 5 + [_p],
+    "ecgmm_avgpool_fwd": [_p, _p, _i, _i, _i, _p],
+    "ecgmm_avgpool_bwd": [_p, _p, _i, _i, _i, _p],
+    # 1-D ResNet-SE specifics
+    "ecgmm_signal_stem_fwd": [_p, _p, _p, _i, _i, _i, _p],
+    "ecgmm_signal_stem_wgrad": [_p, _p, _p, _i, _i, _i, _p],
+    "ecgmm_se_fwd": [_p] * 10 + [_i] * 4 + [_p],
+    "ecgmm_se_bwd": [_p, _p, _i] + [_p] * 9 + [_i] * 4 + [_p],
+    # dense tails / fusion head / losses
+    "ecgmm_sgemm": [_p, _p, _p, _p] + [_i] * 7 + [_p],
+    "ecgmm_colsum": [_p, _p, _i, _i, _i, _p],
+    "ecgmm_layernorm_fwd": [_p] * 6 + [_i, _i, _f, _p],
+    "ecgmm_layernorm_bwd": [_p] * 8 + [_i, _i, _i, _p],
+    "ecgmm_fusion_gate_fwd": [_p] * 6 + [_i] * 4 + [_p],
+    "ecgmm_fusion_gate_bwd": [_p] * 9 + [_i] * 5 + [_p],
+    "ecgmm_var_loss_fwd": [_p] * 6 + [_i] * 4 + [_p],
+    "ecgmm_var_loss_bwd": [_p] * 5 + [_i] * 3 + [_p],
+    "ecgmm_ce_loss": [_p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _p, _p],
+    "ecgmm_dropout_fwd": [_p, _p, _p, _p, _ll, _f, c_ulonglong, _p],
+    "ecgmm_mask_bwd": [_p, _p, _p, _p, _ll, _p],
+    "ecgmm_zscore": [_p, _p, _ll, _i, _f, _p],
+    # optimizer
+    "ecgmm_adam_chunk_bytes": [],
+    "ecgmm_adam_step": [_p, _i, _f, _f, _f, _f, _f, _ll, _f, _p],
 }
 _RESTYPES = {"ecgmm_last_error": c_char_p, "ecgmm_stem_s2d_dims": None}
 

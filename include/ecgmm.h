@@ -87,6 +87,126 @@ int ecgmm_conv2d_dgrad(const ecgmm_bf16* dy, const ecgmm_bf16* w_dgrad, ecgmm_bf
 int ecgmm_conv2d_wgrad(const ecgmm_bf16* x, const ecgmm_bf16* dy, float* dw_oihw, int N, int H, int W, int Cin,
                        int Cout, int R, int S, int stride, int padH, int padW, void* stream);
 
+/* ------------------------------------------------------------------ BatchNorm / ReLU / pooling
+ * Replaces nn.BatchNorm2d + ReLU + residual add + MaxPool2d of torchvision resnet18
+ * (resnet.py:198-200, 92-104; reached from multimodal_paper_modal_balance.py:325) and
+ * nn.BatchNorm1d + ReLU + MaxPool1d + SEBlock scaling of ResNet1D_SE
+ * (multimodal_paper_modal_balance.py:49-64, 83-93, 99-104).
+ * Activations [N][P][C] bf16 (P = H*W or L), C = 8 * 2^k.  Reductions are two-stage and
+ * deterministic: a (split, N) grid writes partial rows [N][split][C], a finalize kernel folds
+ * them in fp64.  Use ecgmm_reduce_split to size the partial buffers. */
+
+/* number of pixel slabs per sample the reduction kernels should use for this shape */
+int ecgmm_reduce_split(int N, int P, int C);
+/* psum / psq [N][split][C] = per-slab sum and sum of squares of x */
+int ecgmm_chan_stats(const ecgmm_bf16* x, float* psum, float* psq, int N, int P, int C, int split, void* stream);
+/* Training-mode BatchNorm statistics from the partials (count = N*P elements per channel):
+ * mean, invstd (saved for backward), scale = gamma*invstd, shift = beta - mean*scale,
+ * running_mean/var update (momentum, unbiased variance; conv_bias, if given, is the bias of the
+ * preceding convolution which the conv kernels do not add: it only moves running_mean),
+ * num_batches += 1, and optionally nsum [N][C] = per-sample sums (the SE squeeze).
+ * gamma/beta/conv_bias/running_x/num_batches/nsum may be NULL. */
+int ecgmm_bn_finalize(const float* psum, const float* psq, int N, int split, int C, long long count,
+                      const float* gamma, const float* beta, const float* conv_bias, float eps, float momentum,
+                      float* running_mean, float* running_var, long long* num_batches, float* mean, float* invstd,
+                      float* scale, float* shift, float* nsum, void* stream);
+/* eval mode: scale = gamma/sqrt(running_var+eps), shift = beta + (conv_bias - running_mean)*scale */
+int ecgmm_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* conv_bias,
+                         const float* running_mean, const float* running_var, float eps, float* scale, float* shift,
+                         void* stream);
+/* y = act((x*scale[c] + shift[c]) * se[n][c] + res); se (fp32 [N][C]) and res may be NULL */
+int ecgmm_bn_apply(const ecgmm_bf16* x, const float* scale, const float* shift, const float* se,
+                   const ecgmm_bf16* res, ecgmm_bf16* y, int N, int P, int C, int relu, void* stream);
+/* stem: y [N][Ho][Wo][C] = maxpool3x3/s2/p1(relu(x*scale+shift)); argmax (may be NULL) [N][Ho][Wo][C] u8 holds the
+ * window position 0..8 of the first maximum.  H == 1 gives MaxPool1d(3,2,1). */
+int ecgmm_bn_relu_maxpool(const ecgmm_bf16* x, const float* scale, const float* shift, ecgmm_bf16* y,
+                          uint8_t* argmax, int N, int H, int W, int C, void* stream);
+/* Backward partials p1/p2 [N][split][C] = sum dz, sum dz*xhat with
+ *   mode 0: dz = dy;  mode 1: dz = dy * (y > 0);  mode 2: stem -- dy is the gradient of the POOLED
+ *   output [N][Ho][Wo][C], routed through argmax and gated by relu(x*scale+shift) > 0. */
+int ecgmm_bn_bwd_reduce(const ecgmm_bf16* x, const ecgmm_bf16* dy, const ecgmm_bf16* y, const uint8_t* argmax,
+                        const float* mean, const float* invstd, const float* scale, const float* shift, float* p1,
+                        float* p2, int N, int H, int W, int C, int split, int mode, void* stream);
+/* Folds the partials into dgamma, dbeta and the coefficients of
+ *   dx = A*se*dz + B*x + D + A*q.   se/q/nsum (all [N][C], NULL outside SE blocks) describe
+ *   du = dz*se + q, the gradient reaching the BatchNorm output of an SE block. */
+int ecgmm_bn_bwd_finalize(const float* p1, const float* p2, int N, int split, int C, long long per_sample,
+                          const float* gamma, const float* mean, const float* invstd, const float* se,
+                          const float* q, const float* nsum, float* dgamma, float* dbeta, float* coefA,
+                          float* coefB, float* coefD, void* stream);
+/* dx (gradient of the convolution output) and optionally dz_out = the masked upstream gradient
+ * (what flows into the residual branch). */
+int ecgmm_bn_bwd_apply(const ecgmm_bf16* x, const ecgmm_bf16* dy, const ecgmm_bf16* y, const uint8_t* argmax,
+                       const float* coefA, const float* coefB, const float* coefD, const float* scale,
+                       const float* shift, const float* se, const float* q, ecgmm_bf16* dx, ecgmm_bf16* dz_out,
+                       int N, int H, int W, int C, int mode, void* stream);
+/* AdaptiveAvgPool to 1x1 (resnet.py:203, multimodal_paper_modal_balance.py:110): [N][P][C] bf16 <-> [N][C] fp32 */
+int ecgmm_avgpool_fwd(const ecgmm_bf16* x, float* out, int N, int P, int C, void* stream);
+int ecgmm_avgpool_bwd(const float* dout, ecgmm_bf16* dx, int N, int P, int C, void* stream);
+
+/* ------------------------------------------------------------------ 1-D ResNet-SE stem
+ * nn.Conv1d(Cin, 64, 7, stride 2, padding 3) of ResNet1D_SE.initial
+ * (multimodal_paper_modal_balance.py:99-100; 12-lead: train_signal_12_af.py:184).
+ * x [B][Cin][L] fp32 (Cin <= 16), w [64][Cin][7] fp32, y/dy [B][Lo][64] bf16, Lo = (L-1)/2+1.
+ * The bias is NOT added (see ecgmm_bn_finalize / ecgmm_bn_eval_coeffs). dw accumulates. */
+int ecgmm_signal_stem_fwd(const float* x, const float* w, ecgmm_bf16* y, int B, int Cin, int L, void* stream);
+int ecgmm_signal_stem_wgrad(const float* x, const ecgmm_bf16* dy, float* dw, int B, int Cin, int L, void* stream);
+/* SEBlock.fc (multimodal_paper_modal_balance.py:52-64) on pooled = scale*nsum/L + shift:
+ * hid = relu(W1 pooled + b1) [N][R], gate = sigmoid(W2 hid + b2) [N][C];  w1 [R][C], w2 [C][R]. */
+int ecgmm_se_fwd(const float* nsum, const float* scale, const float* shift, const float* w1, const float* b1,
+                 const float* w2, const float* b2, float* pooled, float* hid, float* gate, int N, int C, int R, int L,
+                 void* stream);
+/* from the bn_bwd_reduce partials of the block output: q [N][C] (see ecgmm_bn_bwd_finalize) and the
+ * pre-activation gradients dpre2 [N][C], dpre1 [N][R] whose outer products give the SE weight grads. */
+int ecgmm_se_bwd(const float* p1, const float* p2, int split, const float* gamma, const float* beta,
+                 const float* w1, const float* w2, const float* hid, const float* gate, float* q, float* dpre2,
+                 float* dpre1, int N, int C, int R, int L, void* stream);
+
+/* ------------------------------------------------------------------ dense tails and fusion head (fp32)
+ * nn.Linear / nn.LayerNorm / AttentionFusion / var regulariser / losses:
+ * multimodal_paper_modal_balance.py:31-46, 221-223, 256-289, 340-352; train.py:31,72,78;
+ * signal_model.py:91-106 (FocalLoss), 203-206 (z-score). */
+/* C[M][N] (+)= op(A) op(B) (+ bias[N]) (relu).  transA: A stored [K][M]; transB: B stored [N][K]. */
+int ecgmm_sgemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int transA,
+                int transB, int accumulate, int relu, void* stream);
+/* out[n] (+)= sum_m X[m][n] */
+int ecgmm_colsum(const float* X, float* out, int M, int N, int accumulate, void* stream);
+int ecgmm_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                        int rows, int D, float eps, void* stream);
+/* any of dx / dgamma / dbeta may be NULL */
+int ecgmm_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* mean, const float* rstd,
+                        float* dx, float* dgamma, float* dbeta, int rows, int D, int accumulate_dx, void* stream);
+/* fused [B][D0+D1+D2] = cat(w0*f0, w1*f1, w2*f2), w = softmax(weights[3]) (also stored in soft_w) */
+int ecgmm_fusion_gate_fwd(const float* f0, const float* f1, const float* f2, const float* weights, float* fused,
+                          float* soft_w, int B, int D0, int D1, int D2, void* stream);
+int ecgmm_fusion_gate_bwd(const float* dfused, const float* f0, const float* f1, const float* f2,
+                          const float* weights, float* df0, float* df1, float* df2, float* dweights, int B, int D0,
+                          int D1, int D2, int accumulate, void* stream);
+/* loss = sum_{i<j} |v_i - v_j|, v_i = mean_b var_unbiased_d(f_i); row_mean [3][B], coef [3] = dloss/dv_i */
+int ecgmm_var_loss_fwd(const float* f0, const float* f1, const float* f2, float* loss, float* row_mean, float* coef,
+                       int B, int D0, int D1, int D2, void* stream);
+/* one modality: df (+)= gout[0]*coef[0]*2(f-row_mean)/((D-1)B) */
+int ecgmm_var_loss_bwd(const float* f, const float* row_mean, const float* coef, const float* gout, float* df, int B,
+                       int D, int accumulate, void* stream);
+/* mean softmax cross entropy (focal == 0) or focal loss alpha(1-pt)^gamma ce (focal == 1);
+ * dlogits (may be NULL) = gscale * dloss/dlogits.  *bad_label is set to 1 on an out-of-range label. */
+int ecgmm_ce_loss(const float* logits, const long long* labels, float* loss, float* dlogits, int B, int C, int focal,
+                  float alpha, float gamma, float gscale, int* bad_label, void* stream);
+/* y = x*mask; mask_in given (0 or 1/(1-p)) or drawn from (seed, element index); mask_out may be NULL */
+int ecgmm_dropout_fwd(const float* x, const float* mask_in, float* y, float* mask_out, long long n, float p,
+                      unsigned long long seed, void* stream);
+/* dx = dy * mask * (y > 0); y and mask may be NULL */
+int ecgmm_mask_bwd(const float* dy, const float* y, const float* mask, float* dx, long long n, void* stream);
+int ecgmm_zscore(const float* x, float* y, long long rows, int L, float eps, void* stream);
+
+/* ------------------------------------------------------------------ optimizer
+ * torch.optim.Adam step (train.py:43,81).  chunk_table: device array of
+ * { float* p; const float* g; float* m; float* v; long long n; } (ecgmm_adam_chunk_bytes() each);
+ * step is the 1-based step count; gradients are multiplied by grad_scale first. */
+int ecgmm_adam_chunk_bytes(void);
+int ecgmm_adam_step(const void* chunk_table, int n_chunks, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, long long step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
