@@ -522,6 +522,79 @@ __global__ void __launch_bounds__(256) zscore_kernel(const float* __restrict__ x
   for (int i = threadIdx.x; i < L; i += blockDim.x) yr[i] = (xr[i] - mean) * inv;
 }
 
+// ------------------------------------------------------------------------------------------
+// BatchNorm1d over a small fp32 feature matrix [B][C] (clinical MLP,
+// multimodal_paper_modal_balance.py:258): one thread per feature column.
+// ------------------------------------------------------------------------------------------
+__global__ void bn_rows_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long long* __restrict__ num_batches,
+                                   float* __restrict__ y, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out, int B, int C, float eps, float momentum,
+                                   int train, int relu) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && train && num_batches) *num_batches += 1;
+  if (c >= C) return;
+  float mean, invstd;
+  if (train) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += x[(size_t)b * C + c];
+    mean = s / B;
+    float q = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float t = x[(size_t)b * C + c] - mean;
+      q = fmaf(t, t, q);
+    }
+    const float var = q / B;
+    invstd = rsqrtf(var + eps);
+    if (running_mean) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (B > 1 ? q / (B - 1) : var);
+    }
+  } else {
+    mean = running_mean[c];
+    invstd = rsqrtf(running_var[c] + eps);
+  }
+  if (mean_out) mean_out[c] = mean;
+  if (invstd_out) invstd_out[c] = invstd;
+  const float sc = gamma[c] * invstd, sh = beta[c] - mean * sc;
+  for (int b = 0; b < B; ++b) {
+    float v = fmaf(x[(size_t)b * C + c], sc, sh);
+    if (relu) v = fmaxf(v, 0.f);
+    y[(size_t)b * C + c] = v;
+  }
+}
+
+// dy is the gradient of the (optionally ReLU-ed) output y
+__global__ void bn_rows_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                   const float* __restrict__ y, const float* __restrict__ gamma,
+                                   const float* __restrict__ mean, const float* __restrict__ invstd,
+                                   float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                   int B, int C, int relu) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mu = mean[c], is = invstd[c];
+  float s1 = 0.f, s2 = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const size_t i = (size_t)b * C + c;
+    float g = dy[i];
+    if (relu && y[i] <= 0.f) g = 0.f;
+    s1 += g;
+    s2 = fmaf(g, (x[i] - mu) * is, s2);
+  }
+  if (dgamma) dgamma[c] = s2;
+  if (dbeta) dbeta[c] = s1;
+  if (dx) {
+    const float m1 = s1 / B, m2 = s2 / B, k = gamma[c] * is;
+    for (int b = 0; b < B; ++b) {
+      const size_t i = (size_t)b * C + c;
+      float g = dy[i];
+      if (relu && y[i] <= 0.f) g = 0.f;
+      dx[i] = k * (g - m1 - (x[i] - mu) * is * m2);
+    }
+  }
+}
+
 static int ew_grid(size_t n) {
   size_t b = (n + 255) / 256;
   const size_t cap = (size_t)num_sms() * 8;
@@ -669,4 +742,28 @@ extern "C" int ecgmm_zscore(const float* x, float* y, long long rows, int L, flo
   ECGMM_CHECK(rows <= 2147483647ll, ECGMM_ERR_SHAPE, "zscore: too many rows");
   zscore_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, y, L, eps);
   return check_launch("zscore_kernel");
+}
+
+extern "C" int ecgmm_bn_rows_fwd(const float* x, const float* gamma, const float* beta, float* running_mean,
+                                 float* running_var, long long* num_batches, float* y, float* mean, float* invstd,
+                                 int B, int C, float eps, float momentum, int train, int relu, void* stream) {
+  ECGMM_CHECK(x && gamma && beta && y, ECGMM_ERR_ARG, "bn_rows_fwd: null pointer");
+  ECGMM_CHECK(train || (running_mean && running_var), ECGMM_ERR_ARG, "bn_rows_fwd: eval mode needs running stats");
+  ECGMM_CHECK(!train || B > 1, ECGMM_ERR_SHAPE, "bn_rows_fwd: training needs more than 1 row (got %d)", B);
+  if (B == 0 || C == 0) return ECGMM_OK;
+  bn_rows_fwd_kernel<<<ceil_div(C, 64), 64, 0, (cudaStream_t)stream>>>(x, gamma, beta, running_mean, running_var,
+                                                                     num_batches, y, mean, invstd, B, C, eps,
+                                                                     momentum, train, relu);
+  return check_launch("bn_rows_fwd_kernel");
+}
+
+extern "C" int ecgmm_bn_rows_bwd(const float* x, const float* dy, const float* y, const float* gamma,
+                                 const float* mean, const float* invstd, float* dx, float* dgamma, float* dbeta,
+                                 int B, int C, int relu, void* stream) {
+  ECGMM_CHECK(x && dy && gamma && mean && invstd, ECGMM_ERR_ARG, "bn_rows_bwd: null pointer");
+  ECGMM_CHECK(!relu || y, ECGMM_ERR_ARG, "bn_rows_bwd: relu needs y");
+  if (B == 0 || C == 0) return ECGMM_OK;
+  bn_rows_bwd_kernel<<<ceil_div(C, 64), 64, 0, (cudaStream_t)stream>>>(x, dy, y, gamma, mean, invstd, dx, dgamma,
+                                                                     dbeta, B, C, relu);
+  return check_launch("bn_rows_bwd_kernel");
 }

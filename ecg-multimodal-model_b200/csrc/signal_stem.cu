@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) signal_stem_fwd_kernel(const float* __res
                                                                int Lo) {
   extern __shared__ float sm[];
   float* xs = sm;                      // [Cin][kStemSpan]
-  float* ws = sm + Cin * kStemSpan;    // [Cin*7][64]
+  float* ws = sm + ((Cin * kStemSpan + 3) & ~3);  // [Cin*7][64], 16-byte aligned
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * kStemTile;
   const int K = Cin * 7;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) signal_stem_wgrad_kernel(const float* __r
                                                                  int Lo, int tiles_per_row) {
   extern __shared__ float sm[];
   float* xs = sm;                     // [Cin][kStemSpan]
-  float* ds = sm + Cin * kStemSpan;   // [kStemTile][64]
+  float* ds = sm + ((Cin * kStemSpan + 3) & ~3);  // [kStemTile][64]
   const int K = Cin * 7, total_out = K * kStemCo;
   float acc[NOUT];
 #pragma unroll
@@ -130,7 +130,7 @@ extern "C" int ecgmm_signal_stem_fwd(const float* x, const float* w, ecgmm_bf16*
   ECGMM_CHECK(B <= 65535, ECGMM_ERR_SHAPE, "signal_stem_fwd: batch %d too large", B);
   if (B == 0) return ECGMM_OK;
   const int Lo = (L - 1) / 2 + 1;
-  const size_t smem = ((size_t)Cin * kStemSpan + (size_t)Cin * 7 * kStemCo) * sizeof(float);
+  const size_t smem = ((size_t)((Cin * kStemSpan + 3) & ~3) + (size_t)Cin * 7 * kStemCo) * sizeof(float);
   static bool configured = false;
   if (!configured) {
     ECGMM_CUDA(cudaFuncSetAttribute(signal_stem_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -148,7 +148,7 @@ extern "C" int ecgmm_signal_stem_wgrad(const float* x, const ecgmm_bf16* dy, flo
   if (B == 0) return ECGMM_OK;
   const int Lo = (L - 1) / 2 + 1;
   const int tiles = ceil_div(Lo, kStemTile);
-  const size_t smem = ((size_t)Cin * kStemSpan + (size_t)kStemTile * kStemCo) * sizeof(float);
+  const size_t smem = ((size_t)((Cin * kStemSpan + 3) & ~3) + (size_t)kStemTile * kStemCo) * sizeof(float);
   static bool configured = false;
   if (!configured) {
     ECGMM_CUDA(cudaFuncSetAttribute(signal_stem_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,

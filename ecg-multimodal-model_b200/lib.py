@@ -63,6 +63,8 @@ SIGNATURES = {
     "ecgmm_dropout_fwd": [_p, _p, _p, _p, _ll, _f, c_ulonglong, _p],
     "ecgmm_mask_bwd": [_p, _p, _p, _p, _ll, _p],
     "ecgmm_zscore": [_p, _p, _ll, _i, _f, _p],
+    "ecgmm_bn_rows_fwd": [_p] * 9 + [_i, _i, _f, _f, _i, _i, _p],
+    "ecgmm_bn_rows_bwd": [_p] * 9 + [_i, _i, _i, _p],
     # optimizer
     "ecgmm_adam_chunk_bytes": [],
     "ecgmm_adam_step": [_p, _i, _f, _f, _f, _f, _f, _ll, _f, _p],
@@ -75,6 +77,7 @@ class EcgmmError(RuntimeError):
 
 
 _lib = None
+CALLS = 0  # C-ABI calls issued so far (each launches at least one kernel); bench.py reports the delta
 
 
 def load() -> ctypes.CDLL:
@@ -102,6 +105,8 @@ def last_error() -> str:
 
 def call(name: str, *args) -> None:
     """Invoke an int-returning entry point and raise EcgmmError on failure."""
+    global CALLS
+    CALLS += 1
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise EcgmmError(f"{name} failed with status {rc}: {last_error()}")

@@ -1,0 +1,65 @@
+"""Loss modules with the constructors of the ones the reference's loops instantiate, computed by
+the fused libecgmm loss kernel (loss and d(loss)/d(logits) in one launch).
+
+  CrossEntropyLoss  <- nn.CrossEntropyLoss()  train.py:31, train_kfold.py:41 (mean reduction, 2 logits)
+  FocalLoss         <- signal_model.py:91-106 (alpha=1, gamma=2, mean reduction)
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import lib, ops
+
+F32 = torch.float32
+
+
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, focal, alpha, gamma):
+        if not logits.is_cuda:
+            raise lib.EcgmmError("loss inputs must be CUDA tensors (no CPU fallback)")
+        if logits.dim() != 2:
+            raise lib.EcgmmError(f"logits must be [B,C], got {tuple(logits.shape)}")
+        z = logits.detach().to(F32).contiguous()
+        y = labels.detach().to(torch.int64).contiguous()
+        B, C = z.shape
+        out = torch.empty(1 + B * C, dtype=F32, device=z.device)
+        loss, dz = out[0:1], out[1:].view(B, C)
+        lib.call("ecgmm_ce_loss", ops._ptr(z), ops._ptr(y), ops._ptr(loss), ops._ptr(dz), B, C, int(focal),
+                 float(alpha), float(gamma), 1.0, None, ops._s())
+        ctx.save_for_backward(dz)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        # d(total)/d(logits) = g * dz : one SGEMM call with K = 1 (g is a device scalar; no sync)
+        B, C = dz.shape
+        out = ops.sgemm(dz.reshape(B * C, 1), g.detach().to(F32).reshape(1, 1).contiguous(), B * C, 1, 1)
+        return out.view(B, C), None, None, None, None
+
+
+class CrossEntropyLoss(nn.Module):
+    """Mean softmax cross entropy over [B,C] logits and int64 labels."""
+
+    def __init__(self, weight=None, reduction="mean", label_smoothing=0.0, ignore_index=-100):
+        super().__init__()
+        if weight is not None or reduction != "mean" or label_smoothing != 0.0:
+            raise lib.EcgmmError("only the reference configuration nn.CrossEntropyLoss() is implemented")
+
+    def forward(self, logits, labels):
+        return _LossFn.apply(logits, labels, 0, 1.0, 0.0)
+
+
+class FocalLoss(nn.Module):
+    """signal_model.py:91-106: mean(alpha * (1 - pt)^gamma * ce), pt = exp(-ce)."""
+
+    def __init__(self, alpha=1.0, gamma=2.0, reduction="mean"):
+        super().__init__()
+        if reduction != "mean":
+            raise lib.EcgmmError("only reduction='mean' is implemented (the reference default)")
+        self.alpha, self.gamma = float(alpha), float(gamma)
+
+    def forward(self, inputs, targets):
+        return _LossFn.apply(inputs, targets, 1, self.alpha, self.gamma)

@@ -158,3 +158,248 @@ def stem_conv_wgrad(xs: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, H: int
     _chk(dw, torch.float32, "dw")
     assert dw.numel() == 64 * 3 * 49
     lib.call("ecgmm_stem_conv_wgrad", _ptr(xs), _ptr(dy), _ptr(dw), xs.shape[0], H, W, _s())
+
+
+# ---------------------------------------------------------------- BatchNorm / ReLU / pooling
+F32 = torch.float32
+
+
+def _f32(n, dev):
+    return torch.empty(n, dtype=F32, device=dev)
+
+
+class BNStats:
+    """Per-channel quantities produced by the forward statistics pass and reused by backward."""
+    __slots__ = ("mean", "invstd", "scale", "shift", "nsum")
+
+    def __init__(self, mean, invstd, scale, shift, nsum=None):
+        self.mean, self.invstd, self.scale, self.shift, self.nsum = mean, invstd, scale, shift, nsum
+
+
+def _npc(x):
+    """[N,H,W,C] or [N,P,C] -> (N, P, C)."""
+    if x.dim() == 4:
+        return x.shape[0], x.shape[1] * x.shape[2], x.shape[3]
+    return x.shape[0], x.shape[1], x.shape[2]
+
+
+def bn_train_stats(x, gamma, beta, running_mean, running_var, num_batches, eps, momentum, conv_bias=None,
+                   want_nsum=False) -> BNStats:
+    """Training-mode statistics of a channels-last activation + running-stat update."""
+    _chk(x, BF16, "x")
+    N, P, C = _npc(x)
+    dev = x.device
+    split = lib.load().ecgmm_reduce_split(N, P, C)
+    part = _f32(2 * N * split * C, dev)
+    psum, psq = part[: N * split * C], part[N * split * C:]
+    lib.call("ecgmm_chan_stats", _ptr(x), _ptr(psum), _ptr(psq), N, P, C, split, _s())
+    out = _f32(4 * C, dev)
+    mean, invstd, scale, shift = out[:C], out[C:2 * C], out[2 * C:3 * C], out[3 * C:]
+    nsum = _f32(N * C, dev).view(N, C) if want_nsum else None
+    lib.call("ecgmm_bn_finalize", _ptr(psum), _ptr(psq), N, split, C, N * P, _ptr(gamma), _ptr(beta),
+             _ptr(conv_bias), float(eps), float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(num_batches),
+             _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), _ptr(nsum), _s())
+    return BNStats(mean, invstd, scale, shift, nsum)
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, conv_bias=None) -> BNStats:
+    C = running_mean.numel()
+    out = _f32(2 * C, running_mean.device)
+    scale, shift = out[:C], out[C:]
+    lib.call("ecgmm_bn_eval_coeffs", C, _ptr(gamma), _ptr(beta), _ptr(conv_bias), _ptr(running_mean),
+             _ptr(running_var), float(eps), _ptr(scale), _ptr(shift), _s())
+    return BNStats(None, None, scale, shift)
+
+
+def bn_apply(x, st: BNStats, se=None, res=None, relu=True, out=None):
+    _chk(x, BF16, "x")
+    N, P, C = _npc(x)
+    y = torch.empty_like(x) if out is None else out
+    if res is not None:
+        _chk(res, BF16, "res")
+        assert res.shape == x.shape
+    lib.call("ecgmm_bn_apply", _ptr(x), _ptr(st.scale), _ptr(st.shift), _ptr(se), _ptr(res), _ptr(y), N, P, C,
+             int(relu), _s())
+    return y
+
+
+def bn_relu_maxpool(x, st: BNStats, want_argmax=True):
+    """x [N,H,W,C] -> (y [N,Ho,Wo,C], argmax uint8 or None); 3x3 / stride 2 / pad 1."""
+    _chk(x, BF16, "x")
+    N, H, W, C = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((N, Ho, Wo, C), dtype=BF16, device=x.device)
+    arg = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device=x.device) if want_argmax else None
+    lib.call("ecgmm_bn_relu_maxpool", _ptr(x), _ptr(st.scale), _ptr(st.shift), _ptr(y), _ptr(arg), N, H, W, C, _s())
+    return y, arg
+
+
+def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=None, want_dz=False,
+                need_param_grads=True, dgamma=None, dbeta=None):
+    """BatchNorm (+ReLU / +SE gate / +stem max-pool) backward.
+
+    x: raw convolution output [N,H,W,C]; dy: upstream gradient (pooled-shape for the stem, mode 2);
+    y: post-activation output (ReLU mask) or None; argmax: stem pooling indices or None;
+    se / se_ctx: gate [N,C] and a callable (p1, p2, split) -> q [N,C] that runs the SE backward
+    between the reduction and the finalize step.
+    Returns (dx, dz or None); dgamma/dbeta are written into the given fp32 buffers."""
+    _chk(x, BF16, "x")
+    _chk(dy, BF16, "dy")
+    if x.dim() == 3:
+        N, W_, C = x.shape
+        H_ = 1
+    else:
+        N, H_, W_, C = x.shape
+    P = H_ * W_
+    dev = x.device
+    mode = 2 if argmax is not None else (1 if y is not None else 0)
+    split = lib.load().ecgmm_reduce_split(N, P, C)
+    part = _f32(2 * N * split * C, dev)
+    p1, p2 = part[: N * split * C], part[N * split * C:]
+    lib.call("ecgmm_bn_bwd_reduce", _ptr(x), _ptr(dy), _ptr(y), _ptr(argmax), _ptr(st.mean), _ptr(st.invstd),
+             _ptr(st.scale), _ptr(st.shift), _ptr(p1), _ptr(p2), N, H_, W_, C, split, mode, _s())
+    q = None
+    if se is not None:
+        q = se_ctx(p1, p2, split)
+    coef = _f32(3 * C, dev)
+    cA, cB, cD = coef[:C], coef[C:2 * C], coef[2 * C:]
+    lib.call("ecgmm_bn_bwd_finalize", _ptr(p1), _ptr(p2), N, split, C, P, _ptr(gamma), _ptr(st.mean),
+             _ptr(st.invstd), _ptr(se), _ptr(q), _ptr(st.nsum if se is not None else None),
+             _ptr(dgamma if need_param_grads else None), _ptr(dbeta if need_param_grads else None), _ptr(cA),
+             _ptr(cB), _ptr(cD), _s())
+    dx = torch.empty_like(x)
+    dz = torch.empty_like(x) if want_dz else None
+    lib.call("ecgmm_bn_bwd_apply", _ptr(x), _ptr(dy), _ptr(y), _ptr(argmax), _ptr(cA), _ptr(cB), _ptr(cD),
+             _ptr(st.scale), _ptr(st.shift), _ptr(se), _ptr(q), _ptr(dx), _ptr(dz), N, H_, W_, C, mode, _s())
+    return dx, dz
+
+
+def avgpool_fwd(x):
+    _chk(x, BF16, "x")
+    N, P, C = _npc(x)
+    out = torch.empty((N, C), dtype=F32, device=x.device)
+    lib.call("ecgmm_avgpool_fwd", _ptr(x), _ptr(out), N, P, C, _s())
+    return out
+
+
+def avgpool_bwd(dout, like_shape):
+    _chk(dout, F32, "dout")
+    N, C = dout.shape
+    dx = torch.empty(like_shape, dtype=BF16, device=dout.device)
+    P = dx.numel() // (N * C)
+    lib.call("ecgmm_avgpool_bwd", _ptr(dout), _ptr(dx), N, P, C, _s())
+    return dx
+
+
+# ---------------------------------------------------------------- 1-D stem / SE
+def signal_stem_fwd(x, w):
+    """x [B,Cin,L] fp32, w [64,Cin,7] fp32 -> [B,1,Lo,64] bf16 (bias not added)."""
+    _chk(x, F32, "ecg_signal")
+    _chk(w, F32, "w")
+    B, Cin, L = x.shape
+    Lo = (L - 1) // 2 + 1
+    y = torch.empty((B, 1, Lo, 64), dtype=BF16, device=x.device)
+    lib.call("ecgmm_signal_stem_fwd", _ptr(x), _ptr(w), _ptr(y), B, Cin, L, _s())
+    return y
+
+
+def signal_stem_wgrad(x, dy, dw):
+    B, Cin, L = x.shape
+    lib.call("ecgmm_signal_stem_wgrad", _ptr(x), _ptr(dy), _ptr(dw), B, Cin, L, _s())
+
+
+def se_fwd(nsum, st: BNStats, w1, b1, w2, b2, L):
+    N, C = nsum.shape
+    R = w1.shape[0]
+    dev = nsum.device
+    pooled = torch.empty((N, C), dtype=F32, device=dev)
+    hid = torch.empty((N, R), dtype=F32, device=dev)
+    gate = torch.empty((N, C), dtype=F32, device=dev)
+    lib.call("ecgmm_se_fwd", _ptr(nsum), _ptr(st.scale), _ptr(st.shift), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2),
+             _ptr(pooled), _ptr(hid), _ptr(gate), N, C, R, L, _s())
+    return pooled, hid, gate
+
+
+def se_bwd(p1, p2, split, gamma, beta, w1, w2, hid, gate, L):
+    N, C = gate.shape
+    R = w1.shape[0]
+    dev = gate.device
+    q = torch.empty((N, C), dtype=F32, device=dev)
+    dpre2 = torch.empty((N, C), dtype=F32, device=dev)
+    dpre1 = torch.empty((N, R), dtype=F32, device=dev)
+    lib.call("ecgmm_se_bwd", _ptr(p1), _ptr(p2), split, _ptr(gamma), _ptr(beta), _ptr(w1), _ptr(w2), _ptr(hid),
+             _ptr(gate), _ptr(q), _ptr(dpre2), _ptr(dpre1), N, C, R, L, _s())
+    return q, dpre2, dpre1
+
+
+# ---------------------------------------------------------------- dense (fp32)
+def sgemm(A, B, M, N, K, transA=False, transB=False, bias=None, out=None, accumulate=False, relu=False):
+    if out is None:
+        out = torch.empty((M, N), dtype=F32, device=A.device)
+    lib.call("ecgmm_sgemm", _ptr(A), _ptr(B), _ptr(out), _ptr(bias), M, N, K, int(transA), int(transB),
+             int(accumulate), int(relu), _s())
+    return out
+
+
+def linear_fwd(x, w, b=None, relu=False):
+    """x [M,K], w [N,K] -> [M,N]."""
+    _chk(x, F32, "x")
+    return sgemm(x, w, x.shape[0], w.shape[0], w.shape[1], transB=True, bias=b, relu=relu)
+
+
+def linear_bwd(x, w, dy, need_dx=True, dw=None, db=None, dx_out=None, accumulate_dx=False):
+    """dx = dy w ; dw (given buffer [N,K]) = dy^T x ; db (given buffer [N]) = colsum(dy)."""
+    M, K = x.shape
+    N = w.shape[0]
+    dx = None
+    if need_dx:
+        dx = sgemm(dy, w, M, K, N, out=dx_out, accumulate=accumulate_dx)
+    if dw is not None:
+        sgemm(dy, x, N, K, M, transA=True, out=dw)
+    if db is not None:
+        lib.call("ecgmm_colsum", _ptr(dy), _ptr(db), M, N, 0, _s())
+    return dx
+
+
+def layernorm_fwd(x, gamma, beta, eps):
+    _chk(x, F32, "x")
+    rows, D = x.shape
+    y = torch.empty_like(x)
+    st = _f32(2 * rows, x.device)
+    mean, rstd = st[:rows], st[rows:]
+    lib.call("ecgmm_layernorm_fwd", _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), rows, D,
+             float(eps), _s())
+    return y, mean, rstd
+
+
+def layernorm_bwd(x, dy, gamma, mean, rstd, dgamma=None, dbeta=None, need_dx=True):
+    rows, D = x.shape
+    dx = torch.empty_like(x) if need_dx else None
+    lib.call("ecgmm_layernorm_bwd", _ptr(x), _ptr(dy), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dgamma),
+             _ptr(dbeta), rows, D, 0, _s())
+    return dx
+
+
+def dropout_fwd(x, p, seed, mask_in=None):
+    """Returns (y, mask) with mask holding 0 or 1/(1-p)."""
+    _chk(x, F32, "x")
+    y = torch.empty_like(x)
+    mask = torch.empty_like(x) if mask_in is None else mask_in
+    lib.call("ecgmm_dropout_fwd", _ptr(x), _ptr(mask_in), _ptr(y), _ptr(mask if mask_in is None else None),
+             x.numel(), float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _s())
+    return y, mask
+
+
+def mask_bwd(dy, y=None, mask=None):
+    dx = torch.empty_like(dy)
+    lib.call("ecgmm_mask_bwd", _ptr(dy), _ptr(y), _ptr(mask), _ptr(dx), dy.numel(), _s())
+    return dx
+
+
+def zscore(x, eps=1e-8):
+    """(x - mean) / (std_population + eps) along the last dimension (signal_model.py:203-206)."""
+    _chk(x, F32, "x")
+    y = torch.empty_like(x)
+    L = x.shape[-1]
+    lib.call("ecgmm_zscore", _ptr(x), _ptr(y), x.numel() // L, L, float(eps), _s())
+    return y

@@ -1,0 +1,80 @@
+"""Adam with the constructor / param_groups / state_dict of torch.optim.Adam (the optimizer of
+train.py:43, train_kfold.py:42, signal_model.py:157), stepping every parameter of a group in ONE
+multi-tensor libecgmm launch.  `param_group['lr']` may be changed between steps (train.py:158-161,
+OneCycleLR in signal_model.py:158-161): lr is a kernel argument read at every step."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import lib, ops
+
+CHUNK = 1 << 16  # elements per CTA
+
+
+class Adam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False,
+                 grad_scale=1.0):
+        if amsgrad:
+            raise lib.EcgmmError("amsgrad is not implemented (the reference never enables it)")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False)
+        super().__init__(params, defaults)
+        self.grad_scale = float(grad_scale)
+        self._tables = {}
+
+    def _table(self, gi, entries):
+        """Device chunk table for group gi, rebuilt only when a pointer changed."""
+        key = tuple((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()) for p, g, m, v in entries)
+        cached = self._tables.get(gi)
+        if cached is not None and cached[0] == key:
+            return cached[1], cached[2]
+        rows = []
+        for p, g, m, v, n in key:
+            for off in range(0, n, CHUNK):
+                cnt = min(CHUNK, n - off)
+                rows.append((p + 4 * off, g + 4 * off, m + 4 * off, v + 4 * off, cnt))
+        host = torch.from_numpy(np.asarray(rows, dtype=np.int64).reshape(-1, 5)).pin_memory()
+        table = host.to(entries[0][0].device, non_blocking=True)
+        self._tables[gi] = (key, table, len(rows), host)
+        return table, len(rows)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            entries = []
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda:
+                    raise lib.EcgmmError("ecgmm.optim.Adam needs CUDA parameters (no CPU fallback)")
+                if p.dtype != torch.float32 or not p.is_contiguous():
+                    raise lib.EcgmmError("ecgmm.optim.Adam needs contiguous float32 parameters")
+                g = p.grad
+                if g.dtype != torch.float32 or not g.is_contiguous():
+                    g = g.to(torch.float32).contiguous()
+                    p.grad = g
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] = int(st["step"]) + 1
+                entries.append((p, g, st["exp_avg"], st["exp_avg_sq"]))
+            if not entries:
+                continue
+            steps = {int(self.state[e[0]]["step"]) for e in entries}
+            b1, b2 = group["betas"]
+            # parameters that joined late (different step count) get their own launch
+            for stp in sorted(steps):
+                sub = [e for e in entries if int(self.state[e[0]]["step"]) == stp]
+                table, n = self._table((gi, stp if len(steps) > 1 else -1), sub)
+                lib.call("ecgmm_adam_step", ctypes.c_void_p(table.data_ptr()), n, float(group["lr"]), float(b1),
+                         float(b2), float(group["eps"]), float(group["weight_decay"]), stp, self.grad_scale, ops._s())
+            torch.autograd.graph.increment_version([e[0] for e in entries])
+        return loss

@@ -197,6 +197,14 @@ int ecgmm_dropout_fwd(const float* x, const float* mask_in, float* y, float* mas
                       unsigned long long seed, void* stream);
 /* dx = dy * mask * (y > 0); y and mask may be NULL */
 int ecgmm_mask_bwd(const float* dy, const float* y, const float* mask, float* dx, long long n, void* stream);
+/* BatchNorm1d (+ReLU) over a small fp32 matrix [B][C]: clinical MLP, multimodal_paper_modal_balance.py:258.
+ * train != 0: batch statistics + running update (+ num_batches); else running statistics. */
+int ecgmm_bn_rows_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      long long* num_batches, float* y, float* mean, float* invstd, int B, int C, float eps,
+                      float momentum, int train, int relu, void* stream);
+int ecgmm_bn_rows_bwd(const float* x, const float* dy, const float* y, const float* gamma, const float* mean,
+                      const float* invstd, float* dx, float* dgamma, float* dbeta, int B, int C, int relu,
+                      void* stream);
 int ecgmm_zscore(const float* x, float* y, long long rows, int L, float eps, void* stream);
 
 /* ------------------------------------------------------------------ optimizer

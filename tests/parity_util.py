@@ -1,0 +1,233 @@
+"""Shared GPU-vs-oracle comparison used by tests/test_fusion_gpu.py, __graft_entry__.smoke() and
+tools/.  The oracle (oracle/model.py, CPU fp32, pinned bit-identical to the reference) is the
+checker; the thing checked is ecgmm.model.ECGMultimodalModel running on libecgmm kernels.
+
+Tolerances (bf16 activations / fp32 accumulation against an fp32 reference; stated here once):
+  outputs   max|a-b| <= OUT_TOL * max(1, max|b|)          per output tensor
+  argmax    identical on every sample whose reference margin |z1-z0| exceeds 2 * OUT_TOL
+  gradients per parameter tensor, e = ||g-g_ref|| / ||g_ref|| must satisfy
+            e <= max(GRAD_REL, GRAD_NOISE_X * e_bf16)
+            where e_bf16 is the same error measured on the ORACLE ITSELF when its conv/BN/ReLU/pool
+            outputs, conv weights and input image are rounded to bf16 (bf16_emulated_oracle below).
+            Reason: at random init this network's gradients are ill-conditioned (train-mode
+            BatchNorm behind a global average pool cancels most of the upstream gradient), so ANY
+            bf16-activation implementation deviates by tens of percent in relative L2 from fp32;
+            the emulated oracle measures that floor and the CUDA path must not exceed it by more
+            than GRAD_NOISE_X.  The per-kernel tests (tests/test_kernels_gpu.py) pin every kernel
+            to its fp32 operator at bf16-ulp level, and whole residual blocks at 3 %.
+            Tensors whose reference norm is below GRAD_FLOOR * (largest gradient norm), e.g. Conv1d
+            biases (true gradient 0 because BatchNorm follows), only need ||g|| below that floor.
+  BN running statistics: max|a-b| <= STAT_TOL * max(1, max|b|)
+  Adam step: new parameters equal torch.optim.Adam applied to the SAME gradients to ADAM_ABS
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from golden_util import make_inputs, make_oracle, set_dropout  # noqa: E402
+
+OUT_TOL = 4e-2
+GRAD_REL = 5e-2
+GRAD_NOISE_X = 2.0
+GRAD_FLOOR = 1e-4
+STAT_TOL = 2e-2
+ADAM_ABS = 2e-6
+
+
+def bf16_emulated_oracle(ora, image, ecg, clin, labels):
+    """Gradients of the oracle with bf16 storage emulated (see module docstring); returns name -> grad."""
+    import copy
+
+    from oracle import model as om
+
+    m = copy.deepcopy(ora)
+    m.zero_grad(set_to_none=True)
+
+    def hook(mod, i, o):
+        return o.to(torch.bfloat16).float()
+
+    kinds = (torch.nn.Conv2d, torch.nn.BatchNorm2d, torch.nn.Conv1d, torch.nn.BatchNorm1d, torch.nn.ReLU,
+             torch.nn.MaxPool2d, torch.nn.MaxPool1d)
+    with torch.no_grad():
+        for enc in (m.image_encoder, m.signal_encoder):
+            for mod in enc.modules():
+                if isinstance(mod, kinds):
+                    mod.register_forward_hook(hook)
+                if isinstance(mod, (torch.nn.Conv2d, torch.nn.Conv1d)) and mod.weight.shape[1] >= 64:
+                    mod.weight.copy_(mod.weight.to(torch.bfloat16).float())
+        m.image_encoder.conv1.weight.copy_(m.image_encoder.conv1.weight.to(torch.bfloat16).float())
+    out = m(image.to(torch.bfloat16).float(), ecg, clin)
+    om.fusion_loss(out, labels).backward()
+    return {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+
+
+def relmax(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / max(1.0, float(b.abs().max())))
+
+
+def build_pair(seed=7, dims=(256, 256, 256), signal_channels=1, clinical_features=24, dropout=0.0):
+    import ecgmm  # noqa: F401
+    from ecgmm.model import ECGMultimodalModel
+
+    ora = make_oracle(seed, dims, signal_channels, clinical_features)
+    set_dropout(ora, dropout)
+
+    class Cfg:
+        num_classes = 2
+        device = "cuda"
+
+    dut = ECGMultimodalModel(Cfg, dims=dims, clinical_features=clinical_features, signal_channels=signal_channels)
+    dut.load_state_dict(ora.state_dict())
+    set_dropout(dut, dropout)
+    return ora, dut
+
+
+def run_fusion_parity(B=4, H=64, W=160, L=600, train=True, adam=True, seed=7, dims=(256, 256, 256),
+                      signal_channels=1, verbose=False, inputs=None, expect=None):
+    """Runs oracle (CPU) and product (GPU) on identical weights/inputs; returns a report dict.
+
+    `expect`: optional golden dict (outputs / loss / grad_norms) replacing the live oracle run."""
+    from ecgmm import lib
+    from ecgmm import nn as enn
+    from ecgmm import optim as eoptim
+    from oracle import model as om
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_num_threads(os.cpu_count() or 8)
+    ora, dut = build_pair(seed, dims, signal_channels)
+    import copy
+
+    ora_clean = copy.deepcopy(ora)
+    ora_clean.train(train)
+    image, ecg, clin, labels = inputs if inputs is not None else make_inputs(100 + B, B, H, W, L,
+                                                                              signal_channels=signal_channels)
+    ora.train(train)
+    dut.train(train)
+    failures = []
+    rep = {"failures": failures}
+    calls0 = lib.CALLS
+
+    # ---- product
+    dev = "cuda"
+    d_out = dut(image.to(dev), ecg.to(dev), clin.to(dev))
+    crit = enn.CrossEntropyLoss()
+    d_loss = crit(d_out[3], labels.to(dev)) + 0.1 * d_out[4]
+    if train:
+        d_loss.backward()
+    torch.cuda.synchronize()
+    rep["kernels_launched"] = lib.CALLS - calls0
+
+    # ---- oracle
+    if expect is None:
+        o_out = ora(image, ecg, clin)
+        o_loss = om.fusion_loss(o_out, labels)
+        if train:
+            o_loss.backward()
+        o_out = [t.detach() for t in o_out]
+        o_loss = o_loss.detach()
+    else:
+        o_out, o_loss = expect["outputs"], expect["loss"]
+
+    names = ["img_logits", "signal_logits", "clinical_logits", "fusion_logits", "var_loss", "soft_weights"]
+    for n, a, b in zip(names, d_out, o_out):
+        e = relmax(a, b)
+        rep[f"out.{n}"] = e
+        if not e <= OUT_TOL:
+            failures.append(f"output {n}: rel-max error {e:.3g} > {OUT_TOL}")
+    rep["loss"], rep["loss_ref"] = float(d_loss), float(o_loss)
+    if not abs(rep["loss"] - rep["loss_ref"]) <= OUT_TOL * max(1.0, abs(rep["loss_ref"])):
+        failures.append(f"loss {rep['loss']} vs {rep['loss_ref']}")
+    zf, zr = d_out[3].detach().cpu(), o_out[3]
+    margin = (zr[:, 1] - zr[:, 0]).abs()
+    decided = margin > 2 * OUT_TOL
+    same = (zf.argmax(1) == zr.argmax(1))
+    rep["argmax_equal"] = bool(same[decided].all())
+    rep["argmax_decided"] = int(decided.sum())
+    if not rep["argmax_equal"]:
+        failures.append("fusion argmax differs on a sample with a decided margin")
+
+    if train and expect is None:
+        og = {k: p.grad for k, p in ora.named_parameters() if p.grad is not None}
+        dg = {k: p.grad for k, p in dut.named_parameters()}
+        # yardstick: the oracle under emulated bf16 storage (restores BN buffers: deepcopy inside)
+        eg = bf16_emulated_oracle(ora_clean, image, ecg, clin, labels)
+        scale = max(float(g.double().norm()) for g in og.values())
+        worst_ratio, worst_rel = 0.0, 0.0
+        for k, g_ref in og.items():
+            g = dg.get(k)
+            if g is None:
+                failures.append(f"grad {k}: missing")
+                continue
+            g = g.detach().double().cpu()
+            r = g_ref.double()
+            nr = float(r.norm())
+            if nr < GRAD_FLOOR * scale:
+                if float(g.norm()) > GRAD_FLOOR * scale:
+                    failures.append(f"grad {k}: reference ~0 ({nr:.3g}) but got norm {float(g.norm()):.3g}")
+                continue
+            rel = float((g - r).norm()) / nr
+            rel_emul = float((eg[k].double() - r).norm()) / nr
+            allowed = max(GRAD_REL, GRAD_NOISE_X * rel_emul)
+            worst_rel = max(worst_rel, rel)
+            worst_ratio = max(worst_ratio, rel / allowed)
+            if verbose and rel > 0.5 * allowed:
+                print(f"  grad {k:55s} rel {rel:.4f} (bf16-emulated oracle {rel_emul:.4f}) |g_ref| {nr:.4g}")
+            if not rel <= allowed:
+                failures.append(f"grad {k}: rel {rel:.3g} > allowed {allowed:.3g} (emulated {rel_emul:.3g})")
+        rep["grad_worst_rel"], rep["grad_worst_vs_allowed"] = worst_rel, worst_ratio
+        # running statistics after the training-mode forward
+        osd, dsd = ora.state_dict(), dut.state_dict()
+        worst = 0.0
+        for k in osd:
+            if "running_" in k:
+                e = relmax(dsd[k], osd[k])
+                worst = max(worst, e)
+                if not e <= STAT_TOL:
+                    failures.append(f"buffer {k}: {e:.3g}")
+            elif "num_batches" in k and int(dsd[k]) != int(osd[k]):
+                failures.append(f"buffer {k}: {int(dsd[k])} vs {int(osd[k])}")
+        rep["running_stat_worst"] = worst
+        if adam:
+            # same gradients through torch.optim.Adam (CPU) and through the libecgmm multi-tensor Adam
+            shadow = [torch.nn.Parameter(p.detach().cpu().clone()) for p in dut.parameters()]
+            for sp, p in zip(shadow, dut.parameters()):
+                sp.grad = None if p.grad is None else p.grad.detach().cpu().clone()
+            torch.optim.Adam(shadow, lr=1e-4).step()
+            eoptim.Adam(dut.parameters(), lr=1e-4).step()
+            torch.cuda.synchronize()
+            worst = max(float((sp.detach() - p.detach().cpu()).abs().max()) for sp, p in zip(shadow, dut.parameters()))
+            rep["adam_worst_abs"] = worst
+            if not worst <= ADAM_ABS:
+                failures.append(f"adam step differs from torch.optim.Adam on identical grads by {worst:.3g}")
+    rep["ok"] = not failures
+    if verbose:
+        for k, v in rep.items():
+            if k != "failures":
+                print(f"  {k}: {v}")
+        for f in failures[:40]:
+            print("  FAIL", f)
+    return rep
+
+
+if __name__ == "__main__":
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=4)
+    ap.add_argument("--H", type=int, default=64)
+    ap.add_argument("--W", type=int, default=160)
+    ap.add_argument("--L", type=int, default=600)
+    ap.add_argument("--eval", action="store_true")
+    a = ap.parse_args()
+    r = run_fusion_parity(a.B, a.H, a.W, a.L, train=not a.eval, verbose=True)
+    sys.exit(0 if r["ok"] else 1)

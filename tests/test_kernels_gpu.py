@@ -1,0 +1,348 @@
+"""Per-kernel parity: every libecgmm kernel family against the plain fp32 PyTorch operator it
+replaces, on the same (bf16-rounded where the kernel stores bf16) operands.
+
+Tolerances: kernels that write bf16 are compared with rtol 2^-7 (one bf16 ulp is 2^-8) plus a small
+atol scaled to the tensor; fp32-in/fp32-out kernels with 1e-4 relative L2."""
+import zlib
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import ecgmm  # noqa: F401
+from ecgmm import lib, ops
+from ecgmm import nn as enn
+from ecgmm import optim as eoptim
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF = torch.bfloat16
+
+
+def gen(name):
+    return torch.Generator().manual_seed(zlib.crc32(name.encode()) % (2**31))
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def close_bf16(a, b, what, rtol=2.0**-7, atol_scale=2.0**-7):
+    a, b = a.float().cpu(), b.float().cpu()
+    atol = atol_scale * float(b.abs().max()) * 0.25 + 1e-6
+    bad = (a - b).abs() > atol + rtol * b.abs()
+    assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.numel()} outside tolerance, max err {float((a - b).abs().max()):.4g}"
+
+
+def nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x_nhwc):
+    return x_nhwc.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    lib.require_device()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+# ------------------------------------------------------------------ BatchNorm forward
+@pytest.mark.parametrize("N,H,W,C", [(2, 7, 13, 64), (3, 1, 619, 128), (5, 16, 40, 256), (4, 8, 79, 512),
+                                     (130, 3, 5, 64)])
+@pytest.mark.parametrize("mode", ["plain", "res", "norelu"])
+def test_bn_train_forward(N, H, W, C, mode):
+    g = gen(f"bnf{N}{H}{W}{C}{mode}")
+    x = (torch.randn(N, C, H, W, generator=g) * 1.7 + 0.3).to(DEV).to(BF)
+    res = torch.randn(N, C, H, W, generator=g).to(DEV).to(BF) if mode == "res" else None
+    bn = torch.nn.BatchNorm2d(C).to(DEV)
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.3 * torch.randn(C, generator=g))
+        bn.bias.copy_(0.2 * torch.randn(C, generator=g))
+        bn.running_mean.copy_(0.1 * torch.randn(C, generator=g))
+        bn.running_var.copy_(1 + 0.2 * torch.rand(C, generator=g))
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    bias = (0.5 * torch.randn(C, generator=g)).to(DEV)
+    # reference: conv bias added before BN (it cancels in y, shows up in running_mean)
+    y_ref = bn(x.float() + bias.view(1, C, 1, 1))
+    if res is not None:
+        y_ref = y_ref + res.float()
+    if mode != "norelu":
+        y_ref = F.relu(y_ref)
+    rm_ref, rv_ref = bn.running_mean.clone(), bn.running_var.clone()
+    xn = nhwc(x)
+    st = ops.bn_train_stats(xn, bn.weight.detach(), bn.bias.detach(), rm0, rv0, None, bn.eps, bn.momentum,
+                            conv_bias=bias, want_nsum=True)
+    y = ops.bn_apply(xn, st, res=None if res is None else nhwc(res), relu=mode != "norelu")
+    close_bf16(nchw(y), y_ref.detach(), "bn forward")
+    assert rel_l2(rm0, rm_ref) < 1e-4 and rel_l2(rv0, rv_ref) < 1e-4
+    assert rel_l2(st.nsum, x.float().sum(dim=(2, 3))) < 1e-4 or float(st.nsum.abs().max()) < 1e-3
+
+
+def test_bn_eval_coeffs():
+    g = gen("bneval")
+    C = 128
+    x = torch.randn(2, C, 5, 9, generator=g).to(DEV).to(BF)
+    bn = torch.nn.BatchNorm2d(C).to(DEV).eval()
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.3 * torch.randn(C, generator=g))
+        bn.bias.copy_(0.2 * torch.randn(C, generator=g))
+        bn.running_mean.copy_(0.4 * torch.randn(C, generator=g))
+        bn.running_var.copy_(0.5 + torch.rand(C, generator=g))
+    bias = torch.randn(C, generator=g).to(DEV)
+    y_ref = F.relu(bn(x.float() + bias.view(1, C, 1, 1)))
+    st = ops.bn_eval_coeffs(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps, bias)
+    y = ops.bn_apply(nhwc(x), st, relu=True)
+    close_bf16(nchw(y), y_ref, "bn eval")
+
+
+# ------------------------------------------------------------------ BatchNorm backward
+@pytest.mark.parametrize("N,H,W,C", [(2, 7, 13, 64), (3, 1, 310, 128), (4, 8, 79, 512), (70, 4, 6, 256)])
+@pytest.mark.parametrize("mode", ["relu", "res_relu", "linear"])
+def test_bn_backward(N, H, W, C, mode):
+    g = gen(f"bnb{N}{H}{W}{C}{mode}")
+    x = (torch.randn(N, C, H, W, generator=g) * 1.3 + 0.2).to(DEV).to(BF)
+    res = torch.randn(N, C, H, W, generator=g).to(DEV).to(BF) if mode == "res_relu" else None
+    dy = torch.randn(N, C, H, W, generator=g).to(DEV).to(BF)
+    gamma = (1 + 0.3 * torch.randn(C, generator=g)).to(DEV).requires_grad_(True)
+    beta = (0.2 * torch.randn(C, generator=g)).to(DEV).requires_grad_(True)
+    xr = x.float().requires_grad_(True)
+    y_ref = F.batch_norm(xr, None, None, gamma, beta, True, 0.1, 1e-5)
+    if res is not None:
+        y_ref = y_ref + res.float()
+    if mode != "linear":
+        y_ref = F.relu(y_ref)
+    y_ref.backward(dy.float())
+    xn = nhwc(x)
+    st = ops.bn_train_stats(xn, gamma.detach(), beta.detach(), None, None, None, 1e-5, 0.1)
+    y = ops.bn_apply(xn, st, res=None if res is None else nhwc(res), relu=mode != "linear")
+    dg, db = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    dx, dz = ops.bn_backward(xn, nhwc(dy), st, gamma.detach(), y=y if mode != "linear" else None, want_dz=True,
+                             dgamma=dg, dbeta=db)
+    # ReLU mask taken from the bf16 output: elements whose pre-activation rounds to 0 may differ -> L2 metric
+    assert rel_l2(nchw(dx), xr.grad) < 2e-2
+    assert rel_l2(dg, gamma.grad) < 1e-2 and rel_l2(db, beta.grad) < 1e-2
+    if mode != "linear":
+        mask = (y_ref > 0).float()
+        assert rel_l2(nchw(dz), dy.float() * mask) < 1e-2
+
+
+# ------------------------------------------------------------------ stem BN + ReLU + max-pool
+@pytest.mark.parametrize("N,H,W", [(2, 13, 21, ), (3, 1, 75), (2, 32, 50), (1, 125, 64)])
+def test_stem_pool_forward_backward(N, H, W):
+    C = 64
+    g = gen(f"pool{N}{H}{W}")
+    x = (torch.randn(N, C, H, W, generator=g) * 1.5).to(DEV).to(BF)
+    gamma = (1 + 0.3 * torch.randn(C, generator=g)).to(DEV).requires_grad_(True)
+    gamma.data[3] = -0.7  # negative scale: max-pool must run after the affine map
+    beta = (0.2 * torch.randn(C, generator=g)).to(DEV).requires_grad_(True)
+    xr = x.float().requires_grad_(True)
+    a = F.relu(F.batch_norm(xr, None, None, gamma, beta, True, 0.1, 1e-5))
+    y_ref = F.max_pool2d(a, 3, 2, 1)
+    dyp = torch.randn(y_ref.shape, generator=g).to(DEV).to(BF)
+    y_ref.backward(dyp.float())
+    xn = nhwc(x)
+    st = ops.bn_train_stats(xn, gamma.detach(), beta.detach(), None, None, None, 1e-5, 0.1)
+    y, arg = ops.bn_relu_maxpool(xn, st)
+    assert tuple(y.shape) == (N, y_ref.shape[2], y_ref.shape[3], C)
+    close_bf16(nchw(y), y_ref.detach(), "pool forward")
+    dg, db = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    dx, _ = ops.bn_backward(xn, nhwc(dyp), st, gamma.detach(), argmax=arg, dgamma=dg, dbeta=db)
+    assert rel_l2(nchw(dx), xr.grad) < 2e-2
+    assert rel_l2(dg, gamma.grad) < 1e-2 and rel_l2(db, beta.grad) < 1e-2
+
+
+def test_avgpool():
+    g = gen("avg")
+    x = torch.randn(5, 8, 79, 512, generator=g).to(DEV).to(BF)
+    out = ops.avgpool_fwd(x)
+    assert rel_l2(out, x.float().mean(dim=(1, 2))) < 1e-5
+    d = torch.randn(5, 512, generator=g).to(DEV)
+    dx = ops.avgpool_bwd(d, x.shape)
+    close_bf16(dx, (d / (8 * 79)).view(5, 1, 1, 512).expand(5, 8, 79, 512), "avgpool bwd")
+
+
+# ------------------------------------------------------------------ 1-D stem
+@pytest.mark.parametrize("B,Cin,L", [(3, 1, 2476), (2, 12, 5000), (2, 12, 777), (1, 1, 9)])
+def test_signal_stem(B, Cin, L):
+    g = gen(f"sstem{B}{Cin}{L}")
+    x = torch.randn(B, Cin, L, generator=g).to(DEV)
+    w = (torch.randn(64, Cin, 7, generator=g) / (7 * Cin) ** 0.5).to(DEV).requires_grad_(True)
+    y_ref = F.conv1d(x, w, None, 2, 3)
+    y = ops.signal_stem_fwd(x, w.detach())
+    assert tuple(y.shape) == (B, 1, y_ref.shape[2], 64)
+    close_bf16(y[:, 0].permute(0, 2, 1), y_ref.detach(), "signal stem fwd")
+    dy = torch.randn(y_ref.shape, generator=g).to(DEV).to(BF)
+    y_ref.backward(dy.float())
+    dw = torch.zeros_like(w)
+    ops.signal_stem_wgrad(x, dy.permute(0, 2, 1).contiguous().view(B, 1, -1, 64), dw)
+    assert rel_l2(dw, w.grad) < 1e-4
+
+
+# ------------------------------------------------------------------ dense kernels
+@pytest.mark.parametrize("M,N,K", [(5, 2, 128), (512, 256, 512), (37, 64, 24), (130, 128, 768)])
+def test_linear(M, N, K):
+    g = gen(f"lin{M}{N}{K}")
+    x = torch.randn(M, K, generator=g).to(DEV).requires_grad_(True)
+    lin = torch.nn.Linear(K, N).to(DEV)
+    y_ref = F.relu(lin(x))
+    y = ops.linear_fwd(x.detach(), lin.weight.detach(), lin.bias.detach(), relu=True)
+    assert rel_l2(y, y_ref) < 1e-5
+    dy = torch.randn(M, N, generator=g).to(DEV)
+    lin(x).backward(dy)
+    dw, db = torch.empty_like(lin.weight), torch.empty_like(lin.bias)
+    dx = ops.linear_bwd(x.detach(), lin.weight.detach(), dy, dw=dw, db=db)
+    assert rel_l2(dx, x.grad) < 1e-5 and rel_l2(dw, lin.weight.grad) < 1e-5 and rel_l2(db, lin.bias.grad) < 1e-5
+
+
+@pytest.mark.parametrize("rows,D", [(4, 256), (33, 768), (512, 32)])
+def test_layernorm(rows, D):
+    g = gen(f"ln{rows}{D}")
+    x = (torch.randn(rows, D, generator=g) * 2 + 0.5).to(DEV).requires_grad_(True)
+    ln = torch.nn.LayerNorm(D).to(DEV)
+    with torch.no_grad():
+        ln.weight.copy_(1 + 0.2 * torch.randn(D, generator=g))
+        ln.bias.copy_(0.1 * torch.randn(D, generator=g))
+    y_ref = ln(x)
+    dy = torch.randn(rows, D, generator=g).to(DEV)
+    y_ref.backward(dy)
+    y, mean, rstd = ops.layernorm_fwd(x.detach(), ln.weight.detach(), ln.bias.detach(), ln.eps)
+    assert rel_l2(y, y_ref) < 1e-5
+    dg, db = torch.empty(D, device=DEV), torch.empty(D, device=DEV)
+    dx = ops.layernorm_bwd(x.detach(), dy, ln.weight.detach(), mean, rstd, dg, db)
+    assert rel_l2(dx, x.grad) < 1e-4 and rel_l2(dg, ln.weight.grad) < 1e-4 and rel_l2(db, ln.bias.grad) < 1e-4
+
+
+@pytest.mark.parametrize("B,C,focal", [(16, 2, 0), (16, 2, 1), (300, 5, 1), (1, 2, 0)])
+def test_losses(B, C, focal):
+    g = gen(f"loss{B}{C}{focal}")
+    z = (torch.randn(B, C, generator=g) * 2).to(DEV).requires_grad_(True)
+    y = torch.randint(0, C, (B,), generator=g).to(DEV)
+    if focal:
+        ce = F.cross_entropy(z, y, reduction="none")
+        ref = (1.0 * (1 - torch.exp(-ce)) ** 2.0 * ce).mean()
+        crit = enn.FocalLoss()
+    else:
+        ref = F.cross_entropy(z, y)
+        crit = enn.CrossEntropyLoss()
+    (ref * 1.7).backward()
+    z2 = z.detach().clone().requires_grad_(True)
+    out = crit(z2, y)
+    (out * 1.7).backward()
+    assert abs(float(out) - float(ref)) < 1e-5 * max(1, abs(float(ref)))
+    assert rel_l2(z2.grad, z.grad) < 1e-4
+
+
+def test_zscore_and_dropout():
+    g = gen("zs")
+    x = (torch.randn(7, 12, 5000, generator=g) * 3 + 1).to(DEV)
+    y = ops.zscore(x)
+    ref = (x - x.mean(-1, keepdim=True)) / (x.var(-1, unbiased=False, keepdim=True).sqrt() + 1e-8)
+    assert rel_l2(y, ref) < 1e-5
+    h = torch.ones(1 << 16, device=DEV)
+    yd, mask = ops.dropout_fwd(h, 0.3, 1234)
+    keep = float((mask > 0).float().mean())
+    assert abs(keep - 0.7) < 0.01 and abs(float(yd.mean()) - 1.0) < 0.02
+    yd2, _ = ops.dropout_fwd(h, 0.3, 1234)
+    assert torch.equal(yd, yd2)
+    y0, _ = ops.dropout_fwd(h, 0.0, 1)
+    assert torch.equal(y0, h)
+
+
+@pytest.mark.parametrize("steps", [1, 3])
+def test_adam_matches_torch(steps):
+    g = gen("adam")
+    shapes = [(64, 3, 7, 7), (64,), (3,), (128, 64, 3, 3), (70001,)]
+    ps_ref = [torch.nn.Parameter(torch.randn(s, generator=g).to(DEV)) for s in shapes]
+    ps = [torch.nn.Parameter(p.detach().clone()) for p in ps_ref]
+    o_ref = torch.optim.Adam(ps_ref, lr=1e-3)
+    o = eoptim.Adam(ps, lr=1e-3)
+    for it in range(steps):
+        for a, b in zip(ps_ref, ps):
+            gr = torch.randn(a.shape, generator=g).to(DEV) * (0.1 + it)
+            a.grad = gr.clone()
+            b.grad = gr.clone()
+        if it == 2:
+            for grp in o_ref.param_groups + o.param_groups:
+                grp["lr"] /= 10  # train.py:158-161
+        o_ref.step()
+        o.step()
+    for a, b in zip(ps_ref, ps):
+        assert float((a - b).abs().max()) < 2e-6
+    sd = o.state_dict()
+    assert set(sd["state"][0].keys()) >= {"step", "exp_avg", "exp_avg_sq"}
+
+
+# ------------------------------------------------------------------ whole 1-D SE block
+def test_basic_block_1d_se():
+    from ecgmm import model as M
+    from oracle.model import BasicBlock1D as RefBlock
+
+    torch.manual_seed(3)
+    ref = RefBlock(64, 128, stride=2).to(DEV)
+    blk = M.BasicBlock1D(64, 128, stride=2).to(DEV)
+    # weights representable in bf16 so that only activation rounding differs
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.copy_(p.to(BF).float())
+        for m in ref.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.copy_(1 + 0.2 * torch.randn_like(m.weight))
+                m.bias.copy_(0.1 * torch.randn_like(m.bias))
+    blk.load_state_dict(ref.state_dict())
+    g = gen("blk1d")
+    x = torch.randn(6, 64, 619, generator=g).to(DEV).to(BF)
+    xr = x.float().requires_grad_(True)
+    out_ref = ref(xr)
+    dout = torch.randn(out_ref.shape, generator=g).to(DEV).to(BF)
+    out_ref.backward(dout.float())
+    xin = x.permute(0, 2, 1).contiguous().view(6, 1, 619, 64)
+    out, rec = M._conv_block_fwd(blk, xin, save=True)
+    assert rel_l2(out[:, 0].permute(0, 2, 1), out_ref) < 1e-2
+    G = M.GradArena(list(blk.parameters()), DEV)
+    dx = M._conv_block_bwd(blk, rec, dout.permute(0, 2, 1).contiguous().view(6, 1, -1, 128), G)
+    assert rel_l2(dx[:, 0].permute(0, 2, 1), xr.grad) < 5e-2
+    scale = max(float(p.grad.norm()) for p in ref.parameters())
+    for (k, pr), (_, p) in zip(ref.named_parameters(), blk.named_parameters()):
+        if float(pr.grad.norm()) < 1e-4 * scale:
+            assert float(G(p).norm()) < 1e-3 * scale, k
+            continue
+        assert rel_l2(G(p), pr.grad) < 5e-2, (k, rel_l2(G(p), pr.grad))
+    for (k, a), (_, b) in zip(ref.state_dict().items(), blk.state_dict().items()):
+        if "running" in k:
+            assert rel_l2(b, a) < 1e-2, k
+
+
+@pytest.mark.parametrize("cin,cout,stride,H,W", [(64, 64, 1, 16, 40), (64, 128, 2, 17, 45), (256, 512, 2, 16, 39)])
+def test_basic_block_2d(cin, cout, stride, H, W):
+    from ecgmm import model as M
+    from oracle.model import BasicBlock2D as RefBlock
+
+    torch.manual_seed(5)
+    ref = RefBlock(cin, cout, stride).to(DEV)
+    blk = M.BasicBlock(cin, cout, stride).to(DEV)
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.copy_(p.to(BF).float())
+        for m in ref.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.copy_(1 + 0.2 * torch.randn_like(m.weight))
+                m.bias.copy_(0.1 * torch.randn_like(m.bias))
+    blk.load_state_dict(ref.state_dict())
+    g = gen(f"blk2d{cin}{cout}")
+    N = 4
+    x = torch.randn(N, cin, H, W, generator=g).to(DEV).to(BF)
+    xr = x.float().requires_grad_(True)
+    out_ref = ref(xr)
+    dout = torch.randn(out_ref.shape, generator=g).to(DEV).to(BF)
+    out_ref.backward(dout.float())
+    out, rec = M._conv_block_fwd(blk, nhwc(x), save=True)
+    assert rel_l2(nchw(out), out_ref) < 1e-2
+    G = M.GradArena(list(blk.parameters()), DEV)
+    dx = M._conv_block_bwd(blk, rec, nhwc(dout), G)
+    assert rel_l2(nchw(dx), xr.grad) < 5e-2
+    for (k, pr), (_, p) in zip(ref.named_parameters(), blk.named_parameters()):
+        assert rel_l2(G(p), pr.grad) < 5e-2, (k, rel_l2(G(p), pr.grad))
