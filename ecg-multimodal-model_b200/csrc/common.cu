@@ -9,6 +9,7 @@
 namespace ecgmm {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -104,7 +105,9 @@ void pick_tile(int OH, int OW, int npix, int* TH, int* TW) {
 
 extern "C" {
 
-int ecgmm_version(void) { return 100; }
+int ecgmm_version(void) { return 101; }
+
+unsigned long long ecgmm_launch_count(void) { return ecgmm::g_launches; }
 
 const char* ecgmm_last_error(void) { return ecgmm::g_err; }
 

@@ -31,7 +31,11 @@ void set_error(const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
-inline int check_launch(const char* what) {
+// Number of kernel launches issued by this library in this process (ecgmm_launch_count()).
+extern unsigned long long g_launches;
+
+inline int check_launch(const char* what, int n_kernels = 1) {
+  g_launches += (unsigned long long)n_kernels;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("launch of %s failed: %s", what, cudaGetErrorString(e));

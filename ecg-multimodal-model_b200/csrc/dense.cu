@@ -641,7 +641,7 @@ extern "C" int ecgmm_layernorm_bwd(const float* x, const float* dy, const float*
   if (dx) layernorm_bwd_dx_kernel<<<rows, 256, 0, st>>>(x, dy, gamma, mean, rstd, dx, D, accumulate_dx);
   if (dgamma || dbeta)
     layernorm_bwd_params_kernel<<<ceil_div(D, 32), dim3(32, 8), 0, st>>>(x, dy, mean, rstd, dgamma, dbeta, rows, D);
-  return check_launch("layernorm_bwd");
+  return check_launch("layernorm_bwd", (dx ? 1 : 0) + ((dgamma || dbeta) ? 1 : 0));
 }
 
 extern "C" int ecgmm_fusion_gate_fwd(const float* f0, const float* f1, const float* f2, const float* weights,
@@ -664,7 +664,7 @@ extern "C" int ecgmm_fusion_gate_bwd(const float* dfused, const float* f0, const
     fusion_gate_bwd_feat_kernel<<<ew_grid(total), 256, 0, st>>>(dfused, weights, df0, df1, df2, B, D0, D1, D2,
                                                                 accumulate);
   if (dweights) fusion_gate_bwd_w_kernel<<<1, 1024, 0, st>>>(dfused, f0, f1, f2, weights, dweights, B, D0, D1, D2);
-  return check_launch("fusion_gate_bwd");
+  return check_launch("fusion_gate_bwd", ((df0 && df1 && df2) ? 1 : 0) + (dweights ? 1 : 0));
 }
 
 extern "C" int ecgmm_var_loss_fwd(const float* f0, const float* f1, const float* f2, float* loss, float* row_mean,

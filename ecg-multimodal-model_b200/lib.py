@@ -22,6 +22,7 @@ SIGNATURES = {
     "ecgmm_version": [],
     "ecgmm_last_error": [],
     "ecgmm_check_device": [],
+    "ecgmm_launch_count": [],
     "ecgmm_nchw_f32_to_nhwc_bf16": [_p, _p, _i, _i, _i, _i, _p],
     "ecgmm_nhwc_bf16_to_nchw_f32": [_p, _p, _i, _i, _i, _i, _p],
     "ecgmm_conv_weight_prep": [_p, _p, _p, _i, _i, _i, _i, _p],
@@ -69,7 +70,7 @@ SIGNATURES = {
     "ecgmm_adam_chunk_bytes": [],
     "ecgmm_adam_step": [_p, _i, _f, _f, _f, _f, _f, _ll, _f, _p],
 }
-_RESTYPES = {"ecgmm_last_error": c_char_p, "ecgmm_stem_s2d_dims": None}
+_RESTYPES = {"ecgmm_last_error": c_char_p, "ecgmm_stem_s2d_dims": None, "ecgmm_launch_count": c_ulonglong}
 
 
 class EcgmmError(RuntimeError):
@@ -110,6 +111,11 @@ def call(name: str, *args) -> None:
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise EcgmmError(f"{name} failed with status {rc}: {last_error()}")
+
+
+def launch_count() -> int:
+    """Kernels launched by libecgmm in this process so far."""
+    return int(load().ecgmm_launch_count())
 
 
 def stream_ptr() -> int:

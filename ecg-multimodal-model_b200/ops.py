@@ -31,6 +31,22 @@ def _s():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# When bench.py sets PROFILE to a list, every convolution call is bracketed by CUDA events on the
+# launching stream and appended as (kind, algorithmic_flops, start_event, end_event).
+PROFILE = None
+
+
+def _timed(kind, flops, name, *args):
+    if PROFILE is None:
+        lib.call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lib.call(name, *args)
+    e1.record()
+    PROFILE.append((kind, flops, e0, e1))
+
+
 # ---------------------------------------------------------------- layout
 def nchw_to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
     _chk(x, torch.float32, "x")
@@ -76,7 +92,8 @@ def conv2d_fwd(x: torch.Tensor, w_fwd: torch.Tensor, stride: int = 1) -> torch.T
     pH, pW = R // 2, S // 2
     Ho, Wo = _conv_out(H, W, R, S, stride, pH, pW)
     y = torch.empty((N, Ho, Wo, Cout), dtype=BF16, device=x.device)
-    lib.call("ecgmm_conv2d_fwd", _ptr(x), _ptr(w_fwd), _ptr(y), N, H, W, Cin, Cout, R, S, stride, pH, pW, _s())
+    _timed("conv_fwd", 2.0 * N * Ho * Wo * Cout * Cin * R * S, "ecgmm_conv2d_fwd", _ptr(x), _ptr(w_fwd), _ptr(y), N,
+           H, W, Cin, Cout, R, S, stride, pH, pW, _s())
     return y
 
 
@@ -96,8 +113,8 @@ def conv2d_dgrad(dy: torch.Tensor, w_dgrad: torch.Tensor, in_hw, stride: int = 1
     else:
         _chk(out, BF16, "out")
         assert tuple(out.shape) == (N, H, W, Cin)
-    lib.call("ecgmm_conv2d_dgrad", _ptr(dy), _ptr(w_dgrad), _ptr(out), N, H, W, Cin, Cout, R, S, stride, pH, pW,
-             int(accumulate), _s())
+    _timed("conv_dgrad", 2.0 * N * Ho * Wo * Cout * Cin * R * S, "ecgmm_conv2d_dgrad", _ptr(dy), _ptr(w_dgrad),
+           _ptr(out), N, H, W, Cin, Cout, R, S, stride, pH, pW, int(accumulate), _s())
     return out
 
 
@@ -109,8 +126,8 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, R: int, S:
     N, H, W, Cin = x.shape
     Cout = dy.shape[3]
     assert dw.numel() == Cout * Cin * R * S
-    lib.call("ecgmm_conv2d_wgrad", _ptr(x), _ptr(dy), _ptr(dw), N, H, W, Cin, Cout, R, S, stride, R // 2, S // 2,
-             _s())
+    _timed("conv_wgrad", 2.0 * N * dy.shape[1] * dy.shape[2] * Cout * Cin * R * S, "ecgmm_conv2d_wgrad", _ptr(x),
+           _ptr(dy), _ptr(dw), N, H, W, Cin, Cout, R, S, stride, R // 2, S // 2, _s())
 
 
 # ---------------------------------------------------------------- ResNet stem
@@ -148,7 +165,8 @@ def stem_conv_fwd(xs: torch.Tensor, w_s2d: torch.Tensor, H: int, W: int) -> torc
     N = xs.shape[0]
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty((N, Ho, Wo, 64), dtype=BF16, device=xs.device)
-    lib.call("ecgmm_stem_conv_fwd", _ptr(xs), _ptr(w_s2d), _ptr(y), N, H, W, _s())
+    _timed("stem_fwd", 2.0 * N * Ho * Wo * 64 * 147, "ecgmm_stem_conv_fwd", _ptr(xs), _ptr(w_s2d), _ptr(y), N, H, W,
+           _s())
     return y
 
 
@@ -157,7 +175,8 @@ def stem_conv_wgrad(xs: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, H: int
     _chk(dy, BF16, "dy")
     _chk(dw, torch.float32, "dw")
     assert dw.numel() == 64 * 3 * 49
-    lib.call("ecgmm_stem_conv_wgrad", _ptr(xs), _ptr(dy), _ptr(dw), xs.shape[0], H, W, _s())
+    _timed("stem_wgrad", 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * 64 * 147, "ecgmm_stem_conv_wgrad", _ptr(xs),
+           _ptr(dy), _ptr(dw), xs.shape[0], H, W, _s())
 
 
 # ---------------------------------------------------------------- BatchNorm / ReLU / pooling
@@ -192,7 +211,7 @@ def bn_train_stats(x, gamma, beta, running_mean, running_var, num_batches, eps, 
     split = lib.load().ecgmm_reduce_split(N, P, C)
     part = _f32(2 * N * split * C, dev)
     psum, psq = part[: N * split * C], part[N * split * C:]
-    lib.call("ecgmm_chan_stats", _ptr(x), _ptr(psum), _ptr(psq), N, P, C, split, _s())
+    _timed("bn_stats", 2.0 * N * P * C, "ecgmm_chan_stats", _ptr(x), _ptr(psum), _ptr(psq), N, P, C, split, _s())
     out = _f32(4 * C, dev)
     mean, invstd, scale, shift = out[:C], out[C:2 * C], out[2 * C:3 * C], out[3 * C:]
     nsum = _f32(N * C, dev).view(N, C) if want_nsum else None
@@ -218,8 +237,8 @@ def bn_apply(x, st: BNStats, se=None, res=None, relu=True, out=None):
     if res is not None:
         _chk(res, BF16, "res")
         assert res.shape == x.shape
-    lib.call("ecgmm_bn_apply", _ptr(x), _ptr(st.scale), _ptr(st.shift), _ptr(se), _ptr(res), _ptr(y), N, P, C,
-             int(relu), _s())
+    _timed("bn_apply", 2.0 * N * P * C * (3 if res is not None else 2), "ecgmm_bn_apply", _ptr(x), _ptr(st.scale),
+           _ptr(st.shift), _ptr(se), _ptr(res), _ptr(y), N, P, C, int(relu), _s())
     return y
 
 
@@ -230,7 +249,8 @@ def bn_relu_maxpool(x, st: BNStats, want_argmax=True):
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty((N, Ho, Wo, C), dtype=BF16, device=x.device)
     arg = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device=x.device) if want_argmax else None
-    lib.call("ecgmm_bn_relu_maxpool", _ptr(x), _ptr(st.scale), _ptr(st.shift), _ptr(y), _ptr(arg), N, H, W, C, _s())
+    _timed("bn_pool_fwd", 2.0 * N * H * W * C + (3.0 if want_argmax else 2.0) * N * Ho * Wo * C,
+           "ecgmm_bn_relu_maxpool", _ptr(x), _ptr(st.scale), _ptr(st.shift), _ptr(y), _ptr(arg), N, H, W, C, _s())
     return y, arg
 
 
@@ -256,8 +276,10 @@ def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=
     split = lib.load().ecgmm_reduce_split(N, P, C)
     part = _f32(2 * N * split * C, dev)
     p1, p2 = part[: N * split * C], part[N * split * C:]
-    lib.call("ecgmm_bn_bwd_reduce", _ptr(x), _ptr(dy), _ptr(y), _ptr(argmax), _ptr(st.mean), _ptr(st.invstd),
-             _ptr(st.scale), _ptr(st.shift), _ptr(p1), _ptr(p2), N, H_, W_, C, split, mode, _s())
+    # algorithmic bytes of the two backward passes: x + (dy | pooled dy + argmax) [+ y]; the apply pass also writes dx [+ dz]
+    rd = 2.0 * N * P * C * (3 if mode == 1 else 2) if mode != 2 else 2.0 * N * P * C + 3.0 * dy.numel()
+    _timed("bn_bwd_reduce", rd, "ecgmm_bn_bwd_reduce", _ptr(x), _ptr(dy), _ptr(y), _ptr(argmax), _ptr(st.mean),
+           _ptr(st.invstd), _ptr(st.scale), _ptr(st.shift), _ptr(p1), _ptr(p2), N, H_, W_, C, split, mode, _s())
     q = None
     if se is not None:
         q = se_ctx(p1, p2, split)
@@ -269,8 +291,9 @@ def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=
              _ptr(cB), _ptr(cD), _s())
     dx = torch.empty_like(x)
     dz = torch.empty_like(x) if want_dz else None
-    lib.call("ecgmm_bn_bwd_apply", _ptr(x), _ptr(dy), _ptr(y), _ptr(argmax), _ptr(cA), _ptr(cB), _ptr(cD),
-             _ptr(st.scale), _ptr(st.shift), _ptr(se), _ptr(q), _ptr(dx), _ptr(dz), N, H_, W_, C, mode, _s())
+    _timed("bn_bwd_apply", rd + 2.0 * N * P * C * (2 if want_dz else 1), "ecgmm_bn_bwd_apply", _ptr(x), _ptr(dy),
+           _ptr(y), _ptr(argmax), _ptr(cA), _ptr(cB), _ptr(cD), _ptr(st.scale), _ptr(st.shift), _ptr(se), _ptr(q),
+           _ptr(dx), _ptr(dz), N, H_, W_, C, mode, _s())
     return dx, dz
 
 

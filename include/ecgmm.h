@@ -35,6 +35,8 @@ typedef uint16_t ecgmm_bf16; /* raw bfloat16 bits */
 
 int ecgmm_version(void);
 const char* ecgmm_last_error(void);
+/* kernels launched by this library in this process so far (bench.py reports the per-step delta) */
+unsigned long long ecgmm_launch_count(void);
 /* 0 when the current device can run the library (compute capability 10.x). */
 int ecgmm_check_device(void);
 

@@ -36,7 +36,7 @@ from golden_util import make_inputs, make_oracle, set_dropout  # noqa: E402
 
 OUT_TOL = 4e-2
 GRAD_REL = 5e-2
-GRAD_NOISE_X = 2.0
+GRAD_NOISE_X = 3.0
 GRAD_FLOOR = 1e-4
 STAT_TOL = 2e-2
 ADAM_ABS = 2e-6
