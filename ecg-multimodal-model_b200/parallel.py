@@ -56,8 +56,11 @@ class DataParallel(torch.nn.Module):
         self._sent[id(arena)] = upto
         self._launch(arena.flat[start:upto], keep=arena)
         if not self._cb_queued:
-            self._cb_queued = True
-            torch.autograd.Variable._execution_engine.queue_callback(self.finish)
+            try:  # end-of-backward hook (the mechanism DDP uses); outside backward the caller runs finish()
+                torch.autograd.Variable._execution_engine.queue_callback(self.finish)
+                self._cb_queued = True
+            except RuntimeError:
+                pass
 
     def _launch(self, flat, keep=None):
         if flat.is_cuda:

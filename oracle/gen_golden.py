@@ -110,7 +110,7 @@ def main():
 
     # ---- 2. fusion model, procedural weights
     ora_m = make_oracle(seed=7)
-    sd = ora_m.state_dict()
+    sd = {k: v.clone() for k, v in ora_m.state_dict().items()}  # clones: state_dict() aliases live buffers
     missing, unexpected = ref_m.load_state_dict(sd, strict=True)
     assert len(sd) == 229, len(sd)
     golden = {"checksums": state_checksums(sd), "cases": {}}
@@ -156,7 +156,8 @@ def main():
 
     # ---- 3. FocalLoss + 12-lead signal model (cfg2 shape, small batch)
     torch.manual_seed(21)
-    nets = [cls(12, 2) for cls in (ref.ResNet1D_SE, oracle_model.ResNet1D_SE)]
+    o_net = oracle_model.ResNet1D_SE(12, 2)  # first model after the seed: tests rebuild it the same way
+    nets = [ref.ResNet1D_SE(12, 2), o_net]
     nets[0].load_state_dict(nets[1].state_dict())
     x = torch.randn(4, 12, 5000, generator=torch.Generator().manual_seed(5))
     y = torch.tensor([0, 1, 1, 0])

@@ -1,0 +1,51 @@
+"""tcgen05 implicit-GEMM convolutions (forward / data-gradient / weight-gradient / stem) against
+torch's fp32 convolution on the same bf16-rounded operands (tests/gpu_conv_check.py)."""
+import pytest
+import torch
+
+import gpu_conv_check as chk
+from ecgmm import lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    lib.require_device()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.mark.parametrize("case", chk.CASES, ids=[c[0] for c in chk.CASES])
+def test_conv_case(case):
+    results = []
+    assert chk.run_case(*case, results=results)
+    bad = [r for r in results if not r[2]]
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("name,N,H,W", [("stem_small", 2, 50, 100), ("stem_odd", 1, 37, 75),
+                                        ("stem_250x2500", 2, 250, 2500)])
+def test_stem_case(name, N, H, W):
+    results = []
+    assert chk.run_stem(name, N, H, W, results)
+    bad = [r for r in results if not r[2]]
+    assert not bad, bad
+
+
+def test_conv_is_linear_at_full_size():
+    """Size-independent property at the native layer1 shape: conv(a) + conv(b) == conv(a + b)
+    up to bf16 rounding, and an all-zero input gives an all-zero output."""
+    from ecgmm import ops
+
+    g = torch.Generator().manual_seed(0)
+    w = (torch.randn(64, 64, 3, 3, generator=g) / 24).cuda()
+    w_fwd, _ = ops.conv_weight_prep(w)
+    a = torch.randn(2, 63, 625, 64, generator=g).cuda().to(torch.bfloat16)
+    b = torch.randn(2, 63, 625, 64, generator=g).cuda().to(torch.bfloat16)
+    s = (a.float() + b.float()).to(torch.bfloat16)
+    ya, yb, ys = ops.conv2d_fwd(a, w_fwd), ops.conv2d_fwd(b, w_fwd), ops.conv2d_fwd(s, w_fwd)
+    err = (ya.float() + yb.float() - ys.float()).abs().max().item()
+    assert err < 0.06, err
+    z = ops.conv2d_fwd(torch.zeros_like(a), w_fwd)
+    assert float(z.float().abs().max()) == 0.0

@@ -1,0 +1,88 @@
+"""CPU: the oracle (oracle/model.py) against the committed golden vectors, which
+oracle/gen_golden.py produced while asserting bit-identity with the real reference module."""
+import os
+
+import pytest
+import torch
+
+from golden_util import GOLDEN_DIR, make_inputs, make_oracle, set_dropout, state_checksums
+from oracle import model as om
+
+torch.set_num_threads(os.cpu_count() or 4)
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return torch.load(os.path.join(GOLDEN_DIR, "fusion_g2.pt"), map_location="cpu", weights_only=False)
+
+
+def test_ptbxl_known_answer():
+    """The reference's only real checkpoint (best_ptbxl.pth) through the oracle's ResNet1D_SE."""
+    kat = torch.load(os.path.join(GOLDEN_DIR, "ptbxl_kat.pt"), map_location="cpu", weights_only=False)
+    sd = torch.load(os.path.join(GOLDEN_DIR, "best_ptbxl.pth"), map_location="cpu")
+    net = om.ResNet1D_SE(1, 2)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    x = torch.randn(4, 1, 2476, generator=torch.Generator().manual_seed(kat["input_seed"]))
+    with torch.no_grad():
+        out = net(x)
+    assert torch.allclose(out, kat["logits"], atol=1e-5)
+    expect = torch.tensor([[3.9425, 0.3780], [4.0321, 0.0800], [3.9976, 0.2021], [3.8703, 0.1938]])
+    assert torch.allclose(out, expect, atol=1e-3)
+    assert out.argmax(1).tolist() == [0, 0, 0, 0]
+
+
+def test_procedural_weights_match_golden_checksums(golden):
+    sd = make_oracle(seed=7).state_dict()
+    assert len(sd) == 229
+    cs = state_checksums(sd)
+    for k, (s, a) in golden["checksums"].items():
+        assert abs(cs[k][0] - s) <= 1e-6 * max(1.0, abs(a)), k
+        assert abs(cs[k][1] - a) <= 1e-6 * max(1.0, abs(a)), k
+
+
+def test_oracle_matches_golden_small(golden):
+    case = golden["cases"]["small"]
+    B, H, W, L = case["shape"]
+    m = make_oracle(seed=7)
+    inputs = make_inputs(case["input_seed"], B, H, W, L)
+    m.eval()
+    with torch.no_grad():
+        out = m(*inputs[:3])
+    for a, b in zip(out, case["eval"]["outputs"]):
+        assert torch.allclose(a, b, atol=1e-5, rtol=1e-5)
+    set_dropout(m, 0.0)
+    m.train()
+    out = m(*inputs[:3])
+    loss = om.fusion_loss(out, inputs[3])
+    loss.backward()
+    tp = case["train_p0"]
+    assert abs(float(loss) - float(tp["loss"])) < 1e-5
+    for k, g in tp["grads"].items():
+        got = dict(m.named_parameters())[k].grad
+        assert torch.allclose(got, g, atol=1e-6 + 1e-4 * float(g.abs().max())), k
+    for k, v in tp["bn_after"].items():
+        assert torch.allclose(m.state_dict()[k].float(), v.float(), atol=1e-5), k
+
+
+def test_focal_loss_and_zscore_definitions():
+    z = torch.tensor([[2.0, -1.0], [0.3, 0.1]])
+    y = torch.tensor([0, 1])
+    ce = torch.nn.functional.cross_entropy(z, y, reduction="none")
+    want = ((1 - torch.exp(-ce)) ** 2 * ce).mean()
+    assert torch.allclose(om.FocalLoss()(z, y), want)
+    x = torch.tensor([[1.0, 2.0, 3.0, 6.0]])
+    zs = om.z_score(x)
+    assert abs(float(zs.mean())) < 1e-6 and abs(float(zs.var(unbiased=False)) - 1) < 1e-5
+
+
+def test_signal12_golden(golden):
+    s12 = golden["signal12"]
+    torch.manual_seed(s12["init_seed"])
+    net = om.ResNet1D_SE(12, 2)
+    x = torch.randn(4, 12, 5000, generator=torch.Generator().manual_seed(s12["input_seed"]))
+    net.train()
+    set_dropout(net, 0.0)
+    lo = net(x)
+    assert torch.allclose(lo, s12["logits"], atol=1e-5)
+    assert abs(float(om.FocalLoss()(lo, s12["labels"])) - float(s12["focal_loss"])) < 1e-6

@@ -1,0 +1,102 @@
+"""CPU, world_size 2, gloo: the bucketed gradient all-reduce logic of ecgmm.parallel.DataParallel
+(bucket boundaries, averaging, completion before optimizer.step) on stand-in stages."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+class _FakeArena:
+    def __init__(self, n, fill):
+        self.flat = torch.full((n,), float(fill))
+        self.total = n
+
+
+class _FakeStage:
+    pass
+
+
+class _FakeModel(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.zeros(3))
+        self._stages = [_FakeStage(), _FakeStage()]
+
+    def stages(self):
+        return self._stages
+
+    def forward(self, x):
+        return x
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ecgmm.parallel import DataParallel
+
+        m = _FakeModel()
+        with torch.no_grad():
+            m.w.fill_(float(rank + 1))
+        dp = DataParallel(m, min_bucket_elems=4)
+        assert torch.equal(m.w.detach(), torch.ones(3)), "parameters must be broadcast from rank 0"
+        dp(torch.zeros(1))
+        a = _FakeArena(20, fill=rank + 1)     # rank0: 1, rank1: 2 -> mean 1.5
+        b = _FakeArena(6, fill=10 * (rank + 1))
+        cb = m.stages()[0]._grad_ready_cb
+        cb(a, 2)      # below min bucket: deferred
+        assert dp.buckets_last_step == 0
+        cb(a, 8)      # [0, 8)
+        cb(a, 8)      # nothing new
+        cb(a, 20)     # [8, 20), final
+        m.stages()[1]._grad_ready_cb(b, 6)
+        assert dp.buckets_last_step == 3 and dp.bytes_last_step == 4 * 26
+        dp.finish()
+        ok = bool(torch.allclose(a.flat, torch.full((20,), 1.5)) and torch.allclose(b.flat, torch.full((6,), 15.0)))
+
+        # the same through a real backward pass: the collectives must be complete when backward() returns
+        c = _FakeArena(12, fill=4 * (rank + 1))  # mean 6
+
+        class Fn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x):
+                return x * 2
+
+            @staticmethod
+            def backward(ctx, g):
+                cb(c, 5)
+                cb(c, 12)
+                return g * 2
+
+        dp(torch.zeros(1))
+        x = torch.ones(2, requires_grad=True)
+        Fn.apply(x).sum().backward()
+        ok = ok and bool(torch.allclose(c.flat, torch.full((12,), 6.0))) and not dp._pending
+        q.put((rank, ok, dp.buckets_last_step))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] for r in res)
