@@ -81,35 +81,50 @@ __global__ void __launch_bounds__(kRedThreads) chan_stats_kernel(const __nv_bflo
 // apply kernel uses, optional per-sample sums (SE squeeze) and the running-statistics update.
 //   conv_bias: the convolution in front has a bias that the conv kernel does NOT add; in
 //   training mode it only shifts the batch mean (and so running_mean), never the output.
-__global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int rows_total,
-                                   int split, int C, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps,
-                                   float momentum, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, long long* __restrict__ num_batches,
-                                   float* __restrict__ mean_out, float* __restrict__ invstd_out,
-                                   float* __restrict__ scale_out, float* __restrict__ shift_out,
-                                   float* __restrict__ nsum_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && num_batches) *num_batches += 1;
-  if (c >= C) return;
+// One CTA = 32 channels x 32 row lanes; lanes stride over the N*SPLIT partial rows (or over the
+// samples when per-sample sums are wanted), fp64 accumulation, shared-memory fold.
+constexpr int kFinLanes = 32;
+
+__global__ void __launch_bounds__(32 * kFinLanes) bn_finalize_kernel(
+    const float* __restrict__ psum, const float* __restrict__ psq, int rows_total, int split, int C, double count,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps,
+    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+    long long* __restrict__ num_batches, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+    float* __restrict__ scale_out, float* __restrict__ shift_out, float* __restrict__ nsum_out) {
+  __shared__ double sh_s[kFinLanes][33], sh_q[kFinLanes][33];
+  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches) *num_batches += 1;
   double s = 0.0, q = 0.0;
-  if (nsum_out) {
-    const int N = rows_total / split;
-    for (int n = 0; n < N; ++n) {
-      float ns = 0.f;
-      for (int k = 0; k < split; ++k) {
-        const size_t i = ((size_t)n * split + k) * C + c;
-        ns += psum[i];
-        q += psq[i];
+  if (c < C) {
+    if (nsum_out) {
+      const int N = rows_total / split;
+      for (int n = lane; n < N; n += kFinLanes) {
+        float ns = 0.f;
+        for (int k = 0; k < split; ++k) {
+          const size_t i = ((size_t)n * split + k) * C + c;
+          ns += psum[i];
+          q += psq[i];
+        }
+        nsum_out[(size_t)n * C + c] = ns;
+        s += ns;
       }
-      nsum_out[(size_t)n * C + c] = ns;
-      s += ns;
+    } else {
+      for (int i = lane; i < rows_total; i += kFinLanes) {
+        s += psum[(size_t)i * C + c];
+        q += psq[(size_t)i * C + c];
+      }
     }
-  } else {
-    for (int i = 0; i < rows_total; ++i) {
-      s += psum[(size_t)i * C + c];
-      q += psq[(size_t)i * C + c];
-    }
+  }
+  sh_s[lane][cl] = s;
+  sh_q[lane][cl] = q;
+  __syncthreads();
+  if (lane != 0 || c >= C) return;
+  s = 0.0;
+  q = 0.0;
+  for (int i = 0; i < kFinLanes; ++i) {
+    s += sh_s[i][cl];
+    q += sh_q[i][cl];
   }
   const double mean = s / count;
   double var = q / count - mean * mean;
@@ -298,7 +313,39 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   const size_t sbase = (size_t)n * P * CG + cg;
-  for (int p = pa + r; p < pb; p += rows) {
+  int p = pa + r;
+  if (MODE != 2) {
+    constexpr int U = 4;  // independent 16-byte loads in flight per operand
+    for (; p + (U - 1) * rows < pb; p += U * rows) {
+      uint4 vx[U], vd[U], vy[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t i = sbase + (size_t)(p + u * rows) * CG;
+        vx[u] = ld_stream(reinterpret_cast<const uint4*>(x) + i);
+        vd[u] = ld_stream(reinterpret_cast<const uint4*>(dy) + i);
+        if (MODE == 1) vy[u] = ld_stream(reinterpret_cast<const uint4*>(y) + i);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float xv[8], dz[8];
+        unpack8(vx[u], xv);
+        unpack8(vd[u], dz);
+        if (MODE == 1) {
+          float yv[8];
+          unpack8(vy[u], yv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (yv[j] <= 0.f) dz[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += dz[j];
+          q[j] = fmaf(dz[j], (xv[j] - mu[j]) * is[j], q[j]);
+        }
+      }
+    }
+  }
+  for (; p < pb; p += rows) {
     const size_t i = sbase + (size_t)p * CG;
     float xv[8], dz[8];
     unpack8(ld_stream(reinterpret_cast<const uint4*>(x) + i), xv);
@@ -344,32 +391,50 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
 // otherwise) the BatchNorm backward is   dx = A*se*dz + B*x + D + A*q   with per-channel
 //   A = gamma*invstd,  B = -gamma*invstd^2*m2,  D = -A*m1 + gamma*invstd^2*mean*m2,
 //   m1 = mean(du), m2 = mean(du*xhat);  dgamma = sum(du*xhat), dbeta = sum(du).
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int N, int split,
-                                       int C, double per_sample, const float* __restrict__ gamma,
-                                       const float* __restrict__ mean, const float* __restrict__ invstd,
-                                       const float* __restrict__ se, const float* __restrict__ q,
-                                       const float* __restrict__ nsum, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ coefA,
-                                       float* __restrict__ coefB, float* __restrict__ coefD) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double mu = mean[c], is = invstd[c];
+__global__ void __launch_bounds__(32 * kFinLanes) bn_bwd_finalize_kernel(
+    const float* __restrict__ p1, const float* __restrict__ p2, int N, int split, int C, double per_sample,
+    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
+    const float* __restrict__ se, const float* __restrict__ q, const float* __restrict__ nsum,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coefA, float* __restrict__ coefB,
+    float* __restrict__ coefD) {
+  __shared__ double sh_a[kFinLanes][33], sh_b[kFinLanes][33];
+  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
-  for (int n = 0; n < N; ++n) {
-    double a = 0.0, b = 0.0;
-    for (int k = 0; k < split; ++k) {
-      const size_t i = ((size_t)n * split + k) * C + c;
-      a += p1[i];
-      b += p2[i];
-    }
+  double mu = 0.0, is = 0.0;
+  if (c < C) {
+    mu = mean[c];
+    is = invstd[c];
     if (se) {
-      const double g = se[(size_t)n * C + c], qq = q[(size_t)n * C + c];
-      const double sum_xhat = ((double)nsum[(size_t)n * C + c] - per_sample * mu) * is;
-      a = g * a + per_sample * qq;
-      b = g * b + qq * sum_xhat;
+      for (int n = lane; n < N; n += kFinLanes) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < split; ++k) {
+          const size_t i = ((size_t)n * split + k) * C + c;
+          a += p1[i];
+          b += p2[i];
+        }
+        const double g = se[(size_t)n * C + c], qq = q[(size_t)n * C + c];
+        const double sum_xhat = ((double)nsum[(size_t)n * C + c] - per_sample * mu) * is;
+        s1 += g * a + per_sample * qq;
+        s2 += g * b + qq * sum_xhat;
+      }
+    } else {
+      const int rows_total = N * split;
+      for (int i = lane; i < rows_total; i += kFinLanes) {
+        s1 += p1[(size_t)i * C + c];
+        s2 += p2[(size_t)i * C + c];
+      }
     }
-    s1 += a;
-    s2 += b;
+  }
+  sh_a[lane][cl] = s1;
+  sh_b[lane][cl] = s2;
+  __syncthreads();
+  if (lane != 0 || c >= C) return;
+  s1 = 0.0;
+  s2 = 0.0;
+  for (int i = 0; i < kFinLanes; ++i) {
+    s1 += sh_a[i][cl];
+    s2 += sh_b[i][cl];
   }
   const double M = per_sample * N;
   const double m1 = s1 / M, m2 = s2 / M;
@@ -391,44 +456,209 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const float* __restrict__ se, const float* __restrict__ q, __nv_bfloat16* __restrict__ dx,
     __nv_bfloat16* __restrict__ dz_out, int CG, size_t vec_per_sample, size_t total_vec, int H, int W, int Ho,
     int Wo) {
+  constexpr int U = (MODE == 2) ? 1 : 2;  // vectors per thread per trip: U x (2..3) loads in flight
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += stride) {
+  for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < total_vec; i0 += U * stride) {
+    uint4 vx[U], vd[U], vy[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < total_vec) {
+        vx[u] = ld_stream(reinterpret_cast<const uint4*>(x) + i);
+        if (MODE != 2) vd[u] = ld_stream(reinterpret_cast<const uint4*>(dy) + i);
+        if (MODE == 1) vy[u] = ld_stream(reinterpret_cast<const uint4*>(y) + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i >= total_vec) break;
+      const int cg = (int)(i % CG);
+      const size_t n = i / vec_per_sample;
+      float xv[8], dz[8], A[8], B[8], D[8];
+      unpack8(vx[u], xv);
+      load8f(coefA + cg * 8, A);
+      load8f(coefB + cg * 8, B);
+      load8f(coefD + cg * 8, D);
+      if (MODE == 2) {
+        float sc[8], sh[8];
+        load8f(scale + cg * 8, sc);
+        load8f(shift + cg * 8, sh);
+        const size_t p = (i / CG) % ((size_t)H * W);
+        pool_gather_dz(dy, arg, n, (int)(p / W), (int)(p % W), Ho, Wo, CG, cg, xv, sc, sh, dz);
+      } else {
+        unpack8(vd[u], dz);
+        if (MODE == 1) {
+          float yv[8];
+          unpack8(vy[u], yv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (yv[j] <= 0.f) dz[j] = 0.f;
+        }
+      }
+      if (dz_out) reinterpret_cast<uint4*>(dz_out)[i] = pack8(dz);
+      float o[8];
+      if (SE) {
+        float g[8], qq[8];
+        load8f(se + (n * CG + cg) * 8, g);
+        load8f(q + (n * CG + cg) * 8, qq);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], fmaf(g[j], dz[j], qq[j]), fmaf(B[j], xv[j], D[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dz[j], fmaf(B[j], xv[j], D[j]));
+      }
+      reinterpret_cast<uint4*>(dx)[i] = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stem backward (max-pool 3x3/s2/p1 behind BN+ReLU), organised by 2x2 INPUT blocks: block (a, b)
+// = pixels (2a+i, 2b+j) is touched only by the pooling windows (a..a+1, b..b+1), so one thread
+// loads 4 x vectors + 4 argmax words + 4 pooled-gradient vectors (12 independent loads) and
+// produces the gradient of all 4 pixels.  Window position codes (dh*3+dw) are compile-time.
+// ------------------------------------------------------------------------------------------
+struct StemBlock {
+  float xv[4][8];  // x at (i,j) = [2*i + j]
+  float dz[4][8];  // gradient of the pre-activation after pool routing + ReLU gate
+  bool ok[4];
+};
+
+__device__ __forceinline__ void stem_block_load(const __nv_bfloat16* __restrict__ x,
+                                                const __nv_bfloat16* __restrict__ dyp,
+                                                const uint8_t* __restrict__ arg, size_t n, int a, int b, int H,
+                                                int W, int Ho, int Wo, int CG, int cg, const float (&sc)[8],
+                                                const float (&sh)[8], StemBlock& blk) {
+  uint4 vx[4], vg[4];
+  uint2 va[4];
+  bool wok[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int i = t >> 1, j = t & 1;
+    const int h = 2 * a + i, w = 2 * b + j;
+    blk.ok[t] = (h < H) && (w < W);
+    vx[t] = blk.ok[t] ? ld_stream(reinterpret_cast<const uint4*>(x) + ((n * H + h) * W + w) * CG + cg)
+                      : make_uint4(0, 0, 0, 0);
+    const int oh = a + i, ow = b + j;
+    wok[t] = (oh < Ho) && (ow < Wo);
+    const size_t o = ((n * Ho + (wok[t] ? oh : a)) * Wo + (wok[t] ? ow : b)) * CG + cg;
+    vg[t] = reinterpret_cast<const uint4*>(dyp)[o];
+    va[t] = reinterpret_cast<const uint2*>(arg)[o];
+  }
+  float g[4][8];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    unpack8(vx[t], blk.xv[t]);
+    unpack8(vg[t], g[t]);
+    if (!wok[t]) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) g[t][c] = 0.f;
+    }
+  }
+  // code of pixel (i,j) inside window (a+wi, b+wj): dh = i - 2*wi + 1, dw = j - 2*wj + 1
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    int code[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) code[t] = ((c < 4 ? va[t].x : va[t].y) >> (8 * (c & 3))) & 0xff;
+    // window 0 = (a,b), 1 = (a,b+1), 2 = (a+1,b), 3 = (a+1,b+1)
+    float d00 = (code[0] == 4) ? g[0][c] : 0.f;
+    float d01 = ((code[0] == 5) ? g[0][c] : 0.f) + ((code[1] == 3) ? g[1][c] : 0.f);
+    float d10 = ((code[0] == 7) ? g[0][c] : 0.f) + ((code[2] == 1) ? g[2][c] : 0.f);
+    float d11 = ((code[0] == 8) ? g[0][c] : 0.f) + ((code[1] == 6) ? g[1][c] : 0.f) +
+                ((code[2] == 2) ? g[2][c] : 0.f) + ((code[3] == 0) ? g[3][c] : 0.f);
+    blk.dz[0][c] = (fmaf(blk.xv[0][c], sc[c], sh[c]) > 0.f) ? d00 : 0.f;
+    blk.dz[1][c] = (fmaf(blk.xv[1][c], sc[c], sh[c]) > 0.f) ? d01 : 0.f;
+    blk.dz[2][c] = (fmaf(blk.xv[2][c], sc[c], sh[c]) > 0.f) ? d10 : 0.f;
+    blk.dz[3][c] = (fmaf(blk.xv[3][c], sc[c], sh[c]) > 0.f) ? d11 : 0.f;
+  }
+}
+
+// p1/p2 [N][SPLIT][C]; the slab unit is a 2x2 block (= one pooled position)
+__global__ void __launch_bounds__(kRedThreads) stem_bwd_reduce_kernel(
+    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dyp, const uint8_t* __restrict__ arg,
+    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ scale,
+    const float* __restrict__ shift, float* __restrict__ p1, float* __restrict__ p2, int C, int blocks_per_split,
+    int H, int W, int Ho, int Wo) {
+  extern __shared__ float sred[];
+  const int CG = C >> 3;
+  const int rows = kRedThreads / CG;
+  const int cg = threadIdx.x % CG, r = threadIdx.x / CG;
+  const int n = blockIdx.y, split = blockIdx.x;
+  const int nb = Ho * Wo;
+  const int pa = split * blocks_per_split;
+  const int pb = min(nb, pa + blocks_per_split);
+  float mu[8], is[8], sc[8], sh[8], s[8], q[8];
+  load8f(mean + cg * 8, mu);
+  load8f(invstd + cg * 8, is);
+  load8f(scale + cg * 8, sc);
+  load8f(shift + cg * 8, sh);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  for (int p = pa + r; p < pb; p += rows) {
+    StemBlock blk;
+    stem_block_load(x, dyp, arg, n, p / Wo, p % Wo, H, W, Ho, Wo, CG, cg, sc, sh, blk);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (!blk.ok[t]) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += blk.dz[t][j];
+        q[j] = fmaf(blk.dz[t][j], (blk.xv[t][j] - mu[j]) * is[j], q[j]);
+      }
+    }
+  }
+  float* ss = sred;
+  float* sq = sred + rows * C;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ss[r * C + cg * 8 + j] = s[j];
+    sq[r * C + cg * 8 + j] = q[j];
+  }
+  __syncthreads();
+  const size_t orow = ((size_t)n * gridDim.x + split) * C;
+  for (int c = threadIdx.x; c < C; c += kRedThreads) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < rows; ++i) {
+      a += ss[i * C + c];
+      b += sq[i * C + c];
+    }
+    p1[orow + c] = a;
+    p2[orow + c] = b;
+  }
+}
+
+__global__ void __launch_bounds__(256) stem_bwd_apply_kernel(
+    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dyp, const uint8_t* __restrict__ arg,
+    const float* __restrict__ coefA, const float* __restrict__ coefB, const float* __restrict__ coefD,
+    const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ dx, int CG,
+    size_t total_blocks_vec, int H, int W, int Ho, int Wo) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_blocks_vec; i += stride) {
     const int cg = (int)(i % CG);
-    const size_t n = i / vec_per_sample;
-    float xv[8], dz[8], A[8], B[8], D[8];
-    unpack8(ld_stream(reinterpret_cast<const uint4*>(x) + i), xv);
+    size_t t = i / CG;
+    const int b = (int)(t % Wo);
+    t /= Wo;
+    const int a = (int)(t % Ho);
+    const size_t n = t / Ho;
+    float A[8], B[8], D[8], sc[8], sh[8];
     load8f(coefA + cg * 8, A);
     load8f(coefB + cg * 8, B);
     load8f(coefD + cg * 8, D);
-    if (MODE == 2) {
-      float sc[8], sh[8];
-      load8f(scale + cg * 8, sc);
-      load8f(shift + cg * 8, sh);
-      const size_t p = (i / CG) % ((size_t)H * W);
-      pool_gather_dz(dy, arg, n, (int)(p / W), (int)(p % W), Ho, Wo, CG, cg, xv, sc, sh, dz);
-    } else {
-      unpack8(ld_stream(reinterpret_cast<const uint4*>(dy) + i), dz);
-      if (MODE == 1) {
-        float yv[8];
-        unpack8(ld_stream(reinterpret_cast<const uint4*>(y) + i), yv);
+    load8f(scale + cg * 8, sc);
+    load8f(shift + cg * 8, sh);
+    StemBlock blk;
+    stem_block_load(x, dyp, arg, n, a, b, H, W, Ho, Wo, CG, cg, sc, sh, blk);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (yv[j] <= 0.f) dz[j] = 0.f;
-      }
+    for (int k = 0; k < 4; ++k) {
+      if (!blk.ok[k]) continue;
+      const int h = 2 * a + (k >> 1), w = 2 * b + (k & 1);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], blk.dz[k][j], fmaf(B[j], blk.xv[k][j], D[j]));
+      reinterpret_cast<uint4*>(dx)[((n * H + h) * W + w) * CG + cg] = pack8(o);
     }
-    if (dz_out) reinterpret_cast<uint4*>(dz_out)[i] = pack8(dz);
-    float o[8];
-    if (SE) {
-      float g[8], qq[8];
-      load8f(se + (n * CG + cg) * 8, g);
-      load8f(q + (n * CG + cg) * 8, qq);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], fmaf(g[j], dz[j], qq[j]), fmaf(B[j], xv[j], D[j]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dz[j], fmaf(B[j], xv[j], D[j]));
-    }
-    reinterpret_cast<uint4*>(dx)[i] = pack8(o);
   }
 }
 
@@ -529,7 +759,7 @@ extern "C" int ecgmm_bn_finalize(const float* psum, const float* psq, int N, int
                                  void* stream) {
   ECGMM_CHECK(psum && psq && mean && invstd && scale && shift, ECGMM_ERR_ARG, "bn_finalize: null pointer");
   ECGMM_CHECK(count > 0, ECGMM_ERR_SHAPE, "bn_finalize: empty batch");
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+  bn_finalize_kernel<<<ceil_div(C, 32), 32 * kFinLanes, 0, (cudaStream_t)stream>>>(
       psum, psq, N * split, split, C, (double)count, gamma, beta, conv_bias, eps, momentum, running_mean,
       running_var, num_batches, mean, invstd, scale, shift, nsum);
   return check_launch("bn_finalize_kernel");
@@ -616,8 +846,8 @@ extern "C" int ecgmm_bn_bwd_reduce(const ecgmm_bf16* x, const ecgmm_bf16* dy, co
     bn_bwd_reduce_kernel<1><<<grid, kRedThreads, smem, st>>>(xb, dyb, yb, argmax, mean, invstd, scale, shift, p1, p2,
                                                              P, C, rps, H, W, Ho, Wo);
   else
-    bn_bwd_reduce_kernel<2><<<grid, kRedThreads, smem, st>>>(xb, dyb, yb, argmax, mean, invstd, scale, shift, p1, p2,
-                                                             P, C, rps, H, W, Ho, Wo);
+    stem_bwd_reduce_kernel<<<grid, kRedThreads, smem, st>>>(xb, dyb, argmax, mean, invstd, scale, shift, p1, p2, C,
+                                                            rows_per_split(Ho * Wo, split), H, W, Ho, Wo);
   return check_launch("bn_bwd_reduce_kernel");
 }
 
@@ -629,7 +859,7 @@ extern "C" int ecgmm_bn_bwd_finalize(const float* p1, const float* p2, int N, in
   ECGMM_CHECK(p1 && p2 && mean && invstd && coefA && coefB && coefD, ECGMM_ERR_ARG, "bn_bwd_finalize: null pointer");
   ECGMM_CHECK(!se || (q && nsum), ECGMM_ERR_ARG, "bn_bwd_finalize: SE mode needs q and nsum");
   ECGMM_CHECK(N > 0 && per_sample > 0, ECGMM_ERR_SHAPE, "bn_bwd_finalize: empty batch");
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+  bn_bwd_finalize_kernel<<<ceil_div(C, 32), 32 * kFinLanes, 0, (cudaStream_t)stream>>>(
       p1, p2, N, split, C, (double)per_sample, gamma, mean, invstd, se, q, nsum, dgamma, dbeta, coefA, coefB, coefD);
   return check_launch("bn_bwd_finalize_kernel");
 }
@@ -658,9 +888,12 @@ extern "C" int ecgmm_bn_bwd_apply(const ecgmm_bf16* x, const ecgmm_bf16* dy, con
 #define ECGMM_BWD(MODE_, SE_)                                                                                      \
   bn_bwd_apply_kernel<MODE_, SE_><<<g, 256, 0, st>>>(xb, dyb, yb, argmax, coefA, coefB, coefD, scale, shift, se, q, \
                                                      dxb, dzb, C >> 3, vps, total, H, W, Ho, Wo)
-  if (mode == 2)
-    ECGMM_BWD(2, false);
-  else if (mode == 1 && se)
+  if (mode == 2) {
+    ECGMM_CHECK(!dz_out, ECGMM_ERR_ARG, "bn_bwd_apply: mode 2 does not produce dz_out");
+    const size_t tb = (size_t)N * Ho * Wo * (C >> 3);
+    stem_bwd_apply_kernel<<<stream_grid(tb), 256, 0, st>>>(xb, dyb, argmax, coefA, coefB, coefD, scale, shift, dxb,
+                                                           C >> 3, tb, H, W, Ho, Wo);
+  } else if (mode == 1 && se)
     ECGMM_BWD(1, true);
   else if (mode == 1)
     ECGMM_BWD(1, false);
