@@ -15,6 +15,8 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace ecgmm {
 
 struct Tap {
@@ -94,7 +96,9 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_kernel(const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // One elected thread runs the whole loop: under a plain `lane == 0` guard ptxas wraps every
+    // uniform-datapath instruction (UTMALDG / UTCHMMA) in an ELECT..BRA.U.ANY serialisation loop.
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -105,50 +109,50 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_kernel(const __grid_constant_
         const int thi = m % p.tiles_h;
         const int img = m / p.tiles_h;
         const int h0 = thi * p.TH, w0 = twi * p.TW;
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int tap = kb / p.k_chunks;
-          const int kc = kb - tap * p.k_chunks;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
           const Tap tp = p.taps[tap];
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], L::kStage);
-          tma_load_4d(sA + stage * kATile, &p.a_maps[tp.map], &full[stage], kc * 64, w0 + tp.dw, h0 + tp.dh, img);
-          tma_load_2d(sB + stage * L::kBTile, &p.b_map, &full[stage], tp.wk + kc * 64, nt * BN);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], L::kStage);
+            tma_load_4d(sA + stage * kATile, &p.a_maps[tp.map], &full[stage], kc * 64, w0 + tp.dw, h0 + tp.dh, img);
+            tma_load_2d(sB + stage * L::kBTile, &p.b_map, &full[stage], tp.wk + kc * 64, nt * BN);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full[stage], phase);
+    // ------------------------------------------------------------ MMA issuer (single elected thread)
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA), 0, 1024);
+      const uint64_t b_desc0 = make_sw128_desc(smem_u32(sB), 0, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t a_desc = make_sw128_desc(sA_addr + stage * kATile, 0, 1024);
-          const uint64_t b_desc = make_sw128_desc(sB_addr + stage * L::kBTile, 0, 1024);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (kATile >> 4));
+          const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (L::kBTile >> 4));
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 4 x (K = 16) per 64-wide chunk; +32 B inside the swizzle atom
             umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           umma_commit(&empty[stage]);
           if (kb == nkb - 1) umma_commit(&tfull[acc]);
-        }
-        __syncwarp();
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -499,7 +503,7 @@ __global__ void __launch_bounds__(192, 1) igemm_tn_kernel(const __grid_constant_
 
   if (has_work) {
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -531,30 +535,33 @@ __global__ void __launch_bounds__(192, 1) igemm_tn_kernel(const __grid_constant_
         }
       }
     } else if (warp == 1) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
-      const uint32_t s_addr = smem_u32(smem);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t st = s_addr + stage * L::kStage;
-          // MN-major operands: 64-wide atoms kBox bytes apart (LBO), 8 K-rows = 1024 B (SBO)
-          const uint64_t b_desc = make_sw128_desc(st, kBox, 1024);
-          for (int i = 0; i < ns; ++i) {
-            const uint64_t a_desc = make_sw128_desc(st + (L::kNB + 2 * i) * kBox, kBox, 1024);
+      if (elect_one()) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+        const uint32_t s_addr = smem_u32(smem);
+        // MN-major operands: 64-wide atoms kBox bytes apart (LBO), 8 K-rows = 1024 B (SBO)
+        const uint64_t b_desc0 = make_sw128_desc(s_addr, kBox, 1024);
+        const uint64_t a_desc0 = make_sw128_desc(s_addr + L::kNB * kBox, kBox, 1024);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t so = (uint64_t)(stage * (L::kStage >> 4));
 #pragma unroll
-            for (int k = 0; k < kKPix / 16; ++k)  // 16 K-rows = 2048 B further into the box
-              umma_bf16(tmem_base + i * BN, a_desc + k * 128, b_desc + k * 128, idesc, (kb > kb0) || (k > 0));
+          for (int i = 0; i < SMAX; ++i) {
+            if (i < ns) {
+#pragma unroll
+              for (int k = 0; k < kKPix / 16; ++k)  // 16 K-rows = 2048 B further into the box
+                umma_bf16(tmem_base + i * BN, a_desc0 + so + (uint64_t)(i * (2 * kBox >> 4) + k * 128),
+                          b_desc0 + so + (uint64_t)(k * 128), idesc, (kb > kb0) || (k > 0));
+            }
           }
           umma_commit(&empty[stage]);
           if (kb == kb1 - 1) umma_commit(tfull);
-        }
-        __syncwarp();
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     } else {
@@ -636,12 +643,21 @@ static int launch_tn(TnParams& p, cudaStream_t s) {
 
 }  // namespace ecgmm
 
+namespace ecgmm {
+bool wgrad_halo_supported(int Cin, int Cout, int R, int S, int stride);
+int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W, int Cin,
+                      int Cout, int R, int S, int padH, int padW, cudaStream_t st);
+}  // namespace ecgmm
+
 extern "C" int ecgmm_conv2d_wgrad(const ecgmm_bf16* x_, const ecgmm_bf16* dy_, float* dw, int N, int H, int W,
                                   int Cin, int Cout, int R, int S, int stride, int padH, int padW, void* stream) {
   ECGMM_CHECK(x_ && dy_ && dw, ECGMM_ERR_ARG, "conv2d_wgrad: null pointer");
   int rc = check_conv_cfg(Cin, Cout, R, S, stride, padH, padW);
   if (rc) return rc;
   if (N == 0) return ECGMM_OK;
+  if (wgrad_halo_supported(Cin, Cout, R, S, stride) && !getenv("ECGMM_WGRAD_LEGACY"))
+    return launch_wgrad_halo(reinterpret_cast<const __nv_bfloat16*>(x_), reinterpret_cast<const __nv_bfloat16*>(dy_),
+                             dw, N, H, W, Cin, Cout, R, S, padH, padW, static_cast<cudaStream_t>(stream));
   const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
   TnParams p;
   memset(&p, 0, sizeof(p));

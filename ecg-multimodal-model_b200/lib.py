@@ -23,6 +23,7 @@ SIGNATURES = {
     "ecgmm_last_error": [],
     "ecgmm_check_device": [],
     "ecgmm_launch_count": [],
+    "ecgmm_debug_desc_probe": [_p, _p, _p, _i, _i, _p],
     "ecgmm_nchw_f32_to_nhwc_bf16": [_p, _p, _i, _i, _i, _i, _p],
     "ecgmm_nhwc_bf16_to_nchw_f32": [_p, _p, _i, _i, _i, _i, _p],
     "ecgmm_conv_weight_prep": [_p, _p, _p, _i, _i, _i, _i, _p],

@@ -40,6 +40,10 @@ unsigned long long ecgmm_launch_count(void);
 /* 0 when the current device can run the library (compute capability 10.x). */
 int ecgmm_check_device(void);
 
+/* Development probe (tools/desc_probe.py): one tcgen05.mma whose SWIZZLE_128B A descriptor starts
+ * `shift` 128-byte rows into a TMA-written tile.  mode bit0: MN-major operands; bit1: set base-offset. */
+int ecgmm_debug_desc_probe(const ecgmm_bf16* a, const ecgmm_bf16* b, float* out, int shift, int mode, void* stream);
+
 /* ------------------------------------------------------------------ layout / precision */
 
 /* NCHW fp32 -> NHWC bf16 (and back).  Replaces the implicit layout of every torch tensor the

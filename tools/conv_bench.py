@@ -49,6 +49,8 @@ def time_fn(fn, iters, flush):
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    only_layer = sys.argv[3] if len(sys.argv) > 3 else None   # substring filter on the layer name
+    only_op = sys.argv[4] if len(sys.argv) > 4 else None      # fwd | dgrad | wgrad
     ecgmm.lib.require_device()
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0}
@@ -68,12 +70,16 @@ def main():
     fl = 2.0 * B * Ho * Wo * 64 * 147
     for op, fn in (("fwd", lambda: ops.stem_conv_fwd(xs, wst, H, W)),
                    ("wgrad", lambda: ops.stem_conv_wgrad(xs, dy, dw, H, W))):
+        if (only_layer and only_layer not in "stem") or (only_op and only_op != op):
+            continue
         ms = time_fn(fn, iters, flush)
         print(f"{'stem 7x7':16s} {op:6s} {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s (algorithmic)  x1")
         tot_ms += ms
         tot_flop += fl
     del x, xs, dy
     for name, H, W, Cin, Cout, R, S, stride, mult in LAYERS:
+        if only_layer and only_layer not in name:
+            continue
         x = torch.randn(B, H, W, Cin, device="cuda").to(torch.bfloat16)
         w = (torch.randn(Cout, Cin, R, S, generator=g) / (Cin * R * S) ** 0.5).cuda()
         w_fwd, w_dg = ops.conv_weight_prep(w)
@@ -88,6 +94,8 @@ def main():
             "wgrad": lambda: ops.conv2d_wgrad(x, dy, dw, R, S, stride),
         }
         for op, fn in fns.items():
+            if only_op and only_op != op:
+                continue
             ms = time_fn(fn, iters, flush)
             tf = fl / ms / 1e9
             print(f"{name:16s} {op:6s} {ms:8.3f} ms  {tf:8.1f} TFLOP/s  {100 * tf / peak:5.1f}% of measured peak  x{mult}",
@@ -95,6 +103,8 @@ def main():
             tot_ms += ms * mult
             tot_flop += fl * mult
         del x, dy, dx
+    if tot_ms == 0:
+        return
     print(f"TOTAL conv time per step (B={B}): {tot_ms:.2f} ms, {tot_flop / tot_ms / 1e9:.1f} TFLOP/s "
           f"-> conv-only ceiling {B / tot_ms * 1e3:.0f} samples/s")
 
