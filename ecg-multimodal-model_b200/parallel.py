@@ -26,8 +26,8 @@ class DataParallel(torch.nn.Module):
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.min_bucket = int(min_bucket_elems)
         self._pending = []
-        self._sent = {}
         self._cb_queued = False
+        self._enabled = True
         self.buckets_last_step = 0
         self.bytes_last_step = 0
         if broadcast and self.world > 1:
@@ -39,7 +39,6 @@ class DataParallel(torch.nn.Module):
 
     def forward(self, *a, **k):
         self._pending.clear()
-        self._sent.clear()
         self._cb_queued = False
         self.buckets_last_step = 0
         self.bytes_last_step = 0
@@ -47,13 +46,13 @@ class DataParallel(torch.nn.Module):
 
     # ---- called by the stages during backward
     def _on_ready(self, arena, upto):
-        if self.world <= 1:
+        if self.world <= 1 or not self._enabled:
             return
-        start = self._sent.get(id(arena), 0)
+        start = getattr(arena, "_dp_sent", 0)  # progress lives on the arena itself (arenas are per-backward objects)
         final = upto >= arena.total
         if upto - start <= 0 or (upto - start < self.min_bucket and not final):
             return
-        self._sent[id(arena)] = upto
+        arena._dp_sent = upto
         self._launch(arena.flat[start:upto], keep=arena)
         if not self._cb_queued:
             try:  # end-of-backward hook (the mechanism DDP uses); outside backward the caller runs finish()
@@ -71,6 +70,19 @@ class DataParallel(torch.nn.Module):
             self._pending.append((work, flat, keep, True))
         self.buckets_last_step += 1
         self.bytes_last_step += flat.numel() * flat.element_size()
+
+    def no_sync(self):
+        """Context manager: run forward/backward WITHOUT gradient communication (torch DDP's no_sync)."""
+        dp = self
+
+        class _NoSync:
+            def __enter__(self):
+                self.prev, dp._enabled = dp._enabled, False
+
+            def __exit__(self, *exc):
+                dp._enabled = self.prev
+
+        return _NoSync()
 
     def finish(self):
         """Block the current stream until every outstanding gradient all-reduce has completed."""

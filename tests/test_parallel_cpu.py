@@ -82,6 +82,11 @@ def _worker(rank, world, port, q):
         x = torch.ones(2, requires_grad=True)
         Fn.apply(x).sum().backward()
         ok = ok and bool(torch.allclose(c.flat, torch.full((12,), 6.0))) and not dp._pending
+        # no_sync(): gradients stay local
+        d = _FakeArena(4, fill=rank + 1)
+        with dp.no_sync():
+            cb(d, 4)
+        ok = ok and bool(torch.allclose(d.flat, torch.full((4,), float(rank + 1))))
         q.put((rank, ok, dp.buckets_last_step))
     finally:
         dist.destroy_process_group()
