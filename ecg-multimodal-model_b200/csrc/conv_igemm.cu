@@ -322,12 +322,21 @@ static int build_fwd_taps(Tap* taps, bool* used, int R, int S, int stride, int p
 
 using namespace ecgmm;
 
+namespace ecgmm {
+bool nt_halo_supported(int Cin, int Cout, int R, int S, int stride, int W);
+int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int R, int S,
+                   int dgrad, int accumulate, cudaStream_t st);
+}  // namespace ecgmm
+
 extern "C" int ecgmm_conv2d_fwd(const ecgmm_bf16* x_, const ecgmm_bf16* w_, ecgmm_bf16* y_, int N, int H, int W,
                                 int Cin, int Cout, int R, int S, int stride, int padH, int padW, void* stream) {
   ECGMM_CHECK(x_ && w_ && y_, ECGMM_ERR_ARG, "conv2d_fwd: null pointer");
   int rc = check_conv_cfg(Cin, Cout, R, S, stride, padH, padW);
   if (rc) return rc;
   if (N == 0) return ECGMM_OK;
+  if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY"))
+    return launch_nt_halo(reinterpret_cast<const __nv_bfloat16*>(x_), reinterpret_cast<const __nv_bfloat16*>(w_),
+                          reinterpret_cast<__nv_bfloat16*>(y_), N, H, W, R, S, 0, 0, static_cast<cudaStream_t>(stream));
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(x_);
   const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
   NtParams p;
@@ -359,6 +368,10 @@ extern "C" int ecgmm_conv2d_dgrad(const ecgmm_bf16* dy_, const ecgmm_bf16* wt_, 
   int rc = check_conv_cfg(Cin, Cout, R, S, stride, padH, padW);
   if (rc) return rc;
   if (N == 0) return ECGMM_OK;
+  if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY"))
+    return launch_nt_halo(reinterpret_cast<const __nv_bfloat16*>(dy_), reinterpret_cast<const __nv_bfloat16*>(wt_),
+                          reinterpret_cast<__nv_bfloat16*>(dx_), N, H, W, R, S, 1, accumulate,
+                          static_cast<cudaStream_t>(stream));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(dy_);
   __nv_bfloat16* dx = reinterpret_cast<__nv_bfloat16*>(dx_);
@@ -700,10 +713,18 @@ static int stem_input_map(CUtensorMap* m, const ecgmm_bf16* xs, int N, int H, in
   return make_tmap_4d(m, xs, 64, Wo, Hs, N, 32, (uint64_t)Ws * 32, (uint64_t)Hs * Ws * 32, 64, box_w, box_h);
 }
 
+namespace ecgmm {
+int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, int N, int H, int W, cudaStream_t st);
+int launch_stem_wgrad_ring(const void* xs, const void* dy, float* dw, int N, int H, int W, cudaStream_t st);
+}  // namespace ecgmm
+
 extern "C" int ecgmm_stem_conv_fwd(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, int N, int H,
                                    int W, void* stream) {
   ECGMM_CHECK(xs && w_s2d && y, ECGMM_ERR_ARG, "stem_conv_fwd: null pointer");
   if (N == 0) return ECGMM_OK;
+  if (!getenv("ECGMM_STEM_LEGACY"))
+    return launch_stem_fwd_ring(xs, w_s2d, reinterpret_cast<__nv_bfloat16*>(y), N, H, W,
+                                static_cast<cudaStream_t>(stream));
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   NtParams p;
   memset(&p, 0, sizeof(p));
@@ -727,6 +748,8 @@ extern "C" int ecgmm_stem_conv_wgrad(const ecgmm_bf16* xs, const ecgmm_bf16* dy,
                                      void* stream) {
   ECGMM_CHECK(xs && dy && dw, ECGMM_ERR_ARG, "stem_conv_wgrad: null pointer");
   if (N == 0) return ECGMM_OK;
+  if (!getenv("ECGMM_STEM_LEGACY"))
+    return launch_stem_wgrad_ring(xs, dy, dw, N, H, W, static_cast<cudaStream_t>(stream));
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   TnParams p;
   memset(&p, 0, sizeof(p));

@@ -1,0 +1,248 @@
+// Forward / data-gradient of the 64->64 channel 3x3 (and 1x3) stride-1 convolutions with
+// shared-memory halo reuse and CTA-resident weights (ResNet18 layer1: 4 convs x {fwd, dgrad};
+// the 1-D layer1 block).
+//
+// igemm_nt_kernel stages one 16 KB activation box per filter tap: with N = 64 output channels a
+// 128x64 tile moves 9 x (16 + 8) KB for 9.4 MFLOP, 44 flop/B, and the kernel sits on the
+// L2->SM bandwidth cap (measured 38 B/clk/SM of ~42).  Here
+//   * the 9 weight tiles [64 cout][64 cin] (72 KB) are loaded ONCE per persistent CTA;
+//   * an M tile is 128 consecutive output pixels of one image row; the 3 input rows it needs are
+//     staged once each as a box of 130 pixels and filter tap (r,s) is row r's box read from
+//     pixel s onwards (descriptor start += s*128 B; legal because the 128-byte swizzle is a
+//     function of the absolute shared-memory address, see tools/desc_probe.py);
+// so a tile moves 50 KB for the same 9.4 MFLOP.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ecgmm {
+
+constexpr int kNhTile = 128;                               // output pixels per tile
+constexpr int kNhBoxW = kNhTile + 2;                       // staged pixels per input row
+constexpr int kNhBoxBytes = kNhBoxW * 128;                 // 16640
+constexpr int kNhBoxStride = (kNhBoxBytes + 1023) & ~1023;  // 17408
+constexpr int kNhStages = 2;
+constexpr int kNhWTile = 64 * 128;                         // one tap of weights: [64 n][64 k] bf16
+constexpr int kNhMaxTaps = 9;
+
+struct alignas(64) NtHaloParams {
+  CUtensorMap x_map;  // [N][H][W][64], box (64, 130, 1, 1)
+  CUtensorMap w_map;  // [64][ntaps*64] (k contiguous), box (64, 64)
+  int ntaps, rows;    // rows = halo rows staged per tile (3 for 3x3, 1 for 1x3)
+  int8_t tap_row[kNhMaxTaps], tap_shift[kNhMaxTaps];
+  int padW, row0;     // input row of halo row 0 relative to the output row (-(R/2))
+  int tiles_w, H, W, n_img, total_tiles;
+  __nv_bfloat16* out;  // [N][H][W][64]
+  int accumulate;
+};
+
+struct NtHaloSmem {
+  static constexpr int kW = kNhMaxTaps * kNhWTile;                 // 73728
+  static constexpr int kStage = 3 * kNhBoxStride;                  // 52224
+  static constexpr int kBarOff = kW + kNhStages * kStage;          // 178176
+  static constexpr int kBytes = kBarOff + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_constant__ NtHaloParams p) {
+  using L = NtHaloSmem;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + L::kW;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty = full + kNhStages;
+  uint64_t* tfull = empty + kNhStages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* wfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.x_map);
+    tma_prefetch_desc(&p.w_map);
+    for (int i = 0; i < kNhStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    mbar_init(wfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // weights: once per CTA
+      mbar_expect_tx(wfull, p.ntaps * kNhWTile);
+      for (int t = 0; t < p.ntaps; ++t) tma_load_2d(sW + t * kNhWTile, &p.w_map, wfull, t * 64, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = p.rows * kNhBoxBytes;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int twi = t % p.tiles_w;
+        const int m = t / p.tiles_w;
+        const int oh = m % p.H;
+        const int img = m / p.H;
+        const int w0 = twi * kNhTile;
+        uint8_t* st = sA + stage * L::kStage;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], tx);
+        for (int r = 0; r < p.rows; ++r)
+          tma_load_4d(st + r * kNhBoxStride, &p.x_map, &full[stage], 0, w0 - p.padW, oh + p.row0 + r, img);
+        if (++stage == kNhStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+      const uint64_t w_desc0 = make_sw128_desc(smem_u32(sW), 0, 1024);
+      const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA), 0, 1024);
+      // tap -> descriptor offset (in 16-byte units) inside a stage
+      uint32_t a_off[kNhMaxTaps];
+#pragma unroll
+      for (int t = 0; t < kNhMaxTaps; ++t)
+        a_off[t] = (t < p.ntaps) ? ((p.tap_row[t] * kNhBoxStride + p.tap_shift[t] * 128) >> 4) : 0;
+      mbar_wait(wfull, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 64;
+        const uint64_t a_st = a_desc0 + (uint64_t)(stage * (L::kStage >> 4));
+#pragma unroll
+        for (int tap = 0; tap < kNhMaxTaps; ++tap) {
+          if (tap < p.ntaps) {
+            const uint64_t a_desc = a_st + a_off[tap];
+            const uint64_t w_desc = w_desc0 + (uint64_t)(tap * (kNhWTile >> 4));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_desc + 2 * k, w_desc + 2 * k, idesc, (tap | k) != 0);
+          }
+        }
+        umma_commit(&empty[stage]);
+        umma_commit(&tfull[acc]);
+        if (++stage == kNhStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int m_row = quad * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int twi = t % p.tiles_w;
+      const int m = t / p.tiles_w;  // img * H + oh
+      const int ow = twi * kNhTile + m_row;
+      const bool valid = ow < p.W;
+      __nv_bfloat16* dst = p.out + ((size_t)m * p.W + ow) * 64;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c * 32, r);
+        tmem_ld_wait();
+        if (valid) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[q * 8 + j]);
+            if (p.accumulate) {
+              const uint4 old = d4[q];
+              const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 o = __bfloat1622float2(ob[j]);
+                f[2 * j] += o.x;
+                f[2 * j + 1] += o.y;
+              }
+            }
+            uint4 v;
+            __nv_bfloat162* vb = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) vb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            d4[q] = v;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+bool nt_halo_supported(int Cin, int Cout, int R, int S, int stride, int W) {
+  return stride == 1 && Cin == 64 && Cout == 64 && S == 3 && (R == 1 || R == 3) && W >= 96;
+}
+
+// dgrad != 0: w is the [Cin][R][S][Cout] shadow and taps are mirrored (dx[h,w] += dy[h+pad-r, w+pad-s] W[r,s]).
+int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int R, int S,
+                   int dgrad, int accumulate, cudaStream_t st) {
+  NtHaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.ntaps = R * S;
+  p.rows = R;
+  p.padW = S / 2;
+  p.row0 = -(R / 2);
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      const int t = r * S + s;
+      p.tap_row[t] = (int8_t)(dgrad ? (R - 1 - r) : r);
+      p.tap_shift[t] = (int8_t)(dgrad ? (S - 1 - s) : s);
+    }
+  p.tiles_w = ceil_div(W, kNhTile);
+  p.H = H;
+  p.W = W;
+  p.n_img = N;
+  p.total_tiles = N * H * p.tiles_w;
+  p.out = y;
+  p.accumulate = accumulate;
+  const uint64_t e = 2;
+  int rc = make_tmap_4d(&p.x_map, x, 64, W, H, N, 64 * e, (uint64_t)W * 64 * e, (uint64_t)H * W * 64 * e, 64, kNhBoxW, 1);
+  if (rc) return rc;
+  rc = make_tmap_2d(&p.w_map, w, (uint64_t)R * S * 64, 64, (uint64_t)R * S * 64 * e, 64, 64);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    NtHaloSmem::kBytes));
+    configured = true;
+  }
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  igemm_nt_halo_kernel<<<grid, 192, NtHaloSmem::kBytes, st>>>(p);
+  return check_launch("igemm_nt_halo_kernel");
+}
+
+}  // namespace ecgmm

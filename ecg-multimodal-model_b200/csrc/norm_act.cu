@@ -10,6 +10,8 @@
 #include "common.h"
 #include "vec.cuh"
 
+#include <unordered_map>
+
 namespace ecgmm {
 
 constexpr int kRedThreads = 256;
@@ -165,8 +167,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
                                                         const float* __restrict__ shift,
                                                         const float* __restrict__ se,
                                                         const __nv_bfloat16* __restrict__ res,
-                                                        __nv_bfloat16* __restrict__ y, int CG, size_t vec_per_sample,
-                                                        size_t total_vec) {
+                                                        __nv_bfloat16* __restrict__ y,
+                                                        uint8_t* __restrict__ mask_out, int CG,
+                                                        size_t vec_per_sample, size_t total_vec) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += stride) {
     const int cg = (int)(i % CG);
@@ -190,6 +193,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
       for (int j = 0; j < 8; ++j) f[j] += r[j];
     }
     if (RELU) {
+      if (mask_out) {  // 1 bit per element: what the backward pass needs instead of re-reading y
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m |= (f[j] > 0.f ? 1u : 0u) << j;
+        mask_out[i] = (uint8_t)m;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
     }
@@ -224,23 +233,33 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const __nv_bfloat1
       best[j] = -INFINITY;
       bi[j] = 0;
     }
+    // all 9 window loads are issued up front with clamped coordinates (independent loads in
+    // flight); out-of-image taps are masked afterwards
+    uint4 v[9];
+    bool ok[9];
 #pragma unroll
     for (int dh = 0; dh < 3; ++dh) {
       const int h = 2 * oh - 1 + dh;
-      if (h < 0 || h >= H) continue;
+      const int hc = min(max(h, 0), H - 1);
 #pragma unroll
       for (int dw = 0; dw < 3; ++dw) {
         const int w = 2 * ow - 1 + dw;
-        if (w < 0 || w >= W) continue;
-        float f[8];
-        unpack8(reinterpret_cast<const uint4*>(x)[((n * H + h) * W + w) * CG + cg], f);
+        const int wc = min(max(w, 0), W - 1);
+        ok[dh * 3 + dw] = (h == hc) && (w == wc);
+        v[dh * 3 + dw] = reinterpret_cast<const uint4*>(x)[((n * H + hc) * W + wc) * CG + cg];
+      }
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-          if (a > best[j]) {
-            best[j] = a;
-            bi[j] = dh * 3 + dw;
-          }
+    for (int t = 0; t < 9; ++t) {
+      if (!ok[t]) continue;
+      float f[8];
+      unpack8(v[t], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+        if (a > best[j]) {
+          best[j] = a;
+          bi[j] = t;
         }
       }
     }
@@ -318,12 +337,14 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
     constexpr int U = 4;  // independent 16-byte loads in flight per operand
     for (; p + (U - 1) * rows < pb; p += U * rows) {
       uint4 vx[U], vd[U], vy[U];
+      uint32_t vm[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const size_t i = sbase + (size_t)(p + u * rows) * CG;
         vx[u] = ld_stream(reinterpret_cast<const uint4*>(x) + i);
         vd[u] = ld_stream(reinterpret_cast<const uint4*>(dy) + i);
         if (MODE == 1) vy[u] = ld_stream(reinterpret_cast<const uint4*>(y) + i);
+        if (MODE == 3) vm[u] = arg[i];
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -336,6 +357,11 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (yv[j] <= 0.f) dz[j] = 0.f;
+        }
+        if (MODE == 3) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (!((vm[u] >> j) & 1u)) dz[j] = 0.f;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -359,6 +385,12 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (yv[j] <= 0.f) dz[j] = 0.f;
+      }
+      if (MODE == 3) {
+        const uint32_t m = arg[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (!((m >> j) & 1u)) dz[j] = 0.f;
       }
     }
 #pragma unroll
@@ -460,6 +492,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < total_vec; i0 += U * stride) {
     uint4 vx[U], vd[U], vy[U];
+    uint32_t vm[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const size_t i = i0 + u * stride;
@@ -467,6 +500,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
         vx[u] = ld_stream(reinterpret_cast<const uint4*>(x) + i);
         if (MODE != 2) vd[u] = ld_stream(reinterpret_cast<const uint4*>(dy) + i);
         if (MODE == 1) vy[u] = ld_stream(reinterpret_cast<const uint4*>(y) + i);
+        if (MODE == 3) vm[u] = arg[i];
       }
     }
 #pragma unroll
@@ -494,6 +528,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (yv[j] <= 0.f) dz[j] = 0.f;
+        }
+        if (MODE == 3) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (!((vm[u] >> j) & 1u)) dz[j] = 0.f;
         }
       }
       if (dz_out) reinterpret_cast<uint4*>(dz_out)[i] = pack8(dz);
@@ -707,9 +746,16 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
   }
 }
 
-static int stream_grid(size_t total_vec) {
-  size_t b = (total_vec + 255) / 256;
-  const size_t cap = (size_t)num_sms() * 8;
+// Grid for a grid-stride streaming kernel: exactly one wave of resident CTAs (num_sms x occupancy of
+// THAT kernel), so no partially filled last wave; fewer CTAs when the tensor is small.
+template <typename K>
+static int stream_grid(size_t total_vec, K kernel, int vec_per_thread = 1) {
+  static std::unordered_map<const void*, int> cache;  // one host thread per GPU process (header contract)
+  int& occ = cache[reinterpret_cast<const void*>(kernel)];
+  if (occ == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0) != cudaSuccess || occ < 1))
+    occ = 2;
+  const size_t cap = (size_t)num_sms() * occ;
+  size_t b = (total_vec + (size_t)256 * vec_per_thread - 1) / ((size_t)256 * vec_per_thread);
   return (int)(b < cap ? (b ? b : 1) : cap);
 }
 
@@ -728,8 +774,8 @@ typedef __nv_bfloat16 bf16;
 extern "C" int ecgmm_reduce_split(int N, int P, int C) {
   if (N <= 0 || P <= 0 || C < 8) return 1;
   const int rows = kRedThreads / (C >> 3) > 0 ? kRedThreads / (C >> 3) : 1;
-  const int want = ceil_div(num_sms() * 4, N);
-  int max_split = ceil_div(P, rows * 4);
+  const int want = ceil_div(num_sms() * 32, N);  // many small CTAs: the last partially filled wave stays small
+  int max_split = ceil_div(P, rows * 8);
   if (max_split < 1) max_split = 1;
   int s = want < 1 ? 1 : want;
   if (s > max_split) s = max_split;
@@ -775,8 +821,8 @@ extern "C" int ecgmm_bn_eval_coeffs(int C, const float* gamma, const float* beta
 }
 
 extern "C" int ecgmm_bn_apply(const ecgmm_bf16* x_, const float* scale, const float* shift, const float* se,
-                              const ecgmm_bf16* res_, ecgmm_bf16* y_, int N, int P, int C, int relu,
-                              void* stream) {
+                              const ecgmm_bf16* res_, ecgmm_bf16* y_, uint8_t* mask_out, int N, int P, int C,
+                              int relu, void* stream) {
   ECGMM_CHECK(x_ && scale && shift && y_, ECGMM_ERR_ARG, "bn_apply: null pointer");
   ECGMM_CHECK(C % 8 == 0, ECGMM_ERR_SHAPE, "bn_apply: C=%d not a multiple of 8", C);
   const size_t vps = (size_t)P * (C >> 3), total = vps * N;
@@ -784,11 +830,11 @@ extern "C" int ecgmm_bn_apply(const ecgmm_bf16* x_, const float* scale, const fl
   const bf16* x = reinterpret_cast<const bf16*>(x_);
   const bf16* res = reinterpret_cast<const bf16*>(res_);
   bf16* y = reinterpret_cast<bf16*>(y_);
-  const int g = stream_grid(total);
   cudaStream_t st = (cudaStream_t)stream;
   const int CG = C >> 3;
-#define ECGMM_APPLY(SE_, RES_, RELU_) \
-  bn_apply_kernel<SE_, RES_, RELU_><<<g, 256, 0, st>>>(x, scale, shift, se, res, y, CG, vps, total)
+#define ECGMM_APPLY(SE_, RES_, RELU_)                                                                 \
+  bn_apply_kernel<SE_, RES_, RELU_><<<stream_grid(total, bn_apply_kernel<SE_, RES_, RELU_>), 256, 0, st>>>( \
+      x, scale, shift, se, res, y, mask_out, CG, vps, total)
   const int key = (se ? 4 : 0) | (res ? 2 : 0) | (relu ? 1 : 0);
   switch (key) {
     case 0: ECGMM_APPLY(false, false, false); break;
@@ -811,7 +857,7 @@ extern "C" int ecgmm_bn_relu_maxpool(const ecgmm_bf16* x, const float* scale, co
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const size_t total = (size_t)N * Ho * Wo * (C >> 3);
   if (total == 0) return ECGMM_OK;
-  bn_relu_maxpool_kernel<<<stream_grid(total), 256, 0, (cudaStream_t)stream>>>(
+  bn_relu_maxpool_kernel<<<stream_grid(total, bn_relu_maxpool_kernel), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const bf16*>(x), scale, shift, reinterpret_cast<bf16*>(y), argmax, H, W, Ho, Wo, C >> 3,
       total);
   return check_launch("bn_relu_maxpool_kernel");
@@ -822,7 +868,8 @@ extern "C" int ecgmm_bn_bwd_reduce(const ecgmm_bf16* x, const ecgmm_bf16* dy, co
                                    const float* scale, const float* shift, float* p1, float* p2, int N, int H,
                                    int W, int C, int split, int mode, void* stream) {
   ECGMM_CHECK(x && dy && mean && invstd && p1 && p2, ECGMM_ERR_ARG, "bn_bwd_reduce: null pointer");
-  ECGMM_CHECK(mode >= 0 && mode <= 2, ECGMM_ERR_ARG, "bn_bwd_reduce: bad mode %d", mode);
+  ECGMM_CHECK(mode >= 0 && mode <= 3, ECGMM_ERR_ARG, "bn_bwd_reduce: bad mode %d", mode);
+  ECGMM_CHECK(mode != 3 || argmax, ECGMM_ERR_ARG, "bn_bwd_reduce: mode 3 needs the bit mask");
   ECGMM_CHECK(mode != 1 || y, ECGMM_ERR_ARG, "bn_bwd_reduce: mode 1 needs y");
   ECGMM_CHECK(mode != 2 || (argmax && scale && shift), ECGMM_ERR_ARG, "bn_bwd_reduce: mode 2 needs argmax/scale/shift");
   int rc = check_c(C, "bn_bwd_reduce");
@@ -844,6 +891,9 @@ extern "C" int ecgmm_bn_bwd_reduce(const ecgmm_bf16* x, const ecgmm_bf16* dy, co
                                                              P, C, rps, H, W, Ho, Wo);
   else if (mode == 1)
     bn_bwd_reduce_kernel<1><<<grid, kRedThreads, smem, st>>>(xb, dyb, yb, argmax, mean, invstd, scale, shift, p1, p2,
+                                                             P, C, rps, H, W, Ho, Wo);
+  else if (mode == 3)
+    bn_bwd_reduce_kernel<3><<<grid, kRedThreads, smem, st>>>(xb, dyb, yb, argmax, mean, invstd, scale, shift, p1, p2,
                                                              P, C, rps, H, W, Ho, Wo);
   else
     stem_bwd_reduce_kernel<<<grid, kRedThreads, smem, st>>>(xb, dyb, argmax, mean, invstd, scale, shift, p1, p2, C,
@@ -870,7 +920,8 @@ extern "C" int ecgmm_bn_bwd_apply(const ecgmm_bf16* x, const ecgmm_bf16* dy, con
                                   ecgmm_bf16* dx, ecgmm_bf16* dz_out, int N, int H, int W, int C, int mode,
                                   void* stream) {
   ECGMM_CHECK(x && dy && coefA && coefB && coefD && dx, ECGMM_ERR_ARG, "bn_bwd_apply: null pointer");
-  ECGMM_CHECK(mode >= 0 && mode <= 2, ECGMM_ERR_ARG, "bn_bwd_apply: bad mode %d", mode);
+  ECGMM_CHECK(mode >= 0 && mode <= 3, ECGMM_ERR_ARG, "bn_bwd_apply: bad mode %d", mode);
+  ECGMM_CHECK(mode != 3 || argmax, ECGMM_ERR_ARG, "bn_bwd_apply: mode 3 needs the bit mask");
   ECGMM_CHECK(mode != 1 || y, ECGMM_ERR_ARG, "bn_bwd_apply: mode 1 needs y");
   ECGMM_CHECK(mode != 2 || (argmax && scale && shift && !se), ECGMM_ERR_ARG, "bn_bwd_apply: bad mode-2 arguments");
   ECGMM_CHECK(!se || q, ECGMM_ERR_ARG, "bn_bwd_apply: SE mode needs q");
@@ -878,22 +929,25 @@ extern "C" int ecgmm_bn_bwd_apply(const ecgmm_bf16* x, const ecgmm_bf16* dy, con
   const size_t vps = (size_t)H * W * (C >> 3), total = vps * N;
   if (total == 0) return ECGMM_OK;
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  const int g = stream_grid(total);
   cudaStream_t st = (cudaStream_t)stream;
   const bf16* xb = reinterpret_cast<const bf16*>(x);
   const bf16* dyb = reinterpret_cast<const bf16*>(dy);
   const bf16* yb = reinterpret_cast<const bf16*>(y);
   bf16* dxb = reinterpret_cast<bf16*>(dx);
   bf16* dzb = reinterpret_cast<bf16*>(dz_out);
-#define ECGMM_BWD(MODE_, SE_)                                                                                      \
-  bn_bwd_apply_kernel<MODE_, SE_><<<g, 256, 0, st>>>(xb, dyb, yb, argmax, coefA, coefB, coefD, scale, shift, se, q, \
-                                                     dxb, dzb, C >> 3, vps, total, H, W, Ho, Wo)
+#define ECGMM_BWD(MODE_, SE_)                                                                                  \
+  bn_bwd_apply_kernel<MODE_, SE_><<<stream_grid(total, bn_bwd_apply_kernel<MODE_, SE_>, 2), 256, 0, st>>>(     \
+      xb, dyb, yb, argmax, coefA, coefB, coefD, scale, shift, se, q, dxb, dzb, C >> 3, vps, total, H, W, Ho, Wo)
   if (mode == 2) {
     ECGMM_CHECK(!dz_out, ECGMM_ERR_ARG, "bn_bwd_apply: mode 2 does not produce dz_out");
     const size_t tb = (size_t)N * Ho * Wo * (C >> 3);
-    stem_bwd_apply_kernel<<<stream_grid(tb), 256, 0, st>>>(xb, dyb, argmax, coefA, coefB, coefD, scale, shift, dxb,
+    stem_bwd_apply_kernel<<<stream_grid(tb, stem_bwd_apply_kernel), 256, 0, st>>>(xb, dyb, argmax, coefA, coefB, coefD, scale, shift, dxb,
                                                            C >> 3, tb, H, W, Ho, Wo);
-  } else if (mode == 1 && se)
+  } else if (mode == 3 && se)
+    ECGMM_BWD(3, true);
+  else if (mode == 3)
+    ECGMM_BWD(3, false);
+  else if (mode == 1 && se)
     ECGMM_BWD(1, true);
   else if (mode == 1)
     ECGMM_BWD(1, false);
@@ -922,7 +976,7 @@ extern "C" int ecgmm_avgpool_bwd(const float* dout, ecgmm_bf16* dx, int N, int P
   ECGMM_CHECK(C % 8 == 0, ECGMM_ERR_SHAPE, "avgpool_bwd: C=%d not a multiple of 8", C);
   const size_t vps = (size_t)P * (C >> 3), total = vps * N;
   if (total == 0) return ECGMM_OK;
-  avgpool_bwd_kernel<<<stream_grid(total), 256, 0, (cudaStream_t)stream>>>(dout, reinterpret_cast<bf16*>(dx), C >> 3,
+  avgpool_bwd_kernel<<<stream_grid(total, avgpool_bwd_kernel), 256, 0, (cudaStream_t)stream>>>(dout, reinterpret_cast<bf16*>(dx), C >> 3,
                                                                          1.f / (float)P, vps, total);
   return check_launch("avgpool_bwd_kernel");
 }

@@ -40,7 +40,7 @@ SIGNATURES = {
     "ecgmm_chan_stats": [_p, _p, _p, _i, _i, _i, _i, _p],
     "ecgmm_bn_finalize": [_p, _p, _i, _i, _i, _ll, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "ecgmm_bn_eval_coeffs": [_i, _p, _p, _p, _p, _p, _f, _p, _p, _p],
-    "ecgmm_bn_apply": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "ecgmm_bn_apply": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "ecgmm_bn_relu_maxpool": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "ecgmm_bn_bwd_reduce": [_p] * 10 + [_i] * 6 + [_p],
     "ecgmm_bn_bwd_finalize": [_p, _p, _i, _i, _i, _ll] + [_p] * 11 + [_p],

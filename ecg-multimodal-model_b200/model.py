@@ -222,7 +222,7 @@ def _conv_block_fwd(blk, x, save, one_d=False):
     w1f, _ = blk.conv1.shadows()
     a = ops.conv2d_fwd(x, w1f, s)
     sa = _bn_stats(blk.bn1, a, blk.conv1.bias)
-    m = ops.bn_apply(a, sa, relu=True)
+    m, mask_m = ops.bn_apply(a, sa, relu=True, want_mask=save)
     w2f, _ = blk.conv2.shadows()
     b = ops.conv2d_fwd(m, w2f, 1)
     se = getattr(blk, "se", None)
@@ -238,17 +238,18 @@ def _conv_block_fwd(blk, x, save, one_d=False):
         wdf, _ = blk.downsample[0].shadows()
         d = ops.conv2d_fwd(x, wdf, s)
         sd = _bn_stats(blk.downsample[1], d, blk.downsample[0].bias)
-        idn = ops.bn_apply(d, sd, relu=False)
+        idn, _ = ops.bn_apply(d, sd, relu=False)
     else:
         idn = x
-    out = ops.bn_apply(b, sb, se=gate, res=idn, relu=True)
-    rec = (x, a, sa, m, b, sb, d, sd, out, se_rec) if save else None
+    out, mask_out = ops.bn_apply(b, sb, se=gate, res=idn, relu=True, want_mask=save)
+    # backward needs the ReLU masks as bits, not the activations (m / out are kept only as conv inputs)
+    rec = (x, a, sa, m, b, sb, d, sd, mask_m, mask_out, se_rec) if save else None
     return out, rec
 
 
 def _conv_block_bwd(blk, rec, dout, G):
     """Returns the gradient w.r.t. the block input."""
-    x, a, sa, m, b, sb, d, sd, out, se_rec = rec
+    x, a, sa, m, b, sb, d, sd, mask_m, mask_out, se_rec = rec
     s = blk.stride
     _, H, W, _ = x.shape
     R, S = blk.conv1.shadows()[0].shape[1:3]
@@ -269,14 +270,14 @@ def _conv_block_bwd(blk, rec, dout, G):
             lib.call("ecgmm_colsum", ops._ptr(dpre1), ops._ptr(G(se.fc[0].bias)), n, w1.shape[0], 0, ops._s())
             return q
 
-    db_, dz = ops.bn_backward(b, dout, sb, blk.bn2.weight, y=out, se=gate, se_ctx=se_ctx, want_dz=True,
+    db_, dz = ops.bn_backward(b, dout, sb, blk.bn2.weight, mask=mask_out, se=gate, se_ctx=se_ctx, want_dz=True,
                               dgamma=G(blk.bn2.weight), dbeta=G(blk.bn2.bias))
     del dout
     ops.conv2d_wgrad(m, db_, G(blk.conv2.weight), R, S, 1)
     _, w2d = blk.conv2.shadows()
     dm = ops.conv2d_dgrad(db_, w2d, (m.shape[1], m.shape[2]), 1)
     del db_
-    da, _ = ops.bn_backward(a, dm, sa, blk.bn1.weight, y=m, dgamma=G(blk.bn1.weight), dbeta=G(blk.bn1.bias))
+    da, _ = ops.bn_backward(a, dm, sa, blk.bn1.weight, mask=mask_m, dgamma=G(blk.bn1.weight), dbeta=G(blk.bn1.bias))
     del dm
     ops.conv2d_wgrad(x, da, G(blk.conv1.weight), R, S, s)
     _, w1d = blk.conv1.shadows()

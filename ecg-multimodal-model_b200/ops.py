@@ -230,16 +230,20 @@ def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, conv_bias=None) 
     return BNStats(None, None, scale, shift)
 
 
-def bn_apply(x, st: BNStats, se=None, res=None, relu=True, out=None):
+def bn_apply(x, st: BNStats, se=None, res=None, relu=True, out=None, want_mask=False):
+    """y = act((x*scale+shift)*se + res); returns (y, mask).  want_mask: also produce the ReLU bit mask
+    (uint8, one byte per 8 channels) that bn_backward(mask=...) consumes (None otherwise)."""
     _chk(x, BF16, "x")
     N, P, C = _npc(x)
     y = torch.empty_like(x) if out is None else out
     if res is not None:
         _chk(res, BF16, "res")
         assert res.shape == x.shape
-    _timed("bn_apply", 2.0 * N * P * C * (3 if res is not None else 2), "ecgmm_bn_apply", _ptr(x), _ptr(st.scale),
-           _ptr(st.shift), _ptr(se), _ptr(res), _ptr(y), N, P, C, int(relu), _s())
-    return y
+    mask = torch.empty(x.numel() // 8, dtype=torch.uint8, device=x.device) if (want_mask and relu) else None
+    _timed("bn_apply", 2.0 * N * P * C * (3 if res is not None else 2) + (N * P * C / 8 if mask is not None else 0),
+           "ecgmm_bn_apply", _ptr(x), _ptr(st.scale), _ptr(st.shift), _ptr(se), _ptr(res), _ptr(y), _ptr(mask), N, P, C,
+           int(relu), _s())
+    return y, mask
 
 
 def bn_relu_maxpool(x, st: BNStats, want_argmax=True):
@@ -255,11 +259,12 @@ def bn_relu_maxpool(x, st: BNStats, want_argmax=True):
 
 
 def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=None, want_dz=False,
-                need_param_grads=True, dgamma=None, dbeta=None):
+                need_param_grads=True, dgamma=None, dbeta=None, mask=None):
     """BatchNorm (+ReLU / +SE gate / +stem max-pool) backward.
 
     x: raw convolution output [N,H,W,C]; dy: upstream gradient (pooled-shape for the stem, mode 2);
-    y: post-activation output (ReLU mask) or None; argmax: stem pooling indices or None;
+    y: post-activation output (ReLU mask) or None; mask: the bit mask from bn_apply(want_mask=True),
+    used instead of y when given; argmax: stem pooling indices or None;
     se / se_ctx: gate [N,C] and a callable (p1, p2, split) -> q [N,C] that runs the SE backward
     between the reduction and the finalize step.
     Returns (dx, dz or None); dgamma/dbeta are written into the given fp32 buffers."""
@@ -272,12 +277,16 @@ def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=
         N, H_, W_, C = x.shape
     P = H_ * W_
     dev = x.device
-    mode = 2 if argmax is not None else (1 if y is not None else 0)
+    mode = 2 if argmax is not None else (3 if mask is not None else (1 if y is not None else 0))
+    if mode == 3:
+        argmax, y = mask, None  # the C ABI carries the bit mask in the argmax slot
     split = lib.load().ecgmm_reduce_split(N, P, C)
     part = _f32(2 * N * split * C, dev)
     p1, p2 = part[: N * split * C], part[N * split * C:]
     # algorithmic bytes of the two backward passes: x + (dy | pooled dy + argmax) [+ y]; the apply pass also writes dx [+ dz]
     rd = 2.0 * N * P * C * (3 if mode == 1 else 2) if mode != 2 else 2.0 * N * P * C + 3.0 * dy.numel()
+    if mode == 3:
+        rd += N * P * C / 8
     _timed("bn_bwd_reduce", rd, "ecgmm_bn_bwd_reduce", _ptr(x), _ptr(dy), _ptr(y), _ptr(argmax), _ptr(st.mean),
            _ptr(st.invstd), _ptr(st.scale), _ptr(st.shift), _ptr(p1), _ptr(p2), N, H_, W_, C, split, mode, _s())
     q = None

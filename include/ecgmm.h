@@ -120,16 +120,20 @@ int ecgmm_bn_finalize(const float* psum, const float* psq, int N, int split, int
 int ecgmm_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* conv_bias,
                          const float* running_mean, const float* running_var, float eps, float* scale, float* shift,
                          void* stream);
-/* y = act((x*scale[c] + shift[c]) * se[n][c] + res); se (fp32 [N][C]) and res may be NULL */
+/* y = act((x*scale[c] + shift[c]) * se[n][c] + res); se (fp32 [N][C]) and res may be NULL.
+ * relu_mask (may be NULL; only with relu) receives one byte per 8 channels, bit j = (y[8g+j] > 0):
+ * the backward kernels (mode 3) read it instead of y, 1/16 of the bytes. */
 int ecgmm_bn_apply(const ecgmm_bf16* x, const float* scale, const float* shift, const float* se,
-                   const ecgmm_bf16* res, ecgmm_bf16* y, int N, int P, int C, int relu, void* stream);
+                   const ecgmm_bf16* res, ecgmm_bf16* y, uint8_t* relu_mask, int N, int P, int C, int relu,
+                   void* stream);
 /* stem: y [N][Ho][Wo][C] = maxpool3x3/s2/p1(relu(x*scale+shift)); argmax (may be NULL) [N][Ho][Wo][C] u8 holds the
  * window position 0..8 of the first maximum.  H == 1 gives MaxPool1d(3,2,1). */
 int ecgmm_bn_relu_maxpool(const ecgmm_bf16* x, const float* scale, const float* shift, ecgmm_bf16* y,
                           uint8_t* argmax, int N, int H, int W, int C, void* stream);
 /* Backward partials p1/p2 [N][split][C] = sum dz, sum dz*xhat with
  *   mode 0: dz = dy;  mode 1: dz = dy * (y > 0);  mode 2: stem -- dy is the gradient of the POOLED
- *   output [N][Ho][Wo][C], routed through argmax and gated by relu(x*scale+shift) > 0. */
+ *   output [N][Ho][Wo][C], routed through argmax and gated by relu(x*scale+shift) > 0;
+ *   mode 3: dz = dy * bit, the `argmax` argument carrying the relu_mask written by ecgmm_bn_apply. */
 int ecgmm_bn_bwd_reduce(const ecgmm_bf16* x, const ecgmm_bf16* dy, const ecgmm_bf16* y, const uint8_t* argmax,
                         const float* mean, const float* invstd, const float* scale, const float* shift, float* p1,
                         float* p2, int N, int H, int W, int C, int split, int mode, void* stream);

@@ -76,8 +76,12 @@ def test_bn_train_forward(N, H, W, C, mode):
     xn = nhwc(x)
     st = ops.bn_train_stats(xn, bn.weight.detach(), bn.bias.detach(), rm0, rv0, None, bn.eps, bn.momentum,
                             conv_bias=bias, want_nsum=True)
-    y = ops.bn_apply(xn, st, res=None if res is None else nhwc(res), relu=mode != "norelu")
+    y, mask = ops.bn_apply(xn, st, res=None if res is None else nhwc(res), relu=mode != "norelu", want_mask=True)
     close_bf16(nchw(y), y_ref.detach(), "bn forward")
+    if mode != "norelu":  # bit j of byte g = (y[8g+j] > 0)
+        bits = (y.flatten().view(-1, 8) > 0).to(torch.int32)
+        want = (bits << torch.arange(8, device=DEV, dtype=torch.int32)).sum(1)
+        assert torch.equal(mask.to(torch.int32), want)
     assert rel_l2(rm0, rm_ref) < 1e-4 and rel_l2(rv0, rv_ref) < 1e-4
     assert rel_l2(st.nsum, x.float().sum(dim=(2, 3))) < 1e-4 or float(st.nsum.abs().max()) < 1e-3
 
@@ -95,7 +99,7 @@ def test_bn_eval_coeffs():
     bias = torch.randn(C, generator=g).to(DEV)
     y_ref = F.relu(bn(x.float() + bias.view(1, C, 1, 1)))
     st = ops.bn_eval_coeffs(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps, bias)
-    y = ops.bn_apply(nhwc(x), st, relu=True)
+    y, _ = ops.bn_apply(nhwc(x), st, relu=True)
     close_bf16(nchw(y), y_ref, "bn eval")
 
 
@@ -118,10 +122,14 @@ def test_bn_backward(N, H, W, C, mode):
     y_ref.backward(dy.float())
     xn = nhwc(x)
     st = ops.bn_train_stats(xn, gamma.detach(), beta.detach(), None, None, None, 1e-5, 0.1)
-    y = ops.bn_apply(xn, st, res=None if res is None else nhwc(res), relu=mode != "linear")
+    y, mask = ops.bn_apply(xn, st, res=None if res is None else nhwc(res), relu=mode != "linear", want_mask=True)
     dg, db = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
     dx, dz = ops.bn_backward(xn, nhwc(dy), st, gamma.detach(), y=y if mode != "linear" else None, want_dz=True,
                              dgamma=dg, dbeta=db)
+    if mode != "linear":  # the bit-mask path must agree exactly with the y > 0 path
+        dg2, db2 = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+        dx2, dz2 = ops.bn_backward(xn, nhwc(dy), st, gamma.detach(), mask=mask, want_dz=True, dgamma=dg2, dbeta=db2)
+        assert torch.equal(dx, dx2) and torch.equal(dz, dz2) and torch.equal(dg, dg2) and torch.equal(db, db2)
     # ReLU mask taken from the bf16 output: elements whose pre-activation rounds to 0 may differ -> L2 metric
     assert rel_l2(nchw(dx), xr.grad) < 2e-2
     assert rel_l2(dg, gamma.grad) < 1e-2 and rel_l2(db, beta.grad) < 1e-2
