@@ -27,6 +27,7 @@ constexpr int kNhMaxTaps = 9;
 struct alignas(64) NtHaloParams {
   CUtensorMap x_map;  // [N][H][W][64], box (64, 130, 1, 1)
   CUtensorMap w_map;  // [64][ntaps*64] (k contiguous), box (64, 64)
+  CUtensorMap y_map;  // output [N][H][W][64], box (64, 128, 1, 1): epilogue TMA store (and load when accumulating)
   int ntaps, rows;    // rows = halo rows staged per tile (3 for 3x3, 1 for 1x3)
   int8_t tap_row[kNhMaxTaps], tap_shift[kNhMaxTaps];
   int padW, row0;     // input row of halo row 0 relative to the output row (-(R/2))
@@ -38,7 +39,8 @@ struct alignas(64) NtHaloParams {
 struct NtHaloSmem {
   static constexpr int kW = kNhMaxTaps * kNhWTile;                 // 73728
   static constexpr int kStage = 3 * kNhBoxStride;                  // 52224
-  static constexpr int kBarOff = kW + kNhStages * kStage;          // 178176
+  static constexpr int kOut = kW + kNhStages * kStage;             // 178176: 2 output staging tiles of 16 KiB
+  static constexpr int kBarOff = kOut + 2 * kNhTile * 128;         // 210944
   static constexpr int kBytes = kBarOff + 256 + 1024;
 };
 
@@ -54,7 +56,9 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
   uint64_t* tfull = empty + kNhStages;
   uint64_t* tempty = tfull + 2;
   uint64_t* wfull = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  uint64_t* ofull = wfull + 1;  // [2] old output tile landed in the staging buffer (accumulate mode)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ofull + 2);
+  uint8_t* sOut = smem + L::kOut;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -71,6 +75,9 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
       mbar_init(&tempty[i], 4);
     }
     mbar_init(wfull, 1);
+    mbar_init(&ofull[0], 1);
+    mbar_init(&ofull[1], 1);
+    tma_prefetch_desc(&p.y_map);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -148,54 +155,76 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
       }
     }
   } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5, 128 threads)
+    // TMEM -> registers -> bf16 -> SWIZZLE_128B staging tile in shared memory -> ONE TMA tensor store per
+    // tile (full 128-byte lines; pixels past the image edge are clipped by the tensor map).  Writing
+    // 16 bytes per lane straight to global memory touches 32 different lines per instruction and made
+    // the epilogue, not the MMA, the pacing stage (ncu: long-scoreboard stalls behind STG).
     const int quad = warp & 3;
     const int m_row = quad * 32 + lane;
+    const bool leader = (threadIdx.x == 64);
     int it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       const int twi = t % p.tiles_w;
       const int m = t / p.tiles_w;  // img * H + oh
-      const int ow = twi * kNhTile + m_row;
-      const bool valid = ow < p.W;
-      __nv_bfloat16* dst = p.out + ((size_t)m * p.W + ow) * 64;
+      const int oh = m % p.H, img = m / p.H;
+      const int w0 = twi * kNhTile;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      uint8_t* buf = sOut + acc * (kNhTile * 128);
+      if (leader) {
+        tma_store_wait_read<1>();  // the store issued from this buffer two tiles ago has read it
+        if (p.accumulate) {
+          mbar_expect_tx(&ofull[acc], kNhTile * 128);
+          tma_load_4d(buf, &p.y_map, &ofull[acc], 0, w0, oh, img);
+        }
+      }
+      named_bar_sync(1, 128);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      if (p.accumulate) mbar_wait(&ofull[acc], acc_phase);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 64;
+      uint8_t* row = buf + m_row * 128;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(t_addr + c * 32, r);
         tmem_ld_wait();
-        if (valid) {
-          uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float f[8];
+        for (int q = 0; q < 4; ++q) {
+          // 16-byte chunk j of row m lives at chunk (j ^ (m & 7)) of the swizzled tile
+          uint4* d4 = reinterpret_cast<uint4*>(row + (((c * 4 + q) ^ (m_row & 7)) << 4));
+          float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[q * 8 + j]);
-            if (p.accumulate) {
-              const uint4 old = d4[q];
-              const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[q * 8 + j]);
+          if (p.accumulate) {
+            const uint4 old = *d4;
+            const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 o = __bfloat1622float2(ob[j]);
-                f[2 * j] += o.x;
-                f[2 * j + 1] += o.y;
-              }
+            for (int j = 0; j < 4; ++j) {
+              const float2 o = __bfloat1622float2(ob[j]);
+              f[2 * j] += o.x;
+              f[2 * j + 1] += o.y;
             }
-            uint4 v;
-            __nv_bfloat162* vb = reinterpret_cast<__nv_bfloat162*>(&v);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) vb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            d4[q] = v;
           }
+          uint4 v;
+          __nv_bfloat162* vb = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) vb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          *d4 = v;
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) mbar_arrive(&tempty[acc]);  // accumulator may be overwritten by the MMA warp
+      fence_proxy_async_smem();                   // make the staging tile visible to the TMA engine
+      named_bar_sync(1, 128);
+      if (leader) {
+        tma_store_4d(&p.y_map, buf, 0, w0, oh, img);
+        tma_store_commit();
+      }
     }
+    if (leader) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -233,6 +262,8 @@ int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16
   int rc = make_tmap_4d(&p.x_map, x, 64, W, H, N, 64 * e, (uint64_t)W * 64 * e, (uint64_t)H * W * 64 * e, 64, kNhBoxW, 1);
   if (rc) return rc;
   rc = make_tmap_2d(&p.w_map, w, (uint64_t)R * S * 64, 64, (uint64_t)R * S * 64 * e, 64, 64);
+  if (rc) return rc;
+  rc = make_tmap_4d(&p.y_map, y, 64, W, H, N, 64 * e, (uint64_t)W * 64 * e, (uint64_t)H * W * 64 * e, 64, kNhTile, 1);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {

@@ -20,7 +20,7 @@ constexpr int kSrRing = 8;
 struct alignas(64) StemRingParams {
   CUtensorMap x_map;   // overlapping-column view of xs: (64, Wo, Hs, N), box (64, 128, 1, 1)
   CUtensorMap w_map;   // fwd: w_s2d [64][256], box (64, 64)
-  CUtensorMap dy_map;  // wgrad: dy [N][Ho][Wo][64], box (64, 128, 1, 1)
+  CUtensorMap dy_map;  // wgrad: dy [N][Ho][Wo][64], box (64, 128, 1, 1); fwd: the OUTPUT y, same shape (TMA store)
   int Ho, Wo, tiles_w, n_strips;
   __nv_bfloat16* out;  // fwd: y [N][Ho][Wo][64]
   float* dw;           // wgrad: [64][3][7][7]
@@ -29,7 +29,8 @@ struct alignas(64) StemRingParams {
 // ------------------------------------------------------------------------------------- forward
 struct StemFwdSmem {
   static constexpr int kW = 4 * 8192;
-  static constexpr int kBarOff = kW + kSrRing * kSrSlot;
+  static constexpr int kOut = kW + kSrRing * kSrSlot;  // 2 output staging tiles of 16 KiB
+  static constexpr int kBarOff = kOut + 2 * kSrSlot;
   static constexpr int kBytes = kBarOff + 512 + 1024;
 };
 
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.x_map);
     tma_prefetch_desc(&p.w_map);
+    tma_prefetch_desc(&p.dy_map);
     for (int i = 0; i < kSrRing; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -123,41 +125,50 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
       }
     }
   } else {
+    // epilogue: TMEM -> bf16 -> swizzled staging tile -> one TMA tensor store per tile (see conv_nt_halo.cu)
     const int quad = warp & 3;
     const int m_row = quad * 32 + lane;
+    const bool leader = (threadIdx.x == 64);
+    uint8_t* sOut = smem + L::kOut;
     int it = 0;
     for (int s = blockIdx.x; s < p.n_strips; s += gridDim.x) {
-      const int img = s / p.tiles_w, ow = (s % p.tiles_w) * kSrTile + m_row;
-      const bool valid = ow < p.Wo;
+      const int img = s / p.tiles_w, w0 = (s % p.tiles_w) * kSrTile;
       for (int oh = 0; oh < p.Ho; ++oh, ++it) {
-        __nv_bfloat16* dst = p.out + (((size_t)img * p.Ho + oh) * p.Wo + ow) * 64;
         const int acc = it & 1;
+        uint8_t* buf = sOut + acc * kSrSlot;
+        if (leader) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
         mbar_wait(&tfull[acc], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 64;
+        uint8_t* row = buf + m_row * 128;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(t_addr + c * 32, r);
           tmem_ld_wait();
-          if (valid) {
-            uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 v;
-              __nv_bfloat162* vb = reinterpret_cast<__nv_bfloat162*>(&v);
+          for (int g = 0; g < 4; ++g) {
+            uint4 v;
+            __nv_bfloat162* vb = reinterpret_cast<__nv_bfloat162*>(&v);
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                vb[j] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
-              d4[g] = v;
-            }
+            for (int j = 0; j < 4; ++j)
+              vb[j] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
+            *reinterpret_cast<uint4*>(row + (((c * 4 + g) ^ (m_row & 7)) << 4)) = v;
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (leader) {
+          tma_store_4d(&p.dy_map, buf, 0, w0, oh, img);
+          tma_store_commit();
+        }
       }
     }
+    if (leader) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -325,7 +336,8 @@ int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, in
   if (rc) return rc;
   rc = make_tmap_2d(&p.w_map, w_s2d, 256, 64, 512, 64, 64);
   if (rc) return rc;
-  p.dy_map = p.x_map;
+  rc = make_tmap_4d(&p.dy_map, y, 64, Wo, Ho, N, 128, (uint64_t)Wo * 128, (uint64_t)Ho * Wo * 128, 64, kSrTile, 1);
+  if (rc) return rc;
   static bool configured = false;
   if (!configured) {
     ECGMM_CUDA(cudaFuncSetAttribute(stem_fwd_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
