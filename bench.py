@@ -280,12 +280,20 @@ def run_ours(args):
     step(resident)
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
-    classes = {}
+    classes, detail = {}, {}
     for kind, work, a, b in prof:
-        c = classes.setdefault(kind, {"launches": 0, "ms": 0.0, "work": 0.0})
-        c["launches"] += 1
-        c["ms"] += a.elapsed_time(b)
-        c["work"] += work
+        ms = a.elapsed_time(b)
+        for table, key in ((classes, kind.split("/")[0]), (detail, kind)):
+            c = table.setdefault(key, {"launches": 0, "ms": 0.0, "work": 0.0})
+            c["launches"] += 1
+            c["ms"] += ms
+            c["work"] += work
+    if rank == 0 and args.detail:
+        for k, c in sorted(detail.items(), key=lambda kv: -kv[1]["ms"]):
+            tensor = k.startswith("conv") or k.startswith("stem")
+            ach = c["work"] / (c["ms"] * 1e-3) / (1e12 if tensor else 1e9)
+            print(f"# {k:34s} n={c['launches']:3d} {c['ms']:8.3f} ms {ach:9.1f} {'TFLOP/s' if tensor else 'GB/s'}",
+                  file=sys.stderr)
 
     if rank != 0:
         if world > 1:
@@ -361,6 +369,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", action="store_true", help="per-shape kernel timings on stderr")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

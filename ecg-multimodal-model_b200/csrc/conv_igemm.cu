@@ -659,18 +659,27 @@ static int launch_tn(TnParams& p, cudaStream_t s) {
 namespace ecgmm {
 bool wgrad_halo_supported(int Cin, int Cout, int R, int S, int stride);
 int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W, int Cin,
-                      int Cout, int R, int S, int padH, int padW, cudaStream_t st);
+                      int Cout, int R, int S, int padH, int padW, void* workspace, size_t ws_bytes, cudaStream_t st);
+size_t wgrad_halo_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S, int padH, int padW);
 }  // namespace ecgmm
 
+extern "C" long long ecgmm_conv2d_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
+                                                  int padH, int padW) {
+  if (!wgrad_halo_supported(Cin, Cout, R, S, stride) || getenv("ECGMM_WGRAD_LEGACY")) return 0;
+  return (long long)wgrad_halo_workspace_bytes(N, H, W, Cin, Cout, R, S, padH, padW);
+}
+
 extern "C" int ecgmm_conv2d_wgrad(const ecgmm_bf16* x_, const ecgmm_bf16* dy_, float* dw, int N, int H, int W,
-                                  int Cin, int Cout, int R, int S, int stride, int padH, int padW, void* stream) {
+                                  int Cin, int Cout, int R, int S, int stride, int padH, int padW, void* workspace,
+                                  long long workspace_bytes, void* stream) {
   ECGMM_CHECK(x_ && dy_ && dw, ECGMM_ERR_ARG, "conv2d_wgrad: null pointer");
   int rc = check_conv_cfg(Cin, Cout, R, S, stride, padH, padW);
   if (rc) return rc;
   if (N == 0) return ECGMM_OK;
   if (wgrad_halo_supported(Cin, Cout, R, S, stride) && !getenv("ECGMM_WGRAD_LEGACY"))
     return launch_wgrad_halo(reinterpret_cast<const __nv_bfloat16*>(x_), reinterpret_cast<const __nv_bfloat16*>(dy_),
-                             dw, N, H, W, Cin, Cout, R, S, padH, padW, static_cast<cudaStream_t>(stream));
+                             dw, N, H, W, Cin, Cout, R, S, padH, padW, workspace,
+                             workspace_bytes > 0 ? (size_t)workspace_bytes : 0, static_cast<cudaStream_t>(stream));
   const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
   TnParams p;
   memset(&p, 0, sizeof(p));

@@ -25,6 +25,7 @@ struct alignas(64) WgHaloParams {
   CUtensorMap x_map;   // x  [N][H][W][Cin],   box (64, KP+S-1, 1, 1)
   CUtensorMap dy_map;  // dy [N][Ho][Wo][Cout], box (64, KP, 1, 1)
   float* dw;           // [Cout][Cin][R][S]
+  float* ws;           // optional split-K workspace [group][ksplit][slot][64 cols][128 rows]; NULL -> atomics
   int R, S, padH, padW;
   int KP, kmma;              // pixels per stage, KP/16
   int x_box_bytes, x_box_stride, dy_box_bytes, dy_box_stride, stage_bytes, stages;
@@ -152,28 +153,78 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
       for (int i = 0; i < n_slots; ++i) {
         const int tap = 2 * i + (m_row >> 6);
         const bool ok = tap < RS;
-        const int cin = cc * 64 + (m_row & 63);
-        float* dst0 = p.dw + ((size_t)(nt * 64) * p.Cin + cin) * RS + (ok ? tap : 0);
-        const size_t col_stride = (size_t)p.Cin * RS;
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + i * 64;
+        if (p.ws) {
+          // split-K partial, column-major so that the 32 lanes (= rows) of a warp store 128 contiguous bytes
+          float* dst0 = p.ws + ((size_t)(g * p.ksplit + ks) * n_slots + i) * (64 * 128) + m_row;
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_addr + c * 32, r);
-          tmem_ld_wait();
-          if (ok) {
-            float* dst = dst0 + (size_t)(c * 32) * col_stride;
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_addr + c * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + j * col_stride, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; ++j) dst0[(c * 32 + j) * 128] = __uint_as_float(r[j]);
+          }
+        } else {
+          const int cin = cc * 64 + (m_row & 63);
+          float* dst0 = p.dw + ((size_t)(nt * 64) * p.Cin + cin) * RS + (ok ? tap : 0);
+          const size_t col_stride = (size_t)p.Cin * RS;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_addr + c * 32, r);
+            tmem_ld_wait();
+            if (ok) {
+              float* dst = dst0 + (size_t)(c * 32) * col_stride;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) atomicAdd(dst + j * col_stride, __uint_as_float(r[j]));
+            }
           }
         }
       }
+    }
+  } else if (p.ws && warp >= 2) {
+    // a CTA without pixels still owns a workspace slice: the reduction kernel reads every slice
+    const int m_row = (warp & 3) * 32 + lane;
+    for (int i = 0; i < n_slots; ++i) {
+      float* dst0 = p.ws + ((size_t)(g * p.ksplit + ks) * n_slots + i) * (64 * 128) + m_row;
+      for (int c = 0; c < 64; ++c) dst0[c * 128] = 0.f;
     }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// Second stage of the split-K reduction: dw[cout][cin][tap] += sum over the ksplit partials.
+__global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw,
+                                                                 int ksplit, int n_slots, int RS, int cin_chunks,
+                                                                 int Cin, size_t total) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // ((g*n_slots + slot)*64 + c)*128 + m
+  if (idx >= total) return;
+  const int m = (int)(idx & 127);
+  const int c = (int)((idx >> 7) & 63);
+  const size_t gs = idx >> 13;
+  const int slot = (int)(gs % n_slots);
+  const int g = (int)(gs / n_slots);
+  const int tap = 2 * slot + (m >> 6);
+  if (tap >= RS) return;
+  const size_t slice = (size_t)n_slots * 64 * 128;
+  const float* src = ws + (size_t)g * ksplit * slice + ((size_t)slot * 64 + c) * 128 + m;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // independent chains: 4+ loads in flight per thread
+  int k = 0;
+  for (; k + 3 < ksplit; k += 4) {
+    a0 += src[(size_t)k * slice];
+    a1 += src[(size_t)(k + 1) * slice];
+    a2 += src[(size_t)(k + 2) * slice];
+    a3 += src[(size_t)(k + 3) * slice];
+  }
+  for (; k < ksplit; ++k) a0 += src[(size_t)k * slice];
+  const float acc = (a0 + a1) + (a2 + a3);
+  const int cc = g % cin_chunks, nt = g / cin_chunks;
+  const int cin = cc * 64 + (m & 63), cout = nt * 64 + c;
+  dw[((size_t)cout * Cin + cin) * RS + tap] += acc;
 }
 
 // Picks the stage length KP (multiple of 16, <= 128) that wastes the fewest pixel slots on rows of Wo.
@@ -195,8 +246,27 @@ bool wgrad_halo_supported(int Cin, int Cout, int R, int S, int stride) {
          (S == 3);
 }
 
+static void halo_split(int N, int H, int W, int Cin, int Cout, int R, int S, int padH, int padW, int* kp, int* total_kb,
+                       int* groups, int* ksplit) {
+  const int Ho = H + 2 * padH - R + 1, Wo = W + 2 * padW - S + 1;
+  *kp = pick_kp(Wo);
+  *total_kb = N * Ho * ceil_div(Wo, *kp);
+  *groups = (Cin / 64) * (Cout / 64);
+  int ks = num_sms() / *groups;
+  if (ks < 1) ks = 1;
+  if (ks > *total_kb) ks = *total_kb > 0 ? *total_kb : 1;
+  *ksplit = ks;
+}
+
+size_t wgrad_halo_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S, int padH, int padW) {
+  int kp, total_kb, groups, ksplit;
+  halo_split(N, H, W, Cin, Cout, R, S, padH, padW, &kp, &total_kb, &groups, &ksplit);
+  return (size_t)groups * ksplit * ((R * S + 1) / 2) * 64 * 128 * sizeof(float);
+}
+
 int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W, int Cin,
-                      int Cout, int R, int S, int padH, int padW, cudaStream_t st) {
+                      int Cout, int R, int S, int padH, int padW, void* workspace, size_t ws_bytes,
+                      cudaStream_t st) {
   const int Ho = H + 2 * padH - R + 1, Wo = W + 2 * padW - S + 1;
   WgHaloParams p;
   memset(&p, 0, sizeof(p));
@@ -242,8 +312,16 @@ int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
     ECGMM_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = 227 * 1024;
   }
+  const size_t need = wgrad_halo_workspace_bytes(N, H, W, Cin, Cout, R, S, padH, padW);
+  p.ws = (workspace && ws_bytes >= need) ? reinterpret_cast<float*>(workspace) : nullptr;
   wgrad_halo_kernel<<<groups * ksplit, 192, smem, st>>>(p);
-  return check_launch("wgrad_halo_kernel");
+  rc = check_launch("wgrad_halo_kernel");
+  if (rc || !p.ws) return rc;
+  const int n_slots = (R * S + 1) / 2;
+  const size_t total = (size_t)groups * n_slots * 64 * 128;
+  wgrad_halo_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.ws, dw, ksplit, n_slots, R * S,
+                                                                           p.cin_chunks, Cin, total);
+  return check_launch("wgrad_halo_reduce_kernel");
 }
 
 }  // namespace ecgmm

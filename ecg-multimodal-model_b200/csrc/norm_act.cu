@@ -558,64 +558,75 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
 // loads 4 x vectors + 4 argmax words + 4 pooled-gradient vectors (12 independent loads) and
 // produces the gradient of all 4 pixels.  Window position codes (dh*3+dw) are compile-time.
 // ------------------------------------------------------------------------------------------
-struct StemBlock {
-  float xv[4][8];  // x at (i,j) = [2*i + j]
-  float dz[4][8];  // gradient of the pre-activation after pool routing + ReLU gate
-  bool ok[4];
+// raw (still packed) operands of one 2x2 block for 8 channels: 12 independent loads
+struct StemRaw {
+  uint4 vx[4];  // x at pixel t = 2*i + j
+  uint4 vg[4];  // pooled gradient of window t = 2*wi + wj (zeroed when the window does not exist)
+  uint2 va[4];  // argmax codes of window t
+  bool ok[4];   // pixel t inside the image
 };
 
-__device__ __forceinline__ void stem_block_load(const __nv_bfloat16* __restrict__ x,
-                                                const __nv_bfloat16* __restrict__ dyp,
-                                                const uint8_t* __restrict__ arg, size_t n, int a, int b, int H,
-                                                int W, int Ho, int Wo, int CG, int cg, const float (&sc)[8],
-                                                const float (&sh)[8], StemBlock& blk) {
-  uint4 vx[4], vg[4];
-  uint2 va[4];
-  bool wok[4];
+__device__ __forceinline__ void stem_raw_load(const __nv_bfloat16* __restrict__ x,
+                                              const __nv_bfloat16* __restrict__ dyp,
+                                              const uint8_t* __restrict__ arg, size_t n, int a, int b, int H, int W,
+                                              int Ho, int Wo, int CG, int cg, StemRaw& raw) {
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     const int i = t >> 1, j = t & 1;
     const int h = 2 * a + i, w = 2 * b + j;
-    blk.ok[t] = (h < H) && (w < W);
-    vx[t] = blk.ok[t] ? ld_stream(reinterpret_cast<const uint4*>(x) + ((n * H + h) * W + w) * CG + cg)
-                      : make_uint4(0, 0, 0, 0);
+    raw.ok[t] = (h < H) && (w < W);
+    raw.vx[t] = raw.ok[t] ? ld_stream(reinterpret_cast<const uint4*>(x) + ((n * H + h) * W + w) * CG + cg)
+                          : make_uint4(0, 0, 0, 0);
     const int oh = a + i, ow = b + j;
-    wok[t] = (oh < Ho) && (ow < Wo);
-    const size_t o = ((n * Ho + (wok[t] ? oh : a)) * Wo + (wok[t] ? ow : b)) * CG + cg;
-    vg[t] = reinterpret_cast<const uint4*>(dyp)[o];
-    va[t] = reinterpret_cast<const uint2*>(arg)[o];
-  }
-  float g[4][8];
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    unpack8(vx[t], blk.xv[t]);
-    unpack8(vg[t], g[t]);
-    if (!wok[t]) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) g[t][c] = 0.f;
-    }
-  }
-  // code of pixel (i,j) inside window (a+wi, b+wj): dh = i - 2*wi + 1, dw = j - 2*wj + 1
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    int code[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) code[t] = ((c < 4 ? va[t].x : va[t].y) >> (8 * (c & 3))) & 0xff;
-    // window 0 = (a,b), 1 = (a,b+1), 2 = (a+1,b), 3 = (a+1,b+1)
-    float d00 = (code[0] == 4) ? g[0][c] : 0.f;
-    float d01 = ((code[0] == 5) ? g[0][c] : 0.f) + ((code[1] == 3) ? g[1][c] : 0.f);
-    float d10 = ((code[0] == 7) ? g[0][c] : 0.f) + ((code[2] == 1) ? g[2][c] : 0.f);
-    float d11 = ((code[0] == 8) ? g[0][c] : 0.f) + ((code[1] == 6) ? g[1][c] : 0.f) +
-                ((code[2] == 2) ? g[2][c] : 0.f) + ((code[3] == 0) ? g[3][c] : 0.f);
-    blk.dz[0][c] = (fmaf(blk.xv[0][c], sc[c], sh[c]) > 0.f) ? d00 : 0.f;
-    blk.dz[1][c] = (fmaf(blk.xv[1][c], sc[c], sh[c]) > 0.f) ? d01 : 0.f;
-    blk.dz[2][c] = (fmaf(blk.xv[2][c], sc[c], sh[c]) > 0.f) ? d10 : 0.f;
-    blk.dz[3][c] = (fmaf(blk.xv[3][c], sc[c], sh[c]) > 0.f) ? d11 : 0.f;
+    const bool wok = (oh < Ho) && (ow < Wo);
+    const size_t o = ((n * Ho + (wok ? oh : a)) * Wo + (wok ? ow : b)) * CG + cg;
+    raw.vg[t] = reinterpret_cast<const uint4*>(dyp)[o];
+    raw.va[t] = reinterpret_cast<const uint2*>(arg)[o];
+    if (!wok) raw.vg[t] = make_uint4(0, 0, 0, 0);
   }
 }
 
-// p1/p2 [N][SPLIT][C]; the slab unit is a 2x2 block (= one pooled position)
-__global__ void __launch_bounds__(kRedThreads) stem_bwd_reduce_kernel(
+__device__ __forceinline__ uint32_t word_of(const uint4& v, int k) {
+  return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w));
+}
+
+// Channels 2k, 2k+1 of the block: x[t][2] and the routed + ReLU-gated gradient dz[t][2] of its 4 pixels.
+// code of pixel (i,j) inside window (a+wi, b+wj): dh = i - 2*wi + 1, dw = j - 2*wj + 1 (compile-time table).
+__device__ __forceinline__ void stem_pair(const StemRaw& raw, int k, const float* sc, const float* sh,
+                                          float (&xv)[4][2], float (&dz)[4][2]) {
+  float g[4][2];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const uint32_t wx = word_of(raw.vx[t], k), wg = word_of(raw.vg[t], k);
+    const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wx));
+    const float2 fg = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wg));
+    xv[t][0] = fx.x;
+    xv[t][1] = fx.y;
+    g[t][0] = fg.x;
+    g[t][1] = fg.y;
+  }
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int c = 2 * k + e;
+    int code[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) code[t] = ((c < 4 ? raw.va[t].x : raw.va[t].y) >> (8 * (c & 3))) & 0xff;
+    // window 0 = (a,b), 1 = (a,b+1), 2 = (a+1,b), 3 = (a+1,b+1)
+    const float d00 = (code[0] == 4) ? g[0][e] : 0.f;
+    const float d01 = ((code[0] == 5) ? g[0][e] : 0.f) + ((code[1] == 3) ? g[1][e] : 0.f);
+    const float d10 = ((code[0] == 7) ? g[0][e] : 0.f) + ((code[2] == 1) ? g[2][e] : 0.f);
+    const float d11 = ((code[0] == 8) ? g[0][e] : 0.f) + ((code[1] == 6) ? g[1][e] : 0.f) +
+                      ((code[2] == 2) ? g[2][e] : 0.f) + ((code[3] == 0) ? g[3][e] : 0.f);
+    dz[0][e] = (raw.ok[0] && fmaf(xv[0][e], sc[c], sh[c]) > 0.f) ? d00 : 0.f;
+    dz[1][e] = (raw.ok[1] && fmaf(xv[1][e], sc[c], sh[c]) > 0.f) ? d01 : 0.f;
+    dz[2][e] = (raw.ok[2] && fmaf(xv[2][e], sc[c], sh[c]) > 0.f) ? d10 : 0.f;
+    dz[3][e] = (raw.ok[3] && fmaf(xv[3][e], sc[c], sh[c]) > 0.f) ? d11 : 0.f;
+  }
+}
+
+// p1/p2 [N][SPLIT][C]; the slab unit is a 2x2 block (= one pooled position).  Accumulates sum dz and
+// sum dz*x; xhat is applied once per CTA: sum dz*xhat = (sum dz*x - mean * sum dz) * invstd.
+__global__ void __launch_bounds__(kRedThreads, 2) stem_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dyp, const uint8_t* __restrict__ arg,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ scale,
     const float* __restrict__ shift, float* __restrict__ p1, float* __restrict__ p2, int C, int blocks_per_split,
@@ -628,24 +639,25 @@ __global__ void __launch_bounds__(kRedThreads) stem_bwd_reduce_kernel(
   const int nb = Ho * Wo;
   const int pa = split * blocks_per_split;
   const int pb = min(nb, pa + blocks_per_split);
-  float mu[8], is[8], sc[8], sh[8], s[8], q[8];
-  load8f(mean + cg * 8, mu);
-  load8f(invstd + cg * 8, is);
+  float sc[8], sh[8], s[8], q[8];
   load8f(scale + cg * 8, sc);
   load8f(shift + cg * 8, sh);
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   for (int p = pa + r; p < pb; p += rows) {
-    StemBlock blk;
-    stem_block_load(x, dyp, arg, n, p / Wo, p % Wo, H, W, Ho, Wo, CG, cg, sc, sh, blk);
+    StemRaw raw;
+    stem_raw_load(x, dyp, arg, n, p / Wo, p % Wo, H, W, Ho, Wo, CG, cg, raw);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (!blk.ok[t]) continue;
+    for (int k = 0; k < 4; ++k) {
+      float xv[4][2], dz[4][2];
+      stem_pair(raw, k, sc, sh, xv, dz);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += blk.dz[t][j];
-        q[j] = fmaf(blk.dz[t][j], (blk.xv[t][j] - mu[j]) * is[j], q[j]);
-      }
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          s[2 * k + e] += dz[t][e];
+          q[2 * k + e] = fmaf(dz[t][e], xv[t][e], q[2 * k + e]);
+        }
     }
   }
   float* ss = sred;
@@ -664,11 +676,11 @@ __global__ void __launch_bounds__(kRedThreads) stem_bwd_reduce_kernel(
       b += sq[i * C + c];
     }
     p1[orow + c] = a;
-    p2[orow + c] = b;
+    p2[orow + c] = (b - mean[c] * a) * invstd[c];
   }
 }
 
-__global__ void __launch_bounds__(256) stem_bwd_apply_kernel(
+__global__ void __launch_bounds__(256, 2) stem_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dyp, const uint8_t* __restrict__ arg,
     const float* __restrict__ coefA, const float* __restrict__ coefB, const float* __restrict__ coefD,
     const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ dx, int CG,
@@ -681,22 +693,33 @@ __global__ void __launch_bounds__(256) stem_bwd_apply_kernel(
     t /= Wo;
     const int a = (int)(t % Ho);
     const size_t n = t / Ho;
-    float A[8], B[8], D[8], sc[8], sh[8];
-    load8f(coefA + cg * 8, A);
-    load8f(coefB + cg * 8, B);
-    load8f(coefD + cg * 8, D);
-    load8f(scale + cg * 8, sc);
-    load8f(shift + cg * 8, sh);
-    StemBlock blk;
-    stem_block_load(x, dyp, arg, n, a, b, H, W, Ho, Wo, CG, cg, sc, sh, blk);
+    StemRaw raw;
+    stem_raw_load(x, dyp, arg, n, a, b, H, W, Ho, Wo, CG, cg, raw);
+    const float* A = coefA + cg * 8;
+    const float* B = coefB + cg * 8;
+    const float* D = coefD + cg * 8;
+    const float* sc = scale + cg * 8;
+    const float* sh = shift + cg * 8;
+    uint32_t o[4][4];  // packed bf16x2 output words, [pixel][pair]
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (!blk.ok[k]) continue;
-      const int h = 2 * a + (k >> 1), w = 2 * b + (k & 1);
-      float o[8];
+      float xv[4][2], dz[4][2];
+      stem_pair(raw, k, sc, sh, xv, dz);
+      const float2 Ak = *reinterpret_cast<const float2*>(A + 2 * k);
+      const float2 Bk = *reinterpret_cast<const float2*>(B + 2 * k);
+      const float2 Dk = *reinterpret_cast<const float2*>(D + 2 * k);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], blk.dz[k][j], fmaf(B[j], blk.xv[k][j], D[j]));
-      reinterpret_cast<uint4*>(dx)[((n * H + h) * W + w) * CG + cg] = pack8(o);
+      for (int px = 0; px < 4; ++px) {
+        const __nv_bfloat162 v = __floats2bfloat162_rn(fmaf(Ak.x, dz[px][0], fmaf(Bk.x, xv[px][0], Dk.x)),
+                                                      fmaf(Ak.y, dz[px][1], fmaf(Bk.y, xv[px][1], Dk.y)));
+        o[px][k] = *reinterpret_cast<const uint32_t*>(&v);
+      }
+    }
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      if (!raw.ok[px]) continue;
+      const int h = 2 * a + (px >> 1), w = 2 * b + (px & 1);
+      reinterpret_cast<uint4*>(dx)[((n * H + h) * W + w) * CG + cg] = make_uint4(o[px][0], o[px][1], o[px][2], o[px][3]);
     }
   }
 }

@@ -34,7 +34,8 @@ SIGNATURES = {
     "ecgmm_stem_conv_wgrad": [_p, _p, _p, _i, _i, _i, _p],
     "ecgmm_conv2d_fwd": [_p, _p, _p] + [_i] * 10 + [_p],
     "ecgmm_conv2d_dgrad": [_p, _p, _p] + [_i] * 11 + [_p],
-    "ecgmm_conv2d_wgrad": [_p, _p, _p] + [_i] * 10 + [_p],
+    "ecgmm_conv2d_wgrad": [_p, _p, _p] + [_i] * 10 + [_p, _ll, _p],
+    "ecgmm_conv2d_wgrad_workspace": [_i] * 10,
     # BatchNorm / ReLU / pooling
     "ecgmm_reduce_split": [_i, _i, _i],
     "ecgmm_chan_stats": [_p, _p, _p, _i, _i, _i, _i, _p],
@@ -71,7 +72,8 @@ SIGNATURES = {
     "ecgmm_adam_chunk_bytes": [],
     "ecgmm_adam_step": [_p, _i, _f, _f, _f, _f, _f, _ll, _f, _p],
 }
-_RESTYPES = {"ecgmm_last_error": c_char_p, "ecgmm_stem_s2d_dims": None, "ecgmm_launch_count": c_ulonglong}
+_RESTYPES = {"ecgmm_last_error": c_char_p, "ecgmm_stem_s2d_dims": None, "ecgmm_launch_count": c_ulonglong,
+             "ecgmm_conv2d_wgrad_workspace": c_longlong}
 
 
 class EcgmmError(RuntimeError):

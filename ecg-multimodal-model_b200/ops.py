@@ -92,7 +92,7 @@ def conv2d_fwd(x: torch.Tensor, w_fwd: torch.Tensor, stride: int = 1) -> torch.T
     pH, pW = R // 2, S // 2
     Ho, Wo = _conv_out(H, W, R, S, stride, pH, pW)
     y = torch.empty((N, Ho, Wo, Cout), dtype=BF16, device=x.device)
-    _timed("conv_fwd", 2.0 * N * Ho * Wo * Cout * Cin * R * S, "ecgmm_conv2d_fwd", _ptr(x), _ptr(w_fwd), _ptr(y), N,
+    _timed(f"conv_fwd/{Cin}x{Cout}k{R}{S}s{stride}", 2.0 * N * Ho * Wo * Cout * Cin * R * S, "ecgmm_conv2d_fwd", _ptr(x), _ptr(w_fwd), _ptr(y), N,
            H, W, Cin, Cout, R, S, stride, pH, pW, _s())
     return y
 
@@ -113,7 +113,7 @@ def conv2d_dgrad(dy: torch.Tensor, w_dgrad: torch.Tensor, in_hw, stride: int = 1
     else:
         _chk(out, BF16, "out")
         assert tuple(out.shape) == (N, H, W, Cin)
-    _timed("conv_dgrad", 2.0 * N * Ho * Wo * Cout * Cin * R * S, "ecgmm_conv2d_dgrad", _ptr(dy), _ptr(w_dgrad),
+    _timed(f"conv_dgrad/{Cin}x{Cout}k{R}{S}s{stride}", 2.0 * N * Ho * Wo * Cout * Cin * R * S, "ecgmm_conv2d_dgrad", _ptr(dy), _ptr(w_dgrad),
            _ptr(out), N, H, W, Cin, Cout, R, S, stride, pH, pW, int(accumulate), _s())
     return out
 
@@ -126,8 +126,11 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, R: int, S:
     N, H, W, Cin = x.shape
     Cout = dy.shape[3]
     assert dw.numel() == Cout * Cin * R * S
-    _timed("conv_wgrad", 2.0 * N * dy.shape[1] * dy.shape[2] * Cout * Cin * R * S, "ecgmm_conv2d_wgrad", _ptr(x),
-           _ptr(dy), _ptr(dw), N, H, W, Cin, Cout, R, S, stride, R // 2, S // 2, _s())
+    ws_bytes = lib.load().ecgmm_conv2d_wgrad_workspace(N, H, W, Cin, Cout, R, S, stride, R // 2, S // 2)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
+    _timed(f"conv_wgrad/{Cin}x{Cout}k{R}{S}s{stride}", 2.0 * N * dy.shape[1] * dy.shape[2] * Cout * Cin * R * S,
+           "ecgmm_conv2d_wgrad", _ptr(x), _ptr(dy), _ptr(dw), N, H, W, Cin, Cout, R, S, stride, R // 2, S // 2, _ptr(ws),
+           ws_bytes, _s())
 
 
 # ---------------------------------------------------------------- ResNet stem
@@ -211,7 +214,7 @@ def bn_train_stats(x, gamma, beta, running_mean, running_var, num_batches, eps, 
     split = lib.load().ecgmm_reduce_split(N, P, C)
     part = _f32(2 * N * split * C, dev)
     psum, psq = part[: N * split * C], part[N * split * C:]
-    _timed("bn_stats", 2.0 * N * P * C, "ecgmm_chan_stats", _ptr(x), _ptr(psum), _ptr(psq), N, P, C, split, _s())
+    _timed(f"bn_stats/C{C}", 2.0 * N * P * C, "ecgmm_chan_stats", _ptr(x), _ptr(psum), _ptr(psq), N, P, C, split, _s())
     out = _f32(4 * C, dev)
     mean, invstd, scale, shift = out[:C], out[C:2 * C], out[2 * C:3 * C], out[3 * C:]
     nsum = _f32(N * C, dev).view(N, C) if want_nsum else None
@@ -240,7 +243,7 @@ def bn_apply(x, st: BNStats, se=None, res=None, relu=True, out=None, want_mask=F
         _chk(res, BF16, "res")
         assert res.shape == x.shape
     mask = torch.empty(x.numel() // 8, dtype=torch.uint8, device=x.device) if (want_mask and relu) else None
-    _timed("bn_apply", 2.0 * N * P * C * (3 if res is not None else 2) + (N * P * C / 8 if mask is not None else 0),
+    _timed(f"bn_apply/C{C}", 2.0 * N * P * C * (3 if res is not None else 2) + (N * P * C / 8 if mask is not None else 0),
            "ecgmm_bn_apply", _ptr(x), _ptr(st.scale), _ptr(st.shift), _ptr(se), _ptr(res), _ptr(y), _ptr(mask), N, P, C,
            int(relu), _s())
     return y, mask
@@ -287,7 +290,7 @@ def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=
     rd = 2.0 * N * P * C * (3 if mode == 1 else 2) if mode != 2 else 2.0 * N * P * C + 3.0 * dy.numel()
     if mode == 3:
         rd += N * P * C / 8
-    _timed("bn_bwd_reduce", rd, "ecgmm_bn_bwd_reduce", _ptr(x), _ptr(dy), _ptr(y), _ptr(argmax), _ptr(st.mean),
+    _timed(f"bn_bwd_reduce/m{mode}C{C}", rd, "ecgmm_bn_bwd_reduce", _ptr(x), _ptr(dy), _ptr(y), _ptr(argmax), _ptr(st.mean),
            _ptr(st.invstd), _ptr(st.scale), _ptr(st.shift), _ptr(p1), _ptr(p2), N, H_, W_, C, split, mode, _s())
     q = None
     if se is not None:
@@ -300,7 +303,7 @@ def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=
              _ptr(cB), _ptr(cD), _s())
     dx = torch.empty_like(x)
     dz = torch.empty_like(x) if want_dz else None
-    _timed("bn_bwd_apply", rd + 2.0 * N * P * C * (2 if want_dz else 1), "ecgmm_bn_bwd_apply", _ptr(x), _ptr(dy),
+    _timed(f"bn_bwd_apply/m{mode}C{C}{'+dz' if want_dz else ''}", rd + 2.0 * N * P * C * (2 if want_dz else 1), "ecgmm_bn_bwd_apply", _ptr(x), _ptr(dy),
            _ptr(y), _ptr(argmax), _ptr(cA), _ptr(cB), _ptr(cD), _ptr(st.scale), _ptr(st.shift), _ptr(se), _ptr(q),
            _ptr(dx), _ptr(dz), N, H_, W_, C, mode, _s())
     return dx, dz

@@ -89,9 +89,14 @@ int ecgmm_conv2d_fwd(const ecgmm_bf16* x, const ecgmm_bf16* w_fwd, ecgmm_bf16* y
 int ecgmm_conv2d_dgrad(const ecgmm_bf16* dy, const ecgmm_bf16* w_dgrad, ecgmm_bf16* dx, int N, int H, int W,
                        int Cin, int Cout, int R, int S, int stride, int padH, int padW, int accumulate,
                        void* stream);
-/* dw (fp32, OIHW) += x^T * dy (atomic accumulation across CTAs; caller zeroes dw when needed). */
+/* dw (fp32, OIHW) += x^T * dy.  The pixel range is split across CTAs (split-K); with a workspace of at
+ * least ecgmm_conv2d_wgrad_workspace() bytes the partials are combined by a second deterministic kernel,
+ * otherwise (workspace NULL / too small / shape not covered, query returns 0) by fp32 atomics. */
+long long ecgmm_conv2d_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int padH,
+                                       int padW);
 int ecgmm_conv2d_wgrad(const ecgmm_bf16* x, const ecgmm_bf16* dy, float* dw_oihw, int N, int H, int W, int Cin,
-                       int Cout, int R, int S, int stride, int padH, int padW, void* stream);
+                       int Cout, int R, int S, int stride, int padH, int padW, void* workspace,
+                       long long workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ BatchNorm / ReLU / pooling
  * Replaces nn.BatchNorm2d + ReLU + residual add + MaxPool2d of torchvision resnet18

@@ -18,7 +18,7 @@ def parse_header():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     protos = {}
-    for m in re.finditer(r"\b(unsigned long long|int|void|const char\*)\s+(ecgmm_\w+)\s*\(([^)]*)\)\s*;", src):
+    for m in re.finditer(r"\b(unsigned long long|long long|int|void|const char\*)\s+(ecgmm_\w+)\s*\(([^)]*)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
         protos[name] = (ret, params)
