@@ -83,19 +83,21 @@ __global__ void __launch_bounds__(kRedThreads) chan_stats_kernel(const __nv_bflo
 // apply kernel uses, optional per-sample sums (SE squeeze) and the running-statistics update.
 //   conv_bias: the convolution in front has a bias that the conv kernel does NOT add; in
 //   training mode it only shifts the batch mean (and so running_mean), never the output.
-// One CTA = 32 channels x 32 row lanes; lanes stride over the N*SPLIT partial rows (or over the
-// samples when per-sample sums are wanted), fp64 accumulation, shared-memory fold.
-constexpr int kFinLanes = 32;
+// One CTA = 8 channels x 128 row lanes (a 32-byte sector per row read); lanes stride over the N*SPLIT
+// partial rows (or over the samples when per-sample sums are wanted) with 4 independent fp64 chains,
+// then a shared-memory fold.  C/8 CTAs keep this latency-bound fold at a few microseconds.
+constexpr int kFinLanes = 128;
+constexpr int kFinCh = 8;
 
-__global__ void __launch_bounds__(32 * kFinLanes) bn_finalize_kernel(
+__global__ void __launch_bounds__(kFinCh * kFinLanes) bn_finalize_kernel(
     const float* __restrict__ psum, const float* __restrict__ psq, int rows_total, int split, int C, double count,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps,
     float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
     long long* __restrict__ num_batches, float* __restrict__ mean_out, float* __restrict__ invstd_out,
     float* __restrict__ scale_out, float* __restrict__ shift_out, float* __restrict__ nsum_out) {
-  __shared__ double sh_s[kFinLanes][33], sh_q[kFinLanes][33];
-  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  __shared__ double sh_s[kFinLanes][kFinCh + 1], sh_q[kFinLanes][kFinCh + 1];
+  const int cl = threadIdx.x & (kFinCh - 1), lane = threadIdx.x / kFinCh;
+  const int c = blockIdx.x * kFinCh + cl;
   if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches) *num_batches += 1;
   double s = 0.0, q = 0.0;
   if (c < C) {
@@ -112,10 +114,24 @@ __global__ void __launch_bounds__(32 * kFinLanes) bn_finalize_kernel(
         s += ns;
       }
     } else {
-      for (int i = lane; i < rows_total; i += kFinLanes) {
+      double s1 = 0.0, q1 = 0.0, s2 = 0.0, q2 = 0.0, s3 = 0.0, q3 = 0.0;
+      int i = lane;
+      for (; i + 3 * kFinLanes < rows_total; i += 4 * kFinLanes) {
+        s += psum[(size_t)i * C + c];
+        q += psq[(size_t)i * C + c];
+        s1 += psum[(size_t)(i + kFinLanes) * C + c];
+        q1 += psq[(size_t)(i + kFinLanes) * C + c];
+        s2 += psum[(size_t)(i + 2 * kFinLanes) * C + c];
+        q2 += psq[(size_t)(i + 2 * kFinLanes) * C + c];
+        s3 += psum[(size_t)(i + 3 * kFinLanes) * C + c];
+        q3 += psq[(size_t)(i + 3 * kFinLanes) * C + c];
+      }
+      for (; i < rows_total; i += kFinLanes) {
         s += psum[(size_t)i * C + c];
         q += psq[(size_t)i * C + c];
       }
+      s += s1 + s2 + s3;
+      q += q1 + q2 + q3;
     }
   }
   sh_s[lane][cl] = s;
@@ -423,15 +439,15 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
 // otherwise) the BatchNorm backward is   dx = A*se*dz + B*x + D + A*q   with per-channel
 //   A = gamma*invstd,  B = -gamma*invstd^2*m2,  D = -A*m1 + gamma*invstd^2*mean*m2,
 //   m1 = mean(du), m2 = mean(du*xhat);  dgamma = sum(du*xhat), dbeta = sum(du).
-__global__ void __launch_bounds__(32 * kFinLanes) bn_bwd_finalize_kernel(
+__global__ void __launch_bounds__(kFinCh * kFinLanes) bn_bwd_finalize_kernel(
     const float* __restrict__ p1, const float* __restrict__ p2, int N, int split, int C, double per_sample,
     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ se, const float* __restrict__ q, const float* __restrict__ nsum,
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coefA, float* __restrict__ coefB,
     float* __restrict__ coefD) {
-  __shared__ double sh_a[kFinLanes][33], sh_b[kFinLanes][33];
-  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  __shared__ double sh_a[kFinLanes][kFinCh + 1], sh_b[kFinLanes][kFinCh + 1];
+  const int cl = threadIdx.x & (kFinCh - 1), lane = threadIdx.x / kFinCh;
+  const int c = blockIdx.x * kFinCh + cl;
   double s1 = 0.0, s2 = 0.0;
   double mu = 0.0, is = 0.0;
   if (c < C) {
@@ -452,10 +468,24 @@ __global__ void __launch_bounds__(32 * kFinLanes) bn_bwd_finalize_kernel(
       }
     } else {
       const int rows_total = N * split;
-      for (int i = lane; i < rows_total; i += kFinLanes) {
+      double t1 = 0.0, t2 = 0.0, u1 = 0.0, u2 = 0.0, v1 = 0.0, v2 = 0.0;
+      int i = lane;
+      for (; i + 3 * kFinLanes < rows_total; i += 4 * kFinLanes) {
+        s1 += p1[(size_t)i * C + c];
+        s2 += p2[(size_t)i * C + c];
+        t1 += p1[(size_t)(i + kFinLanes) * C + c];
+        t2 += p2[(size_t)(i + kFinLanes) * C + c];
+        u1 += p1[(size_t)(i + 2 * kFinLanes) * C + c];
+        u2 += p2[(size_t)(i + 2 * kFinLanes) * C + c];
+        v1 += p1[(size_t)(i + 3 * kFinLanes) * C + c];
+        v2 += p2[(size_t)(i + 3 * kFinLanes) * C + c];
+      }
+      for (; i < rows_total; i += kFinLanes) {
         s1 += p1[(size_t)i * C + c];
         s2 += p2[(size_t)i * C + c];
       }
+      s1 += t1 + u1 + v1;
+      s2 += t2 + u2 + v2;
     }
   }
   sh_a[lane][cl] = s1;
@@ -828,7 +858,7 @@ extern "C" int ecgmm_bn_finalize(const float* psum, const float* psq, int N, int
                                  void* stream) {
   ECGMM_CHECK(psum && psq && mean && invstd && scale && shift, ECGMM_ERR_ARG, "bn_finalize: null pointer");
   ECGMM_CHECK(count > 0, ECGMM_ERR_SHAPE, "bn_finalize: empty batch");
-  bn_finalize_kernel<<<ceil_div(C, 32), 32 * kFinLanes, 0, (cudaStream_t)stream>>>(
+  bn_finalize_kernel<<<ceil_div(C, kFinCh), kFinCh * kFinLanes, 0, (cudaStream_t)stream>>>(
       psum, psq, N * split, split, C, (double)count, gamma, beta, conv_bias, eps, momentum, running_mean,
       running_var, num_batches, mean, invstd, scale, shift, nsum);
   return check_launch("bn_finalize_kernel");
@@ -932,7 +962,7 @@ extern "C" int ecgmm_bn_bwd_finalize(const float* p1, const float* p2, int N, in
   ECGMM_CHECK(p1 && p2 && mean && invstd && coefA && coefB && coefD, ECGMM_ERR_ARG, "bn_bwd_finalize: null pointer");
   ECGMM_CHECK(!se || (q && nsum), ECGMM_ERR_ARG, "bn_bwd_finalize: SE mode needs q and nsum");
   ECGMM_CHECK(N > 0 && per_sample > 0, ECGMM_ERR_SHAPE, "bn_bwd_finalize: empty batch");
-  bn_bwd_finalize_kernel<<<ceil_div(C, 32), 32 * kFinLanes, 0, (cudaStream_t)stream>>>(
+  bn_bwd_finalize_kernel<<<ceil_div(C, kFinCh), kFinCh * kFinLanes, 0, (cudaStream_t)stream>>>(
       p1, p2, N, split, C, (double)per_sample, gamma, mean, invstd, se, q, nsum, dgamma, dbeta, coefA, coefB, coefD);
   return check_launch("bn_bwd_finalize_kernel");
 }

@@ -859,6 +859,10 @@ class ECGMultimodalModel(nn.Module):
         self.attention_fusion = AttentionFusion(dims=list(dims))
         self.fusion_classifier = MLPHead(sum(dims), 128, num_classes, p=0.3)
         object.__setattr__(self, "_head", FusionHead(self))
+        object.__setattr__(self, "_streams", {})
+        import os as _os
+
+        self.overlap_branches = _os.environ.get("ECGMM_SIDE_STREAM", "1") != "0"
         dev = getattr(config, "device", None)
         if dev is not None and str(dev) != "cpu" and torch.cuda.is_available():
             self.to(dev)
@@ -872,11 +876,33 @@ class ECGMultimodalModel(nn.Module):
     def forward(self, image, ecg_signal, clinical):
         if ecg_signal.dim() == 2:
             ecg_signal = ecg_signal.unsqueeze(1)  # multimodal_paper_modal_balance.py:328
-        e_img = self.image_encoder(image)
-        e_sig = self.signal_encoder(ecg_signal)
-        e_clin = self.clinical_encoder(clinical)
+        if self.overlap_branches and image.is_cuda:
+            # The signal and clinical encoders are ~300 small latency-bound launches that do not depend on
+            # the image encoder: they run on a side stream (forward here, and - because autograd replays a
+            # node's backward on its forward stream - backward too) underneath the big conv / BN kernels.
+            main = torch.cuda.current_stream()
+            side = self._side_stream()
+            side.wait_stream(main)  # inputs (and the previous step's use of recycled buffers) are ready
+            with torch.cuda.stream(side):
+                e_sig = self.signal_encoder(ecg_signal)
+                e_clin = self.clinical_encoder(clinical)
+            e_img = self.image_encoder(image)
+            main.wait_stream(side)
+            for t in (ecg_signal, clinical, e_sig, e_clin):
+                t.record_stream(main if t is e_sig or t is e_clin else side)
+        else:
+            e_img = self.image_encoder(image)
+            e_sig = self.signal_encoder(ecg_signal)
+            e_clin = self.clinical_encoder(clinical)
         out = self._head(e_img, e_sig, e_clin)
         return out[3] if self.fusion_only else out
+
+    def _side_stream(self):
+        dev = torch.cuda.current_device()
+        st = self._streams.get(dev)
+        if st is None:
+            st = self._streams[dev] = torch.cuda.Stream()
+        return st
 
     # ---- checkpoint helpers (multimodal_paper_modal_balance.py:291-322,356-383)
     def load_pretrained_signal_encoder(self, path, load_fc=False):
