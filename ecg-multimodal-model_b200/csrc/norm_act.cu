@@ -341,6 +341,10 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
   float mu[8], is[8], sc[8], sh[8], s[8], q[8];
   load8f(mean + cg * 8, mu);
   load8f(invstd + cg * 8, is);
+  if (MODE == 4) {  // mean := beta, invstd := gamma: xhat of the selected pre-pool element = (y - beta) / gamma
+#pragma unroll
+    for (int j = 0; j < 8; ++j) is[j] = is[j] != 0.f ? 1.f / is[j] : 0.f;
+  }
   if (MODE == 2) {
     load8f(scale + cg * 8, sc);
     load8f(shift + cg * 8, sh);
@@ -379,6 +383,11 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
           for (int j = 0; j < 8; ++j)
             if (!((vm[u] >> j) & 1u)) dz[j] = 0.f;
         }
+        if (MODE == 4) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (xv[j] <= 0.f) dz[j] = 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           s[j] += dz[j];
@@ -407,6 +416,11 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (!((m >> j) & 1u)) dz[j] = 0.f;
+      }
+      if (MODE == 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (xv[j] <= 0.f) dz[j] = 0.f;
       }
     }
 #pragma unroll
@@ -921,7 +935,7 @@ extern "C" int ecgmm_bn_bwd_reduce(const ecgmm_bf16* x, const ecgmm_bf16* dy, co
                                    const float* scale, const float* shift, float* p1, float* p2, int N, int H,
                                    int W, int C, int split, int mode, void* stream) {
   ECGMM_CHECK(x && dy && mean && invstd && p1 && p2, ECGMM_ERR_ARG, "bn_bwd_reduce: null pointer");
-  ECGMM_CHECK(mode >= 0 && mode <= 3, ECGMM_ERR_ARG, "bn_bwd_reduce: bad mode %d", mode);
+  ECGMM_CHECK(mode >= 0 && mode <= 4, ECGMM_ERR_ARG, "bn_bwd_reduce: bad mode %d", mode);
   ECGMM_CHECK(mode != 3 || argmax, ECGMM_ERR_ARG, "bn_bwd_reduce: mode 3 needs the bit mask");
   ECGMM_CHECK(mode != 1 || y, ECGMM_ERR_ARG, "bn_bwd_reduce: mode 1 needs y");
   ECGMM_CHECK(mode != 2 || (argmax && scale && shift), ECGMM_ERR_ARG, "bn_bwd_reduce: mode 2 needs argmax/scale/shift");
@@ -947,6 +961,9 @@ extern "C" int ecgmm_bn_bwd_reduce(const ecgmm_bf16* x, const ecgmm_bf16* dy, co
                                                              P, C, rps, H, W, Ho, Wo);
   else if (mode == 3)
     bn_bwd_reduce_kernel<3><<<grid, kRedThreads, smem, st>>>(xb, dyb, yb, argmax, mean, invstd, scale, shift, p1, p2,
+                                                             P, C, rps, H, W, Ho, Wo);
+  else if (mode == 4)
+    bn_bwd_reduce_kernel<4><<<grid, kRedThreads, smem, st>>>(xb, dyb, yb, argmax, mean, invstd, scale, shift, p1, p2,
                                                              P, C, rps, H, W, Ho, Wo);
   else
     stem_bwd_reduce_kernel<<<grid, kRedThreads, smem, st>>>(xb, dyb, argmax, mean, invstd, scale, shift, p1, p2, C,

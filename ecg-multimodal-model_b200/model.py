@@ -350,6 +350,7 @@ class ResNet18(_Stage):
         pooled = ops.avgpool_fwd(x)
         feat = ops.linear_fwd(pooled, self.fc.weight, self.fc.bias)
         state = (xs, c1, st1, arg, recs, pooled, tuple(x.shape), (H, W)) if save else None
+        # (the pooled stem output lives in recs[0][0]: it is layer1.0's input)
         return feat, state
 
     def run_backward(self, state, grads, need_in):
@@ -361,13 +362,14 @@ class ResNet18(_Stage):
         dpooled = ops.linear_bwd(pooled, self.fc.weight, dfeat, dw=G(self.fc.weight), db=G(self.fc.bias))
         dx = ops.avgpool_bwd(dpooled, last_shape)
         blocks = self.blocks()
+        stem_out = recs[0][0]  # pooled stem output = input of layer1.0
         for i in range(len(blocks) - 1, -1, -1):
             dx = _conv_block_bwd(blocks[i], recs[i], dx, G)
             recs[i] = None
             if i in (6, 4, 2):  # a ResNet stage (2 blocks) is complete: its gradients are final
                 self._notify(G, G.end_of(blocks[i].conv1.weight))
         dc1, _ = ops.bn_backward(c1, dx, st1, self.bn1.weight, argmax=arg, dgamma=G(self.bn1.weight),
-                                 dbeta=G(self.bn1.bias))
+                                 dbeta=G(self.bn1.bias), pooled=stem_out, beta=self.bn1.bias)
         ops.stem_conv_wgrad(xs, dc1, G(self.conv1.weight), H, W)
         self._notify(G, G.total)
         return (None,), [G(p) for p in self.stage_params()]
@@ -609,11 +611,13 @@ class ResNet1D_SE(_Stage):
         dpooled = self.classifier.mlp_backward(mlp_state, dy, G)
         dx = ops.avgpool_bwd(dpooled, last_shape)
         blocks = self.blocks()
+        stem_out = recs[0][0]
         for i in range(len(blocks) - 1, -1, -1):
             dx = _conv_block_bwd(blocks[i], recs[i], dx, G)
             recs[i] = None
         bn0 = self.initial[1]
-        dc0, _ = ops.bn_backward(c0, dx, st0, bn0.weight, argmax=arg, dgamma=G(bn0.weight), dbeta=G(bn0.bias))
+        dc0, _ = ops.bn_backward(c0, dx, st0, bn0.weight, argmax=arg, dgamma=G(bn0.weight), dbeta=G(bn0.bias),
+                                 pooled=stem_out, beta=bn0.bias)
         ops.signal_stem_wgrad(sig, dc0, G(self.initial[0].weight))
         self._notify(G, G.total)
         return (None,), [G(p) for p in self.stage_params()]

@@ -262,12 +262,13 @@ def bn_relu_maxpool(x, st: BNStats, want_argmax=True):
 
 
 def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=None, want_dz=False,
-                need_param_grads=True, dgamma=None, dbeta=None, mask=None):
+                need_param_grads=True, dgamma=None, dbeta=None, mask=None, pooled=None, beta=None):
     """BatchNorm (+ReLU / +SE gate / +stem max-pool) backward.
 
     x: raw convolution output [N,H,W,C]; dy: upstream gradient (pooled-shape for the stem, mode 2);
     y: post-activation output (ReLU mask) or None; mask: the bit mask from bn_apply(want_mask=True),
-    used instead of y when given; argmax: stem pooling indices or None;
+    used instead of y when given; argmax: stem pooling indices or None; pooled (+ beta): the stem's pooled
+    output, which lets the reduction pass run in the pooled domain (mode 4) instead of gathering;
     se / se_ctx: gate [N,C] and a callable (p1, p2, split) -> q [N,C] that runs the SE backward
     between the reduction and the finalize step.
     Returns (dx, dz or None); dgamma/dbeta are written into the given fp32 buffers."""
@@ -290,8 +291,19 @@ def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=
     rd = 2.0 * N * P * C * (3 if mode == 1 else 2) if mode != 2 else 2.0 * N * P * C + 3.0 * dy.numel()
     if mode == 3:
         rd += N * P * C / 8
-    _timed(f"bn_bwd_reduce/m{mode}C{C}", rd, "ecgmm_bn_bwd_reduce", _ptr(x), _ptr(dy), _ptr(y), _ptr(argmax), _ptr(st.mean),
-           _ptr(st.invstd), _ptr(st.scale), _ptr(st.shift), _ptr(p1), _ptr(p2), N, H_, W_, C, split, mode, _s())
+    if mode == 2 and pooled is not None and beta is not None:
+        # stem: sum dz / sum dz*xhat over the pooled tensors (each pooled gradient reaches exactly one pre-pool
+        # element, whose normalised value is (y - beta) / gamma when y > 0)
+        _, Hp, Wp, _ = pooled.shape
+        split = lib.load().ecgmm_reduce_split(N, Hp * Wp, C)
+        part = _f32(2 * N * split * C, dev)
+        p1, p2 = part[: N * split * C], part[N * split * C:]
+        _timed(f"bn_bwd_reduce/m4C{C}", 4.0 * pooled.numel(), "ecgmm_bn_bwd_reduce", _ptr(pooled), _ptr(dy), None,
+               None, _ptr(beta), _ptr(gamma), None, None, _ptr(p1), _ptr(p2), N, Hp, Wp, C, split, 4, _s())
+    else:
+        _timed(f"bn_bwd_reduce/m{mode}C{C}", rd, "ecgmm_bn_bwd_reduce", _ptr(x), _ptr(dy), _ptr(y), _ptr(argmax),
+               _ptr(st.mean), _ptr(st.invstd), _ptr(st.scale), _ptr(st.shift), _ptr(p1), _ptr(p2), N, H_, W_, C, split,
+               mode, _s())
     q = None
     if se is not None:
         q = se_ctx(p1, p2, split)

@@ -138,7 +138,11 @@ int ecgmm_bn_relu_maxpool(const ecgmm_bf16* x, const float* scale, const float* 
 /* Backward partials p1/p2 [N][split][C] = sum dz, sum dz*xhat with
  *   mode 0: dz = dy;  mode 1: dz = dy * (y > 0);  mode 2: stem -- dy is the gradient of the POOLED
  *   output [N][Ho][Wo][C], routed through argmax and gated by relu(x*scale+shift) > 0;
- *   mode 3: dz = dy * bit, the `argmax` argument carrying the relu_mask written by ecgmm_bn_apply. */
+ *   mode 3: dz = dy * bit, the `argmax` argument carrying the relu_mask written by ecgmm_bn_apply;
+ *   mode 4: the stem sums evaluated in the POOLED domain (4x fewer elements, no gather): x is the pooled
+ *           output y = maxpool(relu(bn(.))), dy its gradient, H x W the pooled size, `mean` := beta and
+ *           `invstd` := gamma, so that dz = dy * (y > 0) and xhat = (y - beta) / gamma is the normalised
+ *           value of the one pre-pool element each pooled gradient is routed to. */
 int ecgmm_bn_bwd_reduce(const ecgmm_bf16* x, const ecgmm_bf16* dy, const ecgmm_bf16* y, const uint8_t* argmax,
                         const float* mean, const float* invstd, const float* scale, const float* shift, float* p1,
                         float* p2, int N, int H, int W, int C, int split, int mode, void* stream);

@@ -161,6 +161,12 @@ def test_stem_pool_forward_backward(N, H, W):
     dx, _ = ops.bn_backward(xn, nhwc(dyp), st, gamma.detach(), argmax=arg, dgamma=dg, dbeta=db)
     assert rel_l2(nchw(dx), xr.grad) < 2e-2
     assert rel_l2(dg, gamma.grad) < 1e-2 and rel_l2(db, beta.grad) < 1e-2
+    # pooled-domain reduction (mode 4): same sums from the pooled output, no gather
+    dg2, db2 = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    dx2, _ = ops.bn_backward(xn, nhwc(dyp), st, gamma.detach(), argmax=arg, dgamma=dg2, dbeta=db2, pooled=y,
+                             beta=beta.detach())
+    assert rel_l2(nchw(dx2), xr.grad) < 2e-2
+    assert rel_l2(dg2, gamma.grad) < 1e-2 and rel_l2(db2, beta.grad) < 1e-2
 
 
 def test_avgpool():
