@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
 // stem: y = maxpool3x3/s2/p1(relu(x*scale + shift)), arg = position of the maximum inside the
 // window (first maximum in row-major window order, torch's tie rule), 0..8
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(256, 4) bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ x,
                                                                const float* __restrict__ scale,
                                                                const float* __restrict__ shift,
                                                                __nv_bfloat16* __restrict__ y,
@@ -240,14 +240,19 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const __nv_bfloat1
     t /= Wo;
     const int oh = (int)(t % Ho);
     const size_t n = t / Ho;
-    float sc[8], sh[8], best[8];
-    int bi[8];
+    float sc[8], sh[8];
     load8f(scale + cg * 8, sc);
     load8f(shift + cg * 8, sh);
+    // max over the window of relu(sc*x+sh) = relu(sc*max(x)+sh) for sc > 0 and relu(sc*min(x)+sh) for sc < 0:
+    // the window scan runs on the RAW bf16 pairs (2 channels per instruction), with the sign bit flipped
+    // where sc < 0 so that one packed max serves both cases; the affine map is applied once at the end.
+    // Strict > keeps the first maximum (torch's tie rule).  (sc == 0 exactly: any element is a maximum.)
+    uint32_t flip[4], best2[4], idx2[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      best[j] = -INFINITY;
-      bi[j] = 0;
+    for (int k = 0; k < 4; ++k) {
+      flip[k] = (sc[2 * k] < 0.f ? 0x8000u : 0u) | (sc[2 * k + 1] < 0.f ? 0x80000000u : 0u);
+      best2[k] = 0xFF80FF80u;  // (-inf, -inf)
+      idx2[k] = 0u;
     }
     // all 9 window loads are issued up front with clamped coordinates (independent loads in
     // flight); out-of-image taps are masked afterwards
@@ -268,16 +273,28 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const __nv_bfloat1
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       if (!ok[t]) continue;
-      float f[8];
-      unpack8(v[t], f);
+      const uint32_t code2 = (uint32_t)t | ((uint32_t)t << 16);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float a = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-        if (a > best[j]) {
-          best[j] = a;
-          bi[j] = t;
-        }
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t xw = (k == 0 ? v[t].x : (k == 1 ? v[t].y : (k == 2 ? v[t].z : v[t].w))) ^ flip[k];
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&xw);
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&best2[k]);
+        const uint32_t m = __hgt2_mask(a, b);  // 0xFFFF per half where a > b
+        const __nv_bfloat162 mx = __hmax2(a, b);
+        best2[k] = *reinterpret_cast<const uint32_t*>(&mx);
+        idx2[k] = (idx2[k] & ~m) | (code2 & m);
       }
+    }
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t xw = best2[k] ^ flip[k];
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw));
+      best[2 * k] = fmaxf(fmaf(f.x, sc[2 * k], sh[2 * k]), 0.f);
+      best[2 * k + 1] = fmaxf(fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]), 0.f);
+      bi[2 * k] = idx2[k] & 0xffff;
+      bi[2 * k + 1] = idx2[k] >> 16;
     }
     reinterpret_cast<uint4*>(y)[i] = pack8(best);
     if (arg) {
@@ -724,7 +741,56 @@ __global__ void __launch_bounds__(kRedThreads, 2) stem_bwd_reduce_kernel(
   }
 }
 
-__global__ void __launch_bounds__(256, 2) stem_bwd_apply_kernel(
+// Routed gradient of the 4 pixels of a block for all 8 channels, as packed bf16 pairs dzw[pixel][pair]:
+// the argmax codes of 8 channels are 8 bytes, so "window t selected position K" is ONE byte-wise SIMD
+// compare per 4 channels; the byte masks are widened to 16-bit lanes and ANDed onto the bf16 gradients.
+__device__ __forceinline__ void stem_route(const StemRaw& raw, uint32_t (&dzw)[4][4]) {
+  uint32_t g[4][4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    g[t][0] = raw.vg[t].x;
+    g[t][1] = raw.vg[t].y;
+    g[t][2] = raw.vg[t].z;
+    g[t][3] = raw.vg[t].w;
+  }
+  auto sel = [&](int t, uint32_t code, uint32_t (&out)[4]) {
+    const uint32_t k4 = code * 0x01010101u;
+    const uint32_t m0 = __vcmpeq4(raw.va[t].x, k4), m1 = __vcmpeq4(raw.va[t].y, k4);
+    out[0] = g[t][0] & __byte_perm(m0, 0, 0x1100);
+    out[1] = g[t][1] & __byte_perm(m0, 0, 0x3322);
+    out[2] = g[t][2] & __byte_perm(m1, 0, 0x1100);
+    out[3] = g[t][3] & __byte_perm(m1, 0, 0x3322);
+  };
+  auto add = [](uint32_t (&acc)[4], const uint32_t (&v)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&acc[k]),
+                                       *reinterpret_cast<const __nv_bfloat162*>(&v[k]));
+      acc[k] = *reinterpret_cast<const uint32_t*>(&r);
+    }
+  };
+  uint32_t tmp[4];
+  // pixel (0,0): window 0 code 4
+  sel(0, 4, dzw[0]);
+  // pixel (0,1): window 0 code 5, window 1 code 3
+  sel(0, 5, dzw[1]);
+  sel(1, 3, tmp);
+  add(dzw[1], tmp);
+  // pixel (1,0): window 0 code 7, window 2 code 1
+  sel(0, 7, dzw[2]);
+  sel(2, 1, tmp);
+  add(dzw[2], tmp);
+  // pixel (1,1): window 0 code 8, window 1 code 6, window 2 code 2, window 3 code 0
+  sel(0, 8, dzw[3]);
+  sel(1, 6, tmp);
+  add(dzw[3], tmp);
+  sel(2, 2, tmp);
+  add(dzw[3], tmp);
+  sel(3, 0, tmp);
+  add(dzw[3], tmp);
+}
+
+__global__ void __launch_bounds__(256, 3) stem_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dyp, const uint8_t* __restrict__ arg,
     const float* __restrict__ coefA, const float* __restrict__ coefB, const float* __restrict__ coefD,
     const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ dx, int CG,
@@ -739,31 +805,35 @@ __global__ void __launch_bounds__(256, 2) stem_bwd_apply_kernel(
     const size_t n = t / Ho;
     StemRaw raw;
     stem_raw_load(x, dyp, arg, n, a, b, H, W, Ho, Wo, CG, cg, raw);
+    uint32_t dzw[4][4];
+    stem_route(raw, dzw);
     const float* A = coefA + cg * 8;
     const float* B = coefB + cg * 8;
     const float* D = coefD + cg * 8;
     const float* sc = scale + cg * 8;
     const float* sh = shift + cg * 8;
-    uint32_t o[4][4];  // packed bf16x2 output words, [pixel][pair]
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float xv[4][2], dz[4][2];
-      stem_pair(raw, k, sc, sh, xv, dz);
-      const float2 Ak = *reinterpret_cast<const float2*>(A + 2 * k);
-      const float2 Bk = *reinterpret_cast<const float2*>(B + 2 * k);
-      const float2 Dk = *reinterpret_cast<const float2*>(D + 2 * k);
-#pragma unroll
-      for (int px = 0; px < 4; ++px) {
-        const __nv_bfloat162 v = __floats2bfloat162_rn(fmaf(Ak.x, dz[px][0], fmaf(Bk.x, xv[px][0], Dk.x)),
-                                                      fmaf(Ak.y, dz[px][1], fmaf(Bk.y, xv[px][1], Dk.y)));
-        o[px][k] = *reinterpret_cast<const uint32_t*>(&v);
-      }
-    }
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
       if (!raw.ok[px]) continue;
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t xw = word_of(raw.vx[px], k);
+        const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw));
+        float2 fz = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dzw[px][k]));
+        const float2 s2 = *reinterpret_cast<const float2*>(sc + 2 * k);
+        const float2 h2 = *reinterpret_cast<const float2*>(sh + 2 * k);
+        if (fmaf(fx.x, s2.x, h2.x) <= 0.f) fz.x = 0.f;  // ReLU gate of the pre-pool activation
+        if (fmaf(fx.y, s2.y, h2.y) <= 0.f) fz.y = 0.f;
+        const float2 Ak = *reinterpret_cast<const float2*>(A + 2 * k);
+        const float2 Bk = *reinterpret_cast<const float2*>(B + 2 * k);
+        const float2 Dk = *reinterpret_cast<const float2*>(D + 2 * k);
+        const __nv_bfloat162 v = __floats2bfloat162_rn(fmaf(Ak.x, fz.x, fmaf(Bk.x, fx.x, Dk.x)),
+                                                      fmaf(Ak.y, fz.y, fmaf(Bk.y, fx.y, Dk.y)));
+        o[k] = *reinterpret_cast<const uint32_t*>(&v);
+      }
       const int h = 2 * a + (px >> 1), w = 2 * b + (px & 1);
-      reinterpret_cast<uint4*>(dx)[((n * H + h) * W + w) * CG + cg] = make_uint4(o[px][0], o[px][1], o[px][2], o[px][3]);
+      reinterpret_cast<uint4*>(dx)[((n * H + h) * W + w) * CG + cg] = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
