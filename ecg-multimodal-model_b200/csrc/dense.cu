@@ -11,71 +11,84 @@ namespace ecgmm {
 // ------------------------------------------------------------------------------------------
 // C[M][N] (+)= op(A) * op(B) (+ bias[N]) (relu)
 //   ta == 0: A is [M][K] row-major, ta == 1: A is [K][M];  tb == 0: B is [K][N], tb == 1: B is [N][K].
-// 64x64 tile, 256 threads, 4x4 outputs per thread, K step 16.
+// T x T tile (T = 64: 4x4 outputs per thread, K step 16;  T = 32: 2x2 outputs, K step 32), 256 threads.
+// These GEMMs are latency-bound (a handful of CTAs, K <= 768): the next K slab is fetched into registers
+// while the current one is multiplied, and the host picks T = 32 whenever 64x64 tiles would leave most
+// SMs without a CTA (batch 64: Linear(768,128) is 2 CTAs of 64x64 but 8 of 32x32).
 // ------------------------------------------------------------------------------------------
+template <int T>
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                      float* __restrict__ C, const float* __restrict__ bias, int M,
                                                      int N, int K, int ta, int tb, int accumulate, int relu) {
-  __shared__ float As[16][65];
-  __shared__ float Bs[16][65];
+  constexpr int KS = 1024 / T;  // K extent of one slab: 1024 elements per operand, 4 per thread
+  constexpr int R = T / 16;     // outputs per thread per dimension
+  __shared__ float As[KS][T + 1];
+  __shared__ float Bs[KS][T + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  float acc[4][4];
+  const int m0 = blockIdx.y * T, n0 = blockIdx.x * T;
+  float acc[R][R];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-      int kk, mm;
-      if (ta) {
-        kk = e >> 6;
-        mm = e & 63;
-      } else {
-        mm = e >> 4;
-        kk = e & 15;
-      }
-      const int m = m0 + mm, k = k0 + kk;
-      float v = 0.f;
-      if (m < M && k < K) v = ta ? A[(size_t)k * M + m] : A[(size_t)m * K + k];
-      As[kk][mm] = v;
+    for (int j = 0; j < R; ++j) acc[i][j] = 0.f;
+  // element e of a slab -> (k, row): the fastest-varying index follows the operand's contiguous dimension
+  auto coord = [](int e, int transposed_k_major, int& kk, int& rr) {
+    if (transposed_k_major) {
+      kk = e / T;
+      rr = e % T;
+    } else {
+      rr = e / KS;
+      kk = e % KS;
     }
-    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-      int kk, nn;
-      if (tb) {
-        nn = e >> 4;
-        kk = e & 15;
-      } else {
-        kk = e >> 6;
-        nn = e & 63;
-      }
-      const int n = n0 + nn, k = k0 + kk;
-      float v = 0.f;
-      if (n < N && k < K) v = tb ? B[(size_t)n * K + k] : B[(size_t)k * N + n];
-      Bs[kk][nn] = v;
+  };
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = threadIdx.x + u * 256;
+      int kk, rr;
+      coord(e, ta, kk, rr);
+      const int m = m0 + rr, k = k0 + kk;
+      ra[u] = (m < M && k < K) ? (ta ? A[(size_t)k * M + m] : A[(size_t)m * K + k]) : 0.f;
+      coord(e, !tb, kk, rr);
+      const int n = n0 + rr, k2 = k0 + kk;
+      rb[u] = (n < N && k2 < K) ? (tb ? B[(size_t)n * K + k2] : B[(size_t)k2 * N + n]) : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += KS) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = threadIdx.x + u * 256;
+      int kk, rr;
+      coord(e, ta, kk, rr);
+      As[kk][rr] = ra[u];
+      coord(e, !tb, kk, rr);
+      Bs[kk][rr] = rb[u];
     }
     __syncthreads();
+    if (k0 + KS < K) fetch(k0 + KS);  // in flight during the multiply below
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      float a[4], b[4];
+    for (int kk = 0; kk < KS; ++kk) {
+      float a[R], b[R];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < R; ++i) a[i] = As[kk][ty * R + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+      for (int j = 0; j < R; ++j) b[j] = Bs[kk][tx * R + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < R; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < R; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < R; ++i) {
+    const int m = m0 + ty * R + i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < R; ++j) {
+      const int n = n0 + tx * R + j;
       if (n >= N) continue;
       float v = acc[i][j];
       if (bias) v += bias[n];
@@ -610,9 +623,14 @@ extern "C" int ecgmm_sgemm(const float* A, const float* B, float* C, const float
   ECGMM_CHECK(A && B && C, ECGMM_ERR_ARG, "sgemm: null pointer");
   ECGMM_CHECK(M >= 0 && N >= 0 && K >= 0, ECGMM_ERR_SHAPE, "sgemm: negative extent");
   if (M == 0 || N == 0) return ECGMM_OK;
-  dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+  const bool small = (long long)ceil_div(N, 64) * ceil_div(M, 64) < 2LL * num_sms();
+  const int T = small ? 32 : 64;
+  dim3 grid(ceil_div(N, T), ceil_div(M, T));
   ECGMM_CHECK(grid.y <= 65535, ECGMM_ERR_SHAPE, "sgemm: M=%d too large", M);
-  sgemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, bias, M, N, K, transA, transB, accumulate, relu);
+  if (small)
+    sgemm_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, bias, M, N, K, transA, transB, accumulate, relu);
+  else
+    sgemm_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, bias, M, N, K, transA, transB, accumulate, relu);
   return check_launch("sgemm_kernel");
 }
 

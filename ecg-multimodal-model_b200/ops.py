@@ -15,7 +15,8 @@ BF16 = torch.bfloat16
 
 
 def _ptr(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    # a plain int is accepted for a c_void_p parameter (the prototypes are attached in lib.load()); no wrapper object
+    return None if t is None else t.data_ptr()
 
 
 def _chk(t: torch.Tensor, dtype, name: str):
@@ -27,8 +28,14 @@ def _chk(t: torch.Tensor, dtype, name: str):
         raise lib.EcgmmError(f"{name} must be contiguous")
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream
+_cur_device = torch._C._cuda_getDevice
+
+
 def _s():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """cudaStream_t of torch's current stream on the current device (two C calls; torch.cuda.current_stream()
+    builds a Python Stream object through ~10 Python frames, which was a quarter of the host time of a step)."""
+    return _raw_stream(_cur_device())
 
 
 # When bench.py sets PROFILE to a list, every convolution call is bracketed by CUDA events on the
@@ -45,6 +52,18 @@ def _timed(kind, flops, name, *args):
     lib.call(name, *args)
     e1.record()
     PROFILE.append((kind, flops, e0, e1))
+
+
+# Pure shape queries of the library (no launch): asked once per shape, then served from a dict.
+_SHAPE_CACHE = {}
+
+
+def _shape_query(name, *shape):
+    key = (name, shape)
+    v = _SHAPE_CACHE.get(key)
+    if v is None:
+        v = _SHAPE_CACHE[key] = int(getattr(lib.load(), name)(*shape))
+    return v
 
 
 # ---------------------------------------------------------------- layout
@@ -126,7 +145,7 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, R: int, S:
     N, H, W, Cin = x.shape
     Cout = dy.shape[3]
     assert dw.numel() == Cout * Cin * R * S
-    ws_bytes = lib.load().ecgmm_conv2d_wgrad_workspace(N, H, W, Cin, Cout, R, S, stride, R // 2, S // 2)
+    ws_bytes = _shape_query("ecgmm_conv2d_wgrad_workspace", N, H, W, Cin, Cout, R, S, stride, R // 2, S // 2)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
     _timed(f"conv_wgrad/{Cin}x{Cout}k{R}{S}s{stride}", 2.0 * N * dy.shape[1] * dy.shape[2] * Cout * Cin * R * S,
            "ecgmm_conv2d_wgrad", _ptr(x), _ptr(dy), _ptr(dw), N, H, W, Cin, Cout, R, S, stride, R // 2, S // 2, _ptr(ws),
@@ -211,7 +230,7 @@ def bn_train_stats(x, gamma, beta, running_mean, running_var, num_batches, eps, 
     _chk(x, BF16, "x")
     N, P, C = _npc(x)
     dev = x.device
-    split = lib.load().ecgmm_reduce_split(N, P, C)
+    split = _shape_query("ecgmm_reduce_split", N, P, C)
     part = _f32(2 * N * split * C, dev)
     psum, psq = part[: N * split * C], part[N * split * C:]
     _timed(f"bn_stats/C{C}", 2.0 * N * P * C, "ecgmm_chan_stats", _ptr(x), _ptr(psum), _ptr(psq), N, P, C, split, _s())
@@ -284,7 +303,7 @@ def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=
     mode = 2 if argmax is not None else (3 if mask is not None else (1 if y is not None else 0))
     if mode == 3:
         argmax, y = mask, None  # the C ABI carries the bit mask in the argmax slot
-    split = lib.load().ecgmm_reduce_split(N, P, C)
+    split = _shape_query("ecgmm_reduce_split", N, P, C)
     part = _f32(2 * N * split * C, dev)
     p1, p2 = part[: N * split * C], part[N * split * C:]
     # algorithmic bytes of the two backward passes: x + (dy | pooled dy + argmax) [+ y]; the apply pass also writes dx [+ dz]
@@ -295,7 +314,7 @@ def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=
         # stem: sum dz / sum dz*xhat over the pooled tensors (each pooled gradient reaches exactly one pre-pool
         # element, whose normalised value is (y - beta) / gamma when y > 0)
         _, Hp, Wp, _ = pooled.shape
-        split = lib.load().ecgmm_reduce_split(N, Hp * Wp, C)
+        split = _shape_query("ecgmm_reduce_split", N, Hp * Wp, C)
         part = _f32(2 * N * split * C, dev)
         p1, p2 = part[: N * split * C], part[N * split * C:]
         _timed(f"bn_bwd_reduce/m4C{C}", 4.0 * pooled.numel(), "ecgmm_bn_bwd_reduce", _ptr(pooled), _ptr(dy), None,

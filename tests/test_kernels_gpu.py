@@ -197,7 +197,8 @@ def test_signal_stem(B, Cin, L):
 
 
 # ------------------------------------------------------------------ dense kernels
-@pytest.mark.parametrize("M,N,K", [(5, 2, 128), (512, 256, 512), (37, 64, 24), (130, 128, 768)])
+@pytest.mark.parametrize("M,N,K", [(5, 2, 128), (512, 256, 512), (37, 64, 24), (130, 128, 768),
+                                   (4100, 330, 70)])  # the last one is large enough for the 64x64-tile variant
 def test_linear(M, N, K):
     g = gen(f"lin{M}{N}{K}")
     x = torch.randn(M, K, generator=g).to(DEV).requires_grad_(True)
