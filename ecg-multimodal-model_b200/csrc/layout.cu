@@ -68,6 +68,14 @@ __global__ void stem_weight_prep_kernel(const float* __restrict__ w, __nv_bfloat
   ws[idx] = __float2bfloat16(v);
 }
 
+__device__ __forceinline__ float load_pixel(const float* p) { return *p; }
+__device__ __forceinline__ float load_pixel(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+// uint8 pixels: torchvision ToTensor (u / 255) followed by Normalize(mean 0.5, std 0.5), the transform of
+// dataset.py:119-123, in the same fp32 operation order (so the value equals the reference's tensor element)
+__device__ __forceinline__ float load_pixel(const uint8_t* p) {
+  return __fdiv_rn(__fsub_rn(__fdiv_rn((float)*p, 255.f), 0.5f), 0.5f);
+}
+
 // xs[n][a][b][(dr*2+ds)*3+c] = x[n][c][2a+dr-3][2b+ds-3]  (zero outside the image, channels 12..15 zero)
 template <typename T>
 __global__ void stem_s2d_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ xs, int H, int W, int Hs,
@@ -87,7 +95,7 @@ __global__ void stem_s2d_kernel(const T* __restrict__ x, __nv_bfloat16* __restri
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         float f = 0.f;
-        if (in) f = static_cast<float>(xn[((size_t)c * H + ih) * W + iw]);
+        if (in) f = load_pixel(xn + ((size_t)c * H + ih) * W + iw);
         v[(dr * 2 + ds) * 3 + c] = __float2bfloat16(f);
       }
     }
@@ -145,15 +153,19 @@ extern "C" int ecgmm_stem_weight_prep(const float* w, ecgmm_bf16* w_s2d, void* s
   return check_launch("stem_weight_prep_kernel");
 }
 
-extern "C" int ecgmm_stem_s2d(const void* x, int x_is_bf16, ecgmm_bf16* xs, int N, int H, int W, void* stream) {
+extern "C" int ecgmm_stem_s2d(const void* x, int x_dtype, ecgmm_bf16* xs, int N, int H, int W, void* stream) {
   ECGMM_CHECK(x && xs, ECGMM_ERR_ARG, "stem_s2d: null pointer");
+  ECGMM_CHECK(x_dtype >= 0 && x_dtype <= 2, ECGMM_ERR_ARG, "stem_s2d: x_dtype %d (0 fp32, 1 bf16, 2 uint8)", x_dtype);
   if (N == 0) return ECGMM_OK;
   int Hs, Ws;
   ecgmm_stem_s2d_dims(H, W, &Hs, &Ws);
   ECGMM_CHECK(Hs <= 65535 && N <= 65535, ECGMM_ERR_SHAPE, "stem_s2d: image too tall / batch too large");
   dim3 grid(ceil_div(Ws, 128), Hs, N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (x_is_bf16)
+  if (x_dtype == 2)
+    stem_s2d_kernel<uint8_t><<<grid, 128, 0, st>>>(reinterpret_cast<const uint8_t*>(x),
+                                                   reinterpret_cast<__nv_bfloat16*>(xs), H, W, Hs, Ws);
+  else if (x_dtype == 1)
     stem_s2d_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
                                                         reinterpret_cast<__nv_bfloat16*>(xs), H, W, Hs, Ws);
   else

@@ -1,0 +1,91 @@
+"""Batched perturbation inference of the fusion head (BASELINE.json configs[3]).
+
+The reference's explainers (shap_fusion_modal_balance.py:100-160, lime_fusion_modal_balance.py:101-160) push
+thousands of perturbed copies of one fused embedding through `fusion_classifier`, a few at a time through
+torch.nn on the host's schedule.  Here all V masked variants of all S samples go through ONE tensor-core GEMM:
+
+    variant[s][v] = z[v] * e[s] + (1 - z[v]) * background          z[v] in {0,1}^D
+    prob[s][v]    = softmax(fusion_classifier(variant[s][v]))[class_index]
+
+`fusion_classifier` is the model's MLPHead (Linear(D,128) -> ReLU -> Dropout -> Linear(128,C)); inference
+runs in eval semantics (dropout = identity) whatever the module's mode, like the explainers (model.eval()).
+Operands of the first Linear are bf16 (fp32 accumulation); bias, ReLU, the second Linear and the softmax are
+fp32.  Sharding over GPUs: samples are independent -- give each rank its slice of `e` (parallel.shard_batch);
+there is no collective on this path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import lib, ops
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _head_weights(head):
+    """(w1 bf16 [HID][1][1][D], b1, w2, b2) of an MLPHead, the bf16 copy cached on the module per weight version."""
+    lin1, lin2 = head.lin1, head.lin2
+    w = lin1.weight
+    key = (w.data_ptr(), w._version)
+    if head.__dict__.get("_perturb_key") != key:
+        w1 = w.detach().to(BF16).contiguous().view(w.shape[0], 1, 1, w.shape[1])
+        head.__dict__["_perturb_w1"] = w1
+        head.__dict__["_perturb_key"] = key
+    return head.__dict__["_perturb_w1"], lin1.bias.detach(), lin2.weight.detach(), lin2.bias.detach()
+
+
+def masked_variants(e: torch.Tensor, background: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+    """e [S,D] fp32, background [D] fp32, masks [V,D] uint8/bool -> variants [S,V,D] bf16."""
+    for t, name in ((e, "e"), (background, "background"), (masks, "masks")):
+        if not t.is_cuda:
+            raise lib.EcgmmError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if e.dim() != 2 or background.dim() != 1 or masks.dim() != 2 or not (e.shape[1] == background.shape[0] == masks.shape[1]):
+        raise lib.EcgmmError(f"shapes must be e [S,D], background [D], masks [V,D]; got {tuple(e.shape)}, "
+                             f"{tuple(background.shape)}, {tuple(masks.shape)}")
+    S, D = e.shape
+    V = masks.shape[0]
+    if masks.dtype == torch.bool:
+        masks = masks.view(torch.uint8)
+    if masks.dtype != torch.uint8:
+        raise lib.EcgmmError(f"masks must be uint8 or bool, got {masks.dtype}")
+    e = e.detach().to(F32).contiguous()
+    background = background.detach().to(F32).contiguous()
+    masks = masks.contiguous()
+    out = torch.empty((S, V, D), dtype=BF16, device=e.device)
+    lib.call("ecgmm_perturb_build", ops._ptr(e), ops._ptr(background), ops._ptr(masks), ops._ptr(out), S, V, D,
+             ops._s())
+    return out
+
+
+def head_inference(head, x_bf16: torch.Tensor, class_index: int = 1) -> torch.Tensor:
+    """x [rows, D] bf16 -> softmax(fusion_classifier(x))[:, class_index] fp32 (class_index < 0: the logits)."""
+    ops._chk(x_bf16, BF16, "x")
+    rows, D = x_bf16.shape
+    w1, b1, w2, b2 = _head_weights(head)
+    HID, C = w1.shape[0], w2.shape[0]
+    if w1.shape[3] != D:
+        raise lib.EcgmmError(f"embedding width {D} does not match fusion_classifier[0] ({w1.shape[3]})")
+    hidden = ops.conv2d_fwd(x_bf16.view(1, 1, rows, D), w1, 1).view(rows, HID)
+    out = torch.empty((rows,) if class_index >= 0 else (rows, C), dtype=F32, device=x_bf16.device)
+    lib.call("ecgmm_head_tail", ops._ptr(hidden), ops._ptr(b1), ops._ptr(w2), ops._ptr(b2), ops._ptr(out), rows, HID,
+             C, int(class_index), ops._s())
+    return out
+
+
+def perturbation_inference(fusion_classifier, e, background, masks, class_index: int = 1, chunk_samples: int = 0):
+    """prob [S, V] (or logits [S, V, C] when class_index < 0) for all masked variants of all samples.
+
+    chunk_samples bounds the bf16 variant buffer (S*V*D*2 bytes; 6.3 MB per sample at V=4096, D=768):
+    0 = as many samples per launch as fit in ~4 GB."""
+    S, D = e.shape
+    V = masks.shape[0]
+    if chunk_samples <= 0:
+        chunk_samples = max(1, (4 << 30) // max(1, V * D * 2))
+    outs = []
+    for s0 in range(0, S, chunk_samples):
+        es = e[s0:s0 + chunk_samples]
+        x = masked_variants(es, background, masks)
+        out = head_inference(fusion_classifier, x.view(-1, D), class_index)
+        outs.append(out.view(es.shape[0], V) if class_index >= 0 else out.view(es.shape[0], V, -1))
+    return outs[0] if len(outs) == 1 else torch.cat(outs, 0)

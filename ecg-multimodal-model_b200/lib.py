@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_int, c_void_p, c_float, c_longlong, c_ulonglong, c_char_p, POINTER
+from ctypes import c_int, c_void_p, c_float, c_double, c_longlong, c_ulonglong, c_char_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libecgmm.so")
@@ -16,6 +16,7 @@ _p = c_void_p
 _i = c_int
 _f = c_float
 _ll = c_longlong
+_d = c_double
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 SIGNATURES = {
@@ -66,6 +67,11 @@ SIGNATURES = {
     "ecgmm_dropout_fwd": [_p, _p, _p, _p, _ll, _f, c_ulonglong, _p],
     "ecgmm_mask_bwd": [_p, _p, _p, _p, _ll, _p],
     "ecgmm_zscore": [_p, _p, _ll, _i, _f, _p],
+    "ecgmm_butter_lowpass": [_i, _d, POINTER(c_double), POINTER(c_double), POINTER(c_double)],
+    "ecgmm_signal_preprocess_workspace": [_ll, _i, _i],
+    "ecgmm_signal_preprocess": [_p, _i, _p, _p, _ll, _ll, _i, _i, _i, _d, _i, _d, _p],
+    "ecgmm_perturb_build": [_p, _p, _p, _p, _ll, _i, _i, _p],
+    "ecgmm_head_tail": [_p, _p, _p, _p, _p, _ll, _i, _i, _i, _p],
     "ecgmm_bn_rows_fwd": [_p] * 9 + [_i, _i, _f, _f, _i, _i, _p],
     "ecgmm_bn_rows_bwd": [_p] * 9 + [_i, _i, _i, _p],
     # optimizer
@@ -73,7 +79,7 @@ SIGNATURES = {
     "ecgmm_adam_step": [_p, _i, _f, _f, _f, _f, _f, _ll, _f, _p],
 }
 _RESTYPES = {"ecgmm_last_error": c_char_p, "ecgmm_stem_s2d_dims": None, "ecgmm_launch_count": c_ulonglong,
-             "ecgmm_conv2d_wgrad_workspace": c_longlong}
+             "ecgmm_conv2d_wgrad_workspace": c_longlong, "ecgmm_signal_preprocess_workspace": c_longlong}
 
 
 class EcgmmError(RuntimeError):

@@ -160,16 +160,17 @@ def stem_s2d_dims(H: int, W: int):
 
 
 def stem_s2d(x: torch.Tensor) -> torch.Tensor:
-    """NCHW image (fp32 or bf16, 3 channels) -> space-to-depth staging buffer [N][Hs][Ws][16] bf16."""
-    if x.dtype not in (torch.float32, BF16):
-        raise lib.EcgmmError(f"image must be fp32 or bf16, got {x.dtype}")
+    """NCHW image (3 channels; fp32 / bf16 normalised, or uint8 raw pixels that get ToTensor + Normalize(0.5, 0.5)
+    applied on the fly) -> space-to-depth staging buffer [N][Hs][Ws][16] bf16."""
+    if x.dtype not in (torch.float32, BF16, torch.uint8):
+        raise lib.EcgmmError(f"image must be fp32, bf16 or uint8, got {x.dtype}")
     _chk(x, x.dtype, "image")
     N, C, H, W = x.shape
     if C != 3:
         raise lib.EcgmmError(f"image must have 3 channels, got {C}")
     Hs, Ws = stem_s2d_dims(H, W)
     xs = torch.empty((N, Hs, Ws, 16), dtype=BF16, device=x.device)
-    lib.call("ecgmm_stem_s2d", _ptr(x), int(x.dtype == BF16), _ptr(xs), N, H, W, _s())
+    lib.call("ecgmm_stem_s2d", _ptr(x), {torch.float32: 0, BF16: 1, torch.uint8: 2}[x.dtype], _ptr(xs), N, H, W, _s())
     return xs
 
 

@@ -66,8 +66,11 @@ int ecgmm_conv_weight_prep(const float* w_oihw, ecgmm_bf16* w_fwd, ecgmm_bf16* w
 
 /* geometry of the space-to-depth buffer for an H x W image: rows, cols (16 channels each) */
 void ecgmm_stem_s2d_dims(int H, int W, int* Hs, int* Ws);
-/* image NCHW (3 channels; fp32 if x_is_bf16 == 0, else bf16) -> xs [N][Hs][Ws][16] bf16 */
-int ecgmm_stem_s2d(const void* x, int x_is_bf16, ecgmm_bf16* xs, int N, int H, int W, void* stream);
+/* image NCHW (3 channels) -> xs [N][Hs][Ws][16] bf16.  x_dtype: 0 = fp32, 1 = bf16 (already normalised tensors,
+ * what dataset.py:119-123 yields), 2 = uint8 raw pixels: torchvision ToTensor (u/255) + Normalize(0.5, 0.5) of
+ * dataset.py:119-123 are applied on the fly in fp32, so a batch can cross PCIe at 1 byte per pixel value
+ * (SURVEY.md section 8f rank 2). */
+int ecgmm_stem_s2d(const void* x, int x_dtype, ecgmm_bf16* xs, int N, int H, int W, void* stream);
 /* w [64][3][7][7] fp32 -> w_s2d [64][4][4][16] bf16 */
 int ecgmm_stem_weight_prep(const float* w, ecgmm_bf16* w_s2d, void* stream);
 /* y [N][Ho][Wo][64] bf16, Ho = (H+6-7)/2+1 */
@@ -225,6 +228,39 @@ int ecgmm_bn_rows_bwd(const float* x, const float* dy, const float* y, const flo
                       const float* invstd, float* dx, float* dgamma, float* dbeta, int B, int C, int relu,
                       void* stream);
 int ecgmm_zscore(const float* x, float* y, long long rows, int L, float eps, void* stream);
+
+/* ------------------------------------------------------------------ signal preprocessing
+ * What the reference does per sample on the host inside Dataset.__getitem__ (dataset.py:76-95; identical
+ * copies signal_model.py:203-224, evaluation_signal.py:20-39), batched over `rows` signals of length L:
+ *   window > 0 : remove_baseline_drift -- x - np.convolve(x, ones(window)/window, mode='same')   dataset.py:81-83
+ *   order  > 0 : lowpass_filter -- scipy.signal.butter(order, wn, 'low') + filtfilt(b, a, x)
+ *                (odd extension by 3*(order+1) samples, lfilter_zi initial state)              dataset.py:85-89
+ *   zscore     : z_score_normalize -- (x - mean) / (std_population + eps)                      dataset.py:76-79
+ * in that order, all in float64 like the reference; the float32 result is what dataset.py:68 builds.
+ * x: [rows][L] float32 (x_is_f64 = 0) or float64 (1); y: [rows][L] float32; wn = cutoff / (0.5 * fs).
+ * workspace: ecgmm_signal_preprocess_workspace(rows, L, order) bytes of device scratch (8-byte aligned).
+ * ecgmm_butter_lowpass is the HOST-side filter design used by the launch (b, a: order+1 doubles, zi: order
+ * doubles, host pointers); it touches no device and is exported for tests / callers that want the taps. */
+int ecgmm_butter_lowpass(int order, double wn, double* b, double* a, double* zi);
+long long ecgmm_signal_preprocess_workspace(long long rows, int L, int order);
+int ecgmm_signal_preprocess(const void* x, int x_is_f64, float* y, void* workspace, long long workspace_bytes,
+                            long long rows, int L, int window, int order, double wn, int zscore, double eps,
+                            void* stream);
+
+/* ------------------------------------------------------------------ batched perturbation inference
+ * BASELINE.json configs[3] / SURVEY.md section 8d cfg4: V masked variants per sample of the fused embedding,
+ *     variant[s][v][d] = masks[v][d] ? e[s][d] : bg[d]            (masks: V x D bytes, shared by all samples)
+ * through fusion_classifier (multimodal_paper_modal_balance.py:283-289; driven by
+ * shap_fusion_modal_balance.py:135,159 and lime_fusion_modal_balance.py:118-160) in eval mode.
+ *   ecgmm_perturb_build : e [S][D] fp32, bg [D] fp32, masks [V][D] uint8 -> variants [S*V][D] bf16  (D % 8 == 0)
+ *   (GEMM)              : ecgmm_conv2d_fwd(variants as N=1,H=1,W=S*V,Cin=D; w_fwd = Linear(D,HID).weight as
+ *                         [HID][1][1][D] bf16) -> hidden [S*V][HID] bf16 on the tcgen05 implicit-GEMM kernel
+ *   ecgmm_head_tail     : relu(hidden + b1) -> Linear(HID, C) (w2 [C][HID], b2 [C], fp32) ->
+ *                         out[row] = softmax(logits)[cls]  (cls >= 0)   or   out[row][0..C) = logits (cls < 0) */
+int ecgmm_perturb_build(const float* e, const float* bg, const uint8_t* masks, ecgmm_bf16* variants, long long S,
+                        int V, int D, void* stream);
+int ecgmm_head_tail(const ecgmm_bf16* hidden, const float* b1, const float* w2, const float* b2, float* out,
+                    long long rows, int HID, int C, int cls, void* stream);
 
 /* ------------------------------------------------------------------ optimizer
  * torch.optim.Adam step (train.py:43,81).  chunk_table: device array of

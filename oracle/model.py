@@ -251,3 +251,18 @@ def freeze_encoders(model):
     for enc in (model.image_encoder, model.signal_encoder, model.clinical_encoder):
         for p in enc.parameters():
             p.requires_grad = False
+
+
+def perturbation_inference(fusion_classifier, e, background, masks, class_index=1):
+    """configs[3] / SURVEY.md section 8d cfg4 in plain fp32 torch: every masked variant of every sample's fused
+    embedding, z*e + (1-z)*background, through fusion_classifier in eval mode (what the explainers of
+    shap_fusion_modal_balance.py:135,159 / lime_fusion_modal_balance.py:118-160 evaluate row by row), reduced to
+    softmax(logits)[..., class_index] (class_index < 0: logits).  e [S,D], background [D], masks [V,D] in {0,1}."""
+    was_training = fusion_classifier.training
+    fusion_classifier.eval()
+    with torch.no_grad():
+        z = masks.to(e.dtype)
+        variants = z.unsqueeze(0) * e.unsqueeze(1) + (1.0 - z).unsqueeze(0) * background.view(1, 1, -1)
+        logits = fusion_classifier(variants.reshape(-1, e.shape[1])).view(e.shape[0], masks.shape[0], -1)
+    fusion_classifier.train(was_training)
+    return logits if class_index < 0 else F.softmax(logits, dim=-1)[..., class_index]

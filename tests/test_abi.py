@@ -30,7 +30,7 @@ def ctype_of(param: str):
         return "ptr"
     t = param.rsplit(" ", 1)[0].strip()
     return {"int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong,
-            "unsigned long long": ctypes.c_ulonglong}[t]
+            "unsigned long long": ctypes.c_ulonglong, "double": ctypes.c_double}[t]
 
 
 def test_header_parses_all_entry_points():

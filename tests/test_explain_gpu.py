@@ -1,0 +1,75 @@
+"""GPU: batched perturbation inference of the fusion head (configs[3]) on the tcgen05 GEMM path against the
+fp32 oracle.  Tolerance: the first Linear runs with bf16 operands (fp32 accumulation) and a bf16 hidden
+activation, everything after it in fp32: |p - p_ref| <= 1e-2 on probabilities, logits within OUT_TOL."""
+import pytest
+import torch
+
+from ecgmm import explain, lib
+from oracle import model as om
+from parity_util import OUT_TOL, build_pair, relmax
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _case(S, V, D=768, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    e = torch.randn(S, D, generator=g)
+    bg = torch.randn(100, D, generator=g).mean(0)  # mean of 100 background embeddings
+    masks = (torch.rand(V, D, generator=g) < 0.5).to(torch.uint8)
+    return e, bg, masks
+
+
+@pytest.mark.parametrize("S,V", [(3, 256), (1, 4096), (5, 130)])
+def test_perturbation_inference_matches_oracle(S, V):
+    ora, dut = build_pair(seed=7)
+    e, bg, masks = _case(S, V, seed=S * 1000 + V)
+    ref_p = om.perturbation_inference(ora.fusion_classifier, e, bg, masks, 1)
+    ref_l = om.perturbation_inference(ora.fusion_classifier, e, bg, masks, -1)
+    p = explain.perturbation_inference(dut.fusion_classifier, e.to(DEV), bg.to(DEV), masks.to(DEV), 1)
+    l = explain.perturbation_inference(dut.fusion_classifier, e.to(DEV), bg.to(DEV), masks.to(DEV), -1)
+    assert p.shape == (S, V) and l.shape == (S, V, 2)
+    assert (p.cpu() - ref_p).abs().max().item() <= 1e-2
+    assert relmax(l, ref_l) <= OUT_TOL
+    margin = (ref_l[..., 1] - ref_l[..., 0]).abs() > 2 * OUT_TOL * max(1.0, ref_l.abs().max().item())
+    assert torch.equal(l.cpu().argmax(-1)[margin], ref_l.argmax(-1)[margin])
+
+
+def test_variants_are_exact_selections():
+    e, bg, masks = _case(4, 64, D=768, seed=11)
+    x = explain.masked_variants(e.to(DEV), bg.to(DEV), masks.to(DEV)).cpu()
+    want = torch.where(masks.bool().unsqueeze(0), e.unsqueeze(1), bg.view(1, 1, -1)).to(torch.bfloat16)
+    assert torch.equal(x, want)
+    xb = explain.masked_variants(e.to(DEV), bg.to(DEV), masks.bool().to(DEV)).cpu()
+    assert torch.equal(xb, want)
+
+
+def test_endpoints_and_chunking():
+    """All-ones masks reproduce the model's own fusion logits for e; all-zeros give the background's; chunked
+    evaluation equals the single-launch one bit for bit."""
+    _, dut = build_pair(seed=7)
+    dut.eval()
+    e, bg, _ = _case(6, 8, seed=3)
+    masks = torch.zeros(2, 768, dtype=torch.uint8)
+    masks[1] = 1
+    l = explain.perturbation_inference(dut.fusion_classifier, e.to(DEV), bg.to(DEV), masks.to(DEV), -1)
+    with torch.no_grad():
+        own_e = dut.fusion_classifier(e.to(DEV))
+        own_b = dut.fusion_classifier(bg.to(DEV).view(1, -1))
+    assert relmax(l[:, 1], own_e) <= OUT_TOL
+    assert relmax(l[:, 0], own_b.expand(6, -1)) <= OUT_TOL
+    e2, bg2, m2 = _case(7, 96, seed=5)
+    a = explain.perturbation_inference(dut.fusion_classifier, e2.to(DEV), bg2.to(DEV), m2.to(DEV), 1)
+    b = explain.perturbation_inference(dut.fusion_classifier, e2.to(DEV), bg2.to(DEV), m2.to(DEV), 1, chunk_samples=2)
+    assert torch.equal(a, b)
+
+
+def test_argument_errors():
+    _, dut = build_pair(seed=7)
+    e, bg, masks = _case(2, 8)
+    with pytest.raises(lib.EcgmmError):
+        explain.perturbation_inference(dut.fusion_classifier, e, bg, masks)  # CPU tensors
+    with pytest.raises(lib.EcgmmError):
+        explain.masked_variants(e.to(DEV), bg[:100].to(DEV), masks.to(DEV))
+    with pytest.raises(lib.EcgmmError):
+        explain.masked_variants(e.to(DEV), bg.to(DEV), masks.to(DEV).float())

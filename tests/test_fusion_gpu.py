@@ -223,3 +223,21 @@ def test_state_dict_roundtrip_on_device():
     assert len(sd) == 229 and sd["image_encoder.bn1.num_batches_tracked"].dtype == torch.int64
     ora = make_oracle(seed=99)
     ora.load_state_dict(sd, strict=True)
+
+
+def test_uint8_images_equal_normalised_tensors():
+    """raw uint8 pixels fed to forward() give exactly what the reference's
+    ToTensor + Normalize(0.5, 0.5) tensors (dataset.py:119-123) give, and agree with the oracle on them."""
+    ora, dut = build_pair(seed=7)
+    ora.eval()
+    dut.eval()
+    _, ecg, clin, _ = make_inputs(9, 3, 64, 160, 600)
+    u8 = torch.randint(0, 256, (3, 3, 64, 160), generator=torch.Generator().manual_seed(3), dtype=torch.uint8)
+    norm = ((u8.float() / 255.0) - 0.5) / 0.5
+    with torch.no_grad():
+        a = dut(u8.to(DEV), ecg.to(DEV), clin.to(DEV))
+        b = dut(norm.to(DEV), ecg.to(DEV), clin.to(DEV))
+        r = ora(norm, ecg, clin)
+    for x, y, z in zip(a, b, r):
+        assert torch.equal(x, y)
+        assert relmax(x, z) <= OUT_TOL

@@ -361,3 +361,19 @@ def test_basic_block_2d(cin, cout, stride, H, W):
     assert rel_l2(nchw(dx), xr.grad) < 5e-2
     for (k, pr), (_, p) in zip(ref.named_parameters(), blk.named_parameters()):
         assert rel_l2(G(p), pr.grad) < 5e-2, (k, rel_l2(G(p), pr.grad))
+
+
+# ------------------------------------------------------------------ uint8 image input
+def test_stem_s2d_uint8_equals_totensor_normalize():
+    """Raw uint8 pixels through the stem staging kernel == torchvision ToTensor + Normalize(0.5, 0.5)
+    (dataset.py:119-123) applied on the host and fed as fp32: bit-exact, every one of the 256 levels."""
+    g = gen("u8")
+    u8 = torch.randint(0, 256, (3, 3, 37, 91), generator=g, dtype=torch.uint8)
+    u8[0, :, 0, :86] = torch.arange(256, dtype=torch.uint8)[:86]
+    u8[1].view(-1)[:256] = torch.arange(256, dtype=torch.uint8)
+    ref = ((u8.float() / 255.0) - 0.5) / 0.5
+    a = ops.stem_s2d(u8.to(DEV))
+    b = ops.stem_s2d(ref.to(DEV))
+    assert torch.equal(a, b)
+    with pytest.raises(lib.EcgmmError):
+        ops.stem_s2d(u8.to(DEV).to(torch.int32))
