@@ -11,6 +11,11 @@
 // starts s*128 bytes later (the swizzle is a function of the absolute shared-memory address, probed
 // by tools/desc_probe.py, so any 128-byte row is a legal start).  Both operands are MN-major.
 //
+// A stage covers RPS consecutive output rows of a KP-pixel column strip: RPS dy boxes + RPS+R-1 input rows, so
+// an input row is fetched (RPS+R-1)/RPS times instead of R times.  The kernel is bound by L2->SM traffic, not by
+// the MMA floor (ncu: tensor pipe 51 % busy at 66 KB per 1280-clk stage = 52 B/clk/SM with RPS = 1, KP = 128);
+// (KP, RPS) is chosen per layer to minimise the bytes staged per output pixel with >= 3 stages in flight.
+//
 // Work decomposition: group = (64-channel slice of Cin) x (64-channel slice of Cout); every group is a
 // [R*S*64] x [64] output held in TMEM as ceil(R*S/2) accumulators of 128 lanes x 64 columns; the
 // pixel range is split across CTAs (split-K) and partial results are combined with fp32 atomics.
@@ -27,9 +32,10 @@ struct alignas(64) WgHaloParams {
   float* dw;           // [Cout][Cin][R][S]
   float* ws;           // optional split-K workspace [group][ksplit][slot][64 cols][128 rows]; NULL -> atomics
   int R, S, padH, padW;
-  int KP, kmma;              // pixels per stage, KP/16
+  int KP, kmma;              // pixels per stage row, KP/16
+  int rps;                   // output rows per stage
   int x_box_bytes, x_box_stride, dy_box_bytes, dy_box_stride, stage_bytes, stages;
-  int tiles_w, Ho, total_kblocks;
+  int tiles_w, Ho, row_groups, total_kblocks;  // row_groups = ceil(Ho / rps)
   int cin_chunks, cout_chunks, ksplit;
   int Cin, Cout;
 };
@@ -82,27 +88,32 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
       if (elect_one()) {  // single elected thread: no ELECT serialisation loops around UTMALDG
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t tx = p.dy_box_bytes + p.R * p.x_box_bytes;
+        const int n_xrows = p.rps + p.R - 1;
+        const uint32_t tx = p.rps * p.dy_box_bytes + n_xrows * p.x_box_bytes;
+        const int x_base = p.rps * p.dy_box_stride;
         int twi = kb0 % p.tiles_w;
-        int row = kb0 / p.tiles_w;  // img * Ho + oh
-        int oh = row % p.Ho, img = row / p.Ho;
+        int row = kb0 / p.tiles_w;  // img * row_groups + row group
+        int og = row % p.row_groups, img = row / p.row_groups;
         for (int kb = kb0; kb < kb1; ++kb) {
           const int w0 = twi * p.KP;
+          const int oh0 = og * p.rps;
           uint8_t* st = smem + stage * p.stage_bytes;
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], tx);
-          tma_load_4d(st, &p.dy_map, &full[stage], nt * 64, w0, oh, img);
-          for (int r = 0; r < p.R; ++r)
-            tma_load_4d(st + p.dy_box_stride + r * p.x_box_stride, &p.x_map, &full[stage], cc * 64, w0 - p.padW,
-                        oh + r - p.padH, img);
+          // rows past Ho / outside the image are zero-filled by TMA and contribute nothing
+          for (int j = 0; j < p.rps; ++j)
+            tma_load_4d(st + j * p.dy_box_stride, &p.dy_map, &full[stage], nt * 64, w0, oh0 + j, img);
+          for (int r = 0; r < n_xrows; ++r)
+            tma_load_4d(st + x_base + r * p.x_box_stride, &p.x_map, &full[stage], cc * 64, w0 - p.padW,
+                        oh0 + r - p.padH, img);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
           if (++twi == p.tiles_w) {
             twi = 0;
-            if (++oh == p.Ho) {
-              oh = 0;
+            if (++og == p.row_groups) {
+              og = 0;
               ++img;
             }
           }
@@ -118,8 +129,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
 #pragma unroll
         for (int i = 0; i < kMaxSlots; ++i) {
           const int t0 = min(2 * i, RS - 1), t1 = min(2 * i + 1, RS - 1);
-          const uint32_t a0 = p.dy_box_stride + (t0 / p.S) * p.x_box_stride + (t0 % p.S) * 128;
-          const uint32_t a1 = p.dy_box_stride + (t1 / p.S) * p.x_box_stride + (t1 % p.S) * 128;
+          const uint32_t a0 = p.rps * p.dy_box_stride + (t0 / p.S) * p.x_box_stride + (t0 % p.S) * 128;
+          const uint32_t a1 = p.rps * p.dy_box_stride + (t1 / p.S) * p.x_box_stride + (t1 % p.S) * 128;
           a_rel[i] = make_sw128_desc(s_addr + a0, a1 - a0, 1024);
         }
         const uint64_t b_rel = make_sw128_desc(s_addr, 0, 1024);
@@ -129,12 +140,16 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t so = (uint64_t)((stage * p.stage_bytes) >> 4);
+          for (int j = 0; j < p.rps; ++j) {  // output row j of the stage: dy box j against input rows j .. j+R-1
+            const uint64_t ao = so + (uint64_t)((j * p.x_box_stride) >> 4), bo = so + (uint64_t)((j * p.dy_box_stride) >> 4);
 #pragma unroll
-          for (int i = 0; i < kMaxSlots; ++i) {
-            if (i < n_slots) {
-              const uint64_t a_desc = a_rel[i] + so, b_desc = b_rel + so;
-              for (int k = 0; k < p.kmma; ++k)  // 16 pixel rows = 2048 B further into both boxes
-                umma_bf16(tmem_base + i * 64, a_desc + k * 128, b_desc + k * 128, idesc, (kb > kb0) || (k > 0));
+            for (int i = 0; i < kMaxSlots; ++i) {
+              if (i < n_slots) {
+                const uint64_t a_desc = a_rel[i] + ao, b_desc = b_rel + bo;
+                for (int k = 0; k < p.kmma; ++k)  // 16 pixel rows = 2048 B further into both boxes
+                  umma_bf16(tmem_base + i * 64, a_desc + k * 128, b_desc + k * 128, idesc,
+                            (kb > kb0) || (j > 0) || (k > 0));
+              }
             }
           }
           umma_commit(&empty[stage]);
@@ -227,18 +242,37 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const float* __r
   dw[((size_t)cout * Cin + cin) * RS + tap] += acc;
 }
 
-// Picks the stage length KP (multiple of 16, <= 128) that wastes the fewest pixel slots on rows of Wo.
-static int pick_kp(int Wo) {
-  int best = 64;
-  long best_cost = -1;
-  for (int kp = 128; kp >= 32; kp -= 16) {
-    const long cost = (long)ceil_div(Wo, kp) * kp;
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best = kp;
+// Picks (KP, RPS): KP pixels (multiple of 16, <= 128) x RPS output rows per stage, minimising the bytes staged per
+// useful output pixel (dy rows + input rows incl. the halo, times the slots wasted at the right / bottom edges)
+// among the shapes whose stage fits at least 3 times (else twice) into shared memory.
+static int round1k(int v) { return (v + 1023) & ~1023; }
+static int halo_stage_bytes(int kp, int rps, int R, int S) {
+  return rps * round1k(kp * 128) + (rps + R - 1) * round1k((kp + S - 1) * 128);
+}
+static void pick_shape(int Ho, int Wo, int R, int S, int* kp_out, int* rps_out) {
+  const int budget = 220 * 1024;
+  double best = -1.0;
+  int best_kp = 64, best_rps = 1, best_stages = 0;
+  for (int kp = 128; kp >= 32; kp -= 16)
+    for (int rps = 1; rps <= 8 && rps <= (Ho > 1 ? Ho : 1); ++rps) {
+      const int sb = halo_stage_bytes(kp, rps, R, S);
+      int stages = budget / sb;
+      if (stages < 2) continue;
+      if (stages > 3) stages = 3;
+      const double staged = (double)rps * kp + (double)(rps + R - 1) * (kp + S - 1);
+      const double useful = (double)rps * kp;
+      const double waste = ((double)ceil_div(Wo, kp) * kp / Wo) * ((double)ceil_div(Ho, rps) * rps / Ho);
+      const double cost = staged / useful * waste;
+      // prefer 3 stages; among equal stage counts the cheaper shape; ties -> larger KP (fewer, longer MMAs runs)
+      if (stages > best_stages || (stages == best_stages && (best < 0 || cost < best - 1e-9))) {
+        best = cost;
+        best_kp = kp;
+        best_rps = rps;
+        best_stages = stages;
+      }
     }
-  }
-  return best;
+  *kp_out = best_kp;
+  *rps_out = best_rps;
 }
 
 bool wgrad_halo_supported(int Cin, int Cout, int R, int S, int stride) {
@@ -249,8 +283,9 @@ bool wgrad_halo_supported(int Cin, int Cout, int R, int S, int stride) {
 static void halo_split(int N, int H, int W, int Cin, int Cout, int R, int S, int padH, int padW, int* kp, int* total_kb,
                        int* groups, int* ksplit) {
   const int Ho = H + 2 * padH - R + 1, Wo = W + 2 * padW - S + 1;
-  *kp = pick_kp(Wo);
-  *total_kb = N * Ho * ceil_div(Wo, *kp);
+  int rps;
+  pick_shape(Ho, Wo, R, S, kp, &rps);
+  *total_kb = N * ceil_div(Ho, rps) * ceil_div(Wo, *kp);
   *groups = (Cin / 64) * (Cout / 64);
   int ks = num_sms() / *groups;
   if (ks < 1) ks = 1;
@@ -274,21 +309,22 @@ int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
   p.S = S;
   p.padH = padH;
   p.padW = padW;
-  p.KP = pick_kp(Wo);
+  pick_shape(Ho, Wo, R, S, &p.KP, &p.rps);
   p.kmma = p.KP / 16;
   const int xw = p.KP + S - 1;
   p.x_box_bytes = xw * 128;
   p.x_box_stride = (p.x_box_bytes + 1023) & ~1023;
   p.dy_box_bytes = p.KP * 128;
   p.dy_box_stride = (p.dy_box_bytes + 1023) & ~1023;
-  p.stage_bytes = p.dy_box_stride + R * p.x_box_stride;
+  p.stage_bytes = p.rps * p.dy_box_stride + (p.rps + R - 1) * p.x_box_stride;
   int stages = (220 * 1024) / p.stage_bytes;
   if (stages > kHaloMaxStages) stages = kHaloMaxStages;
   ECGMM_CHECK(stages >= 2, ECGMM_ERR_SHAPE, "wgrad_halo: stage of %d bytes does not fit twice", p.stage_bytes);
   p.stages = stages;
   p.tiles_w = ceil_div(Wo, p.KP);
   p.Ho = Ho;
-  p.total_kblocks = N * Ho * p.tiles_w;
+  p.row_groups = ceil_div(Ho, p.rps);
+  p.total_kblocks = N * p.row_groups * p.tiles_w;
   p.cin_chunks = Cin / 64;
   p.cout_chunks = Cout / 64;
   const int groups = p.cin_chunks * p.cout_chunks;

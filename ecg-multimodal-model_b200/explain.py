@@ -82,6 +82,7 @@ def perturbation_inference(fusion_classifier, e, background, masks, class_index:
     V = masks.shape[0]
     if chunk_samples <= 0:
         chunk_samples = max(1, (4 << 30) // max(1, V * D * 2))
+    chunk_samples = min(chunk_samples, 65535)  # grid.y limit of the variant-build kernel
     outs = []
     for s0 in range(0, S, chunk_samples):
         es = e[s0:s0 + chunk_samples]
