@@ -10,7 +10,11 @@
 //     staged once each as a box of 130 pixels and filter tap (r,s) is row r's box read from
 //     pixel s onwards (descriptor start += s*128 B; legal because the 128-byte swizzle is a
 //     function of the absolute shared-memory address, see tools/desc_probe.py);
-// so a tile moves 50 KB for the same 9.4 MFLOP.
+//   * ROLLING ROWS: a CTA walks DOWN a 128-pixel column strip (a unit = `seg` consecutive output rows of one strip);
+//     input rows live in a ring of 6 shared-memory slots, each fetched once per unit, and the tile of output row
+//     oh reads ring rows oh-1, oh, oh+1 -- one new 16.6 KB row per tile instead of three (the staged-three-rows
+//     version moved 50 + 16 KB per 1152 MMA-clocks = 57 B/clk/SM and was pinned at the L2->SM rate, 75 % of the
+//     MMA floor; now 17*(seg+2)/seg + 16 KB).
 #include "common.h"
 #include "ptx.cuh"
 
@@ -20,7 +24,7 @@ constexpr int kNhTile = 128;                               // output pixels per 
 constexpr int kNhBoxW = kNhTile + 2;                       // staged pixels per input row
 constexpr int kNhBoxBytes = kNhBoxW * 128;                 // 16640
 constexpr int kNhBoxStride = (kNhBoxBytes + 1023) & ~1023;  // 17408
-constexpr int kNhStages = 2;
+constexpr int kNhRing = 6;                                 // input-row slots (each its own full/empty barrier pair)
 constexpr int kNhWTile = 64 * 128;                         // one tap of weights: [64 n][64 k] bf16
 constexpr int kNhMaxTaps = 9;
 
@@ -32,15 +36,16 @@ struct alignas(64) NtHaloParams {
   int8_t tap_row[kNhMaxTaps], tap_shift[kNhMaxTaps];
   int padW, row0;     // input row of halo row 0 relative to the output row (-(R/2))
   int tiles_w, H, W, n_img, total_tiles;
+  int seg, segs_h, total_units;  // unit = (image, column strip, segment of `seg` output rows)
   __nv_bfloat16* out;  // [N][H][W][64]
   int accumulate;
 };
 
 struct NtHaloSmem {
   static constexpr int kW = kNhMaxTaps * kNhWTile;                 // 73728
-  static constexpr int kStage = 3 * kNhBoxStride;                  // 52224
-  static constexpr int kOut = kW + kNhStages * kStage;             // 178176: 2 output staging tiles of 16 KiB
-  static constexpr int kBarOff = kOut + 2 * kNhTile * 128;         // 210944
+  static constexpr int kRing = kNhRing * kNhBoxStride;             // 104448
+  static constexpr int kOut = kW + kRing;                          // 178176: 3 output staging tiles of 16 KiB
+  static constexpr int kBarOff = kOut + 3 * kNhTile * 128;         // 227328
   static constexpr int kBytes = kBarOff + 256 + 1024;
 };
 
@@ -52,12 +57,12 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
   uint8_t* sW = smem;
   uint8_t* sA = smem + L::kW;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* empty = full + kNhStages;
-  uint64_t* tfull = empty + kNhStages;
+  uint64_t* empty = full + kNhRing;
+  uint64_t* tfull = empty + kNhRing;
   uint64_t* tempty = tfull + 2;
   uint64_t* wfull = tempty + 2;
-  uint64_t* ofull = wfull + 1;  // [2] old output tile landed in the staging buffer (accumulate mode)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ofull + 2);
+  uint64_t* ofull = wfull + 1;  // [3] old output tile landed in the staging buffer (accumulate mode)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ofull + 3);
   uint8_t* sOut = smem + L::kOut;
 
   const int warp = threadIdx.x >> 5;
@@ -66,7 +71,7 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.x_map);
     tma_prefetch_desc(&p.w_map);
-    for (int i = 0; i < kNhStages; ++i) {
+    for (int i = 0; i < kNhRing; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -75,8 +80,7 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
       mbar_init(&tempty[i], 4);
     }
     mbar_init(wfull, 1);
-    mbar_init(&ofull[0], 1);
-    mbar_init(&ofull[1], 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&ofull[i], 1);
     tma_prefetch_desc(&p.y_map);
     mbar_fence_init();
   }
@@ -94,23 +98,19 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
       // weights: once per CTA
       mbar_expect_tx(wfull, p.ntaps * kNhWTile);
       for (int t = 0; t < p.ntaps; ++t) tma_load_2d(sW + t * kNhWTile, &p.w_map, wfull, t * 64, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx = p.rows * kNhBoxBytes;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int twi = t % p.tiles_w;
-        const int m = t / p.tiles_w;
-        const int oh = m % p.H;
-        const int img = m / p.H;
+      uint32_t q = 0;  // running input-row sequence number: slot = q % ring, fill parity = (q / ring) & 1
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        const int twi = u % p.tiles_w;
+        const int sg = (u / p.tiles_w) % p.segs_h;
+        const int img = u / (p.tiles_w * p.segs_h);
+        const int oh0 = sg * p.seg;
+        const int n_rows = min(p.seg, p.H - oh0) + p.rows - 1;
         const int w0 = twi * kNhTile;
-        uint8_t* st = sA + stage * L::kStage;
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], tx);
-        for (int r = 0; r < p.rows; ++r)
-          tma_load_4d(st + r * kNhBoxStride, &p.x_map, &full[stage], 0, w0 - p.padW, oh + p.row0 + r, img);
-        if (++stage == kNhStages) {
-          stage = 0;
-          phase ^= 1;
+        for (int j = 0; j < n_rows; ++j, ++q) {
+          const uint32_t slot = q % kNhRing, par = (q / kNhRing) & 1u;
+          mbar_wait(&empty[slot], par ^ 1u);
+          mbar_expect_tx(&full[slot], kNhBoxBytes);
+          tma_load_4d(sA + slot * kNhBoxStride, &p.x_map, &full[slot], 0, w0 - p.padW, oh0 + p.row0 + j, img);
         }
       }
     }
@@ -119,39 +119,40 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
       constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
       const uint64_t w_desc0 = make_sw128_desc(smem_u32(sW), 0, 1024);
       const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA), 0, 1024);
-      // tap -> descriptor offset (in 16-byte units) inside a stage
-      uint32_t a_off[kNhMaxTaps];
-#pragma unroll
-      for (int t = 0; t < kNhMaxTaps; ++t)
-        a_off[t] = (t < p.ntaps) ? ((p.tap_row[t] * kNhBoxStride + p.tap_shift[t] * 128) >> 4) : 0;
       mbar_wait(wfull, 0);
       tc_fence_after();
-      int stage = 0;
-      uint32_t phase = 0;
+      uint32_t q0 = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 64;
-        const uint64_t a_st = a_desc0 + (uint64_t)(stage * (L::kStage >> 4));
-#pragma unroll
-        for (int tap = 0; tap < kNhMaxTaps; ++tap) {
-          if (tap < p.ntaps) {
-            const uint64_t a_desc = a_st + a_off[tap];
-            const uint64_t w_desc = w_desc0 + (uint64_t)(tap * (kNhWTile >> 4));
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_desc + 2 * k, w_desc + 2 * k, idesc, (tap | k) != 0);
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        const int sg = (u / p.tiles_w) % p.segs_h;
+        const int n_tiles = min(p.seg, p.H - sg * p.seg);
+        for (int i = 0; i < n_tiles; ++i, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          mbar_wait(&tempty[acc], acc_phase ^ 1);
+          // rows q0+i .. q0+i+rows-1 of the ring; all but the newest were waited for by the previous tile
+          for (int r = (i == 0 ? 0 : p.rows - 1); r < p.rows; ++r) {
+            const uint32_t qq = q0 + i + r;
+            mbar_wait(&full[qq % kNhRing], (qq / kNhRing) & 1u);
           }
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * 64;
+#pragma unroll
+          for (int tap = 0; tap < kNhMaxTaps; ++tap) {
+            if (tap < p.ntaps) {
+              const uint32_t slot = (q0 + i + p.tap_row[tap]) % kNhRing;
+              const uint64_t a_desc = a_desc0 + (uint64_t)((slot * kNhBoxStride + p.tap_shift[tap] * 128) >> 4);
+              const uint64_t w_desc = w_desc0 + (uint64_t)(tap * (kNhWTile >> 4));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_desc + 2 * k, w_desc + 2 * k, idesc, (tap | k) != 0);
+            }
+          }
+          umma_commit(&empty[(q0 + i) % kNhRing]);  // the oldest row is not read by later tiles
+          if (i == n_tiles - 1)
+            for (int r = 1; r < p.rows; ++r) umma_commit(&empty[(q0 + i + r) % kNhRing]);
+          umma_commit(&tfull[acc]);
         }
-        umma_commit(&empty[stage]);
-        umma_commit(&tfull[acc]);
-        if (++stage == kNhStages) {
-          stage = 0;
-          phase ^= 1;
-        }
+        q0 += n_tiles + p.rows - 1;
       }
     }
   } else {
@@ -163,26 +164,55 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
     const int quad = warp & 3;
     const int m_row = quad * 32 + lane;
     const bool leader = (threadIdx.x == 64);
+    // Staging tiles rotate over 3 buffers (tile `it` uses buffer it % 3).  In accumulate mode the OLD contents of
+    // tile it+1 are fetched (TMA load) while tile `it` is being converted, into the buffer whose last store
+    // (tile it-2) has been read out: the load latency used to sit in front of every tile (280 us against 181 us
+    // without accumulation at batch 64).
+    auto tile_coords = [&](int u, int i, int& w0, int& oh, int& img) {
+      const int twi = u % p.tiles_w;
+      const int sg = (u / p.tiles_w) % p.segs_h;
+      img = u / (p.tiles_w * p.segs_h);
+      w0 = twi * kNhTile;
+      oh = sg * p.seg + i;
+    };
+    if (leader && p.accumulate && (int)blockIdx.x < p.total_units) {
+      int w0, oh, img;
+      tile_coords(blockIdx.x, 0, w0, oh, img);
+      mbar_expect_tx(&ofull[0], kNhTile * 128);
+      tma_load_4d(sOut, &p.y_map, &ofull[0], 0, w0, oh, img);
+    }
     int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      const int twi = t % p.tiles_w;
-      const int m = t / p.tiles_w;  // img * H + oh
-      const int oh = m % p.H, img = m / p.H;
-      const int w0 = twi * kNhTile;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+     const int n_tiles = min(p.seg, p.H - ((u / p.tiles_w) % p.segs_h) * p.seg);
+     for (int i = 0; i < n_tiles; ++i, ++it) {
+      int w0, oh, img;
+      tile_coords(u, i, w0, oh, img);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      uint8_t* buf = sOut + acc * (kNhTile * 128);
+      const int ob = it % 3;
+      const uint32_t ob_phase = (it / 3) & 1;
+      uint8_t* buf = sOut + ob * (kNhTile * 128);
       if (leader) {
-        tma_store_wait_read<1>();  // the store issued from this buffer two tiles ago has read it
+        tma_store_wait_read<1>();  // every store but the newest (tile it-1) has been read out of its buffer
         if (p.accumulate) {
-          mbar_expect_tx(&ofull[acc], kNhTile * 128);
-          tma_load_4d(buf, &p.y_map, &ofull[acc], 0, w0, oh, img);
+          int nu = u, ni = i + 1;
+          if (ni == n_tiles) {
+            nu = u + gridDim.x;
+            ni = 0;
+          }
+          if (nu < p.total_units) {
+            int nw0, noh, nimg;
+            tile_coords(nu, ni, nw0, noh, nimg);
+            const int nb = (it + 1) % 3;
+            mbar_expect_tx(&ofull[nb], kNhTile * 128);
+            tma_load_4d(sOut + nb * (kNhTile * 128), &p.y_map, &ofull[nb], 0, nw0, noh, nimg);
+          }
         }
       }
       named_bar_sync(1, 128);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      if (p.accumulate) mbar_wait(&ofull[acc], acc_phase);
+      if (p.accumulate) mbar_wait(&ofull[ob], ob_phase);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 64;
       uint8_t* row = buf + m_row * 128;
 #pragma unroll
@@ -199,10 +229,10 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[q * 8 + j]);
           if (p.accumulate) {
             const uint4 old = *d4;
-            const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+            const __nv_bfloat162* oldb = reinterpret_cast<const __nv_bfloat162*>(&old);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float2 o = __bfloat1622float2(ob[j]);
+              const float2 o = __bfloat1622float2(oldb[j]);
               f[2 * j] += o.x;
               f[2 * j + 1] += o.y;
             }
@@ -223,6 +253,7 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
         tma_store_4d(&p.y_map, buf, 0, w0, oh, img);
         tma_store_commit();
       }
+     }
     }
     if (leader) tma_store_wait_all<0>();
   }
@@ -256,6 +287,13 @@ int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16
   p.W = W;
   p.n_img = N;
   p.total_tiles = N * H * p.tiles_w;
+  // segment length: long enough to amortise the R-1 extra rows of a unit, short enough for >= 4 units per SM
+  int seg = H < 16 ? H : 16;
+  while (seg > 2 && (long long)N * p.tiles_w * ceil_div(H, seg) < 4LL * num_sms()) seg = (seg + 1) / 2;
+  seg = ceil_div(H, ceil_div(H, seg));  // equalise the segments of a strip
+  p.seg = seg;
+  p.segs_h = ceil_div(H, seg);
+  p.total_units = N * p.tiles_w * p.segs_h;
   p.out = y;
   p.accumulate = accumulate;
   const uint64_t e = 2;
@@ -271,7 +309,7 @@ int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16
                                     NtHaloSmem::kBytes));
     configured = true;
   }
-  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  const int grid = p.total_units < num_sms() ? p.total_units : num_sms();
   igemm_nt_halo_kernel<<<grid, 192, NtHaloSmem::kBytes, st>>>(p);
   return check_launch("igemm_nt_halo_kernel");
 }

@@ -22,6 +22,8 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace ecgmm {
 
 constexpr int kHaloMaxStages = 6;
@@ -242,37 +244,41 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const float* __r
   dw[((size_t)cout * Cin + cin) * RS + tap] += acc;
 }
 
-// Picks (KP, RPS): KP pixels (multiple of 16, <= 128) x RPS output rows per stage, minimising the bytes staged per
-// useful output pixel (dy rows + input rows incl. the halo, times the slots wasted at the right / bottom edges)
-// among the shapes whose stage fits at least 3 times (else twice) into shared memory.
+// Picks (KP, RPS): KP pixels (multiple of 16, <= 128) x RPS output rows per stage.
+// Measured on B200 (tools/conv_bench.py sweep, profiles/r01_wgrad_shape_sweep.txt): the kernel is NOT bound by
+// L2->SM traffic -- halving the staged bytes per pixel (RPS 1 -> 2..7) changes the time by < 4 %, while small KP
+// (more, shorter TMA boxes and MMA runs) costs up to 2x.  What matters is the pixel slots wasted at the right
+// edge of a row, so KP minimises ceil(Wo/KP)*KP (ties: larger KP) and RPS = 2 is taken only where three stages
+// still fit (a small, free reduction of L2 traffic).  The cap is the shared-memory operand bandwidth of the
+// N = 64 MMA shape: 6 KB of operands per 32-clk M128xN64xK16 MMA = 192 B/clk against ~128 B/clk.
 static int round1k(int v) { return (v + 1023) & ~1023; }
 static int halo_stage_bytes(int kp, int rps, int R, int S) {
   return rps * round1k(kp * 128) + (rps + R - 1) * round1k((kp + S - 1) * 128);
 }
 static void pick_shape(int Ho, int Wo, int R, int S, int* kp_out, int* rps_out) {
   const int budget = 220 * 1024;
-  double best = -1.0;
-  int best_kp = 64, best_rps = 1, best_stages = 0;
-  for (int kp = 128; kp >= 32; kp -= 16)
-    for (int rps = 1; rps <= 8 && rps <= (Ho > 1 ? Ho : 1); ++rps) {
-      const int sb = halo_stage_bytes(kp, rps, R, S);
-      int stages = budget / sb;
-      if (stages < 2) continue;
-      if (stages > 3) stages = 3;
-      const double staged = (double)rps * kp + (double)(rps + R - 1) * (kp + S - 1);
-      const double useful = (double)rps * kp;
-      const double waste = ((double)ceil_div(Wo, kp) * kp / Wo) * ((double)ceil_div(Ho, rps) * rps / Ho);
-      const double cost = staged / useful * waste;
-      // prefer 3 stages; among equal stage counts the cheaper shape; ties -> larger KP (fewer, longer MMAs runs)
-      if (stages > best_stages || (stages == best_stages && (best < 0 || cost < best - 1e-9))) {
-        best = cost;
-        best_kp = kp;
-        best_rps = rps;
-        best_stages = stages;
-      }
+  int best_kp = 64;
+  long best_cost = -1;
+  for (int kp = 128; kp >= 32; kp -= 16) {
+    const long cost = (long)ceil_div(Wo, kp) * kp;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_kp = kp;
     }
-  *kp_out = best_kp;
-  *rps_out = best_rps;
+  }
+  int best_rps = 1;
+  if (Ho >= 2 && 3 * halo_stage_bytes(best_kp, 2, R, S) <= budget) best_rps = 2;
+  // development knobs (tools/conv_bench.py sweeps): force a shape
+  const char* ekp = getenv("ECGMM_WG_KP");
+  const char* erps = getenv("ECGMM_WG_RPS");
+  if (ekp && erps) {
+    const int kp = atoi(ekp), rps = atoi(erps);
+    if (kp >= 16 && kp <= 128 && kp % 16 == 0 && rps >= 1 && rps <= (Ho > 1 ? Ho : 1) &&
+        2 * halo_stage_bytes(kp, rps, R, S) <= budget) {
+      *kp_out = kp;
+      *rps_out = rps;
+    }
+  }
 }
 
 bool wgrad_halo_supported(int Cin, int Cout, int R, int S, int stride) {

@@ -89,6 +89,25 @@ __global__ void __launch_bounds__(kRedThreads) chan_stats_kernel(const __nv_bflo
 constexpr int kFinLanes = 128;
 constexpr int kFinCh = 8;
 
+// Sum over the kFinLanes row lanes of a finalize CTA (thread = lane * kFinCh + channel): 7 halving steps in shared
+// memory instead of one thread walking 128 doubles.  Result valid in lane 0.
+__device__ __forceinline__ void fin_fold(double (&sh_a)[kFinLanes][kFinCh + 1], double (&sh_b)[kFinLanes][kFinCh + 1],
+                                         int lane, int cl, double& a, double& b) {
+  sh_a[lane][cl] = a;
+  sh_b[lane][cl] = b;
+  __syncthreads();
+#pragma unroll
+  for (int h = kFinLanes / 2; h >= 1; h >>= 1) {
+    if (lane < h) {
+      sh_a[lane][cl] += sh_a[lane + h][cl];
+      sh_b[lane][cl] += sh_b[lane + h][cl];
+    }
+    __syncthreads();
+  }
+  a = sh_a[0][cl];
+  b = sh_b[0][cl];
+}
+
 __global__ void __launch_bounds__(kFinCh * kFinLanes) bn_finalize_kernel(
     const float* __restrict__ psum, const float* __restrict__ psq, int rows_total, int split, int C, double count,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps,
@@ -134,16 +153,8 @@ __global__ void __launch_bounds__(kFinCh * kFinLanes) bn_finalize_kernel(
       q += q1 + q2 + q3;
     }
   }
-  sh_s[lane][cl] = s;
-  sh_q[lane][cl] = q;
-  __syncthreads();
+  fin_fold(sh_s, sh_q, lane, cl, s, q);
   if (lane != 0 || c >= C) return;
-  s = 0.0;
-  q = 0.0;
-  for (int i = 0; i < kFinLanes; ++i) {
-    s += sh_s[i][cl];
-    q += sh_q[i][cl];
-  }
   const double mean = s / count;
   double var = q / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -519,16 +530,8 @@ __global__ void __launch_bounds__(kFinCh * kFinLanes) bn_bwd_finalize_kernel(
       s2 += t2 + u2 + v2;
     }
   }
-  sh_a[lane][cl] = s1;
-  sh_b[lane][cl] = s2;
-  __syncthreads();
+  fin_fold(sh_a, sh_b, lane, cl, s1, s2);
   if (lane != 0 || c >= C) return;
-  s1 = 0.0;
-  s2 = 0.0;
-  for (int i = 0; i < kFinLanes; ++i) {
-    s1 += sh_a[i][cl];
-    s2 += sh_b[i][cl];
-  }
   const double M = per_sample * N;
   const double m1 = s1 / M, m2 = s2 / M;
   const double g = gamma ? gamma[c] : 1.0;
@@ -911,7 +914,9 @@ typedef __nv_bfloat16 bf16;
 extern "C" int ecgmm_reduce_split(int N, int P, int C) {
   if (N <= 0 || P <= 0 || C < 8) return 1;
   const int rows = kRedThreads / (C >> 3) > 0 ? kRedThreads / (C >> 3) : 1;
-  const int want = ceil_div(num_sms() * 32, N);  // many small CTAs: the last partially filled wave stays small
+  // ~8 CTAs of 256 threads per SM (one resident wave).  The finalize kernels fold N*split partial rows on a handful
+  // of CTAs, a latency-bound step that ran 58 times per training step: 4x fewer rows than the earlier 32 per SM.
+  const int want = ceil_div(num_sms() * 8, N);
   int max_split = ceil_div(P, rows * 8);
   if (max_split < 1) max_split = 1;
   int s = want < 1 ? 1 : want;
