@@ -268,6 +268,8 @@ static void pick_shape(int Ho, int Wo, int R, int S, int* kp_out, int* rps_out) 
   }
   int best_rps = 1;
   if (Ho >= 2 && 3 * halo_stage_bytes(best_kp, 2, R, S) <= budget) best_rps = 2;
+  *kp_out = best_kp;
+  *rps_out = best_rps;
   // development knobs (tools/conv_bench.py sweeps): force a shape
   const char* ekp = getenv("ECGMM_WG_KP");
   const char* erps = getenv("ECGMM_WG_RPS");
