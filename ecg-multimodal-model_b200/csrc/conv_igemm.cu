@@ -14,6 +14,7 @@
 // warp 1 = MMA issuer (+ TMEM allocation), warps 2..5 = epilogue (one TMEM lane quadrant each).
 #include "common.h"
 #include "ptx.cuh"
+#include "vec.cuh"
 
 #include <stdlib.h>
 
@@ -42,6 +43,12 @@ struct alignas(64) NtParams {
   __nv_bfloat16* out;
   long long out_sN, out_sH, out_sW;  // element strides of the output pixel grid
   int accumulate;
+  // BatchNorm batch statistics of the output, produced by the epilogue (forward only; NULL = off):
+  // psum/psq [gridDim.x * 4][stats_C]: per (CTA, epilogue warp) partial sum / sum of squares of every channel
+  // over the VALID pixels of the tiles that warp converted (bf16-rounded values, i.e. of the stored tensor).
+  float* psum;
+  float* psq;
+  int stats_C;
 };
 
 template <int BN, int STAGES>
@@ -49,7 +56,8 @@ struct NtSmem {
   static constexpr int kBTile = BN * 128;
   static constexpr int kStage = kATile + kBTile;
   static constexpr int kBarOff = STAGES * kStage;
-  static constexpr int kBytes = kBarOff + 256 + 1024;  // barriers + alignment slack
+  static constexpr int kStatsOff = kBarOff + 256;   // double [4 warps][2][BN]
+  static constexpr int kBytes = kStatsOff + 4 * 2 * BN * 8 + 1024;  // barriers + statistics + alignment slack
 };
 
 template <int BN, int STAGES>
@@ -162,6 +170,11 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_kernel(const __grid_constant_
     const int m_row = quad * 32 + lane;
     const int hl = m_row >> p.tw_shift;
     const int wl = m_row & (p.TW - 1);
+    // statistics: lane j of this warp owns columns c*32 + j of the CTA's (fixed) N tile
+    double* st_s = reinterpret_cast<double*>(smem + L::kStatsOff) + quad * 2 * BN;
+    double* st_q = st_s + BN;
+    if (p.psum)
+      for (int c = lane; c < BN; c += 32) st_s[c] = st_q[c] = 0.0;
     int it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       const int nt = t % p.n_tiles_n;
@@ -184,6 +197,16 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_kernel(const __grid_constant_
         uint32_t r[32];
         tmem_ld_32x32(t_addr + c * 32, r);
         tmem_ld_wait();
+        if (p.psum) {  // warp-uniform; statistics of the values as they are stored (bf16), invalid rows count as 0
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]))) : 0.f;
+          double s = 0.0, q = 0.0;
+          warp_colstats32(v, lane, s, q);
+          st_s[c * 32 + lane] += s;
+          st_q[c * 32 + lane] += q;
+        }
         if (valid) {
           uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
 #pragma unroll
@@ -213,11 +236,30 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_kernel(const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
+    if (p.psum) {
+      // the host launches a grid that is a multiple of n_tiles_n, so every tile of this CTA has the same nt
+      const int nt = blockIdx.x % p.n_tiles_n;
+      const size_t row = ((size_t)blockIdx.x * 4 + quad) * p.stats_C;
+      for (int c = lane; c < p.stats_C; c += 32) {
+        const int k = c - nt * BN;
+        const bool mine = (k >= 0 && k < BN);
+        p.psum[row + c] = mine ? (float)st_s[k] : 0.f;
+        p.psq[row + c] = mine ? (float)st_q[k] : 0.f;
+      }
+    }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// Persistent grid: one CTA per SM, rounded down to a multiple of the number of N tiles so that a CTA always works
+// on the same N tile (t % n_tiles_n with t = blockIdx.x + k * grid): the statistics epilogue relies on it.
+static int nt_grid(int total_tiles, int n_tiles_n) {
+  int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  if (n_tiles_n > 1 && grid > n_tiles_n) grid -= grid % n_tiles_n;
+  return grid;
 }
 
 template <int BN, int STAGES>
@@ -229,7 +271,7 @@ static int launch_nt_t(const NtParams& p, cudaStream_t s) {
                                     L::kBytes));
     configured = true;
   }
-  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  int grid = nt_grid(p.total_tiles, p.n_tiles_n);
   igemm_nt_kernel<BN, STAGES><<<grid, 192, L::kBytes, s>>>(p);
   return check_launch("igemm_nt_kernel");
 }
@@ -325,18 +367,35 @@ using namespace ecgmm;
 namespace ecgmm {
 bool nt_halo_supported(int Cin, int Cout, int R, int S, int stride, int W);
 int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int R, int S,
-                   int dgrad, int accumulate, cudaStream_t st);
+                   int dgrad, int accumulate, float* psum, float* psq, cudaStream_t st);
+int nt_halo_grid(int N, int H, int W);
 }  // namespace ecgmm
 
-extern "C" int ecgmm_conv2d_fwd(const ecgmm_bf16* x_, const ecgmm_bf16* w_, ecgmm_bf16* y_, int N, int H, int W,
-                                int Cin, int Cout, int R, int S, int stride, int padH, int padW, void* stream) {
+// Rows of the statistics partials the forward kernel chosen for this shape writes: 4 epilogue warps per CTA.
+extern "C" int ecgmm_conv2d_fwd_stats_rows(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int padH,
+                                           int padW) {
+  if (N <= 0 || check_conv_cfg(Cin, Cout, R, S, stride, padH, padW)) return 0;
+  if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY")) return 4 * nt_halo_grid(N, H, W);
+  const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
+  NtParams p;
+  memset(&p, 0, sizeof(p));
+  set_tile_grid(p, N, Ho, Wo);
+  const int bn = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  const int n_tiles_n = Cout / bn;
+  return 4 * nt_grid(p.n_img * p.tiles_h * p.tiles_w * n_tiles_n, n_tiles_n);
+}
+
+static int conv2d_fwd_impl(const ecgmm_bf16* x_, const ecgmm_bf16* w_, ecgmm_bf16* y_, float* psum, float* psq, int N,
+                           int H, int W, int Cin, int Cout, int R, int S, int stride, int padH, int padW,
+                           void* stream) {
   ECGMM_CHECK(x_ && w_ && y_, ECGMM_ERR_ARG, "conv2d_fwd: null pointer");
   int rc = check_conv_cfg(Cin, Cout, R, S, stride, padH, padW);
   if (rc) return rc;
   if (N == 0) return ECGMM_OK;
   if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY"))
     return launch_nt_halo(reinterpret_cast<const __nv_bfloat16*>(x_), reinterpret_cast<const __nv_bfloat16*>(w_),
-                          reinterpret_cast<__nv_bfloat16*>(y_), N, H, W, R, S, 0, 0, static_cast<cudaStream_t>(stream));
+                          reinterpret_cast<__nv_bfloat16*>(y_), N, H, W, R, S, 0, 0, psum, psq,
+                          static_cast<cudaStream_t>(stream));
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(x_);
   const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
   NtParams p;
@@ -358,7 +417,22 @@ extern "C" int ecgmm_conv2d_fwd(const ecgmm_bf16* x_, const ecgmm_bf16* w_, ecgm
   p.out_sH = (long long)Wo * Cout;
   p.out_sN = (long long)Ho * Wo * Cout;
   p.accumulate = 0;
+  p.psum = psum;
+  p.psq = psq;
+  p.stats_C = Cout;
   return launch_nt(p, Cout, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ecgmm_conv2d_fwd(const ecgmm_bf16* x, const ecgmm_bf16* w, ecgmm_bf16* y, int N, int H, int W, int Cin,
+                                int Cout, int R, int S, int stride, int padH, int padW, void* stream) {
+  return conv2d_fwd_impl(x, w, y, nullptr, nullptr, N, H, W, Cin, Cout, R, S, stride, padH, padW, stream);
+}
+
+extern "C" int ecgmm_conv2d_fwd_stats(const ecgmm_bf16* x, const ecgmm_bf16* w, ecgmm_bf16* y, float* psum, float* psq,
+                                      int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int padH,
+                                      int padW, void* stream) {
+  ECGMM_CHECK(psum && psq, ECGMM_ERR_ARG, "conv2d_fwd_stats: null statistics buffer");
+  return conv2d_fwd_impl(x, w, y, psum, psq, N, H, W, Cin, Cout, R, S, stride, padH, padW, stream);
 }
 
 extern "C" int ecgmm_conv2d_dgrad(const ecgmm_bf16* dy_, const ecgmm_bf16* wt_, ecgmm_bf16* dx_, int N, int H,
@@ -370,7 +444,7 @@ extern "C" int ecgmm_conv2d_dgrad(const ecgmm_bf16* dy_, const ecgmm_bf16* wt_, 
   if (N == 0) return ECGMM_OK;
   if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY"))
     return launch_nt_halo(reinterpret_cast<const __nv_bfloat16*>(dy_), reinterpret_cast<const __nv_bfloat16*>(wt_),
-                          reinterpret_cast<__nv_bfloat16*>(dx_), N, H, W, R, S, 1, accumulate,
+                          reinterpret_cast<__nv_bfloat16*>(dx_), N, H, W, R, S, 1, accumulate, nullptr, nullptr,
                           static_cast<cudaStream_t>(stream));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(dy_);
@@ -723,16 +797,27 @@ static int stem_input_map(CUtensorMap* m, const ecgmm_bf16* xs, int N, int H, in
 }
 
 namespace ecgmm {
-int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, int N, int H, int W, cudaStream_t st);
+int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, int N, int H, int W, float* psum,
+                         float* psq, cudaStream_t st);
+int stem_fwd_ring_grid(int N, int H, int W);
 int launch_stem_wgrad_ring(const void* xs, const void* dy, float* dw, int N, int H, int W, cudaStream_t st);
 }  // namespace ecgmm
 
-extern "C" int ecgmm_stem_conv_fwd(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, int N, int H,
-                                   int W, void* stream) {
+extern "C" int ecgmm_stem_conv_fwd_stats_rows(int N, int H, int W) {
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  if (!getenv("ECGMM_STEM_LEGACY")) return 4 * stem_fwd_ring_grid(N, H, W);
+  NtParams p;
+  memset(&p, 0, sizeof(p));
+  set_tile_grid(p, N, (H - 1) / 2 + 1, (W - 1) / 2 + 1);
+  return 4 * nt_grid(p.n_img * p.tiles_h * p.tiles_w, 1);
+}
+
+static int stem_conv_fwd_impl(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, float* psum, float* psq,
+                              int N, int H, int W, void* stream) {
   ECGMM_CHECK(xs && w_s2d && y, ECGMM_ERR_ARG, "stem_conv_fwd: null pointer");
   if (N == 0) return ECGMM_OK;
   if (!getenv("ECGMM_STEM_LEGACY"))
-    return launch_stem_fwd_ring(xs, w_s2d, reinterpret_cast<__nv_bfloat16*>(y), N, H, W,
+    return launch_stem_fwd_ring(xs, w_s2d, reinterpret_cast<__nv_bfloat16*>(y), N, H, W, psum, psq,
                                 static_cast<cudaStream_t>(stream));
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   NtParams p;
@@ -750,7 +835,21 @@ extern "C" int ecgmm_stem_conv_fwd(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d
   p.out_sW = 64;
   p.out_sH = (long long)Wo * 64;
   p.out_sN = (long long)Ho * Wo * 64;
+  p.psum = psum;
+  p.psq = psq;
+  p.stats_C = 64;
   return launch_nt(p, 64, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ecgmm_stem_conv_fwd(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, int N, int H,
+                                   int W, void* stream) {
+  return stem_conv_fwd_impl(xs, w_s2d, y, nullptr, nullptr, N, H, W, stream);
+}
+
+extern "C" int ecgmm_stem_conv_fwd_stats(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, float* psum,
+                                         float* psq, int N, int H, int W, void* stream) {
+  ECGMM_CHECK(psum && psq, ECGMM_ERR_ARG, "stem_conv_fwd_stats: null statistics buffer");
+  return stem_conv_fwd_impl(xs, w_s2d, y, psum, psq, N, H, W, stream);
 }
 
 extern "C" int ecgmm_stem_conv_wgrad(const ecgmm_bf16* xs, const ecgmm_bf16* dy, float* dw, int N, int H, int W,

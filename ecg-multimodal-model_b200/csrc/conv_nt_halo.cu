@@ -10,13 +10,13 @@
 //     staged once each as a box of 130 pixels and filter tap (r,s) is row r's box read from
 //     pixel s onwards (descriptor start += s*128 B; legal because the 128-byte swizzle is a
 //     function of the absolute shared-memory address, see tools/desc_probe.py);
-//   * ROLLING ROWS: a CTA walks DOWN a 128-pixel column strip (a unit = `seg` consecutive output rows of one strip);
-//     input rows live in a ring of 6 shared-memory slots, each fetched once per unit, and the tile of output row
-//     oh reads ring rows oh-1, oh, oh+1 -- one new 16.6 KB row per tile instead of three (the staged-three-rows
-//     version moved 50 + 16 KB per 1152 MMA-clocks = 57 B/clk/SM and was pinned at the L2->SM rate, 75 % of the
-//     MMA floor; now 17*(seg+2)/seg + 16 KB).
+// so a tile moves 50 KB for the same 9.4 MFLOP.
+// (A rolling-row variant -- a CTA walking down a column strip with a ring of input rows, one new row per tile --
+// was measured too: 17 % faster with a cold L2 (tools/conv_bench.py) but 10 % SLOWER inside the training step,
+// where the linear tile order below finds part of the producer's output still in L2; profiles/README.md.)
 #include "common.h"
 #include "ptx.cuh"
+#include "vec.cuh"
 
 namespace ecgmm {
 
@@ -24,7 +24,7 @@ constexpr int kNhTile = 128;                               // output pixels per 
 constexpr int kNhBoxW = kNhTile + 2;                       // staged pixels per input row
 constexpr int kNhBoxBytes = kNhBoxW * 128;                 // 16640
 constexpr int kNhBoxStride = (kNhBoxBytes + 1023) & ~1023;  // 17408
-constexpr int kNhRing = 6;                                 // input-row slots (each its own full/empty barrier pair)
+constexpr int kNhStages = 2;
 constexpr int kNhWTile = 64 * 128;                         // one tap of weights: [64 n][64 k] bf16
 constexpr int kNhMaxTaps = 9;
 
@@ -36,15 +36,16 @@ struct alignas(64) NtHaloParams {
   int8_t tap_row[kNhMaxTaps], tap_shift[kNhMaxTaps];
   int padW, row0;     // input row of halo row 0 relative to the output row (-(R/2))
   int tiles_w, H, W, n_img, total_tiles;
-  int seg, segs_h, total_units;  // unit = (image, column strip, segment of `seg` output rows)
   __nv_bfloat16* out;  // [N][H][W][64]
   int accumulate;
+  float* psum;  // BatchNorm statistics of the output (forward; NULL = off): [gridDim.x * 4][64] partial sums
+  float* psq;   //   and sums of squares per (CTA, epilogue warp), of the bf16 values as stored
 };
 
 struct NtHaloSmem {
   static constexpr int kW = kNhMaxTaps * kNhWTile;                 // 73728
-  static constexpr int kRing = kNhRing * kNhBoxStride;             // 104448
-  static constexpr int kOut = kW + kRing;                          // 178176: 3 output staging tiles of 16 KiB
+  static constexpr int kStage = 3 * kNhBoxStride;                  // 52224
+  static constexpr int kOut = kW + kNhStages * kStage;             // 178176: 3 output staging tiles of 16 KiB
   static constexpr int kBarOff = kOut + 3 * kNhTile * 128;         // 227328
   static constexpr int kBytes = kBarOff + 256 + 1024;
 };
@@ -57,8 +58,8 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
   uint8_t* sW = smem;
   uint8_t* sA = smem + L::kW;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* empty = full + kNhRing;
-  uint64_t* tfull = empty + kNhRing;
+  uint64_t* empty = full + kNhStages;
+  uint64_t* tfull = empty + kNhStages;
   uint64_t* tempty = tfull + 2;
   uint64_t* wfull = tempty + 2;
   uint64_t* ofull = wfull + 1;  // [3] old output tile landed in the staging buffer (accumulate mode)
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.x_map);
     tma_prefetch_desc(&p.w_map);
-    for (int i = 0; i < kNhRing; ++i) {
+    for (int i = 0; i < kNhStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -98,19 +99,23 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
       // weights: once per CTA
       mbar_expect_tx(wfull, p.ntaps * kNhWTile);
       for (int t = 0; t < p.ntaps; ++t) tma_load_2d(sW + t * kNhWTile, &p.w_map, wfull, t * 64, 0);
-      uint32_t q = 0;  // running input-row sequence number: slot = q % ring, fill parity = (q / ring) & 1
-      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-        const int twi = u % p.tiles_w;
-        const int sg = (u / p.tiles_w) % p.segs_h;
-        const int img = u / (p.tiles_w * p.segs_h);
-        const int oh0 = sg * p.seg;
-        const int n_rows = min(p.seg, p.H - oh0) + p.rows - 1;
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = p.rows * kNhBoxBytes;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int twi = t % p.tiles_w;
+        const int m = t / p.tiles_w;
+        const int oh = m % p.H;
+        const int img = m / p.H;
         const int w0 = twi * kNhTile;
-        for (int j = 0; j < n_rows; ++j, ++q) {
-          const uint32_t slot = q % kNhRing, par = (q / kNhRing) & 1u;
-          mbar_wait(&empty[slot], par ^ 1u);
-          mbar_expect_tx(&full[slot], kNhBoxBytes);
-          tma_load_4d(sA + slot * kNhBoxStride, &p.x_map, &full[slot], 0, w0 - p.padW, oh0 + p.row0 + j, img);
+        uint8_t* st = sA + stage * L::kStage;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], tx);
+        for (int r = 0; r < p.rows; ++r)
+          tma_load_4d(st + r * kNhBoxStride, &p.x_map, &full[stage], 0, w0 - p.padW, oh + p.row0 + r, img);
+        if (++stage == kNhStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
@@ -119,40 +124,39 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
       constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
       const uint64_t w_desc0 = make_sw128_desc(smem_u32(sW), 0, 1024);
       const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA), 0, 1024);
+      // tap -> descriptor offset (in 16-byte units) inside a stage
+      uint32_t a_off[kNhMaxTaps];
+#pragma unroll
+      for (int t = 0; t < kNhMaxTaps; ++t)
+        a_off[t] = (t < p.ntaps) ? ((p.tap_row[t] * kNhBoxStride + p.tap_shift[t] * 128) >> 4) : 0;
       mbar_wait(wfull, 0);
       tc_fence_after();
-      uint32_t q0 = 0;
+      int stage = 0;
+      uint32_t phase = 0;
       int it = 0;
-      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-        const int sg = (u / p.tiles_w) % p.segs_h;
-        const int n_tiles = min(p.seg, p.H - sg * p.seg);
-        for (int i = 0; i < n_tiles; ++i, ++it) {
-          const int acc = it & 1;
-          const uint32_t acc_phase = (it >> 1) & 1;
-          mbar_wait(&tempty[acc], acc_phase ^ 1);
-          // rows q0+i .. q0+i+rows-1 of the ring; all but the newest were waited for by the previous tile
-          for (int r = (i == 0 ? 0 : p.rows - 1); r < p.rows; ++r) {
-            const uint32_t qq = q0 + i + r;
-            mbar_wait(&full[qq % kNhRing], (qq / kNhRing) & 1u);
-          }
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * 64;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 64;
+        const uint64_t a_st = a_desc0 + (uint64_t)(stage * (L::kStage >> 4));
 #pragma unroll
-          for (int tap = 0; tap < kNhMaxTaps; ++tap) {
-            if (tap < p.ntaps) {
-              const uint32_t slot = (q0 + i + p.tap_row[tap]) % kNhRing;
-              const uint64_t a_desc = a_desc0 + (uint64_t)((slot * kNhBoxStride + p.tap_shift[tap] * 128) >> 4);
-              const uint64_t w_desc = w_desc0 + (uint64_t)(tap * (kNhWTile >> 4));
+        for (int tap = 0; tap < kNhMaxTaps; ++tap) {
+          if (tap < p.ntaps) {
+            const uint64_t a_desc = a_st + a_off[tap];
+            const uint64_t w_desc = w_desc0 + (uint64_t)(tap * (kNhWTile >> 4));
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_desc + 2 * k, w_desc + 2 * k, idesc, (tap | k) != 0);
-            }
+            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_desc + 2 * k, w_desc + 2 * k, idesc, (tap | k) != 0);
           }
-          umma_commit(&empty[(q0 + i) % kNhRing]);  // the oldest row is not read by later tiles
-          if (i == n_tiles - 1)
-            for (int r = 1; r < p.rows; ++r) umma_commit(&empty[(q0 + i + r) % kNhRing]);
-          umma_commit(&tfull[acc]);
         }
-        q0 += n_tiles + p.rows - 1;
+        umma_commit(&empty[stage]);
+        umma_commit(&tfull[acc]);
+        if (++stage == kNhStages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else {
@@ -168,25 +172,24 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
     // tile it+1 are fetched (TMA load) while tile `it` is being converted, into the buffer whose last store
     // (tile it-2) has been read out: the load latency used to sit in front of every tile (280 us against 181 us
     // without accumulation at batch 64).
-    auto tile_coords = [&](int u, int i, int& w0, int& oh, int& img) {
-      const int twi = u % p.tiles_w;
-      const int sg = (u / p.tiles_w) % p.segs_h;
-      img = u / (p.tiles_w * p.segs_h);
+    auto tile_coords = [&](int t, int& w0, int& oh, int& img) {
+      const int twi = t % p.tiles_w;
+      const int m = t / p.tiles_w;  // img * H + oh
+      oh = m % p.H;
+      img = m / p.H;
       w0 = twi * kNhTile;
-      oh = sg * p.seg + i;
     };
-    if (leader && p.accumulate && (int)blockIdx.x < p.total_units) {
+    if (leader && p.accumulate && (int)blockIdx.x < p.total_tiles) {
       int w0, oh, img;
-      tile_coords(blockIdx.x, 0, w0, oh, img);
+      tile_coords(blockIdx.x, w0, oh, img);
       mbar_expect_tx(&ofull[0], kNhTile * 128);
       tma_load_4d(sOut, &p.y_map, &ofull[0], 0, w0, oh, img);
     }
+    double st_s[2] = {0.0, 0.0}, st_q[2] = {0.0, 0.0};  // lane j: channels j and 32 + j
     int it = 0;
-    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-     const int n_tiles = min(p.seg, p.H - ((u / p.tiles_w) % p.segs_h) * p.seg);
-     for (int i = 0; i < n_tiles; ++i, ++it) {
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       int w0, oh, img;
-      tile_coords(u, i, w0, oh, img);
+      tile_coords(t, w0, oh, img);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int ob = it % 3;
@@ -194,19 +197,13 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
       uint8_t* buf = sOut + ob * (kNhTile * 128);
       if (leader) {
         tma_store_wait_read<1>();  // every store but the newest (tile it-1) has been read out of its buffer
-        if (p.accumulate) {
-          int nu = u, ni = i + 1;
-          if (ni == n_tiles) {
-            nu = u + gridDim.x;
-            ni = 0;
-          }
-          if (nu < p.total_units) {
-            int nw0, noh, nimg;
-            tile_coords(nu, ni, nw0, noh, nimg);
-            const int nb = (it + 1) % 3;
-            mbar_expect_tx(&ofull[nb], kNhTile * 128);
-            tma_load_4d(sOut + nb * (kNhTile * 128), &p.y_map, &ofull[nb], 0, nw0, noh, nimg);
-          }
+        const int tn = t + gridDim.x;
+        if (p.accumulate && tn < p.total_tiles) {
+          int nw0, noh, nimg;
+          tile_coords(tn, nw0, noh, nimg);
+          const int nb = (it + 1) % 3;
+          mbar_expect_tx(&ofull[nb], kNhTile * 128);
+          tma_load_4d(sOut + nb * (kNhTile * 128), &p.y_map, &ofull[nb], 0, nw0, noh, nimg);
         }
       }
       named_bar_sync(1, 128);
@@ -220,6 +217,14 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
         uint32_t r[32];
         tmem_ld_32x32(t_addr + c * 32, r);
         tmem_ld_wait();
+        if (p.psum) {  // statistics of the stored (bf16) values; pixels past the right edge count as 0
+          const bool valid = (w0 + m_row) < p.W;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]))) : 0.f;
+          warp_colstats32(v, lane, st_s[c], st_q[c]);
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           // 16-byte chunk j of row m lives at chunk (j ^ (m & 7)) of the swizzled tile
@@ -253,9 +258,16 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
         tma_store_4d(&p.y_map, buf, 0, w0, oh, img);
         tma_store_commit();
       }
-     }
     }
     if (leader) tma_store_wait_all<0>();
+    if (p.psum) {
+      const size_t row = ((size_t)blockIdx.x * 4 + quad) * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        p.psum[row + c * 32 + lane] = (float)st_s[c];
+        p.psq[row + c * 32 + lane] = (float)st_q[c];
+      }
+    }
   }
 
   tc_fence_before();
@@ -268,8 +280,13 @@ bool nt_halo_supported(int Cin, int Cout, int R, int S, int stride, int W) {
 }
 
 // dgrad != 0: w is the [Cin][R][S][Cout] shadow and taps are mirrored (dx[h,w] += dy[h+pad-r, w+pad-s] W[r,s]).
+int nt_halo_grid(int N, int H, int W) {
+  const int total = N * H * ceil_div(W, kNhTile);
+  return total < num_sms() ? total : num_sms();
+}
+
 int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int R, int S,
-                   int dgrad, int accumulate, cudaStream_t st) {
+                   int dgrad, int accumulate, float* psum, float* psq, cudaStream_t st) {
   NtHaloParams p;
   memset(&p, 0, sizeof(p));
   p.ntaps = R * S;
@@ -287,15 +304,10 @@ int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16
   p.W = W;
   p.n_img = N;
   p.total_tiles = N * H * p.tiles_w;
-  // segment length: long enough to amortise the R-1 extra rows of a unit, short enough for >= 4 units per SM
-  int seg = H < 16 ? H : 16;
-  while (seg > 2 && (long long)N * p.tiles_w * ceil_div(H, seg) < 4LL * num_sms()) seg = (seg + 1) / 2;
-  seg = ceil_div(H, ceil_div(H, seg));  // equalise the segments of a strip
-  p.seg = seg;
-  p.segs_h = ceil_div(H, seg);
-  p.total_units = N * p.tiles_w * p.segs_h;
   p.out = y;
   p.accumulate = accumulate;
+  p.psum = psum;
+  p.psq = psq;
   const uint64_t e = 2;
   int rc = make_tmap_4d(&p.x_map, x, 64, W, H, N, 64 * e, (uint64_t)W * 64 * e, (uint64_t)H * W * 64 * e, 64, kNhBoxW, 1);
   if (rc) return rc;
@@ -309,7 +321,7 @@ int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16
                                     NtHaloSmem::kBytes));
     configured = true;
   }
-  const int grid = p.total_units < num_sms() ? p.total_units : num_sms();
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   igemm_nt_halo_kernel<<<grid, 192, NtHaloSmem::kBytes, st>>>(p);
   return check_launch("igemm_nt_halo_kernel");
 }

@@ -914,9 +914,9 @@ typedef __nv_bfloat16 bf16;
 extern "C" int ecgmm_reduce_split(int N, int P, int C) {
   if (N <= 0 || P <= 0 || C < 8) return 1;
   const int rows = kRedThreads / (C >> 3) > 0 ? kRedThreads / (C >> 3) : 1;
-  // ~8 CTAs of 256 threads per SM (one resident wave).  The finalize kernels fold N*split partial rows on a handful
-  // of CTAs, a latency-bound step that ran 58 times per training step: 4x fewer rows than the earlier 32 per SM.
-  const int want = ceil_div(num_sms() * 8, N);
+  // many small CTAs (32 per SM): with fewer, longer CTAs the partially filled last wave costs up to 30 % (measured:
+  // 8 per SM doubled the statistics pass at batch 512)
+  const int want = ceil_div(num_sms() * 32, N);
   int max_split = ceil_div(P, rows * 8);
   if (max_split < 1) max_split = 1;
   int s = want < 1 ? 1 : want;

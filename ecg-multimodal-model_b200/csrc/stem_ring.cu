@@ -10,6 +10,7 @@
 // the whole strip set in TMEM, fp32 atomics into dW[64][3][7][7] at the end.
 #include "common.h"
 #include "ptx.cuh"
+#include "vec.cuh"
 
 namespace ecgmm {
 
@@ -24,6 +25,8 @@ struct alignas(64) StemRingParams {
   int Ho, Wo, tiles_w, n_strips;
   __nv_bfloat16* out;  // fwd: y [N][Ho][Wo][64]
   float* dw;           // wgrad: [64][3][7][7]
+  float* psum;         // fwd: BatchNorm statistics of y (NULL = off), [gridDim.x * 4][64] per (CTA, epilogue warp)
+  float* psq;
 };
 
 // ------------------------------------------------------------------------------------- forward
@@ -130,9 +133,11 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
     const int m_row = quad * 32 + lane;
     const bool leader = (threadIdx.x == 64);
     uint8_t* sOut = smem + L::kOut;
+    double st_s[2] = {0.0, 0.0}, st_q[2] = {0.0, 0.0};  // lane j: channels j and 32 + j
     int it = 0;
     for (int s = blockIdx.x; s < p.n_strips; s += gridDim.x) {
       const int img = s / p.tiles_w, w0 = (s % p.tiles_w) * kSrTile;
+      const bool valid = (w0 + m_row) < p.Wo;
       for (int oh = 0; oh < p.Ho; ++oh, ++it) {
         const int acc = it & 1;
         uint8_t* buf = sOut + acc * kSrSlot;
@@ -147,6 +152,13 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
           uint32_t r[32];
           tmem_ld_32x32(t_addr + c * 32, r);
           tmem_ld_wait();
+          if (p.psum) {  // statistics of the stored (bf16) values; pixels past the right edge count as 0
+            float vv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              vv[j] = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]))) : 0.f;
+            warp_colstats32(vv, lane, st_s[c], st_q[c]);
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 v;
@@ -169,6 +181,14 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
       }
     }
     if (leader) tma_store_wait_all<0>();
+    if (p.psum) {
+      const size_t row = ((size_t)blockIdx.x * 4 + quad) * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        p.psum[row + c * 32 + lane] = (float)st_s[c];
+        p.psq[row + c * 32 + lane] = (float)st_q[c];
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -323,7 +343,13 @@ static int stem_view(CUtensorMap* m, const void* xs, int N, int Ho, int Wo) {
   return make_tmap_4d(m, xs, 64, Wo, Hs, N, 32, (uint64_t)Ws * 32, (uint64_t)Hs * Ws * 32, 64, kSrTile, 1);
 }
 
-int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, int N, int H, int W, cudaStream_t st) {
+int stem_fwd_ring_grid(int N, int H, int W) {
+  const int n_strips = N * ceil_div((W - 1) / 2 + 1, kSrTile);
+  return n_strips < num_sms() ? n_strips : num_sms();
+}
+
+int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, int N, int H, int W, float* psum,
+                         float* psq, cudaStream_t st) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   StemRingParams p;
   memset(&p, 0, sizeof(p));
@@ -332,6 +358,8 @@ int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, in
   p.tiles_w = ceil_div(Wo, kSrTile);
   p.n_strips = N * p.tiles_w;
   p.out = y;
+  p.psum = psum;
+  p.psq = psq;
   int rc = stem_view(&p.x_map, xs, N, Ho, Wo);
   if (rc) return rc;
   rc = make_tmap_2d(&p.w_map, w_s2d, 256, 64, 512, 64, 64);

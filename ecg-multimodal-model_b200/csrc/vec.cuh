@@ -52,6 +52,39 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Column sums across a warp whose lane l holds row l of a 32-row x 32-column tile (v[j] = column j of its row):
+// a butterfly reduce-scatter, 31 shuffles per quantity; afterwards lane j holds the sum over the 32 rows of
+// column j.  Used by the convolution epilogues to produce BatchNorm batch statistics without a second pass.
+template <int H>
+__device__ __forceinline__ void colsum_step(float (&a)[32], int lane) {
+  const bool up = (lane & H) != 0;
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    const float keep = up ? a[i + H] : a[i];
+    const float send = up ? a[i] : a[i + H];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, H);
+  }
+}
+__device__ __forceinline__ float warp_colsum32(float (&a)[32], int lane) {
+  colsum_step<16>(a, lane);
+  colsum_step<8>(a, lane);
+  colsum_step<4>(a, lane);
+  colsum_step<2>(a, lane);
+  colsum_step<1>(a, lane);
+  return a[0];
+}
+// v: the lane's 32 values (already rounded to what is stored); adds column `lane`'s sum / sum of squares.
+__device__ __forceinline__ void warp_colstats32(const float (&v)[32], int lane, double& s, double& q) {
+  float a[32], b[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    a[j] = v[j];
+    b[j] = v[j] * v[j];
+  }
+  s += (double)warp_colsum32(a, lane);
+  q += (double)warp_colsum32(b, lane);
+}
+
 // Block-wide sum for blockDim.x <= 1024 (multiple of 32); every thread receives the result.
 __device__ __forceinline__ float block_sum(float v, float* red /* >= 33 floats of shared memory */) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

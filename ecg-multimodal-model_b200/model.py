@@ -14,6 +14,8 @@ called directly.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -145,13 +147,25 @@ class Sigmoid(_Marker):
     pass
 
 
-def _bn_stats(bn, x, conv_bias=None, want_nsum=False):
+FUSED_STATS = os.environ.get("ECGMM_FUSED_STATS", "1") != "0"  # BatchNorm sums from the convolution epilogue
+
+
+def _conv_bn(conv_fn, bn, *args, want_nsum=False):
+    """conv -> (y, BatchNorm statistics).  In training mode the convolution epilogue emits the per-channel partial
+    sums (no statistics pass over y) unless per-sample sums are wanted too (SE squeeze)."""
+    if bn.training and FUSED_STATS and not want_nsum:
+        y, part = conv_fn(*args, want_stats=True)
+        return y, part
+    return conv_fn(*args), None
+
+
+def _bn_stats(bn, x, conv_bias=None, want_nsum=False, partials=None):
     """Training: batch statistics (+ running update); eval: running statistics."""
     if bn.training:
         if bn.momentum is None:
             raise lib.EcgmmError("BatchNorm momentum=None (cumulative average) is not supported")
         return ops.bn_train_stats(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                                  bn.eps, bn.momentum, conv_bias, want_nsum)
+                                  bn.eps, bn.momentum, conv_bias, want_nsum, partials)
     st = ops.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, conv_bias)
     if want_nsum:  # SE squeeze needs the per-sample sums even when the statistics are frozen
         tmp = ops.bn_train_stats(x, None, None, None, None, None, bn.eps, 0.0, None, True)
@@ -280,13 +294,13 @@ def _conv_block_fwd(blk, x, save, one_d=False):
     """conv-BN-ReLU-conv-BN(-SE)(+identity / downsample)-ReLU on channels-last bf16 x."""
     s = blk.stride
     w1f, _ = blk.conv1.shadows()
-    a = ops.conv2d_fwd(x, w1f, s)
-    sa = _bn_stats(blk.bn1, a, blk.conv1.bias)
+    a, pa = _conv_bn(ops.conv2d_fwd, blk.bn1, x, w1f, s)
+    sa = _bn_stats(blk.bn1, a, blk.conv1.bias, partials=pa)
     m, mask_m = ops.bn_apply(a, sa, relu=True, want_mask=save)
     w2f, _ = blk.conv2.shadows()
-    b = ops.conv2d_fwd(m, w2f, 1)
     se = getattr(blk, "se", None)
-    sb = _bn_stats(blk.bn2, b, blk.conv2.bias, want_nsum=se is not None)
+    b, pb = _conv_bn(ops.conv2d_fwd, blk.bn2, m, w2f, 1, want_nsum=se is not None)
+    sb = _bn_stats(blk.bn2, b, blk.conv2.bias, want_nsum=se is not None, partials=pb)
     se_rec = None
     gate = None
     if se is not None:
@@ -296,8 +310,8 @@ def _conv_block_fwd(blk, x, save, one_d=False):
     d = sd = None
     if blk.downsample is not None and len(blk.downsample) > 0:
         wdf, _ = blk.downsample[0].shadows()
-        d = ops.conv2d_fwd(x, wdf, s)
-        sd = _bn_stats(blk.downsample[1], d, blk.downsample[0].bias)
+        d, pd = _conv_bn(ops.conv2d_fwd, blk.downsample[1], x, wdf, s)
+        sd = _bn_stats(blk.downsample[1], d, blk.downsample[0].bias, partials=pd)
         idn, _ = ops.bn_apply(d, sd, relu=False)
     else:
         idn = x
@@ -400,8 +414,8 @@ class ResNet18(_Stage):
         H, W = image.shape[2], image.shape[3]
         xs = ops.stem_s2d(image)
         ws, _ = self.conv1.shadows()
-        c1 = ops.stem_conv_fwd(xs, ws, H, W)
-        st1 = _bn_stats(self.bn1, c1)
+        c1, p1 = _conv_bn(ops.stem_conv_fwd, self.bn1, xs, ws, H, W)
+        st1 = _bn_stats(self.bn1, c1, partials=p1)
         x, arg = ops.bn_relu_maxpool(c1, st1, want_argmax=save)
         recs = []
         for blk in self.blocks():

@@ -102,7 +102,18 @@ def _conv_out(H, W, R, S, stride, pH, pW):
     return (H + 2 * pH - R) // stride + 1, (W + 2 * pW - S) // stride + 1
 
 
-def conv2d_fwd(x: torch.Tensor, w_fwd: torch.Tensor, stride: int = 1) -> torch.Tensor:
+class StatPartials:
+    """Partial BatchNorm sums written by a convolution epilogue: psum / psq [rows][C] fp32."""
+    __slots__ = ("psum", "psq", "rows")
+
+    def __init__(self, rows, C, device):
+        buf = torch.empty(2 * rows * C, dtype=torch.float32, device=device)
+        self.psum, self.psq, self.rows = buf[: rows * C], buf[rows * C:], rows
+
+
+def conv2d_fwd(x: torch.Tensor, w_fwd: torch.Tensor, stride: int = 1, want_stats: bool = False):
+    """y = conv(x, w).  want_stats: returns (y, StatPartials) -- the epilogue also emits the per-channel sums
+    that bn_train_stats(partials=...) folds, so training-mode BatchNorm needs no statistics pass over y."""
     _chk(x, BF16, "x")
     _chk(w_fwd, BF16, "w_fwd")
     N, H, W, Cin = x.shape
@@ -111,6 +122,13 @@ def conv2d_fwd(x: torch.Tensor, w_fwd: torch.Tensor, stride: int = 1) -> torch.T
     pH, pW = R // 2, S // 2
     Ho, Wo = _conv_out(H, W, R, S, stride, pH, pW)
     y = torch.empty((N, Ho, Wo, Cout), dtype=BF16, device=x.device)
+    if want_stats:
+        rows = _shape_query("ecgmm_conv2d_fwd_stats_rows", N, H, W, Cin, Cout, R, S, stride, pH, pW)
+        part = StatPartials(rows, Cout, x.device)
+        _timed(f"conv_fwd/{Cin}x{Cout}k{R}{S}s{stride}", 2.0 * N * Ho * Wo * Cout * Cin * R * S, "ecgmm_conv2d_fwd_stats",
+               _ptr(x), _ptr(w_fwd), _ptr(y), _ptr(part.psum), _ptr(part.psq), N, H, W, Cin, Cout, R, S, stride, pH, pW,
+               _s())
+        return y, part
     _timed(f"conv_fwd/{Cin}x{Cout}k{R}{S}s{stride}", 2.0 * N * Ho * Wo * Cout * Cin * R * S, "ecgmm_conv2d_fwd", _ptr(x), _ptr(w_fwd), _ptr(y), N,
            H, W, Cin, Cout, R, S, stride, pH, pW, _s())
     return y
@@ -182,12 +200,17 @@ def stem_weight_prep(w: torch.Tensor) -> torch.Tensor:
     return ws
 
 
-def stem_conv_fwd(xs: torch.Tensor, w_s2d: torch.Tensor, H: int, W: int) -> torch.Tensor:
+def stem_conv_fwd(xs: torch.Tensor, w_s2d: torch.Tensor, H: int, W: int, want_stats: bool = False):
     _chk(xs, BF16, "xs")
     _chk(w_s2d, BF16, "w_s2d")
     N = xs.shape[0]
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty((N, Ho, Wo, 64), dtype=BF16, device=xs.device)
+    if want_stats:
+        part = StatPartials(_shape_query("ecgmm_stem_conv_fwd_stats_rows", N, H, W), 64, xs.device)
+        _timed("stem_fwd", 2.0 * N * Ho * Wo * 64 * 147, "ecgmm_stem_conv_fwd_stats", _ptr(xs), _ptr(w_s2d), _ptr(y),
+               _ptr(part.psum), _ptr(part.psq), N, H, W, _s())
+        return y, part
     _timed("stem_fwd", 2.0 * N * Ho * Wo * 64 * 147, "ecgmm_stem_conv_fwd", _ptr(xs), _ptr(w_s2d), _ptr(y), N, H, W,
            _s())
     return y
@@ -226,19 +249,27 @@ def _npc(x):
 
 
 def bn_train_stats(x, gamma, beta, running_mean, running_var, num_batches, eps, momentum, conv_bias=None,
-                   want_nsum=False) -> BNStats:
-    """Training-mode statistics of a channels-last activation + running-stat update."""
+                   want_nsum=False, partials=None) -> BNStats:
+    """Training-mode statistics of a channels-last activation + running-stat update.
+    partials: StatPartials from the convolution that produced x (conv2d_fwd(want_stats=True)); without them a
+    statistics pass (ecgmm_chan_stats) reads x once more."""
     _chk(x, BF16, "x")
     N, P, C = _npc(x)
     dev = x.device
-    split = _shape_query("ecgmm_reduce_split", N, P, C)
-    part = _f32(2 * N * split * C, dev)
-    psum, psq = part[: N * split * C], part[N * split * C:]
-    _timed(f"bn_stats/C{C}", 2.0 * N * P * C, "ecgmm_chan_stats", _ptr(x), _ptr(psum), _ptr(psq), N, P, C, split, _s())
+    if partials is not None and not want_nsum:
+        psum, psq = partials.psum, partials.psq
+        rows_n, split = partials.rows, 1
+    else:
+        split = _shape_query("ecgmm_reduce_split", N, P, C)
+        part = _f32(2 * N * split * C, dev)
+        psum, psq = part[: N * split * C], part[N * split * C:]
+        rows_n = N
+        _timed(f"bn_stats/C{C}", 2.0 * N * P * C, "ecgmm_chan_stats", _ptr(x), _ptr(psum), _ptr(psq), N, P, C, split,
+               _s())
     out = _f32(4 * C, dev)
     mean, invstd, scale, shift = out[:C], out[C:2 * C], out[2 * C:3 * C], out[3 * C:]
     nsum = _f32(N * C, dev).view(N, C) if want_nsum else None
-    lib.call("ecgmm_bn_finalize", _ptr(psum), _ptr(psq), N, split, C, N * P, _ptr(gamma), _ptr(beta),
+    lib.call("ecgmm_bn_finalize", _ptr(psum), _ptr(psq), rows_n, split, C, N * P, _ptr(gamma), _ptr(beta),
              _ptr(conv_bias), float(eps), float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(num_batches),
              _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), _ptr(nsum), _s())
     return BNStats(mean, invstd, scale, shift, nsum)

@@ -377,3 +377,53 @@ def test_stem_s2d_uint8_equals_totensor_normalize():
     assert torch.equal(a, b)
     with pytest.raises(lib.EcgmmError):
         ops.stem_s2d(u8.to(DEV).to(torch.int32))
+
+
+# ------------------------------------------------------------------ BatchNorm statistics from the conv epilogues
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride", [
+    (3, 21, 150, 64, 64, 3, 1),     # halo kernel (64 -> 64, W >= 96), ragged right edge
+    (2, 9, 40, 64, 64, 3, 1),       # generic kernel, BN = 64
+    (3, 17, 45, 64, 128, 3, 2),     # stride 2, BN = 128
+    (2, 12, 31, 128, 256, 1, 2),    # 1x1 downsample, BN = 256
+    (2, 8, 79, 256, 512, 3, 1),     # two N tiles per pixel tile
+    (5, 1, 310, 128, 128, 3, 1),    # 1-D (H = 1)
+])
+def test_conv_epilogue_statistics(N, H, W, Cin, Cout, k, stride):
+    """conv2d_fwd(want_stats=True): same y as without, and the partial rows fold to the exact per-channel sum /
+    sum of squares of the STORED bf16 tensor (fp32 partials over <= a few thousand values each)."""
+    g = gen(f"cs{N}{H}{W}{Cin}{Cout}{k}{stride}")
+    x = torch.randn(N, H, W, Cin, generator=g).to(DEV).to(torch.bfloat16)
+    R = 1 if H == 1 else k
+    w = (torch.randn(Cout, Cin, R, k, generator=g) / (Cin * R * k) ** 0.5).to(DEV)
+    w_fwd, _ = ops.conv_weight_prep(w)
+    y0 = ops.conv2d_fwd(x, w_fwd, stride)
+    y, part = ops.conv2d_fwd(x, w_fwd, stride, want_stats=True)
+    assert torch.equal(y, y0)
+    yd = y.double().reshape(-1, Cout)
+    s_ref, q_ref = yd.sum(0), (yd * yd).sum(0)
+    s = part.psum.view(part.rows, Cout).double().sum(0)
+    q = part.psq.view(part.rows, Cout).double().sum(0)
+    scale = yd.abs().sum(0)
+    assert ((s - s_ref).abs() <= 1e-5 * scale + 1e-6).all()
+    assert ((q - q_ref).abs() <= 1e-5 * q_ref + 1e-6).all()
+    # and through the finalize kernel: identical BatchNorm coefficients to the separate statistics pass
+    bn = torch.nn.BatchNorm2d(Cout).to(DEV)
+    a = ops.bn_train_stats(y, bn.weight, bn.bias, None, None, None, 1e-5, 0.1)
+    b = ops.bn_train_stats(y, bn.weight, bn.bias, None, None, None, 1e-5, 0.1, partials=part)
+    assert rel_l2(b.mean, a.mean) < 1e-4 and rel_l2(b.invstd, a.invstd) < 1e-5
+
+
+def test_stem_epilogue_statistics():
+    g = gen("stemstats")
+    H, W = 37, 530
+    x = torch.randn(3, 3, H, W, generator=g).clamp(-1, 1).to(DEV)
+    xs = ops.stem_s2d(x)
+    ws = ops.stem_weight_prep((torch.randn(64, 3, 7, 7, generator=g) / 12).to(DEV))
+    y0 = ops.stem_conv_fwd(xs, ws, H, W)
+    y, part = ops.stem_conv_fwd(xs, ws, H, W, want_stats=True)
+    assert torch.equal(y, y0)
+    yd = y.double().reshape(-1, 64)
+    s = part.psum.view(part.rows, 64).double().sum(0)
+    q = part.psq.view(part.rows, 64).double().sum(0)
+    assert ((s - yd.sum(0)).abs() <= 1e-5 * yd.abs().sum(0) + 1e-6).all()
+    assert ((q - (yd * yd).sum(0)).abs() <= 1e-5 * (yd * yd).sum(0) + 1e-6).all()
