@@ -371,11 +371,14 @@ int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16
 int nt_halo_grid(int N, int H, int W);
 }  // namespace ecgmm
 
-// Rows of the statistics partials the forward kernel chosen for this shape writes: 4 epilogue warps per CTA.
+// Rows of the statistics partials the forward kernel chosen for this shape writes (halo kernel: 16 row sets per
+// CTA; generic kernel: 4 epilogue warps per CTA).  0 = not offered: for 1x1 convolutions the generic kernel's tile
+// holds too few MMAs to hide the shuffle reduction (measured), the separate statistics pass is cheaper.
 extern "C" int ecgmm_conv2d_fwd_stats_rows(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int padH,
                                            int padW) {
   if (N <= 0 || check_conv_cfg(Cin, Cout, R, S, stride, padH, padW)) return 0;
-  if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY")) return 4 * nt_halo_grid(N, H, W);
+  if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY")) return 16 * nt_halo_grid(N, H, W);
+  if (R * S * Cin < 512) return 0;
   const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
   NtParams p;
   memset(&p, 0, sizeof(p));
@@ -805,7 +808,7 @@ int launch_stem_wgrad_ring(const void* xs, const void* dy, float* dw, int N, int
 
 extern "C" int ecgmm_stem_conv_fwd_stats_rows(int N, int H, int W) {
   if (N <= 0 || H <= 0 || W <= 0) return 0;
-  if (!getenv("ECGMM_STEM_LEGACY")) return 4 * stem_fwd_ring_grid(N, H, W);
+  if (!getenv("ECGMM_STEM_LEGACY")) return 16 * stem_fwd_ring_grid(N, H, W);
   NtParams p;
   memset(&p, 0, sizeof(p));
   set_tile_grid(p, N, (H - 1) / 2 + 1, (W - 1) / 2 + 1);

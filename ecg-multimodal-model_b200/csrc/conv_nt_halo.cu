@@ -38,8 +38,8 @@ struct alignas(64) NtHaloParams {
   int tiles_w, H, W, n_img, total_tiles;
   __nv_bfloat16* out;  // [N][H][W][64]
   int accumulate;
-  float* psum;  // BatchNorm statistics of the output (forward; NULL = off): [gridDim.x * 4][64] partial sums
-  float* psq;   //   and sums of squares per (CTA, epilogue warp), of the bf16 values as stored
+  float* psum;  // BatchNorm statistics of the output (forward; NULL = off): [gridDim.x * 16][64] partial sums
+  float* psq;   //   and sums of squares per (CTA, row set of the staging tile), of the bf16 values as stored
 };
 
 struct NtHaloSmem {
@@ -185,7 +185,10 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
       mbar_expect_tx(&ofull[0], kNhTile * 128);
       tma_load_4d(sOut, &p.y_map, &ofull[0], 0, w0, oh, img);
     }
-    double st_s[2] = {0.0, 0.0}, st_q[2] = {0.0, 0.0};  // lane j: channels j and 32 + j
+    double st_s[8], st_q[8];  // thread t: channels [8*(t&7), +8) over tile rows (t>>3) + 16k (tile_colstats_smem)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) st_s[j] = st_q[j] = 0.0;
+    const int et = threadIdx.x - 64;
     int it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       int w0, oh, img;
@@ -217,14 +220,6 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
         uint32_t r[32];
         tmem_ld_32x32(t_addr + c * 32, r);
         tmem_ld_wait();
-        if (p.psum) {  // statistics of the stored (bf16) values; pixels past the right edge count as 0
-          const bool valid = (w0 + m_row) < p.W;
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]))) : 0.f;
-          warp_colstats32(v, lane, st_s[c], st_q[c]);
-        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           // 16-byte chunk j of row m lives at chunk (j ^ (m & 7)) of the swizzled tile
@@ -258,14 +253,17 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
         tma_store_4d(&p.y_map, buf, 0, w0, oh, img);
         tma_store_commit();
       }
+      // statistics of the finished tile, read back from the staging buffer (it is rewritten 3 tiles later, behind
+      // two more barriers); pixels past the right edge of the image are skipped
+      if (p.psum) tile_colstats_smem(buf, et, p.W - w0, st_s, st_q);
     }
     if (leader) tma_store_wait_all<0>();
     if (p.psum) {
-      const size_t row = ((size_t)blockIdx.x * 4 + quad) * 64;
+      const size_t o = ((size_t)blockIdx.x * 16 + (et >> 3)) * 64 + (et & 7) * 8;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        p.psum[row + c * 32 + lane] = (float)st_s[c];
-        p.psq[row + c * 32 + lane] = (float)st_q[c];
+      for (int j = 0; j < 8; ++j) {
+        p.psum[o + j] = (float)st_s[j];
+        p.psq[o + j] = (float)st_q[j];
       }
     }
   }

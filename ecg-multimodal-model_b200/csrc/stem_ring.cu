@@ -25,7 +25,7 @@ struct alignas(64) StemRingParams {
   int Ho, Wo, tiles_w, n_strips;
   __nv_bfloat16* out;  // fwd: y [N][Ho][Wo][64]
   float* dw;           // wgrad: [64][3][7][7]
-  float* psum;         // fwd: BatchNorm statistics of y (NULL = off), [gridDim.x * 4][64] per (CTA, epilogue warp)
+  float* psum;         // fwd: BatchNorm statistics of y (NULL = off), [gridDim.x * 16][64] per (CTA, tile row set)
   float* psq;
 };
 
@@ -133,11 +133,13 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
     const int m_row = quad * 32 + lane;
     const bool leader = (threadIdx.x == 64);
     uint8_t* sOut = smem + L::kOut;
-    double st_s[2] = {0.0, 0.0}, st_q[2] = {0.0, 0.0};  // lane j: channels j and 32 + j
+    double st_s[8], st_q[8];  // thread t: channels [8*(t&7), +8) over tile rows (t>>3) + 16k (tile_colstats_smem)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) st_s[j] = st_q[j] = 0.0;
+    const int et = threadIdx.x - 64;
     int it = 0;
     for (int s = blockIdx.x; s < p.n_strips; s += gridDim.x) {
       const int img = s / p.tiles_w, w0 = (s % p.tiles_w) * kSrTile;
-      const bool valid = (w0 + m_row) < p.Wo;
       for (int oh = 0; oh < p.Ho; ++oh, ++it) {
         const int acc = it & 1;
         uint8_t* buf = sOut + acc * kSrSlot;
@@ -152,13 +154,6 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
           uint32_t r[32];
           tmem_ld_32x32(t_addr + c * 32, r);
           tmem_ld_wait();
-          if (p.psum) {  // statistics of the stored (bf16) values; pixels past the right edge count as 0
-            float vv[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              vv[j] = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]))) : 0.f;
-            warp_colstats32(vv, lane, st_s[c], st_q[c]);
-          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 v;
@@ -178,15 +173,17 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
           tma_store_4d(&p.dy_map, buf, 0, w0, oh, img);
           tma_store_commit();
         }
+        // statistics of the finished tile from the staging buffer (rewritten 2 tiles later, behind two barriers)
+        if (p.psum) tile_colstats_smem(buf, et, p.Wo - w0, st_s, st_q);
       }
     }
     if (leader) tma_store_wait_all<0>();
     if (p.psum) {
-      const size_t row = ((size_t)blockIdx.x * 4 + quad) * 64;
+      const size_t o = ((size_t)blockIdx.x * 16 + (et >> 3)) * 64 + (et & 7) * 8;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        p.psum[row + c * 32 + lane] = (float)st_s[c];
-        p.psq[row + c * 32 + lane] = (float)st_q[c];
+      for (int j = 0; j < 8; ++j) {
+        p.psum[o + j] = (float)st_s[j];
+        p.psq[o + j] = (float)st_q[j];
       }
     }
   }

@@ -399,6 +399,9 @@ def test_conv_epilogue_statistics(N, H, W, Cin, Cout, k, stride):
     y0 = ops.conv2d_fwd(x, w_fwd, stride)
     y, part = ops.conv2d_fwd(x, w_fwd, stride, want_stats=True)
     assert torch.equal(y, y0)
+    if k == 1:  # not offered for 1x1 convolutions (too few MMAs per tile to hide it): caller runs the statistics pass
+        assert part is None
+        return
     yd = y.double().reshape(-1, Cout)
     s_ref, q_ref = yd.sum(0), (yd * yd).sum(0)
     s = part.psum.view(part.rows, Cout).double().sum(0)
