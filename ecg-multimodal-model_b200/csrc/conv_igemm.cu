@@ -367,17 +367,18 @@ using namespace ecgmm;
 namespace ecgmm {
 bool nt_halo_supported(int Cin, int Cout, int R, int S, int stride, int W);
 int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int R, int S,
-                   int dgrad, int accumulate, float* psum, float* psq, cudaStream_t st);
-int nt_halo_grid(int N, int H, int W);
+                   int dgrad, int accumulate, cudaStream_t st);
 }  // namespace ecgmm
 
-// Rows of the statistics partials the forward kernel chosen for this shape writes (halo kernel: 16 row sets per
-// CTA; generic kernel: 4 epilogue warps per CTA).  0 = not offered: for 1x1 convolutions the generic kernel's tile
-// holds too few MMAs to hide the shuffle reduction (measured), the separate statistics pass is cheaper.
+// Rows of the statistics partials the forward kernel writes for this shape (4 epilogue warps per CTA of the generic
+// kernel).  0 = not offered: the reduction sits in the epilogue, which has slack only when a tile holds many MMAs.
+// Measured at batch 64 (profiles/README.md): layers 2-4 (K >= 576) +0.04 ms on three convolutions against a 0.13 ms
+// statistics pass; the 64->64 halo kernel (36 MMAs per tile) +0.33 ms against 0.28 ms and the stem (16 MMAs) +0.3 ms
+// against 0.2 ms, whether the reduction is a register shuffle transpose or a read-back of the staging tile.
 extern "C" int ecgmm_conv2d_fwd_stats_rows(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int padH,
                                            int padW) {
   if (N <= 0 || check_conv_cfg(Cin, Cout, R, S, stride, padH, padW)) return 0;
-  if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY")) return 16 * nt_halo_grid(N, H, W);
+  if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY")) return 0;
   if (R * S * Cin < 512) return 0;
   const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
   NtParams p;
@@ -397,8 +398,7 @@ static int conv2d_fwd_impl(const ecgmm_bf16* x_, const ecgmm_bf16* w_, ecgmm_bf1
   if (N == 0) return ECGMM_OK;
   if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY"))
     return launch_nt_halo(reinterpret_cast<const __nv_bfloat16*>(x_), reinterpret_cast<const __nv_bfloat16*>(w_),
-                          reinterpret_cast<__nv_bfloat16*>(y_), N, H, W, R, S, 0, 0, psum, psq,
-                          static_cast<cudaStream_t>(stream));
+                          reinterpret_cast<__nv_bfloat16*>(y_), N, H, W, R, S, 0, 0, static_cast<cudaStream_t>(stream));
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(x_);
   const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
   NtParams p;
@@ -447,7 +447,7 @@ extern "C" int ecgmm_conv2d_dgrad(const ecgmm_bf16* dy_, const ecgmm_bf16* wt_, 
   if (N == 0) return ECGMM_OK;
   if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY"))
     return launch_nt_halo(reinterpret_cast<const __nv_bfloat16*>(dy_), reinterpret_cast<const __nv_bfloat16*>(wt_),
-                          reinterpret_cast<__nv_bfloat16*>(dx_), N, H, W, R, S, 1, accumulate, nullptr, nullptr,
+                          reinterpret_cast<__nv_bfloat16*>(dx_), N, H, W, R, S, 1, accumulate,
                           static_cast<cudaStream_t>(stream));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(dy_);
@@ -800,27 +800,16 @@ static int stem_input_map(CUtensorMap* m, const ecgmm_bf16* xs, int N, int H, in
 }
 
 namespace ecgmm {
-int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, int N, int H, int W, float* psum,
-                         float* psq, cudaStream_t st);
-int stem_fwd_ring_grid(int N, int H, int W);
+int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, int N, int H, int W, cudaStream_t st);
 int launch_stem_wgrad_ring(const void* xs, const void* dy, float* dw, int N, int H, int W, cudaStream_t st);
 }  // namespace ecgmm
 
-extern "C" int ecgmm_stem_conv_fwd_stats_rows(int N, int H, int W) {
-  if (N <= 0 || H <= 0 || W <= 0) return 0;
-  if (!getenv("ECGMM_STEM_LEGACY")) return 16 * stem_fwd_ring_grid(N, H, W);
-  NtParams p;
-  memset(&p, 0, sizeof(p));
-  set_tile_grid(p, N, (H - 1) / 2 + 1, (W - 1) / 2 + 1);
-  return 4 * nt_grid(p.n_img * p.tiles_h * p.tiles_w, 1);
-}
-
-static int stem_conv_fwd_impl(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, float* psum, float* psq,
-                              int N, int H, int W, void* stream) {
+extern "C" int ecgmm_stem_conv_fwd(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, int N, int H,
+                                   int W, void* stream) {
   ECGMM_CHECK(xs && w_s2d && y, ECGMM_ERR_ARG, "stem_conv_fwd: null pointer");
   if (N == 0) return ECGMM_OK;
   if (!getenv("ECGMM_STEM_LEGACY"))
-    return launch_stem_fwd_ring(xs, w_s2d, reinterpret_cast<__nv_bfloat16*>(y), N, H, W, psum, psq,
+    return launch_stem_fwd_ring(xs, w_s2d, reinterpret_cast<__nv_bfloat16*>(y), N, H, W,
                                 static_cast<cudaStream_t>(stream));
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   NtParams p;
@@ -838,21 +827,7 @@ static int stem_conv_fwd_impl(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecg
   p.out_sW = 64;
   p.out_sH = (long long)Wo * 64;
   p.out_sN = (long long)Ho * Wo * 64;
-  p.psum = psum;
-  p.psq = psq;
-  p.stats_C = 64;
   return launch_nt(p, 64, static_cast<cudaStream_t>(stream));
-}
-
-extern "C" int ecgmm_stem_conv_fwd(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, int N, int H,
-                                   int W, void* stream) {
-  return stem_conv_fwd_impl(xs, w_s2d, y, nullptr, nullptr, N, H, W, stream);
-}
-
-extern "C" int ecgmm_stem_conv_fwd_stats(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, float* psum,
-                                         float* psq, int N, int H, int W, void* stream) {
-  ECGMM_CHECK(psum && psq, ECGMM_ERR_ARG, "stem_conv_fwd_stats: null statistics buffer");
-  return stem_conv_fwd_impl(xs, w_s2d, y, psum, psq, N, H, W, stream);
 }
 
 extern "C" int ecgmm_stem_conv_wgrad(const ecgmm_bf16* xs, const ecgmm_bf16* dy, float* dw, int N, int H, int W,

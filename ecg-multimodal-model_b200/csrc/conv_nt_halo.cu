@@ -11,12 +11,17 @@
 //     pixel s onwards (descriptor start += s*128 B; legal because the 128-byte swizzle is a
 //     function of the absolute shared-memory address, see tools/desc_probe.py);
 // so a tile moves 50 KB for the same 9.4 MFLOP.
+// The N = 64 MMA shape itself is the cap: issuing N = 128 MMAs over the same tiles (2x the tensor work, half of it
+// discarded) made this kernel only 24 % slower, i.e. M128xN64xK16 sustains ~62 % of the rate of M128xN128xK16
+// (6 KB of shared-memory operands per 32 MMA-clocks); profiles/r01_mma_n64_vs_n128.txt.
 // (A rolling-row variant -- a CTA walking down a column strip with a ring of input rows, one new row per tile --
 // was measured too: 17 % faster with a cold L2 (tools/conv_bench.py) but 10 % SLOWER inside the training step,
 // where the linear tile order below finds part of the producer's output still in L2; profiles/README.md.)
 #include "common.h"
 #include "ptx.cuh"
 #include "vec.cuh"
+
+#include <stdlib.h>
 
 namespace ecgmm {
 
@@ -38,8 +43,6 @@ struct alignas(64) NtHaloParams {
   int tiles_w, H, W, n_img, total_tiles;
   __nv_bfloat16* out;  // [N][H][W][64]
   int accumulate;
-  float* psum;  // BatchNorm statistics of the output (forward; NULL = off): [gridDim.x * 16][64] partial sums
-  float* psq;   //   and sums of squares per (CTA, row set of the staging tile), of the bf16 values as stored
 };
 
 struct NtHaloSmem {
@@ -185,10 +188,6 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
       mbar_expect_tx(&ofull[0], kNhTile * 128);
       tma_load_4d(sOut, &p.y_map, &ofull[0], 0, w0, oh, img);
     }
-    double st_s[8], st_q[8];  // thread t: channels [8*(t&7), +8) over tile rows (t>>3) + 16k (tile_colstats_smem)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) st_s[j] = st_q[j] = 0.0;
-    const int et = threadIdx.x - 64;
     int it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       int w0, oh, img;
@@ -253,19 +252,9 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
         tma_store_4d(&p.y_map, buf, 0, w0, oh, img);
         tma_store_commit();
       }
-      // statistics of the finished tile, read back from the staging buffer (it is rewritten 3 tiles later, behind
-      // two more barriers); pixels past the right edge of the image are skipped
-      if (p.psum) tile_colstats_smem(buf, et, p.W - w0, st_s, st_q);
     }
     if (leader) tma_store_wait_all<0>();
-    if (p.psum) {
-      const size_t o = ((size_t)blockIdx.x * 16 + (et >> 3)) * 64 + (et & 7) * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        p.psum[o + j] = (float)st_s[j];
-        p.psq[o + j] = (float)st_q[j];
-      }
-    }
+
   }
 
   tc_fence_before();
@@ -278,13 +267,8 @@ bool nt_halo_supported(int Cin, int Cout, int R, int S, int stride, int W) {
 }
 
 // dgrad != 0: w is the [Cin][R][S][Cout] shadow and taps are mirrored (dx[h,w] += dy[h+pad-r, w+pad-s] W[r,s]).
-int nt_halo_grid(int N, int H, int W) {
-  const int total = N * H * ceil_div(W, kNhTile);
-  return total < num_sms() ? total : num_sms();
-}
-
 int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int R, int S,
-                   int dgrad, int accumulate, float* psum, float* psq, cudaStream_t st) {
+                   int dgrad, int accumulate, cudaStream_t st) {
   NtHaloParams p;
   memset(&p, 0, sizeof(p));
   p.ntaps = R * S;
@@ -304,8 +288,6 @@ int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16
   p.total_tiles = N * H * p.tiles_w;
   p.out = y;
   p.accumulate = accumulate;
-  p.psum = psum;
-  p.psq = psq;
   const uint64_t e = 2;
   int rc = make_tmap_4d(&p.x_map, x, 64, W, H, N, 64 * e, (uint64_t)W * 64 * e, (uint64_t)H * W * 64 * e, 64, kNhBoxW, 1);
   if (rc) return rc;

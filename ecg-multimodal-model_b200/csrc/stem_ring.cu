@@ -10,7 +10,6 @@
 // the whole strip set in TMEM, fp32 atomics into dW[64][3][7][7] at the end.
 #include "common.h"
 #include "ptx.cuh"
-#include "vec.cuh"
 
 namespace ecgmm {
 
@@ -25,8 +24,6 @@ struct alignas(64) StemRingParams {
   int Ho, Wo, tiles_w, n_strips;
   __nv_bfloat16* out;  // fwd: y [N][Ho][Wo][64]
   float* dw;           // wgrad: [64][3][7][7]
-  float* psum;         // fwd: BatchNorm statistics of y (NULL = off), [gridDim.x * 16][64] per (CTA, tile row set)
-  float* psq;
 };
 
 // ------------------------------------------------------------------------------------- forward
@@ -133,10 +130,6 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
     const int m_row = quad * 32 + lane;
     const bool leader = (threadIdx.x == 64);
     uint8_t* sOut = smem + L::kOut;
-    double st_s[8], st_q[8];  // thread t: channels [8*(t&7), +8) over tile rows (t>>3) + 16k (tile_colstats_smem)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) st_s[j] = st_q[j] = 0.0;
-    const int et = threadIdx.x - 64;
     int it = 0;
     for (int s = blockIdx.x; s < p.n_strips; s += gridDim.x) {
       const int img = s / p.tiles_w, w0 = (s % p.tiles_w) * kSrTile;
@@ -173,19 +166,9 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
           tma_store_4d(&p.dy_map, buf, 0, w0, oh, img);
           tma_store_commit();
         }
-        // statistics of the finished tile from the staging buffer (rewritten 2 tiles later, behind two barriers)
-        if (p.psum) tile_colstats_smem(buf, et, p.Wo - w0, st_s, st_q);
       }
     }
     if (leader) tma_store_wait_all<0>();
-    if (p.psum) {
-      const size_t o = ((size_t)blockIdx.x * 16 + (et >> 3)) * 64 + (et & 7) * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        p.psum[o + j] = (float)st_s[j];
-        p.psq[o + j] = (float)st_q[j];
-      }
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -340,13 +323,7 @@ static int stem_view(CUtensorMap* m, const void* xs, int N, int Ho, int Wo) {
   return make_tmap_4d(m, xs, 64, Wo, Hs, N, 32, (uint64_t)Ws * 32, (uint64_t)Hs * Ws * 32, 64, kSrTile, 1);
 }
 
-int stem_fwd_ring_grid(int N, int H, int W) {
-  const int n_strips = N * ceil_div((W - 1) / 2 + 1, kSrTile);
-  return n_strips < num_sms() ? n_strips : num_sms();
-}
-
-int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, int N, int H, int W, float* psum,
-                         float* psq, cudaStream_t st) {
+int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, int N, int H, int W, cudaStream_t st) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   StemRingParams p;
   memset(&p, 0, sizeof(p));
@@ -355,8 +332,6 @@ int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, in
   p.tiles_w = ceil_div(Wo, kSrTile);
   p.n_strips = N * p.tiles_w;
   p.out = y;
-  p.psum = psum;
-  p.psq = psq;
   int rc = stem_view(&p.x_map, xs, N, Ho, Wo);
   if (rc) return rc;
   rc = make_tmap_2d(&p.w_map, w_s2d, 256, 64, 512, 64, 64);

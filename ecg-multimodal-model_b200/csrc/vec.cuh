@@ -85,36 +85,6 @@ __device__ __forceinline__ void warp_colstats32(const float (&v)[32], int lane, 
   q += (double)warp_colsum32(b, lane);
 }
 
-// Column statistics of a finished 128-row x 64-channel bf16 staging tile in shared memory (SWIZZLE_128B layout:
-// 16-byte chunk j of row m at chunk j ^ (m & 7)), for 128 threads: thread t owns channels [8*(t&7), +8) of rows
-// (t>>3) + 16k.  8 LDS.128 + ~200 ALU operations per thread and tile -- a third of the shuffle transpose above,
-// which matters for the shallow-K kernels (stem: 16 MMAs per tile, layer1: 36).  Rows >= valid_rows are skipped.
-__device__ __forceinline__ void tile_colstats_smem(const uint8_t* tile, int t, int valid_rows, double (&acc_s)[8],
-                                                   double (&acc_q)[8]) {
-  const int cg = t & 7, rs = t >> 3;
-  float s[8], q[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int row = rs + 16 * k;
-    if (row < valid_rows) {
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(tile + row * 128 + ((cg ^ (row & 7)) << 4)), f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += f[j];
-        q[j] = fmaf(f[j], f[j], q[j]);
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    acc_s[j] += (double)s[j];
-    acc_q[j] += (double)q[j];
-  }
-}
-
 // Block-wide sum for blockDim.x <= 1024 (multiple of 32); every thread receives the result.
 __device__ __forceinline__ float block_sum(float v, float* red /* >= 33 floats of shared memory */) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

@@ -36,8 +36,6 @@ SIGNATURES = {
     "ecgmm_conv2d_fwd": [_p, _p, _p] + [_i] * 10 + [_p],
     "ecgmm_conv2d_fwd_stats_rows": [_i] * 10,
     "ecgmm_conv2d_fwd_stats": [_p, _p, _p, _p, _p] + [_i] * 10 + [_p],
-    "ecgmm_stem_conv_fwd_stats_rows": [_i, _i, _i],
-    "ecgmm_stem_conv_fwd_stats": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "ecgmm_conv2d_dgrad": [_p, _p, _p] + [_i] * 11 + [_p],
     "ecgmm_conv2d_wgrad": [_p, _p, _p] + [_i] * 10 + [_p, _ll, _p],
     "ecgmm_conv2d_wgrad_workspace": [_i] * 10,

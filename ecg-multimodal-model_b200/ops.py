@@ -202,17 +202,12 @@ def stem_weight_prep(w: torch.Tensor) -> torch.Tensor:
     return ws
 
 
-def stem_conv_fwd(xs: torch.Tensor, w_s2d: torch.Tensor, H: int, W: int, want_stats: bool = False):
+def stem_conv_fwd(xs: torch.Tensor, w_s2d: torch.Tensor, H: int, W: int) -> torch.Tensor:
     _chk(xs, BF16, "xs")
     _chk(w_s2d, BF16, "w_s2d")
     N = xs.shape[0]
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty((N, Ho, Wo, 64), dtype=BF16, device=xs.device)
-    if want_stats:
-        part = StatPartials(_shape_query("ecgmm_stem_conv_fwd_stats_rows", N, H, W), 64, xs.device)
-        _timed("stem_fwd", 2.0 * N * Ho * Wo * 64 * 147, "ecgmm_stem_conv_fwd_stats", _ptr(xs), _ptr(w_s2d), _ptr(y),
-               _ptr(part.psum), _ptr(part.psq), N, H, W, _s())
-        return y, part
     _timed("stem_fwd", 2.0 * N * Ho * Wo * 64 * 147, "ecgmm_stem_conv_fwd", _ptr(xs), _ptr(w_s2d), _ptr(y), N, H, W,
            _s())
     return y

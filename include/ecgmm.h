@@ -76,10 +76,6 @@ int ecgmm_stem_weight_prep(const float* w, ecgmm_bf16* w_s2d, void* stream);
 /* y [N][Ho][Wo][64] bf16, Ho = (H+6-7)/2+1 */
 int ecgmm_stem_conv_fwd(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, int N, int H, int W,
                         void* stream);
-/* stem convolution + BatchNorm statistics of its output from the epilogue (see ecgmm_conv2d_fwd_stats) */
-int ecgmm_stem_conv_fwd_stats_rows(int N, int H, int W);
-int ecgmm_stem_conv_fwd_stats(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, float* psum, float* psq,
-                              int N, int H, int W, void* stream);
 /* dw [64][3][7][7] fp32 += sum over pixels (atomic accumulation; caller zeroes dw) */
 int ecgmm_stem_conv_wgrad(const ecgmm_bf16* xs, const ecgmm_bf16* dy, float* dw, int N, int H, int W,
                           void* stream);
@@ -95,7 +91,8 @@ int ecgmm_conv2d_fwd(const ecgmm_bf16* x, const ecgmm_bf16* w_fwd, ecgmm_bf16* y
 /* Same convolution, and the BatchNorm batch statistics of its output produced by the epilogue (no second pass
  * over y): psum / psq [rows][Cout] fp32 receive, per (CTA, epilogue warp) of the kernel, the sum and the sum of
  * squares of every output channel over that warp's pixels -- of the bf16 values as stored.  rows =
- * ecgmm_conv2d_fwd_stats_rows(same shape); ecgmm_bn_finalize(psum, psq, rows, 1, Cout, N*Ho*Wo, ...) folds them
+ * ecgmm_conv2d_fwd_stats_rows(same shape), 0 when the library does not offer it for the shape (1x1 convolutions and
+ * the 64->64 layers: their tiles hold too few MMAs to hide the reduction; use ecgmm_chan_stats); ecgmm_bn_finalize(psum, psq, rows, 1, Cout, N*Ho*Wo, ...) folds them
  * (replaces ecgmm_chan_stats behind torchvision resnet.py:92-97 bn1/bn2 in training mode). */
 int ecgmm_conv2d_fwd_stats_rows(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int padH, int padW);
 int ecgmm_conv2d_fwd_stats(const ecgmm_bf16* x, const ecgmm_bf16* w_fwd, ecgmm_bf16* y, float* psum, float* psq, int N,

@@ -381,7 +381,7 @@ def test_stem_s2d_uint8_equals_totensor_normalize():
 
 # ------------------------------------------------------------------ BatchNorm statistics from the conv epilogues
 @pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride", [
-    (3, 21, 150, 64, 64, 3, 1),     # halo kernel (64 -> 64, W >= 96), ragged right edge
+    (3, 21, 150, 64, 64, 3, 1),     # 64 -> 64 halo kernel: not offered
     (2, 9, 40, 64, 64, 3, 1),       # generic kernel, BN = 64
     (3, 17, 45, 64, 128, 3, 2),     # stride 2, BN = 128
     (2, 12, 31, 128, 256, 1, 2),    # 1x1 downsample, BN = 256
@@ -399,8 +399,8 @@ def test_conv_epilogue_statistics(N, H, W, Cin, Cout, k, stride):
     y0 = ops.conv2d_fwd(x, w_fwd, stride)
     y, part = ops.conv2d_fwd(x, w_fwd, stride, want_stats=True)
     assert torch.equal(y, y0)
-    if k == 1:  # not offered for 1x1 convolutions (too few MMAs per tile to hide it): caller runs the statistics pass
-        assert part is None
+    if k == 1 or (Cin == 64 and Cout == 64 and W >= 96):
+        assert part is None  # not offered (too few MMAs per tile to hide it): the caller runs the statistics pass
         return
     yd = y.double().reshape(-1, Cout)
     s_ref, q_ref = yd.sum(0), (yd * yd).sum(0)
@@ -414,19 +414,3 @@ def test_conv_epilogue_statistics(N, H, W, Cin, Cout, k, stride):
     a = ops.bn_train_stats(y, bn.weight, bn.bias, None, None, None, 1e-5, 0.1)
     b = ops.bn_train_stats(y, bn.weight, bn.bias, None, None, None, 1e-5, 0.1, partials=part)
     assert rel_l2(b.mean, a.mean) < 1e-4 and rel_l2(b.invstd, a.invstd) < 1e-5
-
-
-def test_stem_epilogue_statistics():
-    g = gen("stemstats")
-    H, W = 37, 530
-    x = torch.randn(3, 3, H, W, generator=g).clamp(-1, 1).to(DEV)
-    xs = ops.stem_s2d(x)
-    ws = ops.stem_weight_prep((torch.randn(64, 3, 7, 7, generator=g) / 12).to(DEV))
-    y0 = ops.stem_conv_fwd(xs, ws, H, W)
-    y, part = ops.stem_conv_fwd(xs, ws, H, W, want_stats=True)
-    assert torch.equal(y, y0)
-    yd = y.double().reshape(-1, 64)
-    s = part.psum.view(part.rows, 64).double().sum(0)
-    q = part.psq.view(part.rows, 64).double().sum(0)
-    assert ((s - yd.sum(0)).abs() <= 1e-5 * yd.abs().sum(0) + 1e-6).all()
-    assert ((q - (yd * yd).sum(0)).abs() <= 1e-5 * (yd * yd).sum(0) + 1e-6).all()

@@ -1,8 +1,4 @@
-for seg in 1 2 4 8 16; do
-  echo "=== NH_SEG=$seg batch 64"
-  ECGMM_NH_SEG=$seg python tools/conv_bench.py 64 8 layer1 2>&1 | grep -E "fwd|dgrad"
-done
-for seg in 1 4 16; do
-  echo "=== NH_SEG=$seg batch 256"
-  ECGMM_NH_SEG=$seg python tools/conv_bench.py 256 4 layer1 2>&1 | grep -E "fwd|dgrad"
-done
+echo "=== halo fwd N=64 (normal)"
+python tools/conv_bench.py 64 8 layer1 fwd 2>&1 | grep -E "fwd"
+echo "=== halo fwd EXPERIMENT N=128 MMAs (2x the MMA flops, half of them garbage)"
+ECGMM_EXP_N128=1 python tools/conv_bench.py 64 8 layer1 fwd 2>&1 | grep -E "fwd"
