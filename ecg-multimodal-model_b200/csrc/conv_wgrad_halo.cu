@@ -11,18 +11,30 @@
 // starts s*128 bytes later (the swizzle is a function of the absolute shared-memory address, probed
 // by tools/desc_probe.py, so any 128-byte row is a legal start).  Both operands are MN-major.
 //
-// A stage covers RPS consecutive output rows of a KP-pixel column strip: RPS dy boxes + RPS+R-1 input rows, so
-// an input row is fetched (RPS+R-1)/RPS times instead of R times.  The kernel is bound by L2->SM traffic, not by
-// the MMA floor (ncu: tensor pipe 51 % busy at 66 KB per 1280-clk stage = 52 B/clk/SM with RPS = 1, KP = 128);
-// (KP, RPS) is chosen per layer to minimise the bytes staged per output pixel with >= 3 stages in flight.
+// MMA shape.  M = 128 rows = two (tap, 64-channel Cin slice) atoms, N = BN output channels, K = 16 pixels.
+// BN = 64 everywhere except on layers with >= 64 (cin, cout) slice pairs, where BN = 128 is used (see make_plan
+// for the measurements: the wider N that doubles the rate of the K-major forward MMAs, profiles/
+// r01_mma_n64_vs_n128.txt, does not pay off for these MN-major operands).  A [2 taps x 64] x 128
+// fp32 accumulator is 128 TMEM columns and TMEM has 512: four accumulators = 8 of the 9 taps.  The CTAs of a
+// 3x3 layer therefore come in two TYPES that share one launch:
+//   type A  (cin slice c, cout slice n): taps 0..7 as 4 accumulators                       -> 4 MMA groups per stage
+//   type B  (cin slices 2c and 2c+1, cout slice n): tap 8 of BOTH slices as one accumulator -> 1 MMA group per stage
+// (no half-empty accumulator: the 9 taps of two cin slices are exactly 9 M = 128 groups) and the pixel range
+// (split-K) is divided 4 : 1 between the types so that all CTAs finish together.
+// BN = 64 (Cout = 64, or no workspace): one type, ceil(R*S/2) accumulators, the last one half empty for 3x3.
 //
-// Work decomposition: group = (64-channel slice of Cin) x (64-channel slice of Cout); every group is a
-// [R*S*64] x [64] output held in TMEM as ceil(R*S/2) accumulators of 128 lanes x 64 columns; the
-// pixel range is split across CTAs (split-K) and partial results are combined with fp32 atomics.
+// A stage may cover RPS consecutive output rows (RPS dy boxes + RPS+R-1 input rows).  Measured
+// (profiles/r01_wgrad_shape_sweep.txt): staging fewer bytes per pixel changes nothing -- the kernel is bound by
+// the MMA operand feed, not by L2 -- and short boxes (small KP) hurt, so KP only minimises the pixel slots wasted
+// at the right edge of a row.
+//
+// Split-K partials go to a caller-provided workspace, one [accumulator][BN columns][128 rows] slice per CTA, and
+// wgrad_halo_reduce_kernel folds them in a fixed order (deterministic; fp32 atomics only without workspace).
 #include "common.h"
 #include "ptx.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace ecgmm {
 
@@ -32,16 +44,20 @@ struct alignas(64) WgHaloParams {
   CUtensorMap x_map;   // x  [N][H][W][Cin],   box (64, KP+S-1, 1, 1)
   CUtensorMap dy_map;  // dy [N][Ho][Wo][Cout], box (64, KP, 1, 1)
   float* dw;           // [Cout][Cin][R][S]
-  float* ws;           // optional split-K workspace [group][ksplit][slot][64 cols][128 rows]; NULL -> atomics
+  float* ws;           // split-K workspace (see launch_wgrad_halo); NULL -> atomics (BN = 64 only)
   int R, S, padH, padW;
   int KP, kmma;              // pixels per stage row, KP/16
   int rps;                   // output rows per stage
   int x_box_bytes, x_box_stride, dy_box_bytes, dy_box_stride, stage_bytes, stages;
   int tiles_w, Ho, row_groups, total_kblocks;  // row_groups = ceil(Ho / rps)
-  int cin_chunks, cout_chunks, ksplit;
+  int cin_chunks, cout_tiles;  // Cin / 64, Cout / BN
   int Cin, Cout;
+  // CTA types: blocks [0, nA) are type A (groupsA x ksA), the rest type B (groupsB x ksB); typed == 0: type A only
+  int typed, nA, ksA, ksB, cin_pairs, slotsA;
+  long long wsB_off;  // float offset of the type-B slices in the workspace
 };
 
+template <int BN>
 __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -51,10 +67,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
   uint64_t* tfull = empty + kHaloMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
 
+  constexpr int NB = BN / 64;  // dy boxes (64-channel atoms) per output row
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int RS = p.R * p.S;
-  const int n_slots = (RS + 1) >> 1;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.x_map);
@@ -75,24 +91,37 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // blockIdx -> (k-split id, cin chunk, cout chunk)
-  const int ks = blockIdx.x % p.ksplit;
-  const int g = blockIdx.x / p.ksplit;
-  const int cc = g % p.cin_chunks;
-  const int nt = g / p.cin_chunks;
-  const int per = (p.total_kblocks + p.ksplit - 1) / p.ksplit;
+  // blockIdx -> (type, k-split id, cin slice(s), cout slice)
+  const bool typeB = p.typed && (int)blockIdx.x >= p.nA;
+  const int bid = typeB ? (int)blockIdx.x - p.nA : (int)blockIdx.x;
+  const int ksplit = typeB ? p.ksB : p.ksA;
+  const int ks = bid % ksplit;
+  const int g = bid / ksplit;
+  const int gdiv = typeB ? p.cin_pairs : p.cin_chunks;
+  const int cc = typeB ? 2 * (g % gdiv) : (g % gdiv);  // first (or only) 64-channel Cin slice
+  const int nt = g / gdiv;                             // BN-channel Cout slice
+  const int n_slots = typeB ? 1 : p.slotsA;
+  const bool pair_ok = typeB && (cc + 1 < p.cin_chunks);  // odd slice count: the last type-B CTA has one slice
+  const int per = (p.total_kblocks + ksplit - 1) / ksplit;
   const int kb0 = ks * per;
   const int kb1 = min(p.total_kblocks, kb0 + per);
   const bool has_work = kb0 < kb1;
+  // this CTA's workspace slice: [n_slots][BN][128]
+  float* ws_cta = nullptr;
+  if (p.ws)
+    ws_cta = typeB ? p.ws + p.wsB_off + (size_t)(g * ksplit + ks) * (BN * 128)
+                   : p.ws + (size_t)(g * ksplit + ks) * p.slotsA * (BN * 128);
+  const int n_dy = p.rps * NB;
+  const int x_base = n_dy * p.dy_box_stride;
+  const int n_xrows = typeB ? p.rps : p.rps + p.R - 1;  // input rows staged per Cin slice
 
   if (has_work) {
     if (warp == 0) {
       if (elect_one()) {  // single elected thread: no ELECT serialisation loops around UTMALDG
         int stage = 0;
         uint32_t phase = 0;
-        const int n_xrows = p.rps + p.R - 1;
-        const uint32_t tx = p.rps * p.dy_box_bytes + n_xrows * p.x_box_bytes;
-        const int x_base = p.rps * p.dy_box_stride;
+        const uint32_t tx = n_dy * p.dy_box_bytes + (typeB ? 2 : 1) * n_xrows * p.x_box_bytes;
+        const int row_first = typeB ? p.R - 1 : 0;  // type B only needs the last filter row
         int twi = kb0 % p.tiles_w;
         int row = kb0 / p.tiles_w;  // img * row_groups + row group
         int og = row % p.row_groups, img = row / p.row_groups;
@@ -104,10 +133,16 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
           mbar_expect_tx(&full[stage], tx);
           // rows past Ho / outside the image are zero-filled by TMA and contribute nothing
           for (int j = 0; j < p.rps; ++j)
-            tma_load_4d(st + j * p.dy_box_stride, &p.dy_map, &full[stage], nt * 64, w0, oh0 + j, img);
+            for (int a = 0; a < NB; ++a)
+              tma_load_4d(st + (j * NB + a) * p.dy_box_stride, &p.dy_map, &full[stage], nt * BN + a * 64, w0, oh0 + j,
+                          img);
           for (int r = 0; r < n_xrows; ++r)
             tma_load_4d(st + x_base + r * p.x_box_stride, &p.x_map, &full[stage], cc * 64, w0 - p.padW,
-                        oh0 + r - p.padH, img);
+                        oh0 + row_first + r - p.padH, img);
+          if (typeB)  // second Cin slice (the first one again when there is none: its rows are ignored)
+            for (int r = 0; r < n_xrows; ++r)
+              tma_load_4d(st + x_base + (n_xrows + r) * p.x_box_stride, &p.x_map, &full[stage],
+                          (pair_ok ? cc + 1 : cc) * 64, w0 - p.padW, oh0 + row_first + r - p.padH, img);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -123,33 +158,40 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
       }
     } else if (warp == 1) {
       if (elect_one()) {
-        constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
         const uint32_t s_addr = smem_u32(smem);
-        // per-slot A descriptors relative to the stage base, built once
+        // per-accumulator A descriptors relative to the stage base (output row 0 of the stage), built once
         constexpr int kMaxSlots = 8;
         uint64_t a_rel[kMaxSlots];
 #pragma unroll
         for (int i = 0; i < kMaxSlots; ++i) {
-          const int t0 = min(2 * i, RS - 1), t1 = min(2 * i + 1, RS - 1);
-          const uint32_t a0 = p.rps * p.dy_box_stride + (t0 / p.S) * p.x_box_stride + (t0 % p.S) * 128;
-          const uint32_t a1 = p.rps * p.dy_box_stride + (t1 / p.S) * p.x_box_stride + (t1 % p.S) * 128;
+          uint32_t a0, a1;
+          if (typeB) {  // tap RS-1 of the two Cin slices: same position in two box sets n_xrows boxes apart
+            a0 = x_base + ((RS - 1) % p.S) * 128;
+            a1 = a0 + n_xrows * p.x_box_stride;
+          } else {
+            const int t0 = min(2 * i, RS - 1), t1 = min(2 * i + 1, RS - 1);
+            a0 = x_base + (t0 / p.S) * p.x_box_stride + (t0 % p.S) * 128;
+            a1 = x_base + (t1 / p.S) * p.x_box_stride + (t1 % p.S) * 128;
+          }
           a_rel[i] = make_sw128_desc(s_addr + a0, a1 - a0, 1024);
         }
-        const uint64_t b_rel = make_sw128_desc(s_addr, 0, 1024);
+        const uint64_t b_rel = make_sw128_desc(s_addr, NB > 1 ? p.dy_box_stride : 0, 1024);
         int stage = 0;
         uint32_t phase = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t so = (uint64_t)((stage * p.stage_bytes) >> 4);
-          for (int j = 0; j < p.rps; ++j) {  // output row j of the stage: dy box j against input rows j .. j+R-1
-            const uint64_t ao = so + (uint64_t)((j * p.x_box_stride) >> 4), bo = so + (uint64_t)((j * p.dy_box_stride) >> 4);
+          for (int j = 0; j < p.rps; ++j) {  // output row j of the stage: dy boxes j against input rows j .. j+R-1
+            const uint64_t ao = so + (uint64_t)((j * p.x_box_stride) >> 4);
+            const uint64_t bo = so + (uint64_t)((j * NB * p.dy_box_stride) >> 4);
 #pragma unroll
             for (int i = 0; i < kMaxSlots; ++i) {
               if (i < n_slots) {
                 const uint64_t a_desc = a_rel[i] + ao, b_desc = b_rel + bo;
                 for (int k = 0; k < p.kmma; ++k)  // 16 pixel rows = 2048 B further into both boxes
-                  umma_bf16(tmem_base + i * 64, a_desc + k * 128, b_desc + k * 128, idesc,
+                  umma_bf16(tmem_base + i * BN, a_desc + k * 128, b_desc + k * 128, idesc,
                             (kb > kb0) || (j > 0) || (k > 0));
               }
             }
@@ -168,26 +210,26 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
       mbar_wait(tfull, 0);
       tc_fence_after();
       for (int i = 0; i < n_slots; ++i) {
-        const int tap = 2 * i + (m_row >> 6);
-        const bool ok = tap < RS;
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + i * 64;
-        if (p.ws) {
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + i * BN;
+        if (ws_cta) {
           // split-K partial, column-major so that the 32 lanes (= rows) of a warp store 128 contiguous bytes
-          float* dst0 = p.ws + ((size_t)(g * p.ksplit + ks) * n_slots + i) * (64 * 128) + m_row;
+          float* dst0 = ws_cta + (size_t)i * (BN * 128) + m_row;
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < BN / 32; ++c) {
             uint32_t r[32];
             tmem_ld_32x32(t_addr + c * 32, r);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) dst0[(c * 32 + j) * 128] = __uint_as_float(r[j]);
           }
-        } else {
+        } else {  // BN = 64, one type (the host never launches BN = 128 without a workspace)
+          const int tap = 2 * i + (m_row >> 6);
+          const bool ok = tap < RS;
           const int cin = cc * 64 + (m_row & 63);
-          float* dst0 = p.dw + ((size_t)(nt * 64) * p.Cin + cin) * RS + (ok ? tap : 0);
+          float* dst0 = p.dw + ((size_t)(nt * BN) * p.Cin + cin) * RS + (ok ? tap : 0);
           const size_t col_stride = (size_t)p.Cin * RS;
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < BN / 32; ++c) {
             uint32_t r[32];
             tmem_ld_32x32(t_addr + c * 32, r);
             tmem_ld_wait();
@@ -200,12 +242,12 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
         }
       }
     }
-  } else if (p.ws && warp >= 2) {
+  } else if (ws_cta && warp >= 2) {
     // a CTA without pixels still owns a workspace slice: the reduction kernel reads every slice
     const int m_row = (warp & 3) * 32 + lane;
     for (int i = 0; i < n_slots; ++i) {
-      float* dst0 = p.ws + ((size_t)(g * p.ksplit + ks) * n_slots + i) * (64 * 128) + m_row;
-      for (int c = 0; c < 64; ++c) dst0[c * 128] = 0.f;
+      float* dst0 = ws_cta + (size_t)i * (BN * 128) + m_row;
+      for (int c = 0; c < BN; ++c) dst0[c * 128] = 0.f;
     }
   }
 
@@ -214,21 +256,43 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// Second stage of the split-K reduction: dw[cout][cin][tap] += sum over the ksplit partials.
-__global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw,
-                                                                 int ksplit, int n_slots, int RS, int cin_chunks,
-                                                                 int Cin, size_t total) {
-  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // ((g*n_slots + slot)*64 + c)*128 + m
-  if (idx >= total) return;
+// Second stage of the split-K reduction: dw[cout][cin][tap] += sum over the ksplit partials of the owning CTAs.
+// Thread index = element of one (group, accumulator) result: type-A elements first, then type-B.
+struct WgReduceParams {
+  const float* ws;
+  float* dw;
+  int BN, RS, Cin, cin_chunks, cin_pairs;
+  int slotsA, ksA, ksB;
+  long long totalA, totalB, wsB_off;
+};
+
+__global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const WgReduceParams p) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool typeB = idx >= p.totalA;
+  if (typeB) idx -= p.totalA;
+  if (typeB && idx >= p.totalB) return;
   const int m = (int)(idx & 127);
-  const int c = (int)((idx >> 7) & 63);
-  const size_t gs = idx >> 13;
+  const long long rest = idx >> 7;
+  const int c = (int)(rest % p.BN);
+  const long long gs = rest / p.BN;
+  const int n_slots = typeB ? 1 : p.slotsA;
   const int slot = (int)(gs % n_slots);
   const int g = (int)(gs / n_slots);
-  const int tap = 2 * slot + (m >> 6);
-  if (tap >= RS) return;
-  const size_t slice = (size_t)n_slots * 64 * 128;
-  const float* src = ws + (size_t)g * ksplit * slice + ((size_t)slot * 64 + c) * 128 + m;
+  const int ksplit = typeB ? p.ksB : p.ksA;
+  int tap, chunk, nt;
+  if (typeB) {
+    tap = p.RS - 1;
+    chunk = 2 * (g % p.cin_pairs) + (m >> 6);
+    nt = g / p.cin_pairs;
+    if (chunk >= p.cin_chunks) return;
+  } else {
+    tap = 2 * slot + (m >> 6);
+    chunk = g % p.cin_chunks;
+    nt = g / p.cin_chunks;
+    if (tap >= p.RS) return;
+  }
+  const size_t slice = (size_t)n_slots * p.BN * 128;  // one CTA
+  const float* src = p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + ((size_t)slot * p.BN + c) * 128 + m;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // independent chains: 4+ loads in flight per thread
   int k = 0;
   for (; k + 3 < ksplit; k += 4) {
@@ -239,23 +303,19 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const float* __r
   }
   for (; k < ksplit; ++k) a0 += src[(size_t)k * slice];
   const float acc = (a0 + a1) + (a2 + a3);
-  const int cc = g % cin_chunks, nt = g / cin_chunks;
-  const int cin = cc * 64 + (m & 63), cout = nt * 64 + c;
-  dw[((size_t)cout * Cin + cin) * RS + tap] += acc;
+  const int cin = chunk * 64 + (m & 63), cout = nt * p.BN + c;
+  p.dw[((size_t)cout * p.Cin + cin) * p.RS + tap] += acc;
 }
 
-// Picks (KP, RPS): KP pixels (multiple of 16, <= 128) x RPS output rows per stage.
-// Measured on B200 (tools/conv_bench.py sweep, profiles/r01_wgrad_shape_sweep.txt): the kernel is NOT bound by
-// L2->SM traffic -- halving the staged bytes per pixel (RPS 1 -> 2..7) changes the time by < 4 %, while small KP
-// (more, shorter TMA boxes and MMA runs) costs up to 2x.  What matters is the pixel slots wasted at the right
-// edge of a row, so KP minimises ceil(Wo/KP)*KP (ties: larger KP) and RPS = 2 is taken only where three stages
-// still fit (a small, free reduction of L2 traffic).  The cap is the shared-memory operand bandwidth of the
-// N = 64 MMA shape: 6 KB of operands per 32-clk M128xN64xK16 MMA = 192 B/clk against ~128 B/clk.
+// KP (multiple of 16, <= 128) minimises the pixel slots wasted at the right edge of a row (ties: larger KP); RPS = 2
+// only where three stages still fit (measured: a small, free reduction of L2 traffic, no speed-up by itself).
 static int round1k(int v) { return (v + 1023) & ~1023; }
-static int halo_stage_bytes(int kp, int rps, int R, int S) {
-  return rps * round1k(kp * 128) + (rps + R - 1) * round1k((kp + S - 1) * 128);
+static int halo_stage_bytes(int kp, int rps, int R, int S, int bn, bool typed) {
+  const int xb = round1k((kp + S - 1) * 128);
+  const int a = (rps + R - 1) * xb, b = typed ? 2 * rps * xb : 0;
+  return rps * (bn / 64) * round1k(kp * 128) + (a > b ? a : b);
 }
-static void pick_shape(int Ho, int Wo, int R, int S, int* kp_out, int* rps_out) {
+static void pick_shape(int Ho, int Wo, int R, int S, int bn, bool typed, int* kp_out, int* rps_out) {
   const int budget = 220 * 1024;
   int best_kp = 64;
   long best_cost = -1;
@@ -267,7 +327,7 @@ static void pick_shape(int Ho, int Wo, int R, int S, int* kp_out, int* rps_out) 
     }
   }
   int best_rps = 1;
-  if (Ho >= 2 && 3 * halo_stage_bytes(best_kp, 2, R, S) <= budget) best_rps = 2;
+  if (bn == 64 && Ho >= 2 && 3 * halo_stage_bytes(best_kp, 2, R, S, bn, typed) <= budget) best_rps = 2;
   *kp_out = best_kp;
   *rps_out = best_rps;
   // development knobs (tools/conv_bench.py sweeps): force a shape
@@ -276,7 +336,7 @@ static void pick_shape(int Ho, int Wo, int R, int S, int* kp_out, int* rps_out) 
   if (ekp && erps) {
     const int kp = atoi(ekp), rps = atoi(erps);
     if (kp >= 16 && kp <= 128 && kp % 16 == 0 && rps >= 1 && rps <= (Ho > 1 ? Ho : 1) &&
-        2 * halo_stage_bytes(kp, rps, R, S) <= budget) {
+        2 * halo_stage_bytes(kp, rps, R, S, bn, typed) <= budget) {
       *kp_out = kp;
       *rps_out = rps;
     }
@@ -288,43 +348,96 @@ bool wgrad_halo_supported(int Cin, int Cout, int R, int S, int stride) {
          (S == 3);
 }
 
-static void halo_split(int N, int H, int W, int Cin, int Cout, int R, int S, int padH, int padW, int* kp, int* total_kb,
-                       int* groups, int* ksplit) {
+// The whole decomposition of one problem; shared by the workspace query and the launch.
+struct WgPlan {
+  int bn, typed, slotsA, KP, rps, total_kb;
+  int cin_chunks, cin_pairs, cout_tiles, groupsA, groupsB, ksA, ksB;
+  size_t ws_floats, wsB_off;
+};
+
+static WgPlan make_plan(int N, int H, int W, int Cin, int Cout, int R, int S, int padH, int padW, bool have_ws) {
+  WgPlan q;
+  memset(&q, 0, sizeof(q));
   const int Ho = H + 2 * padH - R + 1, Wo = W + 2 * padW - S + 1;
-  int rps;
-  pick_shape(Ho, Wo, R, S, kp, &rps);
-  *total_kb = N * ceil_div(Ho, rps) * ceil_div(Wo, *kp);
-  *groups = (Cin / 64) * (Cout / 64);
-  int ks = num_sms() / *groups;
-  if (ks < 1) ks = 1;
-  if (ks > *total_kb) ks = *total_kb > 0 ? *total_kb : 1;
-  *ksplit = ks;
+  const int RS = R * S;
+  // Measured (profiles/r01_wgrad_bn128.txt, batch 64): BN = 128 with the two CTA types does NOT beat BN = 64 on
+  // layers 2 and 3 (0.260 / 0.243 ms against 0.217 / 0.228 ms) -- unlike the K-major forward kernels, the MN-major
+  // operand feed does not get faster with the wider N -- and wins only where BN = 64 leaves 2 CTAs per
+  // (cin, cout) slice pair (layer4, 64 pairs: 0.257 against 0.281 ms).  ECGMM_WG_BN = 64 | 128 forces a shape.
+  const char* ebn = getenv("ECGMM_WG_BN");
+  const bool many_groups = (Cin / 64) * (Cout / 64) >= 64;
+  const bool want128 = ebn ? atoi(ebn) == 128 : many_groups;
+  q.bn = (Cout % 128 == 0 && have_ws && want128) ? 128 : 64;
+  const int slots_all = (RS + 1) / 2;
+  q.typed = (q.bn == 128 && slots_all * q.bn > 512) ? 1 : 0;  // does not fit the 512 TMEM columns -> two CTA types
+  q.slotsA = q.typed ? 512 / q.bn : slots_all;                // typed: 4 accumulators = taps 0..7, type B: tap 8
+  pick_shape(Ho, Wo, R, S, q.bn, q.typed != 0, &q.KP, &q.rps);
+  q.total_kb = N * ceil_div(Ho, q.rps) * ceil_div(Wo, q.KP);
+  q.cin_chunks = Cin / 64;
+  q.cin_pairs = (q.cin_chunks + 1) / 2;
+  q.cout_tiles = Cout / q.bn;
+  q.groupsA = q.cin_chunks * q.cout_tiles;
+  q.groupsB = q.typed ? q.cin_pairs * q.cout_tiles : 0;
+  const int sms = num_sms();
+  if (q.typed) {
+    // MMA groups per pixel block: slotsA per type-A group, 1 per type-B group; CTAs in proportion
+    const double per_unit = (double)sms / (double)(q.groupsA * q.slotsA + q.groupsB);
+    q.ksA = (int)(per_unit * q.slotsA);
+    q.ksB = (int)per_unit;
+    if (q.ksA < 1) q.ksA = 1;
+    if (q.ksB < 1) q.ksB = 1;
+  } else {
+    q.ksA = sms / q.groupsA;
+    if (q.ksA < 1) q.ksA = 1;
+    q.ksB = 0;
+  }
+  const int cap = q.total_kb > 0 ? q.total_kb : 1;
+  if (q.ksA > cap) q.ksA = cap;
+  if (q.ksB > cap) q.ksB = cap;
+  q.wsB_off = (size_t)q.groupsA * q.ksA * q.slotsA * q.bn * 128;
+  q.ws_floats = q.wsB_off + (size_t)q.groupsB * q.ksB * q.bn * 128;
+  return q;
 }
 
 size_t wgrad_halo_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S, int padH, int padW) {
-  int kp, total_kb, groups, ksplit;
-  halo_split(N, H, W, Cin, Cout, R, S, padH, padW, &kp, &total_kb, &groups, &ksplit);
-  return (size_t)groups * ksplit * ((R * S + 1) / 2) * 64 * 128 * sizeof(float);
+  const WgPlan q = make_plan(N, H, W, Cin, Cout, R, S, padH, padW, true);
+  return q.ws_floats * sizeof(float);
+}
+
+template <int BN>
+static int launch_typed(const WgHaloParams& p, int grid, int smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    ECGMM_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  wgrad_halo_kernel<BN><<<grid, 192, smem, st>>>(p);
+  return check_launch("wgrad_halo_kernel");
 }
 
 int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int N, int H, int W, int Cin,
                       int Cout, int R, int S, int padH, int padW, void* workspace, size_t ws_bytes,
                       cudaStream_t st) {
   const int Ho = H + 2 * padH - R + 1, Wo = W + 2 * padW - S + 1;
+  // the caller sized the workspace with wgrad_halo_workspace_bytes (the BN = 128 plan when Cout allows it); anything
+  // smaller means "no workspace" and the BN = 64 kernel with atomics
+  const bool have_ws = workspace && ws_bytes >= wgrad_halo_workspace_bytes(N, H, W, Cin, Cout, R, S, padH, padW);
+  const WgPlan q = make_plan(N, H, W, Cin, Cout, R, S, padH, padW, have_ws);
   WgHaloParams p;
   memset(&p, 0, sizeof(p));
   p.R = R;
   p.S = S;
   p.padH = padH;
   p.padW = padW;
-  pick_shape(Ho, Wo, R, S, &p.KP, &p.rps);
+  p.KP = q.KP;
+  p.rps = q.rps;
   p.kmma = p.KP / 16;
   const int xw = p.KP + S - 1;
   p.x_box_bytes = xw * 128;
-  p.x_box_stride = (p.x_box_bytes + 1023) & ~1023;
+  p.x_box_stride = round1k(p.x_box_bytes);
   p.dy_box_bytes = p.KP * 128;
-  p.dy_box_stride = (p.dy_box_bytes + 1023) & ~1023;
-  p.stage_bytes = p.rps * p.dy_box_stride + (p.rps + R - 1) * p.x_box_stride;
+  p.dy_box_stride = round1k(p.dy_box_bytes);
+  p.stage_bytes = halo_stage_bytes(p.KP, p.rps, R, S, q.bn, q.typed != 0);
   int stages = (220 * 1024) / p.stage_bytes;
   if (stages > kHaloMaxStages) stages = kHaloMaxStages;
   ECGMM_CHECK(stages >= 2, ECGMM_ERR_SHAPE, "wgrad_halo: stage of %d bytes does not fit twice", p.stage_bytes);
@@ -332,17 +445,20 @@ int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
   p.tiles_w = ceil_div(Wo, p.KP);
   p.Ho = Ho;
   p.row_groups = ceil_div(Ho, p.rps);
-  p.total_kblocks = N * p.row_groups * p.tiles_w;
-  p.cin_chunks = Cin / 64;
-  p.cout_chunks = Cout / 64;
-  const int groups = p.cin_chunks * p.cout_chunks;
-  int ksplit = num_sms() / groups;
-  if (ksplit < 1) ksplit = 1;
-  if (ksplit > p.total_kblocks) ksplit = p.total_kblocks;
-  p.ksplit = ksplit;
+  p.total_kblocks = q.total_kb;
+  p.cin_chunks = q.cin_chunks;
+  p.cout_tiles = q.cout_tiles;
   p.Cin = Cin;
   p.Cout = Cout;
   p.dw = dw;
+  p.typed = q.typed;
+  p.nA = q.groupsA * q.ksA;
+  p.ksA = q.ksA;
+  p.ksB = q.ksB > 0 ? q.ksB : 1;
+  p.cin_pairs = q.cin_pairs;
+  p.slotsA = q.slotsA;
+  p.wsB_off = (long long)q.wsB_off;
+  p.ws = have_ws ? reinterpret_cast<float*>(workspace) : nullptr;
   const uint64_t e = 2;
   int rc = make_tmap_4d(&p.x_map, x, Cin, W, H, N, (uint64_t)Cin * e, (uint64_t)W * Cin * e, (uint64_t)H * W * Cin * e,
                         64, xw, 1);
@@ -351,20 +467,26 @@ int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
                     (uint64_t)Ho * Wo * Cout * e, 64, p.KP, 1);
   if (rc) return rc;
   const int smem = p.stages * p.stage_bytes + 256 + 1024;
-  static int configured = 0;
-  if (configured < smem) {
-    ECGMM_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = 227 * 1024;
-  }
-  const size_t need = wgrad_halo_workspace_bytes(N, H, W, Cin, Cout, R, S, padH, padW);
-  p.ws = (workspace && ws_bytes >= need) ? reinterpret_cast<float*>(workspace) : nullptr;
-  wgrad_halo_kernel<<<groups * ksplit, 192, smem, st>>>(p);
-  rc = check_launch("wgrad_halo_kernel");
+  const int grid = q.groupsA * q.ksA + q.groupsB * q.ksB;
+  rc = q.bn == 128 ? launch_typed<128>(p, grid, smem, st) : launch_typed<64>(p, grid, smem, st);
   if (rc || !p.ws) return rc;
-  const int n_slots = (R * S + 1) / 2;
-  const size_t total = (size_t)groups * n_slots * 64 * 128;
-  wgrad_halo_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.ws, dw, ksplit, n_slots, R * S,
-                                                                           p.cin_chunks, Cin, total);
+  WgReduceParams r;
+  memset(&r, 0, sizeof(r));
+  r.ws = p.ws;
+  r.dw = dw;
+  r.BN = q.bn;
+  r.RS = R * S;
+  r.Cin = Cin;
+  r.cin_chunks = q.cin_chunks;
+  r.cin_pairs = q.cin_pairs;
+  r.slotsA = q.slotsA;
+  r.ksA = q.ksA;
+  r.ksB = p.ksB;
+  r.totalA = (long long)q.groupsA * q.slotsA * q.bn * 128;
+  r.totalB = (long long)q.groupsB * q.bn * 128;
+  r.wsB_off = (long long)q.wsB_off;
+  const long long total = r.totalA + r.totalB;
+  wgrad_halo_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r);
   return check_launch("wgrad_halo_reduce_kernel");
 }
 

@@ -150,6 +150,12 @@ CASES = [
     ("1x3s2_64_128_1d", 3, 1, 619, 64, 128, 1, 3, 2),
     ("1x1s2_128_256_1d", 2, 1, 310, 128, 256, 1, 1, 2),
     ("3x3s1_64_64_63x625", 2, 63, 625, 64, 64, 3, 3, 1),
+    # weight gradient with N = 128 MMAs: two CTA types (taps 0..7 | tap 8 of a PAIR of Cin slices); odd slice counts
+    ("3x3s1_64_128_oddslices", 2, 11, 50, 64, 128, 3, 3, 1),
+    ("3x3s1_192_256_oddslices", 2, 9, 33, 192, 256, 3, 3, 1),
+    ("3x3s1_128_128_32x313", 3, 32, 313, 128, 128, 3, 3, 1),
+    ("1x3s1_128_128_1d", 3, 1, 310, 128, 128, 1, 3, 1),
+    ("1x3s1_256_256_1d", 2, 1, 155, 256, 256, 1, 3, 1),
 ]
 
 

@@ -24,6 +24,23 @@ def test_conv_case(case):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("bn", ["64", "128"])
+@pytest.mark.parametrize("case", [c for c in chk.CASES if c[7] == 3 and c[8] == 1 and c[5] % 128 == 0],
+                         ids=lambda c: c[0] if isinstance(c, tuple) else str(c))
+def test_wgrad_both_mma_widths(case, bn, monkeypatch):
+    """The weight-gradient kernel picks N = 64 or N = 128 MMAs (two CTA types) per layer; force each on every
+    stride-1 layer with Cout % 128 == 0 (the library reads ECGMM_WG_BN at every call)."""
+    from ecgmm import ops
+
+    monkeypatch.setenv("ECGMM_WG_BN", bn)
+    ops._SHAPE_CACHE.clear()  # workspace sizes depend on the shape
+    results = []
+    assert chk.run_case(*case, results=results)
+    bad = [r for r in results if not r[2]]
+    assert not bad, bad
+    ops._SHAPE_CACHE.clear()
+
+
 @pytest.mark.parametrize("name,N,H,W", [("stem_small", 2, 50, 100), ("stem_odd", 1, 37, 75),
                                         ("stem_250x2500", 2, 250, 2500)])
 def test_stem_case(name, N, H, W):

@@ -1,4 +1,5 @@
-echo "=== halo fwd N=64 (normal)"
-python tools/conv_bench.py 64 8 layer1 fwd 2>&1 | grep -E "fwd"
-echo "=== halo fwd EXPERIMENT N=128 MMAs (2x the MMA flops, half of them garbage)"
-ECGMM_EXP_N128=1 python tools/conv_bench.py 64 8 layer1 fwd 2>&1 | grep -E "fwd"
+python -m pytest tests/test_conv_gpu.py -x -q 2>&1 | tail -5
+echo "=== BN=128 forced (ECGMM_WG_BN=128)"
+ECGMM_WG_BN=128 python tools/conv_bench.py 64 5 3x3 wgrad 2>&1 | grep wgrad
+echo "=== BN=64 forced (ECGMM_WG_BN=64)"
+ECGMM_WG_BN=64 python tools/conv_bench.py 64 5 3x3 wgrad 2>&1 | grep wgrad
