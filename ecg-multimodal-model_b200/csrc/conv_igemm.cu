@@ -373,13 +373,13 @@ int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16
 // Rows of the statistics partials the forward kernel writes for this shape (4 epilogue warps per CTA of the generic
 // kernel).  0 = not offered: the reduction sits in the epilogue, which has slack only when a tile holds many MMAs.
 // Measured at batch 64 (profiles/README.md): layers 2-4 (K >= 576) +0.04 ms on three convolutions against a 0.13 ms
-// statistics pass; the 64->64 halo kernel (36 MMAs per tile) +0.33 ms against 0.28 ms and the stem (16 MMAs) +0.3 ms
+// statistics pass, the 64->128 stride-2 convolution (K = 576) breaks even; the 64->64 halo kernel (36 MMAs per tile) +0.33 ms against 0.28 ms and the stem (16 MMAs) +0.3 ms
 // against 0.2 ms, whether the reduction is a register shuffle transpose or a read-back of the staging tile.
 extern "C" int ecgmm_conv2d_fwd_stats_rows(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int padH,
                                            int padW) {
   if (N <= 0 || check_conv_cfg(Cin, Cout, R, S, stride, padH, padW)) return 0;
   if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY")) return 0;
-  if (R * S * Cin < 512) return 0;
+  if (R * S * Cin < 1152) return 0;
   const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
   NtParams p;
   memset(&p, 0, sizeof(p));

@@ -382,11 +382,13 @@ def test_stem_s2d_uint8_equals_totensor_normalize():
 # ------------------------------------------------------------------ BatchNorm statistics from the conv epilogues
 @pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride", [
     (3, 21, 150, 64, 64, 3, 1),     # 64 -> 64 halo kernel: not offered
-    (2, 9, 40, 64, 64, 3, 1),       # generic kernel, BN = 64
-    (3, 17, 45, 64, 128, 3, 2),     # stride 2, BN = 128
+    (2, 9, 40, 128, 64, 3, 1),      # generic kernel, BN = 64
+    (3, 17, 45, 64, 128, 3, 2),     # stride 2 with K = 576: below the K >= 1152 threshold, not offered
+    (3, 17, 45, 128, 128, 3, 2),    # stride 2, BN = 128
     (2, 12, 31, 128, 256, 1, 2),    # 1x1 downsample, BN = 256
+    (2, 9, 20, 128, 256, 3, 1),     # BN = 256, ragged tiles
     (2, 8, 79, 256, 512, 3, 1),     # two N tiles per pixel tile
-    (5, 1, 310, 128, 128, 3, 1),    # 1-D (H = 1)
+    (5, 1, 310, 512, 128, 3, 1),    # 1-D (H = 1), K = 1536
 ])
 def test_conv_epilogue_statistics(N, H, W, Cin, Cout, k, stride):
     """conv2d_fwd(want_stats=True): same y as without, and the partial rows fold to the exact per-channel sum /
@@ -399,7 +401,7 @@ def test_conv_epilogue_statistics(N, H, W, Cin, Cout, k, stride):
     y0 = ops.conv2d_fwd(x, w_fwd, stride)
     y, part = ops.conv2d_fwd(x, w_fwd, stride, want_stats=True)
     assert torch.equal(y, y0)
-    if k == 1 or (Cin == 64 and Cout == 64 and W >= 96):
+    if k * (1 if H == 1 else k) * Cin < 1152:
         assert part is None  # not offered (too few MMAs per tile to hide it): the caller runs the statistics pass
         return
     yd = y.double().reshape(-1, Cout)
