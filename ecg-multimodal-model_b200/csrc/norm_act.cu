@@ -634,18 +634,23 @@ __device__ __forceinline__ void stem_raw_load(const __nv_bfloat16* __restrict__ 
                                               const __nv_bfloat16* __restrict__ dyp,
                                               const uint8_t* __restrict__ arg, size_t n, int a, int b, int H, int W,
                                               int Ho, int Wo, int CG, int cg, StemRaw& raw) {
+  // one 64-bit base per tensor, the 4 pixels / windows are small constant offsets from it
+  const uint4* xb = reinterpret_cast<const uint4*>(x) + ((n * H + 2 * a) * W + 2 * b) * CG + cg;
+  const size_t ob = ((n * Ho + a) * Wo + b) * CG + cg;
+  const uint4* gb = reinterpret_cast<const uint4*>(dyp) + ob;
+  const uint2* ab = reinterpret_cast<const uint2*>(arg) + ob;
+  const bool h1 = 2 * a + 1 < H, w1 = 2 * b + 1 < W;    // second pixel row / column inside the image
+  const bool oh1 = a + 1 < Ho, ow1 = b + 1 < Wo;        // second window row / column exists
+  const int xrow = W * CG, orow = Wo * CG;
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     const int i = t >> 1, j = t & 1;
-    const int h = 2 * a + i, w = 2 * b + j;
-    raw.ok[t] = (h < H) && (w < W);
-    raw.vx[t] = raw.ok[t] ? ld_stream(reinterpret_cast<const uint4*>(x) + ((n * H + h) * W + w) * CG + cg)
-                          : make_uint4(0, 0, 0, 0);
-    const int oh = a + i, ow = b + j;
-    const bool wok = (oh < Ho) && (ow < Wo);
-    const size_t o = ((n * Ho + (wok ? oh : a)) * Wo + (wok ? ow : b)) * CG + cg;
-    raw.vg[t] = reinterpret_cast<const uint4*>(dyp)[o];
-    raw.va[t] = reinterpret_cast<const uint2*>(arg)[o];
+    raw.ok[t] = (i == 0 || h1) && (j == 0 || w1);
+    raw.vx[t] = raw.ok[t] ? ld_stream(xb + i * xrow + j * CG) : make_uint4(0, 0, 0, 0);
+    const bool wok = (i == 0 || oh1) && (j == 0 || ow1);
+    const int off = wok ? i * orow + j * CG : 0;
+    raw.vg[t] = gb[off];
+    raw.va[t] = ab[off];
     if (!wok) raw.vg[t] = make_uint4(0, 0, 0, 0);
   }
 }
@@ -793,14 +798,24 @@ __device__ __forceinline__ void stem_route(const StemRaw& raw, uint32_t (&dzw)[4
   add(dzw[3], tmp);
 }
 
-__global__ void __launch_bounds__(256, 3) stem_bwd_apply_kernel(
+__global__ void __launch_bounds__(256, 2) stem_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dyp, const uint8_t* __restrict__ arg,
     const float* __restrict__ coefA, const float* __restrict__ coefB, const float* __restrict__ coefD,
     const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ dx, int CG,
     size_t total_blocks_vec, int H, int W, int Ho, int Wo) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_blocks_vec; i += stride) {
-    const int cg = (int)(i % CG);
+  const size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  // CG divides the grid stride (a power of two <= 256), so a thread keeps its channel group for the whole loop and
+  // the five per-channel coefficient vectors live in registers: the kernel was issue-bound (~1040 instructions per
+  // 2x2 block, 80 of them coefficient re-loads inside the pixel loop), not bandwidth-bound.
+  const int cg = (int)(i0 % CG);
+  float A[8], B[8], D[8], sc[8], sh[8];
+  load8f(coefA + cg * 8, A);
+  load8f(coefB + cg * 8, B);
+  load8f(coefD + cg * 8, D);
+  load8f(scale + cg * 8, sc);
+  load8f(shift + cg * 8, sh);
+  for (size_t i = i0; i < total_blocks_vec; i += stride) {
     size_t t = i / CG;
     const int b = (int)(t % Wo);
     t /= Wo;
@@ -810,11 +825,7 @@ __global__ void __launch_bounds__(256, 3) stem_bwd_apply_kernel(
     stem_raw_load(x, dyp, arg, n, a, b, H, W, Ho, Wo, CG, cg, raw);
     uint32_t dzw[4][4];
     stem_route(raw, dzw);
-    const float* A = coefA + cg * 8;
-    const float* B = coefB + cg * 8;
-    const float* D = coefD + cg * 8;
-    const float* sc = scale + cg * 8;
-    const float* sh = shift + cg * 8;
+    uint4* dxb = reinterpret_cast<uint4*>(dx) + ((n * H + 2 * a) * W + 2 * b) * CG + cg;
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
       if (!raw.ok[px]) continue;
@@ -824,19 +835,14 @@ __global__ void __launch_bounds__(256, 3) stem_bwd_apply_kernel(
         const uint32_t xw = word_of(raw.vx[px], k);
         const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw));
         float2 fz = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dzw[px][k]));
-        const float2 s2 = *reinterpret_cast<const float2*>(sc + 2 * k);
-        const float2 h2 = *reinterpret_cast<const float2*>(sh + 2 * k);
-        if (fmaf(fx.x, s2.x, h2.x) <= 0.f) fz.x = 0.f;  // ReLU gate of the pre-pool activation
-        if (fmaf(fx.y, s2.y, h2.y) <= 0.f) fz.y = 0.f;
-        const float2 Ak = *reinterpret_cast<const float2*>(A + 2 * k);
-        const float2 Bk = *reinterpret_cast<const float2*>(B + 2 * k);
-        const float2 Dk = *reinterpret_cast<const float2*>(D + 2 * k);
-        const __nv_bfloat162 v = __floats2bfloat162_rn(fmaf(Ak.x, fz.x, fmaf(Bk.x, fx.x, Dk.x)),
-                                                      fmaf(Ak.y, fz.y, fmaf(Bk.y, fx.y, Dk.y)));
+        if (fmaf(fx.x, sc[2 * k], sh[2 * k]) <= 0.f) fz.x = 0.f;  // ReLU gate of the pre-pool activation
+        if (fmaf(fx.y, sc[2 * k + 1], sh[2 * k + 1]) <= 0.f) fz.y = 0.f;
+        const __nv_bfloat162 v =
+            __floats2bfloat162_rn(fmaf(A[2 * k], fz.x, fmaf(B[2 * k], fx.x, D[2 * k])),
+                                  fmaf(A[2 * k + 1], fz.y, fmaf(B[2 * k + 1], fx.y, D[2 * k + 1])));
         o[k] = *reinterpret_cast<const uint32_t*>(&v);
       }
-      const int h = 2 * a + (px >> 1), w = 2 * b + (px & 1);
-      reinterpret_cast<uint4*>(dx)[((n * H + h) * W + w) * CG + cg] = make_uint4(o[0], o[1], o[2], o[3]);
+      dxb[(px >> 1) * (W * CG) + (px & 1) * CG] = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
@@ -1085,6 +1091,7 @@ extern "C" int ecgmm_bn_bwd_apply(const ecgmm_bf16* x, const ecgmm_bf16* dy, con
       xb, dyb, yb, argmax, coefA, coefB, coefD, scale, shift, se, q, dxb, dzb, C >> 3, vps, total, H, W, Ho, Wo)
   if (mode == 2) {
     ECGMM_CHECK(!dz_out, ECGMM_ERR_ARG, "bn_bwd_apply: mode 2 does not produce dz_out");
+    ECGMM_CHECK(256 % (C >> 3) == 0, ECGMM_ERR_SHAPE, "bn_bwd_apply: mode 2 needs C = 8 * a power of two <= 2048 (got %d)", C);
     const size_t tb = (size_t)N * Ho * Wo * (C >> 3);
     stem_bwd_apply_kernel<<<stream_grid(tb, stem_bwd_apply_kernel), 256, 0, st>>>(xb, dyb, argmax, coefA, coefB, coefD, scale, shift, dxb,
                                                            C >> 3, tb, H, W, Ho, Wo);
