@@ -53,14 +53,13 @@ class GradArena:
         self.offsets = lay.offsets
         self.total = lay.total
         self.flat = torch.zeros(lay.total, dtype=F32, device=device)
-        self._views = {}
 
     def __call__(self, p):
-        v = self._views.get(id(p))
-        if v is None:
-            off, n, shape = self.offsets[id(p)]
-            v = self._views[id(p)] = self.flat[off:off + n].view(shape)
-        return v
+        # A FRESH view every time, never cached: autograd's AccumulateGrad adopts the returned tensor as p.grad only
+        # when nobody else holds a reference to it; otherwise it clones it on the spot -- i.e. BEFORE the
+        # data-parallel all-reduce, which runs asynchronously on this very memory, has delivered the averaged values.
+        off, n, shape = self.offsets[id(p)]
+        return self.flat[off:off + n].view(shape)
 
     def end_of(self, p):
         off, n, _ = self.offsets[id(p)]

@@ -105,3 +105,36 @@ def test_bucketed_allreduce_gloo_world2():
         assert p.exitcode == 0
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] for r in res)
+
+
+def test_param_grads_alias_the_arena():
+    """The contract the overlapped all-reduce relies on: a gradient handed to autograd as a GradArena slice becomes
+    p.grad WITHOUT a copy (AccumulateGrad adopts a tensor nobody else references), so values that the asynchronous
+    all-reduce writes into arena.flat after backward() returned its tensors are what optimizer.step() reads.
+    (A cache of the slice views inside the arena broke exactly this: every p.grad became a pre-reduction clone.)"""
+    from ecgmm.model import GradArena
+
+    w = torch.nn.Parameter(torch.zeros(5, 3))
+    b = torch.nn.Parameter(torch.zeros(7))
+    holder = {}
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w_, b_):
+            return x.clone()
+
+        @staticmethod
+        def backward(ctx, g):
+            G = GradArena([w, b], torch.device("cpu"))
+            G(w).fill_(1.0)  # a kernel writing the gradient; the same accessor is used again for the return value
+            G(b).fill_(2.0)
+            holder["arena"] = G
+            return g, G(w), G(b)
+
+    x = torch.ones(2, requires_grad=True)
+    Fn.apply(x, w, b).sum().backward()
+    G = holder["arena"]
+    lo, hi = G.flat.data_ptr(), G.flat.data_ptr() + G.flat.numel() * 4
+    assert lo <= w.grad.data_ptr() < hi and lo <= b.grad.data_ptr() < hi, "p.grad must alias the arena"
+    G.flat.mul_(0.5)  # what the all-reduce does after the fact
+    assert torch.equal(w.grad, torch.full((5, 3), 0.5)) and torch.equal(b.grad, torch.full((7,), 1.0))
