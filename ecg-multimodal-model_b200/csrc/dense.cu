@@ -414,7 +414,8 @@ __device__ __forceinline__ uint32_t hash_u32(uint64_t k) {  // splitmix64 finali
 // otherwise keep element i iff u(seed, i) >= p; mask_out receives 0 or 1/(1-p).
 __global__ void dropout_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mask_in,
                                    float* __restrict__ y, float* __restrict__ mask_out, size_t n, float p,
-                                   uint64_t seed) {
+                                   uint64_t seed, const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev;  // CUDA-graph replay: the per-step offset lives in device memory
   const float keep_scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float m;
@@ -712,12 +713,13 @@ extern "C" int ecgmm_ce_loss(const float* logits, const long long* labels, float
 }
 
 extern "C" int ecgmm_dropout_fwd(const float* x, const float* mask_in, float* y, float* mask_out, long long n,
-                                 float p, unsigned long long seed, void* stream) {
+                                 float p, unsigned long long seed, const unsigned long long* seed_dev,
+                                 void* stream) {
   ECGMM_CHECK(x && y, ECGMM_ERR_ARG, "dropout_fwd: null pointer");
   ECGMM_CHECK(p >= 0.f && p <= 1.f, ECGMM_ERR_ARG, "dropout_fwd: p=%f", p);
   if (n == 0) return ECGMM_OK;
   dropout_fwd_kernel<<<ew_grid((size_t)n), 256, 0, (cudaStream_t)stream>>>(x, mask_in, y, mask_out, (size_t)n, p,
-                                                                         seed);
+                                                                         seed, seed_dev);
   return check_launch("dropout_fwd_kernel");
 }
 

@@ -66,7 +66,7 @@ SIGNATURES = {
     "ecgmm_var_loss_fwd": [_p] * 6 + [_i] * 4 + [_p],
     "ecgmm_var_loss_bwd": [_p] * 5 + [_i] * 3 + [_p],
     "ecgmm_ce_loss": [_p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _p, _p],
-    "ecgmm_dropout_fwd": [_p, _p, _p, _p, _ll, _f, c_ulonglong, _p],
+    "ecgmm_dropout_fwd": [_p, _p, _p, _p, _ll, _f, c_ulonglong, _p, _p],
     "ecgmm_mask_bwd": [_p, _p, _p, _p, _ll, _p],
     "ecgmm_zscore": [_p, _p, _ll, _i, _f, _p],
     "ecgmm_butter_lowpass": [_i, _d, POINTER(c_double), POINTER(c_double), POINTER(c_double)],
@@ -79,6 +79,8 @@ SIGNATURES = {
     # optimizer
     "ecgmm_adam_chunk_bytes": [],
     "ecgmm_adam_step": [_p, _i, _f, _f, _f, _f, _f, _ll, _f, _p],
+    "ecgmm_step_advance": [_p, _p],
+    "ecgmm_adam_step_dev": [_p, _i, _p, _f, _f, _f, _f, _p, _f, _p],
 }
 _RESTYPES = {"ecgmm_last_error": c_char_p, "ecgmm_stem_s2d_dims": None, "ecgmm_launch_count": c_ulonglong,
              "ecgmm_conv2d_wgrad_workspace": c_longlong, "ecgmm_signal_preprocess_workspace": c_longlong}

@@ -475,13 +475,19 @@ def layernorm_bwd(x, dy, gamma, mean, rstd, dgamma=None, dbeta=None, need_dx=Tru
     return dx
 
 
+# Set by ecgmm.graph while a training step is being captured: a device int64[2] (step count, dropout seed offset).
+# Dropout kernels then add the offset word to their (frozen) seed, so every replay draws a new mask.
+GRAPH_STATE = None
+
+
 def dropout_fwd(x, p, seed, mask_in=None):
     """Returns (y, mask) with mask holding 0 or 1/(1-p)."""
     _chk(x, F32, "x")
     y = torch.empty_like(x)
     mask = torch.empty_like(x) if mask_in is None else mask_in
+    seed_dev = GRAPH_STATE.data_ptr() + 8 if (GRAPH_STATE is not None and mask_in is None) else None
     lib.call("ecgmm_dropout_fwd", _ptr(x), _ptr(mask_in), _ptr(y), _ptr(mask if mask_in is None else None),
-             x.numel(), float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _s())
+             x.numel(), float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, seed_dev, _s())
     return y, mask
 
 

@@ -23,6 +23,8 @@ class Adam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self.grad_scale = float(grad_scale)
         self._tables = {}
+        self._graph_mode = None  # (device step state, device lr vector) while ecgmm.graph captures a step
+        self._reserved = {}      # group index -> (pinned host table, device table) for captured steps
 
     def _table(self, gi, entries):
         """Device chunk table for group gi, rebuilt only when a pointer changed."""
@@ -35,10 +37,33 @@ class Adam(torch.optim.Optimizer):
             for off in range(0, n, CHUNK):
                 cnt = min(CHUNK, n - off)
                 rows.append((p + 4 * off, g + 4 * off, m + 4 * off, v + 4 * off, cnt))
-        host = torch.from_numpy(np.asarray(rows, dtype=np.int64).reshape(-1, 5)).pin_memory()
-        table = host.to(entries[0][0].device, non_blocking=True)
+        arr = np.asarray(rows, dtype=np.int64).reshape(-1, 5)
+        reserved = self._reserved.get(gi[0] if isinstance(gi, tuple) else gi)
+        if self._graph_mode is not None and reserved is not None:
+            # inside a stream capture nothing may be allocated on the host: use the buffers reserve_tables() pinned
+            host, dev = reserved
+            if len(rows) > host.shape[0]:
+                raise lib.EcgmmError("reserved Adam chunk table too small")
+            host[: len(rows)].copy_(torch.from_numpy(arr))
+            table = dev[: len(rows)]
+            table.copy_(host[: len(rows)], non_blocking=True)
+        else:
+            host = torch.from_numpy(arr).pin_memory()
+            table = host.to(entries[0][0].device, non_blocking=True)
         self._tables[gi] = (key, table, len(rows), host)
         return table, len(rows)
+
+    def reserve_tables(self):
+        """Pin host memory and allocate device memory for every group's chunk table (called by ecgmm.graph before a
+        capture, where neither allocation is allowed)."""
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.requires_grad]
+            if not ps:
+                continue
+            n_rows = sum((p.numel() + CHUNK - 1) // CHUNK for p in ps)
+            host = torch.empty((n_rows, 5), dtype=torch.int64).pin_memory()
+            dev = torch.empty((n_rows, 5), dtype=torch.int64, device=ps[0].device)
+            self._reserved[gi] = (host, dev)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -71,6 +96,17 @@ class Adam(torch.optim.Optimizer):
             steps = {int(self.state[e[0]]["step"]) for e in entries}
             b1, b2 = group["betas"]
             # parameters that joined late (different step count) get their own launch
+            if self._graph_mode is not None:
+                # captured step: learning rate and step count come from device memory at replay time
+                if len(steps) != 1:
+                    raise lib.EcgmmError("a captured step needs all parameters of a group at the same step count")
+                state_dev, lr_dev = self._graph_mode
+                table, n = self._table((gi, -1), entries)
+                lib.call("ecgmm_adam_step_dev", ctypes.c_void_p(table.data_ptr()), n, lr_dev.data_ptr() + 4 * gi,
+                         float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                         state_dev.data_ptr(), self.grad_scale, ops._s())
+                torch.autograd.graph.increment_version([e[0] for e in entries])
+                continue
             for stp in sorted(steps):
                 sub = [e for e in entries if int(self.state[e[0]]["step"]) == stp]
                 table, n = self._table((gi, stp if len(steps) > 1 else -1), sub)

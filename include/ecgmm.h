@@ -224,9 +224,10 @@ int ecgmm_var_loss_bwd(const float* f, const float* row_mean, const float* coef,
  * dlogits (may be NULL) = gscale * dloss/dlogits.  *bad_label is set to 1 on an out-of-range label. */
 int ecgmm_ce_loss(const float* logits, const long long* labels, float* loss, float* dlogits, int B, int C, int focal,
                   float alpha, float gamma, float gscale, int* bad_label, void* stream);
-/* y = x*mask; mask_in given (0 or 1/(1-p)) or drawn from (seed, element index); mask_out may be NULL */
+/* y = x*mask; mask_in given (0 or 1/(1-p)) or drawn from (seed, element index); mask_out may be NULL.
+ * seed_dev (may be NULL): device word added to seed at run time -- the per-step offset of a captured CUDA graph */
 int ecgmm_dropout_fwd(const float* x, const float* mask_in, float* y, float* mask_out, long long n, float p,
-                      unsigned long long seed, void* stream);
+                      unsigned long long seed, const unsigned long long* seed_dev, void* stream);
 /* dx = dy * mask * (y > 0); y and mask may be NULL */
 int ecgmm_mask_bwd(const float* dy, const float* y, const float* mask, float* dx, long long n, void* stream);
 /* BatchNorm1d (+ReLU) over a small fp32 matrix [B][C]: clinical MLP, multimodal_paper_modal_balance.py:258.
@@ -279,6 +280,13 @@ int ecgmm_head_tail(const ecgmm_bf16* hidden, const float* b1, const float* w2, 
 int ecgmm_adam_chunk_bytes(void);
 int ecgmm_adam_step(const void* chunk_table, int n_chunks, float lr, float beta1, float beta2, float eps,
                     float weight_decay, long long step, float grad_scale, void* stream);
+/* The same step with the learning rate and the step count read from DEVICE memory, for replay inside a CUDA graph
+ * (kernel arguments are frozen at capture; train.py:158-161 and OneCycleLR change lr between steps).
+ * ecgmm_step_advance(state): state[0] += 1 (the step count ecgmm_adam_step_dev reads), state[1] += odd constant (the
+ * seed_dev word of ecgmm_dropout_fwd); captured at the head of the graph so that every replay sees fresh values. */
+int ecgmm_step_advance(long long* state, void* stream);
+int ecgmm_adam_step_dev(const void* chunk_table, int n_chunks, const float* lr_dev, float beta1, float beta2, float eps,
+                        float weight_decay, const long long* step_dev, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -3,6 +3,7 @@ launch list CSV (--metrics gpu__time_duration.sum).
 
     python tools/ncu_summary.py report.ncu-rep > profiles/rNN_xxx.txt
     python tools/ncu_summary.py launches.csv  > profiles/rNN_launches.txt
+    python tools/ncu_summary.py xxx_full_raw.csv > profiles/rNN_xxx.txt      (raw page exported on the GPU box)
 """
 import collections
 import csv
@@ -37,7 +38,10 @@ def to_us(v, unit):
 
 
 def from_report(path):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):  # `ncu -i x.ncu-rep --page raw --csv` already run on the GPU box (tools/ncu_step.sh)
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {k: hdr.index(k) for k, _ in KEYS if k in hdr}
@@ -85,4 +89,4 @@ def from_launches(path):
 
 if __name__ == "__main__":
     p = sys.argv[1]
-    (from_report if p.endswith(".ncu-rep") else from_launches)(p)
+    (from_report if (p.endswith(".ncu-rep") or p.endswith("_raw.csv")) else from_launches)(p)
