@@ -104,3 +104,11 @@ def shard_batch(tensors, rank, world):
         per = B // world
         out.append(t[rank * per:(rank + 1) * per])
     return out
+
+
+def folds_for_rank(n_folds, rank, world):
+    """Cross-validation folds are independent training jobs (train_kfold.py:151-155 runs them one after another):
+    fold k goes to rank k mod world, no communication between them (SURVEY.md section 8e, configs[4])."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    return [k for k in range(int(n_folds)) if k % world == rank]

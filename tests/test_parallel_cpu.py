@@ -138,3 +138,17 @@ def test_param_grads_alias_the_arena():
     assert lo <= w.grad.data_ptr() < hi and lo <= b.grad.data_ptr() < hi, "p.grad must alias the arena"
     G.flat.mul_(0.5)  # what the all-reduce does after the fact
     assert torch.equal(w.grad, torch.full((5, 3), 0.5)) and torch.equal(b.grad, torch.full((7,), 1.0))
+
+
+def test_folds_are_partitioned_over_ranks():
+    from ecgmm.parallel import folds_for_rank
+
+    for n_folds, world in ((5, 8), (5, 2), (15, 4), (3, 1)):
+        seen = sorted(k for r in range(world) for k in folds_for_rank(n_folds, r, world))
+        assert seen == list(range(n_folds))
+        sizes = [len(folds_for_rank(n_folds, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+    import pytest
+
+    with pytest.raises(ValueError):
+        folds_for_rank(5, 3, 2)

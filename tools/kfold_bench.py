@@ -1,0 +1,116 @@
+"""configs[4]: train_kfold.py-style 5-fold training with the folds sharded across the GPUs of one box, on a synthetic
+tri-modal data set (development / profiles helper).
+
+    python tools/kfold_bench.py [--patients 10000] [--folds 5] [--epochs 1] [--batch 64] [--height 64 --width 160]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/kfold_bench.py
+
+Folds are independent jobs: fold k runs on rank k mod world (ecgmm.parallel.folds_for_rank), no collective on the data
+path; rank 0 gathers the per-fold wall times and accuracies at the end.  StratifiedKFold(5, shuffle, seed 42) as in
+train_kfold.py:137.  The data set is synthetic and SEPARABLE (the label shifts the clinical features and the signal
+amplitude), so the held-out accuracy shows that the folds really train; the default image size is 64x160 to keep
+10 000 patients in memory -- pass --height 250 --width 2500 --patients 2000 for the native resolution.
+Each fold uses ecgmm.graph.GraphedTrainStep (one launch per step) with fusion_only=True (the single-tensor API of
+train_kfold.py:59-64)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--patients", type=int, default=10000)
+    ap.add_argument("--folds", type=int, default=5)
+    ap.add_argument("--epochs", type=int, default=1)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--height", type=int, default=64)
+    ap.add_argument("--width", type=int, default=160)
+    ap.add_argument("--length", type=int, default=2476)
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sklearn.model_selection import StratifiedKFold
+
+    import ecgmm
+    from ecgmm import lib
+    from ecgmm import nn as enn
+    from ecgmm import optim as eoptim
+    from ecgmm.graph import GraphedTrainStep
+    from ecgmm.parallel import folds_for_rank
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    lib.require_device()
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    g = torch.Generator().manual_seed(42)
+    P = args.patients
+    labels = (torch.rand(P, generator=g) < 0.4).long()
+    images = torch.randint(0, 256, (P, 3, args.height, args.width), generator=g, dtype=torch.uint8)  # raw pixels
+    sig = torch.randn(P, args.length, generator=g) * (1.0 + 0.5 * labels.float()).unsqueeze(1)
+    clin = torch.randn(P, 24, generator=g) + 0.8 * labels.float().unsqueeze(1)
+    skf = StratifiedKFold(n_splits=args.folds, shuffle=True, random_state=42)
+    splits = list(skf.split(np.arange(P), labels.numpy()))
+    results = []
+    for k in folds_for_rank(args.folds, rank, world):
+        tr, te = splits[k]
+        tr = torch.from_numpy(tr)
+        te = torch.from_numpy(te)
+
+        class Cfg:
+            num_classes = 2
+            device = dev
+
+        torch.manual_seed(42 + k)
+        model = ecgmm.ECGMultimodalModel(Cfg, fusion_only=True).train()
+        crit = enn.CrossEntropyLoss()
+        opt = eoptim.Adam(model.parameters(), lr=1e-3)
+        B = args.batch
+
+        def batch_of(idx):
+            return [images[idx].to(dev, non_blocking=True), sig[idx].to(dev), clin[idx].to(dev), labels[idx].to(dev)]
+
+        step = GraphedTrainStep(model, crit, opt, batch_of(tr[:B]))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        seen = 0
+        for ep in range(args.epochs):
+            perm = tr[torch.randperm(len(tr), generator=g)]
+            for i in range(0, len(perm) - B + 1, B):
+                step(*batch_of(perm[i:i + B]))
+                seen += B
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        model.eval()
+        correct = 0
+        with torch.no_grad():
+            for i in range(0, len(te), 256):
+                idx = te[i:i + 256]
+                out = model(images[idx].to(dev), sig[idx].to(dev), clin[idx].to(dev))
+                correct += int((out.argmax(1).cpu() == labels[idx]).sum())
+        results.append({"fold": k, "rank": rank, "train_samples": seen, "seconds": round(dt, 3),
+                        "samples_per_s": round(seen / dt, 1), "heldout_acc": round(correct / len(te), 4)})
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, results)
+        results = [r for part in gathered for r in part]
+        dist.destroy_process_group()
+    if rank == 0:
+        results.sort(key=lambda r: r["fold"])
+        print(json.dumps({"metric": "k-fold training, folds sharded over GPUs", "n_gpus": world,
+                          "config": {"workload": "configs[4]", "patients": P, "folds": args.folds, "epochs": args.epochs,
+                                     "image": [3, args.height, args.width], "batch": args.batch, "input": "uint8 pixels"},
+                          "wall_s_max_over_folds": max(r["seconds"] for r in results),
+                          "samples_per_s_sum": round(sum(r["samples_per_s"] for r in results), 1), "folds": results}))
+
+
+if __name__ == "__main__":
+    main()
