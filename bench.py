@@ -346,12 +346,23 @@ def run_ours(args):
     roofline = None
     if dom:
         k = kernels[dom]
-        kname = {"conv_wgrad": "igemm_tn_kernel (conv weight-gradient)", "conv_fwd": "igemm_nt_kernel (conv forward)",
-                 "conv_dgrad": "igemm_nt_kernel (conv data-gradient)"}.get(dom, dom)
+        kname = {"conv_wgrad": "wgrad_halo_kernel + igemm_tn_kernel (conv weight-gradient)",
+                 "conv_fwd": "igemm_nt_kernel + igemm_nt_halo_kernel (conv forward)",
+                 "conv_dgrad": "igemm_nt_kernel + igemm_nt_halo_kernel (conv data-gradient)"}.get(dom, dom)
+        # DRAM bytes per launch of this class from the committed `ncu --set full` capture (profiles/r01_traffic.json,
+        # taken at per-GPU batch 64 through tools/ncu_pick.sh), scaled to this run's per-GPU batch
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            ent = tj.get("classes", {}).get(dom)
+            if ent:
+                traffic = ent["dram_bytes_per_launch"] * B / tj["per_gpu_batch"]
+                traffic_src = tj.get("source")
         roofline = {"kernel": kname, "bound": k["bound"], "achieved": k["achieved"],
                     "peak": tf_peak if k["bound"] == "tensor" else hbm_peak, "unit": k["unit"], "frac": k["frac"],
-                    "traffic": None, "peak_source": src, "share_of_step": round(classes[dom]["ms"] / ms_per_step, 4),
-                    "launches_per_step": k["launches"]}
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": src,
+                    "share_of_step": round(classes[dom]["ms"] / ms_per_step, 4), "launches_per_step": k["launches"]}
     conv_ms = sum(c["ms"] for kd, c in classes.items() if kd.startswith("conv") or kd.startswith("stem"))
     conv_flops = sum(c["work"] for kd, c in classes.items() if kd.startswith("conv") or kd.startswith("stem"))
 

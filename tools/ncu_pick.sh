@@ -20,8 +20,8 @@ pick() {  # name regex launches-to-skip launches-to-capture
   fi
 }
 # per step: 17 wgrad_halo (first 3: layer4 with BN=128 types; last 4 of the image encoder: layer1), 12 halo, ...
-pick wgrad_l4   "wgrad_halo_kernel"   34 1
-pick wgrad_l1   "wgrad_halo_kernel"   46 1
+# the whole weight-gradient class of the third step (bench.py's roofline object: 27 launches): DRAM traffic per launch
+pick wgrad_all  "wgrad_halo_kernel|igemm_tn_kernel" 54 27
 pick nt_halo    "igemm_nt_halo"       26 2
 pick nt_256     "igemm_nt_kernel<256" 50 2
 pick nt_128     "igemm_nt_kernel<128" 40 2
