@@ -266,11 +266,16 @@ struct WgReduceParams {
   long long totalA, totalB, wsB_off;
 };
 
+// A CTA folds 64 consecutive result elements; its 256 threads are 64 elements x 4 interleaved k-groups (k = kg, kg+4,
+// ...), each with 4 independent accumulators: 16 partial loads in flight per element instead of 4 (the fold of the
+// 148 x 160 KB layer1 partials took 29 us, ~0.8 TB/s).  Fixed summation order -> deterministic.
 __global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const WgReduceParams p) {
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const bool typeB = idx >= p.totalA;
+  __shared__ float red[4][64];
+  const int o = threadIdx.x & 63, kg = threadIdx.x >> 6;
+  long long idx = blockIdx.x * 64LL + o;
+  const bool typeB = idx >= p.totalA;  // totalA is a multiple of 64: a CTA never straddles the two regions
   if (typeB) idx -= p.totalA;
-  if (typeB && idx >= p.totalB) return;
+  const bool in_range = !typeB || idx < p.totalB;
   const int m = (int)(idx & 127);
   const long long rest = idx >> 7;
   const int c = (int)(rest % p.BN);
@@ -280,31 +285,41 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const WgReducePa
   const int g = (int)(gs / n_slots);
   const int ksplit = typeB ? p.ksB : p.ksA;
   int tap, chunk, nt;
+  bool live = in_range;
   if (typeB) {
     tap = p.RS - 1;
     chunk = 2 * (g % p.cin_pairs) + (m >> 6);
     nt = g / p.cin_pairs;
-    if (chunk >= p.cin_chunks) return;
+    live = live && chunk < p.cin_chunks;
   } else {
     tap = 2 * slot + (m >> 6);
     chunk = g % p.cin_chunks;
     nt = g / p.cin_chunks;
-    if (tap >= p.RS) return;
+    live = live && tap < p.RS;
   }
-  const size_t slice = (size_t)n_slots * p.BN * 128;  // one CTA
-  const float* src = p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + ((size_t)slot * p.BN + c) * 128 + m;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // independent chains: 4+ loads in flight per thread
-  int k = 0;
-  for (; k + 3 < ksplit; k += 4) {
-    a0 += src[(size_t)k * slice];
-    a1 += src[(size_t)(k + 1) * slice];
-    a2 += src[(size_t)(k + 2) * slice];
-    a3 += src[(size_t)(k + 3) * slice];
+  float acc = 0.f;
+  if (live) {
+    const size_t slice = (size_t)n_slots * p.BN * 128;  // one CTA of the producer kernel
+    const float* src =
+        p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + ((size_t)slot * p.BN + c) * 128 + m;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = kg;
+    for (; k + 12 < ksplit; k += 16) {
+      a0 += src[(size_t)k * slice];
+      a1 += src[(size_t)(k + 4) * slice];
+      a2 += src[(size_t)(k + 8) * slice];
+      a3 += src[(size_t)(k + 12) * slice];
+    }
+    for (; k < ksplit; k += 4) a0 += src[(size_t)k * slice];
+    acc = (a0 + a1) + (a2 + a3);
   }
-  for (; k < ksplit; ++k) a0 += src[(size_t)k * slice];
-  const float acc = (a0 + a1) + (a2 + a3);
-  const int cin = chunk * 64 + (m & 63), cout = nt * p.BN + c;
-  p.dw[((size_t)cout * p.Cin + cin) * p.RS + tap] += acc;
+  red[kg][o] = acc;
+  __syncthreads();
+  if (kg == 0 && live) {
+    const float total = (red[0][o] + red[1][o]) + (red[2][o] + red[3][o]);
+    const int cin = chunk * 64 + (m & 63), cout = nt * p.BN + c;
+    p.dw[((size_t)cout * p.Cin + cin) * p.RS + tap] += total;
+  }
 }
 
 // KP (multiple of 16, <= 128) minimises the pixel slots wasted at the right edge of a row (ties: larger KP); RPS = 2
@@ -485,8 +500,8 @@ int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
   r.totalA = (long long)q.groupsA * q.slotsA * q.bn * 128;
   r.totalB = (long long)q.groupsB * q.bn * 128;
   r.wsB_off = (long long)q.wsB_off;
-  const long long total = r.totalA + r.totalB;
-  wgrad_halo_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r);
+  const long long total = r.totalA + r.totalB;  // both multiples of 64 (BN * 128 elements per accumulator)
+  wgrad_halo_reduce_kernel<<<(unsigned)((total + 63) / 64), 256, 0, st>>>(r);
   return check_launch("wgrad_halo_reduce_kernel");
 }
 

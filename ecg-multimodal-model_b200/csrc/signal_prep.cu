@@ -10,7 +10,8 @@
 // parallel axis is the signal: one thread per signal (B x leads signals per batch), 32 signals per CTA.
 // The float64 scratch row of a signal lives TIME-MAJOR in the caller's workspace (ws[t][signal]), so the 32
 // lanes of a warp touch 32 consecutive doubles at every time step (coalesced); the recurrence itself is two
-// dependent DFMAs per sample (direct form II transposed), which bounds the kernel: ~2*(L+36) steps per pass.
+// dependent DFMAs per sample (direct form II transposed); with ~1 warp per SM the L2 latency of the samples has to be
+// hidden by software prefetch (iir_pass).
 //
 // Host side: the Butterworth design (analog prototype -> pre-warp -> bilinear transform -> polynomial
 // expansion) and the steady-state initial condition of filtfilt (lfilter_zi) are computed here in double
@@ -41,6 +42,32 @@ __device__ __forceinline__ double iir_step(const IirCoef& c, double (&z)[kMaxOrd
   return y;
 }
 
+// One filter pass over n samples of a time-major scratch row, forward (t0, t0+1, ...) or backward (t0, t0-1, ...).
+// A signal is one thread and there is about one warp per SM, so nothing hides the ~700-clock L2 latency of the next
+// sample unless it is in flight early: samples are fetched in chunks of CH, the NEXT chunk is issued before the
+// current one is filtered (16 samples x 2 dependent DFMA each ~ one latency).  emit(t, y) consumes the output.
+template <int ORDER, bool REVERSE, typename Emit>
+__device__ __forceinline__ void iir_pass(const double* w, long long ld, int t0, int n, const IirCoef& c,
+                                         double (&z)[kMaxOrder], Emit&& emit) {
+  constexpr int CH = 16;
+  double cur[CH], nxt[CH];
+  auto at = [&](int k) { return REVERSE ? t0 - k : t0 + k; };
+#pragma unroll
+  for (int k = 0; k < CH; ++k) cur[k] = k < n ? w[(long long)at(k) * ld] : 0.0;
+  for (int done = 0; done < n; done += CH) {
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int kk = done + CH + k;
+      nxt[k] = kk < n ? w[(long long)at(kk) * ld] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+      if (done + k < n) emit(at(done + k), iir_step<ORDER>(c, z, cur[k]));
+#pragma unroll
+    for (int k = 0; k < CH; ++k) cur[k] = nxt[k];
+  }
+}
+
 // ws: [L + 2*edge][ld] doubles, ld = number of signals rounded up to 32.
 template <typename TIn, int ORDER>
 __global__ void __launch_bounds__(32) signal_preprocess_kernel(const TIn* __restrict__ x, float* __restrict__ out,
@@ -61,14 +88,28 @@ __global__ void __launch_bounds__(32) signal_preprocess_kernel(const TIn* __rest
     const double inv = 1.0 / (double)window;
     double S = 0.0;
     for (int t = 0; t <= hi && t < L; ++t) S += (double)xr[t];
-#pragma unroll 4
-    for (int i = 0; i < L; ++i) {
-      w[(long long)(edge + i) * ld] = (double)xr[i] - S * inv;
-      if (i + 1 + hi < L) S += (double)xr[i + 1 + hi];
-      if (i - lo >= 0) S -= (double)xr[i - lo];
+    constexpr int CH = 8;  // the running sum is the only dependence: 3 x CH independent loads per trip
+    for (int i0 = 0; i0 < L; i0 += CH) {
+      double xa[CH], xin[CH], xout[CH];
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        const int i = i0 + k;
+        xa[k] = i < L ? (double)xr[i] : 0.0;
+        xin[k] = (i + 1 + hi < L) ? (double)xr[i + 1 + hi] : 0.0;
+        xout[k] = (i - lo >= 0 && i < L) ? (double)xr[i - lo] : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        const int i = i0 + k;
+        if (i < L) {
+          w[(long long)(edge + i) * ld] = xa[k] - S * inv;
+          S += xin[k];
+          S -= xout[k];
+        }
+      }
     }
   } else {
-#pragma unroll 4
+#pragma unroll 8
     for (int i = 0; i < L; ++i) w[(long long)(edge + i) * ld] = (double)xr[i];
   }
   double s1 = 0.0;
@@ -85,47 +126,49 @@ __global__ void __launch_bounds__(32) signal_preprocess_kernel(const TIn* __rest
     const double x0 = w[0];
 #pragma unroll
     for (int k = 0; k < ORDER; ++k) z[k] = c.zi[k] * x0;
-#pragma unroll 4
-    for (int t = 0; t < n; ++t) {
-      double* p = w + (long long)t * ld;
-      *p = iir_step<ORDER>(c, z, *p);
-    }
-    // ---- backward pass; the un-padded part is the result
+    iir_pass<ORDER, false>(w, ld, 0, n, c, z, [&](int t, double y) { w[(long long)t * ld] = y; });
+    // ---- backward pass from the end down to `edge`; the un-padded part is the result
     const double xl = w[(long long)(n - 1) * ld];
 #pragma unroll
     for (int k = 0; k < ORDER; ++k) z[k] = c.zi[k] * xl;
-#pragma unroll 4
-    for (int t = n - 1; t >= edge; --t) {
-      double* p = w + (long long)t * ld;
-      const double y = iir_step<ORDER>(c, z, *p);
+    iir_pass<ORDER, true>(w, ld, n - 1, n - edge, c, z, [&](int t, double y) {
       if (t < edge + L) {
         if (zscore) {
-          *p = y;
+          w[(long long)t * ld] = y;
           s1 += y;
         } else {
           outr[t - edge] = (float)y;
         }
       }
-    }
+    });
   } else {
     if (!zscore) {
-#pragma unroll 4
+#pragma unroll 8
       for (int i = 0; i < L; ++i) outr[i] = (float)w[(long long)(edge + i) * ld];
     } else {
+#pragma unroll 8
       for (int i = 0; i < L; ++i) s1 += w[(long long)(edge + i) * ld];
     }
   }
   if (zscore) {
     const double mean = s1 / (double)L;
-    double q = 0.0;
-#pragma unroll 4
-    for (int i = 0; i < L; ++i) {
-      const double d = w[(long long)(edge + i) * ld] - mean;
-      q = fma(d, d, q);
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;  // independent chains: the loads, not the adds, should pace this
+    int i = 0;
+    for (; i + 3 < L; i += 4) {
+      const double d0 = w[(long long)(edge + i) * ld] - mean, d1 = w[(long long)(edge + i + 1) * ld] - mean;
+      const double d2 = w[(long long)(edge + i + 2) * ld] - mean, d3 = w[(long long)(edge + i + 3) * ld] - mean;
+      q0 = fma(d0, d0, q0);
+      q1 = fma(d1, d1, q1);
+      q2 = fma(d2, d2, q2);
+      q3 = fma(d3, d3, q3);
     }
-    const double inv = 1.0 / (sqrt(q / (double)L) + eps);
-#pragma unroll 4
-    for (int i = 0; i < L; ++i) outr[i] = (float)((w[(long long)(edge + i) * ld] - mean) * inv);
+    for (; i < L; ++i) {
+      const double d = w[(long long)(edge + i) * ld] - mean;
+      q0 = fma(d, d, q0);
+    }
+    const double inv = 1.0 / (sqrt(((q0 + q1) + (q2 + q3)) / (double)L) + eps);
+#pragma unroll 8
+    for (int i2 = 0; i2 < L; ++i2) outr[i2] = (float)((w[(long long)(edge + i2) * ld] - mean) * inv);
   }
 }
 
