@@ -12,9 +12,9 @@
 // by tools/desc_probe.py, so any 128-byte row is a legal start).  Both operands are MN-major.
 //
 // MMA shape.  M = 128 rows = two (tap, 64-channel Cin slice) atoms, N = BN output channels, K = 16 pixels.
-// BN = 64 everywhere except on layers with >= 64 (cin, cout) slice pairs, where BN = 128 is used (see make_plan
-// for the measurements: the wider N that doubles the rate of the K-major forward MMAs, profiles/
-// r01_mma_n64_vs_n128.txt, does not pay off for these MN-major operands).  A [2 taps x 64] x 128
+// BN = 64 is the default; BN = 128 (ECGMM_WG_BN=128) exists and is tested but measured no faster (see make_plan:
+// the wider N that doubles the rate of the K-major forward MMAs, profiles/r01_mma_n64_vs_n128.txt, does not pay
+// off for these MN-major operands).  A [2 taps x 64] x 128
 // fp32 accumulator is 128 TMEM columns and TMEM has 512: four accumulators = 8 of the 9 taps.  The CTAs of a
 // 3x3 layer therefore come in two TYPES that share one launch:
 //   type A  (cin slice c, cout slice n): taps 0..7 as 4 accumulators                       -> 4 MMA groups per stage
@@ -322,6 +322,48 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const WgReducePa
   }
 }
 
+// One thread per result element (few partials per element: layers with many (cin, cout) slice pairs).
+__global__ void __launch_bounds__(256) wgrad_halo_reduce_flat_kernel(const WgReduceParams p) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool typeB = idx >= p.totalA;
+  if (typeB) idx -= p.totalA;
+  if (typeB && idx >= p.totalB) return;
+  const int m = (int)(idx & 127);
+  const long long rest = idx >> 7;
+  const int c = (int)(rest % p.BN);
+  const long long gs = rest / p.BN;
+  const int n_slots = typeB ? 1 : p.slotsA;
+  const int slot = (int)(gs % n_slots);
+  const int g = (int)(gs / n_slots);
+  const int ksplit = typeB ? p.ksB : p.ksA;
+  int tap, chunk, nt;
+  if (typeB) {
+    tap = p.RS - 1;
+    chunk = 2 * (g % p.cin_pairs) + (m >> 6);
+    nt = g / p.cin_pairs;
+    if (chunk >= p.cin_chunks) return;
+  } else {
+    tap = 2 * slot + (m >> 6);
+    chunk = g % p.cin_chunks;
+    nt = g / p.cin_chunks;
+    if (tap >= p.RS) return;
+  }
+  const size_t slice = (size_t)n_slots * p.BN * 128;
+  const float* src = p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + ((size_t)slot * p.BN + c) * 128 + m;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  for (; k + 3 < ksplit; k += 4) {
+    a0 += src[(size_t)k * slice];
+    a1 += src[(size_t)(k + 1) * slice];
+    a2 += src[(size_t)(k + 2) * slice];
+    a3 += src[(size_t)(k + 3) * slice];
+  }
+  for (; k < ksplit; ++k) a0 += src[(size_t)k * slice];
+  const float acc = (a0 + a1) + (a2 + a3);
+  const int cin = chunk * 64 + (m & 63), cout = nt * p.BN + c;
+  p.dw[((size_t)cout * p.Cin + cin) * p.RS + tap] += acc;
+}
+
 // KP (multiple of 16, <= 128) minimises the pixel slots wasted at the right edge of a row (ties: larger KP); RPS = 2
 // only where three stages still fit (measured: a small, free reduction of L2 traffic, no speed-up by itself).
 static int round1k(int v) { return (v + 1023) & ~1023; }
@@ -377,11 +419,11 @@ static WgPlan make_plan(int N, int H, int W, int Cin, int Cout, int R, int S, in
   const int RS = R * S;
   // Measured (profiles/r01_wgrad_bn128.txt, batch 64): BN = 128 with the two CTA types does NOT beat BN = 64 on
   // layers 2 and 3 (0.260 / 0.243 ms against 0.217 / 0.228 ms) -- unlike the K-major forward kernels, the MN-major
-  // operand feed does not get faster with the wider N -- and wins only where BN = 64 leaves 2 CTAs per
-  // (cin, cout) slice pair (layer4, 64 pairs: 0.257 against 0.281 ms).  ECGMM_WG_BN = 64 | 128 forces a shape.
+  // operand feed does not get faster with the wider N.  On layer4 it wins with a cold L2 (0.257 against 0.281 ms)
+  // but not inside the training step (0.77-0.81 ms per 3 launches against 0.74-0.76 ms), so BN = 64 is the default
+  // everywhere; ECGMM_WG_BN=128 selects the two-type kernel (kept under test: tests/test_conv_gpu.py).
   const char* ebn = getenv("ECGMM_WG_BN");
-  const bool many_groups = (Cin / 64) * (Cout / 64) >= 64;
-  const bool want128 = ebn ? atoi(ebn) == 128 : many_groups;
+  const bool want128 = ebn && atoi(ebn) == 128;
   q.bn = (Cout % 128 == 0 && have_ws && want128) ? 128 : 64;
   const int slots_all = (RS + 1) / 2;
   q.typed = (q.bn == 128 && slots_all * q.bn > 512) ? 1 : 0;  // does not fit the 512 TMEM columns -> two CTA types
@@ -501,7 +543,10 @@ int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
   r.totalB = (long long)q.groupsB * q.bn * 128;
   r.wsB_off = (long long)q.wsB_off;
   const long long total = r.totalA + r.totalB;  // both multiples of 64 (BN * 128 elements per accumulator)
-  wgrad_halo_reduce_kernel<<<(unsigned)((total + 63) / 64), 256, 0, st>>>(r);
+  if (q.ksA >= 16)  // many partials per element: 4 k-groups per element
+    wgrad_halo_reduce_kernel<<<(unsigned)((total + 63) / 64), 256, 0, st>>>(r);
+  else
+    wgrad_halo_reduce_flat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r);
   return check_launch("wgrad_halo_reduce_kernel");
 }
 
