@@ -82,3 +82,16 @@ def test_no_cpu_fallback():
 
     with pytest.raises(lib.EcgmmError):
         ops.nchw_to_nhwc_bf16(torch.zeros(1, 8, 2, 2))
+
+
+def test_smoke_entry_resolves_its_imports_before_asking_for_a_device():
+    """__graft_entry__.smoke() must get as far as the device check on a CPU-only box (a `tests` package in
+    site-packages once shadowed its `from tests.parity_util import ...`)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import __graft_entry__ as g
+
+    with pytest.raises(lib.EcgmmError):
+        g.smoke()
