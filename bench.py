@@ -323,9 +323,30 @@ def run_ours(args):
             print(f"# {k:34s} n={c['launches']:3d} {c['ms']:8.3f} ms {ach:9.1f} {'TFLOP/s' if tensor else 'GB/s'}",
                   file=sys.stderr)
 
+    def shutdown():
+        """Leave the process group without hanging.  Observed on 8 GPUs: after every rank had finished and rank 0 had
+        printed its line, dist.destroy_process_group() did not return while a captured CUDA graph containing NCCL
+        kernels was alive.  So: drain the device, meet the other ranks, drop the graph, then give the teardown 15 s
+        in a helper thread and leave the process hard either way (all results are out by then)."""
+        if world <= 1:
+            return
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        if launch == "cuda_graph":
+            try:
+                gstep.graph.reset()
+            except Exception:
+                pass
+        sys.stdout.flush()
+        sys.stderr.flush()
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(15.0)
+        os._exit(0)  # also skips interpreter finalisation, where the NCCL / graph destructors could block again
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -397,8 +418,7 @@ def run_ours(args):
     if dp is not None:
         line["allreduce"] = {"buckets_per_step": dp.buckets_last_step, "bytes_per_step": dp.bytes_last_step}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():
