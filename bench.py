@@ -228,10 +228,20 @@ def run_ours(args):
     # loop stays available with --launch eager and is what the per-kernel profile below runs
     launch, graph_note = "eager", None
     if args.launch == "graph":
+        gstep = None
         try:
             from ecgmm.graph import GraphedTrainStep
 
             gstep = GraphedTrainStep(net, crit, opt, resident, restore=False)
+        except Exception as ex:  # capture is an optimisation of the HOST side only; say so and carry on eagerly
+            graph_note = f"{type(ex).__name__}: {ex}"[:300]
+            torch.cuda.synchronize()
+        if world > 1:  # every rank replays the graph or none does (the collectives inside have to pair up)
+            okf = torch.tensor([1 if gstep is not None else 0], device=dev)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            if int(okf.item()) == 0 and gstep is not None:
+                gstep, graph_note = None, "capture failed on another rank"
+        if gstep is not None:
             for _ in range(args.warmup):
                 gstep(*gstep.inputs)
             torch.cuda.synchronize()
@@ -242,9 +252,6 @@ def run_ours(args):
 
             resident = gstep.inputs
             launch = "cuda_graph"
-        except Exception as ex:  # capture is an optimisation of the HOST side only; say so and carry on eagerly
-            graph_note = f"{type(ex).__name__}: {ex}"[:300]
-            torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:

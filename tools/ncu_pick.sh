@@ -8,7 +8,7 @@ C="python tools/one_step.py 64 3"
 $C > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.log; exit 1; }
 : > gpurun_out/${TAG}_full_raw.csv
 pick() {  # name regex launches-to-skip launches-to-capture
-  timeout 300 ncu --set full --clock-control none -k regex:"$2" -s "$3" -c "$4" -o gpurun_out/tmp_$1 $C \
+  timeout 300 ncu --set full --clock-control none --kernel-name-base demangled -k regex:"$2" -s "$3" -c "$4" -o gpurun_out/tmp_$1 $C \
     > gpurun_out/${TAG}_ncu_$1.log 2>&1
   if [ -f gpurun_out/tmp_$1.ncu-rep ]; then
     if [ -s gpurun_out/${TAG}_full_raw.csv ]; then
@@ -19,6 +19,8 @@ pick() {  # name regex launches-to-skip launches-to-capture
     rm -f gpurun_out/tmp_$1.ncu-rep
   fi
 }
+# (--kernel-name-base demangled: the template arguments in the patterns below are part of the demangled name only;
+#  without it the "<256", "<3, 0>" patterns of the first run matched nothing)
 # per step: 17 wgrad_halo (first 3: layer4 with BN=128 types; last 4 of the image encoder: layer1), 12 halo, ...
 # the whole weight-gradient class of the third step (bench.py's roofline object: 27 launches): DRAM traffic per launch
 pick wgrad_all  "wgrad_halo_kernel|igemm_tn_kernel" 54 27
