@@ -8,6 +8,8 @@ Pinned: oracle/gen_golden.py imports the real reference from /root/reference, co
 state_dict into both models and asserts bit-identical outputs, losses and gradients (eval and
 train mode, same torch RNG state) before it writes tests/golden/*.  The known-answer logits of
 the reference's only real checkpoint (best_ptbxl.pth) are checked too.
+FocalLoss is pinned against signal_model.FocalLoss by oracle/gen_golden_focal.py (bit-identical value and gradient),
+perturbation_inference against the reference model's own fusion_classifier by oracle/gen_golden_perturb.py.
 
 Each class cites the reference lines it restates:
   AttentionFusion      multimodal_paper_modal_balance.py:31-46   (= multimodal.py:12-27)
@@ -21,6 +23,8 @@ Each class cites the reference lines it restates:
   FocalLoss            signal_model.py:91-106
   fusion_train_step    train.py:60-86 (zero_grad, forward, CE + 0.1*var_loss, backward, Adam step)
   z_score              signal_model.py:203-206
+  perturbation_inference   configs[3]: fusion_classifier.py:5-11 driven as in
+                       shap_fusion_modal_balance.py:126-159 / lime_fusion_modal_balance.py:118-160
 """
 from __future__ import annotations
 

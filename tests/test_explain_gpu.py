@@ -73,3 +73,19 @@ def test_argument_errors():
         explain.masked_variants(e.to(DEV), bg[:100].to(DEV), masks.to(DEV))
     with pytest.raises(lib.EcgmmError):
         explain.masked_variants(e.to(DEV), bg.to(DEV), masks.to(DEV).float())
+
+
+def test_perturbation_inference_matches_reference_golden():
+    """Against tests/golden/perturb_g2.pt (the REFERENCE module's fusion_classifier on the same variants, see
+    oracle/gen_golden_perturb.py), same tolerances as against the live oracle above."""
+    import os
+
+    from golden_util import GOLDEN_DIR
+
+    kat = torch.load(os.path.join(GOLDEN_DIR, "perturb_g2.pt"), map_location="cpu", weights_only=False)
+    _, dut = build_pair(seed=kat["weights_seed"])
+    e, bg, masks = kat["e"].to(DEV), kat["background"].to(DEV), kat["masks"].to(DEV)
+    p = explain.perturbation_inference(dut.fusion_classifier, e, bg, masks, 1)
+    l = explain.perturbation_inference(dut.fusion_classifier, e, bg, masks, -1)
+    assert (p.cpu() - kat["prob1"]).abs().max().item() <= 1e-2
+    assert relmax(l, kat["logits"]) <= OUT_TOL

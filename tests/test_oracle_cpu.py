@@ -86,3 +86,29 @@ def test_signal12_golden(golden):
     lo = net(x)
     assert torch.allclose(lo, s12["logits"], atol=1e-5)
     assert abs(float(om.FocalLoss()(lo, s12["labels"])) - float(s12["focal_loss"])) < 1e-6
+
+
+def test_focal_loss_matches_reference_golden():
+    """tests/golden/focal_kat.pt: written by oracle/gen_golden_focal.py while asserting bit-identity of the oracle's
+    FocalLoss with signal_model.FocalLoss (signal_model.py:91-106), value and gradient."""
+    kat = torch.load(os.path.join(GOLDEN_DIR, "focal_kat.pt"), map_location="cpu", weights_only=False)
+    assert len(kat["cases"]) == 3
+    for c in kat["cases"]:
+        z = c["logits"].clone().requires_grad_(True)
+        loss = om.FocalLoss()(z, c["labels"])
+        loss.backward()
+        assert torch.equal(loss.detach(), c["loss"]) and torch.equal(z.grad, c["grad"])
+
+
+def test_perturbation_inference_matches_reference_golden():
+    """tests/golden/perturb_g2.pt: the reference's own fusion_classifier (through its FusionClassifierWrapper),
+    evaluated row by row on the masked variants by oracle/gen_golden_perturb.py; the oracle's batched evaluation
+    agrees to the last bits of an fp32 GEMM."""
+    kat = torch.load(os.path.join(GOLDEN_DIR, "perturb_g2.pt"), map_location="cpu", weights_only=False)
+    ora = make_oracle(seed=kat["weights_seed"])
+    logits = om.perturbation_inference(ora.fusion_classifier, kat["e"], kat["background"], kat["masks"], -1)
+    prob = om.perturbation_inference(ora.fusion_classifier, kat["e"], kat["background"], kat["masks"], 1)
+    assert logits.shape == kat["logits"].shape == (3, 64, 2)
+    assert float((logits - kat["logits"]).abs().max()) < 1e-6
+    assert float((prob - kat["prob1"]).abs().max()) < 1e-6
+    assert ora.fusion_classifier.training  # the helper restores the module's mode
