@@ -101,3 +101,42 @@ def test_shard_batch():
     assert torch.equal(torch.cat([p[0] for p in parts]), x) and torch.equal(torch.cat([p[1] for p in parts]), y)
     with pytest.raises(ValueError):
         shard_batch((x,), 0, 3)
+
+
+def test_arena_layout_is_reverse_execution_order_and_aligned():
+    """Gradient arenas: parameters in REVERSE execution order (so finished prefixes can be all-reduced early), every
+    slice 16-byte aligned, duplicates laid out once."""
+    from ecgmm.model import ArenaLayout, GradArena
+
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 8, 3, 64)]
+    lay = ArenaLayout(ps)
+    offs = [lay.offsets[id(p)][0] for p in ps]
+    assert offs == sorted(offs, reverse=True) and offs[-1] == 0
+    assert ArenaLayout(ps + [ps[1]]).total == lay.total  # a parameter listed twice is laid out once
+    assert all(o % 4 == 0 for o in offs) and lay.total % 4 == 0
+    G = GradArena(lay, torch.device("cpu"))
+    assert G.flat.numel() == lay.total and float(G.flat.abs().sum()) == 0.0
+    assert G(ps[0]).shape == ps[0].shape and G.end_of(ps[3]) == 64
+    a, b = G(ps[2]), G(ps[2])
+    assert a is not b and a.data_ptr() == b.data_ptr()  # fresh views every time (see test_param_grads_alias_the_arena)
+
+
+def test_stage_caches_are_dropped_on_mode_and_device_changes():
+    """The per-stage parameter list / arena layout caches must not survive train()/eval() or .to()."""
+    m = ecgmm.ECGMultimodalModel(Cfg)
+    enc = m.image_encoder
+    ps = enc.cached_params()
+    assert enc.cached_params() is ps and len(ps) == len(list(enc.parameters()))
+    lay = enc.new_arena(torch.device("cpu")).offsets
+    assert enc.new_arena(torch.device("cpu")).offsets is lay
+    m.eval()
+    assert enc.cached_params() is not ps
+    lay2 = enc.new_arena(torch.device("cpu")).offsets
+    assert lay2 is not lay
+    m.to(torch.float32)
+    assert enc.new_arena(torch.device("cpu")).offsets is not lay2
+    head_ps = m._head.cached_params()
+    m.train()
+    assert m._head.cached_params() is not head_ps
+    # the head borrows the model's modules: fc.weight of a replaced sub-module shows up after the next mode switch
+    assert any(p is m.fusion_classifier.lin1.weight for p in m._head.cached_params())
