@@ -368,6 +368,10 @@ namespace ecgmm {
 bool nt_halo_supported(int Cin, int Cout, int R, int S, int stride, int W);
 int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int R, int S,
                    int dgrad, int accumulate, cudaStream_t st);
+// experimental rolling-accumulator kernel (conv_nt_stack.cu), selected only with ECGMM_NT_STACK=1
+bool nt_stack_supported(int Cin, int Cout, int R, int S, int stride, int W);
+int launch_nt_stack(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int dgrad,
+                    int accumulate, cudaStream_t st);
 }  // namespace ecgmm
 
 // Rows of the statistics partials the forward kernel writes for this shape (4 epilogue warps per CTA of the generic
@@ -396,6 +400,9 @@ static int conv2d_fwd_impl(const ecgmm_bf16* x_, const ecgmm_bf16* w_, ecgmm_bf1
   int rc = check_conv_cfg(Cin, Cout, R, S, stride, padH, padW);
   if (rc) return rc;
   if (N == 0) return ECGMM_OK;
+  if (getenv("ECGMM_NT_STACK") && nt_stack_supported(Cin, Cout, R, S, stride, W))
+    return launch_nt_stack(reinterpret_cast<const __nv_bfloat16*>(x_), reinterpret_cast<const __nv_bfloat16*>(w_),
+                           reinterpret_cast<__nv_bfloat16*>(y_), N, H, W, 0, 0, static_cast<cudaStream_t>(stream));
   if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY"))
     return launch_nt_halo(reinterpret_cast<const __nv_bfloat16*>(x_), reinterpret_cast<const __nv_bfloat16*>(w_),
                           reinterpret_cast<__nv_bfloat16*>(y_), N, H, W, R, S, 0, 0, static_cast<cudaStream_t>(stream));
@@ -445,6 +452,10 @@ extern "C" int ecgmm_conv2d_dgrad(const ecgmm_bf16* dy_, const ecgmm_bf16* wt_, 
   int rc = check_conv_cfg(Cin, Cout, R, S, stride, padH, padW);
   if (rc) return rc;
   if (N == 0) return ECGMM_OK;
+  if (getenv("ECGMM_NT_STACK") && nt_stack_supported(Cin, Cout, R, S, stride, W))
+    return launch_nt_stack(reinterpret_cast<const __nv_bfloat16*>(dy_), reinterpret_cast<const __nv_bfloat16*>(wt_),
+                           reinterpret_cast<__nv_bfloat16*>(dx_), N, H, W, 1, accumulate,
+                           static_cast<cudaStream_t>(stream));
   if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY"))
     return launch_nt_halo(reinterpret_cast<const __nv_bfloat16*>(dy_), reinterpret_cast<const __nv_bfloat16*>(wt_),
                           reinterpret_cast<__nv_bfloat16*>(dx_), N, H, W, R, S, 1, accumulate,

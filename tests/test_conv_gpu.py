@@ -1,5 +1,7 @@
 """tcgen05 implicit-GEMM convolutions (forward / data-gradient / weight-gradient / stem) against
 torch's fp32 convolution on the same bf16-rounded operands (tests/gpu_conv_check.py)."""
+import os
+
 import pytest
 import torch
 
@@ -66,3 +68,18 @@ def test_conv_is_linear_at_full_size():
     assert err < 0.06, err
     z = ops.conv2d_fwd(torch.zeros_like(a), w_fwd)
     assert float(z.float().abs().max()) == 0.0
+
+
+@pytest.mark.skipif(os.environ.get("ECGMM_TEST_EXPERIMENTAL") != "1",
+                    reason="conv_nt_stack.cu is a round-2 work item: compiled, not yet validated on hardware")
+@pytest.mark.parametrize("case", [("stack_63x625", 2, 63, 625, 64, 64, 3, 3, 1), ("stack_ragged", 3, 21, 150, 64, 64, 3, 3, 1),
+                                  ("stack_one_row", 2, 1, 200, 64, 64, 3, 3, 1), ("stack_two_rows", 1, 2, 130, 64, 64, 3, 3, 1)],
+                         ids=lambda c: c[0])
+def test_experimental_rolling_accumulator_kernel(case, monkeypatch):
+    """Forward, data-gradient and accumulating data-gradient of the 64 -> 64 3x3 layers through igemm_nt_stack_kernel
+    (ECGMM_NT_STACK=1): N = 192 MMAs into a ring of output-row accumulators in TMEM."""
+    monkeypatch.setenv("ECGMM_NT_STACK", "1")
+    results = []
+    assert chk.run_case(*case, results=results, do=("fwd", "dgrad"))
+    bad = [r for r in results if not r[2]]
+    assert not bad, bad
