@@ -46,6 +46,15 @@ inline int check_launch(const char* what, int n_kernels = 1) {
 
 int num_sms();
 
+// Index of the current device for per-device one-time setup (cudaFuncSetAttribute): a process normally drives one
+// GPU, but nothing here may silently depend on that.
+constexpr int kMaxDevices = 64;
+inline int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 // 4-D activation view for TMA: dims (C, W, H, N) innermost first, byte strides for W/H/N,
 // box (box_c, box_w, box_h, 1), SWIZZLE_128B, zero fill out of bounds.
 int make_tmap_4d(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,

@@ -265,11 +265,12 @@ static int nt_grid(int total_tiles, int n_tiles_n) {
 template <int BN, int STAGES>
 static int launch_nt_t(const NtParams& p, cudaStream_t s) {
   using L = NtSmem<BN, STAGES>;
-  static bool configured = false;  // one host thread per process drives a GPU (header contract)
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
+  const int ds = device_slot();
+  if (!configured[ds]) {
     ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     L::kBytes));
-    configured = true;
+    configured[ds] = true;
   }
   int grid = nt_grid(p.total_tiles, p.n_tiles_n);
   igemm_nt_kernel<BN, STAGES><<<grid, 192, L::kBytes, s>>>(p);
@@ -715,11 +716,12 @@ __global__ void __launch_bounds__(192, 1) igemm_tn_kernel(const __grid_constant_
 template <int BN, int SMAX, int STAGES>
 static int launch_tn_t(TnParams& p, cudaStream_t s) {
   using L = TnSmem<BN, SMAX, STAGES>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
+  const int ds = device_slot();
+  if (!configured[ds]) {
     ECGMM_CUDA(cudaFuncSetAttribute(igemm_tn_kernel<BN, SMAX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     L::kBytes));
-    configured = true;
+    configured[ds] = true;
   }
   p.n_atoms = p.ntaps * p.cin_chunks;
   p.n_slots = (p.n_atoms + 1) / 2;

@@ -329,11 +329,12 @@ int launch_nt_stack(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat1
   if (rc) return rc;
   rc = make_tmap_4d(&p.y_map, y, 64, W, H, N, 64 * e, (uint64_t)W * 64 * e, (uint64_t)H * W * 64 * e, 64, kStTile, 1);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
+  const int ds = device_slot();
+  if (!configured[ds]) {
     ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     NtStackSmem::kBytes));
-    configured = true;
+    configured[ds] = true;
   }
   const int grid = p.total_units < num_sms() ? p.total_units : num_sms();
   igemm_nt_stack_kernel<<<grid, 192, NtStackSmem::kBytes, st>>>(p);

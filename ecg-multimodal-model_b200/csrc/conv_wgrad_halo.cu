@@ -463,10 +463,11 @@ size_t wgrad_halo_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R,
 
 template <int BN>
 static int launch_typed(const WgHaloParams& p, int grid, int smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
+  const int ds = device_slot();
+  if (!configured[ds]) {
     ECGMM_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+    configured[ds] = true;
   }
   wgrad_halo_kernel<BN><<<grid, 192, smem, st>>>(p);
   return check_launch("wgrad_halo_kernel");

@@ -131,10 +131,11 @@ extern "C" int ecgmm_signal_stem_fwd(const float* x, const float* w, ecgmm_bf16*
   if (B == 0) return ECGMM_OK;
   const int Lo = (L - 1) / 2 + 1;
   const size_t smem = ((size_t)((Cin * kStemSpan + 3) & ~3) + (size_t)Cin * 7 * kStemCo) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
+  const int ds = device_slot();
+  if (!configured[ds]) {
     ECGMM_CUDA(cudaFuncSetAttribute(signal_stem_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    configured = true;
+    configured[ds] = true;
   }
   signal_stem_fwd_kernel<<<dim3(ceil_div(Lo, kStemTile), B), 256, smem, (cudaStream_t)stream>>>(
       x, w, reinterpret_cast<__nv_bfloat16*>(y), Cin, L, Lo);
@@ -149,13 +150,14 @@ extern "C" int ecgmm_signal_stem_wgrad(const float* x, const ecgmm_bf16* dy, flo
   const int Lo = (L - 1) / 2 + 1;
   const int tiles = ceil_div(Lo, kStemTile);
   const size_t smem = ((size_t)((Cin * kStemSpan + 3) & ~3) + (size_t)kStemTile * kStemCo) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
+  const int ds = device_slot();
+  if (!configured[ds]) {
     ECGMM_CUDA(cudaFuncSetAttribute(signal_stem_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     64 * 1024));
     ECGMM_CUDA(cudaFuncSetAttribute(signal_stem_wgrad_kernel<28>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     64 * 1024));
-    configured = true;
+    configured[ds] = true;
   }
   int grid = B * tiles;
   if (grid > num_sms() * 2) grid = num_sms() * 2;

@@ -338,11 +338,12 @@ int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, in
   if (rc) return rc;
   rc = make_tmap_4d(&p.dy_map, y, 64, Wo, Ho, N, 128, (uint64_t)Wo * 128, (uint64_t)Ho * Wo * 128, 64, kSrTile, 1);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
+  const int ds = device_slot();
+  if (!configured[ds]) {
     ECGMM_CUDA(cudaFuncSetAttribute(stem_fwd_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     StemFwdSmem::kBytes));
-    configured = true;
+    configured[ds] = true;
   }
   const int grid = p.n_strips < num_sms() ? p.n_strips : num_sms();
   stem_fwd_ring_kernel<<<grid, 192, StemFwdSmem::kBytes, st>>>(p);
@@ -363,11 +364,12 @@ int launch_stem_wgrad_ring(const void* xs, const void* dy, float* dw, int N, int
   rc = make_tmap_4d(&p.dy_map, dy, 64, Wo, Ho, N, 128, (uint64_t)Wo * 128, (uint64_t)Ho * Wo * 128, 64, kSrTile, 1);
   if (rc) return rc;
   p.w_map = p.x_map;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
+  const int ds = device_slot();
+  if (!configured[ds]) {
     ECGMM_CUDA(cudaFuncSetAttribute(stem_wgrad_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     StemWgSmem::kBytes));
-    configured = true;
+    configured[ds] = true;
   }
   const int grid = p.n_strips < num_sms() ? p.n_strips : num_sms();
   stem_wgrad_ring_kernel<<<grid, 192, StemWgSmem::kBytes, st>>>(p);
