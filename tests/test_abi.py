@@ -95,3 +95,20 @@ def test_smoke_entry_resolves_its_imports_before_asking_for_a_device():
 
     with pytest.raises(lib.EcgmmError):
         g.smoke()
+
+
+def test_product_package_never_touches_the_oracle_or_the_reference():
+    """The oracle is test infrastructure: nothing under ecg-multimodal-model_b200/ may import or read oracle/ or
+    /root/reference, and nothing the GPU box runs may read /root/reference."""
+    import glob
+
+    pkg = glob.glob(os.path.join(ROOT, "ecg-multimodal-model_b200", "*.py"))
+    assert pkg
+    for f in pkg:
+        src = open(f).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+        assert "/root/reference" not in src.replace("/root/reference/multimodal", "REFDOC") or f.endswith("model.py"), f
+    for f in [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")] + \
+            glob.glob(os.path.join(ROOT, "tests", "test_*gpu.py")):
+        code = "\n".join(l for l in open(f).read().splitlines() if not l.strip().startswith("#"))
+        assert 'open("/root/reference' not in code and "sys.path.insert(0, \"/root/reference\")" not in code, f
