@@ -90,3 +90,56 @@ def perturbation_inference(fusion_classifier, e, background, masks, class_index:
         out = head_inference(fusion_classifier, x.view(-1, D), class_index)
         outs.append(out.view(es.shape[0], V) if class_index >= 0 else out.view(es.shape[0], V, -1))
     return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+
+# ---------------------------------------------------------------------------------------------- modality attribution
+# SURVEY.md section 8f rank 3.  The reference's explainers end in a per-MODALITY importance (the |SHAP| mass of the
+# image / signal / clinical slices of the fused embedding, shap_fusion_modal_balance.py:177-200) obtained from
+# third-party samplers (`shap`, `lime`: unpinned, not installed).  With three modalities the Shapley values of
+#     f(S) = softmax(fusion_classifier(z_S * e + (1 - z_S) * background))[class],   S subset of {image, signal, clinical}
+# need no sampling: all 2^3 coalitions are evaluated exactly (8 of the masked variants above) and
+#     phi_i = sum_{S not containing i}  |S|! (2 - |S|)! / 3!  * ( f(S + i) - f(S) ).
+# This is the self-contained spec implemented here and in oracle.model.modality_shapley.
+def coalition_masks(dims, device=None) -> torch.Tensor:
+    """uint8 [8, sum(dims)]: row c keeps modality m (its slice of the fused embedding) iff bit m of c is set."""
+    D = int(sum(dims))
+    m = torch.zeros((8, D), dtype=torch.uint8)
+    off = 0
+    for k, d in enumerate(dims):
+        for c in range(8):
+            if (c >> k) & 1:
+                m[c, off:off + d] = 1
+        off += d
+    return m if device is None else m.to(device)
+
+
+def shapley_matrix() -> torch.Tensor:
+    """[8, 3] fp32: phi = f_coalitions @ this (exact Shapley weights for 3 players, coalition c = bit set)."""
+    w = torch.zeros(8, 3)
+    fact = [1.0, 1.0, 2.0, 6.0]
+    for i in range(3):
+        for c in range(8):
+            if (c >> i) & 1:
+                continue
+            size = bin(c).count("1")
+            wt = fact[size] * fact[2 - size] / fact[3]
+            w[c | (1 << i), i] += wt
+            w[c, i] -= wt
+    return w
+
+
+def modality_shapley(fusion_classifier, e, background, dims=(256, 256, 256), class_index: int = 1):
+    """Exact Shapley values of the three modalities for every sample.
+
+    e [S, sum(dims)] fused embeddings, background [sum(dims)].  Returns (phi [S, 3], f_none [S], f_all [S]) fp32 on
+    e's device; phi.sum(1) == f_all - f_none (efficiency).  One perturbation_inference call with the 8 coalition masks
+    plus one [S,8] x [8,3] product on the library's SGEMM."""
+    if class_index < 0:
+        raise lib.EcgmmError("modality_shapley needs a class index (the value function is a probability)")
+    if e.shape[1] != sum(dims):
+        raise lib.EcgmmError(f"embedding width {e.shape[1]} != sum of modality widths {sum(dims)}")
+    masks = coalition_masks(dims, e.device)
+    f = perturbation_inference(fusion_classifier, e, background, masks, class_index).contiguous()  # [S, 8]
+    wmat = shapley_matrix().to(e.device).contiguous()
+    phi = ops.sgemm(f, wmat, f.shape[0], 3, 8)
+    return phi, f[:, 0].contiguous(), f[:, 7].contiguous()

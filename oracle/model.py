@@ -270,3 +270,29 @@ def perturbation_inference(fusion_classifier, e, background, masks, class_index=
         logits = fusion_classifier(variants.reshape(-1, e.shape[1])).view(e.shape[0], masks.shape[0], -1)
     fusion_classifier.train(was_training)
     return logits if class_index < 0 else F.softmax(logits, dim=-1)[..., class_index]
+
+
+def modality_shapley(fusion_classifier, e, background, dims=(256, 256, 256), class_index=1):
+    """Exact 3-player Shapley values of the modalities under background replacement (the self-contained spec of
+    SURVEY.md section 8f rank 3; the reference reaches a per-modality importance through the unpinned `shap` / `lime`
+    packages, shap_fusion_modal_balance.py:177-200).  Plain enumeration: phi_i = sum_S w(|S|) (f(S+i) - f(S))."""
+    from itertools import combinations
+    from math import factorial
+
+    D = sum(dims)
+    offs = [0, dims[0], dims[0] + dims[1], D]
+
+    def f(players):
+        z = torch.zeros(1, D, dtype=torch.uint8)
+        for k in players:
+            z[0, offs[k]:offs[k + 1]] = 1
+        return perturbation_inference(fusion_classifier, e, background, z, class_index)[:, 0]
+
+    phi = torch.zeros(e.shape[0], 3)
+    for i in range(3):
+        others = [k for k in range(3) if k != i]
+        for r in range(3):
+            for S in combinations(others, r):
+                w = factorial(len(S)) * factorial(2 - len(S)) / factorial(3)
+                phi[:, i] += w * (f(S + (i,)) - f(S))
+    return phi, f(()), f((0, 1, 2))

@@ -112,3 +112,26 @@ def test_perturbation_inference_matches_reference_golden():
     assert float((logits - kat["logits"]).abs().max()) < 1e-6
     assert float((prob - kat["prob1"]).abs().max()) < 1e-6
     assert ora.fusion_classifier.training  # the helper restores the module's mode
+
+
+def test_modality_shapley_spec_properties():
+    """The oracle's enumeration: efficiency (sum phi = f(all) - f(none)), a modality whose slice equals the
+    background gets exactly 0, and the closed-form weight matrix of the product path gives the same numbers."""
+    import ecgmm  # noqa: F401
+    from ecgmm import explain
+
+    ora = make_oracle(seed=7)
+    g = torch.Generator().manual_seed(3)
+    e = torch.randn(5, 768, generator=g)
+    bg = torch.randn(768, generator=g)
+    e[:, 256:512] = bg[256:512]  # the signal slice carries no information beyond the background
+    phi, f0, f1 = om.modality_shapley(ora.fusion_classifier, e, bg)
+    assert phi.shape == (5, 3)
+    assert torch.allclose(phi.sum(1), f1 - f0, atol=1e-6)
+    assert float(phi[:, 1].abs().max()) < 1e-7
+    masks = explain.coalition_masks((256, 256, 256))
+    assert masks.shape == (8, 768) and masks[0].sum() == 0 and masks[7].sum() == 768 and masks[2, 256:512].all()
+    f = om.perturbation_inference(ora.fusion_classifier, e, bg, masks, 1)
+    assert torch.allclose(f @ explain.shapley_matrix(), phi, atol=1e-6)
+    w = explain.shapley_matrix()
+    assert torch.allclose(w.sum(0), torch.zeros(3), atol=1e-7) and torch.allclose(w[7], torch.full((3,), 1 / 3))
