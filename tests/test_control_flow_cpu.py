@@ -1,0 +1,161 @@
+"""CPU: the Python glue of the product path, executed end to end with the kernel launches stubbed out.
+
+Every libecgmm entry point that launches a kernel goes through ecgmm.lib.call; here it is replaced by a recorder, and
+tensors are made to claim `is_cuda`, so forward / backward / optimizer / explainers run their real control flow on
+CPU memory (values are garbage, shapes and call sequences are real).  This catches what a GPU-less build cannot see
+otherwise: wrong argument counts against the ctypes prototypes, missing gradients, stale caches, a code path that only
+the GPU tests would reach."""
+import ctypes
+
+import pytest
+import torch
+
+import ecgmm
+from ecgmm import explain, lib, ops, preprocess
+from ecgmm import nn as enn
+from ecgmm import optim as eoptim
+
+
+class Cfg:
+    num_classes = 2
+    device = "cpu"
+
+
+@pytest.fixture
+def stub(monkeypatch):
+    calls = []
+
+    def fake_call(name, *args):
+        argtypes = lib.SIGNATURES[name]
+        assert len(args) == len(argtypes), f"{name}: {len(args)} arguments for {len(argtypes)} parameters"
+        for a, t in zip(args, argtypes):  # what ctypes would accept
+            if t is ctypes.c_void_p or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+                assert a is None or isinstance(a, (int, ctypes.c_void_p, ctypes.Array)), (name, type(a))
+            elif t in (ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong):
+                assert isinstance(a, int) and not isinstance(a, bool) or isinstance(a, bool), (name, a)
+            else:
+                assert isinstance(a, (int, float)), (name, a)
+        calls.append(name)
+
+    monkeypatch.setattr(lib, "call", fake_call)
+    monkeypatch.setattr(ops, "_s", lambda: 0)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self, raising=False)
+    return calls
+
+
+def _batch(B=2, H=64, W=160, L=600):
+    g = torch.Generator().manual_seed(0)
+    return (torch.randn(B, 3, H, W, generator=g), torch.randn(B, L, generator=g), torch.randn(B, 24, generator=g),
+            torch.tensor([0, 1] * (B // 2)))
+
+
+def test_train_step_flow(stub):
+    m = ecgmm.ECGMultimodalModel(Cfg)
+    m.overlap_branches = False  # the side-stream variant needs real CUDA streams
+    m.train()
+    crit, opt = enn.CrossEntropyLoss(), eoptim.Adam(m.parameters(), lr=1e-3)
+    image, ecg, clin, labels = _batch()
+    per_step = []
+    for _ in range(2):
+        n0 = len(stub)
+        opt.zero_grad()
+        out = m(image, ecg, clin)
+        assert [tuple(o.shape) for o in out] == [(2, 2)] * 4 + [(), (3,)]
+        (crit(out[3], labels) + 0.1 * out[4]).backward()
+        opt.step()
+        per_step.append(len(stub) - n0)
+    assert per_step[0] > 300 and per_step[1] <= per_step[0]  # step 2 re-uses weight-shadow bookkeeping
+    assert all(p.grad is not None for n, p in m.named_parameters()
+               if not n.startswith(("image_classifier", "signal_classifier", "clinical_classifier")))
+    assert all(int(opt.state[p]["step"]) == 2 for p in m.parameters() if p.grad is not None)
+    names = set(stub)
+    for needed in ("ecgmm_stem_s2d", "ecgmm_stem_conv_fwd", "ecgmm_conv2d_fwd", "ecgmm_conv2d_fwd_stats",
+                   "ecgmm_conv2d_dgrad", "ecgmm_conv2d_wgrad", "ecgmm_stem_conv_wgrad", "ecgmm_chan_stats",
+                   "ecgmm_bn_finalize", "ecgmm_bn_apply", "ecgmm_bn_relu_maxpool", "ecgmm_bn_bwd_reduce",
+                   "ecgmm_bn_bwd_finalize", "ecgmm_bn_bwd_apply", "ecgmm_se_fwd", "ecgmm_se_bwd", "ecgmm_ce_loss",
+                   "ecgmm_adam_step", "ecgmm_fusion_gate_fwd", "ecgmm_var_loss_fwd", "ecgmm_dropout_fwd"):
+        assert needed in names, needed
+
+
+def test_eval_uint8_freeze_and_fusion_only_flows(stub):
+    image, ecg, clin, labels = _batch()
+    m = ecgmm.ECGMultimodalModel(Cfg)
+    m.overlap_branches = False
+    m.eval()
+    with torch.no_grad():
+        out = m((image * 100).to(torch.uint8), ecg, clin)  # raw pixels
+    assert out[3].shape == (2, 2)
+    # frozen statistics everywhere; only the three SE blocks of the signal encoder still need their per-sample sums
+    assert "ecgmm_bn_eval_coeffs" in stub and "ecgmm_conv2d_fwd_stats" not in stub and stub.count("ecgmm_chan_stats") == 3
+    # train.py:35-40 freeze mode: only the head trains
+    m.train()
+    for enc in (m.image_encoder, m.signal_encoder, m.clinical_encoder):
+        for p in enc.parameters():
+            p.requires_grad = False
+    del stub[:]
+    out = m(image, ecg, clin)
+    (enn.CrossEntropyLoss()(out[3], labels) + 0.1 * out[4]).backward()
+    assert "ecgmm_conv2d_wgrad" not in stub and "ecgmm_conv2d_dgrad" not in stub
+    assert m.fusion_classifier.lin1.weight.grad is not None and m.image_encoder.conv1.weight.grad is None
+    # single-tensor API of train_kfold.py:59-64 and the 512/128/32 layout of multimodal.py
+    f = ecgmm.ECGMultimodalModel(Cfg, fusion_only=True, dims=(512, 128, 32))
+    f.overlap_branches = False
+    y = f(image, ecg, clin)
+    assert isinstance(y, torch.Tensor) and y.shape == (2, 2)
+
+
+def test_signal_model_and_helpers_flow(stub):
+    net = ecgmm.ResNet1D_SE(12, 2).train()
+    x = torch.randn(4, 12, 1000)
+    opt = eoptim.Adam(net.parameters(), lr=1e-3)
+    loss = enn.FocalLoss()(net(x), torch.tensor([0, 1, 1, 0]))
+    loss.backward()
+    opt.step()
+    assert "ecgmm_signal_stem_fwd" in stub and "ecgmm_signal_stem_wgrad" in stub
+    assert all(p.grad is not None for p in net.parameters())
+    # preprocessing / explainers: argument marshalling of the newer entry points
+    y = preprocess.preprocess_signal(torch.randn(3, 12, 500), zscore=True)
+    assert y.shape == (3, 12, 500) and y.dtype == torch.float32 and stub[-1] == "ecgmm_signal_preprocess"
+    m = ecgmm.ECGMultimodalModel(Cfg)
+    e, bg = torch.randn(5, 768), torch.randn(768)
+    p = explain.perturbation_inference(m.fusion_classifier, e, bg, (torch.rand(16, 768) < 0.5).to(torch.uint8))
+    assert p.shape == (5, 16)
+    assert stub[-3:] == ["ecgmm_perturb_build", "ecgmm_conv2d_fwd", "ecgmm_head_tail"]
+    phi, f0, f1 = explain.modality_shapley(m.fusion_classifier, e, bg)
+    assert phi.shape == (5, 3) and f0.shape == (5,) and f1.shape == (5,) and stub[-1] == "ecgmm_sgemm"
+
+
+def test_graph_mode_marshalling(stub, monkeypatch):
+    """What ecgmm.graph switches on while it captures a step: Adam reads lr / step count from device words through
+    pre-pinned chunk tables, dropout adds the device seed offset."""
+    m = ecgmm.ECGMultimodalModel(Cfg)
+    m.overlap_branches = False
+    m.train()
+    crit, opt = enn.CrossEntropyLoss(), eoptim.Adam(m.parameters(), lr=1e-3)
+    image, ecg, clin, labels = _batch()
+    state = torch.zeros(2, dtype=torch.int64)
+    lr_dev = torch.tensor([1e-3])
+    opt.reserve_tables()
+    monkeypatch.setattr(ops, "GRAPH_STATE", state)
+    opt._graph_mode = (state, lr_dev)
+    seen = []
+    real = lib.call
+
+    def spy(name, *args):
+        if name in ("ecgmm_dropout_fwd", "ecgmm_adam_step_dev"):
+            seen.append((name, args))
+        real(name, *args)
+
+    monkeypatch.setattr(lib, "call", spy)
+    out = m(image, ecg, clin)
+    (crit(out[3], labels) + 0.1 * out[4]).backward()
+    opt.step()
+    opt._graph_mode = None
+    drops = [a for n, a in seen if n == "ecgmm_dropout_fwd"]
+    assert drops and all(a[7] == state.data_ptr() + 8 for a in drops)  # seed_dev -> second word of the state
+    adams = [a for n, a in seen if n == "ecgmm_adam_step_dev"]
+    assert len(adams) == 1 and adams[0][2] == lr_dev.data_ptr() and adams[0][7] == state.data_ptr()
+    assert "ecgmm_adam_step" not in stub
+    host, dev = opt._reserved[0]
+    assert adams[0][1] <= host.shape[0] and int(adams[0][0].value) == dev.data_ptr()
