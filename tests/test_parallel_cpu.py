@@ -152,3 +152,67 @@ def test_folds_are_partitioned_over_ranks():
 
     with pytest.raises(ValueError):
         folds_for_rank(5, 3, 2)
+
+
+def _full_model_worker(rank, world, port, q):
+    """The REAL model under DataParallel over gloo, kernel launches stubbed (see test_control_flow_cpu.py)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ecgmm
+        from ecgmm import lib, ops
+        from ecgmm import nn as enn
+        from ecgmm import optim as eoptim
+        from ecgmm.parallel import DataParallel
+
+        from ecgmm import model as M
+
+        lib.call = lambda name, *a: None
+        ops._s = lambda: 0
+        ops._chk = lambda *a: None            # backward runs with honest CPU tensors (gloo must see them as such)
+        M._require_cuda_f32 = lambda *a: None
+        torch.Tensor.pin_memory = lambda self, *a, **k: self
+
+        class Cfg:
+            num_classes = 2
+            device = "cpu"
+
+        torch.manual_seed(100 + rank)  # different weights per rank: the wrapper must broadcast rank 0's
+        m = ecgmm.ECGMultimodalModel(Cfg)
+        m.overlap_branches = False
+        m.train()
+        dp = DataParallel(m)
+        w0 = m.fusion_classifier.lin1.weight.detach().clone()
+        gathered = [torch.empty_like(w0) for _ in range(world)]
+        dist.all_gather(gathered, w0)
+        same_init = all(torch.equal(gathered[0], t) for t in gathered)
+        torch.Tensor.is_cuda = property(lambda self: True)  # only now: gloo itself must see CPU tensors above
+        g = torch.Generator().manual_seed(rank)
+        image, ecg, clin = torch.randn(2, 3, 64, 160, generator=g), torch.randn(2, 600, generator=g), torch.randn(2, 24, generator=g)
+        opt = eoptim.Adam(m.parameters(), lr=1e-3)
+        opt.zero_grad()
+        out = dp(image, ecg, clin)
+        loss = enn.CrossEntropyLoss()(out[3], torch.tensor([0, 1])) + 0.1 * out[4]
+        del torch.Tensor.is_cuda  # the collectives launched from backward run on gloo
+        loss.backward()
+        ok = same_init and not dp._pending
+        q.put((rank, ok, dp.buckets_last_step, dp.bytes_last_step))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_full_model_buckets_gloo_world2():
+    """Bucket schedule of the real model: 7 all-reduces per step (image encoder 4, signal, clinical, head) covering
+    every trainable parameter once -- the numbers the 8-GPU bench line reports (7 buckets, 47 649 984 bytes)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_full_model_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
+    assert all(r[2] == 7 and r[3] == 47649984 for r in res), res
