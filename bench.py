@@ -337,6 +337,13 @@ def run_ours(args):
         in a helper thread and leave the process hard either way (all results are out by then)."""
         if world <= 1:
             return
+        sys.stdout.flush()
+        sys.stderr.flush()
+        # whatever blocks below (a peer that already died, a communicator that will not drain): every result is out,
+        # so the process leaves after 60 s at the latest instead of holding the launcher until its own limit
+        wd = threading.Timer(60.0, lambda: os._exit(0))
+        wd.daemon = True
+        wd.start()
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()

@@ -1,0 +1,49 @@
+#!/bin/bash
+# First GPU call of the next round: everything that was written after round 1's GPU budget was spent, in ONE gpurun
+# call, each step under its own timeout so that a hanging experimental kernel cannot take the box with it.
+#
+#   gpurun --timeout 1500 -- 'bash tools/r02_first_call.sh r02a'
+#
+# Writes gpurun_out/<tag>_*.log.  Order: (1) the regular GPU suite (incl. the tests collected last that have never
+# run on hardware), (2) smoke, (3) baseline bench lines at per-GPU batch 64 and 512, (4) the gated experiments, each
+# first through its parity test and only then through the bench, (5) the per-config helpers.
+set -u
+TAG=${1:-r02a}
+O=gpurun_out
+mkdir -p $O
+run() {  # name timeout command...
+  local name=$1 lim=$2
+  shift 2
+  echo "== $name: $*" | tee -a $O/${TAG}_index.log
+  timeout "$lim" "$@" > $O/${TAG}_$name.log 2>&1
+  echo "   rc=$? ($(tail -c 300 $O/${TAG}_$name.log | tr '\n' ' ' | cut -c1-200))" | tee -a $O/${TAG}_index.log
+}
+B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
+
+run pytest        600 python -m pytest tests -x -q -m gpu
+run smoke         300 python -c "import __graft_entry__ as g; g.smoke()"
+run base_b64      300 $B --global-batch 64 --detail
+run base_b512     300 $B --detail
+
+# --- experiment 1: rolling-accumulator N=192 kernel for the 64-channel layers (csrc/conv_nt_stack.cu)
+export ECGMM_TEST_EXPERIMENTAL=1
+run stack_test    300 python -m pytest tests/test_conv_gpu.py -x -q -m gpu -k "rolling_accumulator"
+if grep -q " passed" $O/${TAG}_stack_test.log && ! grep -q " failed" $O/${TAG}_stack_test.log; then
+  ECGMM_NT_STACK=1 run stack_b64   300 $B --global-batch 64 --detail
+  ECGMM_NT_STACK=1 run stack_b512  300 $B --detail
+fi
+
+# --- experiment 2: weight gradients on their own stream underneath the BatchNorm backward (model._WgradLane)
+run wgstream_test 300 python -m pytest tests/test_fusion_gpu.py -x -q -m gpu -k "wgrad_lane"
+if grep -q " passed" $O/${TAG}_wgstream_test.log && ! grep -q " failed" $O/${TAG}_wgstream_test.log; then
+  ECGMM_WGRAD_STREAM=1 run wgstream_b64  300 $B --global-batch 64 --detail
+  ECGMM_WGRAD_STREAM=1 run wgstream_b512 300 $B --detail
+fi
+unset ECGMM_TEST_EXPERIMENTAL
+
+# --- the other configs (BASELINE.json configs[1], [3], [4]) and the reference arm
+run signal   300 python tools/signal_bench.py
+run perturb  300 python tools/perturb_bench.py
+run kfold    600 python tools/kfold_bench.py
+run ref_arm  300 python bench.py --impl reference --steps 2 --warmup 1
+cat $O/${TAG}_index.log
