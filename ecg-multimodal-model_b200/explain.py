@@ -143,3 +143,85 @@ def modality_shapley(fusion_classifier, e, background, dims=(256, 256, 256), cla
     wmat = shapley_matrix().to(e.device).contiguous()
     phi = ops.sgemm(f, wmat, f.shape[0], 3, 8)
     return phi, f[:, 0].contiguous(), f[:, 7].contiguous()
+
+
+# ---------------------------------------------------------------------------------------------- expected gradients
+# SURVEY.md section 8f rank 3, the 768-dimensional attribution.  The reference gets `shap_values [S, D, C]` from
+# shap.GradientExplainer(FusionClassifierWrapper(model.fusion_classifier), bg_embeddings).shap_values(fused)
+# (shap_fusion_modal_balance.py:135,159): expected gradients of the LOGITS.  `shap` is unpinned and absent, so the
+# estimator is restated with an explicit sampling plan (the caller's RNG, not the package's):
+#     phi[s, d, c] = mean_k (e[s, d] - bg[j_sk, d]) * d logit_c / d x_d (bg[j_sk] + a_sk (e[s] - bg[j_sk]))
+# For Linear(D,HID) -> ReLU -> Linear(HID,C) the gradient at x is W1^T ([W1 x + b1 > 0] * w2[c]): two fp32 SGEMMs
+# around three bandwidth-bound kernels (csrc/attrib.cu).  fp32 throughout, unlike perturbation_inference: the SIGN of
+# a hidden pre-activation switches a whole column of the gradient on or off.
+def sampling_plan(S: int, K: int, n_background: int, seed: int = 0):
+    """(idx [S,K] int32, alpha [S,K] fp32) on the host: uniform background rows and interpolation weights, the draws
+    shap.GradientExplainer makes internally (nsamples = K, default 200)."""
+    g = torch.Generator().manual_seed(int(seed))
+    idx = torch.randint(0, n_background, (S, K), generator=g, dtype=torch.int32)
+    alpha = torch.rand(S, K, generator=g)
+    return idx, alpha
+
+
+def expected_gradients(fusion_classifier, e, background, idx, alpha, chunk_samples: int = 0):
+    """phi [S, D, C] fp32: expected gradients of fusion_classifier's logits (eval semantics).
+
+    e [S, D] and background [NB, D] fp32 CUDA tensors; idx [S, K] (integer, values in [0, NB)) and alpha [S, K] may
+    live on the host (they are validated there) or on the device.  chunk_samples bounds the [C, S*K, D] gradient
+    buffer (0: ~2 GB)."""
+    for t, name in ((e, "e"), (background, "background")):
+        if not t.is_cuda:
+            raise lib.EcgmmError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if e.dim() != 2 or background.dim() != 2 or e.shape[1] != background.shape[1]:
+        raise lib.EcgmmError(f"shapes must be e [S,D], background [NB,D]; got {tuple(e.shape)}, {tuple(background.shape)}")
+    S, D = e.shape
+    NB = background.shape[0]
+    if idx.dim() != 2 or idx.shape[0] != S or tuple(alpha.shape) != tuple(idx.shape) or idx.shape[1] < 1:
+        raise lib.EcgmmError(f"idx and alpha must both be [S,K] with K >= 1; got {tuple(idx.shape)}, {tuple(alpha.shape)}")
+    if idx.dtype.is_floating_point or idx.dtype == torch.bool:
+        raise lib.EcgmmError(f"idx must be an integer tensor, got {idx.dtype}")
+    if idx.device.type == "cpu" and idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= NB):
+        raise lib.EcgmmError(f"idx values must lie in [0, {NB})")
+    K = idx.shape[1]
+    head = getattr(fusion_classifier, "fusion_classifier", fusion_classifier)  # FusionClassifierWrapper or the head
+    w1, b1 = head.lin1.weight.detach().contiguous(), head.lin1.bias.detach().contiguous()
+    w2 = head.lin2.weight.detach().contiguous()
+    HID, C = w1.shape[0], w2.shape[0]
+    if w1.shape[1] != D:
+        raise lib.EcgmmError(f"embedding width {D} does not match fusion_classifier[0] ({w1.shape[1]})")
+    dev = e.device
+    e = e.detach().to(F32).contiguous()
+    background = background.detach().to(F32).contiguous()
+    idx = idx.to(device=dev, dtype=torch.int32).contiguous()
+    alpha = alpha.to(device=dev, dtype=F32).contiguous()
+    if chunk_samples <= 0:
+        chunk_samples = max(1, (2 << 30) // max(1, C * K * D * 4))
+    chunk_samples = min(chunk_samples, 65535)
+    phi = torch.empty((S, D, C), dtype=F32, device=dev)
+    for s0 in range(0, S, chunk_samples):
+        n = min(chunk_samples, S - s0)
+        rows = n * K
+        es, ix, al = e[s0:s0 + n], idx[s0:s0 + n], alpha[s0:s0 + n]
+        pts = torch.empty((rows, D), dtype=F32, device=dev)
+        lib.call("ecgmm_eg_points", ops._ptr(es), ops._ptr(background), ops._ptr(ix), ops._ptr(al), ops._ptr(pts), n, K,
+                 D, NB, ops._s())
+        hidden = ops.linear_fwd(pts, w1, b1, relu=True)                        # relu(h) > 0  <=>  h > 0
+        gate = torch.empty((C, rows, HID), dtype=F32, device=dev)
+        lib.call("ecgmm_eg_gate", ops._ptr(hidden), ops._ptr(w2), ops._ptr(gate), rows, HID, C, ops._s())
+        grad = ops.sgemm(gate, w1, C * rows, D, HID)                           # [C*rows, HID] x [HID, D]
+        lib.call("ecgmm_eg_reduce", ops._ptr(es), ops._ptr(background), ops._ptr(ix), ops._ptr(grad),
+                 ops._ptr(phi[s0:s0 + n]), n, K, D, C, NB, ops._s())
+    return phi
+
+
+def modality_share(phi, dims=(256, 256, 256)):
+    """shap_fusion_modal_balance.py:177-200 on the device: phi [S, D, C] -> [S, C, 3] percentages of the image / signal
+    / clinical slices' mean |attribution| (0 where all three are 0)."""
+    ops._chk(phi, F32, "phi")
+    if phi.dim() != 3 or len(dims) != 3 or phi.shape[1] != sum(dims) or min(dims) < 1:
+        raise lib.EcgmmError(f"phi must be [S, {sum(dims)}, C] for modality widths {tuple(dims)}; got {tuple(phi.shape)}")
+    S, _, C = phi.shape
+    out = torch.empty((S, C, 3), dtype=F32, device=phi.device)
+    lib.call("ecgmm_modality_share", ops._ptr(phi), ops._ptr(out), S, C, int(dims[0]), int(dims[1]), int(dims[2]),
+             ops._s())
+    return out

@@ -74,6 +74,13 @@ SIGNATURES = {
     "ecgmm_signal_preprocess": [_p, _i, _p, _p, _ll, _ll, _i, _i, _i, _d, _i, _d, _p],
     "ecgmm_perturb_build": [_p, _p, _p, _p, _ll, _i, _i, _p],
     "ecgmm_head_tail": [_p, _p, _p, _p, _p, _ll, _i, _i, _i, _p],
+    "ecgmm_eg_points": [_p, _p, _p, _p, _p, _ll, _i, _i, _i, _p],
+    "ecgmm_eg_gate": [_p, _p, _p, _ll, _i, _i, _p],
+    "ecgmm_eg_reduce": [_p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "ecgmm_modality_share": [_p, _p, _ll, _i, _i, _i, _i, _p],
+    "ecgmm_softmax_rows": [_p, _p, _p, _ll, _i, _p],
+    "ecgmm_gather_rows": [_p, _p, _p, _ll, _i, _i, _p],
+    "ecgmm_gradcam": [_p, _p, _p, _i, _i, _i, _f, _p],
     "ecgmm_bn_rows_fwd": [_p] * 9 + [_i, _i, _f, _f, _i, _i, _p],
     "ecgmm_bn_rows_bwd": [_p] * 9 + [_i, _i, _i, _p],
     # optimizer

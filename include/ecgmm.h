@@ -273,6 +273,42 @@ int ecgmm_perturb_build(const float* e, const float* bg, const uint8_t* masks, e
 int ecgmm_head_tail(const ecgmm_bf16* hidden, const float* b1, const float* w2, const float* b2, float* out,
                     long long rows, int HID, int C, int cls, void* stream);
 
+/* ------------------------------------------------------------------ expected gradients over the fusion head
+ * SURVEY.md section 8f rank 3.  shap_fusion_modal_balance.py:135,159 explains FusionClassifierWrapper (the logits of
+ * fusion_classifier, multimodal_paper_modal_balance.py:283-289) with shap.GradientExplainer = expected gradients;
+ * `shap` is unpinned and absent, so the estimator is restated (ecgmm/explain.py, oracle/model.py) with an EXPLICIT
+ * sampling plan: for sample s and draw k a background row idx[s*K+k] and an interpolation weight alpha[s*K+k]:
+ *     phi[s][d][c] = 1/K * sum_k (e[s][d] - bg[j][d]) * dlogit_c/dx_d (bg[j] + alpha (e[s] - bg[j]))
+ * Everything is fp32 (the sign of the hidden pre-activations decides the gradient).
+ *   ecgmm_eg_points : e [S][D], bg [NB][D], idx [S*K] int32, alpha [S*K] -> points [S*K][D]          (D % 4 == 0)
+ *   (GEMM)          : ecgmm_sgemm  hidden = relu(points W1^T + b1)  [S*K][HID]
+ *   ecgmm_eg_gate   : gate[c][r][h] = hidden[r][h] > 0 ? w2[c][h] : 0      [C][S*K][HID]   (HID % 4 == 0, C <= 8)
+ *   (GEMM)          : ecgmm_sgemm  grad[c] = gate[c] W1   [S*K][D] per class, stored [C][S*K][D]
+ *   ecgmm_eg_reduce : phi [S][D][C] as above
+ *   ecgmm_modality_share : share[s][c][m] = 100 * mean_{d in modality m} |phi[s][d][c]| / sum over the 3 modalities
+ *                          (shap_fusion_modal_balance.py:177-200; 0 when the three means are all 0) */
+int ecgmm_eg_points(const float* e, const float* bg, const int* idx, const float* alpha, float* points, long long S,
+                    int K, int D, int NB, void* stream);
+int ecgmm_eg_gate(const float* hidden, const float* w2, float* gate, long long rows, int HID, int C, void* stream);
+int ecgmm_eg_reduce(const float* e, const float* bg, const int* idx, const float* grad, float* phi, long long S, int K,
+                    int D, int C, int NB, void* stream);
+int ecgmm_modality_share(const float* phi, float* share, long long S, int C, int D0, int D1, int D2, void* stream);
+
+/* ------------------------------------------------------------------ serving helpers (image-only endpoint, Grad-CAM)
+ * the endpoint the mobile app posts to (Groove/components/SubmitButton.tsx:44-45) has no
+ * server code in the reference; what is replaced is the eval-mode chain image_encoder -> image_norm ->
+ * image_classifier (multimodal_paper_modal_balance.py:325-327,337) plus softmax / argmax, and the Grad-CAM map of
+ * the last ResNet stage (artefacts under gpt/, generator not in the repository).
+ *   ecgmm_softmax_rows : logits [rows][C] -> probs [rows][C] and/or argmax [rows] int32 (either may be NULL)
+ *   ecgmm_gather_rows  : out[r][:] = table[idx[r]][:]   (table [NT][D] fp32, idx int32) -- the classifier row of each
+ *                        sample's class is d logit / d feature
+ *   ecgmm_gradcam      : act [N][P][C] bf16 (layer4 output, P = h*w pixels), g [N][C] fp32 (d logit / d pooled) ->
+ *                        cam[n][p] = relu(scale * sum_c g[n][c] act[n][p][c]),  scale = 1/P for the average pool
+ *                        (C % 8 == 0) */
+int ecgmm_softmax_rows(const float* logits, float* probs, int* argmax, long long rows, int C, void* stream);
+int ecgmm_gather_rows(const float* table, const int* idx, float* out, long long rows, int D, int NT, void* stream);
+int ecgmm_gradcam(const ecgmm_bf16* act, const float* g, float* cam, int N, int P, int C, float scale, void* stream);
+
 /* ------------------------------------------------------------------ optimizer
  * torch.optim.Adam step (train.py:43,81).  chunk_table: device array of
  * { float* p; const float* g; float* m; float* v; long long n; } (ecgmm_adam_chunk_bytes() each);

@@ -296,3 +296,64 @@ def modality_shapley(fusion_classifier, e, background, dims=(256, 256, 256), cla
                 w = factorial(len(S)) * factorial(2 - len(S)) / factorial(3)
                 phi[:, i] += w * (f(S + (i,)) - f(S))
     return phi, f(()), f((0, 1, 2))
+
+
+def expected_gradients(fusion_classifier, e, background, idx, alpha):
+    """Expected-gradients attribution of the fusion head's LOGITS, by autograd.
+
+    The reference obtains `shap_values [S, D, C]` from shap.GradientExplainer(FusionClassifierWrapper, bg_embeddings)
+    (shap_fusion_modal_balance.py:135,159); `shap` is unpinned and not installed, so this is the published estimator
+    with an explicit sampling plan instead of the package's internal RNG: for sample s and draw k, a background row
+    idx[s, k] and an interpolation weight alpha[s, k] in [0, 1):
+        phi[s, d, c] = mean_k (e[s, d] - bg[idx[s,k], d]) * d logit_c / d x_d (bg[idx] + alpha (e[s] - bg[idx]))
+    e [S, D], background [NB, D], idx [S, K] integer, alpha [S, K].  Eval mode (dropout = identity)."""
+    was_training = fusion_classifier.training
+    fusion_classifier.eval()
+    S, D = e.shape
+    K = idx.shape[1]
+    b = background[idx.long()]                                    # [S, K, D]
+    diff = e.unsqueeze(1) - b
+    pts = (b + alpha.unsqueeze(-1).to(e.dtype) * diff).detach().reshape(S * K, D).requires_grad_(True)
+    logits = fusion_classifier(pts)
+    C = logits.shape[1]
+    phi = torch.zeros(S, D, C, dtype=e.dtype)
+    for c in range(C):
+        (g,) = torch.autograd.grad(logits[:, c].sum(), pts, retain_graph=c + 1 < C)
+        phi[:, :, c] = (diff * g.view(S, K, D)).mean(1)
+    fusion_classifier.train(was_training)
+    return phi
+
+
+def modality_share(phi, dims=(256, 256, 256)):
+    """shap_fusion_modal_balance.py:177-200: per sample and class, the mean |attribution| of the image / signal /
+    clinical slices of the fused embedding as a percentage of their sum.  phi [S, D, C] -> [S, C, 3]
+    (all-zero attributions give 0, the guard of lime_fusion_modal_balance.py:171-173)."""
+    a = phi.abs()
+    o1, o2 = dims[0], dims[0] + dims[1]
+    m = torch.stack([a[:, :o1].mean(1), a[:, o1:o2].mean(1), a[:, o2:].mean(1)], dim=-1)  # [S, C, 3]
+    total = m.sum(-1, keepdim=True)
+    return torch.where(total > 0, m / total.clamp_min(1e-38) * 100.0, torch.zeros_like(m))
+
+
+def image_endpoint(model, image, class_index=None):
+    """the image-only chain of multimodal_paper_modal_balance.py:325-327,337 in eval mode
+    (image_encoder -> image_norm -> image_classifier), softmax, and the Grad-CAM map of the last ResNet stage:
+        cam[n, y, x] = relu( sum_k alpha[n, k] A[n, k, y, x] ),  alpha[n, k] = mean_{y,x} d logit_c / d A[n, k, y, x]
+    with A = layer4's output and c = class_index (None: each sample's argmax).  Returns (probs [N, C], cam [N, h, w],
+    classes [N])."""
+    was_training = model.training
+    model.eval()
+    enc = model.image_encoder
+    with torch.no_grad():
+        x = enc.maxpool(enc.relu(enc.bn1(enc.conv1(image))))
+        x = enc.layer3(enc.layer2(enc.layer1(x)))
+    act = enc.layer4(x).detach().requires_grad_(True)
+    feat = enc.fc(torch.flatten(enc.avgpool(act), 1))
+    logits = model.image_classifier(model.image_norm(feat))
+    probs = F.softmax(logits.detach(), dim=1)
+    cls = probs.argmax(1) if class_index is None else torch.full((image.shape[0],), int(class_index))
+    (g,) = torch.autograd.grad(logits.gather(1, cls.view(-1, 1)).sum(), act)
+    alpha = g.mean(dim=(2, 3), keepdim=True)
+    cam = F.relu((alpha * act.detach()).sum(1))
+    model.train(was_training)
+    return probs, cam, cls

@@ -159,3 +159,60 @@ def test_graph_mode_marshalling(stub, monkeypatch):
     assert "ecgmm_adam_step" not in stub
     host, dev = opt._reserved[0]
     assert adams[0][1] <= host.shape[0] and int(adams[0][0].value) == dev.data_ptr()
+
+
+def test_attribution_and_serving_flows(stub):
+    """argument marshalling and call sequences of expected gradients, the modality
+    shares, the image endpoint and its Grad-CAM (eager; the graph variant needs real CUDA streams)."""
+    from ecgmm import serve
+
+    m = ecgmm.ECGMultimodalModel(Cfg)
+    e, bg = torch.randn(5, 768), torch.randn(12, 768)
+    idx, alpha = explain.sampling_plan(5, 7, 12, seed=1)
+    assert idx.shape == (5, 7) and idx.dtype == torch.int32 and float(alpha.min()) >= 0 and float(alpha.max()) < 1
+    del stub[:]
+    phi = explain.expected_gradients(m.fusion_classifier, e, bg, idx, alpha)
+    assert phi.shape == (5, 768, 2)
+    assert stub == ["ecgmm_eg_points", "ecgmm_sgemm", "ecgmm_eg_gate", "ecgmm_sgemm", "ecgmm_eg_reduce"]
+    del stub[:]
+    phi = explain.expected_gradients(ecgmm.FusionClassifierWrapper(m.fusion_classifier), e, bg, idx, alpha,
+                                     chunk_samples=2)
+    assert stub.count("ecgmm_eg_reduce") == 3  # 2 + 2 + 1 samples
+    sh = explain.modality_share(phi)
+    assert sh.shape == (5, 2, 3) and stub[-1] == "ecgmm_modality_share"
+    with pytest.raises(lib.EcgmmError):
+        explain.expected_gradients(m.fusion_classifier, e, bg, idx + 12, alpha)  # background row out of range
+    with pytest.raises(lib.EcgmmError):
+        explain.expected_gradients(m.fusion_classifier, e, bg, idx[:, :3], alpha)
+    with pytest.raises(lib.EcgmmError):
+        explain.expected_gradients(m.fusion_classifier, e, bg, idx.float(), alpha)
+    with pytest.raises(lib.EcgmmError):
+        explain.modality_share(phi, dims=(256, 256, 128))
+
+    image = (torch.rand(2, 3, 64, 160) * 255).to(torch.uint8)
+    ep = serve.ImageEndpoint(m, example_image=image, graph=False)
+    with pytest.raises(lib.EcgmmError):
+        ep(image)  # the model is still in train mode
+    m.eval()
+    del stub[:]
+    probs, classes = ep(image)
+    assert probs.shape == (2, 2) and classes.shape == (2,) and classes.dtype == torch.int32
+    assert stub[-1] == "ecgmm_softmax_rows" and "ecgmm_chan_stats" not in stub and "ecgmm_conv2d_fwd_stats" not in stub
+    assert stub.count("ecgmm_bn_eval_coeffs") == 20  # folded once per endpoint ...
+    del stub[:]
+    ep(image)
+    n_classify = len(stub)
+    assert "ecgmm_bn_eval_coeffs" not in stub and "ecgmm_conv_weight_prep" not in stub  # ... not per request
+    ep_cam = serve.ImageEndpoint(m, graph=False, class_index=1)
+    ep_cam.gradcam(image)
+    del stub[:]
+    probs, classes, cam = ep_cam.gradcam(image)
+    assert cam.shape == (2, 2, 5) and cam.dtype == torch.float32
+    assert stub[-4:] == ["ecgmm_gather_rows", "ecgmm_layernorm_bwd", "ecgmm_sgemm", "ecgmm_gradcam"]
+    assert len(stub) == n_classify + 4  # Grad-CAM costs four small launches on top of a classification
+    with torch.no_grad():
+        m.image_encoder.bn1.running_mean.add_(1.0)  # new statistics are picked up: folded again
+    ep_cam.gradcam(image)
+    assert stub.count("ecgmm_bn_eval_coeffs") == 20
+    with pytest.raises(lib.EcgmmError):
+        serve.ImageEndpoint(m, graph=False, class_index=5).gradcam(image)

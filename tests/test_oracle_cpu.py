@@ -135,3 +135,98 @@ def test_modality_shapley_spec_properties():
     assert torch.allclose(f @ explain.shapley_matrix(), phi, atol=1e-6)
     w = explain.shapley_matrix()
     assert torch.allclose(w.sum(0), torch.zeros(3), atol=1e-7) and torch.allclose(w[7], torch.full((3,), 1 / 3))
+
+
+def _eg_case(S=3, K=40, NB=12, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    e = torch.randn(S, 768, generator=g)
+    bg = torch.randn(NB, 768, generator=g)
+    idx = torch.randint(0, NB, (S, K), generator=g, dtype=torch.int32)
+    alpha = torch.rand(S, K, generator=g)
+    return e, bg, idx, alpha
+
+
+def test_expected_gradients_spec_properties():
+    """SURVEY.md section 8f rank 3 (self-contained spec; `shap` is absent): the autograd oracle against (i) the closed
+    form the CUDA path evaluates -- W1^T([W1 x + b1 > 0] * w2[c]) around two GEMMs --, (ii) the exact answer for a
+    head that is linear on the path, (iii) completeness: on a fine alpha grid against ONE background the attributions
+    sum to logit(e) - logit(background)."""
+    ora = make_oracle(seed=7)
+    head = ora.fusion_classifier
+    e, bg, idx, alpha = _eg_case()
+    S, K, D = 3, 40, 768
+    phi = om.expected_gradients(head, e, bg, idx, alpha)
+    assert phi.shape == (S, D, 2)
+    # (i) the device algorithm, step by step in torch
+    W1, b1, W2 = head[0].weight.detach(), head[0].bias.detach(), head[3].weight.detach()
+    b = bg[idx.long()]
+    diff = e[:, None] - b
+    pts = (b + alpha[..., None] * diff).reshape(S * K, D)
+    hidden = torch.relu(pts @ W1.T + b1)
+    gate = (hidden > 0).float()[None] * W2[:, None, :]            # [C, rows, HID]
+    grad = (gate.reshape(-1, W1.shape[0]) @ W1).view(2, S, K, D)  # one [C*rows, HID] x [HID, D] product
+    phi_dev = (diff[None] * grad).mean(2).permute(1, 2, 0)
+    assert torch.allclose(phi, phi_dev, atol=1e-7)
+    # (ii) a bias so large that every hidden unit is active: the head is affine, phi = (e - mean_k bg_jk) * (W2 W1)^T
+    import copy
+
+    lin = copy.deepcopy(head)
+    with torch.no_grad():
+        lin[0].bias.fill_(1e3)
+    phi_lin = om.expected_gradients(lin, e, bg, idx, alpha)
+    expect = (e - b.mean(1))[:, :, None] * (W2 @ W1).T[None]
+    assert torch.allclose(phi_lin, expect, atol=1e-5)
+    # (iii) completeness of the path integral
+    Kf = 2000
+    idx1 = torch.zeros(1, Kf, dtype=torch.int32)
+    alpha1 = ((torch.arange(Kf) + 0.5) / Kf).view(1, Kf)
+    phi1 = om.expected_gradients(head, e[:1], bg[:1], idx1, alpha1)
+    head.eval()
+    with torch.no_grad():
+        delta = head(e[:1]) - head(bg[:1])
+    assert torch.allclose(phi1.sum(1), delta, atol=2e-4)
+
+
+def test_modality_share_spec():
+    """shap_fusion_modal_balance.py:177-200: mean |phi| per modality slice as a percentage of the three."""
+    g = torch.Generator().manual_seed(2)
+    phi = torch.randn(4, 768, 2, generator=g)
+    phi[:, 256:512] *= 3.0
+    sh = om.modality_share(phi)
+    assert sh.shape == (4, 2, 3) and torch.allclose(sh.sum(-1), torch.full((4, 2), 100.0), atol=1e-4)
+    a = phi[1, :, 0].abs()
+    ref = torch.stack([a[:256].mean(), a[256:512].mean(), a[512:].mean()])
+    assert torch.allclose(sh[1, 0], ref / ref.sum() * 100, atol=1e-4) and float(sh[:, :, 1].min()) > 50
+    assert float(om.modality_share(torch.zeros(2, 768, 2)).abs().max()) == 0.0
+    sh2 = om.modality_share(phi[:, :672], dims=(512, 128, 32))
+    assert torch.allclose(sh2.sum(-1), torch.full((4, 2), 100.0), atol=1e-4)
+
+
+def test_image_endpoint_gradcam_spec():
+    """the oracle's autograd Grad-CAM against the closed form the CUDA path evaluates
+    (classifier row -> LayerNorm backward -> fc^T -> 1/(h w)), and the image-only chain against the full forward."""
+    ora = make_oracle(seed=7)
+    ora.eval()
+    g = torch.Generator().manual_seed(9)
+    image = torch.randn(3, 3, 64, 160, generator=g).clamp_(-1, 1)
+    probs, cam, cls = om.image_endpoint(ora, image, class_index=1)
+    with torch.no_grad():
+        full = ora(image, torch.randn(3, 600, generator=g), torch.randn(3, 24, generator=g))
+        enc = ora.image_encoder
+        x = enc.maxpool(enc.relu(enc.bn1(enc.conv1(image))))
+        act = enc.layer4(enc.layer3(enc.layer2(enc.layer1(x))))
+        pooled = act.mean((2, 3))
+        feat = enc.fc(pooled)
+    assert torch.allclose(probs, torch.softmax(full[0], 1), atol=1e-6) and cam.shape == (3,) + tuple(act.shape[2:])
+    assert float(cam.min()) >= 0.0 and float(cam.max()) > 0.0 and cls.tolist() == [1, 1, 1]
+    ln, wc = ora.image_norm, ora.image_classifier.weight.detach()
+    mu = feat.mean(1, keepdim=True)
+    rstd = (feat.var(1, unbiased=False, keepdim=True) + ln.eps).rsqrt()
+    xhat = (feat - mu) * rstd
+    dxh = wc[1][None] * ln.weight.detach()[None]                                 # d logit_1 / d xhat
+    dfeat = rstd * (dxh - dxh.mean(1, keepdim=True) - xhat * (dxh * xhat).mean(1, keepdim=True))
+    dpooled = dfeat @ enc.fc.weight.detach()
+    cam2 = torch.relu((dpooled[:, :, None, None] * act).sum(1) / (act.shape[2] * act.shape[3]))
+    assert torch.allclose(cam, cam2, atol=1e-6 + 1e-4 * float(cam.max()))
+    p2, cam3, cls3 = om.image_endpoint(ora, image)  # argmax classes
+    assert cls3.tolist() == probs.argmax(1).tolist() and not ora.training

@@ -1,0 +1,134 @@
+"""GPU: expected gradients / modality shares and the image endpoint with Grad-CAM (rank 4)
+against the oracle.  Written after the round's GPU budget was spent: the kernels (csrc/attrib.cu) are small
+bandwidth-bound ones and the glue was dry-run on the CPU (tests/test_control_flow_cpu.py), but none of this has run on
+hardware yet -- hence the file name, which makes pytest collect it LAST."""
+import pytest
+import torch
+
+from ecgmm import explain, lib, serve
+from oracle import model as om
+from parity_util import build_pair
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _eg_case(S, K, NB, seed):
+    g = torch.Generator().manual_seed(seed)
+    e = torch.randn(S, 768, generator=g)
+    bg = torch.randn(NB, 768, generator=g)
+    idx, alpha = explain.sampling_plan(S, K, NB, seed=seed + 1)
+    return e, bg, idx, alpha
+
+
+@pytest.mark.parametrize("S,K,NB", [(4, 50, 20), (1, 1, 1), (7, 33, 100)])
+def test_expected_gradients_match_oracle(S, K, NB):
+    """fp32 end to end: |phi - phi_ref| <= 2e-4 (phi ~ 5e-2; one hidden unit whose pre-activation changes sign
+    between the two summation orders moves an entry by ~3e-5)."""
+    ora, dut = build_pair(seed=7)
+    e, bg, idx, alpha = _eg_case(S, K, NB, seed=100 + S)
+    ref = om.expected_gradients(ora.fusion_classifier, e, bg, idx, alpha)
+    phi = explain.expected_gradients(dut.fusion_classifier, e.to(DEV), bg.to(DEV), idx, alpha)
+    assert phi.shape == ref.shape == (S, 768, 2) and phi.dtype == torch.float32
+    assert (phi.cpu() - ref).abs().max().item() <= 2e-4
+    # plan on the device, wrapper module, chunked evaluation: same numbers
+    phi2 = explain.expected_gradients(om_wrapper(dut), e.to(DEV), bg.to(DEV), idx.to(DEV), alpha.to(DEV), chunk_samples=3)
+    assert (phi2 - phi).abs().max().item() <= 1e-6
+    share = explain.modality_share(phi)
+    assert share.shape == (S, 2, 3)
+    assert (share.cpu() - om.modality_share(phi.cpu())).abs().max().item() <= 1e-3
+    assert (share.sum(-1) - 100.0).abs().max().item() <= 1e-3
+
+
+def om_wrapper(dut):
+    import ecgmm
+
+    return ecgmm.FusionClassifierWrapper(dut.fusion_classifier)
+
+
+def test_modality_share_edge_cases():
+    phi = torch.zeros(3, 672, 2, device=DEV)
+    assert float(explain.modality_share(phi, dims=(512, 128, 32)).abs().max()) == 0.0  # the all-zero guard
+    phi[:, 512:640, 1] = -2.0  # only the signal slice of class 1 carries attribution
+    sh = explain.modality_share(phi, dims=(512, 128, 32))
+    assert torch.equal(sh[:, 1].cpu(), torch.tensor([[0.0, 100.0, 0.0]] * 3)) and float(sh[:, 0].abs().max()) == 0.0
+    with pytest.raises(lib.EcgmmError):
+        explain.modality_share(phi, dims=(256, 256, 256))
+
+
+def _images(N, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    u8 = torch.randint(0, 256, (N, 3, H, W), generator=g, dtype=torch.uint8)
+    return u8, (u8.float() / 255.0 - 0.5) / 0.5  # ToTensor + Normalize(0.5, 0.5), dataset.py:119-123
+
+
+def _tail_oracle(ora, act_nchw, classes):
+    """The oracle's Grad-CAM tail (autograd) on a GIVEN layer4 activation."""
+    act = act_nchw.clone().requires_grad_(True)
+    feat = ora.image_encoder.fc(act.mean((2, 3)))
+    logits = ora.image_classifier(ora.image_norm(feat))
+    (g,) = torch.autograd.grad(logits.gather(1, classes.view(-1, 1).long()).sum(), act)
+    cam = torch.relu((g.mean((2, 3), keepdim=True) * act.detach()).sum(1))
+    return torch.softmax(logits.detach(), 1), cam
+
+
+@pytest.mark.parametrize("N,H,W", [(3, 64, 160), (2, 224, 224)])
+def test_image_endpoint_and_gradcam(N, H, W):
+    ora, dut = build_pair(seed=7)
+    ora.eval()
+    dut.eval()
+    u8, img = _images(N, H, W, seed=N * 10 + 1)
+    p_ref, cam_ref, _ = om.image_endpoint(ora, img, class_index=1)
+    ep = serve.ImageEndpoint(dut, graph=False, class_index=1)
+    probs, classes, cam = ep.gradcam(u8.to(DEV))
+    assert classes.tolist() == [1] * N and cam.shape == cam_ref.shape and float(cam.min()) >= 0.0
+    # (1) the whole chain against the fp32 oracle: bf16 activations through 20 convolutions
+    assert (probs.cpu() - p_ref).abs().max().item() <= 4e-2
+    num, den = (cam.cpu() - cam_ref).norm().item(), cam_ref.norm().item()
+    assert den > 0 and num / den <= 0.15, (num, den)
+    # (2) the tail (pool, fc, LayerNorm, classifier, the closed-form gradient, the channel contraction) on the
+    # DEVICE's own layer4 activation: fp32 arithmetic on both sides
+    act, *_ = serve.image_features(dut, u8.to(DEV))
+    act_nchw = act.float().permute(0, 3, 1, 2).contiguous().cpu()
+    p_tail, cam_tail = _tail_oracle(ora, act_nchw, torch.ones(N, dtype=torch.int64))
+    assert (probs.cpu() - p_tail).abs().max().item() <= 1e-5
+    assert (cam.cpu() - cam_tail).abs().max().item() <= 1e-6 + 1e-4 * cam_tail.max().item()
+    # (3) argmax classes; eval mode has no batch statistics, so a sample's result does not depend on its neighbours
+    ep2 = serve.ImageEndpoint(dut, graph=False)
+    probs2, classes2 = ep2(u8.to(DEV))
+    assert (probs2 - probs).abs().max().item() <= 1e-6
+    assert classes2.tolist() == probs2.argmax(1).tolist()
+    probs3, _ = ep2(u8.flip(0).contiguous().to(DEV))
+    assert (probs3.flip(0) - probs2).abs().max().item() <= 1e-5
+    dut.train()
+    with pytest.raises(lib.EcgmmError):
+        ep2(u8.to(DEV))
+
+
+def test_image_endpoint_cuda_graph_replay():
+    """One launch per request: the graphed endpoint returns what the eager one does, for new contents of the input
+    buffer too, and notices new weights."""
+    ora, dut = build_pair(seed=7)
+    dut.eval()
+    u8a, _ = _images(2, 64, 160, seed=5)
+    u8b, _ = _images(2, 64, 160, seed=6)
+    eager = serve.ImageEndpoint(dut, graph=False)
+    ga = serve.ImageEndpoint(dut, example_image=u8a.to(DEV), graph=True)
+    for u8 in (u8a, u8b, u8a):
+        pe, ce, came = [t.clone() for t in eager.gradcam(u8.to(DEV))]
+        pg, cg, camg = ga.gradcam(u8.to(DEV))
+        torch.cuda.synchronize()
+        assert (pg - pe).abs().max().item() <= 1e-6 and cg.tolist() == ce.tolist()
+        assert (camg - came).abs().max().item() <= 1e-6 + 1e-5 * came.max().item()
+        pg2, _ = ga(u8.to(DEV))
+        assert (pg2 - pe).abs().max().item() <= 1e-6
+    n0 = lib.launch_count()
+    ga(u8b.to(DEV))
+    assert lib.launch_count() == n0  # a replay issues no launch of its own from the host side of the library
+    with torch.no_grad():
+        dut.image_classifier.bias.add_(torch.tensor([0.5, -0.5], device=DEV))
+    pe, _ = eager(u8b.to(DEV))
+    pg, _ = ga(u8b.to(DEV))  # re-captured
+    assert (pg - pe).abs().max().item() <= 1e-6
+    with pytest.raises(lib.EcgmmError):
+        ga(u8a[:1].to(DEV))

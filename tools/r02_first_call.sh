@@ -44,6 +44,7 @@ unset ECGMM_TEST_EXPERIMENTAL
 # --- the other configs (BASELINE.json configs[1], [3], [4]) and the reference arm
 run signal   300 python tools/signal_bench.py
 run perturb  300 python tools/perturb_bench.py
+run zz_tests 600 python -m pytest tests/test_zz_modality_shapley_gpu.py tests/test_zz_attrib_serve_gpu.py -q -m gpu
 run kfold    600 python tools/kfold_bench.py
 run ref_arm  300 python bench.py --impl reference --steps 2 --warmup 1
 cat $O/${TAG}_index.log
