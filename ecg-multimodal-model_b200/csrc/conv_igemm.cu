@@ -49,6 +49,13 @@ struct alignas(64) NtParams {
   float* psum;
   float* psq;
   int stats_C;
+  // igemm_nt_kernel<BN, STAGES, true> only (inference): the epilogue stores
+  // act(acc * scale[c] + shift[c] + res) -- folded BatchNorm, optional residual (same layout as out), optional ReLU.
+  // Appended so that the offsets the training kernels read do not move.
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* res;
+  int relu;
 };
 
 template <int BN, int STAGES>
@@ -60,7 +67,7 @@ struct NtSmem {
   static constexpr int kBytes = kStatsOff + 4 * 2 * BN * 8 + 1024;  // barriers + statistics + alignment slack
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool FUSED = false>
 __global__ void __launch_bounds__(192, 1) igemm_nt_kernel(const __grid_constant__ NtParams p) {
   using L = NtSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -214,6 +221,30 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_kernel(const __grid_constant_
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[q * 8 + j]);
+            if constexpr (FUSED) {  // warp-uniform addresses: one L1 line serves the whole warp
+              const int ch = nt * BN + c * 32 + q * 8;
+              const float4* sc = reinterpret_cast<const float4*>(p.scale + ch);
+              const float4* sh = reinterpret_cast<const float4*>(p.shift + ch);
+              const float4 s0 = __ldg(sc), s1 = __ldg(sc + 1), h0 = __ldg(sh), h1 = __ldg(sh + 1);
+              f[0] = fmaf(f[0], s0.x, h0.x); f[1] = fmaf(f[1], s0.y, h0.y);
+              f[2] = fmaf(f[2], s0.z, h0.z); f[3] = fmaf(f[3], s0.w, h0.w);
+              f[4] = fmaf(f[4], s1.x, h1.x); f[5] = fmaf(f[5], s1.y, h1.y);
+              f[6] = fmaf(f[6], s1.z, h1.z); f[7] = fmaf(f[7], s1.w, h1.w);
+              if (p.res) {
+                const uint4 old = *reinterpret_cast<const uint4*>(p.res + (dst - p.out) + c * 32 + q * 8);
+                const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 o = __bfloat1622float2(ob[j]);
+                  f[2 * j] += o.x;
+                  f[2 * j + 1] += o.y;
+                }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+            }
             if (p.accumulate) {
               const uint4 old = d4[q];
               const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
@@ -270,10 +301,15 @@ static int launch_nt_t(const NtParams& p, cudaStream_t s) {
   if (!configured[ds]) {
     ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     L::kBytes));
+    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::kBytes));
     configured[ds] = true;
   }
   int grid = nt_grid(p.total_tiles, p.n_tiles_n);
-  igemm_nt_kernel<BN, STAGES><<<grid, 192, L::kBytes, s>>>(p);
+  if (p.scale)
+    igemm_nt_kernel<BN, STAGES, true><<<grid, 192, L::kBytes, s>>>(p);
+  else
+    igemm_nt_kernel<BN, STAGES><<<grid, 192, L::kBytes, s>>>(p);
   return check_launch("igemm_nt_kernel");
 }
 
@@ -368,7 +404,8 @@ using namespace ecgmm;
 namespace ecgmm {
 bool nt_halo_supported(int Cin, int Cout, int R, int S, int stride, int W);
 int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int R, int S,
-                   int dgrad, int accumulate, cudaStream_t st);
+                   int dgrad, int accumulate, cudaStream_t st, const float* scale = nullptr,
+                   const float* shift = nullptr, const __nv_bfloat16* res = nullptr, int relu = 0);
 // experimental rolling-accumulator kernel (conv_nt_stack.cu), selected only with ECGMM_NT_STACK=1
 bool nt_stack_supported(int Cin, int Cout, int R, int S, int stride, int W);
 int launch_nt_stack(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int dgrad,
@@ -394,19 +431,27 @@ extern "C" int ecgmm_conv2d_fwd_stats_rows(int N, int H, int W, int Cin, int Cou
   return 4 * nt_grid(p.n_img * p.tiles_h * p.tiles_w * n_tiles_n, n_tiles_n);
 }
 
+struct FusedEpilogue {  // folded BatchNorm (+ residual, + ReLU) applied by the forward epilogue; scale == NULL: off
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  const __nv_bfloat16* res = nullptr;
+  int relu = 0;
+};
+
 static int conv2d_fwd_impl(const ecgmm_bf16* x_, const ecgmm_bf16* w_, ecgmm_bf16* y_, float* psum, float* psq, int N,
                            int H, int W, int Cin, int Cout, int R, int S, int stride, int padH, int padW,
-                           void* stream) {
+                           void* stream, const FusedEpilogue& fe = FusedEpilogue()) {
   ECGMM_CHECK(x_ && w_ && y_, ECGMM_ERR_ARG, "conv2d_fwd: null pointer");
   int rc = check_conv_cfg(Cin, Cout, R, S, stride, padH, padW);
   if (rc) return rc;
   if (N == 0) return ECGMM_OK;
-  if (getenv("ECGMM_NT_STACK") && nt_stack_supported(Cin, Cout, R, S, stride, W))
+  if (!fe.scale && getenv("ECGMM_NT_STACK") && nt_stack_supported(Cin, Cout, R, S, stride, W))
     return launch_nt_stack(reinterpret_cast<const __nv_bfloat16*>(x_), reinterpret_cast<const __nv_bfloat16*>(w_),
                            reinterpret_cast<__nv_bfloat16*>(y_), N, H, W, 0, 0, static_cast<cudaStream_t>(stream));
   if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY"))
     return launch_nt_halo(reinterpret_cast<const __nv_bfloat16*>(x_), reinterpret_cast<const __nv_bfloat16*>(w_),
-                          reinterpret_cast<__nv_bfloat16*>(y_), N, H, W, R, S, 0, 0, static_cast<cudaStream_t>(stream));
+                          reinterpret_cast<__nv_bfloat16*>(y_), N, H, W, R, S, 0, 0, static_cast<cudaStream_t>(stream),
+                          fe.scale, fe.shift, fe.res, fe.relu);
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(x_);
   const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
   NtParams p;
@@ -431,7 +476,27 @@ static int conv2d_fwd_impl(const ecgmm_bf16* x_, const ecgmm_bf16* w_, ecgmm_bf1
   p.psum = psum;
   p.psq = psq;
   p.stats_C = Cout;
+  p.scale = fe.scale;
+  p.shift = fe.shift;
+  p.res = fe.res;
+  p.relu = fe.relu;
   return launch_nt(p, Cout, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ecgmm_conv2d_fwd_bn(const ecgmm_bf16* x, const ecgmm_bf16* w, ecgmm_bf16* y, const float* scale,
+                                   const float* shift, const ecgmm_bf16* res, int relu, int N, int H, int W, int Cin,
+                                   int Cout, int R, int S, int stride, int padH, int padW, void* stream) {
+  ECGMM_CHECK(scale && shift, ECGMM_ERR_ARG, "conv2d_fwd_bn: null scale / shift");
+  ECGMM_CHECK((reinterpret_cast<uintptr_t>(scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(shift) & 15) == 0,
+              ECGMM_ERR_ALIGN, "conv2d_fwd_bn: scale / shift must be 16-byte aligned");
+  ECGMM_CHECK(res == nullptr || (reinterpret_cast<uintptr_t>(res) & 15) == 0, ECGMM_ERR_ALIGN,
+              "conv2d_fwd_bn: residual must be 16-byte aligned");
+  FusedEpilogue fe;
+  fe.scale = scale;
+  fe.shift = shift;
+  fe.res = reinterpret_cast<const __nv_bfloat16*>(res);
+  fe.relu = relu;
+  return conv2d_fwd_impl(x, w, y, nullptr, nullptr, N, H, W, Cin, Cout, R, S, stride, padH, padW, stream, fe);
 }
 
 extern "C" int ecgmm_conv2d_fwd(const ecgmm_bf16* x, const ecgmm_bf16* w, ecgmm_bf16* y, int N, int H, int W, int Cin,

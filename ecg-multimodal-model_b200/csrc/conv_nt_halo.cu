@@ -43,6 +43,13 @@ struct alignas(64) NtHaloParams {
   int tiles_w, H, W, n_img, total_tiles;
   __nv_bfloat16* out;  // [N][H][W][64]
   int accumulate;
+  // igemm_nt_halo_kernel<true> only (inference): the epilogue applies the folded
+  // BatchNorm y = acc * scale[c] + shift[c], adds the residual tile fetched through res_map when accumulate != 0,
+  // then ReLU when relu != 0.  Appended so that the offsets the training kernel reads do not move.
+  const float* scale;
+  const float* shift;
+  int relu;
+  CUtensorMap res_map;  // residual [N][H][W][64], box (64, 128, 1, 1)
 };
 
 struct NtHaloSmem {
@@ -51,8 +58,13 @@ struct NtHaloSmem {
   static constexpr int kOut = kW + kNhStages * kStage;             // 178176: 3 output staging tiles of 16 KiB
   static constexpr int kBarOff = kOut + 3 * kNhTile * 128;         // 227328
   static constexpr int kBytes = kBarOff + 256 + 1024;
+  static constexpr int kCoefOff = kBarOff + 256;          // fused epilogue: scale[64], shift[64] fp32
+  static constexpr int kBytesFused = kBytes + 512;
 };
 
+// FUSED = false: forward / data-gradient as used by training.  FUSED = true: forward with the folded-BatchNorm
+// (+ residual, + ReLU) epilogue of the serving path; not selected unless the caller asks for it (ecgmm_conv2d_fwd_bn).
+template <bool FUSED>
 __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_constant__ NtHaloParams p) {
   using L = NtHaloSmem;
   extern __shared__ uint8_t smem_raw[];
@@ -87,6 +99,13 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
     for (int i = 0; i < 3; ++i) mbar_init(&ofull[i], 1);
     tma_prefetch_desc(&p.y_map);
     mbar_fence_init();
+  }
+  if constexpr (FUSED) {
+    float* coef = reinterpret_cast<float*>(smem + L::kCoefOff);
+    if (threadIdx.x >= 64) {
+      const int i = threadIdx.x - 64;  // 128 epilogue threads: scale[0..64) then shift[0..64)
+      coef[i] = i < 64 ? p.scale[i] : p.shift[i - 64];
+    }
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, 128);
@@ -186,7 +205,7 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
       int w0, oh, img;
       tile_coords(blockIdx.x, w0, oh, img);
       mbar_expect_tx(&ofull[0], kNhTile * 128);
-      tma_load_4d(sOut, &p.y_map, &ofull[0], 0, w0, oh, img);
+      tma_load_4d(sOut, FUSED ? &p.res_map : &p.y_map, &ofull[0], 0, w0, oh, img);
     }
     int it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
@@ -205,7 +224,7 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
           tile_coords(tn, nw0, noh, nimg);
           const int nb = (it + 1) % 3;
           mbar_expect_tx(&ofull[nb], kNhTile * 128);
-          tma_load_4d(sOut + nb * (kNhTile * 128), &p.y_map, &ofull[nb], 0, nw0, noh, nimg);
+          tma_load_4d(sOut + nb * (kNhTile * 128), FUSED ? &p.res_map : &p.y_map, &ofull[nb], 0, nw0, noh, nimg);
         }
       }
       named_bar_sync(1, 128);
@@ -226,6 +245,14 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
           float f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[q * 8 + j]);
+          if constexpr (FUSED) {  // broadcast reads: every thread of the warp asks for the same 16 bytes
+            const float4* cf = reinterpret_cast<const float4*>(smem + L::kCoefOff) + (c * 8 + q * 2);
+            const float4 s0 = cf[0], s1 = cf[1], h0 = cf[16], h1 = cf[17];
+            f[0] = fmaf(f[0], s0.x, h0.x); f[1] = fmaf(f[1], s0.y, h0.y);
+            f[2] = fmaf(f[2], s0.z, h0.z); f[3] = fmaf(f[3], s0.w, h0.w);
+            f[4] = fmaf(f[4], s1.x, h1.x); f[5] = fmaf(f[5], s1.y, h1.y);
+            f[6] = fmaf(f[6], s1.z, h1.z); f[7] = fmaf(f[7], s1.w, h1.w);
+          }
           if (p.accumulate) {
             const uint4 old = *d4;
             const __nv_bfloat162* oldb = reinterpret_cast<const __nv_bfloat162*>(&old);
@@ -234,6 +261,12 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_halo_kernel(const __grid_cons
               const float2 o = __bfloat1622float2(oldb[j]);
               f[2 * j] += o.x;
               f[2 * j + 1] += o.y;
+            }
+          }
+          if constexpr (FUSED) {
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
             }
           }
           uint4 v;
@@ -267,8 +300,10 @@ bool nt_halo_supported(int Cin, int Cout, int R, int S, int stride, int W) {
 }
 
 // dgrad != 0: w is the [Cin][R][S][Cout] shadow and taps are mirrored (dx[h,w] += dy[h+pad-r, w+pad-s] W[r,s]).
+// scale != NULL selects the fused inference epilogue (forward only): y = act(conv * scale + shift [+ res]).
 int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int R, int S,
-                   int dgrad, int accumulate, cudaStream_t st) {
+                   int dgrad, int accumulate, cudaStream_t st, const float* scale, const float* shift,
+                   const __nv_bfloat16* res, int relu) {
   NtHaloParams p;
   memset(&p, 0, sizeof(p));
   p.ntaps = R * S;
@@ -288,6 +323,14 @@ int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16
   p.total_tiles = N * H * p.tiles_w;
   p.out = y;
   p.accumulate = accumulate;
+  const bool fused = scale != nullptr;
+  if (fused) {
+    ECGMM_CHECK(shift && !dgrad && !accumulate, ECGMM_ERR_ARG, "nt_halo: the fused epilogue is forward-only");
+    p.scale = scale;
+    p.shift = shift;
+    p.relu = relu;
+    p.accumulate = res != nullptr;  // "old tile" = the residual
+  }
   const uint64_t e = 2;
   int rc = make_tmap_4d(&p.x_map, x, 64, W, H, N, 64 * e, (uint64_t)W * 64 * e, (uint64_t)H * W * 64 * e, 64, kNhBoxW, 1);
   if (rc) return rc;
@@ -295,15 +338,26 @@ int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16
   if (rc) return rc;
   rc = make_tmap_4d(&p.y_map, y, 64, W, H, N, 64 * e, (uint64_t)W * 64 * e, (uint64_t)H * W * 64 * e, 64, kNhTile, 1);
   if (rc) return rc;
+  if (fused && res) {
+    rc = make_tmap_4d(&p.res_map, res, 64, W, H, N, 64 * e, (uint64_t)W * 64 * e, (uint64_t)H * W * 64 * e, 64, kNhTile, 1);
+    if (rc) return rc;
+  } else {
+    p.res_map = p.y_map;
+  }
   static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
   const int ds = device_slot();
   if (!configured[ds]) {
-    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     NtHaloSmem::kBytes));
+    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    NtHaloSmem::kBytesFused));
     configured[ds] = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  igemm_nt_halo_kernel<<<grid, 192, NtHaloSmem::kBytes, st>>>(p);
+  if (fused)
+    igemm_nt_halo_kernel<true><<<grid, 192, NtHaloSmem::kBytesFused, st>>>(p);
+  else
+    igemm_nt_halo_kernel<false><<<grid, 192, NtHaloSmem::kBytes, st>>>(p);
   return check_launch("igemm_nt_halo_kernel");
 }
 

@@ -36,6 +36,7 @@ SIGNATURES = {
     "ecgmm_conv2d_fwd": [_p, _p, _p] + [_i] * 10 + [_p],
     "ecgmm_conv2d_fwd_stats_rows": [_i] * 10,
     "ecgmm_conv2d_fwd_stats": [_p, _p, _p, _p, _p] + [_i] * 10 + [_p],
+    "ecgmm_conv2d_fwd_bn": [_p, _p, _p, _p, _p, _p, _i] + [_i] * 10 + [_p],
     "ecgmm_conv2d_dgrad": [_p, _p, _p] + [_i] * 11 + [_p],
     "ecgmm_conv2d_wgrad": [_p, _p, _p] + [_i] * 10 + [_p, _ll, _p],
     "ecgmm_conv2d_wgrad_workspace": [_i] * 10,

@@ -136,6 +136,26 @@ def conv2d_fwd(x: torch.Tensor, w_fwd: torch.Tensor, stride: int = 1, want_stats
     return y
 
 
+def conv2d_fwd_bn(x: torch.Tensor, w_fwd: torch.Tensor, st, stride: int = 1, res: torch.Tensor = None,
+                  relu: bool = True) -> torch.Tensor:
+    """Serving path: y = act(conv(x, w) * st.scale + st.shift + res) in one kernel (folded BatchNorm epilogue)."""
+    _chk(x, BF16, "x")
+    _chk(w_fwd, BF16, "w_fwd")
+    N, H, W, Cin = x.shape
+    Cout, R, S, Cin2 = w_fwd.shape
+    assert Cin == Cin2
+    pH, pW = R // 2, S // 2
+    Ho, Wo = _conv_out(H, W, R, S, stride, pH, pW)
+    y = torch.empty((N, Ho, Wo, Cout), dtype=BF16, device=x.device)
+    if res is not None:
+        _chk(res, BF16, "res")
+        assert tuple(res.shape) == tuple(y.shape)
+    _timed(f"conv_fwd_bn/{Cin}x{Cout}k{R}{S}s{stride}", 2.0 * N * Ho * Wo * Cout * Cin * R * S, "ecgmm_conv2d_fwd_bn",
+           _ptr(x), _ptr(w_fwd), _ptr(y), _ptr(st.scale), _ptr(st.shift), _ptr(res), int(relu), N, H, W, Cin, Cout, R, S,
+           stride, pH, pW, _s())
+    return y
+
+
 def conv2d_dgrad(dy: torch.Tensor, w_dgrad: torch.Tensor, in_hw, stride: int = 1, out: torch.Tensor = None,
                  accumulate: bool = False) -> torch.Tensor:
     _chk(dy, BF16, "dy")

@@ -24,9 +24,15 @@ from __future__ import annotations
 
 import torch
 
+import os
+
 from . import lib, ops
 
 F32 = torch.float32
+# ECGMM_SERVE_FUSED=1: BatchNorm (+ residual, + ReLU) applied by the convolution epilogue (ecgmm_conv2d_fwd_bn) -- one
+# kernel and one write per conv instead of conv -> scale/shift pass.  Off by default: written after the round's GPU
+# budget was spent, not yet run on hardware.
+FUSED_EPILOGUE = os.environ.get("ECGMM_SERVE_FUSED", "0") == "1"
 
 
 def fold_batchnorm(model):
@@ -43,6 +49,14 @@ def _block_eval(blk, x, co):
     """torchvision BasicBlock (resnet.py:59-104) with folded statistics: conv -> scale/shift+ReLU -> conv ->
     scale/shift (+ identity or its 1x1 projection) -> ReLU."""
     w1f, _ = blk.conv1.shadows()
+    if FUSED_EPILOGUE:
+        m = ops.conv2d_fwd_bn(x, w1f, co[id(blk.bn1)], blk.stride, relu=True)
+        idn = x
+        if blk.downsample is not None:
+            wdf, _ = blk.downsample[0].shadows()
+            idn = ops.conv2d_fwd_bn(x, wdf, co[id(blk.downsample[1])], blk.stride, relu=False)
+        w2f, _ = blk.conv2.shadows()
+        return ops.conv2d_fwd_bn(m, w2f, co[id(blk.bn2)], 1, res=idn, relu=True)
     m, _ = ops.bn_apply(ops.conv2d_fwd(x, w1f, blk.stride), co[id(blk.bn1)], relu=True)
     w2f, _ = blk.conv2.shadows()
     b = ops.conv2d_fwd(m, w2f, 1)

@@ -305,6 +305,16 @@ int ecgmm_modality_share(const float* phi, float* share, long long S, int C, int
  *   ecgmm_gradcam      : act [N][P][C] bf16 (layer4 output, P = h*w pixels), g [N][C] fp32 (d logit / d pooled) ->
  *                        cam[n][p] = relu(scale * sum_c g[n][c] act[n][p][c]),  scale = 1/P for the average pool
  *                        (C % 8 == 0) */
+/* Forward convolution with the folded-BatchNorm epilogue of the serving path (eval mode only: scale / shift come from
+ * the running statistics, ecgmm_bn_eval_coeffs): replaces Conv2d -> BatchNorm2d [-> += identity] [-> ReLU] of a
+ * torchvision BasicBlock (resnet.py:59-104) by ONE kernel,
+ *     y[n][h][w][c] = act( conv(x, w)[n][h][w][c] * scale[c] + shift[c] + res[n][h][w][c] ),
+ * with no bf16 rounding between the convolution and the affine map.  res may be NULL; relu != 0 applies ReLU.
+ * Same shapes / kernels as ecgmm_conv2d_fwd; scale, shift [Cout] fp32 and res (layout of y) 16-byte aligned.
+ * EXPERIMENTAL until it has run on hardware: ecgmm.serve uses it only with ECGMM_SERVE_FUSED=1. */
+int ecgmm_conv2d_fwd_bn(const ecgmm_bf16* x, const ecgmm_bf16* w_fwd, ecgmm_bf16* y, const float* scale,
+                        const float* shift, const ecgmm_bf16* res, int relu, int N, int H, int W, int Cin, int Cout,
+                        int R, int S, int stride, int padH, int padW, void* stream);
 int ecgmm_softmax_rows(const float* logits, float* probs, int* argmax, long long rows, int C, void* stream);
 int ecgmm_gather_rows(const float* table, const int* idx, float* out, long long rows, int D, int NT, void* stream);
 int ecgmm_gradcam(const ecgmm_bf16* act, const float* g, float* cam, int N, int P, int C, float scale, void* stream);

@@ -216,3 +216,20 @@ def test_attribution_and_serving_flows(stub):
     assert stub.count("ecgmm_bn_eval_coeffs") == 20
     with pytest.raises(lib.EcgmmError):
         serve.ImageEndpoint(m, graph=False, class_index=5).gradcam(image)
+
+
+def test_fused_serving_flow(stub, monkeypatch):
+    """ECGMM_SERVE_FUSED=1: every Conv -> BatchNorm (-> += identity) (-> ReLU) of the 8 residual blocks is one
+    ecgmm_conv2d_fwd_bn call: 19 convolutions, no scale/shift pass."""
+    from ecgmm import serve
+
+    monkeypatch.setattr(serve, "FUSED_EPILOGUE", True)
+    m = ecgmm.ECGMultimodalModel(Cfg).eval()
+    image = (torch.rand(2, 3, 64, 160) * 255).to(torch.uint8)
+    ep = serve.ImageEndpoint(m, graph=False)
+    ep(image)
+    del stub[:]
+    probs, classes = ep(image)
+    assert probs.shape == (2, 2)
+    assert stub.count("ecgmm_conv2d_fwd_bn") == 19 and "ecgmm_bn_apply" not in stub and "ecgmm_conv2d_fwd" not in stub
+    assert len(stub) == 27  # s2d, stem conv, bn+relu+maxpool, 19 convs, avgpool, fc, LayerNorm, classifier, softmax

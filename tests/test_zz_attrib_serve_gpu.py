@@ -132,3 +132,70 @@ def test_image_endpoint_cuda_graph_replay():
     assert (pg - pe).abs().max().item() <= 1e-6
     with pytest.raises(lib.EcgmmError):
         ga(u8a[:1].to(DEV))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Fused folded-BatchNorm epilogue (ecgmm_conv2d_fwd_bn, ECGMM_SERVE_FUSED=1): touches the tcgen05 kernels' epilogues
+# (separate template instantiations; the training instantiations' SASS is unchanged) and is off by default, so its
+# tests run only with ECGMM_TEST_EXPERIMENTAL=1 until it has been on hardware once (tools/r02_first_call.sh).
+import os  # noqa: E402
+
+_experimental = pytest.mark.skipif(os.environ.get("ECGMM_TEST_EXPERIMENTAL") != "1",
+                                   reason="ecgmm_conv2d_fwd_bn is a round-2 work item: not yet validated on hardware")
+
+
+@_experimental
+@pytest.mark.parametrize("case", [
+    # N, H, W, Cin, Cout, R, stride, residual, relu          kernel
+    (2, 16, 160, 64, 64, 3, 1, True, True),      # halo kernel, residual through the TMA prefetch
+    (3, 5, 150, 64, 64, 3, 1, False, True),      # halo kernel, ragged width
+    (2, 16, 40, 64, 128, 3, 2, False, True),     # generic N=128, stride 2
+    (2, 16, 40, 64, 128, 1, 2, False, False),    # 1x1 projection, no activation
+    (2, 8, 20, 128, 128, 3, 1, True, True),      # generic N=128 with residual
+    (2, 4, 10, 256, 256, 3, 1, True, True),      # generic N=256
+    (1, 2, 5, 512, 512, 3, 1, True, False),      # two N tiles
+], ids=lambda c: "x".join(str(v) for v in c))
+def test_experimental_conv_bn_epilogue(case):
+    from ecgmm import ops
+
+    N, H, W, Cin, Cout, R, stride, with_res, relu = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, H, W, Cin, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, R, R, generator=g) * (2.0 / (Cin * R * R)) ** 0.5)
+    scale = torch.rand(Cout, generator=g) + 0.5
+    shift = torch.randn(Cout, generator=g) * 0.5
+    Ho, Wo = (H + 2 * (R // 2) - R) // stride + 1, (W + 2 * (R // 2) - R) // stride + 1
+    res = torch.randn(N, Ho, Wo, Cout, generator=g).to(torch.bfloat16) if with_res else None
+    w_fwd = w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)                  # [O][R][S][I]
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w_fwd.float().permute(0, 3, 1, 2), None, stride,
+                                     R // 2).permute(0, 2, 3, 1)
+    ref = ref * scale + shift
+    if with_res:
+        ref = ref + res.float()
+    if relu:
+        ref = torch.relu(ref)
+    st = ops.BNStats(None, None, scale.to(DEV), shift.to(DEV))
+    y = ops.conv2d_fwd_bn(x.to(DEV), w_fwd.to(DEV), st, stride, None if res is None else res.to(DEV), relu)
+    assert tuple(y.shape) == (N, Ho, Wo, Cout)
+    err = (y.float().cpu() - ref).abs()
+    assert float((err / (1.0 + ref.abs())).max()) <= 1e-2  # one bf16 rounding of the result
+
+
+@_experimental
+def test_experimental_fused_endpoint_matches_unfused(monkeypatch):
+    ora, dut = build_pair(seed=7)
+    dut.eval()
+    u8, _ = _images(3, 64, 160, seed=4)
+    plain = [t.clone() for t in serve.ImageEndpoint(dut, graph=False, class_index=1).gradcam(u8.to(DEV))]
+    n0 = lib.launch_count()
+    serve.ImageEndpoint(dut, graph=False, class_index=1).gradcam(u8.to(DEV))
+    n_plain = lib.launch_count() - n0
+    monkeypatch.setattr(serve, "FUSED_EPILOGUE", True)
+    ep = serve.ImageEndpoint(dut, graph=False, class_index=1)
+    fused = ep.gradcam(u8.to(DEV))
+    n0 = lib.launch_count()
+    ep.gradcam(u8.to(DEV))
+    assert lib.launch_count() - n0 < n_plain - 15  # no scale/shift passes (the first request also folds: 20 launches)
+    assert (fused[0] - plain[0]).abs().max().item() <= 2e-2
+    num, den = (fused[2] - plain[2]).norm().item(), plain[2].norm().item()
+    assert num / den <= 0.1

@@ -39,6 +39,13 @@ if grep -q " passed" $O/${TAG}_wgstream_test.log && ! grep -q " failed" $O/${TAG
   ECGMM_WGRAD_STREAM=1 run wgstream_b64  300 $B --global-batch 64 --detail
   ECGMM_WGRAD_STREAM=1 run wgstream_b512 300 $B --detail
 fi
+
+# --- experiment 3: folded-BatchNorm convolution epilogue of the serving path (ecgmm_conv2d_fwd_bn)
+run fusedbn_test  300 python -m pytest tests/test_zz_attrib_serve_gpu.py -x -q -m gpu -k "experimental"
+run serve_plain   300 python tools/serve_bench.py
+if grep -q " passed" $O/${TAG}_fusedbn_test.log && ! grep -q " failed" $O/${TAG}_fusedbn_test.log; then
+  ECGMM_SERVE_FUSED=1 run serve_fused 300 python tools/serve_bench.py
+fi
 unset ECGMM_TEST_EXPERIMENTAL
 
 # --- the other configs (BASELINE.json configs[1], [3], [4]) and the reference arm
