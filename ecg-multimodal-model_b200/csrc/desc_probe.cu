@@ -3,6 +3,11 @@
 // depend on the answer (a filter tap becomes a row offset into ONE staged input tile instead of
 // its own TMA load).  mode bit 0: 0 = K-major A (forward style), 1 = MN-major A (wgrad style);
 // mode bit 1: set the descriptor's base-offset field to (start_address >> 7) & 7.
+// mode bit 2 (round-2 question, DESIGN.md "known headroom" 3): may the 64-wide N atoms of an MN-major SWIZZLE_128B
+// operand OVERLAP, i.e. leading-dimension byte offset = 128 B = one pixel row?  Then ONE staged input-row box is the
+// B operand of an N = 192 MMA whose three atoms are the three horizontal filter taps (the same box read from pixel
+// s, s+1, s+2), which is what a transposed weight-gradient GEMM (M = Cout, N = taps x Cin) needs to leave the
+// shared-memory-bound M128 x N64 shape.  D[m][j*64 + c] = sum_{k<32} a[k][m] * a[k + shift + j][c]; out is [128][192].
 #include "common.h"
 #include "ptx.cuh"
 
@@ -35,7 +40,7 @@ __global__ void __launch_bounds__(128, 1) desc_probe_kernel(const __grid_constan
     mbar_fence_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 64);
+    tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -53,7 +58,12 @@ __global__ void __launch_bounds__(128, 1) desc_probe_kernel(const __grid_constan
     const uint32_t a_addr = smem_u32(sA) + p.shift * 128;
     uint64_t boff = 0;
     if (p.mode & 2) boff = static_cast<uint64_t>((a_addr >> 7) & 7) << 49;
-    if (!mn) {
+    if (p.mode & 4) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 192, 1, 1);
+      const uint64_t a_desc = make_sw128_desc(smem_u32(sA), kAtom, 1024);  // channels 0..63 | 64..127, rows 0..31
+      const uint64_t b_desc = make_sw128_desc(a_addr, 128, 1024) | boff;   // three atoms one 128-byte row apart
+      for (int k = 0; k < 2; ++k) umma_bf16(tmem, a_desc + k * 128, b_desc + k * 128, idesc, k != 0);
+    } else if (!mn) {
       // D[m][n] = sum_k A[m + shift][k] * B[n][k], m < 128 (rows of atom 0), K = 64
       constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
       const uint64_t a_desc = make_sw128_desc(a_addr, 0, 1024) | boff;
@@ -72,14 +82,15 @@ __global__ void __launch_bounds__(128, 1) desc_probe_kernel(const __grid_constan
   mbar_wait(done, 0);
   tc_fence_after();
   uint32_t r[32];
-  for (int c = 0; c < 2; ++c) {
+  const int ncols = (p.mode & 4) ? 192 : 64;
+  for (int c = 0; c < ncols / 32; ++c) {
     tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, r);
     tmem_ld_wait();
-    for (int j = 0; j < 32; ++j) p.out[(warp * 32 + lane) * 64 + c * 32 + j] = __uint_as_float(r[j]);
+    for (int j = 0; j < 32; ++j) p.out[(warp * 32 + lane) * ncols + c * 32 + j] = __uint_as_float(r[j]);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 64);
+  if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 }  // namespace ecgmm

@@ -41,7 +41,8 @@ unsigned long long ecgmm_launch_count(void);
 int ecgmm_check_device(void);
 
 /* Development probe (tools/desc_probe.py): one tcgen05.mma whose SWIZZLE_128B A descriptor starts
- * `shift` 128-byte rows into a TMA-written tile.  mode bit0: MN-major operands; bit1: set base-offset. */
+ * `shift` 128-byte rows into a TMA-written tile.  mode bit0: MN-major operands; bit1: set base-offset;
+ * bit2: N = 192 MN-major B operand whose three 64-wide atoms overlap at a 128-byte pitch (out is then [128][192]). */
 int ecgmm_debug_desc_probe(const ecgmm_bf16* a, const ecgmm_bf16* b, float* out, int shift, int mode, void* stream);
 
 /* ------------------------------------------------------------------ layout / precision */

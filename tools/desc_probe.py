@@ -30,3 +30,18 @@ for mn in (0, 1):
             oks.append(err < 1e-2 * ref.abs().max().item())
         print(f"layout={'MN' if mn else 'K '}-major base_offset={'set' if boff else '0  '}:",
               "".join("Y" if o else "." for o in oks), "(shift 0..16)")
+
+# mode bit 2: overlapping N atoms (leading-dimension offset = one 128-byte row) in an MN-major B operand, N = 192
+for boff in (0, 1):
+    oks = []
+    for shift in range(0, 17):
+        out = torch.full((128, 192), float("nan"), device="cuda")
+        lib.call("ecgmm_debug_desc_probe", ops._ptr(a), ops._ptr(a), ops._ptr(out), shift, 4 | 1 | (boff << 1),
+                 ops._s())
+        torch.cuda.synchronize()
+        af = a.float()
+        ref = torch.cat([af[0:32].t() @ af[shift + j:shift + j + 32, :64] for j in range(3)], dim=1)  # [128][192]
+        err = (out - ref).abs().max().item()
+        oks.append(err < 1e-2 * ref.abs().max().item())
+    print(f"MN-major B, N=192, atoms 128 B apart, base_offset={'set' if boff else '0  '}:",
+          "".join("Y" if o else "." for o in oks), "(shift 0..16)")

@@ -48,6 +48,9 @@ if grep -q " passed" $O/${TAG}_fusedbn_test.log && ! grep -q " failed" $O/${TAG}
 fi
 unset ECGMM_TEST_EXPERIMENTAL
 
+# --- hardware question behind the transposed weight-gradient plan (DESIGN.md known headroom 3)
+run desc_probe 120 python tools/desc_probe.py
+
 # --- the other configs (BASELINE.json configs[1], [3], [4]) and the reference arm
 run signal   300 python tools/signal_bench.py
 run perturb  300 python tools/perturb_bench.py
