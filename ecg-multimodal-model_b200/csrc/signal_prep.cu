@@ -19,6 +19,7 @@
 #include "common.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 #include <complex>
 
@@ -172,6 +173,256 @@ __global__ void __launch_bounds__(32) signal_preprocess_kernel(const TIn* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (ECGMM_PREP_BLOCK=1, off by default; written after the round's GPU budget was spent, NOT yet run on
+// hardware): the same preprocessing, parallel ALONG TIME.  One CTA of 256 threads per signal, the signal in shared
+// memory as float64; a filter pass over n samples is
+//   A. every thread runs the DF2T recurrence over its own block of T consecutive samples from a ZERO state and keeps
+//      the final state f_j (the recurrence is linear: end state = A^T * start state + f_j);
+//   B. the block start states follow from a scan of the affine maps s -> M s + f_j, M = A^T (all blocks share M, so
+//      the scan needs only the powers M^1..M^32): a Hillis-Steele scan inside each warp (5 steps with M^1, M^2, M^4,
+//      M^8, M^16), 8 serial steps across the warps with M^32, one matrix-vector product per thread;
+//   C. every thread reruns its block from its true start state and writes the outputs in place.
+// Twice the recurrence arithmetic of the serial kernel, spread over 256 threads instead of one.  The state matrix is
+// a companion matrix: for narrow-band / high-order designs its powers are badly conditioned and the block result
+// drifts away from the serial recurrence (wn = 0.02, order 5: 1e-2 relative, emulated in float64 on the host), so
+// the launcher selects this kernel only when max |A^k| stays below 1e3 (the reference's two designs, butter(5, 0.1)
+// and butter(5, 0.32): 216 and 2.2; difference to the serial recurrence 1e-9 relative) and keeps the serial kernel
+// for everything else.  tests/test_preprocess_cpu.py emulates exactly this schedule in numpy.
+constexpr int kBlkThreads = 256;
+
+struct BlockPrepParams {
+  IirCoef c;
+  double M[kMaxOrder * kMaxOrder];  // A^T, row-major ORDER x ORDER
+  int T;                            // samples per thread in a filter pass (odd: conflict-free 64-bit smem strides)
+  int chunk;                        // samples per thread in the baseline pass (odd)
+};
+
+__device__ __forceinline__ double block_sum_f64(double v, double* red /* >= 9 doubles */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < kBlkThreads / 32; ++i) t += red[i];
+    red[8] = t;
+  }
+  __syncthreads();
+  return red[8];
+}
+
+// y = Mat * v  (Mat row-major ORDER x ORDER in shared memory)
+template <int ORDER>
+__device__ __forceinline__ void matvec(const double* Mat, const double (&v)[kMaxOrder], double (&y)[kMaxOrder]) {
+#pragma unroll
+  for (int r = 0; r < ORDER; ++r) {
+    double a = 0.0;
+#pragma unroll
+    for (int q = 0; q < ORDER; ++q) a = fma(Mat[r * ORDER + q], v[q], a);
+    y[r] = a;
+  }
+}
+
+// One zero-phase half: filter buf[0..n) in place, forward (REVERSE = false) or from the end backwards.
+template <int ORDER, bool REVERSE>
+__device__ __forceinline__ void block_filter_pass(double* buf, int n, int T, const IirCoef& c, const double* P,
+                                                  double* Fw, double* wsS) {
+  constexpr int OO = ORDER * ORDER;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = (n + T - 1) / T;
+  auto at = [&](int m) { return REVERSE ? n - 1 - m : m; };
+  const int m0 = tid * T, len = tid < nb ? min(T, n - m0) : 0;
+  const double x_first = buf[at(0)];  // read before anybody writes (pass C comes after two barriers)
+  // ---- A: zero-state run
+  double z[kMaxOrder];
+#pragma unroll
+  for (int k = 0; k < kMaxOrder; ++k) z[k] = 0.0;
+  for (int k = 0; k < len; ++k) (void)iir_step<ORDER>(c, z, buf[at(m0 + k)]);
+  // ---- B1: inclusive scan of s -> M s + f inside the warp
+  double v[kMaxOrder], u[kMaxOrder], t[kMaxOrder];
+#pragma unroll
+  for (int k = 0; k < kMaxOrder; ++k) v[k] = k < ORDER ? z[k] : 0.0;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+    for (int k = 0; k < ORDER; ++k) u[k] = __shfl_up_sync(0xffffffffu, v[k], d);
+    matvec<ORDER>(P + d * OO, u, t);
+    if (lane >= d) {
+#pragma unroll
+      for (int k = 0; k < ORDER; ++k) v[k] += t[k];
+    }
+  }
+  double lp[kMaxOrder];  // state at the start of this block if the warp had started from zero
+#pragma unroll
+  for (int k = 0; k < ORDER; ++k) {
+    lp[k] = __shfl_up_sync(0xffffffffu, v[k], 1);
+    if (lane == 0) lp[k] = 0.0;
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int k = 0; k < ORDER; ++k) Fw[warp * ORDER + k] = v[k];
+  }
+  __syncthreads();
+  // ---- B2: across the warps (serial, 8 steps): start state of every warp
+  if (tid == 0) {
+    double s[kMaxOrder], sn[kMaxOrder];
+#pragma unroll
+    for (int k = 0; k < kMaxOrder; ++k) s[k] = k < ORDER ? c.zi[k] * x_first : 0.0;
+    for (int w = 0; w < kBlkThreads / 32; ++w) {
+#pragma unroll
+      for (int k = 0; k < ORDER; ++k) wsS[w * ORDER + k] = s[k];
+      matvec<ORDER>(P + 32 * OO, s, sn);
+#pragma unroll
+      for (int k = 0; k < ORDER; ++k) s[k] = sn[k] + Fw[w * ORDER + k];
+    }
+  }
+  __syncthreads();
+  // ---- B3 + C: true start state, rerun, write in place
+#pragma unroll
+  for (int k = 0; k < kMaxOrder; ++k) u[k] = k < ORDER ? wsS[warp * ORDER + k] : 0.0;
+  matvec<ORDER>(P + lane * OO, u, t);
+#pragma unroll
+  for (int k = 0; k < ORDER; ++k) z[k] = t[k] + lp[k];
+  for (int k = 0; k < len; ++k) {
+    const int i = at(m0 + k);
+    buf[i] = iir_step<ORDER>(c, z, buf[i]);
+  }
+  __syncthreads();
+}
+
+// dynamic shared memory (doubles): xs[L] (raw signal, only if window > 0) | buf[L + 2 edge] | P[33][ORDER^2] |
+// Fw[8][ORDER] | wsS[8][ORDER] | red[9]
+template <typename TIn, int ORDER>
+__global__ void __launch_bounds__(kBlkThreads) signal_preprocess_block_kernel(
+    const TIn* __restrict__ x, float* __restrict__ out, int L, int window, const __grid_constant__ BlockPrepParams prm,
+    int zscore, double eps) {
+  extern __shared__ double sm_d[];
+  constexpr int edge = ORDER > 0 ? 3 * (ORDER + 1) : 0;
+  constexpr int OO = ORDER * ORDER;
+  const int n = L + 2 * edge;
+  double* xs = sm_d;
+  double* buf = xs + (window > 0 ? L : 0);
+  double* P = buf + n;
+  double* Fw = P + 33 * OO;
+  double* wsS = Fw + 8 * (ORDER > 0 ? ORDER : 1);
+  double* red = wsS + 8 * (ORDER > 0 ? ORDER : 1);
+  const int tid = threadIdx.x;
+  const TIn* xr = x + (size_t)blockIdx.x * L;
+  float* outr = out + (size_t)blockIdx.x * L;
+  // ---- load (coalesced), float64 from here on
+  for (int i = tid; i < L; i += kBlkThreads) {
+    const double v = (double)xr[i];
+    if (window > 0)
+      xs[i] = v;
+    else
+      buf[edge + i] = v;
+  }
+  // powers of M = A^T: P[0] = I, P[k] = M P[k-1]  (one thread per matrix entry, 32 dependent steps)
+  if constexpr (ORDER > 0) {
+    if (tid < OO) P[tid] = (tid / ORDER == tid % ORDER) ? 1.0 : 0.0;
+    for (int k = 1; k <= 32; ++k) {
+      __syncthreads();
+      if (tid < OO) {
+        const int r = tid / ORDER, q = tid % ORDER;
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < ORDER; ++j) a = fma(prm.M[r * ORDER + j], P[(k - 1) * OO + j * ORDER + q], a);
+        P[k * OO + tid] = a;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- baseline removal: np.convolve(x, ones(W)/W, 'same')[i] = (1/W) sum x[i-lo .. i+hi], zeros outside
+  if (window > 0) {
+    const int lo = window / 2, hi = window - lo - 1;
+    const double inv = 1.0 / (double)window;
+    const int i0 = tid * prm.chunk, i1 = min(L, i0 + prm.chunk);
+    if (i0 < L) {
+      double S = 0.0;
+      for (int t = max(0, i0 - lo); t <= min(L - 1, i0 + hi); ++t) S += xs[t];
+      for (int i = i0; i < i1; ++i) {
+        buf[edge + i] = xs[i] - S * inv;
+        if (i + 1 + hi < L) S += xs[i + 1 + hi];
+        if (i - lo >= 0) S -= xs[i - lo];
+      }
+    }
+    __syncthreads();
+  }
+  if constexpr (ORDER > 0) {
+    // ---- odd extension by `edge` samples on both sides
+    if (tid >= 1 && tid <= edge) {
+      buf[edge - tid] = 2.0 * buf[edge] - buf[edge + tid];
+      buf[edge + L - 1 + tid] = 2.0 * buf[edge + L - 1] - buf[edge + L - 1 - tid];
+    }
+    __syncthreads();
+    block_filter_pass<ORDER, false>(buf, n, prm.T, prm.c, P, Fw, wsS);
+    block_filter_pass<ORDER, true>(buf, n, prm.T, prm.c, P, Fw, wsS);
+  }
+  // ---- output (float32), optionally z-scored: (y - mean) / (std_population + eps)
+  if (zscore) {
+    double s1 = 0.0;
+    for (int i = tid; i < L; i += kBlkThreads) s1 += buf[edge + i];
+    const double mean = block_sum_f64(s1, red) / (double)L;
+    double q = 0.0;
+    for (int i = tid; i < L; i += kBlkThreads) {
+      const double d = buf[edge + i] - mean;
+      q = fma(d, d, q);
+    }
+    const double inv = 1.0 / (sqrt(block_sum_f64(q, red) / (double)L) + eps);
+    for (int i = tid; i < L; i += kBlkThreads) outr[i] = (float)((buf[edge + i] - mean) * inv);
+  } else {
+    for (int i = tid; i < L; i += kBlkThreads) outr[i] = (float)buf[edge + i];
+  }
+}
+
+// Host side of the block kernel: M = A^T and the conditioning guard.  Returns false when the serial kernel has to run.
+static bool block_plan(int order, const IirCoef& c, int L, int window, BlockPrepParams* prm, size_t* smem_bytes) {
+  const int edge = order > 0 ? 3 * (order + 1) : 0;
+  const int n = L + 2 * edge;
+  int T = (n + kBlkThreads - 1) / kBlkThreads;
+  T |= 1;
+  int chunk = (L + kBlkThreads - 1) / kBlkThreads;
+  chunk |= 1;
+  prm->c = c;
+  prm->T = T;
+  prm->chunk = chunk;
+  for (int i = 0; i < kMaxOrder * kMaxOrder; ++i) prm->M[i] = 0.0;
+  const int oo = order > 0 ? order : 1;
+  *smem_bytes = sizeof(double) * ((size_t)(window > 0 ? L : 0) + n + 33 * (size_t)order * order + 16 * (size_t)oo + 9);
+  if (*smem_bytes > 200 * 1024) return false;
+  if (order == 0) return true;
+  // companion (DF2T) state matrix: z' = A z + B x with A[k][0] = -a[k+1], A[k][k+1] = 1
+  long double A[kMaxOrder][kMaxOrder] = {}, Pw[kMaxOrder][kMaxOrder] = {}, Nx[kMaxOrder][kMaxOrder];
+  for (int k = 0; k < order; ++k) {
+    A[k][0] = -(long double)c.a[k + 1];
+    if (k + 1 < order) A[k][k + 1] = 1.0L;
+    Pw[k][k] = 1.0L;
+  }
+  long double worst = 0.0L;
+  for (int t = 1; t <= 32 * T; ++t) {  // every power that the scan multiplies with lies on this path
+    for (int r = 0; r < order; ++r)
+      for (int q = 0; q < order; ++q) {
+        long double a = 0.0L;
+        for (int j = 0; j < order; ++j) a += A[r][j] * Pw[j][q];
+        Nx[r][q] = a;
+      }
+    for (int r = 0; r < order; ++r)
+      for (int q = 0; q < order; ++q) {
+        Pw[r][q] = Nx[r][q];
+        const long double m = Nx[r][q] < 0 ? -Nx[r][q] : Nx[r][q];
+        if (m > worst) worst = m;
+      }
+    if (t == T)
+      for (int r = 0; r < order; ++r)
+        for (int q = 0; q < order; ++q) prm->M[r * order + q] = (double)Pw[r][q];
+    if (!(worst < 1e3L)) return false;  // badly conditioned design (or unstable): serial kernel
+  }
+  return true;
+}
+
 // scipy.signal.butter(order, wn, 'low') + lfilter_zi, restated (see oracle/preprocess.py for the numpy form).
 static int design_butter_lowpass(int order, double wn, double* b, double* a, double* zi) {
   typedef std::complex<double> cd;
@@ -268,10 +519,45 @@ extern "C" int ecgmm_signal_preprocess(const void* x, int x_is_f64, float* y, vo
     ECGMM_CHECK(wn > 0.0 && wn < 1.0, ECGMM_ERR_ARG, "signal_preprocess: normalised cutoff %g must be in (0, 1)", wn);
     design_butter_lowpass(order, wn, c.b, c.a, c.zi);
   }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (getenv("ECGMM_PREP_BLOCK") && rows <= 0x7fffffffLL) {  // experimental time-parallel kernel (see above)
+    BlockPrepParams prm;
+    size_t smem = 0;
+    if (block_plan(order, c, L, window, &prm, &smem)) {
+#define ECGMM_BLK(T_, O_)                                                                                            \
+  do {                                                                                                               \
+    ECGMM_CUDA(cudaFuncSetAttribute(signal_preprocess_block_kernel<T_, O_>,                                          \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                      \
+    signal_preprocess_block_kernel<T_, O_><<<(unsigned)rows, kBlkThreads, smem, st>>>(                               \
+        reinterpret_cast<const T_*>(x), y, L, window, prm, zscore, eps);                                            \
+  } while (0)
+#define ECGMM_BLK_ORDER(O_)    \
+  case O_:                     \
+    if (x_is_f64)              \
+      ECGMM_BLK(double, O_);   \
+    else                       \
+      ECGMM_BLK(float, O_);    \
+    break
+      switch (order) {
+        ECGMM_BLK_ORDER(0);
+        ECGMM_BLK_ORDER(1);
+        ECGMM_BLK_ORDER(2);
+        ECGMM_BLK_ORDER(3);
+        ECGMM_BLK_ORDER(4);
+        ECGMM_BLK_ORDER(5);
+        ECGMM_BLK_ORDER(6);
+        ECGMM_BLK_ORDER(7);
+        default:
+          ECGMM_BLK_ORDER(8);
+      }
+#undef ECGMM_BLK_ORDER
+#undef ECGMM_BLK
+      return check_launch("signal_preprocess_block_kernel");
+    }
+  }
   const long long ld = (rows + 31) / 32 * 32;
   const unsigned grid = (unsigned)(ld / 32);
   double* ws = reinterpret_cast<double*>(workspace);
-  cudaStream_t st = (cudaStream_t)stream;
 #define ECGMM_PREP(T_, O_)                                                                                          \
   signal_preprocess_kernel<T_, O_><<<grid, 32, 0, st>>>(reinterpret_cast<const T_*>(x), y, ws, rows, ld, L, window, c, \
                                                          zscore, eps)

@@ -85,3 +85,37 @@ def test_shape_errors():
         pp.lowpass_filter(torch.zeros(2, 18, device="cuda"))  # filtfilt needs len(x) > padlen = 18
     with pytest.raises(lib.EcgmmError):
         pp.preprocess_signal(torch.zeros(2, 300, device="cuda", dtype=torch.float16))
+
+
+@pytest.mark.skipif(os.environ.get("ECGMM_TEST_EXPERIMENTAL") != "1",
+                    reason="signal_preprocess_block_kernel is a round-2 work item: not yet validated on hardware")
+def test_experimental_block_parallel_kernel(golden, monkeypatch):
+    """ECGMM_PREP_BLOCK=1: the time-parallel kernel (one CTA per signal, block-wise zero-state runs + a scan of the
+    block start states) against the same golden vectors and oracle, and against the serial kernel."""
+    from ecgmm import preprocess as pp
+
+    serial = {c: pp.preprocess_signal(torch.from_numpy(golden[f"{c}_x"]).cuda()) for c in ("l2476", "l5000")}
+    monkeypatch.setenv("ECGMM_PREP_BLOCK", "1")
+    for case in ("l2476", "l5000", "l200", "l333"):
+        x = torch.from_numpy(golden[f"{case}_x"]).cuda()
+        assert close(pp.preprocess_signal(x), golden[f"{case}_y"]), case
+        assert close(pp.preprocess_signal(x.double()), golden[f"{case}_y"]), case
+    for c, y in serial.items():
+        assert close(pp.preprocess_signal(torch.from_numpy(golden[f"{c}_x"]).cuda()), y.cpu().numpy())
+    x = torch.from_numpy(golden["steps_x"]).cuda()
+    assert close(pp.remove_baseline_drift(x), golden["steps_baseline"])
+    assert close(pp.lowpass_filter(x), golden["steps_lowpass"])
+    assert close(pp.lowpass_filter(x, cutoff=40, fs=250, order=5), golden["steps_lowpass_40_250"])
+    assert close(pp.z_score_normalize(x), golden["steps_zscore"])
+    for shape in [(256, 12, 1000), (70, 2476), (1, 19 + 200), (33, 1, 512)]:
+        g = torch.Generator().manual_seed(sum(shape))
+        xx = (torch.randn(*shape, generator=g).cumsum(-1) * 0.05 + torch.randn(*shape, generator=g)).float()
+        y = pp.preprocess_signal(xx.cuda(), zscore=True)
+        flat = xx.reshape(-1, shape[-1]).numpy()
+        pick = sorted({0, flat.shape[0] // 2, flat.shape[0] - 1})
+        want = np.stack([op.preprocess_signal(flat[i], zscore=True) for i in pick])
+        assert close(y.reshape(-1, shape[-1])[pick], want), shape
+    # a badly conditioned design (narrow band) must fall back to the serial kernel: same numbers as without the switch
+    y_blk = pp.lowpass_filter(x, cutoff=0.005, fs=1.0, order=5)
+    monkeypatch.delenv("ECGMM_PREP_BLOCK")
+    assert torch.equal(y_blk, pp.lowpass_filter(x, cutoff=0.005, fs=1.0, order=5))

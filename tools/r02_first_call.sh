@@ -46,6 +46,12 @@ run serve_plain   300 python tools/serve_bench.py
 if grep -q " passed" $O/${TAG}_fusedbn_test.log && ! grep -q " failed" $O/${TAG}_fusedbn_test.log; then
   ECGMM_SERVE_FUSED=1 run serve_fused 300 python tools/serve_bench.py
 fi
+
+# --- experiment 4: time-parallel signal preprocessing (signal_preprocess_block_kernel)
+run prepblk_test  300 python -m pytest tests/test_preprocess_gpu.py -x -q -m gpu -k "block_parallel"
+if grep -q " passed" $O/${TAG}_prepblk_test.log && ! grep -q " failed" $O/${TAG}_prepblk_test.log; then
+  ECGMM_PREP_BLOCK=1 run signal_blk 300 python tools/signal_bench.py
+fi
 unset ECGMM_TEST_EXPERIMENTAL
 
 # --- hardware question behind the transposed weight-gradient plan (DESIGN.md known headroom 3)
