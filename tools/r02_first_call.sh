@@ -63,4 +63,9 @@ run perturb  300 python tools/perturb_bench.py
 run zz_tests 600 python -m pytest tests/test_zz_modality_shapley_gpu.py tests/test_zz_attrib_serve_gpu.py -q -m gpu
 run kfold    600 python tools/kfold_bench.py
 run ref_arm  300 python bench.py --impl reference --steps 2 --warmup 1
+
+# --- ncu launch list of the bench command itself (per-launch times are cold-cache and serialised: only each kernel's
+# SHARE of the step is comparable with the CUDA-event numbers of the plain run above)
+run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -c 6000 \
+    --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --launch eager
 cat $O/${TAG}_index.log
