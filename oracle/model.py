@@ -306,7 +306,9 @@ def expected_gradients(fusion_classifier, e, background, idx, alpha):
     with an explicit sampling plan instead of the package's internal RNG: for sample s and draw k, a background row
     idx[s, k] and an interpolation weight alpha[s, k] in [0, 1):
         phi[s, d, c] = mean_k (e[s, d] - bg[idx[s,k], d]) * d logit_c / d x_d (bg[idx] + alpha (e[s] - bg[idx]))
-    e [S, D], background [NB, D], idx [S, K] integer, alpha [S, K].  Eval mode (dropout = identity)."""
+    e [S, D], background [NB, D], idx [S, K] integer, alpha [S, K].  Eval mode (dropout = identity).
+    PARITY UNPINNED against `shap` itself (absent, unpinned by the reference): pinned only through fusion_classifier
+    (bit-identical to the reference module) and the estimator's own properties (tests/test_oracle_cpu.py)."""
     was_training = fusion_classifier.training
     fusion_classifier.eval()
     S, D = e.shape
@@ -340,7 +342,8 @@ def image_endpoint(model, image, class_index=None):
     (image_encoder -> image_norm -> image_classifier), softmax, and the Grad-CAM map of the last ResNet stage:
         cam[n, y, x] = relu( sum_k alpha[n, k] A[n, k, y, x] ),  alpha[n, k] = mean_{y,x} d logit_c / d A[n, k, y, x]
     with A = layer4's output and c = class_index (None: each sample's argmax).  Returns (probs [N, C], cam [N, h, w],
-    classes [N])."""
+    classes [N]).  The forward chain is the reference's (bit-identical modules); the Grad-CAM generator is not in the
+    reference repository (only its output images, gpt/*.png): that half is the published definition, PARITY UNPINNED."""
     was_training = model.training
     model.eval()
     enc = model.image_encoder
