@@ -147,6 +147,18 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
+    if not os.path.exists(os.path.join(ROOT, "ecg-multimodal-model_b200", "libecgmm.so")):
+        # (git-ignored artefact) build once; under torchrun only local rank 0 builds, the others wait for the file
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            import __graft_entry__ as g
+
+            g.build()
+        else:
+            for _ in range(600):
+                if os.path.exists(os.path.join(ROOT, "ecg-multimodal-model_b200", "libecgmm.so")):
+                    break
+                time.sleep(1.0)
+            time.sleep(2.0)
     import ecgmm
     from ecgmm import lib, ops
     from ecgmm import nn as enn
