@@ -152,3 +152,68 @@ class GraphedTrainStep:
     def inputs(self):
         """The graph's own input buffers: fill them directly (e.g. from a copy stream) and call step(*step.inputs)."""
         return self.static
+
+
+class GraphedEvalStep:
+    """The INFERENCE step of the fusion model (train.py:183-200, train_kfold.py:80-90: model.eval(), torch.no_grad(),
+    outputs = model(images, ecg_signals, clinical)) as one CUDA graph for a fixed batch shape.
+
+        model.eval()
+        infer = ecgmm.graph.GraphedEvalStep(model, (images, ecg, clinical))       # once
+        outputs = infer(images, ecg, clinical)        # the reference's 6-tuple (or fusion logits for fusion_only)
+
+    Eval mode has no per-step state (frozen BatchNorm statistics, no dropout), so nothing has to move to device
+    memory; the graph is re-captured when a parameter or buffer of the module has changed since (a training epoch in
+    between).  The returned tensors are the graph's output buffers: they are overwritten by the next call."""
+
+    def __init__(self, net, example_inputs):
+        inputs = list(example_inputs)
+        if not inputs or not all(isinstance(t, torch.Tensor) and t.is_cuda for t in inputs):
+            raise lib.EcgmmError("example_inputs must be CUDA tensors")
+        self.net = net
+        self.static = [t.detach().clone() for t in inputs]
+        self.graph, self.outputs, self._versions = None, None, None
+
+    def _module(self):
+        return self.net.module if hasattr(self.net, "module") and isinstance(self.net.module, torch.nn.Module) else self.net
+
+    def _state(self):
+        m = self._module()
+        return tuple((t.data_ptr(), t._version) for t in list(m.parameters()) + list(m.buffers()))
+
+    def _capture(self):
+        if self._module().training:
+            raise lib.EcgmmError("GraphedEvalStep captures eval-mode statistics: call model.eval() first")
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():  # warm-up: allocator, weight shadows, kernel attributes
+            self.net(*self.static)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.outputs = self.net(*self.static)
+        self._versions = self._state()
+
+    def __call__(self, *inputs):
+        if len(inputs) == 1 and isinstance(inputs[0], (tuple, list)):
+            inputs = tuple(inputs[0])
+        if len(inputs) != len(self.static):
+            raise lib.EcgmmError(f"expected {len(self.static)} tensors, got {len(inputs)}")
+        if self.graph is None or self._versions != self._state():
+            self._capture()
+        for dst, src in zip(self.static, inputs):
+            if src is dst:
+                continue
+            if src.shape != dst.shape or src.dtype != dst.dtype:
+                raise lib.EcgmmError(f"input {tuple(src.shape)} {src.dtype} does not match the captured "
+                                     f"{tuple(dst.shape)} {dst.dtype}")
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.outputs
+
+    @property
+    def inputs(self):
+        """The graph's own input buffers: fill them directly and call infer(*infer.inputs)."""
+        return self.static

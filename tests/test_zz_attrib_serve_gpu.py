@@ -199,3 +199,40 @@ def test_experimental_fused_endpoint_matches_unfused(monkeypatch):
     assert (fused[0] - plain[0]).abs().max().item() <= 2e-2
     num, den = (fused[2] - plain[2]).norm().item(), plain[2].norm().item()
     assert num / den <= 0.1
+
+
+def test_graphed_eval_step_matches_eager_forward():
+    """The inference step of the fusion model (train.py:183-200) as one CUDA graph: same outputs as the eager eval
+    forward, for new batch contents too; re-captured after the weights change; refuses train mode."""
+    from ecgmm import graph as eg
+
+    ora, dut = build_pair(seed=7)
+    dut.eval()
+    g = torch.Generator().manual_seed(3)
+
+    def batch():
+        return (torch.randn(4, 3, 64, 160, generator=g).clamp_(-1, 1).to(DEV), torch.randn(4, 600, generator=g).to(DEV),
+                torch.randn(4, 24, generator=g).to(DEV))
+
+    b1, b2 = batch(), batch()
+    infer = eg.GraphedEvalStep(dut, b1)
+    for b in (b1, b2, b1):
+        with torch.no_grad():
+            want = [t.clone() for t in dut(*b)]
+        got = infer(*b)
+        torch.cuda.synchronize()
+        assert len(got) == 6
+        for a, w in zip(got, want):
+            assert (a - w).abs().max().item() <= 1e-6
+    n0 = lib.launch_count()
+    infer(*b2)
+    assert lib.launch_count() == n0
+    with torch.no_grad():
+        dut.fusion_classifier.lin2.bias.add_(1.0)
+        want = dut(*b2)[3].clone()
+    assert (infer(*b2)[3] - want).abs().max().item() <= 1e-6
+    dut.train()
+    with torch.no_grad():
+        dut.fusion_classifier.lin2.bias.add_(1.0)  # forces a re-capture, which must refuse the mode
+    with pytest.raises(lib.EcgmmError):
+        infer(*b2)
