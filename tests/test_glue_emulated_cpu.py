@@ -80,7 +80,8 @@ EMULATORS = {"ecgmm_sgemm": emu_sgemm, "ecgmm_eg_points": emu_eg_points, "ecgmm_
 def emulated(monkeypatch):
     def call(name, *args):
         assert len(args) == len(lib.SIGNATURES[name]), name
-        EMULATORS[name](*args)
+        with torch.no_grad():
+            EMULATORS[name](*args)
 
     monkeypatch.setattr(lib, "call", call)
     monkeypatch.setattr(ops, "_ptr", lambda t: t)  # the emulators take the tensors themselves
@@ -131,3 +132,80 @@ def test_gradcam_tail_glue(emulated):
     rstd = (f.var(1, unbiased=False) + dut.image_norm.eps).rsqrt()
     cam = serve.gradcam_from_features(dut, act, f.contiguous(), mean, rstd, classes)
     assert cam.shape == (3, 2, 5) and torch.allclose(cam, want, atol=1e-6 + 1e-4 * float(want.max()))
+
+
+# ---------------------------------------------------------------------------------------------- serving: block wiring
+def emu_conv_weight_prep(w, w_fwd, w_dg, O, I, R, S, stream):
+    w4 = w.reshape(O, I, R, S)
+    if w_fwd is not None:
+        w_fwd.copy_(w4.permute(0, 2, 3, 1).to(torch.bfloat16))
+    if w_dg is not None:
+        w_dg.copy_(w4.permute(1, 2, 3, 0).to(torch.bfloat16))
+
+
+def _conv(x, w_fwd, stride, pH, pW):
+    return torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w_fwd.float().permute(0, 3, 1, 2), None, stride,
+                                      (pH, pW)).permute(0, 2, 3, 1)
+
+
+def emu_conv2d_fwd(x, w, y, N, H, W, Cin, Cout, R, S, stride, pH, pW, stream):
+    y.copy_(_conv(x, w, stride, pH, pW).to(torch.bfloat16))
+
+
+def emu_conv2d_fwd_bn(x, w, y, scale, shift, res, relu, N, H, W, Cin, Cout, R, S, stride, pH, pW, stream):
+    r = _conv(x, w, stride, pH, pW) * scale + shift
+    if res is not None:
+        r = r + res.float()
+    y.copy_((torch.relu(r) if relu else r).to(torch.bfloat16))
+
+
+def emu_bn_eval_coeffs(C, gamma, beta, conv_bias, mean, var, eps, scale, shift, stream):
+    s = gamma / torch.sqrt(var + eps)
+    scale.copy_(s)
+    shift.copy_(beta - mean * s + (0 if conv_bias is None else conv_bias * s))
+
+
+def emu_bn_apply(x, scale, shift, se, res, y, mask, N, P, C, relu, stream):
+    assert se is None and mask is None
+    r = x.float() * scale + shift
+    if res is not None:
+        r = r + res.float()
+    y.copy_((torch.relu(r) if relu else r).to(torch.bfloat16))
+
+
+BLOCK_EMULATORS = {"ecgmm_conv_weight_prep": emu_conv_weight_prep, "ecgmm_conv2d_fwd": emu_conv2d_fwd,
+                   "ecgmm_conv2d_fwd_bn": emu_conv2d_fwd_bn, "ecgmm_bn_eval_coeffs": emu_bn_eval_coeffs,
+                   "ecgmm_bn_apply": emu_bn_apply}
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("layer,block", [("layer1", 1), ("layer2", 0), ("layer4", 0)])
+def test_serving_block_wiring(emulated, monkeypatch, fused, layer, block):
+    """serve._block_eval (folded BatchNorm, identity or 1x1 projection, optional fused epilogue) against the oracle's
+    torchvision BasicBlock in eval mode with non-trivial running statistics."""
+    for k, v in BLOCK_EMULATORS.items():
+        monkeypatch.setitem(EMULATORS, k, v)
+    monkeypatch.setattr(serve, "FUSED_EPILOGUE", fused)
+    ora = make_oracle(seed=7)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for m in ora.image_encoder.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.weight.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+    dut = ecgmm.ECGMultimodalModel(Cfg)
+    dut.load_state_dict(ora.state_dict())
+    ora.eval()
+    dut.eval()
+    oblk, dblk = getattr(ora.image_encoder, layer)[block], getattr(dut.image_encoder, layer)[block]
+    cin = oblk.conv1.in_channels
+    x = torch.randn(2, 9, 14, cin, generator=g).to(torch.bfloat16)
+    co = serve.fold_batchnorm(dut)
+    out = serve._block_eval(dblk, x, co)
+    with torch.no_grad():
+        ref = oblk(x.float().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape and out.dtype == torch.bfloat16
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 3e-2 * max(1.0, ref.abs().max().item()), err  # bf16 storage of the intermediate activations
