@@ -55,10 +55,24 @@ struct alignas(64) WgHaloParams {
   // CTA types: blocks [0, nA) are type A (groupsA x ksA), the rest type B (groupsB x ksB); typed == 0: type A only
   int typed, nA, ksA, ksB, cin_pairs, slotsA;
   long long wsB_off;  // float offset of the type-B slices in the workspace
+  int tmode;          // wgrad_halo_kernel<128, true> (transposed GEMM, see there)
 };
 
-template <int BN>
+// T = true (EXPERIMENTAL, ECGMM_WG_T=1, 3x3 layers with Cout % 128 == 0; written after the round's GPU budget was spent,
+// NOT yet run on hardware): the TRANSPOSED GEMM
+//     dW^T[cout][(r; s, cin)] = sum_pixels dY[pixel][cout] * X[pixel + (r, s)][cin]
+// M = 128 output channels (dY is the A operand: two 64-wide atoms, as it is staged for BN = 128), N = 192 = the three
+// HORIZONTAL taps of filter row r x a 64-wide Cin slice, all read from ONE staged input-row box as three MN-major atoms
+// 128 B (one pixel) apart -- the overlapping-atom addressing this kernel already uses for its M atoms.  Why: an
+// M128 x N64 MMA reads 6 KB of operands per 32 tensor clocks (192 B/clk against the 128 B/clk the shared memory
+// delivers: capped at 0.67, where the N = 64 kernel is measured, profiles/r01_mma_shape_model.txt); M128 x N192 reads
+// 10 KB per 96 clocks (107 B/clk).  An accumulator is 192 TMEM columns, two fit: type A CTAs hold filter rows 0 and 1
+// of one Cin slice, type B CTAs hold filter row 2 of a PAIR of Cin slices -- equal MMA work per pixel block, so both
+// types get the same split-K count.  Workspace slices are [slot][192 columns][128 rows].
+template <int BN, bool T = false>
 __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
+  static_assert(!T || BN == 128, "the transposed kernel stages dY as two 64-channel atoms");
+  constexpr int NCOL = T ? 192 : BN;  // TMEM / workspace columns of one accumulator
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -100,20 +114,21 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
   const int gdiv = typeB ? p.cin_pairs : p.cin_chunks;
   const int cc = typeB ? 2 * (g % gdiv) : (g % gdiv);  // first (or only) 64-channel Cin slice
   const int nt = g / gdiv;                             // BN-channel Cout slice
-  const int n_slots = typeB ? 1 : p.slotsA;
+  const int n_slots = T ? 2 : (typeB ? 1 : p.slotsA);
   const bool pair_ok = typeB && (cc + 1 < p.cin_chunks);  // odd slice count: the last type-B CTA has one slice
   const int per = (p.total_kblocks + ksplit - 1) / ksplit;
   const int kb0 = ks * per;
   const int kb1 = min(p.total_kblocks, kb0 + per);
   const bool has_work = kb0 < kb1;
-  // this CTA's workspace slice: [n_slots][BN][128]
+  // this CTA's workspace slice: [n_slots][NCOL][128]
   float* ws_cta = nullptr;
   if (p.ws)
-    ws_cta = typeB ? p.ws + p.wsB_off + (size_t)(g * ksplit + ks) * (BN * 128)
-                   : p.ws + (size_t)(g * ksplit + ks) * p.slotsA * (BN * 128);
+    ws_cta = typeB ? p.ws + p.wsB_off + (size_t)(g * ksplit + ks) * ((T ? 2 : 1) * NCOL * 128)
+                   : p.ws + (size_t)(g * ksplit + ks) * p.slotsA * (NCOL * 128);
   const int n_dy = p.rps * NB;
   const int x_base = n_dy * p.dy_box_stride;
-  const int n_xrows = typeB ? p.rps : p.rps + p.R - 1;  // input rows staged per Cin slice
+  // input rows staged per Cin slice (transposed type A: filter rows 0 and 1 only)
+  const int n_xrows = typeB ? p.rps : (T ? p.rps + 1 : p.rps + p.R - 1);
 
   if (has_work) {
     if (warp == 0) {
@@ -158,6 +173,40 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
       }
     } else if (warp == 1) {
       if (elect_one()) {
+        if constexpr (T) {
+          constexpr uint32_t idesc_t = make_idesc_bf16(128, 192, 1, 1);
+          const uint32_t s_addr = smem_u32(smem);
+          // A = dY: 128 output channels = the two 64-wide atoms of a stage row, one dy box apart
+          const uint64_t dy_rel = make_sw128_desc(s_addr, p.dy_box_stride, 1024);
+          // B = one staged input row: taps s = 0, 1, 2 are three atoms one pixel (128 B) apart.  Slot i is filter row
+          // i (type A) or filter row R-1 of Cin slice i (type B: the slices' row sets lie n_xrows boxes apart)
+          uint64_t x_rel[2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            x_rel[i] = make_sw128_desc(s_addr + x_base + i * (typeB ? n_xrows : 1) * p.x_box_stride, 128, 1024);
+          int stage = 0;
+          uint32_t phase = 0;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t so = (uint64_t)((stage * p.stage_bytes) >> 4);
+            for (int j = 0; j < p.rps; ++j) {
+              const uint64_t ao = so + (uint64_t)((j * NB * p.dy_box_stride) >> 4);
+              const uint64_t bo = so + (uint64_t)((j * p.x_box_stride) >> 4);
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+                for (int k = 0; k < p.kmma; ++k)
+                  umma_bf16(tmem_base + i * 192, dy_rel + ao + k * 128, x_rel[i] + bo + k * 128, idesc_t,
+                            (kb > kb0) || (j > 0) || (k > 0));
+            }
+            umma_commit(&empty[stage]);
+            if (kb == kb1 - 1) umma_commit(tfull);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        } else {
         constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
         const uint32_t s_addr = smem_u32(smem);
         // per-accumulator A descriptors relative to the stage base (output row 0 of the stage), built once
@@ -203,6 +252,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
             phase ^= 1;
           }
         }
+        }  // !T
       }
     } else {
       const int quad = warp & 3;
@@ -210,12 +260,12 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
       mbar_wait(tfull, 0);
       tc_fence_after();
       for (int i = 0; i < n_slots; ++i) {
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + i * BN;
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + i * NCOL;
         if (ws_cta) {
           // split-K partial, column-major so that the 32 lanes (= rows) of a warp store 128 contiguous bytes
-          float* dst0 = ws_cta + (size_t)i * (BN * 128) + m_row;
+          float* dst0 = ws_cta + (size_t)i * (NCOL * 128) + m_row;
 #pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
+          for (int c = 0; c < NCOL / 32; ++c) {
             uint32_t r[32];
             tmem_ld_32x32(t_addr + c * 32, r);
             tmem_ld_wait();
@@ -246,8 +296,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
     // a CTA without pixels still owns a workspace slice: the reduction kernel reads every slice
     const int m_row = (warp & 3) * 32 + lane;
     for (int i = 0; i < n_slots; ++i) {
-      float* dst0 = ws_cta + (size_t)i * (BN * 128) + m_row;
-      for (int c = 0; c < BN; ++c) dst0[c * 128] = 0.f;
+      float* dst0 = ws_cta + (size_t)i * (NCOL * 128) + m_row;
+      for (int c = 0; c < NCOL; ++c) dst0[c * 128] = 0.f;
     }
   }
 
@@ -264,7 +314,48 @@ struct WgReduceParams {
   int BN, RS, Cin, cin_chunks, cin_pairs;
   int slotsA, ksA, ksB;
   long long totalA, totalB, wsB_off;
+  int ncol, slotsB, tmode, S;  // columns per accumulator (BN, or 192 transposed), type-B accumulators, transposed layout
 };
+
+// Which dw element a workspace element (type, group g, accumulator slot, column c, row m) belongs to.
+//   original : row m = (tap parity, cin), column c = cout;  type A slot = tap pair, type B = last tap of a Cin-slice pair
+//   transposed: row m = cout, column c = (s, cin);          type A slot = filter row r, type B slot = Cin slice (r = R-1)
+__device__ __forceinline__ bool wg_decode(const WgReduceParams& p, bool typeB, int g, int slot, int c, int m,
+                                          int* tap, int* cin, int* cout) {
+  if (p.tmode) {
+    const int s = c >> 6;
+    int chunk, nt, r;
+    if (typeB) {
+      r = p.RS / p.S - 1;
+      chunk = 2 * (g % p.cin_pairs) + slot;
+      nt = g / p.cin_pairs;
+      if (chunk >= p.cin_chunks) return false;
+    } else {
+      r = slot;
+      chunk = g % p.cin_chunks;
+      nt = g / p.cin_chunks;
+    }
+    *tap = r * p.S + s;
+    *cin = chunk * 64 + (c & 63);
+    *cout = nt * p.BN + m;
+    return true;
+  }
+  int chunk, nt;
+  if (typeB) {
+    *tap = p.RS - 1;
+    chunk = 2 * (g % p.cin_pairs) + (m >> 6);
+    nt = g / p.cin_pairs;
+    if (chunk >= p.cin_chunks) return false;
+  } else {
+    *tap = 2 * slot + (m >> 6);
+    chunk = g % p.cin_chunks;
+    nt = g / p.cin_chunks;
+    if (*tap >= p.RS) return false;
+  }
+  *cin = chunk * 64 + (m & 63);
+  *cout = nt * p.BN + c;
+  return true;
+}
 
 // A CTA folds 64 consecutive result elements; its 256 threads are 64 elements x 4 interleaved k-groups (k = kg, kg+4,
 // ...), each with 4 independent accumulators: 16 partial loads in flight per element instead of 4 (the fold of the
@@ -278,30 +369,19 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const WgReducePa
   const bool in_range = !typeB || idx < p.totalB;
   const int m = (int)(idx & 127);
   const long long rest = idx >> 7;
-  const int c = (int)(rest % p.BN);
-  const long long gs = rest / p.BN;
-  const int n_slots = typeB ? 1 : p.slotsA;
+  const int c = (int)(rest % p.ncol);
+  const long long gs = rest / p.ncol;
+  const int n_slots = typeB ? p.slotsB : p.slotsA;
   const int slot = (int)(gs % n_slots);
   const int g = (int)(gs / n_slots);
   const int ksplit = typeB ? p.ksB : p.ksA;
-  int tap, chunk, nt;
-  bool live = in_range;
-  if (typeB) {
-    tap = p.RS - 1;
-    chunk = 2 * (g % p.cin_pairs) + (m >> 6);
-    nt = g / p.cin_pairs;
-    live = live && chunk < p.cin_chunks;
-  } else {
-    tap = 2 * slot + (m >> 6);
-    chunk = g % p.cin_chunks;
-    nt = g / p.cin_chunks;
-    live = live && tap < p.RS;
-  }
+  int tap = 0, cin = 0, cout = 0;
+  const bool live = in_range && wg_decode(p, typeB, g, slot, c, m, &tap, &cin, &cout);
   float acc = 0.f;
   if (live) {
-    const size_t slice = (size_t)n_slots * p.BN * 128;  // one CTA of the producer kernel
+    const size_t slice = (size_t)n_slots * p.ncol * 128;  // one CTA of the producer kernel
     const float* src =
-        p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + ((size_t)slot * p.BN + c) * 128 + m;
+        p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + ((size_t)slot * p.ncol + c) * 128 + m;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int k = kg;
     for (; k + 12 < ksplit; k += 16) {
@@ -317,7 +397,6 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const WgReducePa
   __syncthreads();
   if (kg == 0 && live) {
     const float total = (red[0][o] + red[1][o]) + (red[2][o] + red[3][o]);
-    const int cin = chunk * 64 + (m & 63), cout = nt * p.BN + c;
     p.dw[((size_t)cout * p.Cin + cin) * p.RS + tap] += total;
   }
 }
@@ -330,26 +409,16 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_flat_kernel(const WgRed
   if (typeB && idx >= p.totalB) return;
   const int m = (int)(idx & 127);
   const long long rest = idx >> 7;
-  const int c = (int)(rest % p.BN);
-  const long long gs = rest / p.BN;
-  const int n_slots = typeB ? 1 : p.slotsA;
+  const int c = (int)(rest % p.ncol);
+  const long long gs = rest / p.ncol;
+  const int n_slots = typeB ? p.slotsB : p.slotsA;
   const int slot = (int)(gs % n_slots);
   const int g = (int)(gs / n_slots);
   const int ksplit = typeB ? p.ksB : p.ksA;
-  int tap, chunk, nt;
-  if (typeB) {
-    tap = p.RS - 1;
-    chunk = 2 * (g % p.cin_pairs) + (m >> 6);
-    nt = g / p.cin_pairs;
-    if (chunk >= p.cin_chunks) return;
-  } else {
-    tap = 2 * slot + (m >> 6);
-    chunk = g % p.cin_chunks;
-    nt = g / p.cin_chunks;
-    if (tap >= p.RS) return;
-  }
-  const size_t slice = (size_t)n_slots * p.BN * 128;
-  const float* src = p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + ((size_t)slot * p.BN + c) * 128 + m;
+  int tap = 0, cin = 0, cout = 0;
+  if (!wg_decode(p, typeB, g, slot, c, m, &tap, &cin, &cout)) return;
+  const size_t slice = (size_t)n_slots * p.ncol * 128;
+  const float* src = p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + ((size_t)slot * p.ncol + c) * 128 + m;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   int k = 0;
   for (; k + 3 < ksplit; k += 4) {
@@ -360,16 +429,15 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_flat_kernel(const WgRed
   }
   for (; k < ksplit; ++k) a0 += src[(size_t)k * slice];
   const float acc = (a0 + a1) + (a2 + a3);
-  const int cin = chunk * 64 + (m & 63), cout = nt * p.BN + c;
   p.dw[((size_t)cout * p.Cin + cin) * p.RS + tap] += acc;
 }
 
 // KP (multiple of 16, <= 128) minimises the pixel slots wasted at the right edge of a row (ties: larger KP); RPS = 2
 // only where three stages still fit (measured: a small, free reduction of L2 traffic, no speed-up by itself).
 static int round1k(int v) { return (v + 1023) & ~1023; }
-static int halo_stage_bytes(int kp, int rps, int R, int S, int bn, bool typed) {
+static int halo_stage_bytes(int kp, int rps, int R, int S, int bn, bool typed, bool tmode = false) {
   const int xb = round1k((kp + S - 1) * 128);
-  const int a = (rps + R - 1) * xb, b = typed ? 2 * rps * xb : 0;
+  const int a = (tmode ? rps + 1 : rps + R - 1) * xb, b = typed ? 2 * rps * xb : 0;
   return rps * (bn / 64) * round1k(kp * 128) + (a > b ? a : b);
 }
 static void pick_shape(int Ho, int Wo, int R, int S, int bn, bool typed, int* kp_out, int* rps_out) {
@@ -407,7 +475,7 @@ bool wgrad_halo_supported(int Cin, int Cout, int R, int S, int stride) {
 
 // The whole decomposition of one problem; shared by the workspace query and the launch.
 struct WgPlan {
-  int bn, typed, slotsA, KP, rps, total_kb;
+  int bn, typed, tmode, slotsA, KP, rps, total_kb;
   int cin_chunks, cin_pairs, cout_tiles, groupsA, groupsB, ksA, ksB;
   size_t ws_floats, wsB_off;
 };
@@ -424,11 +492,19 @@ static WgPlan make_plan(int N, int H, int W, int Cin, int Cout, int R, int S, in
   // everywhere; ECGMM_WG_BN=128 selects the two-type kernel (kept under test: tests/test_conv_gpu.py).
   const char* ebn = getenv("ECGMM_WG_BN");
   const bool want128 = ebn && atoi(ebn) == 128;
-  q.bn = (Cout % 128 == 0 && have_ws && want128) ? 128 : 64;
+  // EXPERIMENTAL transposed GEMM (wgrad_halo_kernel<128, true>): ECGMM_WG_T=1, 3x3, Cout % 128 == 0, workspace
+  const char* et = getenv("ECGMM_WG_T");
+  q.tmode = (et && atoi(et) == 1 && R == 3 && S == 3 && Cout % 128 == 0 && have_ws) ? 1 : 0;
+  q.bn = (Cout % 128 == 0 && have_ws && (want128 || q.tmode)) ? 128 : 64;
   const int slots_all = (RS + 1) / 2;
   q.typed = (q.bn == 128 && slots_all * q.bn > 512) ? 1 : 0;  // does not fit the 512 TMEM columns -> two CTA types
   q.slotsA = q.typed ? 512 / q.bn : slots_all;                // typed: 4 accumulators = taps 0..7, type B: tap 8
+  if (q.tmode) {
+    q.typed = 1;
+    q.slotsA = 2;  // filter rows 0 and 1; type B: filter row 2 of a pair of Cin slices (also 2 accumulators)
+  }
   pick_shape(Ho, Wo, R, S, q.bn, q.typed != 0, &q.KP, &q.rps);
+  if (q.tmode) q.rps = 1;
   q.total_kb = N * ceil_div(Ho, q.rps) * ceil_div(Wo, q.KP);
   q.cin_chunks = Cin / 64;
   q.cin_pairs = (q.cin_chunks + 1) / 2;
@@ -436,7 +512,11 @@ static WgPlan make_plan(int N, int H, int W, int Cin, int Cout, int R, int S, in
   q.groupsA = q.cin_chunks * q.cout_tiles;
   q.groupsB = q.typed ? q.cin_pairs * q.cout_tiles : 0;
   const int sms = num_sms();
-  if (q.typed) {
+  if (q.tmode) {
+    // two MMA groups per pixel block in both types: same split-K count
+    q.ksA = q.ksB = sms / (q.groupsA + q.groupsB);
+    if (q.ksA < 1) q.ksA = q.ksB = 1;
+  } else if (q.typed) {
     // MMA groups per pixel block: slotsA per type-A group, 1 per type-B group; CTAs in proportion
     const double per_unit = (double)sms / (double)(q.groupsA * q.slotsA + q.groupsB);
     q.ksA = (int)(per_unit * q.slotsA);
@@ -451,8 +531,9 @@ static WgPlan make_plan(int N, int H, int W, int Cin, int Cout, int R, int S, in
   const int cap = q.total_kb > 0 ? q.total_kb : 1;
   if (q.ksA > cap) q.ksA = cap;
   if (q.ksB > cap) q.ksB = cap;
-  q.wsB_off = (size_t)q.groupsA * q.ksA * q.slotsA * q.bn * 128;
-  q.ws_floats = q.wsB_off + (size_t)q.groupsB * q.ksB * q.bn * 128;
+  const size_t ncol = q.tmode ? 192 : q.bn, slotsB = q.tmode ? 2 : 1;
+  q.wsB_off = (size_t)q.groupsA * q.ksA * q.slotsA * ncol * 128;
+  q.ws_floats = q.wsB_off + (size_t)q.groupsB * q.ksB * slotsB * ncol * 128;
   return q;
 }
 
@@ -461,15 +542,16 @@ size_t wgrad_halo_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R,
   return q.ws_floats * sizeof(float);
 }
 
-template <int BN>
+template <int BN, bool T = false>
 static int launch_typed(const WgHaloParams& p, int grid, int smem, cudaStream_t st) {
   static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
   const int ds = device_slot();
   if (!configured[ds]) {
-    ECGMM_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ECGMM_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<BN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024));
     configured[ds] = true;
   }
-  wgrad_halo_kernel<BN><<<grid, 192, smem, st>>>(p);
+  wgrad_halo_kernel<BN, T><<<grid, 192, smem, st>>>(p);
   return check_launch("wgrad_halo_kernel");
 }
 
@@ -495,7 +577,8 @@ int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
   p.x_box_stride = round1k(p.x_box_bytes);
   p.dy_box_bytes = p.KP * 128;
   p.dy_box_stride = round1k(p.dy_box_bytes);
-  p.stage_bytes = halo_stage_bytes(p.KP, p.rps, R, S, q.bn, q.typed != 0);
+  p.stage_bytes = halo_stage_bytes(p.KP, p.rps, R, S, q.bn, q.typed != 0, q.tmode != 0);
+  p.tmode = q.tmode;
   int stages = (220 * 1024) / p.stage_bytes;
   if (stages > kHaloMaxStages) stages = kHaloMaxStages;
   ECGMM_CHECK(stages >= 2, ECGMM_ERR_SHAPE, "wgrad_halo: stage of %d bytes does not fit twice", p.stage_bytes);
@@ -526,7 +609,8 @@ int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
   if (rc) return rc;
   const int smem = p.stages * p.stage_bytes + 256 + 1024;
   const int grid = q.groupsA * q.ksA + q.groupsB * q.ksB;
-  rc = q.bn == 128 ? launch_typed<128>(p, grid, smem, st) : launch_typed<64>(p, grid, smem, st);
+  rc = q.tmode ? launch_typed<128, true>(p, grid, smem, st)
+               : (q.bn == 128 ? launch_typed<128>(p, grid, smem, st) : launch_typed<64>(p, grid, smem, st));
   if (rc || !p.ws) return rc;
   WgReduceParams r;
   memset(&r, 0, sizeof(r));
@@ -540,8 +624,12 @@ int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
   r.slotsA = q.slotsA;
   r.ksA = q.ksA;
   r.ksB = p.ksB;
-  r.totalA = (long long)q.groupsA * q.slotsA * q.bn * 128;
-  r.totalB = (long long)q.groupsB * q.bn * 128;
+  r.ncol = q.tmode ? 192 : q.bn;
+  r.slotsB = q.tmode ? 2 : 1;
+  r.tmode = q.tmode;
+  r.S = S;
+  r.totalA = (long long)q.groupsA * q.slotsA * r.ncol * 128;
+  r.totalB = (long long)q.groupsB * r.slotsB * r.ncol * 128;
   r.wsB_off = (long long)q.wsB_off;
   const long long total = r.totalA + r.totalB;  // both multiples of 64 (BN * 128 elements per accumulator)
   if (q.ksA >= 16)  // many partials per element: 4 k-groups per element

@@ -43,6 +43,24 @@ def test_wgrad_both_mma_widths(case, bn, monkeypatch):
     ops._SHAPE_CACHE.clear()
 
 
+@pytest.mark.skipif(os.environ.get("ECGMM_TEST_EXPERIMENTAL") != "1",
+                    reason="the transposed weight gradient is a round-2 work item: not yet validated on hardware")
+@pytest.mark.parametrize("case", [c for c in chk.CASES if c[6] == 3 and c[7] == 3 and c[8] == 1 and c[5] % 128 == 0],
+                         ids=lambda c: c[0] if isinstance(c, tuple) else str(c))
+def test_experimental_transposed_wgrad(case, monkeypatch):
+    """ECGMM_WG_T=1: M = 128 output channels x N = 192 (three horizontal taps x 64 input channels) MMAs, two CTA types
+    (wgrad_halo_kernel<128, true>); bookkeeping emulated in tests/test_wgrad_t_emulation_cpu.py."""
+    from ecgmm import ops
+
+    monkeypatch.setenv("ECGMM_WG_T", "1")
+    ops._SHAPE_CACHE.clear()  # workspace sizes depend on the mode
+    results = []
+    assert chk.run_case(*case, results=results, do=("wgrad",))
+    bad = [r for r in results if not r[2]]
+    assert not bad, bad
+    ops._SHAPE_CACHE.clear()
+
+
 @pytest.mark.parametrize("name,N,H,W", [("stem_small", 2, 50, 100), ("stem_odd", 1, 37, 75),
                                         ("stem_250x2500", 2, 250, 2500)])
 def test_stem_case(name, N, H, W):

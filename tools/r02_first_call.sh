@@ -40,6 +40,13 @@ if grep -q " passed" $O/${TAG}_wgstream_test.log && ! grep -q " failed" $O/${TAG
   ECGMM_WGRAD_STREAM=1 run wgstream_b512 300 $B --detail
 fi
 
+# --- experiment 2b: transposed weight gradient (M = Cout, N = 192: wgrad_halo_kernel<128, true>)
+run wgT_test 300 python -m pytest tests/test_conv_gpu.py -x -q -m gpu -k "transposed_wgrad"
+if grep -q " passed" $O/${TAG}_wgT_test.log && ! grep -q " failed" $O/${TAG}_wgT_test.log; then
+  ECGMM_WG_T=1 run wgT_b64  300 $B --global-batch 64 --detail
+  ECGMM_WG_T=1 run wgT_b512 300 $B --detail
+fi
+
 # --- experiment 3: folded-BatchNorm convolution epilogue of the serving path (ecgmm_conv2d_fwd_bn)
 run fusedbn_test  300 python -m pytest tests/test_zz_attrib_serve_gpu.py -x -q -m gpu -k "experimental"
 run serve_plain   300 python tools/serve_bench.py
