@@ -2,7 +2,7 @@
 # First GPU call of the next round: everything that was written after round 1's GPU budget was spent, in ONE gpurun
 # call, each step under its own timeout so that a hanging experimental kernel cannot take the box with it.
 #
-#   gpurun --timeout 1500 -- 'bash tools/r02_first_call.sh r02a'
+#   gpurun --timeout 2700 -- 'bash tools/r02_first_call.sh r02a'      (about 30-40 GPU-minutes)
 #
 # Writes gpurun_out/<tag>_*.log.  Order: (1) the regular GPU suite (incl. the tests collected last that have never
 # run on hardware), (2) smoke, (3) baseline bench lines at per-GPU batch 64 and 512, (4) the gated experiments, each
