@@ -474,6 +474,21 @@ static int design_butter_lowpass(int order, double wn, double* b, double* a, dou
   return ECGMM_OK;
 }
 
+template <typename TIn, int ORDER>
+static int launch_block(const void* x, float* y, long long rows, int L, int window, const BlockPrepParams& prm,
+                        int zscore, double eps, size_t smem, cudaStream_t st) {
+  static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
+  const int ds = device_slot();
+  if (!configured[ds]) {
+    ECGMM_CUDA(cudaFuncSetAttribute(signal_preprocess_block_kernel<TIn, ORDER>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured[ds] = true;
+  }
+  signal_preprocess_block_kernel<TIn, ORDER><<<(unsigned)rows, kBlkThreads, smem, st>>>(
+      reinterpret_cast<const TIn*>(x), y, L, window, prm, zscore, eps);
+  return ECGMM_OK;
+}
+
 }  // namespace ecgmm
 
 using namespace ecgmm;
@@ -524,20 +539,12 @@ extern "C" int ecgmm_signal_preprocess(const void* x, int x_is_f64, float* y, vo
     BlockPrepParams prm;
     size_t smem = 0;
     if (block_plan(order, c, L, window, &prm, &smem)) {
-#define ECGMM_BLK(T_, O_)                                                                                            \
-  do {                                                                                                               \
-    ECGMM_CUDA(cudaFuncSetAttribute(signal_preprocess_block_kernel<T_, O_>,                                          \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                      \
-    signal_preprocess_block_kernel<T_, O_><<<(unsigned)rows, kBlkThreads, smem, st>>>(                               \
-        reinterpret_cast<const T_*>(x), y, L, window, prm, zscore, eps);                                            \
-  } while (0)
-#define ECGMM_BLK_ORDER(O_)    \
-  case O_:                     \
-    if (x_is_f64)              \
-      ECGMM_BLK(double, O_);   \
-    else                       \
-      ECGMM_BLK(float, O_);    \
+#define ECGMM_BLK_ORDER(O_)                                                                                     \
+  case O_:                                                                                                      \
+    rc = x_is_f64 ? launch_block<double, O_>(x, y, rows, L, window, prm, zscore, eps, smem, st)                 \
+                  : launch_block<float, O_>(x, y, rows, L, window, prm, zscore, eps, smem, st);                 \
     break
+      int rc = ECGMM_OK;
       switch (order) {
         ECGMM_BLK_ORDER(0);
         ECGMM_BLK_ORDER(1);
@@ -551,7 +558,7 @@ extern "C" int ecgmm_signal_preprocess(const void* x, int x_is_f64, float* y, vo
           ECGMM_BLK_ORDER(8);
       }
 #undef ECGMM_BLK_ORDER
-#undef ECGMM_BLK
+      if (rc) return rc;
       return check_launch("signal_preprocess_block_kernel");
     }
   }
