@@ -67,7 +67,7 @@ run desc_probe 120 python tools/desc_probe.py
 # --- the other configs (BASELINE.json configs[1], [3], [4]) and the reference arm
 run signal   300 python tools/signal_bench.py
 run perturb  300 python tools/perturb_bench.py
-run zz_tests 600 python -m pytest tests/test_zz_modality_shapley_gpu.py tests/test_zz_attrib_serve_gpu.py -q -m gpu
+ECGMM_TEST_EXPERIMENTAL=1 run zz_tests 600 python -m pytest tests/test_zz_modality_shapley_gpu.py tests/test_zz_attrib_serve_gpu.py -q -m gpu
 run kfold    600 python tools/kfold_bench.py
 run ref_arm  300 python bench.py --impl reference --steps 2 --warmup 1
 
