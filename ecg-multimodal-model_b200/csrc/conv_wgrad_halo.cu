@@ -314,48 +314,8 @@ struct WgReduceParams {
   int BN, RS, Cin, cin_chunks, cin_pairs;
   int slotsA, ksA, ksB;
   long long totalA, totalB, wsB_off;
-  int ncol, slotsB, tmode, S;  // columns per accumulator (BN, or 192 transposed), type-B accumulators, transposed layout
+  int S;  // transposed layout only (wgrad_halo_reduce_t_kernel); appended: the kernels below read the same offsets as before
 };
-
-// Which dw element a workspace element (type, group g, accumulator slot, column c, row m) belongs to.
-//   original : row m = (tap parity, cin), column c = cout;  type A slot = tap pair, type B = last tap of a Cin-slice pair
-//   transposed: row m = cout, column c = (s, cin);          type A slot = filter row r, type B slot = Cin slice (r = R-1)
-__device__ __forceinline__ bool wg_decode(const WgReduceParams& p, bool typeB, int g, int slot, int c, int m,
-                                          int* tap, int* cin, int* cout) {
-  if (p.tmode) {
-    const int s = c >> 6;
-    int chunk, nt, r;
-    if (typeB) {
-      r = p.RS / p.S - 1;
-      chunk = 2 * (g % p.cin_pairs) + slot;
-      nt = g / p.cin_pairs;
-      if (chunk >= p.cin_chunks) return false;
-    } else {
-      r = slot;
-      chunk = g % p.cin_chunks;
-      nt = g / p.cin_chunks;
-    }
-    *tap = r * p.S + s;
-    *cin = chunk * 64 + (c & 63);
-    *cout = nt * p.BN + m;
-    return true;
-  }
-  int chunk, nt;
-  if (typeB) {
-    *tap = p.RS - 1;
-    chunk = 2 * (g % p.cin_pairs) + (m >> 6);
-    nt = g / p.cin_pairs;
-    if (chunk >= p.cin_chunks) return false;
-  } else {
-    *tap = 2 * slot + (m >> 6);
-    chunk = g % p.cin_chunks;
-    nt = g / p.cin_chunks;
-    if (*tap >= p.RS) return false;
-  }
-  *cin = chunk * 64 + (m & 63);
-  *cout = nt * p.BN + c;
-  return true;
-}
 
 // A CTA folds 64 consecutive result elements; its 256 threads are 64 elements x 4 interleaved k-groups (k = kg, kg+4,
 // ...), each with 4 independent accumulators: 16 partial loads in flight per element instead of 4 (the fold of the
@@ -369,19 +329,30 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const WgReducePa
   const bool in_range = !typeB || idx < p.totalB;
   const int m = (int)(idx & 127);
   const long long rest = idx >> 7;
-  const int c = (int)(rest % p.ncol);
-  const long long gs = rest / p.ncol;
-  const int n_slots = typeB ? p.slotsB : p.slotsA;
+  const int c = (int)(rest % p.BN);
+  const long long gs = rest / p.BN;
+  const int n_slots = typeB ? 1 : p.slotsA;
   const int slot = (int)(gs % n_slots);
   const int g = (int)(gs / n_slots);
   const int ksplit = typeB ? p.ksB : p.ksA;
-  int tap = 0, cin = 0, cout = 0;
-  const bool live = in_range && wg_decode(p, typeB, g, slot, c, m, &tap, &cin, &cout);
+  int tap, chunk, nt;
+  bool live = in_range;
+  if (typeB) {
+    tap = p.RS - 1;
+    chunk = 2 * (g % p.cin_pairs) + (m >> 6);
+    nt = g / p.cin_pairs;
+    live = live && chunk < p.cin_chunks;
+  } else {
+    tap = 2 * slot + (m >> 6);
+    chunk = g % p.cin_chunks;
+    nt = g / p.cin_chunks;
+    live = live && tap < p.RS;
+  }
   float acc = 0.f;
   if (live) {
-    const size_t slice = (size_t)n_slots * p.ncol * 128;  // one CTA of the producer kernel
+    const size_t slice = (size_t)n_slots * p.BN * 128;  // one CTA of the producer kernel
     const float* src =
-        p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + ((size_t)slot * p.ncol + c) * 128 + m;
+        p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + ((size_t)slot * p.BN + c) * 128 + m;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int k = kg;
     for (; k + 12 < ksplit; k += 16) {
@@ -397,6 +368,7 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_kernel(const WgReducePa
   __syncthreads();
   if (kg == 0 && live) {
     const float total = (red[0][o] + red[1][o]) + (red[2][o] + red[3][o]);
+    const int cin = chunk * 64 + (m & 63), cout = nt * p.BN + c;
     p.dw[((size_t)cout * p.Cin + cin) * p.RS + tap] += total;
   }
 }
@@ -409,16 +381,26 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_flat_kernel(const WgRed
   if (typeB && idx >= p.totalB) return;
   const int m = (int)(idx & 127);
   const long long rest = idx >> 7;
-  const int c = (int)(rest % p.ncol);
-  const long long gs = rest / p.ncol;
-  const int n_slots = typeB ? p.slotsB : p.slotsA;
+  const int c = (int)(rest % p.BN);
+  const long long gs = rest / p.BN;
+  const int n_slots = typeB ? 1 : p.slotsA;
   const int slot = (int)(gs % n_slots);
   const int g = (int)(gs / n_slots);
   const int ksplit = typeB ? p.ksB : p.ksA;
-  int tap = 0, cin = 0, cout = 0;
-  if (!wg_decode(p, typeB, g, slot, c, m, &tap, &cin, &cout)) return;
-  const size_t slice = (size_t)n_slots * p.ncol * 128;
-  const float* src = p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + ((size_t)slot * p.ncol + c) * 128 + m;
+  int tap, chunk, nt;
+  if (typeB) {
+    tap = p.RS - 1;
+    chunk = 2 * (g % p.cin_pairs) + (m >> 6);
+    nt = g / p.cin_pairs;
+    if (chunk >= p.cin_chunks) return;
+  } else {
+    tap = 2 * slot + (m >> 6);
+    chunk = g % p.cin_chunks;
+    nt = g / p.cin_chunks;
+    if (tap >= p.RS) return;
+  }
+  const size_t slice = (size_t)n_slots * p.BN * 128;
+  const float* src = p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + ((size_t)slot * p.BN + c) * 128 + m;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   int k = 0;
   for (; k + 3 < ksplit; k += 4) {
@@ -429,7 +411,51 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_flat_kernel(const WgRed
   }
   for (; k < ksplit; ++k) a0 += src[(size_t)k * slice];
   const float acc = (a0 + a1) + (a2 + a3);
+  const int cin = chunk * 64 + (m & 63), cout = nt * p.BN + c;
   p.dw[((size_t)cout * p.Cin + cin) * p.RS + tap] += acc;
+}
+
+// Reduction of the TRANSPOSED kernel's partials (wgrad_halo_kernel<128, true>; experimental, see there): workspace
+// slices [2 slots][192 columns][128 rows]; row m = output channel, column c = (s, cin); type A slot = filter row r of
+// Cin slice g % cin_chunks, type B slot = Cin slice 2 (g % cin_pairs) + slot with r = R - 1.  One thread per element.
+// (A separate kernel so that the two reducers above stay exactly the code that has run on hardware.)
+__global__ void __launch_bounds__(256) wgrad_halo_reduce_t_kernel(const WgReduceParams p) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool typeB = idx >= p.totalA;
+  if (typeB) idx -= p.totalA;
+  if (typeB && idx >= p.totalB) return;
+  const int m = (int)(idx & 127);
+  const long long rest = idx >> 7;
+  const int c = (int)(rest % 192);
+  const long long gs = rest / 192;
+  const int slot = (int)(gs % 2);
+  const int g = (int)(gs / 2);
+  const int ksplit = typeB ? p.ksB : p.ksA;
+  int r, chunk, nt;
+  if (typeB) {
+    r = p.RS / p.S - 1;
+    chunk = 2 * (g % p.cin_pairs) + slot;
+    nt = g / p.cin_pairs;
+    if (chunk >= p.cin_chunks) return;
+  } else {
+    r = slot;
+    chunk = g % p.cin_chunks;
+    nt = g / p.cin_chunks;
+  }
+  const int tap = r * p.S + (c >> 6);
+  const int cin = chunk * 64 + (c & 63), cout = nt * p.BN + m;
+  const size_t slice = (size_t)2 * 192 * 128;
+  const float* src = p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + ((size_t)slot * 192 + c) * 128 + m;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  for (; k + 3 < ksplit; k += 4) {
+    a0 += src[(size_t)k * slice];
+    a1 += src[(size_t)(k + 1) * slice];
+    a2 += src[(size_t)(k + 2) * slice];
+    a3 += src[(size_t)(k + 3) * slice];
+  }
+  for (; k < ksplit; ++k) a0 += src[(size_t)k * slice];
+  p.dw[((size_t)cout * p.Cin + cin) * p.RS + tap] += (a0 + a1) + (a2 + a3);
 }
 
 // KP (multiple of 16, <= 128) minimises the pixel slots wasted at the right edge of a row (ties: larger KP); RPS = 2
@@ -624,15 +650,15 @@ int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
   r.slotsA = q.slotsA;
   r.ksA = q.ksA;
   r.ksB = p.ksB;
-  r.ncol = q.tmode ? 192 : q.bn;
-  r.slotsB = q.tmode ? 2 : 1;
-  r.tmode = q.tmode;
   r.S = S;
-  r.totalA = (long long)q.groupsA * q.slotsA * r.ncol * 128;
-  r.totalB = (long long)q.groupsB * r.slotsB * r.ncol * 128;
+  const long long ncol = q.tmode ? 192 : q.bn, slotsB = q.tmode ? 2 : 1;
+  r.totalA = (long long)q.groupsA * q.slotsA * ncol * 128;
+  r.totalB = (long long)q.groupsB * slotsB * ncol * 128;
   r.wsB_off = (long long)q.wsB_off;
   const long long total = r.totalA + r.totalB;  // both multiples of 64 (BN * 128 elements per accumulator)
-  if (q.ksA >= 16)  // many partials per element: 4 k-groups per element
+  if (q.tmode)
+    wgrad_halo_reduce_t_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r);
+  else if (q.ksA >= 16)  // many partials per element: 4 k-groups per element
     wgrad_halo_reduce_kernel<<<(unsigned)((total + 63) / 64), 256, 0, st>>>(r);
   else
     wgrad_halo_reduce_flat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r);
