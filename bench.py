@@ -383,20 +383,21 @@ def run_ours(args):
         wd = threading.Timer(60.0, lambda: os._exit(0))
         wd.daemon = True
         wd.start()
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        if launch == "cuda_graph":
-            try:
+        try:
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            if launch == "cuda_graph":
                 gstep.graph.reset()
-            except Exception:
-                pass
-        sys.stdout.flush()
-        sys.stderr.flush()
-        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
-        t.start()
-        t.join(15.0)
-        os._exit(0)  # also skips interpreter finalisation, where the NCCL / graph destructors could block again
+            t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+            t.start()
+            t.join(15.0)
+        except Exception as ex:  # the measurement is complete and printed: a teardown problem must not fail the run
+            print(f"# teardown: {type(ex).__name__}: {ex}", file=sys.stderr)
+        finally:
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)  # also skips interpreter finalisation, where the NCCL / graph destructors could block again
 
     if rank != 0:
         shutdown()
