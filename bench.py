@@ -417,6 +417,17 @@ def run_ours(args):
                          "ms_per_step": round(c["ms"], 4), "achieved": round(ach, 2),
                          "unit": "TFLOP/s" if tensor else "GB/s",
                          "frac": round(ach / (tf_peak if tensor else hbm_peak), 4)}
+    # The 7x7 stem is HBM-bound (arithmetic intensity 124 flop/B): next to its tensor figure,
+    # report the bytes it has to move -- the space-to-depth image (32 B per 2x2 pixel block) and the 64-channel output
+    # (128 B per output pixel), once each -- against the HBM peak.
+    try:
+        stem_bytes = float(B) * (((H + 1) // 2) * ((W + 1) // 2) * 32 + ((H - 1) // 2 + 1) * ((W - 1) // 2 + 1) * 128)
+        for kind in ("stem_fwd", "stem_wgrad"):
+            if kind in kernels and classes[kind]["ms"] > 0:
+                gbs = stem_bytes / (classes[kind]["ms"] * 1e-3) / 1e9
+                kernels[kind]["hbm"] = {"achieved": round(gbs, 1), "unit": "GB/s", "frac": round(gbs / hbm_peak, 4)}
+    except Exception:
+        pass
     dom = max(classes, key=lambda k: classes[k]["ms"]) if classes else None
     roofline = None
     if dom:
