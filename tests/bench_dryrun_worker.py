@@ -17,7 +17,7 @@ import torch.distributed as dist  # noqa: E402
 import bench  # noqa: E402
 import ecgmm  # noqa: E402,F401
 from ecgmm import lib, ops  # noqa: E402
-from test_bench_dryrun_cpu import FakeEvent, FakeStream  # noqa: E402
+from test_bench_dryrun_cpu import FakeEvent, FakeGraph, FakeStream  # noqa: E402
 
 calls = []
 
@@ -61,12 +61,15 @@ torch.cuda.Stream = FakeStream
 torch.cuda.stream = lambda s: contextlib.nullcontext()
 torch.cuda.current_stream = lambda *a: FakeStream()
 torch.cuda.current_device = lambda: 0
+torch.cuda.CUDAGraph = FakeGraph
+torch.cuda.graph = lambda g, *a, **k: contextlib.nullcontext()
+torch.cuda.empty_cache = lambda: None
 os.environ["ECGMM_SIDE_STREAM"] = "0"
 _real_init = dist.init_process_group
 dist.init_process_group = lambda backend=None, **k: _real_init("gloo")
 
 bench.H, bench.W, bench.L = 64, 160, 600
 args = types.SimpleNamespace(gpus=int(os.environ["WORLD_SIZE"]), steps=2, warmup=3, impl="ours", global_batch=4,
-                             no_cpu_baseline=True, detail=False, launch="eager")
+                             no_cpu_baseline=True, detail=False, launch="graph")
 bench.run_ours(args)
 print("WORKER RETURNED WITHOUT THE HARD EXIT", flush=True)  # shutdown() ends every rank of a multi-rank run itself

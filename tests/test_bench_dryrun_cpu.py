@@ -28,6 +28,17 @@ class FakeEvent:
         return 2.0
 
 
+class FakeGraph:
+    def __init__(self, *a, **k):
+        self.replays = 0
+
+    def replay(self):
+        self.replays += 1
+
+    def reset(self):
+        pass
+
+
 class FakeStream:
     cuda_stream = 0
 
@@ -81,18 +92,21 @@ def fake_cuda(monkeypatch):
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: FakeStream())
     monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
+    monkeypatch.setattr(torch.cuda, "graph", lambda g, *a, **k: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
     monkeypatch.setenv("ECGMM_SIDE_STREAM", "0")
     return calls
 
 
-@pytest.mark.parametrize("sync_loss", ["0", "1"])
-def test_bench_own_arm_dry_run(fake_cuda, monkeypatch, capsys, sync_loss):
+@pytest.mark.parametrize("sync_loss,launch", [("0", "eager"), ("1", "eager"), ("0", "graph")])
+def test_bench_own_arm_dry_run(fake_cuda, monkeypatch, capsys, sync_loss, launch):
     monkeypatch.setenv("ECGMM_BENCH_SYNC_LOSS", sync_loss)
     monkeypatch.setattr(bench, "H", 64)
     monkeypatch.setattr(bench, "W", 160)
     monkeypatch.setattr(bench, "L", 600)
     args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, impl="ours", global_batch=2, no_cpu_baseline=True,
-                                 detail=True, launch="eager")
+                                 detail=True, launch=launch)
     bench.run_ours(args)
     out = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
     assert len(out) == 1
@@ -100,7 +114,8 @@ def test_bench_own_arm_dry_run(fake_cuda, monkeypatch, capsys, sync_loss):
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "kernels"):
         assert key in line, key
-    assert line["config"]["workload"].startswith("configs[2]") and line["config"]["launch"] == "eager"
+    assert line["config"]["workload"].startswith("configs[2]") and line["graph_note"] is None
+    assert line["config"]["launch"] == ("cuda_graph" if launch == "graph" else "eager")
     assert line["e2e"]["loss_read"].startswith("blocking" if sync_loss == "1" else "pipelined")
     assert line["e2e"]["note"] is None and line["e2e"]["h2d_bytes_per_step"] > 0 and line["gpu_launches"] > 300
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
@@ -130,5 +145,6 @@ def test_bench_two_ranks_dry_run():
     assert len(lines) == 1, p.stdout[-2000:]
     line = json.loads(lines[0])
     assert line["n_gpus"] == 2 and line["config"]["parallelism"] == "dp2" and line["config"]["per_gpu_batch"] == 2
+    assert line["config"]["launch"] == "cuda_graph" and line["graph_note"] is None
     assert line["allreduce"]["buckets_per_step"] >= 4 and line["cpu_baseline"] is None
     assert "WORKER RETURNED" not in p.stdout
