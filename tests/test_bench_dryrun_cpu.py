@@ -148,3 +148,46 @@ def test_bench_two_ranks_dry_run():
     assert line["config"]["launch"] == "cuda_graph" and line["graph_note"] is None
     assert line["allreduce"]["buckets_per_step"] >= 4 and line["cpu_baseline"] is None
     assert "WORKER RETURNED" not in p.stdout
+
+
+def test_endpoint_and_eval_graph_plumbing(fake_cuda):
+    """ecgmm.serve.ImageEndpoint(graph=True) and ecgmm.graph.GraphedEvalStep with a fake CUDAGraph: warm-up + capture
+    once per request kind, replays issue no library call, a changed weight re-captures, shape / mode errors raise."""
+    import ecgmm
+    from ecgmm import graph as eg
+    from ecgmm import serve
+
+    class Cfg:
+        num_classes = 2
+        device = "cpu"
+
+    m = ecgmm.ECGMultimodalModel(Cfg).eval()
+    m.overlap_branches = False
+    u8 = (torch.rand(2, 3, 64, 160) * 255).to(torch.uint8)
+    ep = serve.ImageEndpoint(m, example_image=u8, graph=True)
+    probs, classes = ep(u8)
+    assert probs.shape == (2, 2) and classes.shape == (2,)
+    n0 = len(fake_cuda)
+    ep(u8 + 1)
+    assert len(fake_cuda) == n0 and ep._graphs["classify"][0].replays == 2
+    p2, c2, cam = ep.gradcam(u8)
+    assert cam.shape == (2, 2, 5) and set(ep._graphs) == {"classify", "cam"}
+    with torch.no_grad():
+        m.image_classifier.bias.add_(1.0)
+    g_old = ep._graphs["classify"][0]
+    ep(u8)
+    assert ep._graphs["classify"][0] is not g_old  # new weights: captured again
+    with pytest.raises(lib.EcgmmError):
+        ep(u8[:1])
+    batch = (torch.randn(2, 3, 64, 160), torch.randn(2, 600), torch.randn(2, 24))
+    infer = eg.GraphedEvalStep(m, batch)
+    out = infer(*batch)
+    assert len(out) == 6 and out[3].shape == (2, 2)
+    n0 = len(fake_cuda)
+    infer(*batch)
+    assert len(fake_cuda) == n0 and infer.graph.replays == 2
+    m.train()
+    with torch.no_grad():
+        m.image_classifier.bias.add_(1.0)
+    with pytest.raises(lib.EcgmmError):
+        infer(*batch)
