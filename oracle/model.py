@@ -307,8 +307,9 @@ def expected_gradients(fusion_classifier, e, background, idx, alpha):
     idx[s, k] and an interpolation weight alpha[s, k] in [0, 1):
         phi[s, d, c] = mean_k (e[s, d] - bg[idx[s,k], d]) * d logit_c / d x_d (bg[idx] + alpha (e[s] - bg[idx]))
     e [S, D], background [NB, D], idx [S, K] integer, alpha [S, K].  Eval mode (dropout = identity).
-    PARITY UNPINNED against `shap` itself (absent, unpinned by the reference): pinned only through fusion_classifier
-    (bit-identical to the reference module) and the estimator's own properties (tests/test_oracle_cpu.py)."""
+    PARITY UNPINNED against `shap` itself (absent, unpinned by the reference).  Pinned: the same estimator evaluated
+    with torch.autograd on the REAL reference model's fusion_classifier gives bit-identical attributions
+    (oracle/gen_golden_attrib.py -> tests/golden/attrib_g2.pt), plus the estimator's own properties."""
     was_training = fusion_classifier.training
     fusion_classifier.eval()
     S, D = e.shape
@@ -343,7 +344,9 @@ def image_endpoint(model, image, class_index=None):
         cam[n, y, x] = relu( sum_k alpha[n, k] A[n, k, y, x] ),  alpha[n, k] = mean_{y,x} d logit_c / d A[n, k, y, x]
     with A = layer4's output and c = class_index (None: each sample's argmax).  Returns (probs [N, C], cam [N, h, w],
     classes [N]).  The forward chain is the reference's (bit-identical modules); the Grad-CAM generator is not in the
-    reference repository (only its output images, gpt/*.png): that half is the published definition, PARITY UNPINNED."""
+    reference repository (only its output images, gpt/*.png): that half is the published definition (parity with the
+    missing script unpinned), checked against autograd on the REAL reference model's image branch
+    (oracle/gen_golden_attrib.py -> tests/golden/attrib_g2.pt)."""
     was_training = model.training
     model.eval()
     enc = model.image_encoder

@@ -230,3 +230,20 @@ def test_image_endpoint_gradcam_spec():
     assert torch.allclose(cam, cam2, atol=1e-6 + 1e-4 * float(cam.max()))
     p2, cam3, cls3 = om.image_endpoint(ora, image)  # argmax classes
     assert cls3.tolist() == probs.argmax(1).tolist() and not ora.training
+
+
+def test_attribution_oracles_match_reference_golden():
+    """tests/golden/attrib_g2.pt (oracle/gen_golden_attrib.py): expected gradients and Grad-CAM evaluated on the REAL
+    reference model's own fusion_classifier / image branch with torch.autograd -- the oracle reproduces them."""
+    import os
+
+    from golden_util import GOLDEN_DIR
+
+    gold = torch.load(os.path.join(GOLDEN_DIR, "attrib_g2.pt"))
+    ora = make_oracle(seed=7)
+    phi = om.expected_gradients(ora.fusion_classifier, gold["e"], gold["bg"], gold["idx"], gold["alpha"])
+    assert torch.allclose(phi, gold["phi"], atol=1e-7)
+    assert torch.allclose(om.modality_share(phi), gold["share"], atol=1e-4)
+    image = (gold["u8"].float() / 255.0 - 0.5) / 0.5
+    probs, cam, _ = om.image_endpoint(ora, image, class_index=gold["class_index"])
+    assert torch.allclose(probs, gold["probs"], atol=1e-6) and torch.allclose(cam, gold["cam"], atol=1e-7)

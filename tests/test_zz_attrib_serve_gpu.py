@@ -240,3 +240,24 @@ def test_graphed_eval_step_matches_eager_forward():
         dut.fusion_classifier.lin2.bias.add_(1.0)  # forces a re-capture, which must refuse the mode
     with pytest.raises(lib.EcgmmError):
         infer(*b2)
+
+
+def test_attribution_and_endpoint_match_reference_golden():
+    """Against tests/golden/attrib_g2.pt: attributions and Grad-CAM evaluated on the real reference model's own modules
+    (oracle/gen_golden_attrib.py)."""
+    import os
+
+    from golden_util import GOLDEN_DIR
+
+    gold = torch.load(os.path.join(GOLDEN_DIR, "attrib_g2.pt"))
+    ora, dut = build_pair(seed=7)
+    dut.eval()
+    phi = explain.expected_gradients(dut.fusion_classifier, gold["e"].to(DEV), gold["bg"].to(DEV), gold["idx"],
+                                     gold["alpha"])
+    assert (phi.cpu() - gold["phi"]).abs().max().item() <= 2e-4
+    assert (explain.modality_share(phi).cpu() - gold["share"]).abs().max().item() <= 0.5  # percent
+    ep = serve.ImageEndpoint(dut, graph=False, class_index=gold["class_index"])
+    probs, classes, cam = ep.gradcam(gold["u8"].to(DEV))
+    assert (probs.cpu() - gold["probs"]).abs().max().item() <= 4e-2
+    num, den = (cam.cpu() - gold["cam"]).norm().item(), gold["cam"].norm().item()
+    assert num / den <= 0.15, (num, den)
