@@ -191,3 +191,23 @@ def test_endpoint_and_eval_graph_plumbing(fake_cuda):
         m.image_classifier.bias.add_(1.0)
     with pytest.raises(lib.EcgmmError):
         infer(*batch)
+
+
+def test_serve_bench_dry_run(fake_cuda, monkeypatch, capsys):
+    """tools/serve_bench.py (written without hardware) end to end with CUDA faked."""
+    import importlib.util
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("serve_bench", os.path.join(root, "tools", "serve_bench.py"))
+    sb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sb)
+    monkeypatch.setattr(sb, "H", 64)
+    monkeypatch.setattr(sb, "W", 160)
+    monkeypatch.setattr(sys, "argv", ["serve_bench.py", "--batch", "2", "--iters", "2", "--cpu-images", "1"])
+    sb.main()
+    line = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][0])
+    assert line["metric"] == "image-endpoint images/sec" and line["config"]["batch"] == 2
+    assert line["eager"]["launches_per_request"] > 40 and line["e2e"]["h2d_bytes_per_step"] == 2 * 3 * 64 * 160
+    assert line["cpu_baseline"]["kind"] == "port" and line["with_gradcam"]["images_per_s"] > 0
