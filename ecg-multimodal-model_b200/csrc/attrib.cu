@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) eg_reduce_kernel(const float* __restrict_
 
 // one warp per (sample, class): the three slice means of |phi| and their shares in percent
 __global__ void __launch_bounds__(256) modality_share_kernel(const float* __restrict__ phi, float* __restrict__ share,
-                                                             size_t pairs, int C, int D0, int D1, int D2) {
+                                                             size_t pairs, int C, int D0, int D1, int D2, int use_sum) {
   const int lane = threadIdx.x & 31;
   const size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
   if (w >= pairs) return;
@@ -109,9 +109,9 @@ __global__ void __launch_bounds__(256) modality_share_kernel(const float* __rest
     else
       m[2] += v;
   }
-  m[0] = warp_sum(m[0]) / (float)D0;
-  m[1] = warp_sum(m[1]) / (float)D1;
-  m[2] = warp_sum(m[2]) / (float)D2;
+  m[0] = warp_sum(m[0]) / (use_sum ? 1.f : (float)D0);
+  m[1] = warp_sum(m[1]) / (use_sum ? 1.f : (float)D1);
+  m[2] = warp_sum(m[2]) / (use_sum ? 1.f : (float)D2);
   const float total = m[0] + m[1] + m[2];
   if (lane < 3) {
     const float mine = lane == 0 ? m[0] : (lane == 1 ? m[1] : m[2]);
@@ -224,14 +224,14 @@ extern "C" int ecgmm_eg_reduce(const float* e, const float* bg, const int* idx, 
 }
 
 extern "C" int ecgmm_modality_share(const float* phi, float* share, long long S, int C, int D0, int D1, int D2,
-                                    void* stream) {
+                                    int use_sum, void* stream) {
   ECGMM_CHECK(phi && share, ECGMM_ERR_ARG, "modality_share: null pointer");
   ECGMM_CHECK(C >= 1 && D0 > 0 && D1 > 0 && D2 > 0, ECGMM_ERR_SHAPE, "modality_share: bad extents C=%d dims=%d,%d,%d",
               C, D0, D1, D2);
   if (S <= 0) return ECGMM_OK;
   const size_t pairs = (size_t)S * C;
   modality_share_kernel<<<(unsigned)((pairs + 7) / 8), 256, 0, (cudaStream_t)stream>>>(phi, share, pairs, C, D0, D1,
-                                                                                        D2);
+                                                                                        D2, use_sum);
   return check_launch("modality_share_kernel");
 }
 

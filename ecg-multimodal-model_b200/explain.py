@@ -214,14 +214,82 @@ def expected_gradients(fusion_classifier, e, background, idx, alpha, chunk_sampl
     return phi
 
 
-def modality_share(phi, dims=(256, 256, 256)):
-    """shap_fusion_modal_balance.py:177-200 on the device: phi [S, D, C] -> [S, C, 3] percentages of the image / signal
-    / clinical slices' mean |attribution| (0 where all three are 0)."""
+def modality_share(phi, dims=(256, 256, 256), reduce: str = "mean"):
+    """phi [S, D, C] -> [S, C, 3] percentages of the image / signal / clinical slices' |attribution| on the device
+    (0 where all three are 0).  reduce="mean": mean |phi| per slice (shap_fusion_modal_balance.py:189-200);
+    reduce="sum": summed |phi| per slice (lime_fusion_modal_balance.py:163-175).  Equal for equally wide modalities."""
+    if reduce not in ("mean", "sum"):
+        raise lib.EcgmmError(f"reduce must be 'mean' or 'sum', got {reduce!r}")
     ops._chk(phi, F32, "phi")
     if phi.dim() != 3 or len(dims) != 3 or phi.shape[1] != sum(dims) or min(dims) < 1:
         raise lib.EcgmmError(f"phi must be [S, {sum(dims)}, C] for modality widths {tuple(dims)}; got {tuple(phi.shape)}")
     S, _, C = phi.shape
     out = torch.empty((S, C, 3), dtype=F32, device=phi.device)
     lib.call("ecgmm_modality_share", ops._ptr(phi), ops._ptr(out), S, C, int(dims[0]), int(dims[1]), int(dims[2]),
-             ops._s())
+             int(reduce == "sum"), ops._s())
     return out
+
+
+# ---------------------------------------------------------------------------------------------- local surrogate (LIME)
+# lime_fusion_modal_balance.py:118-123,158-160: LimeTabularExplainer.explain_instance(fused[b], predict_fn,
+# num_features=768, num_samples=1000) perturbs the fused embedding, weighs the perturbed rows with an exponential kernel
+# of their distance to the instance and fits lime's default regressor -- sklearn Ridge(alpha=1, fit_intercept=True,
+# sample_weight=kernel weights) -- to the class-1 probability; the |coefficients| are then summed per modality (:163-175).
+# `lime` is unpinned and absent; its sampler (quartile discretisation of training-set statistics) is replaced by the
+# binary keep-masks of the perturbation path with an explicit plan, its REGRESSOR is reproduced exactly (pinned against
+# sklearn's Ridge in tests/test_oracle_cpu.py).  The fit is linear in the responses, so its operator is designed once
+# per plan on the host (ecgmm_ridge_operator, float64, like the filter taps of preprocess.butter_lowpass) and every
+# sample's coefficients are one row of a device GEMM.  Shapley-kernel weights in `weights` give KernelSHAP instead.
+def lime_plan(V: int, D: int, seed: int = 0, keep_prob: float = 0.5, kernel_width: float = None):
+    """(masks [V, D] uint8, weights [V] float64) on the host.  Row 0 is the instance itself (all kept), like lime's first
+    sample; weights = sqrt(exp(-d^2 / kernel_width^2)) with d = Euclidean distance of the binary row to the instance and
+    kernel_width = 0.75 sqrt(D) (lime_tabular's defaults)."""
+    g = torch.Generator().manual_seed(int(seed))
+    masks = (torch.rand(V, D, generator=g) < keep_prob).to(torch.uint8)
+    masks[0] = 1
+    kw = 0.75 * (D ** 0.5) if kernel_width is None else float(kernel_width)
+    d2 = (1 - masks.to(torch.float64)).sum(1)
+    return masks, torch.sqrt(torch.exp(-d2 / (kw * kw)))
+
+
+def regression_operator(masks, weights, alpha: float = 1.0, device=None):
+    """R [(D+1), V] fp32: (coefficients, intercept) = R @ responses for the weighted ridge fit on the binary masks.
+    masks [V, D] uint8 / bool and weights [V] are HOST tensors (the sampling plan); the design runs in libecgmm on the
+    host in float64 and the result is moved to `device` (a CUDA device) when given."""
+    if masks.device.type != "cpu" or weights.device.type != "cpu":
+        raise lib.EcgmmError("masks and weights are the host-side sampling plan: pass CPU tensors")
+    if masks.dim() != 2 or weights.dim() != 1 or weights.shape[0] != masks.shape[0]:
+        raise lib.EcgmmError(f"shapes must be masks [V,D], weights [V]; got {tuple(masks.shape)}, {tuple(weights.shape)}")
+    if masks.dtype == torch.bool:
+        masks = masks.to(torch.uint8)
+    if masks.dtype != torch.uint8:
+        raise lib.EcgmmError(f"masks must be uint8 or bool, got {masks.dtype}")
+    masks = masks.contiguous()
+    weights = weights.to(torch.float64).contiguous()
+    V, D = masks.shape
+    R = torch.empty((D + 1, V), dtype=F32)
+    lib.call("ecgmm_ridge_operator", masks.data_ptr(), weights.data_ptr(), V, D, float(alpha), R.data_ptr())
+    return R if device is None else R.to(device)
+
+
+def masked_regression(fusion_classifier, e, background, masks, weights=None, alpha: float = 1.0, class_index: int = 1,
+                      operator=None):
+    """Local linear surrogate of softmax(fusion_classifier(.))[class_index] around every sample.
+
+    e [S, D], background [D] CUDA tensors; masks [V, D] (host or device; the plan) and weights [V] (host) as returned by
+    lime_plan, or a ready `operator` = regression_operator(...) on e's device.  Returns (coef [S, D], intercept [S]):
+    all V x S model evaluations through perturbation_inference, then ONE [S, V] x [V, D+1] product."""
+    if class_index < 0:
+        raise lib.EcgmmError("masked_regression explains a class probability: class_index >= 0")
+    S, D = e.shape
+    if operator is None:
+        if weights is None:
+            raise lib.EcgmmError("pass weights (with host-side masks) or a ready operator")
+        operator = regression_operator(masks.cpu(), weights, alpha, e.device)
+    V = masks.shape[0]
+    if tuple(operator.shape) != (D + 1, V):
+        raise lib.EcgmmError(f"operator must be [{D + 1}, {V}], got {tuple(operator.shape)}")
+    ops._chk(operator, F32, "operator")
+    f = perturbation_inference(fusion_classifier, e, background, masks.to(e.device), class_index).contiguous()  # [S, V]
+    coef = ops.sgemm(f, operator, S, D + 1, V, transB=True)
+    return coef[:, :D].contiguous(), coef[:, D].contiguous()

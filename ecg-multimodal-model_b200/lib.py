@@ -78,7 +78,8 @@ SIGNATURES = {
     "ecgmm_eg_points": [_p, _p, _p, _p, _p, _ll, _i, _i, _i, _p],
     "ecgmm_eg_gate": [_p, _p, _p, _ll, _i, _i, _p],
     "ecgmm_eg_reduce": [_p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
-    "ecgmm_modality_share": [_p, _p, _ll, _i, _i, _i, _i, _p],
+    "ecgmm_modality_share": [_p, _p, _ll, _i, _i, _i, _i, _i, _p],
+    "ecgmm_ridge_operator": [_p, _p, _i, _i, _d, _p],
     "ecgmm_softmax_rows": [_p, _p, _p, _ll, _i, _p],
     "ecgmm_gather_rows": [_p, _p, _p, _ll, _i, _i, _p],
     "ecgmm_gradcam": [_p, _p, _p, _i, _i, _i, _f, _p],

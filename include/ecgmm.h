@@ -287,13 +287,28 @@ int ecgmm_head_tail(const ecgmm_bf16* hidden, const float* b1, const float* w2, 
  *   (GEMM)          : ecgmm_sgemm  grad[c] = gate[c] W1   [S*K][D] per class, stored [C][S*K][D]
  *   ecgmm_eg_reduce : phi [S][D][C] as above
  *   ecgmm_modality_share : share[s][c][m] = 100 * mean_{d in modality m} |phi[s][d][c]| / sum over the 3 modalities
- *                          (shap_fusion_modal_balance.py:177-200; 0 when the three means are all 0) */
+ *                          (shap_fusion_modal_balance.py:177-200; 0 when the three means are all 0); use_sum: see below */
 int ecgmm_eg_points(const float* e, const float* bg, const int* idx, const float* alpha, float* points, long long S,
                     int K, int D, int NB, void* stream);
 int ecgmm_eg_gate(const float* hidden, const float* w2, float* gate, long long rows, int HID, int C, void* stream);
 int ecgmm_eg_reduce(const float* e, const float* bg, const int* idx, const float* grad, float* phi, long long S, int K,
                     int D, int C, int NB, void* stream);
-int ecgmm_modality_share(const float* phi, float* share, long long S, int C, int D0, int D1, int D2, void* stream);
+int ecgmm_modality_share(const float* phi, float* share, long long S, int C, int D0, int D1, int D2, int use_sum,
+                         void* stream);
+
+/* ------------------------------------------------------------------ local surrogate regression (LIME / KernelSHAP)
+ * lime_fusion_modal_balance.py:158-160 fits, per explained instance, lime's default regressor -- sklearn
+ * Ridge(alpha=1, fit_intercept=True) with the kernel weights as sample_weight -- to the model's responses on perturbed
+ * rows; KernelSHAP is the same weighted least squares with Shapley-kernel weights.  On the binary keep-masks of
+ * ecgmm_perturb_build the fit is linear in the responses f [V]:  (w, b) = R f  with
+ *     zbar = sum pi z / sum pi,  Zc = Z - zbar,  w = (Zc^T diag(pi) Zc + alpha I)^-1 Zc^T diag(pi) f,
+ *     b = pi.f / sum pi - zbar.w
+ * ecgmm_ridge_operator designs R [(D+1)][V] (row D = intercept) ON THE HOST in float64 -- it depends only on the
+ * sampling plan, like the filter taps of ecgmm_butter_lowpass; all pointers are HOST pointers, no device is touched.
+ * Per sample the device then computes coefficients [S][D+1] = f [S][V] R^T with ecgmm_sgemm.
+ * ecgmm_modality_share(use_sum = 1) aggregates |w| per modality by SUM (lime_fusion_modal_balance.py:163-175); use_sum
+ * = 0 by MEAN (shap_fusion_modal_balance.py:189-200). */
+int ecgmm_ridge_operator(const uint8_t* masks, const double* weights, int V, int D, double alpha, float* R);
 
 /* ------------------------------------------------------------------ serving helpers (image-only endpoint, Grad-CAM)
  * the endpoint the mobile app posts to (Groove/components/SubmitButton.tsx:44-45) has no

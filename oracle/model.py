@@ -327,13 +327,30 @@ def expected_gradients(fusion_classifier, e, background, idx, alpha):
     return phi
 
 
-def modality_share(phi, dims=(256, 256, 256)):
+def masked_regression(fusion_classifier, e, background, masks, weights, alpha=1.0, class_index=1):
+    """The regressor of lime_fusion_modal_balance.py:158-160 -- lime's default model_regressor, sklearn
+    Ridge(alpha=1, fit_intercept=True) with the kernel weights as sample_weight -- fitted to the class probability on the
+    binary keep-masks of perturbation_inference (lime's own sampler is unpinned and absent; the plan is explicit).
+    Closed form in float64: centre with the weighted means, solve the normal equations.  Returns (coef [S, D],
+    intercept [S]) float32.  Pinned against sklearn.linear_model.Ridge in tests/test_oracle_cpu.py."""
+    f = perturbation_inference(fusion_classifier, e, background, masks, class_index).double()          # [S, V]
+    Z, pi = masks.double(), weights.double()
+    sw = pi.sum()
+    zbar, fbar = (pi[:, None] * Z).sum(0) / sw, (f * pi).sum(1) / sw
+    Zc = Z - zbar
+    G = Zc.T @ (pi[:, None] * Zc) + alpha * torch.eye(Z.shape[1], dtype=torch.float64)
+    w = torch.linalg.solve(G, Zc.T @ (pi[:, None] * (f - fbar[:, None]).T))                            # [D, S]
+    return w.T.float().contiguous(), (fbar - w.T @ zbar).float()
+
+
+def modality_share(phi, dims=(256, 256, 256), reduce="mean"):
     """shap_fusion_modal_balance.py:177-200: per sample and class, the mean |attribution| of the image / signal /
     clinical slices of the fused embedding as a percentage of their sum.  phi [S, D, C] -> [S, C, 3]
     (all-zero attributions give 0, the guard of lime_fusion_modal_balance.py:171-173)."""
     a = phi.abs()
     o1, o2 = dims[0], dims[0] + dims[1]
-    m = torch.stack([a[:, :o1].mean(1), a[:, o1:o2].mean(1), a[:, o2:].mean(1)], dim=-1)  # [S, C, 3]
+    red = (lambda t: t.mean(1)) if reduce == "mean" else (lambda t: t.sum(1))  # lime_fusion_modal_balance.py:163-175 sums
+    m = torch.stack([red(a[:, :o1]), red(a[:, o1:o2]), red(a[:, o2:])], dim=-1)  # [S, C, 3]
     total = m.sum(-1, keepdim=True)
     return torch.where(total > 0, m / total.clamp_min(1e-38) * 100.0, torch.zeros_like(m))
 

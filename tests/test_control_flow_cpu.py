@@ -188,6 +188,18 @@ def test_attribution_and_serving_flows(stub):
         explain.expected_gradients(m.fusion_classifier, e, bg, idx.float(), alpha)
     with pytest.raises(lib.EcgmmError):
         explain.modality_share(phi, dims=(256, 256, 128))
+    # LIME-style surrogate: the plan's operator is designed by a host function of the library (not a launch); every
+    # sample then costs the perturbation path plus one SGEMM
+    masks, w = explain.lime_plan(40, 768, seed=3)
+    del stub[:]
+    coef, icpt = explain.masked_regression(m.fusion_classifier, e, bg[0], masks, w, alpha=1.0)
+    assert coef.shape == (5, 768) and icpt.shape == (5,)
+    assert stub == ["ecgmm_ridge_operator", "ecgmm_perturb_build", "ecgmm_conv2d_fwd", "ecgmm_head_tail", "ecgmm_sgemm"]
+    explain.modality_share(coef.unsqueeze(-1).contiguous(), reduce="sum")
+    with pytest.raises(lib.EcgmmError):
+        explain.masked_regression(m.fusion_classifier, e, bg[0], masks)  # neither weights nor operator
+    with pytest.raises(lib.EcgmmError):
+        explain.modality_share(phi, reduce="max")
 
     image = (torch.rand(2, 3, 64, 160) * 255).to(torch.uint8)
     ep = serve.ImageEndpoint(m, example_image=image, graph=False)

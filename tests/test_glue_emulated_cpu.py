@@ -48,8 +48,9 @@ def emu_eg_reduce(e, bg, idx, grad, phi, S, K, D, C, NB, stream):
     phi.reshape(-1)[: S * D * C].view(S, D, C).copy_((diff.unsqueeze(0) * g).mean(2).permute(1, 2, 0))
 
 
-def emu_modality_share(phi, share, S, C, D0, D1, D2, stream):
-    share.reshape(-1)[: S * C * 3].view(S, C, 3).copy_(om.modality_share(phi.view(S, D0 + D1 + D2, C), (D0, D1, D2)))
+def emu_modality_share(phi, share, S, C, D0, D1, D2, use_sum, stream):
+    share.reshape(-1)[: S * C * 3].view(S, C, 3).copy_(
+        om.modality_share(phi.view(S, D0 + D1 + D2, C), (D0, D1, D2), "sum" if use_sum else "mean"))
 
 
 def emu_gather_rows(table, idx, out, rows, D, NT, stream):
@@ -209,3 +210,47 @@ def test_serving_block_wiring(emulated, monkeypatch, fused, layer, block):
     assert out.shape == ref.shape and out.dtype == torch.bfloat16
     err = (out.float() - ref).abs().max().item()
     assert err <= 3e-2 * max(1.0, ref.abs().max().item()), err  # bf16 storage of the intermediate activations
+
+
+# ---------------------------------------------------------------------------------------------- LIME surrogate glue
+def emu_perturb_build(e, bg, masks, out, S, V, D, stream):
+    z = _mat(masks, V, D).float()
+    out.reshape(-1)[: S * V * D].view(S, V, D).copy_(
+        (z.unsqueeze(0) * _mat(e, S, D).unsqueeze(1) + (1 - z).unsqueeze(0) * bg.reshape(1, 1, D)).to(torch.bfloat16))
+
+
+def emu_head_tail(hidden, b1, w2, b2, out, rows, HID, C, cls, stream):
+    h = torch.relu(_mat(hidden, rows, HID).float() + b1.reshape(1, HID))
+    logits = h @ _mat(w2, C, HID).t() + b2.reshape(1, C)
+    if cls < 0:
+        _mat(out, rows, C).copy_(logits)
+    else:
+        out.reshape(-1)[:rows].copy_(torch.softmax(logits, 1)[:, cls])
+
+
+def test_masked_regression_glue(emulated, monkeypatch):
+    """explain.masked_regression: perturbation inference (bf16 operands of the first Linear, as on the device) and the
+    [S, V] x [V, D+1] product with the REAL host-designed operator, against the fp32 oracle."""
+    for k, v in {"ecgmm_perturb_build": emu_perturb_build, "ecgmm_conv2d_fwd": emu_conv2d_fwd,
+                 "ecgmm_head_tail": emu_head_tail}.items():
+        monkeypatch.setitem(EMULATORS, k, v)
+    ora, dut = _pair()
+    g = torch.Generator().manual_seed(8)
+    S, V, D = 4, 200, 768
+    e, bg = torch.randn(S, D, generator=g), torch.randn(D, generator=g)
+    masks, w = explain.lime_plan(V, D, seed=2)
+    # the operator design is a HOST function of libecgmm: call the real one, not an emulator
+    import ctypes
+
+    so = lib.load()
+    R = torch.empty((D + 1, V), dtype=torch.float32)
+    assert so.ecgmm_ridge_operator(ctypes.c_void_p(masks.data_ptr()), ctypes.cast(w.data_ptr(), ctypes.POINTER(ctypes.c_double)),
+                                   V, D, 1.0, ctypes.c_void_p(R.data_ptr())) == 0
+    coef, b = explain.masked_regression(dut.fusion_classifier, e, bg, masks, operator=R)
+    cref, bref = om.masked_regression(ora.fusion_classifier, e, bg, masks, w, 1.0)
+    # the responses differ from the fp32 oracle by the bf16 rounding of the variants / first-layer weights (~1e-3 on a
+    # probability); the fit is a contraction of those differences
+    assert coef.shape == (S, D) and b.shape == (S,)
+    assert (coef - cref).abs().max().item() <= 2e-4 and (b - bref).abs().max().item() <= 5e-3
+    sh = explain.modality_share(coef.unsqueeze(-1).contiguous(), reduce="sum")
+    assert torch.allclose(sh, om.modality_share(coef.unsqueeze(-1), reduce="sum"), atol=1e-3)

@@ -247,3 +247,48 @@ def test_attribution_oracles_match_reference_golden():
     image = (gold["u8"].float() / 255.0 - 0.5) / 0.5
     probs, cam, _ = om.image_endpoint(ora, image, class_index=gold["class_index"])
     assert torch.allclose(probs, gold["probs"], atol=1e-6) and torch.allclose(cam, gold["cam"], atol=1e-7)
+
+
+def test_masked_regression_is_sklearn_ridge_and_host_operator_matches():
+    """The LIME regressor (lime_fusion_modal_balance.py:158-160 -> sklearn Ridge(alpha=1, fit_intercept=True,
+    sample_weight=kernel weights)): the oracle's closed form against sklearn itself, and libecgmm's host-side operator
+    design (ecgmm_ridge_operator, the product path's plan step: runs on the CPU by design) against the oracle."""
+    import numpy as np
+    from sklearn.linear_model import Ridge
+
+    import ecgmm  # noqa: F401
+    from ecgmm import explain, lib
+
+    ora = make_oracle(seed=7)
+    g = torch.Generator().manual_seed(4)
+    S, V, D = 3, 260, 768
+    e, bg = torch.randn(S, D, generator=g), torch.randn(D, generator=g)
+    masks, w = explain.lime_plan(V, D, seed=9)
+    assert masks.shape == (V, D) and masks[0].all() and w.dtype == torch.float64 and float(w[0]) == 1.0
+    coef, b = om.masked_regression(ora.fusion_classifier, e, bg, masks, w, alpha=1.0)
+    f = om.perturbation_inference(ora.fusion_classifier, e, bg, masks, 1)
+    for s in range(S):
+        r = Ridge(alpha=1.0, fit_intercept=True).fit(masks.numpy().astype(np.float64), f[s].double().numpy(),
+                                                     sample_weight=w.numpy())
+        assert np.abs(r.coef_ - coef[s].numpy()).max() < 1e-7 and abs(r.intercept_ - float(b[s])) < 1e-6
+    R = explain.regression_operator(masks, w, 1.0)
+    assert R.shape == (D + 1, V) and R.dtype == torch.float32
+    fit = f @ R.T
+    assert torch.allclose(fit[:, :D], coef, atol=1e-6) and torch.allclose(fit[:, D], b, atol=1e-6)
+    # KernelSHAP-style weights (a few huge ones) and another alpha go through the same operator
+    w2 = torch.rand(V, generator=g, dtype=torch.float64)
+    w2[:2] = 1e4
+    c2, b2 = om.masked_regression(ora.fusion_classifier, e, bg, masks, w2, alpha=0.1)
+    fit2 = f @ explain.regression_operator(masks, w2, 0.1).T
+    assert torch.allclose(fit2[:, :D], c2, atol=1e-5) and torch.allclose(fit2[:, D], b2, atol=1e-5)
+    # summed |coefficients| per modality (lime_fusion_modal_balance.py:163-175)
+    sh = om.modality_share(coef.unsqueeze(-1), reduce="sum")
+    assert sh.shape == (S, 1, 3) and torch.allclose(sh.sum(-1), torch.full((S, 1), 100.0), atol=1e-3)
+    with pytest.raises(lib.EcgmmError):  # alpha = 0 and a constant column (row 0 is all ones, make column 0 all ones)
+        m = masks.clone()
+        m[:, 0] = 1
+        explain.regression_operator(m, w, 0.0)
+    with pytest.raises(lib.EcgmmError):
+        explain.regression_operator(masks, -w, 1.0)
+    with pytest.raises(lib.EcgmmError):
+        explain.regression_operator(masks, w[:-1], 1.0)

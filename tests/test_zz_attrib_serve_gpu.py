@@ -261,3 +261,22 @@ def test_attribution_and_endpoint_match_reference_golden():
     assert (probs.cpu() - gold["probs"]).abs().max().item() <= 4e-2
     num, den = (cam.cpu() - gold["cam"]).norm().item(), gold["cam"].norm().item()
     assert num / den <= 0.15, (num, den)
+
+
+def test_masked_regression_matches_oracle():
+    """LIME-style local surrogate (sklearn-Ridge-equivalent fit on binary keep-masks): V model evaluations per sample on
+    the tensor-core perturbation path + one SGEMM with the host-designed operator, against the fp32 oracle."""
+    ora, dut = build_pair(seed=7)
+    g = torch.Generator().manual_seed(12)
+    S, V, D = 5, 300, 768
+    e, bg = torch.randn(S, D, generator=g), torch.randn(D, generator=g)
+    masks, w = explain.lime_plan(V, D, seed=4)
+    cref, bref = om.masked_regression(ora.fusion_classifier, e, bg, masks, w, 1.0)
+    coef, b = explain.masked_regression(dut.fusion_classifier, e.to(DEV), bg.to(DEV), masks, w, alpha=1.0)
+    assert coef.shape == (S, D) and b.shape == (S,)
+    assert (coef.cpu() - cref).abs().max().item() <= 2e-4 and (b.cpu() - bref).abs().max().item() <= 5e-3
+    R = explain.regression_operator(masks, w, 1.0, torch.device(DEV))  # a ready operator, masks on the device
+    coef2, b2 = explain.masked_regression(dut.fusion_classifier, e.to(DEV), bg.to(DEV), masks.to(DEV), operator=R)
+    assert (coef2 - coef).abs().max().item() <= 1e-6 and (b2 - b).abs().max().item() <= 1e-6
+    sh = explain.modality_share(coef.unsqueeze(-1).contiguous(), reduce="sum")
+    assert (sh.cpu() - om.modality_share(coef.cpu().unsqueeze(-1), reduce="sum")).abs().max().item() <= 1e-2
