@@ -105,7 +105,7 @@ void pick_tile(int OH, int OW, int npix, int* TH, int* TW) {
 
 extern "C" {
 
-int ecgmm_version(void) { return 106; }
+int ecgmm_version(void) { return 107; }
 
 unsigned long long ecgmm_launch_count(void) { return ecgmm::g_launches; }
 

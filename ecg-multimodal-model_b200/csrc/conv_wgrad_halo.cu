@@ -518,9 +518,12 @@ static WgPlan make_plan(int N, int H, int W, int Cin, int Cout, int R, int S, in
   // everywhere; ECGMM_WG_BN=128 selects the two-type kernel (kept under test: tests/test_conv_gpu.py).
   const char* ebn = getenv("ECGMM_WG_BN");
   const bool want128 = ebn && atoi(ebn) == 128;
-  // EXPERIMENTAL transposed GEMM (wgrad_halo_kernel<128, true>): ECGMM_WG_T=1, 3x3, Cout % 128 == 0, workspace
+  // Transposed GEMM (wgrad_halo_kernel<128, true>: M = 128 output channels, N = 192 = three horizontal taps x 64
+  // input channels) for every 3x3 layer with Cout % 128 == 0 when a workspace is given: measured on a B200 inside the
+  // training step (profiles/r02a_*): layer2 1000 -> 1443, layer3 ~780 -> 1555, layer4 ~610 -> 1542 TFLOP/s at batch 512.
+  // ECGMM_WG_T=0 selects the M = 128 (two taps) x N = 64 kernel again (kept under test).
   const char* et = getenv("ECGMM_WG_T");
-  q.tmode = (et && atoi(et) == 1 && R == 3 && S == 3 && Cout % 128 == 0 && have_ws) ? 1 : 0;
+  q.tmode = (!(et && atoi(et) == 0) && !want128 && R == 3 && S == 3 && Cout % 128 == 0 && have_ws) ? 1 : 0;
   q.bn = (Cout % 128 == 0 && have_ws && (want128 || q.tmode)) ? 128 : 64;
   const int slots_all = (RS + 1) / 2;
   q.typed = (q.bn == 128 && slots_all * q.bn > 512) ? 1 : 0;  // does not fit the 512 TMEM columns -> two CTA types

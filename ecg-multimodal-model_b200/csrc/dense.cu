@@ -361,14 +361,32 @@ __global__ void __launch_bounds__(256) ce_loss_kernel(const float* __restrict__ 
                                                        const long long* __restrict__ labels,
                                                        float* __restrict__ loss, float* __restrict__ dlogits, int B,
                                                        int C, int focal, float alpha, float gamma, float gscale,
-                                                       int* __restrict__ bad_label) {
+                                                       long long ignore_index, int* __restrict__ bad_label) {
+  // Rows labelled ignore_index do not count (torch: mean over the other rows, zero gradient); any other label outside
+  // [0, C) is an error (torch: device assert): flagged in *bad_label, zero gradient, and the loss becomes NaN so that
+  // the failure is loud even when nobody reads the flag.
   __shared__ float red[33];
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  float cnt = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const long long y = labels[b];
+    if (y == ignore_index) continue;
+    if (y < 0 || y >= C) s_bad = 1;  // benign race: every writer stores 1 (after the barrier inside block_sum)
+    else cnt += 1.f;
+  }
+  // CrossEntropyLoss(mean) averages over the rows that are not ignored; the focal loss is a plain mean over ALL rows
+  // of per-row values (signal_model.py:99-106: reduction='none', then .mean()) in which an ignored row is 0
+  const float n_valid = focal ? (float)B : block_sum(cnt, red);
+  __syncthreads();
   float acc = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const float* z = logits + (size_t)b * C;
     const long long y = labels[b];
-    if (y < 0 || y >= C) {
-      if (bad_label) *bad_label = 1;
+    if (y < 0 || y >= C) {  // ignored or invalid: no contribution, zero gradient row
+      if (dlogits)
+        for (int c = 0; c < C; ++c) dlogits[(size_t)b * C + c] = 0.f;
       continue;
     }
     float m = z[0];
@@ -388,7 +406,7 @@ __global__ void __launch_bounds__(256) ce_loss_kernel(const float* __restrict__ 
     }
     acc += li;
     if (dlogits) {
-      const float k = dce * gscale / B;
+      const float k = dce * gscale / n_valid;
       for (int c = 0; c < C; ++c) {
         const float p = expf(z[c] - lse);
         dlogits[(size_t)b * C + c] = k * (p - (c == y ? 1.f : 0.f));
@@ -396,7 +414,10 @@ __global__ void __launch_bounds__(256) ce_loss_kernel(const float* __restrict__ 
     }
   }
   const float t = block_sum(acc, red);
-  if (threadIdx.x == 0) *loss = t / B;
+  if (threadIdx.x == 0) {
+    *loss = s_bad ? __int_as_float(0x7fc00000) : t / n_valid;  // n_valid == 0 -> NaN, as torch
+    if (bad_label && s_bad) *bad_label = 1;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -704,11 +725,12 @@ extern "C" int ecgmm_var_loss_bwd(const float* f, const float* row_mean, const f
 }
 
 extern "C" int ecgmm_ce_loss(const float* logits, const long long* labels, float* loss, float* dlogits, int B, int C,
-                             int focal, float alpha, float gamma, float gscale, int* bad_label, void* stream) {
+                             int focal, float alpha, float gamma, float gscale, long long ignore_index,
+                             int* bad_label, void* stream) {
   ECGMM_CHECK(logits && labels && loss, ECGMM_ERR_ARG, "ce_loss: null pointer");
   ECGMM_CHECK(B > 0 && C > 0, ECGMM_ERR_SHAPE, "ce_loss: empty batch");
   ce_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, labels, loss, dlogits, B, C, focal, alpha, gamma,
-                                                     gscale, bad_label);
+                                                     gscale, ignore_index, bad_label);
   return check_launch("ce_loss_kernel");
 }
 

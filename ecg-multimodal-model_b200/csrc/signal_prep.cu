@@ -535,7 +535,8 @@ extern "C" int ecgmm_signal_preprocess(const void* x, int x_is_f64, float* y, vo
     design_butter_lowpass(order, wn, c.b, c.a, c.zi);
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (getenv("ECGMM_PREP_BLOCK") && rows <= 0x7fffffffLL) {  // experimental time-parallel kernel (see above)
+  const char* eblk = getenv("ECGMM_PREP_BLOCK");  // "0": force the one-thread-per-signal kernel
+  if (!(eblk && atoi(eblk) == 0) && rows <= 0x7fffffffLL) {  // time-parallel kernel when the design is well conditioned
     BlockPrepParams prm;
     size_t smem = 0;
     if (block_plan(order, c, L, window, &prm, &smem)) {

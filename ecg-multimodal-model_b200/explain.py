@@ -25,6 +25,7 @@ F32 = torch.float32
 
 def _head_weights(head):
     """(w1 bf16 [HID][1][1][D], b1, w2, b2) of an MLPHead, the bf16 copy cached on the module per weight version."""
+    head = getattr(head, "fusion_classifier", head)  # FusionClassifierWrapper (shap_fusion_modal_balance.py:100-108)
     lin1, lin2 = head.lin1, head.lin2
     w = lin1.weight
     key = (w.data_ptr(), w._version)

@@ -24,7 +24,6 @@ SIGNATURES = {
     "ecgmm_last_error": [],
     "ecgmm_check_device": [],
     "ecgmm_launch_count": [],
-    "ecgmm_debug_desc_probe": [_p, _p, _p, _i, _i, _p],
     "ecgmm_nchw_f32_to_nhwc_bf16": [_p, _p, _i, _i, _i, _i, _p],
     "ecgmm_nhwc_bf16_to_nchw_f32": [_p, _p, _i, _i, _i, _i, _p],
     "ecgmm_conv_weight_prep": [_p, _p, _p, _i, _i, _i, _i, _p],
@@ -66,7 +65,7 @@ SIGNATURES = {
     "ecgmm_fusion_gate_bwd": [_p] * 9 + [_i] * 5 + [_p],
     "ecgmm_var_loss_fwd": [_p] * 6 + [_i] * 4 + [_p],
     "ecgmm_var_loss_bwd": [_p] * 5 + [_i] * 3 + [_p],
-    "ecgmm_ce_loss": [_p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _p, _p],
+    "ecgmm_ce_loss": [_p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _ll, _p, _p],
     "ecgmm_dropout_fwd": [_p, _p, _p, _p, _ll, _f, c_ulonglong, _p, _p],
     "ecgmm_mask_bwd": [_p, _p, _p, _p, _ll, _p],
     "ecgmm_zscore": [_p, _p, _ll, _i, _f, _p],

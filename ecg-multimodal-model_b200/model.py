@@ -320,47 +320,10 @@ def _conv_block_fwd(blk, x, save, one_d=False):
     return out, rec
 
 
-class _WgradLane:
-    """EXPERIMENTAL (ECGMM_WGRAD_STREAM=1, off by default; not yet measured): weight gradients on their own stream.
-
-    A weight gradient is needed only when its bucket is all-reduced, while the data gradient next to it feeds the
-    BatchNorm backward of the next layer at once.  The weight-gradient GEMM is bound by its shared-memory operand feed
-    and the BatchNorm-backward kernels by HBM, so the two can share the SMs: the data gradient is enqueued FIRST (two
-    persistent GEMM kernels cannot co-reside, launch order decides), the weight gradient follows on this lane and runs
-    underneath the bandwidth-bound kernels of the main stream.  join() before a gradient bucket is published."""
-
-    def __init__(self):
-        self.main = torch.cuda.current_stream()
-        key = (self.main.device.index, self.main.cuda_stream)
-        st = _WgradLane._streams.get(key)
-        if st is None:
-            st = _WgradLane._streams[key] = torch.cuda.Stream(device=self.main.device)
-        self.lane = st
-        self.dirty = False
-
-    _streams = {}
-
-    def wgrad(self, x, dy, dw, R, S, stride, arena):
-        self.lane.wait_stream(self.main)  # dy (and the zeroed arena) are ready
-        with torch.cuda.stream(self.lane):
-            ops.conv2d_wgrad(x, dy, dw, R, S, stride)
-        for t in (x, dy, arena.flat):
-            t.record_stream(self.lane)
-        self.dirty = True
-
-    def join(self):
-        if self.dirty:
-            self.main.wait_stream(self.lane)
-            self.dirty = False
-
-
-WGRAD_STREAM = os.environ.get("ECGMM_WGRAD_STREAM", "0") == "1"
-
-
-def _conv_block_bwd(blk, rec, dout, G, lane=None):
-    """Returns the gradient w.r.t. the block input.  lane: optional _WgradLane (see there)."""
-    if lane is not None:
-        return _conv_block_bwd_overlapped(blk, rec, dout, G, lane)
+def _conv_block_bwd(blk, rec, dout, G):
+    """Returns the gradient w.r.t. the block input.
+    (Weight gradients on their own stream underneath the BatchNorm backward were tried and measured on a B200 --
+    profiles/r02a_*: batch 512 131.5 vs 132.4 ms, the weight-gradient class itself 42 vs 34 ms -- and removed.)"""
     x, a, sa, m, b, sb, d, sd, mask_m, mask_out, se_rec = rec
     s = blk.stride
     _, H, W, _ = x.shape
@@ -401,36 +364,6 @@ def _conv_block_bwd(blk, rec, dout, G, lane=None):
         ops.conv2d_dgrad(dd, dsc.shadows()[1], (H, W), s, out=dx, accumulate=True)
     else:
         dx = ops.conv2d_dgrad(da, w1d, (H, W), s, out=dz, accumulate=True)
-    return dx
-
-
-def _conv_block_bwd_overlapped(blk, rec, dout, G, lane):
-    """_conv_block_bwd for the 2-D blocks (no SE) with every weight gradient issued AFTER the data gradient that shares
-    its operand, on the weight-gradient lane."""
-    x, a, sa, m, b, sb, d, sd, mask_m, mask_out, _ = rec
-    s = blk.stride
-    _, H, W, _ = x.shape
-    R, S = blk.conv1.shadows()[0].shape[1:3]
-    db_, dz = ops.bn_backward(b, dout, sb, blk.bn2.weight, mask=mask_out, want_dz=True, dgamma=G(blk.bn2.weight),
-                              dbeta=G(blk.bn2.bias))
-    del dout
-    _, w2d = blk.conv2.shadows()
-    dm = ops.conv2d_dgrad(db_, w2d, (m.shape[1], m.shape[2]), 1)
-    lane.wgrad(m, db_, G(blk.conv2.weight), R, S, 1, G)
-    del db_
-    da, _ = ops.bn_backward(a, dm, sa, blk.bn1.weight, mask=mask_m, dgamma=G(blk.bn1.weight), dbeta=G(blk.bn1.bias))
-    del dm
-    _, w1d = blk.conv1.shadows()
-    if d is not None:
-        dsc, dsbn = blk.downsample[0], blk.downsample[1]
-        dd, _ = ops.bn_backward(d, dz, sd, dsbn.weight, y=None, dgamma=G(dsbn.weight), dbeta=G(dsbn.bias))
-        dx = ops.conv2d_dgrad(da, w1d, (H, W), s)
-        ops.conv2d_dgrad(dd, dsc.shadows()[1], (H, W), s, out=dx, accumulate=True)
-        lane.wgrad(x, da, G(blk.conv1.weight), R, S, s, G)
-        lane.wgrad(x, dd, G(dsc.weight), 1, 1, s, G)
-    else:
-        dx = ops.conv2d_dgrad(da, w1d, (H, W), s, out=dz, accumulate=True)
-        lane.wgrad(x, da, G(blk.conv1.weight), R, S, s, G)
     return dx
 
 
@@ -505,19 +438,14 @@ class ResNet18(_Stage):
         dx = ops.avgpool_bwd(dpooled, last_shape)
         blocks = self.blocks()
         stem_out = recs[0][0]  # pooled stem output = input of layer1.0
-        lane = _WgradLane() if (WGRAD_STREAM and dfeat.is_cuda) else None
         for i in range(len(blocks) - 1, -1, -1):
-            dx = _conv_block_bwd(blocks[i], recs[i], dx, G, lane)
+            dx = _conv_block_bwd(blocks[i], recs[i], dx, G)
             recs[i] = None
             if i in (6, 4, 2):  # a ResNet stage (2 blocks) is complete: its gradients are final
-                if lane is not None and getattr(self, "_grad_ready_cb", None) is not None:
-                    lane.join()  # only a data-parallel wrapper consumes the bucket this early
                 self._notify(G, G.end_of(blocks[i].conv1.weight))
         dc1, _ = ops.bn_backward(c1, dx, st1, self.bn1.weight, argmax=arg, dgamma=G(self.bn1.weight),
                                  dbeta=G(self.bn1.bias), pooled=stem_out, beta=self.bn1.bias)
         ops.stem_conv_wgrad(xs, dc1, G(self.conv1.weight), H, W)
-        if lane is not None:
-            lane.join()
         self._notify(G, G.total)
         return (None,), [G(p) for p in self.cached_params()]
 

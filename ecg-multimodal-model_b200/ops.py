@@ -26,6 +26,11 @@ def _chk(t: torch.Tensor, dtype, name: str):
         raise lib.EcgmmError(f"{name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise lib.EcgmmError(f"{name} must be contiguous")
+    if t.device.type == "cuda" and t.device.index != _cur_device():
+        # kernels and TMA descriptors are issued on the CURRENT device's stream: a tensor of another device would be
+        # a fault or a silent peer access (torch operators switch device themselves; this library does not)
+        raise lib.EcgmmError(f"{name} lives on cuda:{t.device.index} but the current device is cuda:{_cur_device()}; "
+                             "call torch.cuda.set_device() (one process per GPU) before using ecgmm")
 
 
 _raw_stream = torch._C._cuda_getCurrentRawStream

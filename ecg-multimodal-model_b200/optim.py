@@ -107,9 +107,11 @@ class Adam(torch.optim.Optimizer):
                          state_dev.data_ptr(), self.grad_scale, ops._s())
                 torch.autograd.graph.increment_version([e[0] for e in entries])
                 continue
-            for stp in sorted(steps):
+            for ordinal, stp in enumerate(sorted(steps)):
                 sub = [e for e in entries if int(self.state[e[0]]["step"]) == stp]
-                table, n = self._table((gi, stp if len(steps) > 1 else -1), sub)
+                # cache slot = (group, ordinal of the sub-group): the step count itself changes every step and would
+                # rebuild (and leak) one table per step
+                table, n = self._table((gi, ordinal if len(steps) > 1 else -1), sub)
                 lib.call("ecgmm_adam_step", ctypes.c_void_p(table.data_ptr()), n, float(group["lr"]), float(b1),
                          float(b2), float(group["eps"]), float(group["weight_decay"]), stp, self.grad_scale, ops._s())
             torch.autograd.graph.increment_version([e[0] for e in entries])

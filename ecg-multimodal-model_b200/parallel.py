@@ -11,6 +11,12 @@ NCCL's own stream, which orders itself after the kernels launched so far), so th
 encoder's layer4/layer3/layer2 gradients travel over NVLink while layer1 and the stem are still
 in backward.  A callback queued on the autograd engine waits for the outstanding collectives at
 the end of backward(), so optimizer.step() may follow immediately, as in train.py:80-81.
+
+The in-place all-reduce of the arena is only the gradient when autograd ADOPTS the arena slices as p.grad, i.e. when
+p.grad was None (optimizer.zero_grad() default).  When a stage's parameters already carry gradients -- accumulation
+under no_sync(), zero_grad(set_to_none=False) -- autograd adds the arena into p.grad instead, so for that stage the
+wrapper does what torch DDP does: it leaves the arena alone during backward and all-reduces the ACCUMULATED p.grad
+tensors in the end-of-backward callback (one flat collective, no overlap: the slow but correct path).
 """
 from __future__ import annotations
 
@@ -26,6 +32,7 @@ class DataParallel(torch.nn.Module):
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.min_bucket = int(min_bucket_elems)
         self._pending = []
+        self._deferred = []  # parameters whose accumulated .grad is reduced at the end of backward
         self._cb_queued = False
         self._enabled = True
         self.buckets_last_step = 0
@@ -35,25 +42,34 @@ class DataParallel(torch.nn.Module):
                 for t in list(module.parameters()) + list(module.buffers()):
                     dist.broadcast(t, src=0, group=process_group)
         for st in module.stages():
-            object.__setattr__(st, "_grad_ready_cb", self._on_ready)
+            object.__setattr__(st, "_grad_ready_cb", lambda arena, upto, _st=st: self._on_ready(arena, upto, _st))
 
     def forward(self, *a, **k):
         self._pending.clear()
+        self._deferred.clear()
         self._cb_queued = False
         self.buckets_last_step = 0
         self.bytes_last_step = 0
         return self.module(*a, **k)
 
     # ---- called by the stages during backward
-    def _on_ready(self, arena, upto):
+    def _on_ready(self, arena, upto, stage=None):
         if self.world <= 1 or not self._enabled:
             return
-        start = getattr(arena, "_dp_sent", 0)  # progress lives on the arena itself (arenas are per-backward objects)
-        final = upto >= arena.total
-        if upto - start <= 0 or (upto - start < self.min_bucket and not final):
-            return
-        arena._dp_sent = upto
-        self._launch(arena.flat[start:upto], keep=arena)
+        mode = getattr(arena, "_dp_deferred", None)  # decided once per arena (arenas are per-backward objects)
+        if mode is None:
+            params = stage.cached_params() if hasattr(stage, "cached_params") else ()
+            held = [p for p in params if p.requires_grad and p.grad is not None]
+            mode = arena._dp_deferred = bool(held)
+            if mode:  # autograd will ADD this arena into the existing p.grad: reduce p.grad itself, afterwards
+                self._deferred.extend(p for p in params if p.requires_grad)
+        if not mode:
+            start = getattr(arena, "_dp_sent", 0)  # progress lives on the arena itself
+            final = upto >= arena.total
+            if upto - start <= 0 or (upto - start < self.min_bucket and not final):
+                return
+            arena._dp_sent = upto
+            self._launch(arena.flat[start:upto], keep=arena)
         if not self._cb_queued:
             try:  # end-of-backward hook (the mechanism DDP uses); outside backward the caller runs finish()
                 torch.autograd.Variable._execution_engine.queue_callback(self.finish)
@@ -92,6 +108,21 @@ class DataParallel(torch.nn.Module):
                 flat.div_(self.world)
         self._pending.clear()
         self._cb_queued = False
+        if self._deferred:  # runs after every AccumulateGrad of this backward (engine final callback)
+            seen, grads = set(), []
+            for p in self._deferred:
+                if id(p) not in seen and p.grad is not None:
+                    seen.add(id(p))
+                    grads.append(p.grad)
+            self._deferred.clear()
+            if grads:
+                flat = torch._utils._flatten_dense_tensors(grads)
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+                flat.div_(self.world)
+                for g, r in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                    g.copy_(r)
+                self.buckets_last_step += 1
+                self.bytes_last_step += flat.numel() * flat.element_size()
 
 
 def shard_batch(tensors, rank, world):

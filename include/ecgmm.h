@@ -40,11 +40,6 @@ unsigned long long ecgmm_launch_count(void);
 /* 0 when the current device can run the library (compute capability 10.x). */
 int ecgmm_check_device(void);
 
-/* Development probe (tools/desc_probe.py): one tcgen05.mma whose SWIZZLE_128B A descriptor starts
- * `shift` 128-byte rows into a TMA-written tile.  mode bit0: MN-major operands; bit1: set base-offset;
- * bit2: N = 192 MN-major B operand whose three 64-wide atoms overlap at a 128-byte pitch (out is then [128][192]). */
-int ecgmm_debug_desc_probe(const ecgmm_bf16* a, const ecgmm_bf16* b, float* out, int shift, int mode, void* stream);
-
 /* ------------------------------------------------------------------ layout / precision */
 
 /* NCHW fp32 -> NHWC bf16 (and back).  Replaces the implicit layout of every torch tensor the
@@ -222,9 +217,11 @@ int ecgmm_var_loss_fwd(const float* f0, const float* f1, const float* f2, float*
 int ecgmm_var_loss_bwd(const float* f, const float* row_mean, const float* coef, const float* gout, float* df, int B,
                        int D, int accumulate, void* stream);
 /* mean softmax cross entropy (focal == 0) or focal loss alpha(1-pt)^gamma ce (focal == 1);
- * dlogits (may be NULL) = gscale * dloss/dlogits.  *bad_label is set to 1 on an out-of-range label. */
+ * dlogits (may be NULL) = gscale * dloss/dlogits.  Rows labelled ignore_index are skipped as torch does (zero gradient;
+ * CrossEntropyLoss averages over the remaining rows, the focal loss over all rows).  Any other label outside [0, C):
+ * *bad_label (may be NULL) is set to 1, the row's gradient is zero and the loss is NaN (torch: device-side assert). */
 int ecgmm_ce_loss(const float* logits, const long long* labels, float* loss, float* dlogits, int B, int C, int focal,
-                  float alpha, float gamma, float gscale, int* bad_label, void* stream);
+                  float alpha, float gamma, float gscale, long long ignore_index, int* bad_label, void* stream);
 /* y = x*mask; mask_in given (0 or 1/(1-p)) or drawn from (seed, element index); mask_out may be NULL.
  * seed_dev (may be NULL): device word added to seed at run time -- the per-step offset of a captured CUDA graph */
 int ecgmm_dropout_fwd(const float* x, const float* mask_in, float* y, float* mask_out, long long n, float p,

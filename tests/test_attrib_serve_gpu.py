@@ -1,9 +1,6 @@
 """GPU: expected gradients / modality shares and the image endpoint with Grad-CAM (rank 4)
-against the oracle.  Written after the round's GPU budget was spent: the kernels (csrc/attrib.cu) are small
-bandwidth-bound ones and the glue was dry-run on the CPU (tests/test_control_flow_cpu.py), but none of this has run on
-hardware yet -- hence the file name, which makes pytest collect it LAST, and the ECGMM_TEST_EXPERIMENTAL=1 gate:
-the suite the driver runs at the end of a round stays the one that has been green on hardware, and
-tools/r02_first_call.sh runs this file (with the gate open) first thing in the next round."""
+against the oracle (first green on a B200 in round 2, gpurun_out/r02a_zz_tests.log; part of the default GPU suite)."""
+
 import os
 
 import pytest
@@ -13,9 +10,7 @@ from ecgmm import explain, lib, serve
 from oracle import model as om
 from parity_util import build_pair
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ECGMM_TEST_EXPERIMENTAL") != "1",
-                                 reason="attribution / serving rows: written without hardware, not yet validated")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
@@ -141,14 +136,8 @@ def test_image_endpoint_cuda_graph_replay():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# Fused folded-BatchNorm epilogue (ecgmm_conv2d_fwd_bn, ECGMM_SERVE_FUSED=1): touches the tcgen05 kernels' epilogues
-# (separate template instantiations; the training instantiations' SASS is unchanged) and is off by default, so its
-# tests run only with ECGMM_TEST_EXPERIMENTAL=1 until it has been on hardware once (tools/r02_first_call.sh).
-_experimental = pytest.mark.skipif(os.environ.get("ECGMM_TEST_EXPERIMENTAL") != "1",
-                                   reason="ecgmm_conv2d_fwd_bn is a round-2 work item: not yet validated on hardware")
-
-
-@_experimental
+# Fused folded-BatchNorm epilogue (ecgmm_conv2d_fwd_bn, the serving default): separate template instantiations of the
+# tcgen05 kernels (the training instantiations' SASS is unchanged).
 @pytest.mark.parametrize("case", [
     # N, H, W, Cin, Cout, R, stride, residual, relu          kernel
     (2, 16, 160, 64, 64, 3, 1, True, True),      # halo kernel, residual through the TMA prefetch
@@ -159,7 +148,7 @@ _experimental = pytest.mark.skipif(os.environ.get("ECGMM_TEST_EXPERIMENTAL") != 
     (2, 4, 10, 256, 256, 3, 1, True, True),      # generic N=256
     (1, 2, 5, 512, 512, 3, 1, True, False),      # two N tiles
 ], ids=lambda c: "x".join(str(v) for v in c))
-def test_experimental_conv_bn_epilogue(case):
+def test_conv_bn_epilogue(case):
     from ecgmm import ops
 
     N, H, W, Cin, Cout, R, stride, with_res, relu = case
@@ -185,11 +174,11 @@ def test_experimental_conv_bn_epilogue(case):
     assert float((err / (1.0 + ref.abs())).max()) <= 1e-2  # one bf16 rounding of the result
 
 
-@_experimental
-def test_experimental_fused_endpoint_matches_unfused(monkeypatch):
+def test_fused_endpoint_matches_unfused(monkeypatch):
     ora, dut = build_pair(seed=7)
     dut.eval()
     u8, _ = _images(3, 64, 160, seed=4)
+    monkeypatch.setattr(serve, "FUSED_EPILOGUE", False)
     plain = [t.clone() for t in serve.ImageEndpoint(dut, graph=False, class_index=1).gradcam(u8.to(DEV))]
     n0 = lib.launch_count()
     serve.ImageEndpoint(dut, graph=False, class_index=1).gradcam(u8.to(DEV))

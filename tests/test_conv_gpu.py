@@ -35,6 +35,7 @@ def test_wgrad_both_mma_widths(case, bn, monkeypatch):
     from ecgmm import ops
 
     monkeypatch.setenv("ECGMM_WG_BN", bn)
+    monkeypatch.setenv("ECGMM_WG_T", "0")  # the default for these layers is the transposed kernel (next test)
     ops._SHAPE_CACHE.clear()  # workspace sizes depend on the shape
     results = []
     assert chk.run_case(*case, results=results)
@@ -43,13 +44,12 @@ def test_wgrad_both_mma_widths(case, bn, monkeypatch):
     ops._SHAPE_CACHE.clear()
 
 
-@pytest.mark.skipif(os.environ.get("ECGMM_TEST_EXPERIMENTAL") != "1",
-                    reason="the transposed weight gradient is a round-2 work item: not yet validated on hardware")
 @pytest.mark.parametrize("case", [c for c in chk.CASES if c[6] == 3 and c[7] == 3 and c[8] == 1 and c[5] % 128 == 0],
                          ids=lambda c: c[0] if isinstance(c, tuple) else str(c))
-def test_experimental_transposed_wgrad(case, monkeypatch):
-    """ECGMM_WG_T=1: M = 128 output channels x N = 192 (three horizontal taps x 64 input channels) MMAs, two CTA types
-    (wgrad_halo_kernel<128, true>); bookkeeping emulated in tests/test_wgrad_t_emulation_cpu.py."""
+def test_transposed_wgrad(case, monkeypatch):
+    """The default for 3x3 layers with Cout % 128 == 0: M = 128 output channels x N = 192 (three horizontal taps x 64
+    input channels) MMAs, two CTA types (wgrad_halo_kernel<128, true>); bookkeeping emulated in
+    tests/test_wgrad_t_emulation_cpu.py.  (test_layer_case runs it too; this test pins the switch explicitly.)"""
     from ecgmm import ops
 
     monkeypatch.setenv("ECGMM_WG_T", "1")
@@ -88,15 +88,15 @@ def test_conv_is_linear_at_full_size():
     assert float(z.float().abs().max()) == 0.0
 
 
-@pytest.mark.skipif(os.environ.get("ECGMM_TEST_EXPERIMENTAL") != "1",
-                    reason="conv_nt_stack.cu is a round-2 work item: compiled, not yet validated on hardware")
+@pytest.mark.parametrize("stack", ["1", "0"], ids=["rolling_accumulators", "halo_kernel"])
 @pytest.mark.parametrize("case", [("stack_63x625", 2, 63, 625, 64, 64, 3, 3, 1), ("stack_ragged", 3, 21, 150, 64, 64, 3, 3, 1),
                                   ("stack_one_row", 2, 1, 200, 64, 64, 3, 3, 1), ("stack_two_rows", 1, 2, 130, 64, 64, 3, 3, 1)],
                          ids=lambda c: c[0])
-def test_experimental_rolling_accumulator_kernel(case, monkeypatch):
+def test_layer1_kernels(case, stack, monkeypatch):
     """Forward, data-gradient and accumulating data-gradient of the 64 -> 64 3x3 layers through igemm_nt_stack_kernel
-    (ECGMM_NT_STACK=1): N = 192 MMAs into a ring of output-row accumulators in TMEM."""
-    monkeypatch.setenv("ECGMM_NT_STACK", "1")
+    (the default: N = 192 MMAs into a ring of output-row accumulators in TMEM) and through igemm_nt_halo_kernel
+    (ECGMM_NT_STACK=0)."""
+    monkeypatch.setenv("ECGMM_NT_STACK", stack)
     results = []
     assert chk.run_case(*case, results=results, do=("fwd", "dgrad"))
     bad = [r for r in results if not r[2]]

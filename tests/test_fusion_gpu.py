@@ -241,14 +241,3 @@ def test_uint8_images_equal_normalised_tensors():
     for x, y, z in zip(a, b, r):
         assert torch.equal(x, y)
         assert relmax(x, z) <= OUT_TOL
-
-
-@pytest.mark.skipif(os.environ.get("ECGMM_TEST_EXPERIMENTAL") != "1",
-                    reason="ECGMM_WGRAD_STREAM is a round-2 work item: not yet validated / measured on hardware")
-def test_experimental_wgrad_lane_keeps_parity(monkeypatch):
-    """Weight gradients on their own stream underneath the BatchNorm-backward kernels (model._WgradLane)."""
-    from ecgmm import model as M
-
-    monkeypatch.setattr(M, "WGRAD_STREAM", True)
-    rep = run_fusion_parity(B=4, H=64, W=160, L=600, train=True)
-    assert rep["ok"], rep["failures"][:10]

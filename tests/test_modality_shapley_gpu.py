@@ -1,8 +1,5 @@
 """GPU: exact modality Shapley values -- ecgmm.explain.modality_shapley against the
-oracle's enumeration.  Written after the round's GPU budget was spent: it composes GPU-verified pieces (the perturbation
-inference path and the small SGEMM) and was dry-run on the CPU with those two calls replaced by their oracle
-counterparts, but it has not run on hardware yet -- hence the file name, which makes pytest collect it LAST."""
-import os
+oracle's enumeration (first green on a B200 in round 2, gpurun_out/r02a_zz_tests.log)."""
 
 import pytest
 import torch
@@ -11,11 +8,7 @@ from ecgmm import explain, lib
 from oracle import model as om
 from parity_util import build_pair
 
-# gated like every row written without hardware: the round-end suite stays the one that has been green on a B200;
-# tools/r02_first_call.sh opens the gate
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ECGMM_TEST_EXPERIMENTAL") != "1",
-                                 reason="modality Shapley values: written without hardware, not yet validated")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 

@@ -140,6 +140,91 @@ def test_param_grads_alias_the_arena():
     assert torch.equal(w.grad, torch.full((5, 3), 0.5)) and torch.equal(b.grad, torch.full((7,), 1.0))
 
 
+def _accum_worker(rank, world, port, q):
+    """Gradient accumulation: a micro-batch under no_sync(), then a synchronising one; and zero_grad(set_to_none=False).
+    In both cases p.grad exists when backward runs, so autograd ADDS the arena into it: the wrapper must reduce the
+    accumulated p.grad (torch DDP semantics), not the arena."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ecgmm.model import GradArena
+        from ecgmm.parallel import DataParallel
+
+        class Stage:
+            def __init__(self):
+                self.w = torch.nn.Parameter(torch.zeros(5, 3))
+                self.b = torch.nn.Parameter(torch.zeros(7))
+
+            def cached_params(self):
+                return [self.w, self.b]
+
+        class Model(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.st = Stage()
+                self.w, self.b = self.st.w, self.st.b
+
+            def stages(self):
+                return [self.st]
+
+            def forward(self, x, scale):
+                st = self.st
+
+                class Fn(torch.autograd.Function):
+                    @staticmethod
+                    def forward(ctx, x_, w_, b_):
+                        return x_.clone()
+
+                    @staticmethod
+                    def backward(ctx, g):
+                        G = GradArena([st.w, st.b], torch.device("cpu"))
+                        G(st.w).fill_(scale * (rank + 1))       # rank0: s, rank1: 2s -> mean 1.5 s
+                        G(st.b).fill_(10 * scale * (rank + 1))  # mean 15 s
+                        st._grad_ready_cb(G, G.end_of(st.b))    # a prefix bucket ...
+                        st._grad_ready_cb(G, G.total)           # ... and the rest
+                        return g, G(st.w), G(st.b)
+
+                return Fn.apply(x, st.w, st.b)
+
+        m = Model()
+        dp = DataParallel(m)
+        x = torch.ones(2, requires_grad=True)
+        # (1) plain step: arena adopted, reduced in place, two buckets
+        dp(x, 1.0).sum().backward()
+        ok = bool(torch.allclose(m.w.grad, torch.full((5, 3), 1.5)) and torch.allclose(m.b.grad, torch.full((7,), 15.0)))
+        ok = ok and dp.buckets_last_step == 2
+        # (2) accumulate: micro-batch 1 local (scale 1), micro-batch 2 synchronising (scale 3) -> mean of (1+3)*(rank+1)
+        m.w.grad = m.b.grad = None
+        with dp.no_sync():
+            dp(x, 1.0).sum().backward()
+        ok = ok and bool(torch.allclose(m.w.grad, torch.full((5, 3), float(rank + 1))))
+        dp(x, 3.0).sum().backward()
+        ok = ok and bool(torch.allclose(m.w.grad, torch.full((5, 3), 6.0)) and torch.allclose(m.b.grad, torch.full((7,), 60.0)))
+        ok = ok and dp.buckets_last_step == 1 and not dp._pending and not dp._deferred
+        # (3) zero_grad(set_to_none=False): p.grad is a zero tensor that autograd accumulates into
+        m.w.grad.zero_()
+        m.b.grad.zero_()
+        dp(x, 2.0).sum().backward()
+        ok = ok and bool(torch.allclose(m.w.grad, torch.full((5, 3), 3.0)) and torch.allclose(m.b.grad, torch.full((7,), 30.0)))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_accumulated_grads_are_reduced_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_accum_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
+
+
 def test_folds_are_partitioned_over_ranks():
     from ecgmm.parallel import folds_for_rank
 

@@ -87,13 +87,12 @@ def test_shape_errors():
         pp.preprocess_signal(torch.zeros(2, 300, device="cuda", dtype=torch.float16))
 
 
-@pytest.mark.skipif(os.environ.get("ECGMM_TEST_EXPERIMENTAL") != "1",
-                    reason="signal_preprocess_block_kernel is a round-2 work item: not yet validated on hardware")
-def test_experimental_block_parallel_kernel(golden, monkeypatch):
-    """ECGMM_PREP_BLOCK=1: the time-parallel kernel (one CTA per signal, block-wise zero-state runs + a scan of the
-    block start states) against the same golden vectors and oracle, and against the serial kernel."""
+def test_block_parallel_kernel(golden, monkeypatch):
+    """The time-parallel kernel (the default; one CTA per signal, block-wise zero-state runs + a scan of the block
+    start states) against the same golden vectors and oracle, and against the serial kernel (ECGMM_PREP_BLOCK=0)."""
     from ecgmm import preprocess as pp
 
+    monkeypatch.setenv("ECGMM_PREP_BLOCK", "0")
     serial = {c: pp.preprocess_signal(torch.from_numpy(golden[f"{c}_x"]).cuda()) for c in ("l2476", "l5000")}
     monkeypatch.setenv("ECGMM_PREP_BLOCK", "1")
     for case in ("l2476", "l5000", "l200", "l333"):
@@ -117,5 +116,5 @@ def test_experimental_block_parallel_kernel(golden, monkeypatch):
         assert close(y.reshape(-1, shape[-1])[pick], want), shape
     # a badly conditioned design (narrow band) must fall back to the serial kernel: same numbers as without the switch
     y_blk = pp.lowpass_filter(x, cutoff=0.005, fs=1.0, order=5)
-    monkeypatch.delenv("ECGMM_PREP_BLOCK")
+    monkeypatch.setenv("ECGMM_PREP_BLOCK", "0")
     assert torch.equal(y_blk, pp.lowpass_filter(x, cutoff=0.005, fs=1.0, order=5))

@@ -1,4 +1,4 @@
-// Hardware probe (development / test only): can a SWIZZLE_128B shared-memory matrix descriptor
+// Hardware probe (development only): can a SWIZZLE_128B shared-memory matrix descriptor
 // start at an arbitrary 128-byte row of a TMA-written tile?  The halo-reuse convolution kernels
 // depend on the answer (a filter tap becomes a row offset into ONE staged input tile instead of
 // its own TMA load).  mode bit 0: 0 = K-major A (forward style), 1 = MN-major A (wgrad style);
@@ -8,8 +8,9 @@
 // B operand of an N = 192 MMA whose three atoms are the three horizontal filter taps (the same box read from pixel
 // s, s+1, s+2), which is what a transposed weight-gradient GEMM (M = Cout, N = taps x Cin) needs to leave the
 // shared-memory-bound M128 x N64 shape.  D[m][j*64 + c] = sum_{k<32} a[k][m] * a[k + shift + j][c]; out is [128][192].
-#include "common.h"
-#include "ptx.cuh"
+// Not part of libecgmm.so: tools/desc_probe.py compiles this file (+ csrc/common.cu) into tools/build/libecgmm_probe.so.
+#include "../../ecg-multimodal-model_b200/csrc/common.h"
+#include "../../ecg-multimodal-model_b200/csrc/ptx.cuh"
 
 namespace ecgmm {
 

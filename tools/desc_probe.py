@@ -1,16 +1,41 @@
-"""Runs ecgmm_debug_desc_probe for every (layout, base-offset mode, row shift) and reports which
-combinations reproduce the expected product.  Development tool (needs a B200)."""
+"""Runs the descriptor probe kernel (tools/csrc/desc_probe.cu) for every (layout, base-offset mode, row shift) and
+reports which combinations reproduce the expected product.  Development tool (needs a B200); the probe is built into
+its own shared library (tools/build/libecgmm_probe.so), it is not part of libecgmm.so or include/ecgmm.h.
+Last result: profiles/r02_desc_probe.txt."""
 import ctypes
 import os
+import subprocess
 import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
 import ecgmm  # noqa: E402
-from ecgmm import lib, ops  # noqa: E402
+from ecgmm import lib as _lib, ops  # noqa: E402
 
-lib.require_device()
+_lib.require_device()
+SO = os.path.join(HERE, "build", "libecgmm_probe.so")
+if not os.path.exists(SO):
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    csrc = os.path.join(ROOT, "ecg-multimodal-model_b200", "csrc")
+    subprocess.run(["/usr/local/cuda/bin/nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+                    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-cudart", "static", "-shared",
+                    "-I", os.path.join(ROOT, "include"), "-o", SO, os.path.join(HERE, "csrc", "desc_probe.cu"),
+                    os.path.join(csrc, "common.cu")], check=True)
+_so = ctypes.CDLL(SO)
+_so.ecgmm_debug_desc_probe.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2 + [ctypes.c_void_p]
+
+
+class lib:  # same call shape as ecgmm.lib.call
+    @staticmethod
+    def call(name, *args):
+        rc = getattr(_so, name)(*args)
+        if rc != 0:
+            raise RuntimeError(f"{name} failed with status {rc}")
+
+
 g = torch.Generator().manual_seed(0)
 a = torch.randn(160, 128, generator=g).cuda().to(torch.bfloat16)
 for mn in (0, 1):

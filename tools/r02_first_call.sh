@@ -73,6 +73,6 @@ run ref_arm  300 python bench.py --impl reference --steps 2 --warmup 1
 
 # --- ncu launch list of the bench command itself (per-launch times are cold-cache and serialised: only each kernel's
 # SHARE of the step is comparable with the CUDA-event numbers of the plain run above)
-run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -c 6000 \
+[ "${ECGMM_FIRSTCALL_NCU:-0}" = 1 ] && run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -c 6000 \
     --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --launch eager
 cat $O/${TAG}_index.log
