@@ -34,11 +34,18 @@ CONV_GFLOP_TRAIN_PER_SAMPLE = 135.642
 CONFIG_NAME = "configs[2]: full multimodal training step, 3x250x2500 bf16 images, global batch 512, data-parallel"
 
 
-def synth_batch(B, seed, pinned=False):
+def synth_batch(B, seed, pinned=False, image_dtype="uint8"):
+    """SURVEY.md section 8d cfg3 inputs.  image_dtype: what the loader hands over -- "uint8" (default: the 8-bit pixels
+    the reference's ToTensor + Normalize(0.5, 0.5) starts from, dataset.py:119-123; the normalisation runs inside the
+    first kernel, bit-identical to the host transform), "fp32" (the reference loader's own output) or "bf16"."""
     import torch
 
     g = torch.Generator().manual_seed(seed)
-    image = torch.randn(B, 3, H, W, generator=g).clamp_(-1, 1).to(torch.bfloat16)
+    image = torch.randn(B, 3, H, W, generator=g).clamp_(-1, 1)
+    if image_dtype == "uint8":
+        image = image.mul_(127.5).add_(127.5).round_().clamp_(0, 255).to(torch.uint8)
+    elif image_dtype == "bf16":
+        image = image.to(torch.bfloat16)
     ecg = torch.randn(B, L, generator=g)
     clin = torch.randn(B, F, generator=g)
     labels = (torch.rand(B, generator=g) < 0.4).long()  # 88/220 abnormal in the reference data set
@@ -109,8 +116,7 @@ def cpu_reference_steps(steps, warmup, batch):
     m = om.ECGMultimodalModel()
     m.train()
     opt = torch.optim.Adam(m.parameters(), lr=1e-4)
-    image, ecg, clin, labels = synth_batch(batch, 42)
-    image = image.float()
+    image, ecg, clin, labels = synth_batch(batch, 42, image_dtype="fp32")
     for _ in range(warmup):
         om.fusion_train_step(m, opt, image, ecg, clin, labels)
     t0 = time.perf_counter()
@@ -194,9 +200,8 @@ def run_ours(args):
     crit = enn.CrossEntropyLoss()
     opt = eoptim.Adam(model.parameters(), lr=1e-4)
 
-    host = synth_batch(B, 42 + rank, pinned=True)
+    host = synth_batch(B, 42 + rank, pinned=True, image_dtype=args.image_dtype)
     resident = [t.to(dev) for t in host]
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
 
     def step(batch):
         image, ecg, clin, labels = batch
@@ -277,22 +282,24 @@ def run_ours(args):
     value = gb / (ms_per_step / 1e3)
     host_enqueue_ms = host_ms["last"]
 
-    # ---- end to end: pinned host batch -> device every step, loss read back every step.
-    # Double-buffered: the H2D copy of step i+1 runs on a copy stream while step i computes; every
-    # copy and every loss read-back happens inside the timed region.
-    bufs = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
-    copy_stream = torch.cuda.Stream()
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    # ---- end to end through the public API: the loop of train.py:60-86 over ecgmm.data.Prefetcher (pinned host batch
+    # -> device every step on a copy stream, double-buffered, overlapping the previous step) + the loss read back every
+    # step; every copy and every read-back happens inside the timed region.
+    from ecgmm.data import Prefetcher
+
+    class HostLoader:  # a "DataLoader" that yields the same pinned host batch n times
+        def __init__(self, n):
+            self.n = n
+
+        def __len__(self):
+            return self.n
+
+        def __iter__(self):
+            return iter([host] * self.n)
+
+    prefetch = Prefetcher(HostLoader(0), dev, depth=2)
     last = {}
     state = {"i": 0}
-
-    def issue_copy(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])  # the step that last used this slot has finished with it
-            for d, h in zip(bufs[slot], host):
-                d.copy_(h, non_blocking=True)
-            ready[slot].record(copy_stream)
 
     # The loss of step i is copied D2H (pinned scalar, enqueued right behind the step) and READ by the host while step
     # i+1 runs: every step's loss is read inside the timed region, but the host never sits between two steps waiting
@@ -302,13 +309,10 @@ def run_ours(args):
     loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step():
+    def e2e_step(batch):
         i = state["i"]
         slot = i & 1
-        torch.cuda.current_stream().wait_event(ready[slot])
-        issue_copy(slot ^ 1)  # prefetch the next step's batch
-        loss = step(bufs[slot])
-        consumed[slot].record()
+        loss = step(batch)
         if sync_loss:
             last["loss"] = float(loss.item())  # D2H read of the step's result
         else:
@@ -321,11 +325,9 @@ def run_ours(args):
 
     def e2e_run(steps):
         state["i"] = 0
-        for ev in consumed:
-            ev.record()
-        issue_copy(0)
-        for _ in range(steps):
-            e2e_step()
+        prefetch.loader = HostLoader(steps)
+        for batch in prefetch:
+            e2e_step(batch)
         if not sync_loss and steps > 0:  # the last step's loss
             s_last = (state["i"] - 1) & 1
             loss_ev[s_last].synchronize()
@@ -339,17 +341,24 @@ def run_ours(args):
         sync_loss = True
         torch.cuda.synchronize()
         e2e_run(2)
+    h2d0 = prefetch.h2d_bytes
     e2e_ms = timed(lambda: e2e_run(args.steps), 1) / args.steps
+    h2d_per_step = (prefetch.h2d_bytes - h2d0) / args.steps
     e2e_value = gb / (e2e_ms / 1e3)
     clocks = sampler.stop() if sampler else None
 
     # ---- per-kernel-class device times over one more (eager) step (CUDA events on the launching stream)
     if launch == "cuda_graph":
         step = eager_step
+    # (the signal / clinical branches normally run on a side stream underneath the image encoder; for this pass they
+    # are serialised onto the main stream, otherwise an event pair around a small side-stream kernel also measures the
+    # time it waited for SMs and pollutes its class)
+    overlap, model.overlap_branches = model.overlap_branches, False
     ops.PROFILE = []
     step(resident)
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
+    model.overlap_branches = overlap
     n0 = lib.launch_count()
     step(resident)  # kernels of one step, counted by the library (a graph replay re-issues exactly these)
     torch.cuda.synchronize()
@@ -464,9 +473,12 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": CONFIG_NAME, "image": [3, H, W], "signal_len": L, "clinical_features": F,
                    "global_batch": gb, "per_gpu_batch": B, "parallelism": f"dp{world}", "launch": launch,
+                   "image_input": {"uint8": "uint8 pixels; ToTensor + Normalize(0.5, 0.5) fused into the first kernel",
+                                   "fp32": "fp32 normalised tensors (the reference loader's output)",
+                                   "bf16": "bf16 normalised tensors"}[args.image_dtype],
                    "l2": "per-step working set (>= 7 GB of activations per GPU) exceeds the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": h2d_bytes * world * (args.steps + 1) / args.steps,
+                "h2d_bytes_per_step": h2d_per_step * world, "api": "ecgmm.data.Prefetcher + the train.py loop body",
                 "d2h_bytes_per_step": 4 * world, "last_loss": last.get("loss"),
                 "loss_read": "blocking" if sync_loss else "pipelined: step i's loss read while step i+1 runs",
                 "note": e2e_note},
@@ -496,6 +508,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--image-dtype", default="uint8", choices=["uint8", "fp32", "bf16"],
+                    help="what the loader hands over (host side of e2e and the resident batch alike)")
     ap.add_argument("--detail", action="store_true", help="per-shape kernel timings on stderr")
     ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
                     help="graph: the training step replayed as one CUDA graph (ecgmm.graph); eager: kernel by kernel")

@@ -10,9 +10,9 @@ Import name: ``ecgmm`` (the directory is ``ecg-multimodal-model_b200``; the root
 """
 from . import lib  # noqa: F401
 from . import ops  # noqa: F401
-from . import explain, graph, model, nn, optim, preprocess, serve  # noqa: F401
+from . import data, explain, graph, model, nn, optim, preprocess, serve  # noqa: F401
 from .model import ECGMultimodalModel, FusionClassifierWrapper, MultimodalModel, ResNet1D_SE, ResNet18  # noqa: F401
 from .nn import CrossEntropyLoss, FocalLoss  # noqa: F401
 
-__all__ = ["lib", "ops", "model", "nn", "optim", "preprocess", "explain", "graph", "serve", "ECGMultimodalModel", "MultimodalModel", "ResNet1D_SE", "ResNet18",
+__all__ = ["lib", "ops", "data", "model", "nn", "optim", "preprocess", "explain", "graph", "serve", "ECGMultimodalModel", "MultimodalModel", "ResNet1D_SE", "ResNet18",
            "FusionClassifierWrapper", "CrossEntropyLoss", "FocalLoss"]

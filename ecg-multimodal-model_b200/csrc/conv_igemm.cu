@@ -417,7 +417,8 @@ static bool nt_stack_enabled() {
   return !(e && atoi(e) == 0);
 }
 int launch_nt_stack(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int dgrad,
-                    int accumulate, cudaStream_t st);
+                    int accumulate, cudaStream_t st, float* psum = nullptr, float* psq = nullptr);
+int nt_stack_stats_rows(int N, int H, int W);
 }  // namespace ecgmm
 
 // Rows of the statistics partials the forward kernel writes for this shape (4 epilogue warps per CTA of the generic
@@ -428,6 +429,8 @@ int launch_nt_stack(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat1
 extern "C" int ecgmm_conv2d_fwd_stats_rows(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int padH,
                                            int padW) {
   if (N <= 0 || check_conv_cfg(Cin, Cout, R, S, stride, padH, padW)) return 0;
+  // the rolling-accumulator kernel keeps the sums in registers (one row of partials per CTA)
+  if (nt_stack_enabled() && nt_stack_supported(Cin, Cout, R, S, stride, W)) return nt_stack_stats_rows(N, H, W);
   if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY")) return 0;
   if (R * S * Cin < 1152) return 0;
   const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
@@ -455,11 +458,14 @@ static int conv2d_fwd_impl(const ecgmm_bf16* x_, const ecgmm_bf16* w_, ecgmm_bf1
   if (N == 0) return ECGMM_OK;
   if (!fe.scale && nt_stack_enabled() && nt_stack_supported(Cin, Cout, R, S, stride, W))
     return launch_nt_stack(reinterpret_cast<const __nv_bfloat16*>(x_), reinterpret_cast<const __nv_bfloat16*>(w_),
-                           reinterpret_cast<__nv_bfloat16*>(y_), N, H, W, 0, 0, static_cast<cudaStream_t>(stream));
-  if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY"))
+                           reinterpret_cast<__nv_bfloat16*>(y_), N, H, W, 0, 0, static_cast<cudaStream_t>(stream), psum,
+                           psq);
+  if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY")) {
+    ECGMM_CHECK(!psum, ECGMM_ERR_SHAPE, "conv2d_fwd_stats: not offered for this shape (see ecgmm_conv2d_fwd_stats_rows)");
     return launch_nt_halo(reinterpret_cast<const __nv_bfloat16*>(x_), reinterpret_cast<const __nv_bfloat16*>(w_),
                           reinterpret_cast<__nv_bfloat16*>(y_), N, H, W, R, S, 0, 0, static_cast<cudaStream_t>(stream),
                           fe.scale, fe.shift, fe.res, fe.relu);
+  }
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(x_);
   const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
   NtParams p;
@@ -619,6 +625,7 @@ struct alignas(64) TnParams {
   int slots_per_group, n_groups_m, n_tiles_n, ksplit;
   int TH, TW, tiles_h, tiles_w, n_img, total_kblocks;
   float* dw;
+  float* ws;  // split-K partials [CTA][slot][128 rows][BN] (deterministic fold by tn_reduce_kernel); NULL: fp32 atomics
   int Cin, Cout, RS;
   int mode;  // 0: dw is OIHW [Cout][Cin][R][S];  1: ResNet stem (space-to-depth atoms -> [64][3][7][7])
 };
@@ -766,6 +773,21 @@ __global__ void __launch_bounds__(192, 1) igemm_tn_kernel(const __grid_constant_
           col_stride = 147;
         }
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + i * BN;
+        if (p.ws) {  // deterministic path: this CTA's partial tile goes to the workspace as it is
+          float4* dst = reinterpret_cast<float4*>(
+              p.ws + (((size_t)blockIdx.x * p.slots_per_group + i) * 128 + m_row) * BN);
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_addr + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[c * 8 + j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          }
+          continue;
+        }
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
@@ -786,16 +808,42 @@ __global__ void __launch_bounds__(192, 1) igemm_tn_kernel(const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-template <int BN, int SMAX, int STAGES>
-static int launch_tn_t(TnParams& p, cudaStream_t s) {
-  using L = TnSmem<BN, SMAX, STAGES>;
-  static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
-  const int ds = device_slot();
-  if (!configured[ds]) {
-    ECGMM_CUDA(cudaFuncSetAttribute(igemm_tn_kernel<BN, SMAX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    L::kBytes));
-    configured[ds] = true;
+// Fixed-order fold of the split-K partials written by igemm_tn_kernel (mode 0): one thread per dW element of a slot
+// group, partials added in k-split order, then ONE += into dw -- bit-reproducible, unlike the atomics it replaces.
+__global__ void __launch_bounds__(256) tn_reduce_kernel(TnParams p, int BN) {
+  const long long per_group = (long long)p.slots_per_group * 128 * BN;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per_group * p.n_groups_m * p.n_tiles_n) return;
+  const int g = (int)(idx / per_group);
+  long long rem = idx - (long long)g * per_group;
+  const int i = (int)(rem / (128 * BN));
+  rem -= (long long)i * 128 * BN;
+  const int m_row = (int)(rem / BN), col = (int)(rem - (long long)m_row * BN);
+  const int gm = g % p.n_groups_m, nt = g / p.n_groups_m;
+  const int s0 = gm * p.slots_per_group;
+  if (i >= min(p.slots_per_group, p.n_slots - s0)) return;
+  const int atom = 2 * (s0 + i) + (m_row >> 6);
+  if (atom >= p.n_atoms) return;
+  const int tap = atom / p.cin_chunks, cc = atom - tap * p.cin_chunks;
+  const int cin = cc * 64 + (m_row & 63), cout = nt * BN + col;
+  const int per = (p.total_kblocks + p.ksplit - 1) / p.ksplit;
+  const int n_ks = min(p.ksplit, (p.total_kblocks + per - 1) / per);  // CTAs with ks >= n_ks had no pixel block
+  const size_t stride = (size_t)p.slots_per_group * 128 * BN;
+  const float* src = p.ws + (size_t)g * p.ksplit * stride + ((size_t)i * 128 + m_row) * BN + col;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  for (; k + 3 < n_ks; k += 4) {
+    a0 += src[(size_t)k * stride];
+    a1 += src[(size_t)(k + 1) * stride];
+    a2 += src[(size_t)(k + 2) * stride];
+    a3 += src[(size_t)(k + 3) * stride];
   }
+  for (; k < n_ks; ++k) a0 += src[(size_t)k * stride];
+  p.dw[((size_t)cout * p.Cin + cin) * p.RS + p.taps[tap].id] += (a0 + a1) + (a2 + a3);
+}
+
+// Decomposition shared by the launch and the workspace query.
+static void tn_plan(TnParams& p, int BN, int SMAX) {
   p.n_atoms = p.ntaps * p.cin_chunks;
   p.n_slots = (p.n_atoms + 1) / 2;
   p.n_groups_m = ceil_div(p.n_slots, SMAX);
@@ -806,8 +854,34 @@ static int launch_tn_t(TnParams& p, cudaStream_t s) {
   if (ksplit < 1) ksplit = 1;
   if (ksplit > p.total_kblocks) ksplit = p.total_kblocks;
   p.ksplit = ksplit;
-  igemm_tn_kernel<BN, SMAX, STAGES><<<groups * ksplit, 192, L::kBytes, s>>>(p);
-  return check_launch("igemm_tn_kernel");
+}
+static void tn_shape(int Cout, int* BN, int* SMAX) {
+  if (Cout % 256 == 0) { *BN = 256; *SMAX = 2; }
+  else if (Cout % 128 == 0) { *BN = 128; *SMAX = 4; }
+  else { *BN = 64; *SMAX = 5; }
+}
+static size_t tn_workspace_floats(const TnParams& p, int BN) {
+  return (size_t)p.n_groups_m * p.n_tiles_n * p.ksplit * p.slots_per_group * 128 * BN;
+}
+
+template <int BN, int SMAX, int STAGES>
+static int launch_tn_t(TnParams& p, cudaStream_t s) {
+  using L = TnSmem<BN, SMAX, STAGES>;
+  static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
+  const int ds = device_slot();
+  if (!configured[ds]) {
+    ECGMM_CUDA(cudaFuncSetAttribute(igemm_tn_kernel<BN, SMAX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::kBytes));
+    configured[ds] = true;
+  }
+  tn_plan(p, BN, SMAX);
+  const int groups = p.n_groups_m * p.n_tiles_n;
+  igemm_tn_kernel<BN, SMAX, STAGES><<<groups * p.ksplit, 192, L::kBytes, s>>>(p);
+  int rc = check_launch("igemm_tn_kernel");
+  if (rc || !p.ws) return rc;
+  const long long total = (long long)groups * p.slots_per_group * 128 * BN;
+  tn_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p, BN);
+  return check_launch("tn_reduce_kernel");
 }
 
 static int launch_tn(TnParams& p, cudaStream_t s) {
@@ -826,10 +900,32 @@ int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
 size_t wgrad_halo_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S, int padH, int padW);
 }  // namespace ecgmm
 
+// Pixel-block decomposition of the generic weight-gradient kernel (stride-2 and 1x1 shapes).
+static void tn_pixel_blocks(TnParams& p, int N, int Ho, int Wo) {
+  pick_tile(Ho, Wo, kKPix, &p.TH, &p.TW);
+  p.tiles_h = ceil_div(Ho, p.TH);
+  p.tiles_w = ceil_div(Wo, p.TW);
+  p.n_img = N;
+  p.total_kblocks = N * p.tiles_h * p.tiles_w;
+}
+
 extern "C" long long ecgmm_conv2d_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
                                                   int padH, int padW) {
-  if (!wgrad_halo_supported(Cin, Cout, R, S, stride) || getenv("ECGMM_WGRAD_LEGACY")) return 0;
-  return (long long)wgrad_halo_workspace_bytes(N, H, W, Cin, Cout, R, S, padH, padW);
+  if (N <= 0 || check_conv_cfg(Cin, Cout, R, S, stride, padH, padW)) return 0;
+  if (wgrad_halo_supported(Cin, Cout, R, S, stride) && !getenv("ECGMM_WGRAD_LEGACY"))
+    return (long long)wgrad_halo_workspace_bytes(N, H, W, Cin, Cout, R, S, padH, padW);
+  // generic kernel: split-K partials for the deterministic fold (without a workspace it falls back to fp32 atomics)
+  TnParams p;
+  memset(&p, 0, sizeof(p));
+  tn_pixel_blocks(p, N, (H + 2 * padH - R) / stride + 1, (W + 2 * padW - S) / stride + 1);
+  if (p.total_kblocks == 0) return 0;
+  p.ntaps = R * S;
+  p.cin_chunks = Cin / 64;
+  p.Cout = Cout;
+  int bn, smax;
+  tn_shape(Cout, &bn, &smax);
+  tn_plan(p, bn, smax);
+  return (long long)(tn_workspace_floats(p, bn) * sizeof(float));
 }
 
 extern "C" int ecgmm_conv2d_wgrad(const ecgmm_bf16* x_, const ecgmm_bf16* dy_, float* dw, int N, int H, int W,
@@ -846,14 +942,19 @@ extern "C" int ecgmm_conv2d_wgrad(const ecgmm_bf16* x_, const ecgmm_bf16* dy_, f
   const int Ho = (H + 2 * padH - R) / stride + 1, Wo = (W + 2 * padW - S) / stride + 1;
   TnParams p;
   memset(&p, 0, sizeof(p));
-  pick_tile(Ho, Wo, kKPix, &p.TH, &p.TW);
-  p.tiles_h = ceil_div(Ho, p.TH);
-  p.tiles_w = ceil_div(Wo, p.TW);
-  p.n_img = N;
-  p.total_kblocks = N * p.tiles_h * p.tiles_w;
+  tn_pixel_blocks(p, N, Ho, Wo);
   bool used[4] = {false, false, false, false};
   p.ntaps = build_fwd_taps(p.taps, used, R, S, stride, padH, padW, Cin);
   p.cin_chunks = Cin / 64;
+  p.Cout = Cout;
+  {  // a workspace of the size ecgmm_conv2d_wgrad_workspace() reports selects the deterministic fold
+    int bn, smax;
+    tn_shape(Cout, &bn, &smax);
+    tn_plan(p, bn, smax);
+    const size_t need = tn_workspace_floats(p, bn) * sizeof(float);
+    p.ws = (workspace && workspace_bytes > 0 && (size_t)workspace_bytes >= need && p.total_kblocks > 0)
+               ? reinterpret_cast<float*>(workspace) : nullptr;
+  }
   rc = make_input_maps(p.x_maps, used, reinterpret_cast<const __nv_bfloat16*>(x_), N, H, W, Cin, stride, p.TW, p.TH);
   if (rc) return rc;
   for (int i = 0; i < 4; ++i)
@@ -886,9 +987,27 @@ static int stem_input_map(CUtensorMap* m, const ecgmm_bf16* xs, int N, int H, in
 }
 
 namespace ecgmm {
-int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, int N, int H, int W, cudaStream_t st);
-int launch_stem_wgrad_ring(const void* xs, const void* dy, float* dw, int N, int H, int W, cudaStream_t st);
+int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, int N, int H, int W, cudaStream_t st,
+                         float* psum = nullptr, float* psq = nullptr);
+int stem_fwd_ring_stats_rows(int N, int H, int W);
+int launch_stem_wgrad_ring(const void* xs, const void* dy, float* dw, int N, int H, int W, void* workspace,
+                           size_t ws_bytes, cudaStream_t st);
+size_t stem_wgrad_ring_workspace_bytes(int N, int H, int W);
 }  // namespace ecgmm
+
+extern "C" int ecgmm_stem_conv_fwd_stats_rows(int N, int H, int W) {
+  if (N <= 0 || H <= 0 || W <= 0 || getenv("ECGMM_STEM_LEGACY")) return 0;
+  return stem_fwd_ring_stats_rows(N, H, W);
+}
+
+extern "C" int ecgmm_stem_conv_fwd_stats(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, float* psum,
+                                         float* psq, int N, int H, int W, void* stream) {
+  ECGMM_CHECK(xs && w_s2d && y && psum && psq, ECGMM_ERR_ARG, "stem_conv_fwd_stats: null pointer");
+  ECGMM_CHECK(!getenv("ECGMM_STEM_LEGACY"), ECGMM_ERR_SHAPE, "stem_conv_fwd_stats: not offered by the legacy kernel");
+  if (N == 0) return ECGMM_OK;
+  return launch_stem_fwd_ring(xs, w_s2d, reinterpret_cast<__nv_bfloat16*>(y), N, H, W,
+                              static_cast<cudaStream_t>(stream), psum, psq);
+}
 
 extern "C" int ecgmm_stem_conv_fwd(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, int N, int H,
                                    int W, void* stream) {
@@ -916,12 +1035,18 @@ extern "C" int ecgmm_stem_conv_fwd(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d
   return launch_nt(p, 64, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" long long ecgmm_stem_conv_wgrad_workspace(int N, int H, int W) {
+  if (N <= 0 || H <= 0 || W <= 0 || getenv("ECGMM_STEM_LEGACY")) return 0;
+  return (long long)stem_wgrad_ring_workspace_bytes(N, H, W);
+}
+
 extern "C" int ecgmm_stem_conv_wgrad(const ecgmm_bf16* xs, const ecgmm_bf16* dy, float* dw, int N, int H, int W,
-                                     void* stream) {
+                                     void* workspace, long long workspace_bytes, void* stream) {
   ECGMM_CHECK(xs && dy && dw, ECGMM_ERR_ARG, "stem_conv_wgrad: null pointer");
   if (N == 0) return ECGMM_OK;
   if (!getenv("ECGMM_STEM_LEGACY"))
-    return launch_stem_wgrad_ring(xs, dy, dw, N, H, W, static_cast<cudaStream_t>(stream));
+    return launch_stem_wgrad_ring(xs, dy, dw, N, H, W, workspace, workspace_bytes > 0 ? (size_t)workspace_bytes : 0,
+                                  static_cast<cudaStream_t>(stream));
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   TnParams p;
   memset(&p, 0, sizeof(p));

@@ -1,6 +1,3 @@
-// EXPERIMENTAL (round-2 work item, DESIGN.md section 8 "known headroom" 1) -- compiled, NOT yet run on hardware,
-// never selected unless ECGMM_NT_STACK=1 is set; tests/test_conv_gpu.py runs it only with ECGMM_TEST_EXPERIMENTAL=1.
-//
 // Forward / data-gradient of the 64 -> 64 channel 3x3 stride-1 convolutions (ResNet18 layer1) with ROLLING
 // ACCUMULATORS and N = 192 MMAs.
 //
@@ -42,6 +39,8 @@ struct alignas(64) NtStackParams {
   int tiles_w, H, W, n_img;
   int seg, segs_h, total_units;  // unit = (image, column strip, segment of `seg` output rows)
   int accumulate;
+  float* psum;  // STATS: per-CTA BatchNorm partial sums of the stored (bf16-rounded) output, [gridDim.x][64]
+  float* psq;   //        ... and sums of squares
 };
 
 struct NtStackSmem {
@@ -64,6 +63,11 @@ __device__ __forceinline__ void tmem_st_zero_32x32(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// STATS: the epilogue also accumulates the per-channel sum and sum of squares of everything this CTA stores.  An
+// epilogue thread owns one pixel slot of every tile and all 64 channels of it, so the sums live in 128 registers per
+// thread for the whole kernel (no shuffles, no shared-memory traffic per tile -- the two variants that were measured
+// slower than a separate statistics pass in round 1) and are folded across the 128 threads ONCE, at the end.
+template <bool STATS>
 __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_constant__ NtStackParams p) {
   using L = NtStackSmem;
   extern __shared__ uint8_t smem_raw[];
@@ -215,12 +219,18 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
       mbar_expect_tx(&oldfull[0], kStTile * 128);
       tma_load_4d(sOut, &p.y_map, &oldfull[0], 0, w0, oh, img);
     }
+    float ssum[STATS ? 64 : 1], ssq[STATS ? 64 : 1];
+    if constexpr (STATS) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) ssum[i] = ssq[i] = 0.f;
+    }
     uint32_t g = 0;  // virtual output-row index (as in the MMA issuer); also the staging-buffer counter
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
       const int rows = unit_rows(u);
       for (int i = 0; i < rows; ++i, ++g) {
         int w0, oh, img;
         tile_coords(u, i, w0, oh, img);
+        const bool in_image = w0 + m_row < p.W;  // pixel slots right of the image edge are computed but never stored
         const int blk = (int)(g % kStBlocks);
         const int ob = (int)(g % 3);
         uint8_t* buf = sOut + ob * (kStTile * 128);
@@ -275,6 +285,19 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 4; ++j) vb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
             *d4 = v;
+            if constexpr (STATS) {
+              if (in_image) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 s2 = __bfloat1622float2(vb[j]);  // statistics of what is stored, not of the fp32 value
+                  const int ch = c * 32 + q * 8 + 2 * j;
+                  ssum[ch] += s2.x;
+                  ssq[ch] = fmaf(s2.x, s2.x, ssq[ch]);
+                  ssum[ch + 1] += s2.y;
+                  ssq[ch + 1] = fmaf(s2.y, s2.y, ssq[ch + 1]);
+                }
+              }
+            }
           }
         }
         tmem_st_wait();
@@ -290,6 +313,22 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
       }
     }
     if (leader) tma_store_wait_all<0>();
+    if constexpr (STATS) {
+      // fold the 128 threads' sums: the input-row ring is idle now (every MMA that read it has completed, or the last
+      // ofull wait above would not have returned); rows of 129 floats keep the column reads conflict-free
+      float* scr = reinterpret_cast<float*>(sA);
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        scr[m_row * 129 + i] = ssum[i];
+        scr[m_row * 129 + 64 + i] = ssq[i];
+      }
+      named_bar_sync(1, 128);
+      double acc = 0.0;
+      for (int r = 0; r < 128; ++r) acc += (double)scr[r * 129 + m_row];
+      float* dst = (m_row < 64) ? p.psum : p.psq;
+      dst[(size_t)blockIdx.x * 64 + (m_row & 63)] = (float)acc;
+    }
   }
 
   tc_fence_before();
@@ -301,16 +340,8 @@ bool nt_stack_supported(int Cin, int Cout, int R, int S, int stride, int W) {
   return stride == 1 && Cin == 64 && Cout == 64 && S == 3 && R == 3 && W >= 96;
 }
 
-// dgrad != 0: w is the [Cin][R][S][Cout] shadow and taps are mirrored (dx[h,w] += dy[h+1-r, w+1-s] W[r,s]).
-int launch_nt_stack(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int dgrad,
-                    int accumulate, cudaStream_t st) {
-  NtStackParams p;
-  memset(&p, 0, sizeof(p));
-  // weight tile q = shift*3 + k feeds output row i-1+k from input row i read `shift` pixels to the right of w0-1.
-  //   forward : out[oh][w] = sum x[oh+r-1][w+s-1] W[r][s]   ->  input row i = oh+r-1: k = 2-r ... r = 2-k, s = shift
-  //   dgrad   : dx[h][w]   = sum dy[h+1-r][w+1-s] Wt[r][s]  ->  input row i = h+1-r : k = r,          s = 2-shift
-  for (int sh = 0; sh < 3; ++sh)
-    for (int k = 0; k < 3; ++k) p.tap_of_q[sh * 3 + k] = (int8_t)(dgrad ? (k * 3 + (2 - sh)) : ((2 - k) * 3 + sh));
+// Work decomposition (shared with the statistics-row query): unit = (image, 128-pixel column strip, segment of rows).
+static void nt_stack_units(NtStackParams& p, int N, int H, int W) {
   p.tiles_w = ceil_div(W, kStTile);
   p.H = H;
   p.W = W;
@@ -321,6 +352,30 @@ int launch_nt_stack(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat1
   p.seg = seg;
   p.segs_h = ceil_div(H, seg);
   p.total_units = N * p.tiles_w * p.segs_h;
+}
+
+// rows of the [rows][64] statistics partials a forward launch with psum/psq writes (= its grid size)
+int nt_stack_stats_rows(int N, int H, int W) {
+  NtStackParams p;
+  memset(&p, 0, sizeof(p));
+  nt_stack_units(p, N, H, W);
+  return p.total_units < num_sms() ? p.total_units : num_sms();
+}
+
+// dgrad != 0: w is the [Cin][R][S][Cout] shadow and taps are mirrored (dx[h,w] += dy[h+1-r, w+1-s] W[r,s]).
+// psum / psq (forward only, may be NULL): BatchNorm partial sums, nt_stack_stats_rows() rows of 64 floats each.
+int launch_nt_stack(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int dgrad,
+                    int accumulate, cudaStream_t st, float* psum, float* psq) {
+  NtStackParams p;
+  memset(&p, 0, sizeof(p));
+  p.psum = psum;
+  p.psq = psq;
+  // weight tile q = shift*3 + k feeds output row i-1+k from input row i read `shift` pixels to the right of w0-1.
+  //   forward : out[oh][w] = sum x[oh+r-1][w+s-1] W[r][s]   ->  input row i = oh+r-1: k = 2-r ... r = 2-k, s = shift
+  //   dgrad   : dx[h][w]   = sum dy[h+1-r][w+1-s] Wt[r][s]  ->  input row i = h+1-r : k = r,          s = 2-shift
+  for (int sh = 0; sh < 3; ++sh)
+    for (int k = 0; k < 3; ++k) p.tap_of_q[sh * 3 + k] = (int8_t)(dgrad ? (k * 3 + (2 - sh)) : ((2 - k) * 3 + sh));
+  nt_stack_units(p, N, H, W);
   p.accumulate = accumulate;
   const uint64_t e = 2;
   int rc = make_tmap_4d(&p.x_map, x, 64, W, H, N, 64 * e, (uint64_t)W * 64 * e, (uint64_t)H * W * 64 * e, 64, kStBoxW, 1);
@@ -332,12 +387,17 @@ int launch_nt_stack(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat1
   static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
   const int ds = device_slot();
   if (!configured[ds]) {
-    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    NtStackSmem::kBytes));
+    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     NtStackSmem::kBytes));
     configured[ds] = true;
   }
   const int grid = p.total_units < num_sms() ? p.total_units : num_sms();
-  igemm_nt_stack_kernel<<<grid, 192, NtStackSmem::kBytes, st>>>(p);
+  if (psum && psq && !dgrad)
+    igemm_nt_stack_kernel<true><<<grid, 192, NtStackSmem::kBytes, st>>>(p);
+  else
+    igemm_nt_stack_kernel<false><<<grid, 192, NtStackSmem::kBytes, st>>>(p);
   return check_launch("igemm_nt_stack_kernel");
 }
 

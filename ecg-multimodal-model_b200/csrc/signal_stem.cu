@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(256) signal_stem_fwd_kernel(const float* __res
 template <int NOUT>  // outputs per thread = ceil(64*Cin*7 / 256)
 __global__ void __launch_bounds__(256) signal_stem_wgrad_kernel(const float* __restrict__ x,
                                                                  const __nv_bfloat16* __restrict__ dy,
-                                                                 float* __restrict__ dw, int B, int Cin, int L,
-                                                                 int Lo, int tiles_per_row) {
+                                                                 float* __restrict__ dw, float* __restrict__ ws,
+                                                                 int B, int Cin, int L, int Lo, int tiles_per_row) {
   extern __shared__ float sm[];
   float* xs = sm;                     // [Cin][kStemSpan]
   float* ds = sm + ((Cin * kStemSpan + 3) & ~3);  // [kStemTile][64]
@@ -115,8 +115,28 @@ __global__ void __launch_bounds__(256) signal_stem_wgrad_kernel(const float* __r
 #pragma unroll
   for (int j = 0; j < NOUT; ++j) {
     const int kk = (threadIdx.x >> 6) + 4 * j;
-    if (kk < K && o * K + kk < total_out) atomicAdd(dw + (size_t)o * K + kk, acc[j]);
+    if (kk < K && o * K + kk < total_out) {
+      if (ws)  // deterministic path: per-CTA partials, folded in CTA order by signal_stem_wgrad_reduce_kernel
+        ws[(size_t)blockIdx.x * total_out + (size_t)o * K + kk] = acc[j];
+      else
+        atomicAdd(dw + (size_t)o * K + kk, acc[j]);
+    }
   }
+}
+
+__global__ void __launch_bounds__(256) signal_stem_wgrad_reduce_kernel(const float* __restrict__ ws,
+                                                                        float* __restrict__ dw, int total_out,
+                                                                        int n_parts) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_out) return;
+  float a0 = 0.f, a1 = 0.f;
+  int k = 0;
+  for (; k + 1 < n_parts; k += 2) {
+    a0 += ws[(size_t)k * total_out + idx];
+    a1 += ws[(size_t)(k + 1) * total_out + idx];
+  }
+  if (k < n_parts) a0 += ws[(size_t)k * total_out + idx];
+  dw[idx] += a0 + a1;
 }
 
 }  // namespace ecgmm
@@ -142,13 +162,27 @@ extern "C" int ecgmm_signal_stem_fwd(const float* x, const float* w, ecgmm_bf16*
   return check_launch("signal_stem_fwd_kernel");
 }
 
+static int signal_stem_wgrad_grid(int B, int L) {
+  const int Lo = (L - 1) / 2 + 1;
+  int grid = B * ceil_div(Lo, kStemTile);
+  if (grid > num_sms() * 2) grid = num_sms() * 2;
+  return grid;
+}
+
+extern "C" long long ecgmm_signal_stem_wgrad_workspace(int B, int Cin, int L) {
+  if (B <= 0 || Cin < 1 || Cin > kStemMaxCin || L < 1) return 0;
+  return (long long)signal_stem_wgrad_grid(B, L) * Cin * 7 * kStemCo * (long long)sizeof(float);
+}
+
 extern "C" int ecgmm_signal_stem_wgrad(const float* x, const ecgmm_bf16* dy, float* dw, int B, int Cin, int L,
-                                       void* stream) {
+                                       void* workspace, long long workspace_bytes, void* stream) {
   ECGMM_CHECK(x && dy && dw, ECGMM_ERR_ARG, "signal_stem_wgrad: null pointer");
   ECGMM_CHECK(Cin >= 1 && Cin <= kStemMaxCin && L >= 1, ECGMM_ERR_SHAPE, "signal_stem_wgrad: Cin=%d L=%d", Cin, L);
   if (B == 0) return ECGMM_OK;
   const int Lo = (L - 1) / 2 + 1;
   const int tiles = ceil_div(Lo, kStemTile);
+  float* ws = (workspace && workspace_bytes >= ecgmm_signal_stem_wgrad_workspace(B, Cin, L))
+                  ? static_cast<float*>(workspace) : nullptr;
   const size_t smem = ((size_t)((Cin * kStemSpan + 3) & ~3) + (size_t)kStemTile * kStemCo) * sizeof(float);
   static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
   const int ds = device_slot();
@@ -159,13 +193,16 @@ extern "C" int ecgmm_signal_stem_wgrad(const float* x, const ecgmm_bf16* dy, flo
                                     64 * 1024));
     configured[ds] = true;
   }
-  int grid = B * tiles;
-  if (grid > num_sms() * 2) grid = num_sms() * 2;
+  const int grid = signal_stem_wgrad_grid(B, L);
   const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 1)
-    signal_stem_wgrad_kernel<2><<<grid, 256, smem, st>>>(x, dyb, dw, B, Cin, L, Lo, tiles);
+    signal_stem_wgrad_kernel<2><<<grid, 256, smem, st>>>(x, dyb, dw, ws, B, Cin, L, Lo, tiles);
   else
-    signal_stem_wgrad_kernel<28><<<grid, 256, smem, st>>>(x, dyb, dw, B, Cin, L, Lo, tiles);
-  return check_launch("signal_stem_wgrad_kernel");
+    signal_stem_wgrad_kernel<28><<<grid, 256, smem, st>>>(x, dyb, dw, ws, B, Cin, L, Lo, tiles);
+  int rc = check_launch("signal_stem_wgrad_kernel");
+  if (rc || !ws) return rc;
+  const int total_out = Cin * 7 * kStemCo;
+  signal_stem_wgrad_reduce_kernel<<<ceil_div(total_out, 256), 256, 0, st>>>(ws, dw, total_out, grid);
+  return check_launch("signal_stem_wgrad_reduce_kernel");
 }

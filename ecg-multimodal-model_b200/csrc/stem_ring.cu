@@ -24,6 +24,9 @@ struct alignas(64) StemRingParams {
   int Ho, Wo, tiles_w, n_strips;
   __nv_bfloat16* out;  // fwd: y [N][Ho][Wo][64]
   float* dw;           // wgrad: [64][3][7][7]
+  float* ws;           // wgrad: per-CTA partial tiles [grid][2][128][64] (deterministic fold); NULL: fp32 atomics
+  float* psum;         // fwd<STATS>: per-CTA BatchNorm partial sums of the stored output, [gridDim.x][64]
+  float* psq;          //             ... and sums of squares
 };
 
 // ------------------------------------------------------------------------------------- forward
@@ -34,6 +37,9 @@ struct StemFwdSmem {
   static constexpr int kBytes = kBarOff + 512 + 1024;
 };
 
+// STATS: per-channel sum / sum of squares of the stored output, accumulated in 128 registers per epilogue thread over
+// the whole kernel and folded across threads once at the end (same scheme as igemm_nt_stack_kernel<true>).
+template <bool STATS>
 __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_constant__ StemRingParams p) {
   using L = StemFwdSmem;
   extern __shared__ uint8_t smem_raw[];
@@ -130,9 +136,15 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
     const int m_row = quad * 32 + lane;
     const bool leader = (threadIdx.x == 64);
     uint8_t* sOut = smem + L::kOut;
+    float ssum[STATS ? 64 : 1], ssq[STATS ? 64 : 1];
+    if constexpr (STATS) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) ssum[i] = ssq[i] = 0.f;
+    }
     int it = 0;
     for (int s = blockIdx.x; s < p.n_strips; s += gridDim.x) {
       const int img = s / p.tiles_w, w0 = (s % p.tiles_w) * kSrTile;
+      const bool in_image = w0 + m_row < p.Wo;
       for (int oh = 0; oh < p.Ho; ++oh, ++it) {
         const int acc = it & 1;
         uint8_t* buf = sOut + acc * kSrSlot;
@@ -155,6 +167,19 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
             for (int j = 0; j < 4; ++j)
               vb[j] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
             *reinterpret_cast<uint4*>(row + (((c * 4 + g) ^ (m_row & 7)) << 4)) = v;
+            if constexpr (STATS) {
+              if (in_image) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 s2 = __bfloat1622float2(vb[j]);
+                  const int ch = c * 32 + g * 8 + 2 * j;
+                  ssum[ch] += s2.x;
+                  ssq[ch] = fmaf(s2.x, s2.x, ssq[ch]);
+                  ssum[ch + 1] += s2.y;
+                  ssq[ch + 1] = fmaf(s2.y, s2.y, ssq[ch + 1]);
+                }
+              }
+            }
           }
         }
         tc_fence_before();
@@ -169,6 +194,20 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
       }
     }
     if (leader) tma_store_wait_all<0>();
+    if constexpr (STATS) {
+      float* scr = reinterpret_cast<float*>(sX);  // the input ring is idle: all MMAs of this CTA have completed
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        scr[m_row * 129 + i] = ssum[i];
+        scr[m_row * 129 + 64 + i] = ssq[i];
+      }
+      named_bar_sync(1, 128);
+      double acc = 0.0;
+      for (int r = 0; r < 128; ++r) acc += (double)scr[r * 129 + m_row];
+      float* dst = (m_row < 64) ? p.psum : p.psq;
+      dst[(size_t)blockIdx.x * 64 + (m_row & 63)] = (float)acc;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -304,7 +343,13 @@ __global__ void __launch_bounds__(192, 1) stem_wgrad_ring_kernel(const __grid_co
           uint32_t r[32];
           tmem_ld_32x32(t_addr + cc * 32, r);
           tmem_ld_wait();
-          if (ok) {
+          if (p.ws) {  // deterministic path: partial [pair][128 rows][64 cout] of this CTA, folded by stem_wgrad_reduce
+            float4* dst = reinterpret_cast<float4*>(p.ws + (((size_t)blockIdx.x * 2 + pair) * 128 + m_row) * 64 + cc * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          } else if (ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) atomicAdd(dst0 + (size_t)(cc * 32 + j) * 147, __uint_as_float(r[j]));
           }
@@ -323,10 +368,19 @@ static int stem_view(CUtensorMap* m, const void* xs, int N, int Ho, int Wo) {
   return make_tmap_4d(m, xs, 64, Wo, Hs, N, 32, (uint64_t)Ws * 32, (uint64_t)Hs * Ws * 32, 64, kSrTile, 1);
 }
 
-int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, int N, int H, int W, cudaStream_t st) {
+int stem_fwd_ring_stats_rows(int N, int H, int W) {
+  (void)H;
+  const int strips = N * ceil_div((W - 1) / 2 + 1, kSrTile);
+  return strips < num_sms() ? strips : num_sms();
+}
+
+int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, int N, int H, int W, cudaStream_t st,
+                         float* psum, float* psq) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   StemRingParams p;
   memset(&p, 0, sizeof(p));
+  p.psum = psum;
+  p.psq = psq;
   p.Ho = Ho;
   p.Wo = Wo;
   p.tiles_w = ceil_div(Wo, kSrTile);
@@ -341,19 +395,60 @@ int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, in
   static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
   const int ds = device_slot();
   if (!configured[ds]) {
-    ECGMM_CUDA(cudaFuncSetAttribute(stem_fwd_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ECGMM_CUDA(cudaFuncSetAttribute(stem_fwd_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    StemFwdSmem::kBytes));
+    ECGMM_CUDA(cudaFuncSetAttribute(stem_fwd_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     StemFwdSmem::kBytes));
     configured[ds] = true;
   }
   const int grid = p.n_strips < num_sms() ? p.n_strips : num_sms();
-  stem_fwd_ring_kernel<<<grid, 192, StemFwdSmem::kBytes, st>>>(p);
+  if (psum && psq)
+    stem_fwd_ring_kernel<true><<<grid, 192, StemFwdSmem::kBytes, st>>>(p);
+  else
+    stem_fwd_ring_kernel<false><<<grid, 192, StemFwdSmem::kBytes, st>>>(p);
   return check_launch("stem_fwd_ring_kernel");
 }
 
-int launch_stem_wgrad_ring(const void* xs, const void* dy, float* dw, int N, int H, int W, cudaStream_t st) {
+// dw[cout][c][r7][s7] += sum over CTAs (in CTA order) of the partial tiles written by stem_wgrad_ring_kernel.
+__global__ void __launch_bounds__(256) stem_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw,
+                                                                int n_parts) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // = cout * 147 + (c * 7 + r7) * 7 + s7
+  if (idx >= 64 * 147) return;
+  const int cout = idx / 147, rest = idx - cout * 147;
+  const int c = rest / 49, r7 = (rest % 49) / 7, s7 = rest % 7;
+  const int ra = r7 >> 1, dr = r7 & 1, sa = s7 >> 1, dsx = s7 & 1;
+  const int ch = (dr * 2 + dsx) * 3 + c;
+  const int pair = ra >> 1, m_row = (ra & 1) * 64 + sa * 16 + ch;
+  const float* src = ws + ((size_t)pair * 128 + m_row) * 64 + cout;
+  const size_t stride = (size_t)2 * 128 * 64;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  for (; k + 3 < n_parts; k += 4) {
+    a0 += src[(size_t)k * stride];
+    a1 += src[(size_t)(k + 1) * stride];
+    a2 += src[(size_t)(k + 2) * stride];
+    a3 += src[(size_t)(k + 3) * stride];
+  }
+  for (; k < n_parts; ++k) a0 += src[(size_t)k * stride];
+  dw[idx] += (a0 + a1) + (a2 + a3);
+}
+
+static int stem_wgrad_grid(int N, int W) {
+  const int Wo = (W - 1) / 2 + 1;
+  const int strips = N * ceil_div(Wo, kSrTile);
+  return strips < num_sms() ? strips : num_sms();
+}
+size_t stem_wgrad_ring_workspace_bytes(int N, int H, int W) {
+  (void)H;
+  return (size_t)stem_wgrad_grid(N, W) * 2 * 128 * 64 * sizeof(float);
+}
+
+int launch_stem_wgrad_ring(const void* xs, const void* dy, float* dw, int N, int H, int W, void* workspace,
+                           size_t ws_bytes, cudaStream_t st) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   StemRingParams p;
   memset(&p, 0, sizeof(p));
+  p.ws = (workspace && ws_bytes >= stem_wgrad_ring_workspace_bytes(N, H, W)) ? static_cast<float*>(workspace) : nullptr;
   p.Ho = Ho;
   p.Wo = Wo;
   p.tiles_w = ceil_div(Wo, kSrTile);
@@ -371,9 +466,12 @@ int launch_stem_wgrad_ring(const void* xs, const void* dy, float* dw, int N, int
                                     StemWgSmem::kBytes));
     configured[ds] = true;
   }
-  const int grid = p.n_strips < num_sms() ? p.n_strips : num_sms();
+  const int grid = stem_wgrad_grid(N, W);
   stem_wgrad_ring_kernel<<<grid, 192, StemWgSmem::kBytes, st>>>(p);
-  return check_launch("stem_wgrad_ring_kernel");
+  rc = check_launch("stem_wgrad_ring_kernel");
+  if (rc || !p.ws) return rc;
+  stem_wgrad_reduce_kernel<<<ceil_div(64 * 147, 256), 256, 0, st>>>(p.ws, dw, grid);
+  return check_launch("stem_wgrad_reduce_kernel");
 }
 
 }  // namespace ecgmm

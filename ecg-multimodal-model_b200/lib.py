@@ -31,7 +31,10 @@ SIGNATURES = {
     "ecgmm_stem_s2d": [_p, _i, _p, _i, _i, _i, _p],
     "ecgmm_stem_weight_prep": [_p, _p, _p],
     "ecgmm_stem_conv_fwd": [_p, _p, _p, _i, _i, _i, _p],
-    "ecgmm_stem_conv_wgrad": [_p, _p, _p, _i, _i, _i, _p],
+    "ecgmm_stem_conv_fwd_stats_rows": [_i, _i, _i],
+    "ecgmm_stem_conv_fwd_stats": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "ecgmm_stem_conv_wgrad_workspace": [_i, _i, _i],
+    "ecgmm_stem_conv_wgrad": [_p, _p, _p, _i, _i, _i, _p, _ll, _p],
     "ecgmm_conv2d_fwd": [_p, _p, _p] + [_i] * 10 + [_p],
     "ecgmm_conv2d_fwd_stats_rows": [_i] * 10,
     "ecgmm_conv2d_fwd_stats": [_p, _p, _p, _p, _p] + [_i] * 10 + [_p],
@@ -53,7 +56,8 @@ SIGNATURES = {
     "ecgmm_avgpool_bwd": [_p, _p, _i, _i, _i, _p],
     # 1-D ResNet-SE specifics
     "ecgmm_signal_stem_fwd": [_p, _p, _p, _i, _i, _i, _p],
-    "ecgmm_signal_stem_wgrad": [_p, _p, _p, _i, _i, _i, _p],
+    "ecgmm_signal_stem_wgrad_workspace": [_i, _i, _i],
+    "ecgmm_signal_stem_wgrad": [_p, _p, _p, _i, _i, _i, _p, _ll, _p],
     "ecgmm_se_fwd": [_p] * 10 + [_i] * 4 + [_p],
     "ecgmm_se_bwd": [_p, _p, _i] + [_p] * 9 + [_i] * 4 + [_p],
     # dense tails / fusion head / losses
@@ -91,7 +95,8 @@ SIGNATURES = {
     "ecgmm_adam_step_dev": [_p, _i, _p, _f, _f, _f, _f, _p, _f, _p],
 }
 _RESTYPES = {"ecgmm_last_error": c_char_p, "ecgmm_stem_s2d_dims": None, "ecgmm_launch_count": c_ulonglong,
-             "ecgmm_conv2d_wgrad_workspace": c_longlong, "ecgmm_signal_preprocess_workspace": c_longlong}
+             "ecgmm_conv2d_wgrad_workspace": c_longlong, "ecgmm_signal_preprocess_workspace": c_longlong,
+             "ecgmm_stem_conv_wgrad_workspace": c_longlong, "ecgmm_signal_stem_wgrad_workspace": c_longlong}
 
 
 class EcgmmError(RuntimeError):

@@ -415,8 +415,11 @@ class ResNet18(_Stage):
         H, W = image.shape[2], image.shape[3]
         xs = ops.stem_s2d(image)
         ws, _ = self.conv1.shadows()
-        c1 = ops.stem_conv_fwd(xs, ws, H, W)
-        st1 = _bn_stats(self.bn1, c1)
+        if self.bn1.training and FUSED_STATS:
+            c1, p1 = ops.stem_conv_fwd(xs, ws, H, W, want_stats=True)
+        else:
+            c1, p1 = ops.stem_conv_fwd(xs, ws, H, W), None
+        st1 = _bn_stats(self.bn1, c1, partials=p1)
         x, arg = ops.bn_relu_maxpool(c1, st1, want_argmax=save)
         recs = []
         for blk in self.blocks():

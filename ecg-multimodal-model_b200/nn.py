@@ -61,6 +61,8 @@ class _LabelCheck:
 
     def _publish(self):
         dev, host = self.__dict__["_label_state"]
+        if dev.device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            return  # a captured step keeps the flag on the device (check() reads it); its loss is NaN all the same
         host.copy_(dev, non_blocking=True)
 
     def check(self):

@@ -227,12 +227,21 @@ def stem_weight_prep(w: torch.Tensor) -> torch.Tensor:
     return ws
 
 
-def stem_conv_fwd(xs: torch.Tensor, w_s2d: torch.Tensor, H: int, W: int) -> torch.Tensor:
+def stem_conv_fwd(xs: torch.Tensor, w_s2d: torch.Tensor, H: int, W: int, want_stats: bool = False):
+    """want_stats: returns (y, StatPartials or None) -- the BatchNorm sums of y from the convolution epilogue."""
     _chk(xs, BF16, "xs")
     _chk(w_s2d, BF16, "w_s2d")
     N = xs.shape[0]
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty((N, Ho, Wo, 64), dtype=BF16, device=xs.device)
+    if want_stats:
+        rows = _shape_query("ecgmm_stem_conv_fwd_stats_rows", N, H, W)
+        if rows == 0:
+            return stem_conv_fwd(xs, w_s2d, H, W), None
+        part = StatPartials(rows, 64, xs.device)
+        _timed("stem_fwd", 2.0 * N * Ho * Wo * 64 * 147, "ecgmm_stem_conv_fwd_stats", _ptr(xs), _ptr(w_s2d), _ptr(y),
+               _ptr(part.psum), _ptr(part.psq), N, H, W, _s())
+        return y, part
     _timed("stem_fwd", 2.0 * N * Ho * Wo * 64 * 147, "ecgmm_stem_conv_fwd", _ptr(xs), _ptr(w_s2d), _ptr(y), N, H, W,
            _s())
     return y
@@ -243,8 +252,10 @@ def stem_conv_wgrad(xs: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, H: int
     _chk(dy, BF16, "dy")
     _chk(dw, torch.float32, "dw")
     assert dw.numel() == 64 * 3 * 49
+    ws_bytes = _shape_query("ecgmm_stem_conv_wgrad_workspace", xs.shape[0], H, W)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xs.device) if ws_bytes > 0 else None
     _timed("stem_wgrad", 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * 64 * 147, "ecgmm_stem_conv_wgrad", _ptr(xs),
-           _ptr(dy), _ptr(dw), xs.shape[0], H, W, _s())
+           _ptr(dy), _ptr(dw), xs.shape[0], H, W, _ptr(ws), ws_bytes, _s())
 
 
 # ---------------------------------------------------------------- BatchNorm / ReLU / pooling
@@ -425,7 +436,9 @@ def signal_stem_fwd(x, w):
 
 def signal_stem_wgrad(x, dy, dw):
     B, Cin, L = x.shape
-    lib.call("ecgmm_signal_stem_wgrad", _ptr(x), _ptr(dy), _ptr(dw), B, Cin, L, _s())
+    ws_bytes = _shape_query("ecgmm_signal_stem_wgrad_workspace", B, Cin, L)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
+    lib.call("ecgmm_signal_stem_wgrad", _ptr(x), _ptr(dy), _ptr(dw), B, Cin, L, _ptr(ws), ws_bytes, _s())
 
 
 def se_fwd(nsum, st: BNStats, w1, b1, w2, b2, L):

@@ -72,9 +72,17 @@ int ecgmm_stem_weight_prep(const float* w, ecgmm_bf16* w_s2d, void* stream);
 /* y [N][Ho][Wo][64] bf16, Ho = (H+6-7)/2+1 */
 int ecgmm_stem_conv_fwd(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, int N, int H, int W,
                         void* stream);
-/* dw [64][3][7][7] fp32 += sum over pixels (atomic accumulation; caller zeroes dw) */
+/* The same convolution + the BatchNorm batch statistics of its (stored, bf16) output from the epilogue: psum / psq
+ * [ecgmm_stem_conv_fwd_stats_rows()][64] fp32 partial sums for ecgmm_bn_finalize (replaces the statistics pass of
+ * nn.BatchNorm2d(64) in training mode, torchvision resnet.py:197-198,268-269).  rows == 0: not offered. */
+int ecgmm_stem_conv_fwd_stats_rows(int N, int H, int W);
+int ecgmm_stem_conv_fwd_stats(const ecgmm_bf16* xs, const ecgmm_bf16* w_s2d, ecgmm_bf16* y, float* psum, float* psq,
+                              int N, int H, int W, void* stream);
+/* dw [64][3][7][7] fp32 += sum over pixels.  With a workspace of ecgmm_stem_conv_wgrad_workspace() bytes the per-CTA
+ * partial sums are folded in a fixed order (bit-reproducible); workspace == NULL: fp32 atomics. */
+long long ecgmm_stem_conv_wgrad_workspace(int N, int H, int W);
 int ecgmm_stem_conv_wgrad(const ecgmm_bf16* xs, const ecgmm_bf16* dy, float* dw, int N, int H, int W,
-                          void* stream);
+                          void* workspace, long long workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ implicit-GEMM convolutions
  * Replaces nn.Conv2d in torchvision BasicBlock (resnet.py:59-104) and nn.Conv1d in
@@ -178,7 +186,10 @@ int ecgmm_avgpool_bwd(const float* dout, ecgmm_bf16* dx, int N, int P, int C, vo
  * x [B][Cin][L] fp32 (Cin <= 16), w [64][Cin][7] fp32, y/dy [B][Lo][64] bf16, Lo = (L-1)/2+1.
  * The bias is NOT added (see ecgmm_bn_finalize / ecgmm_bn_eval_coeffs). dw accumulates. */
 int ecgmm_signal_stem_fwd(const float* x, const float* w, ecgmm_bf16* y, int B, int Cin, int L, void* stream);
-int ecgmm_signal_stem_wgrad(const float* x, const ecgmm_bf16* dy, float* dw, int B, int Cin, int L, void* stream);
+/* workspace of ecgmm_signal_stem_wgrad_workspace() bytes: fixed-order fold of the per-CTA partial sums; NULL: atomics */
+long long ecgmm_signal_stem_wgrad_workspace(int B, int Cin, int L);
+int ecgmm_signal_stem_wgrad(const float* x, const ecgmm_bf16* dy, float* dw, int B, int Cin, int L, void* workspace,
+                            long long workspace_bytes, void* stream);
 /* SEBlock.fc (multimodal_paper_modal_balance.py:52-64) on pooled = scale*nsum/L + shift:
  * hid = relu(W1 pooled + b1) [N][R], gate = sigmoid(W2 hid + b2) [N][C];  w1 [R][C], w2 [C][R]. */
 int ecgmm_se_fwd(const float* nsum, const float* scale, const float* shift, const float* w1, const float* b1,

@@ -240,6 +240,12 @@ def fusion_loss(outputs, labels, var_weight=0.1):
     return F.cross_entropy(outputs[3], labels) + var_weight * outputs[4]
 
 
+def branch_fusion_loss(outputs, labels):
+    """train_exhausted.py:70-75 -- the sum of four cross entropies: image, signal and clinical branch heads + fusion."""
+    return (F.cross_entropy(outputs[0], labels) + F.cross_entropy(outputs[1], labels) +
+            F.cross_entropy(outputs[2], labels) + F.cross_entropy(outputs[3], labels))
+
+
 def fusion_train_step(model, optimizer, image, ecg_signal, clinical, labels):
     """One iteration of train.py:60-86.  Returns (total_loss, outputs)."""
     optimizer.zero_grad()

@@ -70,6 +70,6 @@ dist.init_process_group = lambda backend=None, **k: _real_init("gloo")
 
 bench.H, bench.W, bench.L = 64, 160, 600
 args = types.SimpleNamespace(gpus=int(os.environ["WORLD_SIZE"]), steps=2, warmup=3, impl="ours", global_batch=4,
-                             no_cpu_baseline=True, detail=False, launch="graph")
+                             no_cpu_baseline=True, detail=False, launch="graph", image_dtype="uint8")
 bench.run_ours(args)
 print("WORKER RETURNED WITHOUT THE HARD EXIT", flush=True)  # shutdown() ends every rank of a multi-rank run itself

@@ -55,6 +55,23 @@ def make_inputs(seed, B, H, W, L, F=24, signal_channels=1):
     return image, ecg, clinical, labels
 
 
+def make_varied_inputs(seed, B, H, W, L, F=24):
+    """Inputs whose statistics differ from sample to sample (per-sample image brightness / contrast / a sinusoidal
+    pattern, signal amplitude and drift, wide clinical features), so that the logits of different rows differ by much
+    more than the rounding noise -- used by the label-argmax test over many rows."""
+    g = torch.Generator().manual_seed(seed)
+    mu = torch.rand(B, 1, 1, 1, generator=g) * 1.2 - 0.6
+    sig = torch.rand(B, 1, 1, 1, generator=g) * 0.8 + 0.2
+    freq = torch.rand(B, 1, 1, 1, generator=g) * 0.2 + 0.01
+    xs = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W)
+    image = (torch.randn(B, 3, H, W, generator=g) * sig + mu + 0.3 * torch.sin(freq * xs)).clamp(-1, 1)
+    amp = torch.rand(B, 1, generator=g) * 2 + 0.2
+    ecg = torch.randn(B, L, generator=g) * amp + torch.linspace(-1, 1, L).view(1, L) * (torch.rand(B, 1, generator=g) - 0.5)
+    clinical = torch.randn(B, F, generator=g) * 2.0
+    labels = torch.randint(0, 2, (B,), generator=g)
+    return image, ecg, clinical, labels
+
+
 def state_checksums(sd):
     """name -> (sum, abs-sum) in float64; cheap drift detector for procedural weights."""
     out = {}

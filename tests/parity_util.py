@@ -6,7 +6,7 @@ Tolerances (bf16 activations / fp32 accumulation against an fp32 reference; stat
   outputs   max|a-b| <= OUT_TOL * max(1, max|b|)          per output tensor
   argmax    identical on every sample whose reference margin |z1-z0| exceeds 2 * OUT_TOL
   gradients per parameter tensor, e = ||g-g_ref|| / ||g_ref|| must satisfy
-            e <= max(GRAD_REL, GRAD_NOISE_X * e_bf16)
+            e <= max(GRAD_REL, GRAD_NOISE_X * e_bf16, GRAD_MEDIAN_X * median over tensors of e_bf16)
             where e_bf16 is the same error measured on the ORACLE ITSELF when its conv/BN/ReLU/pool
             outputs, conv weights and input image are rounded to bf16 (bf16_emulated_oracle below).
             Reason: at random init this network's gradients are ill-conditioned (train-mode
@@ -37,6 +37,7 @@ from golden_util import make_inputs, make_oracle, set_dropout  # noqa: E402
 OUT_TOL = 4e-2
 GRAD_REL = 5e-2
 GRAD_NOISE_X = 3.0
+GRAD_MEDIAN_X = 1.5
 GRAD_FLOOR = 1e-4
 MATCHED_REL = float(os.environ.get("ECGMM_MATCHED_REL", "1e9"))   # calibrated on hardware, see module docstring
 MATCHED_COS = float(os.environ.get("ECGMM_MATCHED_COS", "-1"))
@@ -44,11 +45,13 @@ STAT_TOL = 2e-2
 ADAM_ABS = 2e-6
 
 
-def bf16_emulated_oracle(ora, image, ecg, clin, labels):
+def bf16_emulated_oracle(ora, image, ecg, clin, labels, loss_fn=None):
     """Gradients of the oracle with bf16 storage emulated (see module docstring); returns name -> grad."""
     import copy
 
     from oracle import model as om
+
+    loss_fn = loss_fn or om.fusion_loss
 
     m = copy.deepcopy(ora)
     m.zero_grad(set_to_none=True)
@@ -67,11 +70,11 @@ def bf16_emulated_oracle(ora, image, ecg, clin, labels):
                     mod.weight.copy_(mod.weight.to(torch.bfloat16).float())
         m.image_encoder.conv1.weight.copy_(m.image_encoder.conv1.weight.to(torch.bfloat16).float())
     out = m(image.to(torch.bfloat16).float(), ecg, clin)
-    om.fusion_loss(out, labels).backward()
+    loss_fn(out, labels).backward()
     return {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
 
 
-def storage_matched_oracle(ora, image, ecg, clin, labels):
+def storage_matched_oracle(ora, image, ecg, clin, labels, loss_fn=None):
     """Gradients of the oracle computed in fp32 arithmetic but with bf16 rounding at EXACTLY the tensors the product
     stores as bf16 (name -> grad).  Differences to bf16_emulated_oracle: the second BatchNorm of a residual block is
     NOT rounded (the product adds the identity and applies the ReLU in fp32 registers and rounds once), and the
@@ -82,6 +85,7 @@ def storage_matched_oracle(ora, image, ecg, clin, labels):
 
     from oracle import model as om
 
+    loss_fn = loss_fn or om.fusion_loss
     m = copy.deepcopy(ora)
     m.zero_grad(set_to_none=True)
     for mod in m.modules():
@@ -110,7 +114,7 @@ def storage_matched_oracle(ora, image, ecg, clin, labels):
                     mod.weight.copy_(mod.weight.to(torch.bfloat16).float())
         m.image_encoder.conv1.weight.copy_(m.image_encoder.conv1.weight.to(torch.bfloat16).float())
     out = m(image.to(torch.bfloat16).float(), ecg, clin)
-    om.fusion_loss(out, labels).backward()
+    loss_fn(out, labels).backward()
     return {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
 
 
@@ -137,7 +141,7 @@ def build_pair(seed=7, dims=(256, 256, 256), signal_channels=1, clinical_feature
 
 
 def run_fusion_parity(B=4, H=64, W=160, L=600, train=True, adam=True, seed=7, dims=(256, 256, 256),
-                      signal_channels=1, verbose=False, inputs=None, expect=None):
+                      signal_channels=1, verbose=False, inputs=None, expect=None, loss="fusion"):
     """Runs oracle (CPU) and product (GPU) on identical weights/inputs; returns a report dict.
 
     `expect`: optional golden dict (outputs / loss / grad_norms) replacing the live oracle run."""
@@ -166,7 +170,13 @@ def run_fusion_parity(B=4, H=64, W=160, L=600, train=True, adam=True, seed=7, di
     dev = "cuda"
     d_out = dut(image.to(dev), ecg.to(dev), clin.to(dev))
     crit = enn.CrossEntropyLoss()
-    d_loss = crit(d_out[3], labels.to(dev)) + 0.1 * d_out[4]
+    lab_d = labels.to(dev)
+    if loss == "branches":  # train_exhausted.py:70-75: the three branch heads get gradients too
+        o_loss_fn = om.branch_fusion_loss
+        d_loss = crit(d_out[0], lab_d) + crit(d_out[1], lab_d) + crit(d_out[2], lab_d) + crit(d_out[3], lab_d)
+    else:
+        o_loss_fn = om.fusion_loss
+        d_loss = crit(d_out[3], lab_d) + 0.1 * d_out[4]
     if train:
         d_loss.backward()
     torch.cuda.synchronize()
@@ -175,7 +185,7 @@ def run_fusion_parity(B=4, H=64, W=160, L=600, train=True, adam=True, seed=7, di
     # ---- oracle
     if expect is None:
         o_out = ora(image, ecg, clin)
-        o_loss = om.fusion_loss(o_out, labels)
+        o_loss = o_loss_fn(o_out, labels)
         if train:
             o_loss.backward()
         o_out = [t.detach() for t in o_out]
@@ -205,9 +215,16 @@ def run_fusion_parity(B=4, H=64, W=160, L=600, train=True, adam=True, seed=7, di
         og = {k: p.grad for k, p in ora.named_parameters() if p.grad is not None}
         dg = {k: p.grad for k, p in dut.named_parameters()}
         # yardstick: the oracle under emulated bf16 storage (restores BN buffers: deepcopy inside)
-        eg = bf16_emulated_oracle(ora_clean, image, ecg, clin, labels)
-        sg = storage_matched_oracle(ora_clean, image, ecg, clin, labels)
+        eg = bf16_emulated_oracle(ora_clean, image, ecg, clin, labels, o_loss_fn)
+        sg = storage_matched_oracle(ora_clean, image, ecg, clin, labels, o_loss_fn)
+        rep["matched"] = {}
         scale = max(float(g.double().norm()) for g in og.values())
+        # the noise level of this network at this shape: median over tensors of the emulated oracle's own error.  A
+        # tensor whose single emulated sample happens to come out small is still subject to that level of noise.
+        emul_all = sorted(float((eg[k].double() - r.double()).norm()) / float(r.double().norm())
+                          for k, r in og.items() if float(r.double().norm()) >= GRAD_FLOOR * scale)
+        noise_floor = GRAD_MEDIAN_X * emul_all[len(emul_all) // 2]
+        rep["grad_noise_floor"] = noise_floor
         worst_ratio, worst_rel = 0.0, 0.0
         worst_matched, worst_cos = (0.0, ""), (1.0, "")
         for k, g_ref in og.items():
@@ -227,13 +244,14 @@ def run_fusion_parity(B=4, H=64, W=160, L=600, train=True, adam=True, seed=7, di
             sm = sg[k].double()
             rel_sm = float((g - sm).norm()) / max(float(sm.norm()), 1e-30)
             cos_sm = float((g * sm).sum() / max(float(g.norm()) * float(sm.norm()), 1e-30))
+            rep["matched"][k] = (rel_sm, cos_sm, rel, rel_emul)
             worst_matched = max(worst_matched, (rel_sm, k))
             worst_cos = min(worst_cos, (cos_sm, k))
             if verbose and rel_sm > MATCHED_REL / 2:
                 print(f"  grad {k:55s} vs storage-matched oracle: rel {rel_sm:.4f} cos {cos_sm:.5f}")
             if not (rel_sm <= MATCHED_REL and cos_sm >= MATCHED_COS):
                 failures.append(f"grad {k}: vs storage-matched oracle rel {rel_sm:.3g} cos {cos_sm:.5f}")
-            allowed = max(GRAD_REL, GRAD_NOISE_X * rel_emul)
+            allowed = max(GRAD_REL, GRAD_NOISE_X * rel_emul, noise_floor)
             worst_rel = max(worst_rel, rel)
             worst_ratio = max(worst_ratio, rel / allowed)
             if verbose and rel > 0.5 * allowed:
@@ -269,7 +287,7 @@ def run_fusion_parity(B=4, H=64, W=160, L=600, train=True, adam=True, seed=7, di
     rep["ok"] = not failures
     if verbose:
         for k, v in rep.items():
-            if k != "failures":
+            if k not in ("failures", "matched"):
                 print(f"  {k}: {v}")
         for f in failures[:40]:
             print("  FAIL", f)

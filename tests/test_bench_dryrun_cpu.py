@@ -106,7 +106,7 @@ def test_bench_own_arm_dry_run(fake_cuda, monkeypatch, capsys, sync_loss, launch
     monkeypatch.setattr(bench, "W", 160)
     monkeypatch.setattr(bench, "L", 600)
     args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, impl="ours", global_batch=2, no_cpu_baseline=True,
-                                 detail=True, launch=launch)
+                                 detail=True, launch=launch, image_dtype="uint8")
     bench.run_ours(args)
     out = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
     assert len(out) == 1

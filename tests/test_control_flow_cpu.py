@@ -70,7 +70,7 @@ def test_train_step_flow(stub):
                if not n.startswith(("image_classifier", "signal_classifier", "clinical_classifier")))
     assert all(int(opt.state[p]["step"]) == 2 for p in m.parameters() if p.grad is not None)
     names = set(stub)
-    for needed in ("ecgmm_stem_s2d", "ecgmm_stem_conv_fwd", "ecgmm_conv2d_fwd", "ecgmm_conv2d_fwd_stats",
+    for needed in ("ecgmm_stem_s2d", "ecgmm_stem_conv_fwd_stats", "ecgmm_conv2d_fwd", "ecgmm_conv2d_fwd_stats",
                    "ecgmm_conv2d_dgrad", "ecgmm_conv2d_wgrad", "ecgmm_stem_conv_wgrad", "ecgmm_chan_stats",
                    "ecgmm_bn_finalize", "ecgmm_bn_apply", "ecgmm_bn_relu_maxpool", "ecgmm_bn_bwd_reduce",
                    "ecgmm_bn_bwd_finalize", "ecgmm_bn_bwd_apply", "ecgmm_se_fwd", "ecgmm_se_bwd", "ecgmm_ce_loss",

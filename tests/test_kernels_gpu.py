@@ -381,7 +381,9 @@ def test_stem_s2d_uint8_equals_totensor_normalize():
 
 # ------------------------------------------------------------------ BatchNorm statistics from the conv epilogues
 @pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride", [
-    (3, 21, 150, 64, 64, 3, 1),     # 64 -> 64 halo kernel: not offered
+    (3, 21, 150, 64, 64, 3, 1),     # 64 -> 64 rolling-accumulator kernel: sums kept in registers, one row per CTA
+    (4, 63, 625, 64, 64, 3, 1),     # ... at the native layer1 size (many tiles per CTA)
+    (2, 1, 300, 64, 64, 3, 1),      # 1-D 64 -> 64 (halo kernel): not offered
     (2, 9, 40, 128, 64, 3, 1),      # generic kernel, BN = 64
     (3, 17, 45, 64, 128, 3, 2),     # stride 2 with K = 576: below the K >= 1152 threshold, not offered
     (3, 17, 45, 128, 128, 3, 2),    # stride 2, BN = 128
@@ -401,7 +403,8 @@ def test_conv_epilogue_statistics(N, H, W, Cin, Cout, k, stride):
     y0 = ops.conv2d_fwd(x, w_fwd, stride)
     y, part = ops.conv2d_fwd(x, w_fwd, stride, want_stats=True)
     assert torch.equal(y, y0)
-    if k * (1 if H == 1 else k) * Cin < 1152:
+    stack = (Cin == 64 and Cout == 64 and k == 3 and H > 1 and stride == 1 and W >= 96)
+    if k * (1 if H == 1 else k) * Cin < 1152 and not stack:
         assert part is None  # not offered (too few MMAs per tile to hide it): the caller runs the statistics pass
         return
     yd = y.double().reshape(-1, Cout)
@@ -416,3 +419,21 @@ def test_conv_epilogue_statistics(N, H, W, Cin, Cout, k, stride):
     a = ops.bn_train_stats(y, bn.weight, bn.bias, None, None, None, 1e-5, 0.1)
     b = ops.bn_train_stats(y, bn.weight, bn.bias, None, None, None, 1e-5, 0.1, partials=part)
     assert rel_l2(b.mean, a.mean) < 1e-4 and rel_l2(b.invstd, a.invstd) < 1e-5
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 50, 100), (3, 37, 75), (2, 250, 2500)])
+def test_stem_epilogue_statistics(N, H, W):
+    """stem_conv_fwd(want_stats=True): same y, and the per-CTA partial rows (sums kept in registers for the whole
+    kernel) fold to the per-channel sum / sum of squares of the STORED bf16 tensor."""
+    g = gen(f"stemstats{N}{H}{W}")
+    image = torch.randn(N, 3, H, W, generator=g).clamp(-1, 1).to(DEV)
+    w = (torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5).to(DEV)
+    xs, ws = ops.stem_s2d(image), ops.stem_weight_prep(w)
+    y0 = ops.stem_conv_fwd(xs, ws, H, W)
+    y, part = ops.stem_conv_fwd(xs, ws, H, W, want_stats=True)
+    assert part is not None and torch.equal(y, y0)
+    yd = y.double().reshape(-1, 64)
+    s = part.psum.view(part.rows, 64).double().sum(0)
+    q = part.psq.view(part.rows, 64).double().sum(0)
+    assert ((s - yd.sum(0)).abs() <= 1e-5 * yd.abs().sum(0) + 1e-6).all()
+    assert ((q - (yd * yd).sum(0)).abs() <= 1e-5 * (yd * yd).sum(0) + 1e-6).all()

@@ -1,0 +1,15 @@
+#!/bin/bash
+# second GPU call of round 2: full GPU suite on the new defaults + deterministic folds, gradient-tolerance calibration,
+# bench lines at per-GPU batch 64 and 512 (uint8 input, library Prefetcher)
+set -u
+TAG=${1:-r02b}
+O=gpurun_out
+mkdir -p $O
+run() { local name=$1 lim=$2; shift 2; echo "== $name: $*" | tee -a $O/${TAG}_index.log
+  timeout "$lim" "$@" > $O/${TAG}_$name.log 2>&1
+  echo "   rc=$? ($(tail -c 300 $O/${TAG}_$name.log | tr '\n' ' ' | cut -c1-220))" | tee -a $O/${TAG}_index.log; }
+run pytest 900 python -m pytest tests -q -m gpu -x --durations=15
+run probe  600 python tools/grad_parity_probe.py native
+run b64    300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --global-batch 64 --detail
+run b512   300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --detail
+cat $O/${TAG}_index.log
