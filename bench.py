@@ -364,7 +364,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches_per_step_eager = lib.launch_count() - n0
     classes, detail = {}, {}
-    for kind, work, a, b in prof:
+    for kind, work, a, b, *_ in prof:
         ms = a.elapsed_time(b)
         for table, key in ((classes, kind.split("/")[0]), (detail, kind)):
             c = table.setdefault(key, {"launches": 0, "ms": 0.0, "work": 0.0})
@@ -511,9 +511,21 @@ def main():
     ap.add_argument("--image-dtype", default="uint8", choices=["uint8", "fp32", "bf16"],
                     help="what the loader hands over (host side of e2e and the resident batch alike)")
     ap.add_argument("--detail", action="store_true", help="per-shape kernel timings on stderr")
+    ap.add_argument("--config", default="train", choices=["train", "signal", "perturb", "kfold"],
+                    help="train: configs[2] of BASELINE.json, the headline (default); signal: configs[1] (12-lead 1D-CNN, "
+                         "batch 256, 1 GPU); perturb: configs[3] (4096 masked variants per sample, samples sharded over "
+                         "the GPUs); kfold: configs[4] (5 folds of a 10k-patient synthetic data set, folds sharded over the "
+                         "GPUs).  The other configs print their own JSON line (tools/*_bench.py); extra arguments after "
+                         "`--` are passed on to them")
+    ap.add_argument("rest", nargs="*", help=argparse.SUPPRESS)
     ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
                     help="graph: the training step replayed as one CUDA graph (ecgmm.graph); eager: kernel by kernel")
     args = ap.parse_args()
+    if args.config != "train" and args.impl == "ours":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        mod = {"signal": "signal_bench", "perturb": "perturb_bench", "kfold": "kfold_bench"}[args.config]
+        __import__(mod).main(list(args.rest))
+        return
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":

@@ -417,7 +417,9 @@ static bool nt_stack_enabled() {
   return !(e && atoi(e) == 0);
 }
 int launch_nt_stack(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int dgrad,
-                    int accumulate, cudaStream_t st, float* psum = nullptr, float* psq = nullptr);
+                    int accumulate, cudaStream_t st, float* psum = nullptr, float* psq = nullptr,
+                    const __nv_bfloat16* red_x = nullptr, const uint8_t* red_mask = nullptr,
+                    const float* red_mean = nullptr, const float* red_invstd = nullptr);
 int nt_stack_stats_rows(int N, int H, int W);
 }  // namespace ecgmm
 
@@ -525,9 +527,42 @@ extern "C" int ecgmm_conv2d_fwd_stats(const ecgmm_bf16* x, const ecgmm_bf16* w, 
   return conv2d_fwd_impl(x, w, y, psum, psq, N, H, W, Cin, Cout, R, S, stride, padH, padW, stream);
 }
 
+// BatchNorm-backward sums from the data-gradient epilogue: rows of the [rows][Cin] partials, 0 = not offered.
+extern "C" int ecgmm_conv2d_dgrad_reduce_rows(int N, int H, int W, int Cin, int Cout, int R, int S, int stride,
+                                              int padH, int padW) {
+  if (N <= 0 || check_conv_cfg(Cin, Cout, R, S, stride, padH, padW)) return 0;
+  if (nt_stack_enabled() && nt_stack_supported(Cin, Cout, R, S, stride, W)) return nt_stack_stats_rows(N, H, W);
+  return 0;
+}
+
+static int conv2d_dgrad_impl(const ecgmm_bf16* dy_, const ecgmm_bf16* wt_, ecgmm_bf16* dx_, int N, int H, int W,
+                             int Cin, int Cout, int R, int S, int stride, int padH, int padW, int accumulate,
+                             void* stream, const ecgmm_bf16* red_x, const uint8_t* red_mask, const float* red_mean,
+                             const float* red_invstd, float* p1, float* p2);
+
+extern "C" int ecgmm_conv2d_dgrad_reduce(const ecgmm_bf16* dy, const ecgmm_bf16* wt, ecgmm_bf16* dx,
+                                         const ecgmm_bf16* bn_x, const uint8_t* bn_mask, const float* bn_mean,
+                                         const float* bn_invstd, float* p1, float* p2, int N, int H, int W, int Cin,
+                                         int Cout, int R, int S, int stride, int padH, int padW, int accumulate,
+                                         void* stream) {
+  ECGMM_CHECK(bn_x && bn_mean && bn_invstd && p1 && p2, ECGMM_ERR_ARG, "conv2d_dgrad_reduce: null pointer");
+  ECGMM_CHECK(ecgmm_conv2d_dgrad_reduce_rows(N, H, W, Cin, Cout, R, S, stride, padH, padW) > 0 || N == 0,
+              ECGMM_ERR_SHAPE, "conv2d_dgrad_reduce: not offered for this shape (see ecgmm_conv2d_dgrad_reduce_rows)");
+  return conv2d_dgrad_impl(dy, wt, dx, N, H, W, Cin, Cout, R, S, stride, padH, padW, accumulate, stream, bn_x,
+                           bn_mask, bn_mean, bn_invstd, p1, p2);
+}
+
 extern "C" int ecgmm_conv2d_dgrad(const ecgmm_bf16* dy_, const ecgmm_bf16* wt_, ecgmm_bf16* dx_, int N, int H,
                                   int W, int Cin, int Cout, int R, int S, int stride, int padH, int padW,
                                   int accumulate, void* stream) {
+  return conv2d_dgrad_impl(dy_, wt_, dx_, N, H, W, Cin, Cout, R, S, stride, padH, padW, accumulate, stream, nullptr,
+                           nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+static int conv2d_dgrad_impl(const ecgmm_bf16* dy_, const ecgmm_bf16* wt_, ecgmm_bf16* dx_, int N, int H, int W,
+                             int Cin, int Cout, int R, int S, int stride, int padH, int padW, int accumulate,
+                             void* stream, const ecgmm_bf16* red_x, const uint8_t* red_mask, const float* red_mean,
+                             const float* red_invstd, float* p1, float* p2) {
   ECGMM_CHECK(dy_ && wt_ && dx_, ECGMM_ERR_ARG, "conv2d_dgrad: null pointer");
   int rc = check_conv_cfg(Cin, Cout, R, S, stride, padH, padW);
   if (rc) return rc;
@@ -535,7 +570,8 @@ extern "C" int ecgmm_conv2d_dgrad(const ecgmm_bf16* dy_, const ecgmm_bf16* wt_, 
   if (nt_stack_enabled() && nt_stack_supported(Cin, Cout, R, S, stride, W))
     return launch_nt_stack(reinterpret_cast<const __nv_bfloat16*>(dy_), reinterpret_cast<const __nv_bfloat16*>(wt_),
                            reinterpret_cast<__nv_bfloat16*>(dx_), N, H, W, 1, accumulate,
-                           static_cast<cudaStream_t>(stream));
+                           static_cast<cudaStream_t>(stream), p1, p2, reinterpret_cast<const __nv_bfloat16*>(red_x),
+                           red_mask, red_mean, red_invstd);
   if (nt_halo_supported(Cin, Cout, R, S, stride, W) && !getenv("ECGMM_NT_LEGACY"))
     return launch_nt_halo(reinterpret_cast<const __nv_bfloat16*>(dy_), reinterpret_cast<const __nv_bfloat16*>(wt_),
                           reinterpret_cast<__nv_bfloat16*>(dx_), N, H, W, R, S, 1, accumulate,

@@ -39,8 +39,13 @@ struct alignas(64) NtStackParams {
   int tiles_w, H, W, n_img;
   int seg, segs_h, total_units;  // unit = (image, column strip, segment of `seg` output rows)
   int accumulate;
-  float* psum;  // STATS: per-CTA BatchNorm partial sums of the stored (bf16-rounded) output, [gridDim.x][64]
-  float* psq;   //        ... and sums of squares
+  float* psum;  // STATS 1: per-CTA BatchNorm partial sums of the stored (bf16-rounded) output, [gridDim.x][64]
+  float* psq;   //          ... and sums of squares.   STATS 2: sum dz and sum dz * xhat (see below)
+  // STATS 2 (data gradient): the output dx is the upstream gradient of a BatchNorm (+ReLU) whose input was red_x
+  const __nv_bfloat16* red_x;  // [N][H][W][64] raw convolution output that BatchNorm normalised
+  const uint8_t* red_mask;     // ReLU decisions, one byte per 8 channels (NULL: no ReLU)
+  const float* red_mean;       // [64] batch mean / inverse standard deviation of red_x
+  const float* red_invstd;
 };
 
 struct NtStackSmem {
@@ -63,11 +68,15 @@ __device__ __forceinline__ void tmem_st_zero_32x32(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// STATS: the epilogue also accumulates the per-channel sum and sum of squares of everything this CTA stores.  An
+// STATS = 1: the epilogue also accumulates the per-channel sum and sum of squares of everything this CTA stores.  An
 // epilogue thread owns one pixel slot of every tile and all 64 channels of it, so the sums live in 128 registers per
 // thread for the whole kernel (no shuffles, no shared-memory traffic per tile -- the two variants that were measured
 // slower than a separate statistics pass in round 1) and are folded across the 128 threads ONCE, at the end.
-template <bool STATS>
+// STATS = 2 (data gradient): the tile being stored is the gradient dy of a BatchNorm(+ReLU) output; the thread also
+// loads its pixel's row of that BatchNorm's INPUT x (128 contiguous bytes) and ReLU bits (8 bytes) and accumulates the
+// two sums the BatchNorm backward needs, sum dz and sum dz * x with dz = dy * relu'(.), so that the separate reduction
+// pass over (x, dy) -- ecgmm_bn_bwd_reduce -- disappears.  Written out as sum dz and sum dz * xhat.
+template <int STATS>
 __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_constant__ NtStackParams p) {
   using L = NtStackSmem;
   extern __shared__ uint8_t smem_raw[];
@@ -220,7 +229,7 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
       tma_load_4d(sOut, &p.y_map, &oldfull[0], 0, w0, oh, img);
     }
     float ssum[STATS ? 64 : 1], ssq[STATS ? 64 : 1];
-    if constexpr (STATS) {
+    if constexpr (STATS != 0) {
 #pragma unroll
       for (int i = 0; i < 64; ++i) ssum[i] = ssq[i] = 0.f;
     }
@@ -234,6 +243,17 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
         const int blk = (int)(g % kStBlocks);
         const int ob = (int)(g % 3);
         uint8_t* buf = sOut + ob * (kStTile * 128);
+        uint4 xrow[STATS == 2 ? 8 : 1];
+        uint2 mbits = make_uint2(0xffffffffu, 0xffffffffu);
+        if constexpr (STATS == 2) {  // issued before the accumulator wait: the latency hides behind the MMAs
+          if (in_image) {
+            const size_t pix = ((size_t)img * p.H + oh) * p.W + (w0 + m_row);
+            const uint4* xs = reinterpret_cast<const uint4*>(p.red_x + pix * 64);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xrow[k] = __ldg(xs + k);
+            if (p.red_mask) mbits = __ldg(reinterpret_cast<const uint2*>(p.red_mask + pix * 8));
+          }
+        }
         if (leader) {
           tma_store_wait_read<1>();  // every store but the newest has been read out of its buffer
           if (p.accumulate) {
@@ -285,7 +305,7 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 4; ++j) vb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
             *d4 = v;
-            if constexpr (STATS) {
+            if constexpr (STATS == 1) {
               if (in_image) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -295,6 +315,24 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
                   ssq[ch] = fmaf(s2.x, s2.x, ssq[ch]);
                   ssum[ch + 1] += s2.y;
                   ssq[ch + 1] = fmaf(s2.y, s2.y, ssq[ch + 1]);
+                }
+              }
+            }
+            if constexpr (STATS == 2) {
+              if (in_image) {
+                const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&xrow[c * 4 + q]);
+                const uint32_t bits = ((c * 4 + q) < 4 ? mbits.x : mbits.y) >> (8 * ((c * 4 + q) & 3));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float2 d = __bfloat1622float2(vb[j]);  // the gradient as the BatchNorm backward will read it
+                  const float2 xx = __bfloat1622float2(xb[j]);
+                  if (!((bits >> (2 * j)) & 1u)) d.x = 0.f;
+                  if (!((bits >> (2 * j + 1)) & 1u)) d.y = 0.f;
+                  const int ch = c * 32 + q * 8 + 2 * j;
+                  ssum[ch] += d.x;
+                  ssq[ch] = fmaf(d.x, xx.x, ssq[ch]);
+                  ssum[ch + 1] += d.y;
+                  ssq[ch + 1] = fmaf(d.y, xx.y, ssq[ch + 1]);
                 }
               }
             }
@@ -313,7 +351,7 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
       }
     }
     if (leader) tma_store_wait_all<0>();
-    if constexpr (STATS) {
+    if constexpr (STATS != 0) {
       // fold the 128 threads' sums: the input-row ring is idle now (every MMA that read it has completed, or the last
       // ofull wait above would not have returned); rows of 129 floats keep the column reads conflict-free
       float* scr = reinterpret_cast<float*>(sA);
@@ -324,10 +362,22 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
         scr[m_row * 129 + 64 + i] = ssq[i];
       }
       named_bar_sync(1, 128);
-      double acc = 0.0;
-      for (int r = 0; r < 128; ++r) acc += (double)scr[r * 129 + m_row];
-      float* dst = (m_row < 64) ? p.psum : p.psq;
-      dst[(size_t)blockIdx.x * 64 + (m_row & 63)] = (float)acc;
+      if constexpr (STATS == 1) {
+        double acc = 0.0;
+        for (int r = 0; r < 128; ++r) acc += (double)scr[r * 129 + m_row];
+        float* dst = (m_row < 64) ? p.psum : p.psq;
+        dst[(size_t)blockIdx.x * 64 + (m_row & 63)] = (float)acc;
+      } else if (m_row < 64) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int r = 0; r < 128; ++r) {
+          s1 += (double)scr[r * 129 + m_row];
+          s2 += (double)scr[r * 129 + 64 + m_row];
+        }
+        // sum dz * xhat = invstd * (sum dz * x - mean * sum dz), in double
+        p.psum[(size_t)blockIdx.x * 64 + m_row] = (float)s1;
+        p.psq[(size_t)blockIdx.x * 64 + m_row] =
+            (float)((double)p.red_invstd[m_row] * (s2 - (double)p.red_mean[m_row] * s1));
+      }
     }
   }
 
@@ -363,13 +413,19 @@ int nt_stack_stats_rows(int N, int H, int W) {
 }
 
 // dgrad != 0: w is the [Cin][R][S][Cout] shadow and taps are mirrored (dx[h,w] += dy[h+1-r, w+1-s] W[r,s]).
-// psum / psq (forward only, may be NULL): BatchNorm partial sums, nt_stack_stats_rows() rows of 64 floats each.
+// psum / psq (may be NULL): nt_stack_stats_rows() rows of 64 floats each -- forward: BatchNorm partial sums of y;
+// dgrad with red != NULL: the BatchNorm-backward sums of (red->x, y) (struct NtStackReduce in the caller's terms).
 int launch_nt_stack(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int dgrad,
-                    int accumulate, cudaStream_t st, float* psum, float* psq) {
+                    int accumulate, cudaStream_t st, float* psum, float* psq, const __nv_bfloat16* red_x,
+                    const uint8_t* red_mask, const float* red_mean, const float* red_invstd) {
   NtStackParams p;
   memset(&p, 0, sizeof(p));
   p.psum = psum;
   p.psq = psq;
+  p.red_x = red_x;
+  p.red_mask = red_mask;
+  p.red_mean = red_mean;
+  p.red_invstd = red_invstd;
   // weight tile q = shift*3 + k feeds output row i-1+k from input row i read `shift` pixels to the right of w0-1.
   //   forward : out[oh][w] = sum x[oh+r-1][w+s-1] W[r][s]   ->  input row i = oh+r-1: k = 2-r ... r = 2-k, s = shift
   //   dgrad   : dx[h][w]   = sum dy[h+1-r][w+1-s] Wt[r][s]  ->  input row i = h+1-r : k = r,          s = 2-shift
@@ -387,17 +443,21 @@ int launch_nt_stack(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat1
   static bool configured[kMaxDevices] = {};  // the shared-memory limit of a kernel is a per-device attribute
   const int ds = device_slot();
   if (!configured[ds]) {
-    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_stack_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     NtStackSmem::kBytes));
-    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_stack_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    NtStackSmem::kBytes));
+    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_stack_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     NtStackSmem::kBytes));
     configured[ds] = true;
   }
   const int grid = p.total_units < num_sms() ? p.total_units : num_sms();
   if (psum && psq && !dgrad)
-    igemm_nt_stack_kernel<true><<<grid, 192, NtStackSmem::kBytes, st>>>(p);
+    igemm_nt_stack_kernel<1><<<grid, 192, NtStackSmem::kBytes, st>>>(p);
+  else if (psum && psq && dgrad && red_x && red_mean && red_invstd)
+    igemm_nt_stack_kernel<2><<<grid, 192, NtStackSmem::kBytes, st>>>(p);
   else
-    igemm_nt_stack_kernel<false><<<grid, 192, NtStackSmem::kBytes, st>>>(p);
+    igemm_nt_stack_kernel<0><<<grid, 192, NtStackSmem::kBytes, st>>>(p);
   return check_launch("igemm_nt_stack_kernel");
 }
 

@@ -483,10 +483,10 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
 //   m1 = mean(du), m2 = mean(du*xhat);  dgamma = sum(du*xhat), dbeta = sum(du).
 __global__ void __launch_bounds__(kFinCh * kFinLanes) bn_bwd_finalize_kernel(
     const float* __restrict__ p1, const float* __restrict__ p2, int N, int split, int C, double per_sample,
-    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
-    const float* __restrict__ se, const float* __restrict__ q, const float* __restrict__ nsum,
-    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coefA, float* __restrict__ coefB,
-    float* __restrict__ coefD) {
+    double count, const float* __restrict__ gamma, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ se, const float* __restrict__ q,
+    const float* __restrict__ nsum, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    float* __restrict__ coefA, float* __restrict__ coefB, float* __restrict__ coefD) {
   __shared__ double sh_a[kFinLanes][kFinCh + 1], sh_b[kFinLanes][kFinCh + 1];
   const int cl = threadIdx.x & (kFinCh - 1), lane = threadIdx.x / kFinCh;
   const int c = blockIdx.x * kFinCh + cl;
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(kFinCh * kFinLanes) bn_bwd_finalize_kernel(
   }
   fin_fold(sh_a, sh_b, lane, cl, s1, s2);
   if (lane != 0 || c >= C) return;
-  const double M = per_sample * N;
+  const double M = count > 0.0 ? count : per_sample * N;
   const double m1 = s1 / M, m2 = s2 / M;
   const double g = gamma ? gamma[c] : 1.0;
   if (dgamma) dgamma[c] = (float)s2;
@@ -1056,12 +1056,14 @@ extern "C" int ecgmm_bn_bwd_finalize(const float* p1, const float* p2, int N, in
                                      long long per_sample, const float* gamma, const float* mean,
                                      const float* invstd, const float* se, const float* q, const float* nsum,
                                      float* dgamma, float* dbeta, float* coefA, float* coefB, float* coefD,
-                                     void* stream) {
+                                     long long count, void* stream) {
+  ECGMM_CHECK(count >= 0 && (count == 0 || !se), ECGMM_ERR_ARG, "bn_bwd_finalize: bad count %lld", count);
   ECGMM_CHECK(p1 && p2 && mean && invstd && coefA && coefB && coefD, ECGMM_ERR_ARG, "bn_bwd_finalize: null pointer");
   ECGMM_CHECK(!se || (q && nsum), ECGMM_ERR_ARG, "bn_bwd_finalize: SE mode needs q and nsum");
   ECGMM_CHECK(N > 0 && per_sample > 0, ECGMM_ERR_SHAPE, "bn_bwd_finalize: empty batch");
   bn_bwd_finalize_kernel<<<ceil_div(C, kFinCh), kFinCh * kFinLanes, 0, (cudaStream_t)stream>>>(
-      p1, p2, N, split, C, (double)per_sample, gamma, mean, invstd, se, q, nsum, dgamma, dbeta, coefA, coefB, coefD);
+      p1, p2, N, split, C, (double)per_sample, (double)count, gamma, mean, invstd, se, q, nsum, dgamma, dbeta, coefA,
+      coefB, coefD);
   return check_launch("bn_bwd_finalize_kernel");
 }
 

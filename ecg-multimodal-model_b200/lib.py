@@ -40,6 +40,8 @@ SIGNATURES = {
     "ecgmm_conv2d_fwd_stats": [_p, _p, _p, _p, _p] + [_i] * 10 + [_p],
     "ecgmm_conv2d_fwd_bn": [_p, _p, _p, _p, _p, _p, _i] + [_i] * 10 + [_p],
     "ecgmm_conv2d_dgrad": [_p, _p, _p] + [_i] * 11 + [_p],
+    "ecgmm_conv2d_dgrad_reduce_rows": [_i] * 10,
+    "ecgmm_conv2d_dgrad_reduce": [_p] * 9 + [_i] * 11 + [_p],
     "ecgmm_conv2d_wgrad": [_p, _p, _p] + [_i] * 10 + [_p, _ll, _p],
     "ecgmm_conv2d_wgrad_workspace": [_i] * 10,
     # BatchNorm / ReLU / pooling
@@ -50,7 +52,7 @@ SIGNATURES = {
     "ecgmm_bn_apply": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "ecgmm_bn_relu_maxpool": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "ecgmm_bn_bwd_reduce": [_p] * 10 + [_i] * 6 + [_p],
-    "ecgmm_bn_bwd_finalize": [_p, _p, _i, _i, _i, _ll] + [_p] * 11 + [_p],
+    "ecgmm_bn_bwd_finalize": [_p, _p, _i, _i, _i, _ll] + [_p] * 11 + [_ll, _p],
     "ecgmm_bn_bwd_apply": [_p] * 13 + [_i] * 5 + [_p],
     "ecgmm_avgpool_fwd": [_p, _p, _i, _i, _i, _p],
     "ecgmm_avgpool_bwd": [_p, _p, _i, _i, _i, _p],

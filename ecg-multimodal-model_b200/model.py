@@ -320,8 +320,20 @@ def _conv_block_fwd(blk, x, save, one_d=False):
     return out, rec
 
 
-def _conv_block_bwd(blk, rec, dout, G):
-    """Returns the gradient w.r.t. the block input.
+# BatchNorm-backward sums (sum dz, sum dz * xhat) from the epilogue of the data gradient that produces dz
+# (ecgmm_conv2d_dgrad_reduce, offered for the 64-channel layers).  Correct and under test, but OFF by default: measured
+# on a B200 at batch 512 (profiles/r02e_*) the three reduction passes it removes cost 2.8 ms while the epilogue work
+# makes those three data gradients 4.7 ms slower (one epilogue warp per TMEM quadrant is the bottleneck: ~2500 clocks
+# per tile against 1152 of MMAs) -- step 123.3 ms with, 121.4 ms without.
+FUSED_BWD_REDUCE = os.environ.get("ECGMM_FUSED_BWD_REDUCE", "0") == "1"
+
+
+def _conv_block_bwd(blk, rec, dout, G, dout_partials=None, next_reduce=None):
+    """Returns (gradient w.r.t. the block input, BwdPartials or None).
+    dout_partials: the producer of `dout` already reduced it against this block's bn2 (ops.conv2d_dgrad(reduce_for=));
+    next_reduce = (bn_x, mask, BNStats) of the BatchNorm that will consume the returned gradient (the previous block's
+    bn2): where the library offers it, the last data gradient of this block reduces for it and the partials are
+    returned alongside.
     (Weight gradients on their own stream underneath the BatchNorm backward were tried and measured on a B200 --
     profiles/r02a_*: batch 512 131.5 vs 132.4 ms, the weight-gradient class itself 42 vs 34 ms -- and removed.)"""
     x, a, sa, m, b, sb, d, sd, mask_m, mask_out, se_rec = rec
@@ -345,14 +357,18 @@ def _conv_block_bwd(blk, rec, dout, G):
             lib.call("ecgmm_colsum", ops._ptr(dpre1), ops._ptr(G(se.fc[0].bias)), n, w1.shape[0], 0, ops._s())
             return q
 
+    fuse = FUSED_BWD_REDUCE and se is None
     db_, dz = ops.bn_backward(b, dout, sb, blk.bn2.weight, mask=mask_out, se=gate, se_ctx=se_ctx, want_dz=True,
-                              dgamma=G(blk.bn2.weight), dbeta=G(blk.bn2.bias))
+                              dgamma=G(blk.bn2.weight), dbeta=G(blk.bn2.bias),
+                              partials=dout_partials if fuse else None)
     del dout
     ops.conv2d_wgrad(m, db_, G(blk.conv2.weight), R, S, 1)
     _, w2d = blk.conv2.shadows()
-    dm = ops.conv2d_dgrad(db_, w2d, (m.shape[1], m.shape[2]), 1)
+    dm, pm = ops.conv2d_dgrad(db_, w2d, (m.shape[1], m.shape[2]), 1, reduce_for=(a, mask_m, sa)) if fuse else \
+        (ops.conv2d_dgrad(db_, w2d, (m.shape[1], m.shape[2]), 1), None)
     del db_
-    da, _ = ops.bn_backward(a, dm, sa, blk.bn1.weight, mask=mask_m, dgamma=G(blk.bn1.weight), dbeta=G(blk.bn1.bias))
+    da, _ = ops.bn_backward(a, dm, sa, blk.bn1.weight, mask=mask_m, dgamma=G(blk.bn1.weight), dbeta=G(blk.bn1.bias),
+                            partials=pm)
     del dm
     ops.conv2d_wgrad(x, da, G(blk.conv1.weight), R, S, s)
     _, w1d = blk.conv1.shadows()
@@ -361,10 +377,16 @@ def _conv_block_bwd(blk, rec, dout, G):
         dd, _ = ops.bn_backward(d, dz, sd, dsbn.weight, y=None, dgamma=G(dsbn.weight), dbeta=G(dsbn.bias))
         ops.conv2d_wgrad(x, dd, G(dsc.weight), 1, 1, s)
         dx = ops.conv2d_dgrad(da, w1d, (H, W), s)
-        ops.conv2d_dgrad(dd, dsc.shadows()[1], (H, W), s, out=dx, accumulate=True)
+        if fuse and next_reduce is not None:
+            dx, px = ops.conv2d_dgrad(dd, dsc.shadows()[1], (H, W), s, out=dx, accumulate=True, reduce_for=next_reduce)
+        else:
+            px = None
+            ops.conv2d_dgrad(dd, dsc.shadows()[1], (H, W), s, out=dx, accumulate=True)
+    elif fuse and next_reduce is not None:
+        dx, px = ops.conv2d_dgrad(da, w1d, (H, W), s, out=dz, accumulate=True, reduce_for=next_reduce)
     else:
-        dx = ops.conv2d_dgrad(da, w1d, (H, W), s, out=dz, accumulate=True)
-    return dx
+        dx, px = ops.conv2d_dgrad(da, w1d, (H, W), s, out=dz, accumulate=True), None
+    return dx, px
 
 
 class ResNet18(_Stage):
@@ -441,8 +463,12 @@ class ResNet18(_Stage):
         dx = ops.avgpool_bwd(dpooled, last_shape)
         blocks = self.blocks()
         stem_out = recs[0][0]  # pooled stem output = input of layer1.0
+        px = None
         for i in range(len(blocks) - 1, -1, -1):
-            dx = _conv_block_bwd(blocks[i], recs[i], dx, G)
+            # rec = (x, a, sa, m, b, sb, d, sd, mask_m, mask_out, se_rec): the gradient this block returns is the
+            # upstream gradient of the previous block's bn2 (input b, ReLU mask mask_out, statistics sb)
+            nr = (recs[i - 1][4], recs[i - 1][9], recs[i - 1][5]) if i > 0 else None
+            dx, px = _conv_block_bwd(blocks[i], recs[i], dx, G, dout_partials=px, next_reduce=nr)
             recs[i] = None
             if i in (6, 4, 2):  # a ResNet stage (2 blocks) is complete: its gradients are final
                 self._notify(G, G.end_of(blocks[i].conv1.weight))
@@ -691,7 +717,7 @@ class ResNet1D_SE(_Stage):
         blocks = self.blocks()
         stem_out = recs[0][0]
         for i in range(len(blocks) - 1, -1, -1):
-            dx = _conv_block_bwd(blocks[i], recs[i], dx, G)
+            dx, _ = _conv_block_bwd(blocks[i], recs[i], dx, G)
             recs[i] = None
         bn0 = self.initial[1]
         dc0, _ = ops.bn_backward(c0, dx, st0, bn0.weight, argmax=arg, dgamma=G(bn0.weight), dbeta=G(bn0.bias),

@@ -48,7 +48,9 @@ def _s():
 PROFILE = None
 
 
-def _timed(kind, flops, name, *args):
+def _timed(kind, flops, name, *args, nbytes=None):
+    """flops: the class's roofline work (FLOPs for the conv kinds, bytes for the bandwidth-bound ones);
+    nbytes: for conv kinds additionally the activation + weight bytes a launch has to move (HBM side of the roofline)."""
     if PROFILE is None:
         lib.call(name, *args)
         return
@@ -56,7 +58,7 @@ def _timed(kind, flops, name, *args):
     e0.record()
     lib.call(name, *args)
     e1.record()
-    PROFILE.append((kind, flops, e0, e1))
+    PROFILE.append((kind, flops, e0, e1, nbytes))
 
 
 # Pure shape queries of the library (no launch): asked once per shape, then served from a dict.
@@ -134,10 +136,10 @@ def conv2d_fwd(x: torch.Tensor, w_fwd: torch.Tensor, stride: int = 1, want_stats
         part = StatPartials(rows, Cout, x.device)
         _timed(f"conv_fwd/{Cin}x{Cout}k{R}{S}s{stride}", 2.0 * N * Ho * Wo * Cout * Cin * R * S, "ecgmm_conv2d_fwd_stats",
                _ptr(x), _ptr(w_fwd), _ptr(y), _ptr(part.psum), _ptr(part.psq), N, H, W, Cin, Cout, R, S, stride, pH, pW,
-               _s())
+               _s(), nbytes=2.0 * (x.numel() + y.numel() + w_fwd.numel()))
         return y, part
     _timed(f"conv_fwd/{Cin}x{Cout}k{R}{S}s{stride}", 2.0 * N * Ho * Wo * Cout * Cin * R * S, "ecgmm_conv2d_fwd", _ptr(x), _ptr(w_fwd), _ptr(y), N,
-           H, W, Cin, Cout, R, S, stride, pH, pW, _s())
+           H, W, Cin, Cout, R, S, stride, pH, pW, _s(), nbytes=2.0 * (x.numel() + y.numel() + w_fwd.numel()))
     return y
 
 
@@ -161,8 +163,46 @@ def conv2d_fwd_bn(x: torch.Tensor, w_fwd: torch.Tensor, st, stride: int = 1, res
     return y
 
 
+class BwdPartials:
+    """Partial BatchNorm-backward sums (sum dz, sum dz * xhat) written by a data-gradient epilogue: p1 / p2
+    [rows][C] fp32, for bn_backward(partials=...)."""
+    __slots__ = ("p1", "p2", "rows")
+
+    def __init__(self, rows, C, device):
+        buf = torch.empty(2 * rows * C, dtype=torch.float32, device=device)
+        self.p1, self.p2, self.rows = buf[: rows * C], buf[rows * C:], rows
+
+
 def conv2d_dgrad(dy: torch.Tensor, w_dgrad: torch.Tensor, in_hw, stride: int = 1, out: torch.Tensor = None,
-                 accumulate: bool = False) -> torch.Tensor:
+                 accumulate: bool = False, reduce_for=None):
+    """dx = conv_transpose(dy, w) (+= when accumulate).
+    reduce_for = (bn_x, mask or None, BNStats): dx is the upstream gradient of that BatchNorm(+ReLU); returns
+    (dx, BwdPartials or None) -- the reduction pass of its backward from the epilogue where the library offers it."""
+    if reduce_for is not None:
+        bn_x, bn_mask, st = reduce_for
+        N, Ho, Wo, Cout = dy.shape
+        Cin, R, S, _ = w_dgrad.shape
+        H, W = in_hw
+        rows = _shape_query("ecgmm_conv2d_dgrad_reduce_rows", N, H, W, Cin, Cout, R, S, stride, R // 2, S // 2)
+        if rows == 0:
+            return conv2d_dgrad(dy, w_dgrad, in_hw, stride, out, accumulate), None
+        _chk(dy, BF16, "dy")
+        _chk(w_dgrad, BF16, "w_dgrad")
+        _chk(bn_x, BF16, "bn_x")
+        assert tuple(bn_x.shape) == (N, H, W, Cin)
+        if out is None:
+            assert not accumulate
+            out = torch.empty((N, H, W, Cin), dtype=BF16, device=dy.device)
+        else:
+            _chk(out, BF16, "out")
+            assert tuple(out.shape) == (N, H, W, Cin)
+        part = BwdPartials(rows, Cin, dy.device)
+        _timed(f"conv_dgrad/{Cin}x{Cout}k{R}{S}s{stride}+red", 2.0 * N * Ho * Wo * Cout * Cin * R * S,
+               "ecgmm_conv2d_dgrad_reduce", _ptr(dy), _ptr(w_dgrad), _ptr(out), _ptr(bn_x), _ptr(bn_mask),
+               _ptr(st.mean), _ptr(st.invstd), _ptr(part.p1), _ptr(part.p2), N, H, W, Cin, Cout, R, S, stride, R // 2,
+               S // 2, int(accumulate), _s(),
+               nbytes=2.0 * (dy.numel() + (3 if accumulate else 2) * out.numel() + w_dgrad.numel()) + out.numel() / 8)
+        return out, part
     _chk(dy, BF16, "dy")
     _chk(w_dgrad, BF16, "w_dgrad")
     N, Ho, Wo, Cout = dy.shape
@@ -178,7 +218,8 @@ def conv2d_dgrad(dy: torch.Tensor, w_dgrad: torch.Tensor, in_hw, stride: int = 1
         _chk(out, BF16, "out")
         assert tuple(out.shape) == (N, H, W, Cin)
     _timed(f"conv_dgrad/{Cin}x{Cout}k{R}{S}s{stride}", 2.0 * N * Ho * Wo * Cout * Cin * R * S, "ecgmm_conv2d_dgrad", _ptr(dy), _ptr(w_dgrad),
-           _ptr(out), N, H, W, Cin, Cout, R, S, stride, pH, pW, int(accumulate), _s())
+           _ptr(out), N, H, W, Cin, Cout, R, S, stride, pH, pW, int(accumulate), _s(),
+           nbytes=2.0 * (dy.numel() + (2 if accumulate else 1) * out.numel() + w_dgrad.numel()))
     return out
 
 
@@ -194,7 +235,7 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, R: int, S:
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
     _timed(f"conv_wgrad/{Cin}x{Cout}k{R}{S}s{stride}", 2.0 * N * dy.shape[1] * dy.shape[2] * Cout * Cin * R * S,
            "ecgmm_conv2d_wgrad", _ptr(x), _ptr(dy), _ptr(dw), N, H, W, Cin, Cout, R, S, stride, R // 2, S // 2, _ptr(ws),
-           ws_bytes, _s())
+           ws_bytes, _s(), nbytes=2.0 * (x.numel() + dy.numel()) + 4.0 * dw.numel())
 
 
 # ---------------------------------------------------------------- ResNet stem
@@ -346,7 +387,7 @@ def bn_relu_maxpool(x, st: BNStats, want_argmax=True):
 
 
 def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=None, want_dz=False,
-                need_param_grads=True, dgamma=None, dbeta=None, mask=None, pooled=None, beta=None):
+                need_param_grads=True, dgamma=None, dbeta=None, mask=None, pooled=None, beta=None, partials=None):
     """BatchNorm (+ReLU / +SE gate / +stem max-pool) backward.
 
     x: raw convolution output [N,H,W,C]; dy: upstream gradient (pooled-shape for the stem, mode 2);
@@ -368,14 +409,16 @@ def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=
     mode = 2 if argmax is not None else (3 if mask is not None else (1 if y is not None else 0))
     if mode == 3:
         argmax, y = mask, None  # the C ABI carries the bit mask in the argmax slot
-    split = _shape_query("ecgmm_reduce_split", N, P, C)
-    part = _f32(2 * N * split * C, dev)
-    p1, p2 = part[: N * split * C], part[N * split * C:]
     # algorithmic bytes of the two backward passes: x + (dy | pooled dy + argmax) [+ y]; the apply pass also writes dx [+ dz]
     rd = 2.0 * N * P * C * (3 if mode == 1 else 2) if mode != 2 else 2.0 * N * P * C + 3.0 * dy.numel()
     if mode == 3:
         rd += N * P * C / 8
-    if mode == 2 and pooled is not None and beta is not None:
+    count = 0
+    if partials is not None:
+        # the data gradient that produced dy already reduced (x, dy, mask): one row of partials per CTA
+        assert se is None and mode in (0, 3)
+        p1, p2, split, count = partials.p1, partials.p2, 1, N * P
+    elif mode == 2 and pooled is not None and beta is not None:
         # stem: sum dz / sum dz*xhat over the pooled tensors (each pooled gradient reaches exactly one pre-pool
         # element, whose normalised value is (y - beta) / gamma when y > 0)
         _, Hp, Wp, _ = pooled.shape
@@ -385,6 +428,9 @@ def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=
         _timed(f"bn_bwd_reduce/m4C{C}", 4.0 * pooled.numel(), "ecgmm_bn_bwd_reduce", _ptr(pooled), _ptr(dy), None,
                None, _ptr(beta), _ptr(gamma), None, None, _ptr(p1), _ptr(p2), N, Hp, Wp, C, split, 4, _s())
     else:
+        split = _shape_query("ecgmm_reduce_split", N, P, C)
+        part = _f32(2 * N * split * C, dev)
+        p1, p2 = part[: N * split * C], part[N * split * C:]
         _timed(f"bn_bwd_reduce/m{mode}C{C}", rd, "ecgmm_bn_bwd_reduce", _ptr(x), _ptr(dy), _ptr(y), _ptr(argmax),
                _ptr(st.mean), _ptr(st.invstd), _ptr(st.scale), _ptr(st.shift), _ptr(p1), _ptr(p2), N, H_, W_, C, split,
                mode, _s())
@@ -393,10 +439,10 @@ def bn_backward(x, dy, st: BNStats, gamma, y=None, argmax=None, se=None, se_ctx=
         q = se_ctx(p1, p2, split)
     coef = _f32(3 * C, dev)
     cA, cB, cD = coef[:C], coef[C:2 * C], coef[2 * C:]
-    lib.call("ecgmm_bn_bwd_finalize", _ptr(p1), _ptr(p2), N, split, C, P, _ptr(gamma), _ptr(st.mean),
-             _ptr(st.invstd), _ptr(se), _ptr(q), _ptr(st.nsum if se is not None else None),
-             _ptr(dgamma if need_param_grads else None), _ptr(dbeta if need_param_grads else None), _ptr(cA),
-             _ptr(cB), _ptr(cD), _s())
+    lib.call("ecgmm_bn_bwd_finalize", _ptr(p1), _ptr(p2), partials.rows if partials is not None else N, split, C, P,
+             _ptr(gamma), _ptr(st.mean), _ptr(st.invstd), _ptr(se), _ptr(q),
+             _ptr(st.nsum if se is not None else None), _ptr(dgamma if need_param_grads else None),
+             _ptr(dbeta if need_param_grads else None), _ptr(cA), _ptr(cB), _ptr(cD), count, _s())
     dx = torch.empty_like(x)
     dz = torch.empty_like(x) if want_dz else None
     _timed(f"bn_bwd_apply/m{mode}C{C}{'+dz' if want_dz else ''}", rd + 2.0 * N * P * C * (2 if want_dz else 1), "ecgmm_bn_bwd_apply", _ptr(x), _ptr(dy),
@@ -430,7 +476,8 @@ def signal_stem_fwd(x, w):
     B, Cin, L = x.shape
     Lo = (L - 1) // 2 + 1
     y = torch.empty((B, 1, Lo, 64), dtype=BF16, device=x.device)
-    lib.call("ecgmm_signal_stem_fwd", _ptr(x), _ptr(w), _ptr(y), B, Cin, L, _s())
+    _timed("signal_stem_fwd", 2.0 * B * Lo * 64 * Cin * 7, "ecgmm_signal_stem_fwd", _ptr(x), _ptr(w), _ptr(y), B, Cin, L,
+           _s(), nbytes=4.0 * x.numel() + 2.0 * y.numel())
     return y
 
 
@@ -438,7 +485,8 @@ def signal_stem_wgrad(x, dy, dw):
     B, Cin, L = x.shape
     ws_bytes = _shape_query("ecgmm_signal_stem_wgrad_workspace", B, Cin, L)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
-    lib.call("ecgmm_signal_stem_wgrad", _ptr(x), _ptr(dy), _ptr(dw), B, Cin, L, _ptr(ws), ws_bytes, _s())
+    _timed("signal_stem_wgrad", 2.0 * dy.numel() * Cin * 7, "ecgmm_signal_stem_wgrad", _ptr(x), _ptr(dy), _ptr(dw), B, Cin,
+           L, _ptr(ws), ws_bytes, _s(), nbytes=4.0 * x.numel() + 2.0 * dy.numel())
 
 
 def se_fwd(nsum, st: BNStats, w1, b1, w2, b2, L):

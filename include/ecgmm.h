@@ -106,6 +106,17 @@ int ecgmm_conv2d_fwd_stats(const ecgmm_bf16* x, const ecgmm_bf16* w_fwd, ecgmm_b
 int ecgmm_conv2d_dgrad(const ecgmm_bf16* dy, const ecgmm_bf16* w_dgrad, ecgmm_bf16* dx, int N, int H, int W,
                        int Cin, int Cout, int R, int S, int stride, int padH, int padW, int accumulate,
                        void* stream);
+/* The same data gradient + the reduction pass of the BatchNorm(+ReLU) backward that consumes dx as its upstream
+ * gradient (torch: batch_norm_backward's sum(dy), sum(dy * xhat)), computed in the epilogue while the dx tile is on
+ * chip: bn_x [N][H][W][Cin] is that BatchNorm's input, bn_mask its ReLU decisions (one byte per 8 channels; NULL: no
+ * ReLU), bn_mean / bn_invstd [Cin] its batch statistics; p1 / p2 [ecgmm_conv2d_dgrad_reduce_rows()][Cin] receive
+ * partial sums of dz and dz * xhat (dz = dx * relu') for ecgmm_bn_bwd_finalize(count = N*H*W).  rows == 0: not
+ * offered for the shape -- use ecgmm_conv2d_dgrad + ecgmm_bn_bwd_reduce. */
+int ecgmm_conv2d_dgrad_reduce_rows(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int padH, int padW);
+int ecgmm_conv2d_dgrad_reduce(const ecgmm_bf16* dy, const ecgmm_bf16* w_dgrad, ecgmm_bf16* dx, const ecgmm_bf16* bn_x,
+                              const uint8_t* bn_mask, const float* bn_mean, const float* bn_invstd, float* p1,
+                              float* p2, int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int padH,
+                              int padW, int accumulate, void* stream);
 /* dw (fp32, OIHW) += x^T * dy.  The pixel range is split across CTAs (split-K); with a workspace of at
  * least ecgmm_conv2d_wgrad_workspace() bytes the partials are combined by a second deterministic kernel,
  * otherwise (workspace NULL / too small / shape not covered, query returns 0) by fp32 atomics. */
@@ -169,7 +180,9 @@ int ecgmm_bn_bwd_reduce(const ecgmm_bf16* x, const ecgmm_bf16* dy, const ecgmm_b
 int ecgmm_bn_bwd_finalize(const float* p1, const float* p2, int N, int split, int C, long long per_sample,
                           const float* gamma, const float* mean, const float* invstd, const float* se,
                           const float* q, const float* nsum, float* dgamma, float* dbeta, float* coefA,
-                          float* coefB, float* coefD, void* stream);
+                          float* coefB, float* coefD, long long count, void* stream);
+/* (p1 / p2 hold N * split rows; the mean is taken over count elements per channel, or over N * per_sample when count
+ *  is 0 -- partials written by ecgmm_conv2d_dgrad_reduce have one row per CTA, not per sample: pass count = N*H*W) */
 /* dx (gradient of the convolution output) and optionally dz_out = the masked upstream gradient
  * (what flows into the residual branch). */
 int ecgmm_bn_bwd_apply(const ecgmm_bf16* x, const ecgmm_bf16* dy, const ecgmm_bf16* y, const uint8_t* argmax,

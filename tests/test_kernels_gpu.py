@@ -318,7 +318,7 @@ def test_basic_block_1d_se():
     out, rec = M._conv_block_fwd(blk, xin, save=True)
     assert rel_l2(out[:, 0].permute(0, 2, 1), out_ref) < 1e-2
     G = M.GradArena(list(blk.parameters()), DEV)
-    dx = M._conv_block_bwd(blk, rec, dout.permute(0, 2, 1).contiguous().view(6, 1, -1, 128), G)
+    dx, _ = M._conv_block_bwd(blk, rec, dout.permute(0, 2, 1).contiguous().view(6, 1, -1, 128), G)
     assert rel_l2(dx[:, 0].permute(0, 2, 1), xr.grad) < 5e-2
     scale = max(float(p.grad.norm()) for p in ref.parameters())
     for (k, pr), (_, p) in zip(ref.named_parameters(), blk.named_parameters()):
@@ -357,7 +357,7 @@ def test_basic_block_2d(cin, cout, stride, H, W):
     out, rec = M._conv_block_fwd(blk, nhwc(x), save=True)
     assert rel_l2(nchw(out), out_ref) < 1e-2
     G = M.GradArena(list(blk.parameters()), DEV)
-    dx = M._conv_block_bwd(blk, rec, nhwc(dout), G)
+    dx, _ = M._conv_block_bwd(blk, rec, nhwc(dout), G)
     assert rel_l2(nchw(dx), xr.grad) < 5e-2
     for (k, pr), (_, p) in zip(ref.named_parameters(), blk.named_parameters()):
         assert rel_l2(G(p), pr.grad) < 5e-2, (k, rel_l2(G(p), pr.grad))
@@ -437,3 +437,42 @@ def test_stem_epilogue_statistics(N, H, W):
     q = part.psq.view(part.rows, 64).double().sum(0)
     assert ((s - yd.sum(0)).abs() <= 1e-5 * yd.abs().sum(0) + 1e-6).all()
     assert ((q - (yd * yd).sum(0)).abs() <= 1e-5 * (yd * yd).sum(0) + 1e-6).all()
+
+
+@pytest.mark.parametrize("N,H,W,accumulate,with_mask", [(3, 21, 150, False, True), (2, 63, 625, True, True),
+                                                         (2, 5, 130, True, False)])
+def test_dgrad_epilogue_reduces_for_batchnorm_backward(N, H, W, accumulate, with_mask):
+    """conv2d_dgrad(reduce_for=(x, mask, stats)): same dx as without, and the partial rows fold to sum dz and
+    sum dz * xhat of the STORED dx against that BatchNorm's input -- so bn_backward(partials=...) returns what the
+    separate reduction pass returns."""
+    g = gen(f"dgred{N}{H}{W}{accumulate}{with_mask}")
+    C = 64
+    dy = torch.randn(N, H, W, C, generator=g).to(DEV).to(BF)
+    w = (torch.randn(C, C, 3, 3, generator=g) / 24).to(DEV)
+    _, w_dg = ops.conv_weight_prep(w)
+    xbn = (torch.randn(N, H, W, C, generator=g) * 1.5 + 0.3).to(DEV).to(BF)
+    bn = torch.nn.BatchNorm2d(C).to(DEV)
+    st = ops.bn_train_stats(xbn, bn.weight, bn.bias, None, None, None, 1e-5, 0.1)
+    mask = None
+    if with_mask:
+        _, mask = ops.bn_apply(xbn, st, relu=True, want_mask=True)
+    old = torch.randn(N, H, W, C, generator=g).to(DEV).to(BF) if accumulate else None
+    ref_dx = ops.conv2d_dgrad(dy, w_dg, (H, W), 1, out=None if old is None else old.clone(), accumulate=accumulate)
+    dx, part = ops.conv2d_dgrad(dy, w_dg, (H, W), 1, out=None if old is None else old.clone(), accumulate=accumulate,
+                                reduce_for=(xbn, mask, st))
+    assert part is not None and torch.equal(dx, ref_dx)
+    dz = dx.double()
+    if with_mask:
+        bits = torch.stack([(mask.view(N, H, W, C // 8) >> j) & 1 for j in range(8)], dim=-1).reshape(N, H, W, C)
+        dz = dz * bits.double()
+    xhat = (xbn.double() - st.mean.double()) * st.invstd.double()
+    s1, s2 = dz.reshape(-1, C).sum(0), (dz * xhat).reshape(-1, C).sum(0)
+    p1 = part.p1.view(part.rows, C).double().sum(0)
+    p2 = part.p2.view(part.rows, C).double().sum(0)
+    scale1, scale2 = dz.abs().reshape(-1, C).sum(0), (dz * xhat).abs().reshape(-1, C).sum(0)
+    assert ((p1 - s1).abs() <= 2e-5 * scale1 + 1e-5).all()
+    assert ((p2 - s2).abs() <= 2e-5 * scale2 + 1e-5).all()
+    dg_a, db_a, dg_b, db_b = (torch.zeros(C, device=DEV) for _ in range(4))
+    a, _ = ops.bn_backward(xbn, dx, st, bn.weight, mask=mask, dgamma=dg_a, dbeta=db_a)
+    b, _ = ops.bn_backward(xbn, dx, st, bn.weight, mask=mask, dgamma=dg_b, dbeta=db_b, partials=part)
+    assert rel_l2(b, a) < 2e-3 and rel_l2(dg_b, dg_a) < 1e-4 and rel_l2(db_b, db_a) < 1e-4

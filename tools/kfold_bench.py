@@ -1,14 +1,16 @@
 """configs[4]: train_kfold.py-style 5-fold training with the folds sharded across the GPUs of one box, on a synthetic
 tri-modal data set (development / profiles helper).
 
-    python tools/kfold_bench.py [--patients 10000] [--folds 5] [--epochs 1] [--batch 64] [--height 64 --width 160]
+    python tools/kfold_bench.py [--patients 10000] [--folds 5] [--epochs 1] [--batch 64] [--height 224 --width 224]
+    (= bench.py --config kfold)
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/kfold_bench.py
 
 Folds are independent jobs: fold k runs on rank k mod world (ecgmm.parallel.folds_for_rank), no collective on the data
 path; rank 0 gathers the per-fold wall times and accuracies at the end.  StratifiedKFold(5, shuffle, seed 42) as in
 train_kfold.py:137.  The data set is synthetic and SEPARABLE (the label shifts the clinical features and the signal
-amplitude), so the held-out accuracy shows that the folds really train; the default image size is 64x160 to keep
-10 000 patients in memory -- pass --height 250 --width 2500 --patients 2000 for the native resolution.
+amplitude), so the held-out accuracy shows that the folds really train.  Image size: 224 x 224 (SURVEY.md section 8d
+allows "the same per-sample shapes as cfg3 or 224^2 for tractability -- state which": 10 000 patients are 1.5 GB of
+uint8 pixels on the host at 224^2 and 18.75 GB at 250 x 2500; pass --height 250 --width 2500 for the native size).
 Each fold uses ecgmm.graph.GraphedTrainStep (one launch per step) with fusion_only=True (the single-tensor API of
 train_kfold.py:59-64)."""
 import argparse
@@ -21,16 +23,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--patients", type=int, default=10000)
     ap.add_argument("--folds", type=int, default=5)
     ap.add_argument("--epochs", type=int, default=1)
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--height", type=int, default=64)
-    ap.add_argument("--width", type=int, default=160)
+    ap.add_argument("--height", type=int, default=224)
+    ap.add_argument("--width", type=int, default=224)
     ap.add_argument("--length", type=int, default=2476)
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -50,6 +52,7 @@ def main():
     lib.require_device()
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     g = torch.Generator().manual_seed(42)
     P = args.patients
@@ -105,7 +108,9 @@ def main():
         dist.destroy_process_group()
     if rank == 0:
         results.sort(key=lambda r: r["fold"])
-        print(json.dumps({"metric": "k-fold training, folds sharded over GPUs", "n_gpus": world,
+        print(json.dumps({"metric": "k-fold training, folds sharded over GPUs", "n_gpus": world, "unit": "samples/s",
+                          "value": round(sum(r["train_samples"] for r in results) / max(r["seconds"] for r in results), 1),
+                          "higher_is_better": True,
                           "config": {"workload": "configs[4]", "patients": P, "folds": args.folds, "epochs": args.epochs,
                                      "image": [3, args.height, args.width], "batch": args.batch, "input": "uint8 pixels"},
                           "wall_s_max_over_folds": max(r["seconds"] for r in results),

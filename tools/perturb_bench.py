@@ -1,6 +1,9 @@
-"""configs[3] on one B200: 4096 masked variants per sample through the fusion head (development / profiles helper).
+"""configs[3]: 4096 masked variants per sample through the fusion head, samples sharded over the GPUs of one box
+(replicas only: no collective on the data path, the [samples, variants] probabilities are gathered on rank 0 at the end
+of every call, inside the timed region).  = bench.py --config perturb
 
-    python tools/perturb_bench.py [--samples 256] [--variants 4096] [--cpu-samples 2]
+    python tools/perturb_bench.py [--samples 256 (per GPU)] [--variants 4096] [--cpu-samples 2]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/perturb_bench.py
 
 Prints one JSON line: samples/s and variants/s of ecgmm.explain.perturbation_inference (device-resident inputs,
 CUDA events), the per-kernel split (variant build: HBM-bound, GEMM: tensor-bound, tail: HBM-bound) with achieved
@@ -15,22 +18,31 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--samples", type=int, default=256)
     ap.add_argument("--variants", type=int, default=4096)
     ap.add_argument("--cpu-samples", type=int, default=2)
     ap.add_argument("--iters", type=int, default=10)
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     import torch
+    import torch.distributed as dist
 
     import ecgmm
     from ecgmm import explain, lib
+    from ecgmm.parallel import shard_batch
     from oracle import model as om
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
     lib.require_device()
-    dev = torch.device("cuda", 0)
-    S, V, D, HID = args.samples, args.variants, 768, 128
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    S, V, D, HID = args.samples, args.variants, 768, 128  # S = samples per GPU (weak scaling)
 
     class Cfg:
         num_classes = 2
@@ -40,25 +52,40 @@ def main():
     model = ecgmm.ECGMultimodalModel(Cfg).eval()
     head = model.fusion_classifier
     g = torch.Generator().manual_seed(42)
-    e = torch.randn(S, D, generator=g)
+    e_all = torch.randn(S * world, D, generator=g)     # the whole job's samples; rank r takes its shard
+    (e,) = shard_batch([e_all], rank, world)
     bg = torch.randn(100, D, generator=g).mean(0)
     masks = (torch.rand(V, D, generator=g) < 0.5).to(torch.uint8)
     ed, bd, md = e.to(dev), bg.to(dev), masks.to(dev)
+    gathered = [torch.empty(S, V, dtype=torch.float32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def job():
+        out = explain.perturbation_inference(head, ed, bd, md, 1)
+        if world > 1:  # [S, V] probabilities of every shard -> rank 0
+            dist.gather(out.contiguous(), gathered, dst=0)
+        return out
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
     for _ in range(3):
-        explain.perturbation_inference(head, ed, bd, md, 1)
+        job()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     t = {"build": 0.0, "gemm": 0.0, "tail": 0.0}
     e0, e1 = ev(), ev()
     e0.record()
     for _ in range(args.iters):
-        out = explain.perturbation_inference(head, ed, bd, md, 1)
+        out = job()
     e1.record()
     torch.cuda.synchronize()
     total_ms = e0.elapsed_time(e1) / args.iters
+    if world > 1:  # the job is as slow as its slowest rank
+        tm = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        total_ms = float(tm.item())
     # per-kernel split (same calls, bracketed individually)
     from ecgmm import ops
 
@@ -95,6 +122,10 @@ def main():
     kern["perturb_build"]["frac"] = round(kern["perturb_build"]["achieved_GBs"] / peaks["hbm_gbs"], 3)
     kern["gemm_1x1_tcgen05"]["frac"] = round(kern["gemm_1x1_tcgen05"]["achieved_TFLOPs"] / peaks["bf16_tflops_sustained"], 3)
     kern["head_tail"]["frac"] = round(kern["head_tail"]["achieved_GBs"] / peaks["hbm_gbs"], 3)
+    if rank != 0:
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     # CPU oracle on a bounded sample
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -104,13 +135,19 @@ def main():
     t0 = time.perf_counter()
     ref = om.perturbation_inference(ora.fusion_classifier, e[:ns], bg, masks, 1)
     cpu_s = time.perf_counter() - t0
-    line = {"metric": "perturbation-inference samples/sec (4096 variants each)", "value": S / (total_ms * 1e-3),
-            "unit": "samples/s", "variants_per_s": rows / (total_ms * 1e-3), "ms_per_call": total_ms, "n_gpus": 1,
-            "config": {"workload": "configs[3]: masked variants through fusion_classifier", "samples": S, "variants": V,
-                       "D": D, "hidden": HID}, "dtype": "bf16", "kernels": kern,
+    line = {"metric": "perturbation-inference samples/sec (4096 variants each)", "value": S * world / (total_ms * 1e-3),
+            "unit": "samples/s", "variants_per_s": rows * world / (total_ms * 1e-3), "ms_per_call": total_ms,
+            "n_gpus": world, "scaling": "weak", "higher_is_better": True,
+            "config": {"workload": "configs[3]: masked variants through fusion_classifier", "samples_per_gpu": S,
+                       "samples": S * world, "variants": V, "D": D, "hidden": HID,
+                       "parallelism": f"samples sharded over {world} GPU(s), probabilities gathered on rank 0"},
+            "dtype": "bf16", "kernels": kern,
             "cpu_baseline": {"value": ns / cpu_s, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": f"{ns} samples x {V} variants through oracle.model.perturbation_inference (fp32)"}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
