@@ -56,6 +56,11 @@ struct alignas(64) NtParams {
   const float* shift;
   const __nv_bfloat16* res;
   int relu;
+  // igemm_nt_pair_kernel (cta_group::2): the weight matrix with a box of HALF an N tile (each CTA of a pair loads and
+  // feeds half of B), the number of 128-pixel tiles and of (tile pair, N tile) work items
+  CUtensorMap b_map_half;
+  int m_tiles, total_pairs;
+  int pair_ok;  // b_map_half has been built
 };
 
 template <int BN, int STAGES>
@@ -285,6 +290,248 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_kernel(const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same GEMM on CTA PAIRS (tcgen05 cta_group::2): the two CTAs of a cluster work on two adjacent 128-pixel tiles and
+// the same N tile; ONE MMA of M = 256 per K step, issued by rank 0, reads rank r's 128 A rows and rank r's HALF of the
+// B tile from rank r's shared memory and writes rank r's accumulator rows to rank r's TMEM.
+// Why (findings): the shared memory of an SM moves 128 B/clk, and TMA writes and MMA operand reads share
+// it.  The single-CTA kernel writes and reads (16 KB A + BN x 128 B of B) per 64-wide K chunk: 256 B/clk at BN = 128 (tensor pipe <=
+// 50 % busy: measured 965 of 1940 TFLOP/s at the power-capped clock), 188 B/clk at BN = 256 (<= 68 %: measured 1320).
+// With half of B per CTA: 192 B/clk (<= 67 %) at BN = 128 and 128 B/clk (not bound) at BN = 256.
+// Barriers: every CTA owns empty[] / tfull[] (arrived on by rank 0's multicast tcgen05.commit); full[] and tempty[]
+// are rank 0's (both producers' TMA bytes and all 8 epilogue warps of the pair arrive there).
+template <int BN, int STAGES>
+struct NtPairSmem {
+  static constexpr int kBHalf = (BN / 2) * 128;
+  static constexpr int kStage = kATile + kBHalf;
+  static constexpr int kBarOff = STAGES * kStage;
+  static constexpr int kStatsOff = kBarOff + 256;  // double [4 warps][2][BN]
+  static constexpr int kBytes = kStatsOff + 4 * 2 * BN * 8 + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+    igemm_nt_pair_kernel(const __grid_constant__ NtParams p) {
+  using L = NtPairSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // identical in both CTAs (same kernel, same layout)
+
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kATile;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_maps[i]);
+    tma_prefetch_desc(&p.b_map_half);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);  // 4 epilogue warps of each CTA
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, 2 * BN);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barrier initialisation and the TMEM address are visible to the whole pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nkb = p.ntaps * p.k_chunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int q = cid; q < p.total_pairs; q += n_clusters) {
+        const int nt = q % p.n_tiles_n;
+        int m = 2 * (q / p.n_tiles_n) + (int)rank;  // beyond the last tile: coordinates outside the tensor, zero fill
+        const int twi = m % p.tiles_w;
+        m /= p.tiles_w;
+        const int thi = m % p.tiles_h;
+        const int img = m / p.tiles_h;
+        const int h0 = thi * p.TH, w0 = twi * p.TW;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const Tap tp = p.taps[tap];
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * L::kStage);  // the bytes of BOTH CTAs land on this barrier
+            tma_load_4d_pair(sA + stage * kATile, &p.a_maps[tp.map], &full[stage], kc * 64, w0 + tp.dw, h0 + tp.dh,
+                             img);
+            tma_load_2d_pair(sB + stage * L::kBHalf, &p.b_map_half, &full[stage], tp.wk + kc * 64,
+                             nt * BN + (int)rank * (BN / 2));
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (rank 0 only, one elected thread)
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+      const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA), 0, 1024);
+      const uint64_t b_desc0 = make_sw128_desc(smem_u32(sB), 0, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int q = cid; q < p.total_pairs; q += n_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (kATile >> 4));
+          const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (L::kBHalf >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_pair(&empty[stage]);
+          if (kb == nkb - 1) umma_commit_pair(&tfull[acc]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (both CTAs: own 128 rows, all BN columns)
+    const int quad = warp & 3;
+    const int m_row = quad * 32 + lane;
+    const int hl = m_row >> p.tw_shift;
+    const int wl = m_row & (p.TW - 1);
+    double* st_s = reinterpret_cast<double*>(smem + L::kStatsOff) + quad * 2 * BN;
+    double* st_q = st_s + BN;
+    if (p.psum)
+      for (int c = lane; c < BN; c += 32) st_s[c] = st_q[c] = 0.0;
+    int it = 0;
+    for (int q = cid; q < p.total_pairs; q += n_clusters, ++it) {
+      const int nt = q % p.n_tiles_n;
+      const int mt = 2 * (q / p.n_tiles_n) + (int)rank;
+      int m = mt;
+      const int twi = m % p.tiles_w;
+      m /= p.tiles_w;
+      const int thi = m % p.tiles_h;
+      const int img = m / p.tiles_h;
+      const int oh = thi * p.TH + hl, ow = twi * p.TW + wl;
+      const bool valid = (mt < p.m_tiles) && (oh < p.OH) && (ow < p.OW);
+      __nv_bfloat16* dst = p.out + img * p.out_sN + oh * p.out_sH + ow * p.out_sW + nt * BN;
+
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c * 32, r);
+        tmem_ld_wait();
+        if (p.psum) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j]))) : 0.f;
+          double s = 0.0, qq = 0.0;
+          warp_colstats32(v, lane, s, qq);
+          st_s[c * 32 + lane] += s;
+          st_q[c * 32 + lane] += qq;
+        }
+        if (valid) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[g * 8 + j]);
+            if (p.accumulate) {
+              const uint4 old = d4[g];
+              const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 o = __bfloat1622float2(ob[j]);
+                f[2 * j] += o.x;
+                f[2 * j + 1] += o.y;
+              }
+            }
+            uint4 v;
+            __nv_bfloat162* vb = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) vb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            d4[g] = v;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_rank0(&tempty[acc]);  // rank 0's MMA thread waits for all 8 warps of the pair
+    }
+    if (p.psum) {
+      // the host launches a cluster count that is a multiple of n_tiles_n: every pair of this cluster has the same nt
+      const int nt = cid % p.n_tiles_n;
+      const size_t row = ((size_t)blockIdx.x * 4 + quad) * p.stats_C;
+      for (int c = lane; c < p.stats_C; c += 32) {
+        const int k = c - nt * BN;
+        const bool mine = (k >= 0 && k < BN);
+        p.psum[row + c] = mine ? (float)st_s[k] : 0.f;
+        p.psq[row + c] = mine ? (float)st_q[k] : 0.f;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // neither CTA may leave (or free TMEM) while the other can still signal or be written to
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 2 * BN);
+}
+
+// CTA pairs are used for N tiles of 128 and 256 columns (64-column layers have their own kernels) when the problem has
+// at least one pair of pixel tiles per N tile.  ECGMM_NT_PAIR=0 selects the single-CTA kernel (kept under test).
+static bool nt_pair_enabled() {
+  const char* e = getenv("ECGMM_NT_PAIR");
+  return !(e && atoi(e) == 0);
+}
+static int nt_pair_clusters(int total_pairs, int n_tiles_n) {
+  int c = total_pairs < num_sms() / 2 ? total_pairs : num_sms() / 2;
+  if (n_tiles_n > 1 && c > n_tiles_n) c -= c % n_tiles_n;
+  return c;
+}
+
+template <int BN, int STAGES>
+static int launch_nt_pair_t(NtParams& p, cudaStream_t s) {
+  using L = NtPairSmem<BN, STAGES>;
+  static bool configured[kMaxDevices] = {};
+  const int ds = device_slot();
+  if (!configured[ds]) {
+    ECGMM_CUDA(cudaFuncSetAttribute(igemm_nt_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::kBytes));
+    configured[ds] = true;
+  }
+  const int grid = 2 * nt_pair_clusters(p.total_pairs, p.n_tiles_n);
+  igemm_nt_pair_kernel<BN, STAGES><<<grid, 192, L::kBytes, s>>>(p);
+  return check_launch("igemm_nt_pair_kernel");
+}
+
 // Persistent grid: one CTA per SM, rounded down to a multiple of the number of N tiles so that a CTA always works
 // on the same N tile (t % n_tiles_n with t = blockIdx.x + k * grid): the statistics epilogue relies on it.
 static int nt_grid(int total_tiles, int n_tiles_n) {
@@ -318,8 +565,13 @@ static int launch_nt(NtParams& p, int n_gemm, cudaStream_t s) {
   ECGMM_CHECK(n_gemm % 64 == 0, ECGMM_ERR_SHAPE, "GEMM N=%d must be a multiple of 64", n_gemm);
   int bn = (n_gemm % 256 == 0) ? 256 : (n_gemm % 128 == 0 ? 128 : 64);
   p.n_tiles_n = n_gemm / bn;
-  p.total_tiles = p.n_img * p.tiles_h * p.tiles_w * p.n_tiles_n;
+  p.m_tiles = p.n_img * p.tiles_h * p.tiles_w;
+  p.total_tiles = p.m_tiles * p.n_tiles_n;
   if (p.total_tiles == 0) return ECGMM_OK;
+  if (nt_pair_enabled() && bn >= 128 && !p.scale && p.pair_ok && p.m_tiles >= 2) {
+    p.total_pairs = ((p.m_tiles + 1) / 2) * p.n_tiles_n;
+    return bn == 256 ? launch_nt_pair_t<256, 6>(p, s) : launch_nt_pair_t<128, 8>(p, s);
+  }
   if (bn == 256) return launch_nt_t<256, 4>(p, s);
   if (bn == 128) return launch_nt_t<128, 6>(p, s);
   return launch_nt_t<64, 6>(p, s);
@@ -441,7 +693,10 @@ extern "C" int ecgmm_conv2d_fwd_stats_rows(int N, int H, int W, int Cin, int Cou
   set_tile_grid(p, N, Ho, Wo);
   const int bn = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
   const int n_tiles_n = Cout / bn;
-  return 4 * nt_grid(p.n_img * p.tiles_h * p.tiles_w * n_tiles_n, n_tiles_n);
+  const int m_tiles = p.n_img * p.tiles_h * p.tiles_w;
+  if (nt_pair_enabled() && bn >= 128 && m_tiles >= 2)  // CTA pairs: 4 epilogue warps in each of 2 * clusters CTAs
+    return 4 * 2 * nt_pair_clusters(((m_tiles + 1) / 2) * n_tiles_n, n_tiles_n);
+  return 4 * nt_grid(m_tiles * n_tiles_n, n_tiles_n);
 }
 
 struct FusedEpilogue {  // folded BatchNorm (+ residual, + ReLU) applied by the forward epilogue; scale == NULL: off
@@ -484,6 +739,11 @@ static int conv2d_fwd_impl(const ecgmm_bf16* x_, const ecgmm_bf16* w_, ecgmm_bf1
   const int bn = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
   rc = make_tmap_2d(&p.b_map, w_, (uint64_t)R * S * Cin, Cout, (uint64_t)R * S * Cin * 2, 64, bn);
   if (rc) return rc;
+  if (bn >= 128) {
+    rc = make_tmap_2d(&p.b_map_half, w_, (uint64_t)R * S * Cin, Cout, (uint64_t)R * S * Cin * 2, 64, bn / 2);
+    if (rc) return rc;
+    p.pair_ok = 1;
+  }
   p.out = reinterpret_cast<__nv_bfloat16*>(y_);
   p.out_sW = Cout;
   p.out_sH = (long long)Wo * Cout;
@@ -631,6 +891,11 @@ static int conv2d_dgrad_impl(const ecgmm_bf16* dy_, const ecgmm_bf16* wt_, ecgmm
       for (int i = 1; i < 4; ++i) p.a_maps[i] = p.a_maps[0];
       rc = make_tmap_2d(&p.b_map, wt_, (uint64_t)R * S * Cout, Cin, (uint64_t)R * S * Cout * 2, 64, bn);
       if (rc) return rc;
+      if (bn >= 128) {
+        rc = make_tmap_2d(&p.b_map_half, wt_, (uint64_t)R * S * Cout, Cin, (uint64_t)R * S * Cout * 2, 64, bn / 2);
+        if (rc) return rc;
+        p.pair_ok = 1;
+      }
       p.out = dx + ((size_t)ph * W + pw) * Cin * (stride == 2 ? 1 : 0);
       p.out_sW = (long long)stride * Cin;
       p.out_sH = (long long)stride * W * Cin;

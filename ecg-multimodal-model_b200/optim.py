@@ -12,6 +12,7 @@ import torch
 from . import lib, ops
 
 CHUNK = 1 << 16  # elements per CTA
+_CAPTURED_PINNED = []  # pinned buffers whose copies were captured into CUDA graphs (see Adam.reserve_tables)
 
 
 class Adam(torch.optim.Optimizer):
@@ -64,6 +65,11 @@ class Adam(torch.optim.Optimizer):
             host = torch.empty((n_rows, 5), dtype=torch.int64).pin_memory()
             dev = torch.empty((n_rows, 5), dtype=torch.int64, device=ps[0].device)
             self._reserved[gi] = (host, dev)
+            # The H2D copy of this buffer is recorded INSIDE a stream capture.  torch's pinned-memory allocator tags
+            # a block with an event per asynchronous copy and queries those events once the block has been freed; an
+            # event recorded during capture cannot be queried (cudaErrorInvalidValue surfaces at some later, unrelated
+            # pinned allocation such as Tensor.item()).  So these few kilobytes are never handed back.
+            _CAPTURED_PINNED.append(host)
 
     @torch.no_grad()
     def step(self, closure=None):

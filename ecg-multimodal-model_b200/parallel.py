@@ -78,10 +78,10 @@ class DataParallel(torch.nn.Module):
                 pass
 
     def _launch(self, flat, keep=None):
-        if flat.is_cuda:
+        if dist.get_backend(self.pg) == "nccl":
             work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
             self._pending.append((work, flat, keep, False))
-        else:  # gloo (CPU tests): no AVG reduction
+        else:  # gloo (CPU tests, and the 2-ranks-on-one-GPU parity run of tests/test_dp_gpu.py): no AVG reduction
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
             self._pending.append((work, flat, keep, True))
         self.buckets_last_step += 1

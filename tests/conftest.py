@@ -31,3 +31,15 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _fresh_shape_cache():
+    """ecgmm.ops caches the library's pure shape queries (workspace sizes, partial-row counts) per shape.  Several tests
+    switch kernels through ECGMM_* environment variables, which changes those answers: a cached value from another
+    configuration would under- or over-size a buffer.  (Production processes never change the switches mid-run.)"""
+    from ecgmm import ops
+
+    ops._SHAPE_CACHE.clear()
+    yield
+    ops._SHAPE_CACHE.clear()

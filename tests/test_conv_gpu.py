@@ -61,6 +61,27 @@ def test_transposed_wgrad(case, monkeypatch):
     ops._SHAPE_CACHE.clear()
 
 
+PAIR_CASES = [c for c in chk.CASES if c[4] % 128 == 0 or c[5] % 128 == 0] + [
+    ("pair_odd_tiles_128", 1, 9, 40, 128, 128, 3, 3, 1),      # 3 pixel tiles: the last pair has a dummy second tile
+    ("pair_one_tile_256", 1, 4, 20, 256, 256, 3, 3, 1),       # a single tile: falls back to the single-CTA kernel
+    ("pair_layer3_16x157", 4, 16, 157, 256, 256, 3, 3, 1),
+    ("pair_layer4_8x79", 6, 8, 79, 512, 512, 3, 3, 1),
+]
+
+
+@pytest.mark.parametrize("pair", ["1", "0"], ids=["cta_pair", "single_cta"])
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+def test_cta_pair_kernels(case, pair, monkeypatch):
+    """Forward / data-gradient (+ accumulating) of every shape whose GEMM N is a multiple of 128 through
+    igemm_nt_pair_kernel (tcgen05 cta_group::2: two CTAs, one M = 256 MMA, half of B per CTA) and through the
+    single-CTA igemm_nt_kernel."""
+    monkeypatch.setenv("ECGMM_NT_PAIR", pair)
+    results = []
+    assert chk.run_case(*case, results=results, do=("fwd", "dgrad"))
+    bad = [r for r in results if not r[2]]
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("name,N,H,W", [("stem_small", 2, 50, 100), ("stem_odd", 1, 37, 75),
                                         ("stem_250x2500", 2, 250, 2500)])
 def test_stem_case(name, N, H, W):

@@ -392,9 +392,12 @@ def test_stem_s2d_uint8_equals_totensor_normalize():
     (2, 8, 79, 256, 512, 3, 1),     # two N tiles per pixel tile
     (5, 1, 310, 512, 128, 3, 1),    # 1-D (H = 1), K = 1536
 ])
-def test_conv_epilogue_statistics(N, H, W, Cin, Cout, k, stride):
+@pytest.mark.parametrize("pair", ["1", "0"], ids=["cta_pair", "single_cta"])
+def test_conv_epilogue_statistics(N, H, W, Cin, Cout, k, stride, pair, monkeypatch):
     """conv2d_fwd(want_stats=True): same y as without, and the partial rows fold to the exact per-channel sum /
     sum of squares of the STORED bf16 tensor (fp32 partials over <= a few thousand values each)."""
+    monkeypatch.setenv("ECGMM_NT_PAIR", pair)
+    ops._SHAPE_CACHE.clear()  # the number of partial rows depends on the kernel
     g = gen(f"cs{N}{H}{W}{Cin}{Cout}{k}{stride}")
     x = torch.randn(N, H, W, Cin, generator=g).to(DEV).to(torch.bfloat16)
     R = 1 if H == 1 else k
