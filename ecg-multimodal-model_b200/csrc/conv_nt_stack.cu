@@ -13,7 +13,10 @@
 // tcgen05.st and handed back, so that every MMA accumulates.  At the first / last rows of a unit, and where the three
 // blocks wrap around the ring, narrower (N = 64 / 128) groups are issued.
 //
-// Roles: warp 0 = TMA producer (input rows, one box each, used once), warp 1 = MMA issuer, warps 2..5 = epilogue.
+// Roles: warp 0 = TMA producer (input rows, one box each, used once), warp 1 = MMA issuer, warps 2..9 = epilogue: TWO
+// warps per TMEM lane quadrant, 32 of the 64 columns each -- with one warp per quadrant the epilogue (TMEM read, bf16
+// pack, swizzled staging store, accumulator zeroing, + optional statistics) was the longest per-tile chain of the
+// kernel as soon as anything was added to it.
 // Shared memory: 9 weight tiles (72 KB, resident) + ring of 6 input rows (102 KB) + 3 output staging tiles (48 KB).
 #include "common.h"
 #include "ptx.cuh"
@@ -76,8 +79,11 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // loads its pixel's row of that BatchNorm's INPUT x (128 contiguous bytes) and ReLU bits (8 bytes) and accumulates the
 // two sums the BatchNorm backward needs, sum dz and sum dz * x with dz = dy * relu'(.), so that the separate reduction
 // pass over (x, dy) -- ecgmm_bn_bwd_reduce -- disappears.  Written out as sum dz and sum dz * xhat.
+constexpr int kStThreads = 320;   // 10 warps
+constexpr int kStEpiThreads = 256;
+
 template <int STATS>
-__global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_constant__ NtStackParams p) {
+__global__ void __launch_bounds__(kStThreads, 1) igemm_nt_stack_kernel(const __grid_constant__ NtStackParams p) {
   using L = NtStackSmem;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
     }
     for (int i = 0; i < kStBlocks; ++i) {
       mbar_init(&ofull[i], 1);
-      mbar_init(&bfree[i], 4);  // one arrival per epilogue warp
+      mbar_init(&bfree[i], 8);  // one arrival per epilogue warp
     }
     mbar_init(wfull, 1);
     for (int i = 0; i < 3; ++i) mbar_init(&oldfull[i], 1);
@@ -199,16 +205,15 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue (warps 2..5, 128 threads)
-    const int quad = warp & 3;
+    // ---------------------------------------------------------------- epilogue (warps 2..9, 256 threads)
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;   // which 32 of the 64 columns (channels) this warp converts
     const int m_row = quad * 32 + lane;
+    const int et = (int)threadIdx.x - 64;  // 0..255
     const bool leader = (threadIdx.x == 64);
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + half * 32;
     // hand over all accumulators zeroed (completion #0 of every bfree barrier)
-    for (int b = 0; b < kStBlocks; ++b) {
-      tmem_st_zero_32x32(lane_base + b * 64);
-      tmem_st_zero_32x32(lane_base + b * 64 + 32);
-    }
+    for (int b = 0; b < kStBlocks; ++b) tmem_st_zero_32x32(lane_base + b * 64);
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
@@ -228,10 +233,10 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
       mbar_expect_tx(&oldfull[0], kStTile * 128);
       tma_load_4d(sOut, &p.y_map, &oldfull[0], 0, w0, oh, img);
     }
-    float ssum[STATS ? 64 : 1], ssq[STATS ? 64 : 1];
+    float ssum[STATS ? 32 : 1], ssq[STATS ? 32 : 1];  // this thread's pixel slot x its 32 channels, whole kernel
     if constexpr (STATS != 0) {
 #pragma unroll
-      for (int i = 0; i < 64; ++i) ssum[i] = ssq[i] = 0.f;
+      for (int i = 0; i < 32; ++i) ssum[i] = ssq[i] = 0.f;
     }
     uint32_t g = 0;  // virtual output-row index (as in the MMA issuer); also the staging-buffer counter
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
@@ -243,15 +248,15 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
         const int blk = (int)(g % kStBlocks);
         const int ob = (int)(g % 3);
         uint8_t* buf = sOut + ob * (kStTile * 128);
-        uint4 xrow[STATS == 2 ? 8 : 1];
-        uint2 mbits = make_uint2(0xffffffffu, 0xffffffffu);
+        uint4 xrow[STATS == 2 ? 4 : 1];
+        uint32_t mbits = 0xffffffffu;
         if constexpr (STATS == 2) {  // issued before the accumulator wait: the latency hides behind the MMAs
           if (in_image) {
             const size_t pix = ((size_t)img * p.H + oh) * p.W + (w0 + m_row);
-            const uint4* xs = reinterpret_cast<const uint4*>(p.red_x + pix * 64);
+            const uint4* xs = reinterpret_cast<const uint4*>(p.red_x + pix * 64 + half * 32);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) xrow[k] = __ldg(xs + k);
-            if (p.red_mask) mbits = __ldg(reinterpret_cast<const uint2*>(p.red_mask + pix * 8));
+            for (int k = 0; k < 4; ++k) xrow[k] = __ldg(xs + k);
+            if (p.red_mask) mbits = __ldg(reinterpret_cast<const uint32_t*>(p.red_mask + pix * 8 + half * 4));
           }
         }
         if (leader) {
@@ -271,18 +276,18 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
             }
           }
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kStEpiThreads);
         mbar_wait(&ofull[blk], (g / kStBlocks) & 1u);
         tc_fence_after();
         if (p.accumulate) mbar_wait(&oldfull[ob], (g / 3) & 1u);
         const uint32_t t_addr = lane_base + blk * 64;
         uint8_t* row = buf + m_row * 128;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        {
+          const int c = half;
           uint32_t r[32];
-          tmem_ld_32x32(t_addr + c * 32, r);
+          tmem_ld_32x32(t_addr, r);
           tmem_ld_wait();
-          tmem_st_zero_32x32(t_addr + c * 32);  // hand the accumulator back empty
+          tmem_st_zero_32x32(t_addr);  // hand the accumulator back empty
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             // 16-byte chunk j of row m lives at chunk (j ^ (m & 7)) of the swizzled tile
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float2 s2 = __bfloat1622float2(vb[j]);  // statistics of what is stored, not of the fp32 value
-                  const int ch = c * 32 + q * 8 + 2 * j;
+                  const int ch = q * 8 + 2 * j;
                   ssum[ch] += s2.x;
                   ssq[ch] = fmaf(s2.x, s2.x, ssq[ch]);
                   ssum[ch + 1] += s2.y;
@@ -320,15 +325,15 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
             }
             if constexpr (STATS == 2) {
               if (in_image) {
-                const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&xrow[c * 4 + q]);
-                const uint32_t bits = ((c * 4 + q) < 4 ? mbits.x : mbits.y) >> (8 * ((c * 4 + q) & 3));
+                const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&xrow[q]);
+                const uint32_t bits = mbits >> (8 * q);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   float2 d = __bfloat1622float2(vb[j]);  // the gradient as the BatchNorm backward will read it
                   const float2 xx = __bfloat1622float2(xb[j]);
                   if (!((bits >> (2 * j)) & 1u)) d.x = 0.f;
                   if (!((bits >> (2 * j + 1)) & 1u)) d.y = 0.f;
-                  const int ch = c * 32 + q * 8 + 2 * j;
+                  const int ch = q * 8 + 2 * j;
                   ssum[ch] += d.x;
                   ssq[ch] = fmaf(d.x, xx.x, ssq[ch]);
                   ssum[ch + 1] += d.y;
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(&bfree[blk]);  // the MMA issuer may start the next output row in this block
         fence_proxy_async_smem();                  // make the staging tile visible to the TMA engine
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kStEpiThreads);
         if (leader) {
           tma_store_4d(&p.y_map, buf, 0, w0, oh, img);
           tma_store_commit();
@@ -355,28 +360,29 @@ __global__ void __launch_bounds__(192, 1) igemm_nt_stack_kernel(const __grid_con
       // fold the 128 threads' sums: the input-row ring is idle now (every MMA that read it has completed, or the last
       // ofull wait above would not have returned); rows of 129 floats keep the column reads conflict-free
       float* scr = reinterpret_cast<float*>(sA);
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kStEpiThreads);
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        scr[m_row * 129 + i] = ssum[i];
-        scr[m_row * 129 + 64 + i] = ssq[i];
+      for (int i = 0; i < 32; ++i) {
+        scr[m_row * 129 + half * 32 + i] = ssum[i];
+        scr[m_row * 129 + 64 + half * 32 + i] = ssq[i];
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kStEpiThreads);
       if constexpr (STATS == 1) {
-        double acc = 0.0;
-        for (int r = 0; r < 128; ++r) acc += (double)scr[r * 129 + m_row];
-        float* dst = (m_row < 64) ? p.psum : p.psq;
-        dst[(size_t)blockIdx.x * 64 + (m_row & 63)] = (float)acc;
-      } else if (m_row < 64) {
+        if (et < 128) {  // column et of the [128 pixel slots][sum 0..63 | sq 64..127] table
+          double acc = 0.0;
+          for (int r = 0; r < 128; ++r) acc += (double)scr[r * 129 + et];
+          float* dst = (et < 64) ? p.psum : p.psq;
+          dst[(size_t)blockIdx.x * 64 + (et & 63)] = (float)acc;
+        }
+      } else if (et < 64) {
         double s1 = 0.0, s2 = 0.0;
         for (int r = 0; r < 128; ++r) {
-          s1 += (double)scr[r * 129 + m_row];
-          s2 += (double)scr[r * 129 + 64 + m_row];
+          s1 += (double)scr[r * 129 + et];
+          s2 += (double)scr[r * 129 + 64 + et];
         }
         // sum dz * xhat = invstd * (sum dz * x - mean * sum dz), in double
-        p.psum[(size_t)blockIdx.x * 64 + m_row] = (float)s1;
-        p.psq[(size_t)blockIdx.x * 64 + m_row] =
-            (float)((double)p.red_invstd[m_row] * (s2 - (double)p.red_mean[m_row] * s1));
+        p.psum[(size_t)blockIdx.x * 64 + et] = (float)s1;
+        p.psq[(size_t)blockIdx.x * 64 + et] = (float)((double)p.red_invstd[et] * (s2 - (double)p.red_mean[et] * s1));
       }
     }
   }
@@ -453,11 +459,11 @@ int launch_nt_stack(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat1
   }
   const int grid = p.total_units < num_sms() ? p.total_units : num_sms();
   if (psum && psq && !dgrad)
-    igemm_nt_stack_kernel<1><<<grid, 192, NtStackSmem::kBytes, st>>>(p);
+    igemm_nt_stack_kernel<1><<<grid, kStThreads, NtStackSmem::kBytes, st>>>(p);
   else if (psum && psq && dgrad && red_x && red_mean && red_invstd)
-    igemm_nt_stack_kernel<2><<<grid, 192, NtStackSmem::kBytes, st>>>(p);
+    igemm_nt_stack_kernel<2><<<grid, kStThreads, NtStackSmem::kBytes, st>>>(p);
   else
-    igemm_nt_stack_kernel<0><<<grid, 192, NtStackSmem::kBytes, st>>>(p);
+    igemm_nt_stack_kernel<0><<<grid, kStThreads, NtStackSmem::kBytes, st>>>(p);
   return check_launch("igemm_nt_stack_kernel");
 }
 

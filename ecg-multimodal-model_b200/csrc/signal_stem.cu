@@ -139,9 +139,96 @@ __global__ void __launch_bounds__(256) signal_stem_wgrad_reduce_kernel(const flo
   dw[idx] += a0 + a1;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same layer on the TENSOR cores (measured: the CUDA-core kernels above were 1.26 of the 3.2 ms training step of
+// the 12-lead model at batch 256).  Grouping FOUR consecutive samples of all leads into one 64-channel "pixel"
+//        xs4[b][q][j * Cin + ci] = x[b][ci][4q + j]          (bf16, channels >= 4 * Cin are zero)
+// turns Conv1d(Cin, 64, k 7, stride 2, pad 3) into a 1x3 stride-1 pad-1 convolution with 64 input and 128 output
+// channels over the q axis: output pixel q holds the stem outputs 2q (channels 0..63) and 2q+1 (channels 64..127), i.e.
+// [B][Lq][128] IS the [B][2 Lq][64] channels-last stem output.  Output 2q+e reads x[4q + 2e + k - 3], k = 0..6: block tap
+// t (block q+t-1), sample j of the block  ->  k = 4 (t-1) + j - 2e + 3.  Forward, weight gradient (and nothing else: the
+// stem has no data gradient) then run through the generic tcgen05 kernels; three small kernels do the regrouping.
+// Requires 2 * ceil(L/4) == ceil(L/2) (L mod 4 in {0, 3}); other lengths keep the CUDA-core kernels.
+__global__ void __launch_bounds__(256) signal_s4d_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xs4,
+                                                          int Cin, int L, int Lq, size_t total_vec) {
+  // one thread = 8 channels (16 bytes) of one pixel; vector v of a pixel covers channels 8v..8v+7
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i & 7);
+    const size_t pix = i >> 3;
+    const int q = (int)(pix % Lq);
+    const size_t b = pix / Lq;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = v * 8 + e;
+      const int j = ch / Cin, ci = ch - j * Cin;
+      const int t = 4 * q + j;
+      f[e] = (j < 4 && t < L) ? __ldg(x + (b * Cin + ci) * (size_t)L + t) : 0.f;
+    }
+    reinterpret_cast<uint4*>(xs4)[i] = pack8(f);
+  }
+}
+
+// w [64][Cin][7] fp32 -> w4 [128][1][3][64] bf16 (the [O][R][S][I] operand layout of the forward kernels)
+__global__ void signal_stem_w4_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w4, int Cin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // ((e*64 + co) * 3 + t) * 64 + ch
+  if (i >= 128 * 3 * 64) return;
+  const int ch = i & 63, t = (i >> 6) % 3, o = i / 192;
+  const int e = o >> 6, co = o & 63;
+  const int j = ch / Cin, ci = ch - j * Cin;
+  const int k = 4 * (t - 1) + j - 2 * e + 3;
+  const bool ok = j < 4 && k >= 0 && k < 7;
+  w4[i] = __float2bfloat16_rn(ok ? w[(co * Cin + ci) * 7 + k] : 0.f);
+}
+
+// dw [64][Cin][7] += the entries of dw4 [128][64][1][3] (OIHW of the regrouped convolution) that map onto it
+__global__ void signal_stem_dw4_fold_kernel(const float* __restrict__ dw4, float* __restrict__ dw, int Cin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (co * Cin + ci) * 7 + k
+  if (i >= 64 * Cin * 7) return;
+  const int k = i % 7, ci = (i / 7) % Cin, co = i / (7 * Cin);
+  float acc = 0.f;
+  for (int e = 0; e < 2; ++e)
+    for (int t = 0; t < 3; ++t) {
+      const int j = k - 4 * (t - 1) + 2 * e - 3;
+      if (j >= 0 && j < 4) acc += dw4[((size_t)(e * 64 + co) * 64 + j * Cin + ci) * 3 + t];
+    }
+  dw[i] += acc;
+}
+
 }  // namespace ecgmm
 
 using namespace ecgmm;
+
+extern "C" int ecgmm_signal_s4d_len(int L) { return L > 0 && (L % 4 == 0 || L % 4 == 3) ? (L + 3) / 4 : 0; }
+
+extern "C" int ecgmm_signal_s4d(const float* x, ecgmm_bf16* xs4, int B, int Cin, int L, void* stream) {
+  ECGMM_CHECK(x && xs4, ECGMM_ERR_ARG, "signal_s4d: null pointer");
+  ECGMM_CHECK(Cin >= 1 && Cin <= kStemMaxCin, ECGMM_ERR_SHAPE, "signal_s4d: Cin=%d", Cin);
+  const int Lq = ecgmm_signal_s4d_len(L);
+  ECGMM_CHECK(Lq > 0, ECGMM_ERR_SHAPE, "signal_s4d: L=%d is not 0 or 3 modulo 4 (use the direct stem kernels)", L);
+  if (B == 0) return ECGMM_OK;
+  const size_t total = (size_t)B * Lq * 8;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
+  signal_s4d_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(xs4), Cin, L,
+                                                                        Lq, total);
+  return check_launch("signal_s4d_kernel");
+}
+
+extern "C" int ecgmm_signal_stem_w4(const float* w, ecgmm_bf16* w4, int Cin, void* stream) {
+  ECGMM_CHECK(w && w4, ECGMM_ERR_ARG, "signal_stem_w4: null pointer");
+  ECGMM_CHECK(Cin >= 1 && Cin <= kStemMaxCin, ECGMM_ERR_SHAPE, "signal_stem_w4: Cin=%d", Cin);
+  signal_stem_w4_kernel<<<ceil_div(128 * 3 * 64, 256), 256, 0, (cudaStream_t)stream>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(w4), Cin);
+  return check_launch("signal_stem_w4_kernel");
+}
+
+extern "C" int ecgmm_signal_stem_dw4_fold(const float* dw4, float* dw, int Cin, void* stream) {
+  ECGMM_CHECK(dw4 && dw, ECGMM_ERR_ARG, "signal_stem_dw4_fold: null pointer");
+  ECGMM_CHECK(Cin >= 1 && Cin <= kStemMaxCin, ECGMM_ERR_SHAPE, "signal_stem_dw4_fold: Cin=%d", Cin);
+  signal_stem_dw4_fold_kernel<<<ceil_div(64 * Cin * 7, 256), 256, 0, (cudaStream_t)stream>>>(dw4, dw, Cin);
+  return check_launch("signal_stem_dw4_fold_kernel");
+}
 
 extern "C" int ecgmm_signal_stem_fwd(const float* x, const float* w, ecgmm_bf16* y, int B, int Cin, int L,
                                      void* stream) {

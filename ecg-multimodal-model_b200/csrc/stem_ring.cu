@@ -39,8 +39,11 @@ struct StemFwdSmem {
 
 // STATS: per-channel sum / sum of squares of the stored output, accumulated in 128 registers per epilogue thread over
 // the whole kernel and folded across threads once at the end (same scheme as igemm_nt_stack_kernel<true>).
+// Epilogue: warps 2..9, two per TMEM lane quadrant, 32 of the 64 channels each (the per-tile epilogue chain of a single
+// warp per quadrant was what bounded this kernel once the statistics were added: 2.7 -> 3.4 ms at batch 512).
+constexpr int kSrFwdThreads = 320;
 template <bool STATS>
-__global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_constant__ StemRingParams p) {
+__global__ void __launch_bounds__(kSrFwdThreads, 1) stem_fwd_ring_kernel(const __grid_constant__ StemRingParams p) {
   using L = StemFwdSmem;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     mbar_init(wfull, 1);
     mbar_fence_init();
@@ -133,13 +136,15 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
   } else {
     // epilogue: TMEM -> bf16 -> swizzled staging tile -> one TMA tensor store per tile (see conv_nt_halo.cu)
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;  // which 32 of the 64 channels
     const int m_row = quad * 32 + lane;
+    const int et = (int)threadIdx.x - 64;
     const bool leader = (threadIdx.x == 64);
     uint8_t* sOut = smem + L::kOut;
-    float ssum[STATS ? 64 : 1], ssq[STATS ? 64 : 1];
+    float ssum[STATS ? 32 : 1], ssq[STATS ? 32 : 1];
     if constexpr (STATS) {
 #pragma unroll
-      for (int i = 0; i < 64; ++i) ssum[i] = ssq[i] = 0.f;
+      for (int i = 0; i < 32; ++i) ssum[i] = ssq[i] = 0.f;
     }
     int it = 0;
     for (int s = blockIdx.x; s < p.n_strips; s += gridDim.x) {
@@ -149,15 +154,15 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
         const int acc = it & 1;
         uint8_t* buf = sOut + acc * kSrSlot;
         if (leader) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         mbar_wait(&tfull[acc], (it >> 1) & 1);
         tc_fence_after();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 64;
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 64 + half * 32;
         uint8_t* row = buf + m_row * 128;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        {
+          const int c = half;
           uint32_t r[32];
-          tmem_ld_32x32(t_addr + c * 32, r);
+          tmem_ld_32x32(t_addr, r);
           tmem_ld_wait();
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float2 s2 = __bfloat1622float2(vb[j]);
-                  const int ch = c * 32 + g * 8 + 2 * j;
+                  const int ch = g * 8 + 2 * j;
                   ssum[ch] += s2.x;
                   ssq[ch] = fmaf(s2.x, s2.x, ssq[ch]);
                   ssum[ch + 1] += s2.y;
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         if (leader) {
           tma_store_4d(&p.dy_map, buf, 0, w0, oh, img);
           tma_store_commit();
@@ -196,17 +201,19 @@ __global__ void __launch_bounds__(192, 1) stem_fwd_ring_kernel(const __grid_cons
     if (leader) tma_store_wait_all<0>();
     if constexpr (STATS) {
       float* scr = reinterpret_cast<float*>(sX);  // the input ring is idle: all MMAs of this CTA have completed
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        scr[m_row * 129 + i] = ssum[i];
-        scr[m_row * 129 + 64 + i] = ssq[i];
+      for (int i = 0; i < 32; ++i) {
+        scr[m_row * 129 + half * 32 + i] = ssum[i];
+        scr[m_row * 129 + 64 + half * 32 + i] = ssq[i];
       }
-      named_bar_sync(1, 128);
-      double acc = 0.0;
-      for (int r = 0; r < 128; ++r) acc += (double)scr[r * 129 + m_row];
-      float* dst = (m_row < 64) ? p.psum : p.psq;
-      dst[(size_t)blockIdx.x * 64 + (m_row & 63)] = (float)acc;
+      named_bar_sync(1, 256);
+      if (et < 128) {
+        double acc = 0.0;
+        for (int r = 0; r < 128; ++r) acc += (double)scr[r * 129 + et];
+        float* dst = (et < 64) ? p.psum : p.psq;
+        dst[(size_t)blockIdx.x * 64 + (et & 63)] = (float)acc;
+      }
     }
   }
   tc_fence_before();
@@ -403,9 +410,9 @@ int launch_stem_fwd_ring(const void* xs, const void* w_s2d, __nv_bfloat16* y, in
   }
   const int grid = p.n_strips < num_sms() ? p.n_strips : num_sms();
   if (psum && psq)
-    stem_fwd_ring_kernel<true><<<grid, 192, StemFwdSmem::kBytes, st>>>(p);
+    stem_fwd_ring_kernel<true><<<grid, kSrFwdThreads, StemFwdSmem::kBytes, st>>>(p);
   else
-    stem_fwd_ring_kernel<false><<<grid, 192, StemFwdSmem::kBytes, st>>>(p);
+    stem_fwd_ring_kernel<false><<<grid, kSrFwdThreads, StemFwdSmem::kBytes, st>>>(p);
   return check_launch("stem_fwd_ring_kernel");
 }
 

@@ -58,6 +58,10 @@ SIGNATURES = {
     "ecgmm_avgpool_bwd": [_p, _p, _i, _i, _i, _p],
     # 1-D ResNet-SE specifics
     "ecgmm_signal_stem_fwd": [_p, _p, _p, _i, _i, _i, _p],
+    "ecgmm_signal_s4d_len": [_i],
+    "ecgmm_signal_s4d": [_p, _p, _i, _i, _i, _p],
+    "ecgmm_signal_stem_w4": [_p, _p, _i, _p],
+    "ecgmm_signal_stem_dw4_fold": [_p, _p, _i, _p],
     "ecgmm_signal_stem_wgrad_workspace": [_i, _i, _i],
     "ecgmm_signal_stem_wgrad": [_p, _p, _p, _i, _i, _i, _p, _ll, _p],
     "ecgmm_se_fwd": [_p] * 10 + [_i] * 4 + [_p],

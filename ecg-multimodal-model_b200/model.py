@@ -108,8 +108,9 @@ class StemConv2d(_ShadowMixin, _ContainerMixin, nn.Conv2d):
         return (ops.stem_weight_prep(w), None)
 
 
-class SignalStemConv1d(_ContainerMixin, nn.Conv1d):
-    pass
+class SignalStemConv1d(_ShadowMixin, _ContainerMixin, nn.Conv1d):
+    def _make_shadows(self, w):
+        return (ops.signal_stem_w4(w), None)
 
 
 class BatchNorm2d(_ContainerMixin, nn.BatchNorm2d):
@@ -147,6 +148,7 @@ class Sigmoid(_Marker):
 
 
 FUSED_STATS = os.environ.get("ECGMM_FUSED_STATS", "1") != "0"  # BatchNorm sums from the convolution epilogue
+SIGNAL_STEM_TC = os.environ.get("ECGMM_SIGNAL_STEM_TC", "1") != "0"  # Conv1d(Cin,64,7,2) stem on the tensor cores
 
 
 def _conv_bn(conv_fn, bn, *args, want_nsum=False):
@@ -694,7 +696,13 @@ class ResNet1D_SE(_Stage):
             raise lib.EcgmmError("signal must be a CUDA tensor (no CPU fallback)")
         sig = sig.detach().to(F32).contiguous()
         stem, bn0 = self.initial[0], self.initial[1]
-        c0 = ops.signal_stem_fwd(sig, stem.weight.detach())
+        # tensor-core stem (4 samples of all leads per 64-channel pixel) where the length allows it, else the direct kernels
+        xs4 = ops.signal_s4d(sig) if SIGNAL_STEM_TC else None
+        if xs4 is not None:
+            c0 = ops.conv2d_fwd(xs4, stem.shadows()[0], 1).view(sig.shape[0], 1, -1, 64)
+            sig = xs4  # what backward needs
+        else:
+            c0 = ops.signal_stem_fwd(sig, stem.weight.detach())
         st0 = _bn_stats(bn0, c0, stem.bias)
         x, arg = ops.bn_relu_maxpool(c0, st0, want_argmax=save)
         recs = []
@@ -722,7 +730,10 @@ class ResNet1D_SE(_Stage):
         bn0 = self.initial[1]
         dc0, _ = ops.bn_backward(c0, dx, st0, bn0.weight, argmax=arg, dgamma=G(bn0.weight), dbeta=G(bn0.bias),
                                  pooled=stem_out, beta=bn0.bias)
-        ops.signal_stem_wgrad(sig, dc0, G(self.initial[0].weight))
+        if sig.dtype == BF16:  # the regrouped signal of the tensor-core stem
+            ops.signal_stem_wgrad_s4d(sig, dc0, G(self.initial[0].weight))
+        else:
+            ops.signal_stem_wgrad(sig, dc0, G(self.initial[0].weight))
         self._notify(G, G.total)
         return (None,), [G(p) for p in self.cached_params()]
 

@@ -481,6 +481,35 @@ def signal_stem_fwd(x, w):
     return y
 
 
+def signal_s4d(x):
+    """x [B,Cin,L] fp32 -> xs4 [B,1,Lq,64] bf16 (4 consecutive samples of all leads per 64-channel pixel), or None when
+    the length does not allow the tensor-core stem (L mod 4 in {1, 2})."""
+    _chk(x, F32, "ecg_signal")
+    B, Cin, L = x.shape
+    Lq = _shape_query("ecgmm_signal_s4d_len", L)
+    if Lq == 0 or Cin > 16:
+        return None
+    xs4 = torch.empty((B, 1, Lq, 64), dtype=BF16, device=x.device)
+    lib.call("ecgmm_signal_s4d", _ptr(x), _ptr(xs4), B, Cin, L, _s())
+    return xs4
+
+
+def signal_stem_w4(w):
+    """w [64,Cin,7] fp32 -> the regrouped forward operand [128,1,3,64] bf16."""
+    _chk(w, F32, "w")
+    w4 = torch.empty((128, 1, 3, 64), dtype=BF16, device=w.device)
+    lib.call("ecgmm_signal_stem_w4", _ptr(w), _ptr(w4), w.shape[1], _s())
+    return w4
+
+
+def signal_stem_wgrad_s4d(xs4, dy, dw):
+    """dw [64,Cin,7] += weight gradient of the stem from xs4 [B,1,Lq,64] and dy [B,1,2 Lq,64] (tensor-core path)."""
+    B, _, Lq, _ = xs4.shape
+    dw4 = torch.zeros((128, 64, 1, 3), dtype=F32, device=xs4.device)
+    conv2d_wgrad(xs4, dy.view(B, 1, Lq, 128), dw4, 1, 3, 1)
+    lib.call("ecgmm_signal_stem_dw4_fold", _ptr(dw4), _ptr(dw), dw.shape[1], _s())
+
+
 def signal_stem_wgrad(x, dy, dw):
     B, Cin, L = x.shape
     ws_bytes = _shape_query("ecgmm_signal_stem_wgrad_workspace", B, Cin, L)

@@ -12,7 +12,7 @@ import torch
 from . import lib, ops
 
 CHUNK = 1 << 16  # elements per CTA
-_CAPTURED_PINNED = []  # pinned buffers whose copies were captured into CUDA graphs (see Adam.reserve_tables)
+_CAPTURED_PINNED = []  # page-locked buffers whose copies were captured into CUDA graphs (see Adam.reserve_tables)
 
 
 class Adam(torch.optim.Optimizer):
@@ -62,13 +62,18 @@ class Adam(torch.optim.Optimizer):
             if not ps:
                 continue
             n_rows = sum((p.numel() + CHUNK - 1) // CHUNK for p in ps)
-            host = torch.empty((n_rows, 5), dtype=torch.int64).pin_memory()
+            # The H2D copy of this buffer is recorded INSIDE a stream capture.  It must not come from torch's pinned
+            # allocator: that allocator tags a block with a CUDA event per asynchronous copy and queries all such
+            # events at later pinned allocations (Tensor.item() makes one); an event whose last record sits in a
+            # captured graph cannot be queried once that graph has been destroyed (cudaErrorInvalidValue at some
+            # unrelated call, depending on when the garbage collector drops the graph).  So: page-lock our own buffer
+            # (the allocator does not know it and records nothing) and never hand these few kilobytes back.
+            host = torch.empty((n_rows, 5), dtype=torch.int64)
+            rc = torch.cuda.cudart().cudaHostRegister(host.data_ptr(), host.numel() * 8, 0)
+            if int(rc) != 0:
+                raise lib.EcgmmError(f"cudaHostRegister failed with {rc}")
             dev = torch.empty((n_rows, 5), dtype=torch.int64, device=ps[0].device)
             self._reserved[gi] = (host, dev)
-            # The H2D copy of this buffer is recorded INSIDE a stream capture.  torch's pinned-memory allocator tags
-            # a block with an event per asynchronous copy and queries those events once the block has been freed; an
-            # event recorded during capture cannot be queried (cudaErrorInvalidValue surfaces at some later, unrelated
-            # pinned allocation such as Tensor.item()).  So these few kilobytes are never handed back.
             _CAPTURED_PINNED.append(host)
 
     @torch.no_grad()

@@ -199,6 +199,15 @@ int ecgmm_avgpool_bwd(const float* dout, ecgmm_bf16* dx, int N, int P, int C, vo
  * x [B][Cin][L] fp32 (Cin <= 16), w [64][Cin][7] fp32, y/dy [B][Lo][64] bf16, Lo = (L-1)/2+1.
  * The bias is NOT added (see ecgmm_bn_finalize / ecgmm_bn_eval_coeffs). dw accumulates. */
 int ecgmm_signal_stem_fwd(const float* x, const float* w, ecgmm_bf16* y, int B, int Cin, int L, void* stream);
+/* The same layer through the tensor-core kernels: xs4 [B][Lq][64] bf16 groups 4 consecutive samples of all leads
+ * (channel j*Cin + ci = x[b][ci][4q + j]); with w4 [128][1][3][64] (ecgmm_signal_stem_w4) the stem is
+ * ecgmm_conv2d_fwd(xs4 as [B][1][Lq][64], w4, stride 1) -> [B][1][Lq][128] == [B][2 Lq][64], its weight gradient
+ * ecgmm_conv2d_wgrad into dw4 [128][64][1][3] followed by ecgmm_signal_stem_dw4_fold (dw [64][Cin][7] += ...).
+ * ecgmm_signal_s4d_len(L) = Lq = ceil(L/4) when 2*Lq equals the stem's output length (L mod 4 in {0,3}), else 0. */
+int ecgmm_signal_s4d_len(int L);
+int ecgmm_signal_s4d(const float* x, ecgmm_bf16* xs4, int B, int Cin, int L, void* stream);
+int ecgmm_signal_stem_w4(const float* w, ecgmm_bf16* w4, int Cin, void* stream);
+int ecgmm_signal_stem_dw4_fold(const float* dw4, float* dw, int Cin, void* stream);
 /* workspace of ecgmm_signal_stem_wgrad_workspace() bytes: fixed-order fold of the per-CTA partial sums; NULL: atomics */
 long long ecgmm_signal_stem_wgrad_workspace(int B, int Cin, int L);
 int ecgmm_signal_stem_wgrad(const float* x, const ecgmm_bf16* dy, float* dw, int B, int Cin, int L, void* workspace,

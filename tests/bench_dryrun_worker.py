@@ -64,6 +64,7 @@ torch.cuda.current_device = lambda: 0
 torch.cuda.CUDAGraph = FakeGraph
 torch.cuda.graph = lambda g, *a, **k: contextlib.nullcontext()
 torch.cuda.empty_cache = lambda: None
+torch.cuda.cudart = lambda: types.SimpleNamespace(cudaHostRegister=lambda *a: 0)
 os.environ["ECGMM_SIDE_STREAM"] = "0"
 _real_init = dist.init_process_group
 dist.init_process_group = lambda backend=None, **k: _real_init("gloo")

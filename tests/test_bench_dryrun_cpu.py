@@ -95,6 +95,7 @@ def fake_cuda(monkeypatch):
     monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
     monkeypatch.setattr(torch.cuda, "graph", lambda g, *a, **k: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+    monkeypatch.setattr(torch.cuda, "cudart", lambda: types.SimpleNamespace(cudaHostRegister=lambda *a: 0))
     monkeypatch.setenv("ECGMM_SIDE_STREAM", "0")
     return calls
 

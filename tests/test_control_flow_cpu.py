@@ -41,6 +41,9 @@ def stub(monkeypatch):
     monkeypatch.setattr(ops, "_s", lambda: 0)
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self, raising=False)
+    import types
+
+    monkeypatch.setattr(torch.cuda, "cudart", lambda: types.SimpleNamespace(cudaHostRegister=lambda *a: 0))
     return calls
 
 
@@ -112,8 +115,13 @@ def test_signal_model_and_helpers_flow(stub):
     loss = enn.FocalLoss()(net(x), torch.tensor([0, 1, 1, 0]))
     loss.backward()
     opt.step()
-    assert "ecgmm_signal_stem_fwd" in stub and "ecgmm_signal_stem_wgrad" in stub
+    # L = 1000 (0 mod 4): the stem runs on the tensor cores through the regrouped signal
+    assert "ecgmm_signal_s4d" in stub and "ecgmm_signal_stem_w4" in stub and "ecgmm_signal_stem_dw4_fold" in stub
+    assert "ecgmm_signal_stem_fwd" not in stub
     assert all(p.grad is not None for p in net.parameters())
+    del stub[:]
+    enn.FocalLoss()(net(torch.randn(4, 12, 1001)), torch.tensor([0, 1, 1, 0])).backward()   # 1 mod 4: direct kernels
+    assert "ecgmm_signal_stem_fwd" in stub and "ecgmm_signal_stem_wgrad" in stub and "ecgmm_signal_s4d" not in stub
     # preprocessing / explainers: argument marshalling of the newer entry points
     y = preprocess.preprocess_signal(torch.randn(3, 12, 500), zscore=True)
     assert y.shape == (3, 12, 500) and y.dtype == torch.float32 and stub[-1] == "ecgmm_signal_preprocess"

@@ -479,3 +479,25 @@ def test_dgrad_epilogue_reduces_for_batchnorm_backward(N, H, W, accumulate, with
     a, _ = ops.bn_backward(xbn, dx, st, bn.weight, mask=mask, dgamma=dg_a, dbeta=db_a)
     b, _ = ops.bn_backward(xbn, dx, st, bn.weight, mask=mask, dgamma=dg_b, dbeta=db_b, partials=part)
     assert rel_l2(b, a) < 2e-3 and rel_l2(dg_b, dg_a) < 1e-4 and rel_l2(db_b, db_a) < 1e-4
+
+
+@pytest.mark.parametrize("B,Cin,L", [(4, 12, 5000), (3, 1, 2476), (2, 12, 603), (2, 5, 64)])
+def test_signal_stem_on_tensor_cores(B, Cin, L):
+    """Conv1d(Cin, 64, k 7, stride 2, pad 3) as a 1x3 convolution over 4-sample groups (signal_s4d + the generic tcgen05
+    forward / weight-gradient kernels) against torch's conv1d on the same bf16-rounded operands."""
+    g = gen(f"s4d{B}{Cin}{L}")
+    x = torch.randn(B, Cin, L, generator=g).to(DEV)
+    w = (torch.randn(64, Cin, 7, generator=g) / (7 * Cin) ** 0.5).to(DEV)
+    xs4 = ops.signal_s4d(x)
+    assert xs4 is not None
+    y = ops.conv2d_fwd(xs4, ops.signal_stem_w4(w), 1).view(B, -1, 64)
+    wr = w.to(BF).float().requires_grad_(True)
+    ref = torch.nn.functional.conv1d(x.to(BF).float(), wr, None, 2, 3)
+    assert y.shape[1] == ref.shape[2]
+    assert rel_l2(y.float().permute(0, 2, 1), ref) < 6e-3
+    dy = torch.randn(ref.shape, generator=g).to(DEV).to(BF)
+    ref.backward(dy.float())
+    dw = torch.zeros_like(w)
+    ops.signal_stem_wgrad_s4d(xs4, dy.permute(0, 2, 1).contiguous().view(B, 1, -1, 64), dw)
+    assert rel_l2(dw, wr.grad) < 2e-3
+    assert ops.signal_s4d(torch.zeros(2, Cin, 601, device=DEV)) is None  # L mod 4 == 1: direct kernels
