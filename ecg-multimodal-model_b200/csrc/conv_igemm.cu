@@ -1143,6 +1143,53 @@ __global__ void __launch_bounds__(256) tn_reduce_kernel(TnParams p, int BN) {
   p.dw[((size_t)cout * p.Cin + cin) * p.RS + p.taps[tap].id] += (a0 + a1) + (a2 + a3);
 }
 
+// The same fold with coalesced accesses (OIHW output): a CTA owns 16 output channels x one 64-wide Cin slice, gathers
+// all RS taps of it from wherever their atoms sit in the workspace (atom = tap * cin_chunks + slice -> accumulator
+// slot, 64-row half, slot group) into a [16][64 cin x RS] tile in shared memory laid out like dw, and adds RS * 64
+// contiguous floats per output channel.  Reads run along the output channel (contiguous in the workspace), writes along
+// (cin, tap) (contiguous in dw); the kernel above does a 32-byte sector read-modify-write per 4 useful bytes.
+// Same per-element summation order -> bit-identical.
+constexpr int kTnRedM = 16;
+__global__ void __launch_bounds__(256) tn_reduce_tile_kernel(TnParams p, int BN) {
+  __shared__ float tile[kTnRedM][64 * 9 + 1];
+  const int mblocks = BN / kTnRedM;
+  const int mb = blockIdx.x % mblocks;
+  int rest = blockIdx.x / mblocks;
+  const int cc = rest % p.cin_chunks, nt = rest / p.cin_chunks;
+  const int mi = threadIdx.x & (kTnRedM - 1), r0 = threadIdx.x / kTnRedM;  // 16 couts x 16 row lanes
+  const int per = (p.total_kblocks + p.ksplit - 1) / p.ksplit;
+  const int n_ks = min(p.ksplit, (p.total_kblocks + per - 1) / per);
+  const size_t stride = (size_t)p.slots_per_group * 128 * BN;
+  const int col = mb * kTnRedM + mi;
+  for (int tap = 0; tap < p.ntaps; ++tap) {
+    const int atom = tap * p.cin_chunks + cc;
+    const int s = atom >> 1, half = atom & 1;
+    const int gm = s / p.slots_per_group, i = s - gm * p.slots_per_group;
+    const int g = nt * p.n_groups_m + gm;
+    const float* base = p.ws + (size_t)g * p.ksplit * stride + ((size_t)i * 128 + half * 64) * BN + col;
+    const int id = p.taps[tap].id;
+    for (int e = r0; e < 64; e += 256 / kTnRedM) {
+      const float* src = base + (size_t)e * BN;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int k = 0;
+      for (; k + 3 < n_ks; k += 4) {
+        a0 += src[(size_t)k * stride];
+        a1 += src[(size_t)(k + 1) * stride];
+        a2 += src[(size_t)(k + 2) * stride];
+        a3 += src[(size_t)(k + 3) * stride];
+      }
+      for (; k < n_ks; ++k) a0 += src[(size_t)k * stride];
+      tile[mi][e * p.RS + id] = (a0 + a1) + (a2 + a3);
+    }
+  }
+  __syncthreads();
+  const int row_len = 64 * p.RS;
+  for (int row = 0; row < kTnRedM; ++row) {
+    float* dst = p.dw + ((size_t)(nt * BN + mb * kTnRedM + row) * p.Cin + cc * 64) * p.RS;
+    for (int j = threadIdx.x; j < row_len; j += 256) dst[j] += tile[row][j];
+  }
+}
+
 // Decomposition shared by the launch and the workspace query.
 static void tn_plan(TnParams& p, int BN, int SMAX) {
   p.n_atoms = p.ntaps * p.cin_chunks;
@@ -1180,6 +1227,12 @@ static int launch_tn_t(TnParams& p, cudaStream_t s) {
   igemm_tn_kernel<BN, SMAX, STAGES><<<groups * p.ksplit, 192, L::kBytes, s>>>(p);
   int rc = check_launch("igemm_tn_kernel");
   if (rc || !p.ws) return rc;
+  const char* etr = getenv("ECGMM_TN_REDUCE_LEGACY");
+  const bool tiled = etr ? atoi(etr) == 0 : (p.ksplit <= 6);  // few partials: writes dominate (see wgrad_halo_reduce_t3)
+  if (p.mode == 0 && p.RS <= 9 && p.ntaps == p.RS && tiled) {
+    tn_reduce_tile_kernel<<<(unsigned)(p.n_tiles_n * (BN / kTnRedM) * p.cin_chunks), 256, 0, s>>>(p, BN);
+    return check_launch("tn_reduce_tile_kernel");
+  }
   const long long total = (long long)groups * p.slots_per_group * 128 * BN;
   tn_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p, BN);
   return check_launch("tn_reduce_kernel");

@@ -458,6 +458,49 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_t_kernel(const WgReduce
   p.dw[((size_t)cout * p.Cin + cin) * p.RS + tap] += (a0 + a1) + (a2 + a3);
 }
 
+// The same fold with COALESCED writes (3x3 only).  The kernel above is one thread per workspace element with the output
+// channel fastest: neighbouring threads update dw elements Cin * 9 floats apart, a read-modify-write of a 32-byte sector
+// per 4 useful bytes -- 50 us per launch at any batch size (profiles/r02_ncu_launches_gb64.txt: 2.6 % of the batch-64
+// step).  Here a CTA owns 16 output channels x one 64-wide Cin slice, gathers the three filter rows of it (type A slots
+// 0 / 1 of group (nt, chunk), type B slot chunk % 2 of group (nt, chunk / 2)) into a [16][64 cin x 9 taps] tile in
+// shared memory in dw's own order, and adds 576 contiguous floats per output channel.  Same summation order per
+// element (k-split index ascending in four interleaved accumulators) -> bit-identical results.
+constexpr int kRtM = 16;
+__global__ void __launch_bounds__(256) wgrad_halo_reduce_t3_kernel(const WgReduceParams p) {
+  __shared__ float tile[kRtM][577];
+  const int mb = blockIdx.x % (128 / kRtM);
+  const int gc = blockIdx.x / (128 / kRtM);  // (nt, chunk)
+  const int chunk = gc % p.cin_chunks, nt = gc / p.cin_chunks;
+  const int mi = threadIdx.x & (kRtM - 1), c0 = threadIdx.x / kRtM;  // 16 x 16
+  const size_t slice = (size_t)2 * 192 * 128;
+  const int m = mb * kRtM + mi;
+  for (int r = 0; r < 3; ++r) {
+    const bool typeB = (r == 2);
+    const int g = typeB ? nt * p.cin_pairs + (chunk >> 1) : nt * p.cin_chunks + chunk;
+    const int slot = typeB ? (chunk & 1) : r;
+    const int ksplit = typeB ? p.ksB : p.ksA;
+    const float* base = p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + (size_t)slot * 192 * 128 + m;
+    for (int c = c0; c < 192; c += 256 / kRtM) {
+      const float* src = base + (size_t)c * 128;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int k = 0;
+      for (; k + 3 < ksplit; k += 4) {
+        a0 += src[(size_t)k * slice];
+        a1 += src[(size_t)(k + 1) * slice];
+        a2 += src[(size_t)(k + 2) * slice];
+        a3 += src[(size_t)(k + 3) * slice];
+      }
+      for (; k < ksplit; ++k) a0 += src[(size_t)k * slice];
+      tile[mi][(c & 63) * 9 + r * 3 + (c >> 6)] = (a0 + a1) + (a2 + a3);
+    }
+  }
+  __syncthreads();
+  for (int row = 0; row < kRtM; ++row) {
+    float* dst = p.dw + ((size_t)(nt * 128 + mb * kRtM + row) * p.Cin + chunk * 64) * 9;
+    for (int j = threadIdx.x; j < 576; j += 256) dst[j] += tile[row][j];
+  }
+}
+
 // KP (multiple of 16, <= 128) minimises the pixel slots wasted at the right edge of a row (ties: larger KP); RPS = 2
 // only where three stages still fit (measured: a small, free reduction of L2 traffic, no speed-up by itself).
 static int round1k(int v) { return (v + 1023) & ~1023; }
@@ -659,7 +702,14 @@ int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
   r.totalB = (long long)q.groupsB * slotsB * ncol * 128;
   r.wsB_off = (long long)q.wsB_off;
   const long long total = r.totalA + r.totalB;  // both multiples of 64 (BN * 128 elements per accumulator)
-  if (q.tmode)
+  // (measured at batch 64: with few partials per element the scattered writes dominate and the tiled fold wins --
+  //  512 channels, k-split 3: 0.638 -> 0.553 ms per 3 launches -- with many partials the one-thread-per-element kernel's
+  //  parallelism wins: 128 channels, k-split 49: 0.420 vs 0.839 ms)
+  const char* ert = getenv("ECGMM_WG_REDUCE_T_LEGACY");
+  const bool tiled = ert ? atoi(ert) == 0 : (q.ksA <= 6);
+  if (q.tmode && R == 3 && S == 3 && tiled)
+    wgrad_halo_reduce_t3_kernel<<<(unsigned)(q.cout_tiles * q.cin_chunks * (128 / kRtM)), 256, 0, st>>>(r);
+  else if (q.tmode)
     wgrad_halo_reduce_t_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r);
   else if (q.ksA >= 16)  // many partials per element: 4 k-groups per element
     wgrad_halo_reduce_kernel<<<(unsigned)((total + 63) / 64), 256, 0, st>>>(r);

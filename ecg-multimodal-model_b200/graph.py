@@ -24,9 +24,28 @@ for another shape.  Memory: the graph owns the activations of one step for its l
 """
 from __future__ import annotations
 
+import contextlib
+import gc
+
 import torch
 
 from . import lib, ops
+
+
+@contextlib.contextmanager
+def _quiet_gc():
+    """No garbage collection while a stream capture is running: a collected object may own pinned host memory, and
+    torch's pinned allocator records an event on every stream that used a block when the block is freed -- on a
+    capturing stream that is a captured event which cannot be queried later (cudaErrorInvalidValue at some unrelated
+    Tensor.item())."""
+    was = gc.isenabled()
+    gc.collect()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
 
 
 def _default_loss(criterion):
@@ -110,7 +129,7 @@ class GraphedTrainStep:
         ops.GRAPH_STATE = self.state
         optimizer._graph_mode = (self.state, self.lr_dev)
         try:
-            with torch.cuda.graph(self.graph):
+            with _quiet_gc(), torch.cuda.graph(self.graph):
                 lib.call("ecgmm_step_advance", ops._ptr(self.state), ops._s())
                 self.loss = eager_step()
         finally:
@@ -192,7 +211,7 @@ class GraphedEvalStep:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
+        with _quiet_gc(), torch.no_grad(), torch.cuda.graph(self.graph):
             self.outputs = self.net(*self.static)
         self._versions = self._state()
 

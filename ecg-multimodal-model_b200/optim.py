@@ -26,6 +26,7 @@ class Adam(torch.optim.Optimizer):
         self._tables = {}
         self._graph_mode = None  # (device step state, device lr vector) while ecgmm.graph captures a step
         self._reserved = {}      # group index -> (pinned host table, device table) for captured steps
+        self._retired = []       # replaced table entries kept alive across a stream capture (see _table)
 
     def _table(self, gi, entries):
         """Device chunk table for group gi, rebuilt only when a pointer changed."""
@@ -51,6 +52,18 @@ class Adam(torch.optim.Optimizer):
         else:
             host = torch.from_numpy(arr).pin_memory()
             table = host.to(entries[0][0].device, non_blocking=True)
+        old = self._tables.get(gi)
+        if old is not None:
+            # Do not let the replaced entry die here if a stream capture is running: its pinned host buffer belongs
+            # to torch's pinned allocator, which records an event on every stream that used the block WHEN THE BLOCK IS
+            # FREED.  If one of those streams is the capturing stream (torch hands out streams from a small pool, so
+            # the warm-up stream of an earlier step can be the capture stream of this one) that event is a captured
+            # event, and the allocator's next query of it -- at an unrelated pinned allocation such as Tensor.item()
+            # -- fails with cudaErrorInvalidValue.  Retired entries are dropped at the next call outside a capture.
+            self._retired.append(old)
+        if self._retired and not (entries[0][0].is_cuda and entries[0][0].device.type == "cuda"
+                                  and torch.cuda.is_current_stream_capturing()):
+            self._retired.clear()
         self._tables[gi] = (key, table, len(rows), host)
         return table, len(rows)
 

@@ -26,6 +26,7 @@ import torch
 
 import os
 
+from . import graph as graph_mod
 from . import lib, ops
 
 F32 = torch.float32
@@ -186,7 +187,7 @@ class ImageEndpoint:
             cur.wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.no_grad(), torch.cuda.graph(g):
+            with graph_mod._quiet_gc(), torch.no_grad(), torch.cuda.graph(g):
                 outs = body(self._static)
             ent = self._graphs[key] = (g, outs, vers)
         return ent

@@ -109,6 +109,43 @@ def test_conv_is_linear_at_full_size():
     assert float(z.float().abs().max()) == 0.0
 
 
+def test_transposed_wgrad_coalesced_fold_is_bit_identical(monkeypatch):
+    """wgrad_halo_reduce_t3_kernel (coalesced writes through a shared-memory tile) against the one-thread-per-element
+    fold it replaces: same summation order per element, so the weight gradients are equal bit for bit."""
+    from ecgmm import ops
+
+    g = torch.Generator().manual_seed(5)
+    for N, H, W, Cin, Cout in ((3, 16, 157, 256, 256), (2, 9, 33, 192, 256), (4, 8, 79, 512, 512)):
+        x = torch.randn(N, H, W, Cin, generator=g).cuda().to(torch.bfloat16)
+        dy = torch.randn(N, H, W, Cout, generator=g).cuda().to(torch.bfloat16)
+        out = []
+        for legacy in ("1", None):
+            monkeypatch.setenv("ECGMM_WG_REDUCE_T_LEGACY", legacy or "0")
+            dw = torch.zeros(Cout, Cin, 3, 3, device="cuda")
+            ops.conv2d_wgrad(x, dy, dw, 3, 3, 1)
+            out.append(dw)
+        assert torch.equal(out[0], out[1]), (Cin, Cout)
+
+
+def test_generic_wgrad_tiled_fold_is_bit_identical(monkeypatch):
+    """tn_reduce_tile_kernel (stride-2 3x3 and 1x1 weight gradients) against the one-thread-per-element fold."""
+    from ecgmm import ops
+
+    g = torch.Generator().manual_seed(6)
+    for N, H, W, Cin, Cout, R, stride in ((3, 17, 45, 64, 128, 3, 2), (2, 16, 39, 256, 512, 3, 2), (3, 17, 45, 64, 128, 1, 2),
+                                          (2, 8, 16, 64, 64, 1, 1), (2, 16, 40, 128, 256, 1, 2)):
+        Ho, Wo = (H + 2 * (R // 2) - R) // stride + 1, (W + 2 * (R // 2) - R) // stride + 1
+        x = torch.randn(N, H, W, Cin, generator=g).cuda().to(torch.bfloat16)
+        dy = torch.randn(N, Ho, Wo, Cout, generator=g).cuda().to(torch.bfloat16)
+        out = []
+        for legacy in ("1", None):
+            monkeypatch.setenv("ECGMM_TN_REDUCE_LEGACY", legacy or "0")
+            dw = torch.zeros(Cout, Cin, R, R, device="cuda")
+            ops.conv2d_wgrad(x, dy, dw, R, R, stride)
+            out.append(dw)
+        assert torch.equal(out[0], out[1]), (Cin, Cout, R, stride)
+
+
 @pytest.mark.parametrize("stack", ["1", "0"], ids=["rolling_accumulators", "halo_kernel"])
 @pytest.mark.parametrize("case", [("stack_63x625", 2, 63, 625, 64, 64, 3, 3, 1), ("stack_ragged", 3, 21, 150, 64, 64, 3, 3, 1),
                                   ("stack_one_row", 2, 1, 200, 64, 64, 3, 3, 1), ("stack_two_rows", 1, 2, 130, 64, 64, 3, 3, 1)],

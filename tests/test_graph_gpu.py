@@ -76,6 +76,27 @@ def test_graphed_steps_match_eager_steps():
     assert float((ya - yb).abs().max()) <= 2e-2 * max(1.0, float(ya.abs().max()))
 
 
+def test_second_graphed_step_after_the_first_is_gone():
+    """Regression: a replaced Adam chunk table (pinned host memory) used to be freed INSIDE the capture of the next
+    graphed step; torch's pinned allocator then recorded its free-time event on a capturing stream whenever torch's
+    stream pool had handed the earlier warm-up stream out again as the capture stream, and the next Tensor.item()
+    died with cudaErrorInvalidValue (cuEventQuery of a captured event).  Build, drop and rebuild several times."""
+    import gc
+
+    for i in range(3):
+        _, b = _pair(0.0)
+        crit = enn.CrossEntropyLoss()
+        ob = eoptim.Adam(b.parameters(), lr=2e-4)
+        batch = _batches(1)[0]
+        step = egraph.GraphedTrainStep(b, crit, ob, batch)
+        losses = [float(step(*batch)) for _ in range(2)]
+        assert losses[1] < losses[0]
+        del step, ob, b
+        gc.collect()
+        for _ in range(40):  # walk torch's stream pool so that different pool streams meet the capture
+            torch.cuda.Stream()
+
+
 def test_dropout_masks_change_between_replays():
     _, b = _pair(0.3)
     crit = enn.CrossEntropyLoss()
