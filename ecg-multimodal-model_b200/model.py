@@ -323,11 +323,20 @@ def _conv_block_fwd(blk, x, save, one_d=False):
 
 
 # BatchNorm-backward sums (sum dz, sum dz * xhat) from the epilogue of the data gradient that produces dz
-# (ecgmm_conv2d_dgrad_reduce, offered for the 64-channel layers).  Correct and under test, but OFF by default: measured
-# on a B200 at batch 512 (profiles/r02e_*) the three reduction passes it removes cost 2.8 ms while the epilogue work
-# makes those three data gradients 4.7 ms slower (one epilogue warp per TMEM quadrant is the bottleneck: ~2500 clocks
-# per tile against 1152 of MMAs) -- step 123.3 ms with, 121.4 ms without.
-FUSED_BWD_REDUCE = os.environ.get("ECGMM_FUSED_BWD_REDUCE", "0") == "1"
+# (ecgmm_conv2d_dgrad_reduce): the separate reduction pass over (x, dz) disappears.  Correct and under test, but OFF by
+# default.  Measured on a B200 inside the batch-512 step (profiles/r02e_*, r02h_*, r02p_*):
+#   * 64-channel layers (rolling-accumulator kernel, 1152 MMA clocks per tile): the three passes it removes cost 2.8 ms,
+#     the epilogue work costs 4.7 ms with one epilogue warp per TMEM quadrant and 3.1 ms with two;
+#   * >= 128 channels (a variant of the CTA-pair kernel with a warp-shuffle transposed reduction, not kept): reduction
+#     passes -2.5 ms, data gradients +3.5 ms, although a tile holds 9-37 k MMA clocks -- the step runs at the board's
+#     power limit (SM clock 1.55-1.65 of 1.965 GHz), where the extra ALU / shuffle work costs clock for everything else.
+FUSED_BWD_REDUCE = os.environ.get("ECGMM_FUSED_BWD_REDUCE", "0")
+
+
+def _fuse_reduce(channels, se):
+    if se is not None or FUSED_BWD_REDUCE == "0":
+        return False
+    return True
 
 
 def _conv_block_bwd(blk, rec, dout, G, dout_partials=None, next_reduce=None):
@@ -359,10 +368,11 @@ def _conv_block_bwd(blk, rec, dout, G, dout_partials=None, next_reduce=None):
             lib.call("ecgmm_colsum", ops._ptr(dpre1), ops._ptr(G(se.fc[0].bias)), n, w1.shape[0], 0, ops._s())
             return q
 
-    fuse = FUSED_BWD_REDUCE and se is None
+    fuse = _fuse_reduce(a.shape[-1], se)                    # for dm (this block's bn1)
+    fuse_in = _fuse_reduce(x.shape[-1], se) and next_reduce is not None  # for dx (the previous block's bn2)
     db_, dz = ops.bn_backward(b, dout, sb, blk.bn2.weight, mask=mask_out, se=gate, se_ctx=se_ctx, want_dz=True,
                               dgamma=G(blk.bn2.weight), dbeta=G(blk.bn2.bias),
-                              partials=dout_partials if fuse else None)
+                              partials=dout_partials if se is None else None)
     del dout
     ops.conv2d_wgrad(m, db_, G(blk.conv2.weight), R, S, 1)
     _, w2d = blk.conv2.shadows()
@@ -379,12 +389,12 @@ def _conv_block_bwd(blk, rec, dout, G, dout_partials=None, next_reduce=None):
         dd, _ = ops.bn_backward(d, dz, sd, dsbn.weight, y=None, dgamma=G(dsbn.weight), dbeta=G(dsbn.bias))
         ops.conv2d_wgrad(x, dd, G(dsc.weight), 1, 1, s)
         dx = ops.conv2d_dgrad(da, w1d, (H, W), s)
-        if fuse and next_reduce is not None:
+        if fuse_in:
             dx, px = ops.conv2d_dgrad(dd, dsc.shadows()[1], (H, W), s, out=dx, accumulate=True, reduce_for=next_reduce)
         else:
             px = None
             ops.conv2d_dgrad(dd, dsc.shadows()[1], (H, W), s, out=dx, accumulate=True)
-    elif fuse and next_reduce is not None:
+    elif fuse_in:
         dx, px = ops.conv2d_dgrad(da, w1d, (H, W), s, out=dz, accumulate=True, reduce_for=next_reduce)
     else:
         dx, px = ops.conv2d_dgrad(da, w1d, (H, W), s, out=dz, accumulate=True), None

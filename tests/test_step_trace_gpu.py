@@ -48,8 +48,10 @@ class Trace:
     def _wrap(self, name, fn):
         def wrapped(*a, **k):
             pre = {}
-            if name == "conv2d_dgrad" and k.get("accumulate"):
-                pre["out0"] = k["out"].clone()
+            if name == "conv2d_dgrad":
+                out_arg = k.get("out", a[4] if len(a) > 4 else None)
+                if k.get("accumulate", a[5] if len(a) > 5 else False):
+                    pre["out0"] = out_arg.clone()
             if name in ("conv2d_wgrad", "stem_conv_wgrad"):
                 pre["dw0"] = a[2].clone()
             if name == "bn_backward":
