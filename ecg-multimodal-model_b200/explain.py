@@ -21,6 +21,9 @@ from . import lib, ops
 
 BF16 = torch.bfloat16
 F32 = torch.float32
+# ECGMM_PERTURB_FUSED=0 keeps the three-kernel path (variants and hidden layer through HBM) for A/B measurements; shapes
+# the fused kernel does not cover (D % 64 != 0, D > 768, hidden != 128) take it regardless.
+FUSED = __import__("os").environ.get("ECGMM_PERTURB_FUSED", "1") != "0"
 
 
 def _head_weights(head):
@@ -59,11 +62,12 @@ def masked_variants(e: torch.Tensor, background: torch.Tensor, masks: torch.Tens
     return out
 
 
-def head_inference(head, x_bf16: torch.Tensor, class_index: int = 1) -> torch.Tensor:
-    """x [rows, D] bf16 -> softmax(fusion_classifier(x))[:, class_index] fp32 (class_index < 0: the logits)."""
+def head_inference(head, x_bf16: torch.Tensor, class_index: int = 1, weights=None) -> torch.Tensor:
+    """x [rows, D] bf16 -> softmax(fusion_classifier(x))[:, class_index] fp32 (class_index < 0: the logits).
+    weights: (w1, b1, w2, b2) as _head_weights returns them, when the caller has already prepared (padded) them."""
     ops._chk(x_bf16, BF16, "x")
     rows, D = x_bf16.shape
-    w1, b1, w2, b2 = _head_weights(head)
+    w1, b1, w2, b2 = weights if weights is not None else _head_weights(head)
     HID, C = w1.shape[0], w2.shape[0]
     if w1.shape[3] != D:
         raise lib.EcgmmError(f"embedding width {D} does not match fusion_classifier[0] ({w1.shape[3]})")
@@ -74,13 +78,72 @@ def head_inference(head, x_bf16: torch.Tensor, class_index: int = 1) -> torch.Te
     return out
 
 
+def _to_bf16(x: torch.Tensor) -> torch.Tensor:
+    x = x.detach().to(F32).contiguous()
+    y = torch.empty(x.shape, dtype=BF16, device=x.device)
+    lib.call("ecgmm_f32_to_bf16", ops._ptr(x), ops._ptr(y), x.numel(), ops._s())
+    return y
+
+
+def _perturbation_inference_fused(w1, b1, w2, b2, e, background, masks, class_index):
+    """One kernel for the whole path (csrc/perturb_fused.cu): the variants only ever exist in shared memory."""
+    for t, name in ((e, "e"), (background, "background"), (masks, "masks")):
+        if not t.is_cuda:
+            raise lib.EcgmmError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if e.dim() != 2 or background.dim() != 1 or masks.dim() != 2 or not (e.shape[1] == background.shape[0] == masks.shape[1]):
+        raise lib.EcgmmError(f"shapes must be e [S,D], background [D], masks [V,D]; got {tuple(e.shape)}, "
+                             f"{tuple(background.shape)}, {tuple(masks.shape)}")
+    if w1.shape[3] != e.shape[1]:
+        raise lib.EcgmmError(f"embedding width {e.shape[1]} does not match fusion_classifier[0] ({w1.shape[3]})")
+    if masks.dtype == torch.bool:
+        masks = masks.view(torch.uint8)
+    if masks.dtype != torch.uint8:
+        raise lib.EcgmmError(f"masks must be uint8 or bool, got {masks.dtype}")
+    S, D = e.shape
+    V, C = masks.shape[0], w2.shape[0]
+    if class_index >= C:
+        raise lib.EcgmmError(f"class_index {class_index} out of range for {C} classes")
+    eb, bb, masks = _to_bf16(e), _to_bf16(background), masks.contiguous()
+    bits = torch.empty((V, D // 32), dtype=torch.int32, device=e.device)
+    lib.call("ecgmm_perturb_pack_masks", ops._ptr(masks), ops._ptr(bits), V, D, ops._s())
+    out = torch.empty((S, V) if class_index >= 0 else (S, V, C), dtype=F32, device=e.device)
+    lib.call("ecgmm_perturb_head_fused", ops._ptr(eb), ops._ptr(bb), ops._ptr(bits), ops._ptr(w1),
+             ops._ptr(b1.to(F32).contiguous()), ops._ptr(w2.to(F32).contiguous()), ops._ptr(b2.to(F32).contiguous()),
+             ops._ptr(out), S, V, D, C, int(class_index), ops._s())
+    return out
+
+
+def _pad_width(head, e, background, masks):
+    """Embedding widths that are not a multiple of 64 (G3's 3 x 224 = 672): zero columns change nothing --
+    0 * w = 0 whichever of e / background the mask selects -- so pad every operand to the next multiple of 64."""
+    D = e.shape[1]
+    pad = (-D) % 64
+    w1, b1, w2, b2 = _head_weights(head)
+    if w1.shape[3] != D or background.shape[0] != D or masks.shape[1] != D:
+        raise lib.EcgmmError(f"embedding width: e {D}, background {background.shape[0]}, masks {masks.shape[1]}, "
+                             f"fusion_classifier[0] {w1.shape[3]}")
+    if pad == 0:
+        return w1, b1, w2, b2, e, background, masks
+    if masks.dtype == torch.bool:
+        masks = masks.view(torch.uint8)
+    P = torch.nn.functional.pad
+    return (P(w1.view(w1.shape[0], D), (0, pad)).view(w1.shape[0], 1, 1, D + pad), b1, w2, b2, P(e.detach(), (0, pad)),
+            P(background.detach(), (0, pad)), P(masks, (0, pad)))
+
+
 def perturbation_inference(fusion_classifier, e, background, masks, class_index: int = 1, chunk_samples: int = 0):
     """prob [S, V] (or logits [S, V, C] when class_index < 0) for all masked variants of all samples.
 
     chunk_samples bounds the bf16 variant buffer (S*V*D*2 bytes; 6.3 MB per sample at V=4096, D=768):
     0 = as many samples per launch as fit in ~4 GB."""
-    S, D = e.shape
-    V = masks.shape[0]
+    if e.dim() != 2 or masks.dim() != 2 or background.dim() != 1:
+        raise lib.EcgmmError(f"shapes must be e [S,D], background [D], masks [V,D]; got {tuple(e.shape)}, "
+                             f"{tuple(background.shape)}, {tuple(masks.shape)}")
+    S, V = e.shape[0], masks.shape[0]
+    w1, b1, w2, b2, e, background, masks = _pad_width(fusion_classifier, e, background, masks)
+    D = e.shape[1]
+    if FUSED and ops._shape_query("ecgmm_perturb_head_fused_supported", D, w1.shape[0], w2.shape[0]):
+        return _perturbation_inference_fused(w1, b1, w2, b2, e, background, masks, class_index)
     if chunk_samples <= 0:
         chunk_samples = max(1, (4 << 30) // max(1, V * D * 2))
     chunk_samples = min(chunk_samples, 65535)  # grid.y limit of the variant-build kernel
@@ -88,7 +151,7 @@ def perturbation_inference(fusion_classifier, e, background, masks, class_index:
     for s0 in range(0, S, chunk_samples):
         es = e[s0:s0 + chunk_samples]
         x = masked_variants(es, background, masks)
-        out = head_inference(fusion_classifier, x.view(-1, D), class_index)
+        out = head_inference(fusion_classifier, x.view(-1, D), class_index, weights=(w1, b1, w2, b2))
         outs.append(out.view(es.shape[0], V) if class_index >= 0 else out.view(es.shape[0], V, -1))
     return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 

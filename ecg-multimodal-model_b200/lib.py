@@ -84,6 +84,10 @@ SIGNATURES = {
     "ecgmm_signal_preprocess": [_p, _i, _p, _p, _ll, _ll, _i, _i, _i, _d, _i, _d, _p],
     "ecgmm_perturb_build": [_p, _p, _p, _p, _ll, _i, _i, _p],
     "ecgmm_head_tail": [_p, _p, _p, _p, _p, _ll, _i, _i, _i, _p],
+    "ecgmm_perturb_head_fused_supported": [_i, _i, _i],
+    "ecgmm_perturb_pack_masks": [_p, _p, _i, _i, _p],
+    "ecgmm_perturb_head_fused": [_p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "ecgmm_f32_to_bf16": [_p, _p, _ll, _p],
     "ecgmm_eg_points": [_p, _p, _p, _p, _p, _ll, _i, _i, _i, _p],
     "ecgmm_eg_gate": [_p, _p, _p, _ll, _i, _i, _p],
     "ecgmm_eg_reduce": [_p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],

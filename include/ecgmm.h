@@ -303,6 +303,20 @@ int ecgmm_perturb_build(const float* e, const float* bg, const uint8_t* masks, e
                         int V, int D, void* stream);
 int ecgmm_head_tail(const ecgmm_bf16* hidden, const float* b1, const float* w2, const float* b2, float* out,
                     long long rows, int HID, int C, int cls, void* stream);
+/* The same path in ONE kernel (csrc/perturb_fused.cu): the masked variants are built by producer warps straight into the
+ * SWIZZLE_128B shared-memory operand of the tcgen05 GEMM (W1 resident in shared memory), the epilogue applies
+ * bias / ReLU / Linear(HID, C) / softmax from TMEM: no variant or hidden tensor in HBM.  e and bg are bf16 here
+ * (ecgmm_f32_to_bf16; the selection between them is exact); the masks are packed once per call to one bit per element
+ * (ecgmm_perturb_pack_masks: masks [V][D] bytes, 16-byte aligned, D % 32 == 0 -> bits [V][D/32] uint32, in the bit
+ * order the kernel expands).  Covered: HID == 128, D % 64 == 0, D <= 768, C <= 8
+ * (ecgmm_perturb_head_fused_supported returns 1); w1 [128][D] bf16, k contiguous.
+ *   out [S][V] = softmax(logits)[cls] (cls >= 0)   or   out [S][V][C] = logits (cls < 0) */
+int ecgmm_perturb_head_fused_supported(int D, int HID, int C);
+int ecgmm_perturb_pack_masks(const uint8_t* masks, uint32_t* bits, int V, int D, void* stream);
+int ecgmm_perturb_head_fused(const ecgmm_bf16* e, const ecgmm_bf16* bg, const uint32_t* bits, const ecgmm_bf16* w1,
+                             const float* b1, const float* w2, const float* b2, float* out, long long S, int V, int D,
+                             int C, int cls, void* stream);
+int ecgmm_f32_to_bf16(const float* x, ecgmm_bf16* y, long long n, void* stream);
 
 /* ------------------------------------------------------------------ expected gradients over the fusion head
  * SURVEY.md section 8f rank 3.  shap_fusion_modal_balance.py:135,159 explains FusionClassifierWrapper (the logits of

@@ -129,7 +129,17 @@ def test_signal_model_and_helpers_flow(stub):
     e, bg = torch.randn(5, 768), torch.randn(768)
     p = explain.perturbation_inference(m.fusion_classifier, e, bg, (torch.rand(16, 768) < 0.5).to(torch.uint8))
     assert p.shape == (5, 16)
-    assert stub[-3:] == ["ecgmm_perturb_build", "ecgmm_conv2d_fwd", "ecgmm_head_tail"]
+    assert stub[-4:] == ["ecgmm_f32_to_bf16", "ecgmm_f32_to_bf16", "ecgmm_perturb_pack_masks", "ecgmm_perturb_head_fused"]
+    # widths the fused kernel does not cover (> 768) take the three-kernel path; 672 = 3 x 224 (G3) is zero-padded to 704
+    from ecgmm.model import MLPHead
+
+    p = explain.perturbation_inference(MLPHead(672, 128, 2), torch.randn(5, 672), torch.randn(672),
+                                       (torch.rand(16, 672) < 0.5).to(torch.uint8))
+    assert p.shape == (5, 16) and stub[-1] == "ecgmm_perturb_head_fused"
+    p = explain.perturbation_inference(MLPHead(1024, 128, 2), torch.randn(5, 1024), torch.randn(1024),
+                                       (torch.rand(16, 1024) < 0.5).to(torch.uint8))
+    assert p.shape == (5, 16)
+    assert stub[-3:] == ["ecgmm_perturb_build", "ecgmm_conv2d_fwd", "ecgmm_head_tail"]  # the uncovered-shape path
     phi, f0, f1 = explain.modality_shapley(m.fusion_classifier, e, bg)
     assert phi.shape == (5, 3) and f0.shape == (5,) and f1.shape == (5,) and stub[-1] == "ecgmm_sgemm"
 
@@ -202,7 +212,8 @@ def test_attribution_and_serving_flows(stub):
     del stub[:]
     coef, icpt = explain.masked_regression(m.fusion_classifier, e, bg[0], masks, w, alpha=1.0)
     assert coef.shape == (5, 768) and icpt.shape == (5,)
-    assert stub == ["ecgmm_ridge_operator", "ecgmm_perturb_build", "ecgmm_conv2d_fwd", "ecgmm_head_tail", "ecgmm_sgemm"]
+    assert stub == ["ecgmm_ridge_operator", "ecgmm_f32_to_bf16", "ecgmm_f32_to_bf16", "ecgmm_perturb_pack_masks",
+                    "ecgmm_perturb_head_fused", "ecgmm_sgemm"]
     explain.modality_share(coef.unsqueeze(-1).contiguous(), reduce="sum")
     with pytest.raises(lib.EcgmmError):
         explain.masked_regression(m.fusion_classifier, e, bg[0], masks)  # neither weights nor operator

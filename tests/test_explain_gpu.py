@@ -1,6 +1,8 @@
 """GPU: batched perturbation inference of the fusion head (configs[3]) on the tcgen05 GEMM path against the
-fp32 oracle.  Tolerance: the first Linear runs with bf16 operands (fp32 accumulation) and a bf16 hidden
-activation, everything after it in fp32: |p - p_ref| <= 1e-2 on probabilities, logits within OUT_TOL."""
+fp32 oracle.  Tolerance: the first Linear runs with bf16 operands (fp32 accumulation), everything after it in fp32:
+|p - p_ref| <= 1e-2 on probabilities, logits within OUT_TOL.  Widths that are a multiple of 64 (<= 768) run the
+one-kernel path (csrc/perturb_fused.cu), the others the three-kernel path; both are checked, and the fused kernel
+additionally against the exact fp32 evaluation of its own bf16-rounded operands."""
 import pytest
 import torch
 
@@ -33,6 +35,57 @@ def test_perturbation_inference_matches_oracle(S, V):
     assert relmax(l, ref_l) <= OUT_TOL
     margin = (ref_l[..., 1] - ref_l[..., 0]).abs() > 2 * OUT_TOL * max(1.0, ref_l.abs().max().item())
     assert torch.equal(l.cpu().argmax(-1)[margin], ref_l.argmax(-1)[margin])
+
+
+@pytest.mark.parametrize("S,V,D,C", [(1, 1, 64, 2), (3, 127, 256, 5), (2, 129, 768, 2), (300, 130, 768, 2),
+                                     (1, 4096, 768, 8), (40, 1000, 768, 2), (5, 128, 192, 3)])
+def test_fused_kernel_against_exact_evaluation_of_its_operands(S, V, D, C):
+    """The fused kernel selects bf16 bit patterns (exact) and accumulates bf16 x bf16 products in fp32: against torch
+    fp32 on the SAME rounded operands only the summation order differs.  (300, 130): 600 tiles, several per CTA, so
+    both A stages and both TMEM accumulators wrap; V = 1 / 127 / 129 / 1000: ragged last tiles."""
+    from ecgmm.model import MLPHead
+
+    torch.manual_seed(S + V + D + C)
+    head = MLPHead(D, 128, C).to(DEV)
+    e, bg, masks = _case(S, V, D=D, seed=S + 7 * V)
+    e, bg, masks = e.to(DEV), bg.to(DEV), masks.to(DEV)
+    assert lib.load().ecgmm_perturb_head_fused_supported(D, 128, C) == 1
+    l = explain.perturbation_inference(head, e, bg, masks, -1)
+    p = explain.perturbation_inference(head, e, bg, masks, C - 1)
+    eb, bb = e.to(torch.bfloat16).float(), bg.to(torch.bfloat16).float()
+    w1 = head.lin1.weight.detach().to(torch.bfloat16).float()
+    for s0 in range(0, S, 64):
+        x = torch.where(masks.bool().unsqueeze(0), eb[s0:s0 + 64].unsqueeze(1), bb.view(1, 1, -1))
+        h = torch.relu(x @ w1.t() + head.lin1.bias.detach())
+        ref = h @ head.lin2.weight.detach().t() + head.lin2.bias.detach()
+        assert relmax(l[s0:s0 + 64], ref) <= 2e-5, (s0, relmax(l[s0:s0 + 64], ref))
+        assert (p[s0:s0 + 64] - torch.softmax(ref, -1)[..., C - 1]).abs().max().item() <= 1e-5
+
+
+def test_fused_and_three_kernel_paths_agree(monkeypatch):
+    """Same inputs through both paths: they differ only by the bf16 rounding of the hidden activation that the
+    three-kernel path stores; a width the fused kernel does not cover (672 = 3 x 224, G3) takes the latter."""
+    _, dut = build_pair(seed=7)
+    e, bg, masks = _case(9, 700, seed=21)
+    a = explain.perturbation_inference(dut.fusion_classifier, e.to(DEV), bg.to(DEV), masks.to(DEV), -1)
+    monkeypatch.setattr(explain, "FUSED", False)
+    b = explain.perturbation_inference(dut.fusion_classifier, e.to(DEV), bg.to(DEV), masks.to(DEV), -1)
+    assert relmax(a, b) <= OUT_TOL
+    monkeypatch.undo()
+    from ecgmm.model import MLPHead
+
+    # a width that is not a multiple of 64 (672 = 3 x 224, G3) is zero-padded by the glue, on either path
+    assert lib.load().ecgmm_perturb_head_fused_supported(672, 128, 2) == 0
+    torch.manual_seed(1)
+    head = MLPHead(672, 128, 2).to(DEV)
+    e, bg, masks = _case(4, 200, D=672, seed=22)
+    x = torch.where(masks.bool().unsqueeze(0), e.unsqueeze(1), bg.view(1, 1, -1)).to(DEV)
+    with torch.no_grad():
+        ref = torch.relu(x @ head.lin1.weight.t() + head.lin1.bias) @ head.lin2.weight.t() + head.lin2.bias
+    for fused in (True, False):
+        monkeypatch.setattr(explain, "FUSED", fused)
+        l = explain.perturbation_inference(head, e.to(DEV), bg.to(DEV), masks.bool().to(DEV), -1)
+        assert l.shape == (4, 200, 2) and relmax(l, ref) <= OUT_TOL
 
 
 def test_variants_are_exact_selections():

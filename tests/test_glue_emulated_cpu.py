@@ -228,11 +228,42 @@ def emu_head_tail(hidden, b1, w2, b2, out, rows, HID, C, cls, stream):
         out.reshape(-1)[:rows].copy_(torch.softmax(logits, 1)[:, cls])
 
 
+def emu_f32_to_bf16(x, y, n, stream):
+    y.reshape(-1)[:n].copy_(x.reshape(-1)[:n].to(torch.bfloat16))
+
+
+def emu_perturb_pack_masks(masks, bits, V, D, stream):
+    """Element 4k + b of each 32-element word on bit 8b + 7 - k (include/ecgmm.h)."""
+    m = (_mat(masks, V, D) != 0).view(V, D // 32, 8, 4).long()  # [.., k, b]
+    k, b = torch.arange(8).view(8, 1), torch.arange(4).view(1, 4)
+    w = (m << (8 * b + 7 - k)).sum((-1, -2))
+    _mat(bits, V, D // 32).copy_(torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32))
+
+
+def _unpack_masks(bits, V, D):
+    w = _mat(bits, V, D // 32).long() & 0xFFFFFFFF
+    k, b = torch.arange(8).view(8, 1), torch.arange(4).view(1, 4)
+    return ((w.view(V, D // 32, 1, 1) >> (8 * b + 7 - k)) & 1).view(V, D).bool()
+
+
+def emu_perturb_head_fused(e, bg, bits, w1, b1, w2, b2, out, S, V, D, C, cls, stream):
+    z = _unpack_masks(bits, V, D)
+    x = torch.where(z.unsqueeze(0), _mat(e, S, D).unsqueeze(1), bg.reshape(1, 1, D))  # bf16: an exact selection
+    h = torch.relu(x.float().view(S * V, D) @ _mat(w1, 128, D).float().t() + b1.reshape(1, 128))
+    logits = h @ _mat(w2, C, 128).t() + b2.reshape(1, C)
+    if cls < 0:
+        _mat(out, S * V, C).copy_(logits)
+    else:
+        out.reshape(-1)[: S * V].copy_(torch.softmax(logits, 1)[:, cls])
+
+
 def test_masked_regression_glue(emulated, monkeypatch):
     """explain.masked_regression: perturbation inference (bf16 operands of the first Linear, as on the device) and the
     [S, V] x [V, D+1] product with the REAL host-designed operator, against the fp32 oracle."""
     for k, v in {"ecgmm_perturb_build": emu_perturb_build, "ecgmm_conv2d_fwd": emu_conv2d_fwd,
-                 "ecgmm_head_tail": emu_head_tail}.items():
+                 "ecgmm_head_tail": emu_head_tail, "ecgmm_f32_to_bf16": emu_f32_to_bf16,
+                 "ecgmm_perturb_pack_masks": emu_perturb_pack_masks,
+                 "ecgmm_perturb_head_fused": emu_perturb_head_fused}.items():
         monkeypatch.setitem(EMULATORS, k, v)
     ora, dut = _pair()
     g = torch.Generator().manual_seed(8)
