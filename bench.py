@@ -441,18 +441,19 @@ def run_ours(args):
     roofline = None
     if dom:
         k = kernels[dom]
-        kname = {"conv_wgrad": "wgrad_halo_kernel + igemm_tn_kernel (conv weight-gradient)",
-                 "conv_fwd": "igemm_nt_kernel + igemm_nt_halo_kernel (conv forward)",
-                 "conv_dgrad": "igemm_nt_kernel + igemm_nt_halo_kernel (conv data-gradient)"}.get(dom, dom)
-        # DRAM bytes per launch of this class from the committed `ncu --set full` capture (profiles/r01_traffic.json,
-        # taken at per-GPU batch 64 through tools/ncu_pick.sh), scaled to this run's per-GPU batch
+        kname = {"conv_wgrad": "wgrad_halo_kernel<128,T> / <64> + igemm_tn_kernel + their split-K folds (conv weight-gradient)",
+                 "conv_fwd": "igemm_nt_pair_kernel + igemm_nt_stack_kernel + igemm_nt_kernel (conv forward)",
+                 "conv_dgrad": "igemm_nt_pair_kernel + igemm_nt_stack_kernel + igemm_nt_kernel (conv data-gradient)",
+                 "bn_bwd_apply": "bn_bwd_apply_kernel + stem_bwd_apply_kernel (BatchNorm backward, dx)"}.get(dom, dom)
+        # DRAM bytes of this class from the committed `ncu --set full` capture of one training step at per-GPU batch 64
+        # (profiles/r02_traffic.json, tools/ncu_traffic_r02.sh), scaled to this run's per-GPU batch, per call of the class
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             ent = tj.get("classes", {}).get(dom)
-            if ent:
-                traffic = ent["dram_bytes_per_launch"] * B / tj["per_gpu_batch"]
+            if ent and k["launches"]:
+                traffic = ent["dram_bytes_per_step"] * B / tj["per_gpu_batch"] / k["launches"]
                 traffic_src = tj.get("source")
         roofline = {"kernel": kname, "bound": k["bound"], "achieved": k["achieved"],
                     "peak": tf_peak if k["bound"] == "tensor" else hbm_peak, "unit": k["unit"], "frac": k["frac"],

@@ -6,6 +6,7 @@ computes with torch operators; torch only owns the memory and the stream.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -46,12 +47,23 @@ def _s():
 # When bench.py sets PROFILE to a list, every convolution call is bracketed by CUDA events on the
 # launching stream and appended as (kind, algorithmic_flops, start_event, end_event).
 PROFILE = None
+# ECGMM_NVTX=1: every launch of a roofline class runs inside an NVTX push/pop range named after the class
+# ("conv_fwd", "conv_dgrad", "conv_wgrad", "bn_bwd_apply", ...), so that `ncu --nvtx --nvtx-include "conv_fwd]"`
+# captures exactly the launches bench.py sums under that name (tools/ncu_traffic_r02.sh).
+NVTX = os.environ.get("ECGMM_NVTX", "0") == "1"
 
 
 def _timed(kind, flops, name, *args, nbytes=None):
     """flops: the class's roofline work (FLOPs for the conv kinds, bytes for the bandwidth-bound ones);
     nbytes: for conv kinds additionally the activation + weight bytes a launch has to move (HBM side of the roofline)."""
     if PROFILE is None:
+        if NVTX:
+            torch.cuda.nvtx.range_push(kind.split("/", 1)[0])
+            try:
+                lib.call(name, *args)
+            finally:
+                torch.cuda.nvtx.range_pop()
+            return
         lib.call(name, *args)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -20,6 +20,8 @@ tensors in the end-of-backward callback (one flat collective, no overlap: the sl
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -30,7 +32,8 @@ class DataParallel(torch.nn.Module):
         self.module = module
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
-        self.min_bucket = int(min_bucket_elems)
+        # smallest prefix worth a collective of its own (0: every stage report); ECGMM_DP_MIN_BUCKET overrides the default
+        self.min_bucket = int(min_bucket_elems) or int(os.environ.get("ECGMM_DP_MIN_BUCKET", "0"))
         self._pending = []
         self._deferred = []  # parameters whose accumulated .grad is reduced at the end of backward
         self._cb_queued = False
