@@ -195,6 +195,33 @@ __device__ __forceinline__ void tma_load_4d_pair(void* smem, const void* desc, u
 __device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
+// The same arrival as a RELEASE at cluster scope: the arriving thread's earlier writes (made visible to the async proxy
+// with fence.proxy.async) are ordered before what rank 0's waiter does next -- for operands a CTA builds with ordinary
+// stores instead of TMA.  Pairs with mbar_wait_cluster.
+__device__ __forceinline__ void mbar_arrive_rank0_release(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint64_t t0 = global_timer_ns();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000)
+        : "memory");
+    if (ok) return;
+    if (global_timer_ns() - t0 > 4000000000ull) {
+      printf("ecgmm: cluster mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
                "r"(ncols)

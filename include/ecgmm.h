@@ -307,9 +307,10 @@ int ecgmm_head_tail(const ecgmm_bf16* hidden, const float* b1, const float* w2, 
  * SWIZZLE_128B shared-memory operand of the tcgen05 GEMM (W1 resident in shared memory), the epilogue applies
  * bias / ReLU / Linear(HID, C) / softmax from TMEM: no variant or hidden tensor in HBM.  e and bg are bf16 here
  * (ecgmm_f32_to_bf16; the selection between them is exact); the masks are packed once per call to one bit per element
- * (ecgmm_perturb_pack_masks: masks [V][D] bytes, 16-byte aligned, D % 32 == 0 -> bits [V][D/32] uint32, in the bit
- * order the kernel expands).  Covered: HID == 128, D % 64 == 0, D <= 768, C <= 8
- * (ecgmm_perturb_head_fused_supported returns 1); w1 [128][D] bf16, k contiguous.
+ * (ecgmm_perturb_pack_masks: masks [V][D] bytes, 16-byte aligned, D % 64 == 0 -> V * D / 32 uint32 words laid out
+ * [D/64 chunks][V][2], in the bit order the kernel expands).  Covered: HID == 128, D % 64 == 0, D <= 768, C <= 8
+ * (ecgmm_perturb_head_fused_supported returns 1); w1 [128][D] bf16, k contiguous.  b1 / w2 / b2 are copied to constant
+ * memory on the launch's stream: calls with DIFFERENT heads must not run concurrently on two streams of one device.
  *   out [S][V] = softmax(logits)[cls] (cls >= 0)   or   out [S][V][C] = logits (cls < 0) */
 int ecgmm_perturb_head_fused_supported(int D, int HID, int C);
 int ecgmm_perturb_pack_masks(const uint8_t* masks, uint32_t* bits, int V, int D, void* stream);

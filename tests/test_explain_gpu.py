@@ -38,13 +38,17 @@ def test_perturbation_inference_matches_oracle(S, V):
 
 
 @pytest.mark.parametrize("S,V,D,C", [(1, 1, 64, 2), (3, 127, 256, 5), (2, 129, 768, 2), (300, 130, 768, 2),
-                                     (1, 4096, 768, 8), (40, 1000, 768, 2), (5, 128, 192, 3)])
-def test_fused_kernel_against_exact_evaluation_of_its_operands(S, V, D, C):
+                                     (1, 4096, 768, 8), (40, 1000, 768, 2), (5, 128, 192, 3), (7, 700, 192, 2),
+                                     (3, 300, 64, 2)])
+@pytest.mark.parametrize("pair", ["1", "0"], ids=["cta_pairs", "single_cta"])
+def test_fused_kernel_against_exact_evaluation_of_its_operands(S, V, D, C, pair, monkeypatch):
     """The fused kernel selects bf16 bit patterns (exact) and accumulates bf16 x bf16 products in fp32: against torch
     fp32 on the SAME rounded operands only the summation order differs.  (300, 130): 600 tiles, several per CTA, so
-    both A stages and both TMEM accumulators wrap; V = 1 / 127 / 129 / 1000: ragged last tiles."""
+    the ring stages and both TMEM accumulators wrap; V = 1 / 127 / 129 / 1000: ragged last tiles.  Both kernels: CTA
+    pairs (cta_group::2, 256 variants per tile, half of W1 per CTA, 8-stage ring) and the single-CTA one."""
     from ecgmm.model import MLPHead
 
+    monkeypatch.setenv("ECGMM_PERTURB_PAIR", pair)  # V <= 128 runs the single-CTA kernel either way
     torch.manual_seed(S + V + D + C)
     head = MLPHead(D, 128, C).to(DEV)
     e, bg, masks = _case(S, V, D=D, seed=S + 7 * V)

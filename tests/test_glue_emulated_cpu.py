@@ -4,7 +4,7 @@ tests/test_control_flow_cpu.py checks call sequences with the launches stubbed o
 use are replaced by torch restatements of what include/ecgmm.h says each one computes (operating on the tensors whose
 pointers the glue passes), so the glue's own arithmetic -- which operand goes where, which GEMM is transposed, how the
 chunks are sliced -- is checked numerically against the oracle without a GPU.  The CUDA code itself is what the GPU
-tests (tests/test_zz_attrib_serve_gpu.py) check."""
+tests (tests/test_attrib_serve_gpu.py) check."""
 import pytest
 import torch
 
@@ -233,15 +233,16 @@ def emu_f32_to_bf16(x, y, n, stream):
 
 
 def emu_perturb_pack_masks(masks, bits, V, D, stream):
-    """Element 4k + b of each 32-element word on bit 8b + 7 - k (include/ecgmm.h)."""
+    """Element 4k + b of each 32-element word on bit 8b + 7 - k; words laid out [D/64 chunks][V][2] (include/ecgmm.h)."""
     m = (_mat(masks, V, D) != 0).view(V, D // 32, 8, 4).long()  # [.., k, b]
     k, b = torch.arange(8).view(8, 1), torch.arange(4).view(1, 4)
-    w = (m << (8 * b + 7 - k)).sum((-1, -2))
-    _mat(bits, V, D // 32).copy_(torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32))
+    w = (m << (8 * b + 7 - k)).sum((-1, -2))  # [V, D/32]
+    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32)
+    bits.reshape(-1)[: V * (D // 32)].view(D // 64, V, 2).copy_(w.view(V, D // 64, 2).permute(1, 0, 2))
 
 
 def _unpack_masks(bits, V, D):
-    w = _mat(bits, V, D // 32).long() & 0xFFFFFFFF
+    w = bits.reshape(-1)[: V * (D // 32)].view(D // 64, V, 2).permute(1, 0, 2).reshape(V, D // 32).long() & 0xFFFFFFFF
     k, b = torch.arange(8).view(8, 1), torch.arange(4).view(1, 4)
     return ((w.view(V, D // 32, 1, 1) >> (8 * b + 7 - k)) & 1).view(V, D).bool()
 

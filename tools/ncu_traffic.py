@@ -1,66 +1,108 @@
-"""profiles/r02_traffic.json from the per-class `ncu --set full` captures of tools/ncu_traffic_r02.sh.
+"""profiles/r02_traffic.json + a per-class table from the light ncu pass of tools/ncu_traffic_r02.sh.
 
-    python tools/ncu_traffic.py gpurun_out/r02z > profiles/r02_ncu_class_traffic.txt     (also writes the JSON)
+    python tools/ncu_traffic.py gpurun_out/r02z_step_metrics.csv > profiles/r02z_ncu_class_traffic.txt   (also writes the JSON)
 
-Each capture holds ONE training step's launches of one roofline class of bench.py (third step at per-GPU batch 64,
-selected by NVTX range).  Per class: launches, device time, DRAM bytes read + written (dram__bytes_read.sum +
-dram__bytes_write.sum), time-weighted tensor-pipe and DRAM utilisation.  bench.py scales dram_bytes_per_step by
-batch / 64 and divides by the class's calls per step to report roofline.traffic per launch."""
+Input: `ncu --profile-from-start off --metrics <time, dram read, dram write, tensor pipe %, dram %> --csv` over every
+launch of ONE training step (the third step of tools/one_step.py at per-GPU batch 64, ECGMM_SIDE_STREAM=0).  Launches
+are assigned to bench.py's roofline classes by kernel name; the conv forward and data-gradient classes share kernels and
+are told apart by order (every forward launch of a step precedes every backward launch: the first 28 launches of the
+igemm_nt family are the forward).  Per class: launches, device time, DRAM bytes read + written
+(dram__bytes_read.sum + dram__bytes_write.sum), time-weighted tensor-pipe and DRAM utilisation.  bench.py scales
+dram_bytes_per_step by batch / 64 and divides by the class's calls per step to report roofline.traffic per launch."""
+import collections
 import csv
 import json
 import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CLASSES = ["conv_fwd", "conv_dgrad", "conv_wgrad", "bn_bwd_apply", "bn_bwd_reduce", "bn_apply", "perturb_fused"]
-UNIT_B = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-UNIT_T = {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}
+UNIT_B = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+UNIT_T = {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond": 1, "msecond": 1e3, "second": 1e6}
+FWD_LAUNCHES = 28  # conv forward calls per training step of the fusion model (kernels.conv_fwd.launches of the bench line)
 
 
-def load(path):
-    rows = list(csv.reader(open(path).read().splitlines()))
-    if len(rows) < 3:
-        return []
-    hdr, units = rows[0], rows[1]
-    col = {k: hdr.index(k) for k in ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-                                      "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-                                      "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed") if k in hdr}
-    out = []
-    for r in rows[2:]:
-        if len(r) < len(hdr):
-            continue
-        f = lambda k: float(r[col[k]].replace(",", "") or 0)  # noqa: E731
-        out.append({"name": r[col["Kernel Name"]].split("(")[0].replace("ecgmm::", "").replace("void ", ""),
-                    "us": f("gpu__time_duration.sum") * UNIT_T.get(units[col["gpu__time_duration.sum"]], 1),
-                    "rd": f("dram__bytes_read.sum") * UNIT_B.get(units[col["dram__bytes_read.sum"]], 1),
-                    "wr": f("dram__bytes_write.sum") * UNIT_B.get(units[col["dram__bytes_write.sum"]], 1),
-                    "tensor": f("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
-                    "dram": f("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")})
-    return out
+def launches(path):
+    lines = [l for l in open(path) if l.startswith('"')]
+    out = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        d = out.setdefault(row["ID"], {"name": row["Kernel Name"].split("(")[0].replace("ecgmm::", "").replace("void ", "")})
+        v = float(row["Metric Value"].replace(",", "") or 0)
+        m, u = row["Metric Name"], row["Metric Unit"]
+        if m == "gpu__time_duration.sum":
+            d["us"] = v * UNIT_T.get(u, 1)
+        elif m == "dram__bytes_read.sum":
+            d["rd"] = v * UNIT_B.get(u, 1)
+        elif m == "dram__bytes_write.sum":
+            d["wr"] = v * UNIT_B.get(u, 1)
+        elif m.startswith("sm__pipe_tensor"):
+            d["tensor"] = v
+        elif m.startswith("gpu__dram_throughput"):
+            d["dram"] = v
+    return list(out.values())
+
+
+def classify(ls):
+    nt_seen = 0
+    for x in ls:
+        n = x["name"]
+        if n.startswith("igemm_nt"):
+            x["cls"] = "conv_fwd" if nt_seen < FWD_LAUNCHES else "conv_dgrad"
+            nt_seen += 1
+        elif n.startswith("wgrad_halo") or n.startswith("igemm_tn") or n.startswith("tn_reduce"):
+            x["cls"] = "conv_wgrad"
+        elif n.startswith("bn_bwd_apply") or n.startswith("stem_bwd_apply"):
+            x["cls"] = "bn_bwd_apply"
+        elif n.startswith("bn_bwd_reduce"):
+            x["cls"] = "bn_bwd_reduce"
+        elif n.startswith("bn_apply"):
+            x["cls"] = "bn_apply"
+        elif n.startswith("bn_relu_maxpool"):
+            x["cls"] = "bn_pool_fwd"
+        elif n.startswith("stem_fwd_ring"):
+            x["cls"] = "stem_fwd"
+        elif n.startswith("stem_wgrad"):
+            x["cls"] = "stem_wgrad"
+        elif n.startswith("chan_stats"):
+            x["cls"] = "bn_stats"
+        else:
+            x["cls"] = "other"
+    return ls
 
 
 def main():
-    prefix = sys.argv[1]
-    result = {"source": f"{os.path.basename(prefix)}_full_<class>.csv: ncu --set full --clock-control none, the launches of "
-                        "one training step (third step of tools/one_step.py at per-GPU batch 64) per roofline class, selected "
-                        "by the NVTX ranges of ecgmm.ops (tools/ncu_traffic_r02.sh); dram__bytes_read.sum + dram__bytes_write.sum",
-              "per_gpu_batch": 64, "classes": {}}
-    for c in CLASSES:
-        path = f"{prefix}_full_{c}.csv"
-        if not os.path.exists(path):
-            continue
-        ls = load(path)
-        if not ls:
-            continue
-        t = sum(x["us"] for x in ls)
-        by = sum(x["rd"] + x["wr"] for x in ls)
-        print(f"# {c}: {len(ls)} launches, {t:.1f} us, DRAM {by / 1e6:.1f} MB "
-              f"(read {sum(x['rd'] for x in ls) / 1e6:.1f} / write {sum(x['wr'] for x in ls) / 1e6:.1f}), "
-              f"tensor pipe {sum(x['tensor'] * x['us'] for x in ls) / t:.1f} %, DRAM {sum(x['dram'] * x['us'] for x in ls) / t:.1f} % (time-weighted)")
-        for x in ls:
-            print(f"   {x['name'][:52]:52s} {x['us']:9.1f} us  rd {x['rd'] / 1e6:9.2f} MB  wr {x['wr'] / 1e6:9.2f} MB  "
-                  f"tensor {x['tensor']:5.1f} %  dram {x['dram']:5.1f} %")
-        result["classes"][c] = {"dram_bytes_per_step": by, "kernels_profiled": len(ls), "device_us": round(t, 1)}
+    path = sys.argv[1]
+    ls = classify([x for x in launches(path) if "us" in x])
+    total = sum(x["us"] for x in ls)
+    result = {"source": f"{os.path.basename(path)}: ncu --profile-from-start off --metrics (time, dram__bytes_read.sum, "
+                        "dram__bytes_write.sum, tensor pipe %, dram %) --clock-control none over every launch of the third "
+                        "training step of tools/one_step.py at per-GPU batch 64 (tools/ncu_traffic_r02.sh), classified by "
+                        "tools/ncu_traffic.py", "per_gpu_batch": 64, "classes": {}}
+    print(f"# {path}: {len(ls)} launches of one training step at batch 64, {total:.0f} us of device time "
+          "(cold-cache, serialised under ncu: compare shares)")
+    agg = collections.OrderedDict()
+    for x in ls:
+        a = agg.setdefault(x["cls"], {"n": 0, "us": 0.0, "rd": 0.0, "wr": 0.0, "t": 0.0, "d": 0.0, "k": collections.OrderedDict()})
+        a["n"] += 1
+        a["us"] += x["us"]
+        a["rd"] += x.get("rd", 0)
+        a["wr"] += x.get("wr", 0)
+        a["t"] += x.get("tensor", 0) * x["us"]
+        a["d"] += x.get("dram", 0) * x["us"]
+        k = a["k"].setdefault(x["name"], [0, 0.0, 0.0])
+        k[0] += 1
+        k[1] += x["us"]
+        k[2] += x.get("rd", 0) + x.get("wr", 0)
+    print(f"{'class':16s} {'launches':>8s} {'us':>10s} {'share':>7s} {'DRAM rd MB':>11s} {'DRAM wr MB':>11s} {'tensor %':>9s} {'DRAM %':>7s}")
+    for c, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+        print(f"{c:16s} {a['n']:8d} {a['us']:10.1f} {a['us'] / total:7.3f} {a['rd'] / 1e6:11.1f} {a['wr'] / 1e6:11.1f} "
+              f"{a['t'] / a['us']:9.1f} {a['d'] / a['us']:7.1f}")
+        if c != "other":
+            result["classes"][c] = {"dram_bytes_per_step": a["rd"] + a["wr"], "kernels_profiled": a["n"],
+                                    "device_us": round(a["us"], 1)}
+    print("\n# per kernel within a class: launches, us, DRAM MB")
+    for c, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+        for k, v in sorted(a["k"].items(), key=lambda kv: -kv[1][1])[:12]:
+            print(f"{c:16s} {k[:56]:56s} n={v[0]:3d} {v[1]:9.1f} us {v[2] / 1e6:9.1f} MB")
     json.dump(result, open(os.path.join(ROOT, "profiles", "r02_traffic.json"), "w"), indent=1)
 
 

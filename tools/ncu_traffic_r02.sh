@@ -1,46 +1,39 @@
 #!/bin/bash
 # Final-build profiles (one ncu-using gpurun call, run only after the same commands exited 0 without ncu):
 #  (1) launch list of the bench command at per-GPU batch 64 (cold-cache, serialised: compare SHARES);
-#  (2) `ncu --set full` of ONE training step's launches of each dominant roofline class (third step of tools/one_step.py
-#      at batch 64, selected through the NVTX ranges ecgmm.ops opens with ECGMM_NVTX=1), for roofline.traffic;
-#  (3) `ncu --set full` of the one-kernel perturbation path (configs[3]).
-# Only the raw-page CSVs are kept; tools/ncu_traffic.py turns them into profiles/r02_traffic.json + a table.
+#  (2) ONE light pass (5 metrics, no replay of the full set) over EVERY launch of the third training step of
+#      tools/one_step.py at batch 64: time, DRAM bytes read / written, tensor-pipe %, DRAM % -> per-class traffic
+#      (tools/ncu_traffic.py classifies the launches by kernel name and order);
+#  (3) `ncu --set full` of two launches of the CTA-pair conv kernel and of the one-kernel perturbation path (the
+#      kernels that are new since the mid-round full capture profiles/r02_ncu_full_summary.txt); raw-page CSV only.
+# A first version captured `--set full` per class through NVTX ranges: 6 minutes per class (every pass restores the
+# multi-GB activations the kernel writes) -- it ran into the call's time limit.
 set -u
 TAG=${1:-r02z}
 O=gpurun_out
 mkdir -p $O
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --launch eager --global-batch 64"
 $B > $O/${TAG}_ncu_plain_bench.log 2>&1 || { echo "plain bench run failed"; tail -5 $O/${TAG}_ncu_plain_bench.log; exit 1; }
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -c 8000 --csv \
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -c 8000 --csv \
   --log-file $O/${TAG}_launches.csv $B > $O/${TAG}_ncu_launches.log 2>&1
-export ECGMM_NVTX=1 ECGMM_SIDE_STREAM=0
+echo "launch list: $(wc -l < $O/${TAG}_launches.csv) lines"
+export ECGMM_SIDE_STREAM=0
 C="python tools/one_step.py 64 3"
 $C > $O/${TAG}_ncu_plain_step.log 2>&1 || { echo "plain step run failed"; tail -5 $O/${TAG}_ncu_plain_step.log; exit 1; }
-pick() {  # class launches-per-step
-  timeout 500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled --nvtx --nvtx-include "$1]" \
-    -s $((2 * $2)) -c "$2" -o $O/tmp_$1 $C > $O/${TAG}_ncu_$1.log 2>&1
-  if [ -f $O/tmp_$1.ncu-rep ]; then
-    ncu -i $O/tmp_$1.ncu-rep --page raw --csv 2>/dev/null > $O/${TAG}_full_$1.csv
-    [ "$1" = "conv_fwd" ] && cp $O/tmp_$1.ncu-rep $O/${TAG}_conv_fwd.ncu-rep   # one report kept whole (source page)
-    rm -f $O/tmp_$1.ncu-rep
-  fi
-  echo "$1: $(wc -l < $O/${TAG}_full_$1.csv 2>/dev/null) csv lines; $(tail -2 $O/${TAG}_ncu_$1.log | tr '\n' ' ')"
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
+M=$M,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed
+ECGMM_PROFILE_LAST=1 timeout 400 ncu --profile-from-start off --metrics $M --clock-control none \
+  --kernel-name-base demangled --csv --log-file $O/${TAG}_step_metrics.csv $C > $O/${TAG}_ncu_step.log 2>&1
+echo "step metrics: $(wc -l < $O/${TAG}_step_metrics.csv) lines"
+full() {  # name regex skip count command...
+  local name=$1 re=$2 skip=$3 cnt=$4; shift 4
+  timeout 300 ncu --set full --clock-control none --kernel-name-base demangled -k regex:"$re" -s "$skip" -c "$cnt" \
+    -o /tmp/ncu_$name "$@" > $O/${TAG}_ncu_$name.log 2>&1
+  [ -f /tmp/ncu_$name.ncu-rep ] && ncu -i /tmp/ncu_$name.ncu-rep --page raw --csv 2>/dev/null > $O/${TAG}_full_$name.csv
+  echo "$name: $(wc -l < $O/${TAG}_full_$name.csv 2>/dev/null) csv lines"
 }
-# launches per training step of the fusion model at 250x2500 (kernels.<class>.launches of the bench line; a weight
-# gradient with a split-K workspace is two kernels per call, the stem-side classes are separate)
-pick conv_fwd 28
-pick conv_dgrad 27
-pick conv_wgrad 56
-pick bn_bwd_apply 29
-pick bn_bwd_reduce 29
-pick bn_apply 27
-unset ECGMM_NVTX ECGMM_SIDE_STREAM
-P="python tools/perturb_bench.py --samples 64 --iters 2"
-$P > $O/${TAG}_ncu_plain_perturb.log 2>&1 && timeout 300 ncu --set full --clock-control none --import-source on \
-  --kernel-name-base demangled -k regex:perturb_fused_kernel -s 3 -c 1 -o $O/tmp_pf $P > $O/${TAG}_ncu_perturb.log 2>&1
-if [ -f $O/tmp_pf.ncu-rep ]; then
-  ncu -i $O/tmp_pf.ncu-rep --page raw --csv 2>/dev/null > $O/${TAG}_full_perturb_fused.csv
-  cp $O/tmp_pf.ncu-rep $O/${TAG}_perturb_fused.ncu-rep
-fi
-rm -f $O/tmp_*.ncu-rep
-ls -la $O/${TAG}_*
+full nt_pair "igemm_nt_pair_kernel" 60 2 $C
+unset ECGMM_SIDE_STREAM
+P="python tools/perturb_bench.py --samples 64 --iters 2 --cpu-samples 1"
+$P > $O/${TAG}_ncu_plain_perturb.log 2>&1 && full perturb_fused "perturb_fused_kernel" 3 1 $P
+du -sh $O; ls -la $O/${TAG}_*

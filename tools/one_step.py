@@ -1,5 +1,6 @@
 """Three training steps of the fusion model at a given per-GPU batch and nothing else (profiling target: ncu
-attaches to this instead of the whole bench.py).   python tools/one_step.py [batch=64] [steps=3]"""
+attaches to this instead of the whole bench.py).   python tools/one_step.py [batch=64] [steps=3]
+ECGMM_PROFILE_LAST=1: cudaProfilerStart() before the last step (for `ncu --profile-from-start off`)."""
 import os
 import sys
 
@@ -27,7 +28,10 @@ model = ecgmm.ECGMultimodalModel(Cfg).train()
 crit = enn.CrossEntropyLoss()
 opt = eoptim.Adam(model.parameters(), lr=1e-4)
 image, ecg, clin, labels = [t.to(dev) for t in bench.synth_batch(B, 42)]
-for _ in range(steps):
+for i in range(steps):
+    if i == steps - 1 and os.environ.get("ECGMM_PROFILE_LAST") == "1":  # ncu --profile-from-start off: last step only
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
     opt.zero_grad()
     out = model(image, ecg, clin)
     (crit(out[3], labels) + 0.1 * out[4]).backward()
