@@ -5,19 +5,22 @@
 //
 // The three-kernel path of perturb.cu writes the S*V x D variants to HBM as bf16, reads them back in the GEMM and
 // round-trips the hidden layer once more (head_tail).  Here the variants never exist outside shared memory:
-//   warps 2..9  (producers) build the A operand of the GEMM directly in its SWIZZLE_128B K-major shared-memory layout.
+//   producer warps          build the A operand of the GEMM directly in its SWIZZLE_128B K-major shared-memory layout.
 //                           The masks are shared by all samples: they are packed once per call to one BIT per element
-//                           (ecgmm_perturb_pack_masks: V x D / 8 bytes, L1/L2-resident) in an order chosen so that one
+//                           (ecgmm_perturb_pack_masks: V x D / 8 bytes, chunk-major) in an order chosen so that one
 //                           shift puts four elements' bits on the sign bits of a register's four bytes and PRMT's
 //                           sign-replicate mode expands them to the 16-bit select masks of two bf16 pairs.  The
-//                           selection between the bf16 bit patterns of e[s] and b is exact (no arithmetic).  Two
-//                           groups of four warps alternate over the K chunks (one group per stage of the ring) with
-//                           the mask words prefetched two chunks ahead, so the L2 latency never sits on the ring;
-//   warp 1                  tcgen05.mma M128 x N128 x K16 against W1, which stays RESIDENT in shared memory for the
-//                           whole persistent CTA (D <= 768: 192 KB), accumulators double-buffered in TMEM;
-//   warps 10..13 (epilogue) TMEM -> + b1 -> ReLU -> Linear(128, C) -> softmax, fp32, one thread per variant row.
-// HBM traffic per variant: 4 (or 4 C) bytes out.  Bound: shared-memory bandwidth (MMA operand reads 128 B/clk + producer
-// writes 64 B/clk of the 128 B/clk an SM moves), i.e. ~2/3 of the tensor pipe.
+//                           selection between the bf16 bit patterns of e[s] and b is exact (no arithmetic).  Groups of
+//                           four warps take turns over the K chunks (one ring stage each); a thread owns ONE 16-byte
+//                           piece of e[s] / b and eight rows (see PfChunk), the next chunk's operands are loaded
+//                           before the current one is built;
+//   one MMA warp            tcgen05.mma (M128 or, on CTA pairs, M256) x N128 x K16 against W1, which stays RESIDENT in
+//                           shared memory for the whole persistent CTA, accumulators double-buffered in TMEM;
+//   4 epilogue warps        TMEM -> + b1 -> ReLU -> Linear(128, C) -> softmax, fp32, one thread per variant row, the
+//                           head's operands in constant memory.
+// Two kernels: perturb_fused_pair_kernel (default when a sample has more than 128 variants; cta_group::2, half of W1
+// per CTA, 8-stage ring, 16 producer warps: 0.73 of the measured tensor peak at D = 768) and perturb_fused_kernel (single
+// CTA, all of W1 resident = 192 KB, 2-stage ring: 0.54).  HBM traffic per variant: 4 (or 4 C) bytes out.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -306,20 +309,16 @@ __global__ void __launch_bounds__(kPfThreads, 1) perturb_fused_kernel(const __gr
 // ---------------------------------------------------------------------------------------------------------------------
 // The same path on CTA PAIRS (tcgen05 cta_group::2, M = 256): the two CTAs of a cluster take two adjacent 128-variant
 // tiles of the same sample; each keeps HALF of W1 resident (64 of the 128 hidden units: 96 KB at D = 768), which frees
-// 128 KB for an 8-stage ring of A chunks.  ncu on the single-CTA kernel (profiles/r02z_ncu_full_pair_and_perturb.txt):
-// tensor pipe 26 % busy, 845 clocks per K chunk against 256 of MMA -- with only two 16 KB stages next to the resident W1
-// the producers' latency (mask word -> select -> st.shared -> fence.proxy.async -> arrive) cannot be overlapped with
-// more than one chunk of MMA.  Here four chunks per producer group are in flight, and each SM reads half of B.
+// 128 KB for an 8-stage ring of A chunks, and each SM reads half of B (shared-memory traffic per chunk: 16 KB written +
+// 24 KB read instead of 16 + 32).
 // Barriers: every CTA owns aempty[] / tfull[] (rank 0's multicast tcgen05.commit arrives on both copies); afull[],
 // tempty[] and wfull are rank 0's: the 4 producer warps of EACH CTA arrive on afull[stage] (release at cluster scope
 // after fence.proxy.async: the tensor core reads rank 1's shared memory on behalf of rank 0's MMA), all 8 epilogue
 // warps on tempty[], and both CTAs' TMA bytes of W1 complete on wfull.
 constexpr int kPpStages = 8;
 constexpr int kPpWChunk = 64 * 128;  // one 64-wide K chunk of HALF of W1: 64 hidden units x 128 B
-// Producer groups of 4 warps; group g builds the chunks i = g (mod kPpGroups).  A producer warp needs ~215 instructions
-// (and one L1 round trip, one fence.proxy.async) per chunk and runs at a warp's serial issue rate: with two groups the
-// kernel sat at ~810 clocks per chunk with the schedulers 33 % busy, whatever the ring depth.  More groups = more chunks
-// under construction at once; the ring has room for them.
+// Producer groups of 4 warps; group g builds the chunks i = g (mod kPpGroups): four chunks under construction at once,
+// the ring has room for them.
 constexpr int kPpGroups = 4;
 constexpr int kPpThreads = (2 + 4 * kPpGroups + 4) * 32;
 
