@@ -12,5 +12,5 @@ T4="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 
 run bench_n8 300 $T8 bench.py --gpus 8 --steps 10 --warmup 3
 run perturb_n8 200 $T8 bench.py --config perturb
 run kfold_n8 300 $T8 bench.py --config kfold
-run dp_check_n4 300 $T4 tools/dp_check.py
+
 cat $O/${TAG}_index.log
