@@ -2,6 +2,8 @@
 // and the space-to-depth staging of the ResNet stem input.
 #include "common.h"
 
+#include <string.h>
+
 namespace ecgmm {
 
 // [N][C][P] fp32 -> [N][P][C] bf16 through a 32x32 shared-memory tile (P = H*W).
@@ -181,6 +183,80 @@ extern "C" int ecgmm_conv_weight_prep(const float* w, ecgmm_bf16* w_fwd, ecgmm_b
   conv_weight_prep_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, reinterpret_cast<__nv_bfloat16*>(w_fwd), reinterpret_cast<__nv_bfloat16*>(w_dgrad), O, I, R * S);
   return check_launch("conv_weight_prep_kernel");
+}
+
+// All stale convolution weights of a stage in ONE launch (27 launches of conv_weight_prep_kernel per training step
+// were 0.2 ms at per-GPU batch 64, mostly launch gaps and 2-byte scattered stores).  A CTA converts a 32 (o) x 32 (i) x RS
+// block: coalesced fp32 reads (32 i x RS contiguous floats per output channel), a bf16 tile in shared memory, then
+// 64-byte runs along i for w_fwd [O][RS][I] and along o for w_dgrad [I][RS][O].
+constexpr int kPrepBatch = 32;
+struct PrepBatchParams {
+  const float* w[kPrepBatch];
+  __nv_bfloat16* fwd[kPrepBatch];
+  __nv_bfloat16* dg[kPrepBatch];
+  int O[kPrepBatch], I[kPrepBatch], RS[kPrepBatch];
+  int block_end[kPrepBatch];  // exclusive prefix sum of the CTAs per tensor
+  int n;
+};
+
+__global__ void __launch_bounds__(256) conv_weight_prep_batch_kernel(const __grid_constant__ PrepBatchParams p) {
+  __shared__ __nv_bfloat16 tile[32][32 * 9 + 2];  // [o][i * RS + t], row padded against bank conflicts
+  int k = 0;
+  while (k < p.n - 1 && (int)blockIdx.x >= p.block_end[k]) ++k;
+  const int b = blockIdx.x - (k ? p.block_end[k - 1] : 0);
+  const int O = p.O[k], I = p.I[k], RS = p.RS[k];
+  const int ib = I / 32;
+  const int o0 = (b / ib) * 32, i0 = (b % ib) * 32;
+  const float* w = p.w[k];
+  const int run = 32 * RS;  // contiguous floats per output channel of this block
+  for (int e = threadIdx.x; e < 32 * run; e += 256) {
+    const int o = e / run, r = e - o * run;
+    tile[o][r] = __float2bfloat16(w[((size_t)(o0 + o) * I + i0) * RS + r]);
+  }
+  __syncthreads();
+  __nv_bfloat16* fwd = p.fwd[k];
+  __nv_bfloat16* dg = p.dg[k];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;  // 8 warps
+  for (int ot = grp; ot < 32 * RS; ot += 8) {  // (o, t) rows of w_fwd: 32 consecutive i
+    const int o = ot / RS, t = ot - o * RS;
+    if (fwd) fwd[((size_t)(o0 + o) * RS + t) * I + i0 + lane] = tile[o][lane * RS + t];
+  }
+  for (int it = grp; it < 32 * RS; it += 8) {  // (i, t) rows of w_dgrad: 32 consecutive o
+    const int i = it / RS, t = it - i * RS;
+    if (dg) dg[((size_t)(i0 + i) * RS + t) * O + o0 + lane] = tile[lane][i * RS + t];
+  }
+}
+
+extern "C" int ecgmm_conv_weight_prep_batch(const ecgmm_weight_prep_desc* descs, int n, void* stream) {
+  ECGMM_CHECK(n >= 0 && (descs || n == 0), ECGMM_ERR_ARG, "conv_weight_prep_batch: null descriptor array");
+  for (int base = 0; base < n; base += kPrepBatch) {
+    PrepBatchParams p;
+    memset(&p, 0, sizeof(p));
+    int blocks = 0;
+    const int m = n - base < kPrepBatch ? n - base : kPrepBatch;
+    for (int k = 0; k < m; ++k) {
+      const ecgmm_weight_prep_desc& d = descs[base + k];
+      const int RS = d.R * d.S;
+      ECGMM_CHECK(d.w && (d.w_fwd || d.w_dgrad), ECGMM_ERR_ARG, "conv_weight_prep_batch: null pointer in descriptor %d", base + k);
+      ECGMM_CHECK(d.O > 0 && d.I > 0 && d.O % 32 == 0 && d.I % 32 == 0 && RS >= 1 && RS <= 9, ECGMM_ERR_SHAPE,
+                  "conv_weight_prep_batch: descriptor %d: O=%d I=%d must be multiples of 32, R*S=%d <= 9 "
+                  "(use ecgmm_conv_weight_prep otherwise)", base + k, d.O, d.I, RS);
+      p.w[k] = d.w;
+      p.fwd[k] = reinterpret_cast<__nv_bfloat16*>(d.w_fwd);
+      p.dg[k] = reinterpret_cast<__nv_bfloat16*>(d.w_dgrad);
+      p.O[k] = d.O;
+      p.I[k] = d.I;
+      p.RS[k] = RS;
+      blocks += (d.O / 32) * (d.I / 32);
+      p.block_end[k] = blocks;
+    }
+    p.n = m;
+    if (blocks == 0) continue;
+    conv_weight_prep_batch_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    int rc = check_launch("conv_weight_prep_batch_kernel");
+    if (rc) return rc;
+  }
+  return ECGMM_OK;
 }
 
 extern "C" int ecgmm_stem_weight_prep(const float* w, ecgmm_bf16* w_s2d, void* stream) {

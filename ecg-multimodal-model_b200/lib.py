@@ -27,6 +27,7 @@ SIGNATURES = {
     "ecgmm_nchw_f32_to_nhwc_bf16": [_p, _p, _i, _i, _i, _i, _p],
     "ecgmm_nhwc_bf16_to_nchw_f32": [_p, _p, _i, _i, _i, _i, _p],
     "ecgmm_conv_weight_prep": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "ecgmm_conv_weight_prep_batch": [_p, _i, _p],
     "ecgmm_stem_s2d_dims": [_i, _i, POINTER(c_int), POINTER(c_int)],
     "ecgmm_stem_s2d": [_p, _i, _p, _i, _i, _i, _p],
     "ecgmm_stem_weight_prep": [_p, _p, _p],
@@ -107,6 +108,11 @@ SIGNATURES = {
 _RESTYPES = {"ecgmm_last_error": c_char_p, "ecgmm_stem_s2d_dims": None, "ecgmm_launch_count": c_ulonglong,
              "ecgmm_conv2d_wgrad_workspace": c_longlong, "ecgmm_signal_preprocess_workspace": c_longlong,
              "ecgmm_stem_conv_wgrad_workspace": c_longlong, "ecgmm_signal_stem_wgrad_workspace": c_longlong}
+
+
+class WeightPrepDesc(ctypes.Structure):
+    """ecgmm_weight_prep_desc (include/ecgmm.h)."""
+    _fields_ = [("w", _p), ("w_fwd", _p), ("w_dgrad", _p), ("O", _i), ("I", _i), ("R", _i), ("S", _i)]
 
 
 class EcgmmError(RuntimeError):

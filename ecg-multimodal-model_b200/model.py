@@ -95,6 +95,20 @@ class _ShadowMixin:
         return ops.conv_weight_prep(w, need_dgrad=True)
 
 
+def _refresh_conv_shadows(stage):
+    """Refresh the stale bf16 shadows of all plain convolutions of a stage in ONE launch (after an optimizer step every
+    weight is stale: 27 single-tensor launches per training step otherwise)."""
+    convs = stage.__dict__.get("_plain_convs")
+    if convs is None:
+        convs = stage.__dict__["_plain_convs"] = [m for m in stage.modules() if type(m) in (Conv2d, Conv1d)]
+    stale = [m for m in convs if getattr(m, "_shadow_key", None) != (m.weight.data_ptr(), m.weight._version)]
+    if len(stale) < 2:
+        return
+    for m, sh in zip(stale, ops.conv_weight_prep_batch([m.weight.detach() for m in stale])):
+        m._shadow = sh
+        m._shadow_key = (m.weight.data_ptr(), m.weight._version)
+
+
 class Conv2d(_ShadowMixin, _ContainerMixin, nn.Conv2d):
     pass
 
@@ -447,6 +461,7 @@ class ResNet18(_Stage):
             raise lib.EcgmmError("image must be a CUDA tensor (no CPU fallback)")
         image = image.detach().contiguous()
         H, W = image.shape[2], image.shape[3]
+        _refresh_conv_shadows(self)
         xs = ops.stem_s2d(image)
         ws, _ = self.conv1.shadows()
         if self.bn1.training and FUSED_STATS:
@@ -705,6 +720,7 @@ class ResNet1D_SE(_Stage):
         if not sig.is_cuda:
             raise lib.EcgmmError("signal must be a CUDA tensor (no CPU fallback)")
         sig = sig.detach().to(F32).contiguous()
+        _refresh_conv_shadows(self)
         stem, bn0 = self.initial[0], self.initial[1]
         # tensor-core stem (4 samples of all leads per 64-channel pixel) where the length allows it, else the direct kernels
         xs4 = ops.signal_s4d(sig) if SIGNAL_STEM_TC else None

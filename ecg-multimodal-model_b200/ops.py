@@ -116,6 +116,28 @@ def conv_weight_prep(w: torch.Tensor, need_dgrad: bool = True):
     return w_fwd, w_dg
 
 
+def conv_weight_prep_batch(ws):
+    """conv_weight_prep for a list of weights in one launch -> [(w_fwd, w_dgrad), ...].  Weights whose channel counts
+    are not multiples of 32 go through the single-tensor kernel."""
+    out = [None] * len(ws)
+    batch = []
+    for k, w in enumerate(ws):
+        _chk(w, torch.float32, "w")
+        O, I = w.shape[0], w.shape[1]
+        R, S = (1, w.shape[2]) if w.dim() == 3 else (w.shape[2], w.shape[3])
+        if O % 32 or I % 32 or R * S > 9:
+            out[k] = conv_weight_prep(w)
+            continue
+        w_fwd = torch.empty((O, R, S, I), dtype=BF16, device=w.device)
+        w_dg = torch.empty((I, R, S, O), dtype=BF16, device=w.device)
+        out[k] = (w_fwd, w_dg)
+        batch.append((_ptr(w), _ptr(w_fwd), _ptr(w_dg), O, I, R, S))
+    if batch:
+        arr = (lib.WeightPrepDesc * len(batch))(*batch)
+        lib.call("ecgmm_conv_weight_prep_batch", arr, len(batch), _s())
+    return out
+
+
 # ---------------------------------------------------------------- convolutions
 def _conv_out(H, W, R, S, stride, pH, pW):
     return (H + 2 * pH - R) // stride + 1, (W + 2 * pW - S) // stride + 1

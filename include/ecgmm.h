@@ -53,6 +53,15 @@ int ecgmm_nhwc_bf16_to_nchw_f32(const ecgmm_bf16* x, float* y, int N, int C, int
  * Either output may be NULL.  Master weights stay fp32 in the state_dict. */
 int ecgmm_conv_weight_prep(const float* w_oihw, ecgmm_bf16* w_fwd, ecgmm_bf16* w_dgrad, int O, int I, int R, int S,
                            void* stream);
+/* The same conversion for n weights in one launch (a HOST array of descriptors; O and I multiples of 32, R * S <= 9):
+ * the 27 convolutions of the fusion model's two ResNets are refreshed after every optimizer step. */
+typedef struct {
+  const float* w;      /* fp32 [O][I][R][S] */
+  ecgmm_bf16* w_fwd;   /* [O][R][S][I] or NULL */
+  ecgmm_bf16* w_dgrad; /* [I][R][S][O] or NULL */
+  int O, I, R, S;
+} ecgmm_weight_prep_desc;
+int ecgmm_conv_weight_prep_batch(const ecgmm_weight_prep_desc* descs, int n, void* stream);
 
 /* ------------------------------------------------------------------ ResNet18 stem
  * torchvision resnet.py:197 conv1 = Conv2d(3,64,k7,s2,p3,bias=False), reached from

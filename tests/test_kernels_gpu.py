@@ -501,3 +501,19 @@ def test_signal_stem_on_tensor_cores(B, Cin, L):
     ops.signal_stem_wgrad_s4d(xs4, dy.permute(0, 2, 1).contiguous().view(B, 1, -1, 64), dw)
     assert rel_l2(dw, wr.grad) < 2e-3
     assert ops.signal_s4d(torch.zeros(2, Cin, 601, device=DEV)) is None  # L mod 4 == 1: direct kernels
+
+
+def test_batched_weight_prep_is_bit_identical_to_the_single_tensor_kernel():
+    """ecgmm_conv_weight_prep_batch (all stale convolution weights of a stage in one launch) against
+    ecgmm_conv_weight_prep, for every weight shape of the two ResNets plus a channel count it hands back (12)."""
+    from ecgmm import ops
+
+    g = torch.Generator().manual_seed(3)
+    shapes = [(64, 64, 3, 3), (128, 64, 3, 3), (128, 64, 1, 1), (128, 128, 3, 3), (256, 128, 3, 3), (256, 128, 1, 1),
+              (256, 256, 3, 3), (512, 256, 3, 3), (512, 256, 1, 1), (512, 512, 3, 3), (64, 64, 3), (128, 64, 3),
+              (128, 64, 1), (256, 256, 3), (64, 12, 7), (96, 32, 2, 2)]
+    ws = [torch.randn(*sh, generator=g).cuda() for sh in shapes]
+    got = ops.conv_weight_prep_batch(ws * 3)  # 48 tensors: more than one launch of 32
+    for k, (f, d) in enumerate(got):
+        rf, rd = ops.conv_weight_prep(ws[k % len(ws)])
+        assert torch.equal(f, rf) and torch.equal(d, rd), shapes[k % len(ws)]
