@@ -43,26 +43,14 @@ __device__ __forceinline__ uint32_t prmt_sign(uint32_t a, uint32_t selector) {
   return d;
 }
 
-// Cache policy of the three kinds of global loads in these kernels.  The L1 left beside 227 KB of shared memory is ~28 KB;
-// a tile's mask words touch up to 256 different 128-byte lines (one 8-byte word per row and K chunk), which pushed the hot
-// 4.5 KB (e[s], b, b1, W2 -- re-read for every chunk) out of it: the first use of the e / b loads was the top stall of
-// the producers (14.9 % of all samples, long scoreboard = an L2 round trip per chunk).  Mask words therefore bypass L1
-// (they are prefetched two chunks ahead anyway) and the hot rows are marked evict-last.
-__device__ __forceinline__ uint2 ldg_stream_u2(const void* ptr) {
-  uint2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(ptr));
-  return v;
-}
+// Cache policy of the global loads in these kernels.  The L1 left beside 227 KB of shared memory is ~28 KB: the mask words
+// (streamed, each used once) bypass it, the e[s] / b pieces (re-read by every tile of a sample) are marked evict-last.
 __device__ __forceinline__ uint4 ldg_hot_u4(const void* ptr) {
   uint4 v;
   asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0, %1, %2, %3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(ptr));
   return v;
-}
-__device__ __forceinline__ float4 ldg_hot_f4(const float* ptr) {
-  const uint4 v = ldg_hot_u4(ptr);
-  return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
 }
 
 struct alignas(64) PerturbFusedParams {
@@ -312,9 +300,9 @@ __global__ void __launch_bounds__(kPfThreads, 1) perturb_fused_kernel(const __gr
 // 128 KB for an 8-stage ring of A chunks, and each SM reads half of B (shared-memory traffic per chunk: 16 KB written +
 // 24 KB read instead of 16 + 32).
 // Barriers: every CTA owns aempty[] / tfull[] (rank 0's multicast tcgen05.commit arrives on both copies); afull[],
-// tempty[] and wfull are rank 0's: the 4 producer warps of EACH CTA arrive on afull[stage] (release at cluster scope
-// after fence.proxy.async: the tensor core reads rank 1's shared memory on behalf of rank 0's MMA), all 8 epilogue
-// warps on tempty[], and both CTAs' TMA bytes of W1 complete on wfull.
+// tempty[] and wfull are rank 0's: the 4 producer warps of EACH CTA arrive on afull[stage] (after fence.proxy.async:
+// the tensor core reads rank 1's shared memory on behalf of rank 0's MMA, whose thread waits with an acquire at cluster
+// scope), all 8 epilogue warps on tempty[], and both CTAs' TMA bytes of W1 complete on wfull.
 constexpr int kPpStages = 8;
 constexpr int kPpWChunk = 64 * 128;  // one 64-wide K chunk of HALF of W1: 64 hidden units x 128 B
 // Producer groups of 4 warps; group g builds the chunks i = g (mod kPpGroups): four chunks under construction at once,

@@ -195,13 +195,10 @@ __device__ __forceinline__ void tma_load_4d_pair(void* smem, const void* desc, u
 __device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
-// The same arrival as a RELEASE at cluster scope: the arriving thread's earlier writes (made visible to the async proxy
-// with fence.proxy.async) are ordered before what rank 0's waiter does next -- for operands a CTA builds with ordinary
-// stores instead of TMA.  Pairs with mbar_wait_cluster.
-__device__ __forceinline__ void mbar_arrive_rank0_release(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
-               : "memory");
-}
+// Waiter's side for operands that the CTAs of a pair build with ordinary stores (fence.proxy.async, then
+// mbar_arrive_rank0 from either CTA): acquire at cluster scope.  (A release at cluster scope on the ARRIVING side compiles
+// to MEMBAR.ALL.CTA + ERRBAR per arrival -- 15 % of all stall samples in the perturbation kernel -- and is not needed
+// once fence.proxy.async has been executed; CUTLASS's 2-SM transform kernels use the plain remote arrival as well.)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   const uint64_t t0 = global_timer_ns();
   for (;;) {
