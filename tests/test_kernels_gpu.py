@@ -517,3 +517,21 @@ def test_batched_weight_prep_is_bit_identical_to_the_single_tensor_kernel():
     for k, (f, d) in enumerate(got):
         rf, rd = ops.conv_weight_prep(ws[k % len(ws)])
         assert torch.equal(f, rf) and torch.equal(d, rd), shapes[k % len(ws)]
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 125, 1250), (3, 33, 70), (1, 8, 32), (2, 9, 35), (1, 40, 33)])
+def test_tiled_stem_maxpool_is_bit_identical(N, H, W, monkeypatch):
+    """bn_relu_maxpool_tiled_kernel (window staged in shared memory, C = 64) against the per-output kernel: outputs and
+    argmax codes must be identical, including ragged tiles and the image border."""
+    from ecgmm import ops
+
+    g = gen(f"tiledpool{N}{H}{W}")
+    x = nhwc((torch.randn(N, 64, H, W, generator=g) * 1.5).to(DEV).to(BF))
+    gamma = (1 + 0.3 * torch.randn(64, generator=g)).to(DEV)
+    gamma[5] = -0.6
+    beta = (0.2 * torch.randn(64, generator=g)).to(DEV)
+    st = ops.bn_train_stats(x, gamma, beta, None, None, None, 1e-5, 0.1)
+    y1, a1 = ops.bn_relu_maxpool(x, st)
+    monkeypatch.setenv("ECGMM_POOL_LEGACY", "1")
+    y0, a0 = ops.bn_relu_maxpool(x, st)
+    assert torch.equal(y0, y1) and torch.equal(a0, a1)
