@@ -658,7 +658,7 @@ bool nt_halo_supported(int Cin, int Cout, int R, int S, int stride, int W);
 int launch_nt_halo(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y, int N, int H, int W, int R, int S,
                    int dgrad, int accumulate, cudaStream_t st, const float* scale = nullptr,
                    const float* shift = nullptr, const __nv_bfloat16* res = nullptr, int relu = 0);
-// experimental rolling-accumulator kernel (conv_nt_stack.cu), selected only with ECGMM_NT_STACK=1
+// rolling-accumulator kernel (conv_nt_stack.cu)
 bool nt_stack_supported(int Cin, int Cout, int R, int S, int stride, int W);
 // The rolling-accumulator kernel (conv_nt_stack.cu) is the default for the 64 -> 64 3x3 layers (measured inside the
 // training step at batch 512: forward 1068 -> 1296, accumulating data gradient 961 -> 1109 TFLOP/s);

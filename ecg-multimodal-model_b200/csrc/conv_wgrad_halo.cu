@@ -58,8 +58,8 @@ struct alignas(64) WgHaloParams {
   int tmode;          // wgrad_halo_kernel<128, true> (transposed GEMM, see there)
 };
 
-// T = true (EXPERIMENTAL, ECGMM_WG_T=1, 3x3 layers with Cout % 128 == 0; written after the round's GPU budget was spent,
-// NOT yet run on hardware): the TRANSPOSED GEMM
+// T = true (the default for 3x3 layers with Cout % 128 == 0 since round 2; ECGMM_WG_T=0 selects the untransposed kernel):
+// the TRANSPOSED GEMM
 //     dW^T[cout][(r; s, cin)] = sum_pixels dY[pixel][cout] * X[pixel + (r, s)][cin]
 // M = 128 output channels (dY is the A operand: two 64-wide atoms, as it is staged for BN = 128), N = 192 = the three
 // HORIZONTAL taps of filter row r x a 64-wide Cin slice, all read from ONE staged input-row box as three MN-major atoms
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_flat_kernel(const WgRed
   p.dw[((size_t)cout * p.Cin + cin) * p.RS + tap] += acc;
 }
 
-// Reduction of the TRANSPOSED kernel's partials (wgrad_halo_kernel<128, true>; experimental, see there): workspace
+// Reduction of the TRANSPOSED kernel's partials (wgrad_halo_kernel<128, true>, see there): workspace
 // slices [2 slots][192 columns][128 rows]; row m = output channel, column c = (s, cin); type A slot = filter row r of
 // Cin slice g % cin_chunks, type B slot = Cin slice 2 (g % cin_pairs) + slot with r = R - 1.  One thread per element.
 // (A separate kernel so that the two reducers above stay exactly the code that has run on hardware.)

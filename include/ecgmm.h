@@ -381,7 +381,7 @@ int ecgmm_ridge_operator(const uint8_t* masks, const double* weights, int V, int
  *     y[n][h][w][c] = act( conv(x, w)[n][h][w][c] * scale[c] + shift[c] + res[n][h][w][c] ),
  * with no bf16 rounding between the convolution and the affine map.  res may be NULL; relu != 0 applies ReLU.
  * Same shapes / kernels as ecgmm_conv2d_fwd; scale, shift [Cout] fp32 and res (layout of y) 16-byte aligned.
- * EXPERIMENTAL until it has run on hardware: ecgmm.serve uses it only with ECGMM_SERVE_FUSED=1. */
+ * ecgmm.serve uses it by default (ECGMM_SERVE_FUSED=0 selects separate convolution and BatchNorm kernels). */
 int ecgmm_conv2d_fwd_bn(const ecgmm_bf16* x, const ecgmm_bf16* w_fwd, ecgmm_bf16* y, const float* scale,
                         const float* shift, const ecgmm_bf16* res, int relu, int N, int H, int W, int Cin, int Cout,
                         int R, int S, int stride, int padH, int padW, void* stream);

@@ -78,7 +78,7 @@ def test_preprocess_has_no_cpu_fallback():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# Schedule emulation of the experimental time-parallel kernel (csrc/signal_prep.cu, signal_preprocess_block_kernel):
+# Schedule emulation of the time-parallel kernel (csrc/signal_prep.cu, signal_preprocess_block_kernel):
 # 256 blocks of T (odd) samples, zero-state runs, Hillis-Steele scan of s -> M s + f inside 32-block warps with the
 # powers M^1, M^2, M^4, M^8, M^16, a serial pass over the 8 warps with M^32, one matrix-vector product per block, rerun.
 def _df2t(b, a, x, z):

@@ -1,4 +1,4 @@
-"""CPU emulation of the CONTROL LOGIC of the experimental rolling-accumulator kernel (csrc/conv_nt_stack.cu): the
+"""CPU emulation of the CONTROL LOGIC of the rolling-accumulator kernel (csrc/conv_nt_stack.cu): the
 weight-tile order, which output rows an input row feeds at the edges of a unit, the accumulator ring with its wrap
 split, the hand-back discipline (a block is zero when first touched, complete when emitted).  The arithmetic of each
 "MMA group" is a plain matmul here; what is checked is that the schedule of groups adds up to the convolution

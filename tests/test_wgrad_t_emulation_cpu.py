@@ -1,8 +1,8 @@
-"""CPU: index-level emulation of the EXPERIMENTAL transposed weight-gradient mode (csrc/conv_wgrad_halo.cu,
+"""CPU: index-level emulation of the transposed weight-gradient mode (csrc/conv_wgrad_halo.cu,
 wgrad_halo_kernel<128, true> + make_plan + wgrad_halo_reduce_t_kernel): CTA types, split-K ranges, the operands each accumulator slot
 multiplies (dY as A, one staged input row read at three pixel shifts as the N = 192 B operand), the workspace layout
 [slot][192 columns][128 rows] and the reduction's decode back to dw[cout][cin][r][s] -- against torch's weight gradient.
-The kernel has not run on hardware yet; this pins the bookkeeping it was written from."""
+The GPU parity of the kernel is in tests/test_conv_gpu.py; this pins the bookkeeping it was written from."""
 import numpy as np
 import pytest
 import torch
