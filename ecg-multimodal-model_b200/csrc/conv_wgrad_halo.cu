@@ -466,10 +466,16 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_t_kernel(const WgReduce
 // shared memory in dw's own order, and adds 576 contiguous floats per output channel.  Same summation order per
 // element (k-split index ascending in four interleaved accumulators) -> bit-identical results.
 constexpr int kRtM = 16;
+constexpr int kRtCinSplit = 4;                  // a CTA folds 16 output channels x 16 input channels x 9 taps
+constexpr int kRtCin = 64 / kRtCinSplit;
 __global__ void __launch_bounds__(256) wgrad_halo_reduce_t3_kernel(const WgReduceParams p) {
-  __shared__ float tile[kRtM][577];
-  const int mb = blockIdx.x % (128 / kRtM);
-  const int gc = blockIdx.x / (128 / kRtM);  // (nt, chunk)
+  // (a 64-wide Cin slice per CTA meant 256 CTAs for the 512-channel layers: 65 us for a 9 MB result; split 4 ways)
+  __shared__ float tile[kRtM][kRtCin * 9 + 1];
+  int b = blockIdx.x;
+  const int cs = b % kRtCinSplit;
+  b /= kRtCinSplit;
+  const int mb = b % (128 / kRtM);
+  const int gc = b / (128 / kRtM);  // (nt, chunk)
   const int chunk = gc % p.cin_chunks, nt = gc / p.cin_chunks;
   const int mi = threadIdx.x & (kRtM - 1), c0 = threadIdx.x / kRtM;  // 16 x 16
   const size_t slice = (size_t)2 * 192 * 128;
@@ -480,7 +486,9 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_t3_kernel(const WgReduc
     const int slot = typeB ? (chunk & 1) : r;
     const int ksplit = typeB ? p.ksB : p.ksA;
     const float* base = p.ws + (typeB ? p.wsB_off : 0) + (size_t)g * ksplit * slice + (size_t)slot * 192 * 128 + m;
-    for (int c = c0; c < 192; c += 256 / kRtM) {
+    for (int cc = c0; cc < 3 * kRtCin; cc += 256 / kRtM) {  // column c = s * 64 + cin, cin in this CTA's quarter
+      const int sft = cc / kRtCin, ci = cc - sft * kRtCin;
+      const int c = sft * 64 + cs * kRtCin + ci;
       const float* src = base + (size_t)c * 128;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       int k = 0;
@@ -491,13 +499,13 @@ __global__ void __launch_bounds__(256) wgrad_halo_reduce_t3_kernel(const WgReduc
         a3 += src[(size_t)(k + 3) * slice];
       }
       for (; k < ksplit; ++k) a0 += src[(size_t)k * slice];
-      tile[mi][(c & 63) * 9 + r * 3 + (c >> 6)] = (a0 + a1) + (a2 + a3);
+      tile[mi][ci * 9 + r * 3 + sft] = (a0 + a1) + (a2 + a3);
     }
   }
   __syncthreads();
   for (int row = 0; row < kRtM; ++row) {
-    float* dst = p.dw + ((size_t)(nt * 128 + mb * kRtM + row) * p.Cin + chunk * 64) * 9;
-    for (int j = threadIdx.x; j < 576; j += 256) dst[j] += tile[row][j];
+    float* dst = p.dw + ((size_t)(nt * 128 + mb * kRtM + row) * p.Cin + chunk * 64 + cs * kRtCin) * 9;
+    for (int j = threadIdx.x; j < kRtCin * 9; j += 256) dst[j] += tile[row][j];
   }
 }
 
@@ -704,11 +712,14 @@ int launch_wgrad_halo(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw
   const long long total = r.totalA + r.totalB;  // both multiples of 64 (BN * 128 elements per accumulator)
   // (measured at batch 64: with few partials per element the scattered writes dominate and the tiled fold wins --
   //  512 channels, k-split 3: 0.638 -> 0.553 ms per 3 launches -- with many partials the one-thread-per-element kernel's
-  //  parallelism wins: 128 channels, k-split 49: 0.420 vs 0.839 ms)
+  //  parallelism wins: 128 channels, k-split 49: 0.420 vs 0.839 ms.  With the tiled fold's CTAs split 4 ways along Cin
+  //  the crossover moved: whole step at batch 64 with the threshold at 0 / 6 / 12 / 24 / 64 partials:
+  //  16.12 / 16.02 / 15.89 / 15.87 / 15.92 ms)
   const char* ert = getenv("ECGMM_WG_REDUCE_T_LEGACY");
-  const bool tiled = ert ? atoi(ert) == 0 : (q.ksA <= 6);
+  const char* emk = getenv("ECGMM_WG_REDUCE_T_MAXKS");
+  const bool tiled = ert ? atoi(ert) == 0 : (q.ksA <= (emk ? atoi(emk) : 24));
   if (q.tmode && R == 3 && S == 3 && tiled)
-    wgrad_halo_reduce_t3_kernel<<<(unsigned)(q.cout_tiles * q.cin_chunks * (128 / kRtM)), 256, 0, st>>>(r);
+    wgrad_halo_reduce_t3_kernel<<<(unsigned)(q.cout_tiles * q.cin_chunks * (128 / kRtM) * kRtCinSplit), 256, 0, st>>>(r);
   else if (q.tmode)
     wgrad_halo_reduce_t_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r);
   else if (q.ksA >= 16)  // many partials per element: 4 k-groups per element
