@@ -1175,11 +1175,16 @@ __global__ void __launch_bounds__(256) tn_reduce_kernel(TnParams p, int BN) {
 // (cin, tap) (contiguous in dw); the kernel above does a 32-byte sector read-modify-write per 4 useful bytes.
 // Same per-element summation order -> bit-identical.
 constexpr int kTnRedM = 16;
+constexpr int kTnCinSplit = 4;  // a CTA folds 16 couts x 16 cins x RS taps (a whole 64-wide slice per CTA left the
+constexpr int kTnCin = 64 / kTnCinSplit;  // 512-channel stride-2 layer with 128 CTAs)
 __global__ void __launch_bounds__(256) tn_reduce_tile_kernel(TnParams p, int BN) {
-  __shared__ float tile[kTnRedM][64 * 9 + 1];
+  __shared__ float tile[kTnRedM][kTnCin * 9 + 1];
   const int mblocks = BN / kTnRedM;
-  const int mb = blockIdx.x % mblocks;
-  int rest = blockIdx.x / mblocks;
+  int rest = blockIdx.x;
+  const int cs = rest % kTnCinSplit;
+  rest /= kTnCinSplit;
+  const int mb = rest % mblocks;
+  rest /= mblocks;
   const int cc = rest % p.cin_chunks, nt = rest / p.cin_chunks;
   const int mi = threadIdx.x & (kTnRedM - 1), r0 = threadIdx.x / kTnRedM;  // 16 couts x 16 row lanes
   const int per = (p.total_kblocks + p.ksplit - 1) / p.ksplit;
@@ -1191,17 +1196,17 @@ __global__ void __launch_bounds__(256) tn_reduce_tile_kernel(TnParams p, int BN)
     const int s = atom >> 1, half = atom & 1;
     const int gm = s / p.slots_per_group, i = s - gm * p.slots_per_group;
     const int g = nt * p.n_groups_m + gm;
-    const float* base = p.ws + (size_t)g * p.ksplit * stride + ((size_t)i * 128 + half * 64) * BN + col;
+    const float* base = p.ws + (size_t)g * p.ksplit * stride + ((size_t)i * 128 + half * 64 + cs * kTnCin) * BN + col;
     const int id = p.taps[tap].id;
-    for (int e = r0; e < 64; e += 256 / kTnRedM) {
+    for (int e = r0; e < kTnCin; e += 256 / kTnRedM) {
       const float* src = base + (size_t)e * BN;
       tile[mi][e * p.RS + id] = tn_fold(src, stride, n_ks);
     }
   }
   __syncthreads();
-  const int row_len = 64 * p.RS;
+  const int row_len = kTnCin * p.RS;
   for (int row = 0; row < kTnRedM; ++row) {
-    float* dst = p.dw + ((size_t)(nt * BN + mb * kTnRedM + row) * p.Cin + cc * 64) * p.RS;
+    float* dst = p.dw + ((size_t)(nt * BN + mb * kTnRedM + row) * p.Cin + cc * 64 + cs * kTnCin) * p.RS;
     for (int j = threadIdx.x; j < row_len; j += 256) dst[j] += tile[row][j];
   }
 }
@@ -1244,9 +1249,13 @@ static int launch_tn_t(TnParams& p, cudaStream_t s) {
   int rc = check_launch("igemm_tn_kernel");
   if (rc || !p.ws) return rc;
   const char* etr = getenv("ECGMM_TN_REDUCE_LEGACY");
-  const bool tiled = etr ? atoi(etr) == 0 : (p.ksplit <= 6);  // few partials: writes dominate (see wgrad_halo_reduce_t3)
+  const char* emk = getenv("ECGMM_TN_REDUCE_MAXKS");
+  // few partials: the scattered writes of the per-element fold dominate; many (the 1x1 projections, up to 148): its
+  // parallelism wins.  Whole step at batch 64 with the threshold at 0 / 6 / 16 / 40 / 200 partials: 16.24 / 16.19 / 16.15 /
+  // 16.01 / 16.21 ms.
+  const bool tiled = etr ? atoi(etr) == 0 : (p.ksplit <= (emk ? atoi(emk) : 40));
   if (p.mode == 0 && p.RS <= 9 && p.ntaps == p.RS && tiled) {
-    tn_reduce_tile_kernel<<<(unsigned)(p.n_tiles_n * (BN / kTnRedM) * p.cin_chunks), 256, 0, s>>>(p, BN);
+    tn_reduce_tile_kernel<<<(unsigned)(p.n_tiles_n * (BN / kTnRedM) * p.cin_chunks * kTnCinSplit), 256, 0, s>>>(p, BN);
     return check_launch("tn_reduce_tile_kernel");
   }
   const long long total = (long long)groups * p.slots_per_group * 128 * BN;
