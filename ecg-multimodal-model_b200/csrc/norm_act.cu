@@ -88,6 +88,9 @@ __global__ void __launch_bounds__(kRedThreads) chan_stats_kernel(const __nv_bflo
 // One CTA = 8 channels x 128 row lanes (a 32-byte sector per row read); lanes stride over the N*SPLIT
 // partial rows (or over the samples when per-sample sums are wanted) with 4 independent fp64 chains,
 // then a shared-memory fold.  C/8 CTAs keep this latency-bound fold at a few microseconds.
+// (Measured and not kept, round 2: a cluster of 8 CTAs per channel group sharing the rows, rank 0 adding their sums
+// through distributed shared memory - equal at C <= 128, 5-15 us slower per launch at C >= 256: the fold is not the
+// latency chain it looks like, the cluster launch costs more than the trips it saves.  profiles/r02ee_ab*.txt.)
 constexpr int kFinLanes = 128;
 constexpr int kFinCh = 8;
 
@@ -235,6 +238,63 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
   }
 }
 
+// bn_apply_kernel without squeeze-excite for C/8 a power of two <= 256: the grid stride is a multiple of C/8, so a
+// thread keeps its channel group and scale / shift live in registers (the generic kernel pays a 64-bit modulo and four
+// 16-byte coefficient loads per vector: ~140 instructions per 16 bytes, which at the power-capped clock is as much of
+// a limit as the HBM), two vectors per trip.  Same arithmetic per element.
+template <bool RES, bool RELU>
+__global__ void __launch_bounds__(256) bn_apply_fast_kernel(const uint4* __restrict__ x,
+                                                             const float* __restrict__ scale,
+                                                             const float* __restrict__ shift,
+                                                             const uint4* __restrict__ res, uint4* __restrict__ y,
+                                                             uint8_t* __restrict__ mask_out, int CG,
+                                                             size_t total_vec) {
+  constexpr int U = 2;
+  const size_t stride = (size_t)gridDim.x * 256;
+  const size_t i0 = blockIdx.x * (size_t)256 + threadIdx.x;
+  const int cg = (int)(i0 & (size_t)(CG - 1));
+  float sc[8], sh[8];
+  load8f(scale + cg * 8, sc);
+  load8f(shift + cg * 8, sh);
+  for (size_t i = i0; i < total_vec; i += U * stride) {
+    uint4 vx[U], vr[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t k = i + u * stride;
+      if (k < total_vec) {
+        vx[u] = ld_stream(x + k);
+        if (RES) vr[u] = ld_stream(res + k);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t k = i + u * stride;
+      if (k >= total_vec) break;
+      float f[8];
+      unpack8(vx[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (RES) {
+        float r[8];
+        unpack8(vr[u], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += r[j];
+      }
+      if (RELU) {
+        if (mask_out) {
+          uint32_t m = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m |= (f[j] > 0.f ? 1u : 0u) << j;
+          mask_out[k] = (uint8_t)m;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      y[k] = pack8(f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // stem: y = maxpool3x3/s2/p1(relu(x*scale + shift)), arg = position of the maximum inside the
 // window (first maximum in row-major window order, torch's tie rule), 0..8
@@ -326,6 +386,12 @@ __global__ void __launch_bounds__(256, 4) bn_relu_maxpool_kernel(const __nv_bflo
 // Same arithmetic and tie rule -> bit-identical outputs and argmax codes.
 constexpr int kPoolTOH = 4, kPoolTOW = 16, kPoolIH = 2 * kPoolTOH + 1, kPoolIW = 2 * kPoolTOW + 1;
 
+// BRANCHFREE (default): the tile is stored in the "flipped" domain (sign bit toggled where scale < 0, which is what
+// the scan compares anyway) and positions outside the image hold -inf there, so the 9-tap scan needs no bounds
+// tests (the v1 scan carried 18 divergent-branch regions per thread) and the 4 XORs per tap move to the fill.  A
+// thread's channel group is tid & 7 in the fill AND in the scan (256 % 8 == 0), so the flip words are per-thread
+// constants.  -inf never wins a strict > against the initial -inf: same winners, same codes as v1.
+template <bool BRANCHFREE>
 __global__ void __launch_bounds__(256) bn_relu_maxpool_tiled_kernel(const __nv_bfloat16* __restrict__ x,
                                                                     const float* __restrict__ scale,
                                                                     const float* __restrict__ shift,
@@ -341,40 +407,77 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_tiled_kernel(const __nv_b
   const int oh0 = th * kPoolTOH, ow0 = tw * kPoolTOW;
   const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
   const uint4* xin = reinterpret_cast<const uint4*>(x) + n * (size_t)H * W * 8;
-  for (int e = threadIdx.x; e < kPoolIH * kPoolIW * 8; e += 256) {
-    const int cg = e & 7, pix = e >> 3;
-    const int r = pix / kPoolIW, c = pix - r * kPoolIW;
-    const int h = ih0 + r, w = iw0 + c;
-    if (h >= 0 && h < H && w >= 0 && w < W) tile[e] = xin[((size_t)h * W + w) * 8 + cg];
+  const int cg = threadIdx.x & 7;
+  float sc[8], sh[8];
+  load8f(scale + cg * 8, sc);
+  load8f(shift + cg * 8, sh);
+  uint32_t flip[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    flip[q] = (sc[2 * q] < 0.f ? 0x8000u : 0u) | (sc[2 * q + 1] < 0.f ? 0x80000000u : 0u);
+  constexpr int kTileVec = kPoolIH * kPoolIW * 8;
+  if (BRANCHFREE) {
+    constexpr int kIters = (kTileVec + 255) / 256;
+    uint4 v[kIters];
+    int r = 0, c = threadIdx.x >> 3;  // tile pixel of this thread: advances by 32 pixels per iteration (32 < kPoolIW)
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {  // all loads of the thread in flight before the first store
+      const int h = ih0 + r, w = iw0 + c;
+      const bool in = threadIdx.x + 256 * it < kTileVec && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W;
+      v[it] = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);  // (-inf, -inf) in the flipped domain
+      if (in) {
+        v[it] = xin[(h * W + w) * 8 + cg];
+        v[it].x ^= flip[0];
+        v[it].y ^= flip[1];
+        v[it].z ^= flip[2];
+        v[it].w ^= flip[3];
+      }
+      c += 32;
+      if (c >= kPoolIW) {
+        c -= kPoolIW;
+        ++r;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int e = threadIdx.x + 256 * it;
+      if (e < kTileVec) tile[e] = v[it];
+    }
+  } else {
+    for (int e = threadIdx.x; e < kTileVec; e += 256) {
+      const int pix = e >> 3;
+      const int r = pix / kPoolIW, c = pix - r * kPoolIW;
+      const int h = ih0 + r, w = iw0 + c;
+      if (h >= 0 && h < H && w >= 0 && w < W) tile[e] = xin[((size_t)h * W + w) * 8 + cg];
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int item = threadIdx.x + 256 * k;
-    const int cg = item & 7, px = item >> 3;
+    const int px = item >> 3;
     const int tow = px & (kPoolTOW - 1), toh = px >> 4;
     const int oh = oh0 + toh, ow = ow0 + tow;
     if (oh >= Ho || ow >= Wo) continue;
-    float sc[8], sh[8];
-    load8f(scale + cg * 8, sc);
-    load8f(shift + cg * 8, sh);
-    uint32_t flip[4], best2[4], idx2[4];
+    uint32_t best2[4], idx2[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      flip[q] = (sc[2 * q] < 0.f ? 0x8000u : 0u) | (sc[2 * q + 1] < 0.f ? 0x80000000u : 0u);
       best2[q] = 0xFF80FF80u;  // (-inf, -inf)
       idx2[q] = 0u;
     }
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int dh = t / 3, dw = t - 3 * dh;
-      const int h = 2 * oh - 1 + dh, w = 2 * ow - 1 + dw;
-      if (h < 0 || h >= H || w < 0 || w >= W) continue;
+      if (!BRANCHFREE) {
+        const int h = 2 * oh - 1 + dh, w = 2 * ow - 1 + dw;
+        if (h < 0 || h >= H || w < 0 || w >= W) continue;
+      }
       const uint4 v = tile[((2 * toh + dh) * kPoolIW + 2 * tow + dw) * 8 + cg];
       const uint32_t code2 = (uint32_t)t | ((uint32_t)t << 16);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint32_t xw = (q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w))) ^ flip[q];
+        const uint32_t raw = (q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w)));
+        const uint32_t xw = BRANCHFREE ? raw : (raw ^ flip[q]);
         const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&xw);
         const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(&best2[q]);
         const uint32_t m = __hgt2_mask(a, bb);
@@ -486,6 +589,7 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
       for (int u = 0; u < U; ++u) {
         float xv[8], dz[8];
         unpack8(vx[u], xv);
+        if (MODE == 3) relu_mask_words(vm[u], vd[u]);  // masked lanes become +0.0 (what `dz = 0.f` was)
         unpack8(vd[u], dz);
         if (MODE == 1) {
           float yv[8];
@@ -493,11 +597,6 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (yv[j] <= 0.f) dz[j] = 0.f;
-        }
-        if (MODE == 3) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (!((vm[u] >> j) & 1u)) dz[j] = 0.f;
         }
         if (MODE == 4) {
 #pragma unroll
@@ -700,6 +799,50 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
         for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dz[j], fmaf(B[j], xv[j], D[j]));
       }
       reinterpret_cast<uint4*>(dx)[i] = pack8(o);
+    }
+  }
+}
+
+// bn_bwd_apply_kernel<0 | 3, false> for C/8 a power of two <= 256 (see bn_apply_fast_kernel): the three coefficient
+// vectors in registers, no divisions; the ReLU bit mask is applied to the PACKED gradient words (relu_mask_words), so
+// the dz output is the masked input words as they are (no unpack / select / repack).  Same arithmetic per element.
+template <bool MASK, bool DZ>
+__global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(
+    const uint4* __restrict__ x, const uint4* __restrict__ dy, const uint8_t* __restrict__ mask,
+    const float* __restrict__ coefA, const float* __restrict__ coefB, const float* __restrict__ coefD,
+    uint4* __restrict__ dx, uint4* __restrict__ dz_out, int CG, size_t total_vec) {
+  constexpr int U = 2;
+  const size_t stride = (size_t)gridDim.x * 256;
+  const size_t i0 = blockIdx.x * (size_t)256 + threadIdx.x;
+  const int cg = (int)(i0 & (size_t)(CG - 1));
+  float A[8], B[8], D[8];
+  load8f(coefA + cg * 8, A);
+  load8f(coefB + cg * 8, B);
+  load8f(coefD + cg * 8, D);
+  for (size_t i = i0; i < total_vec; i += U * stride) {
+    uint4 vx[U], vd[U];
+    uint32_t vm[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t k = i + u * stride;
+      if (k < total_vec) {
+        vx[u] = ld_stream(x + k);
+        vd[u] = ld_stream(dy + k);
+        if (MASK) vm[u] = mask[k];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t k = i + u * stride;
+      if (k >= total_vec) break;
+      if (MASK) relu_mask_words(vm[u], vd[u]);
+      if (DZ) dz_out[k] = vd[u];
+      float xv[8], dz[8], o[8];
+      unpack8(vx[u], xv);
+      unpack8(vd[u], dz);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dz[j], fmaf(B[j], xv[j], D[j]));
+      dx[k] = pack8(o);
     }
   }
 }
@@ -935,6 +1078,83 @@ __global__ void __launch_bounds__(256, 2) stem_bwd_apply_kernel(
   }
 }
 
+// The same operation with one CTA per (sample, pooled row): the thread index inside the row is (b, cg) by a shift, so
+// the grid-stride kernel's 64-bit divisions (i / CG, % Wo, / Ho per 2x2 block) disappear, and the row bases of the
+// three tensors are loop invariants.  VARIANT 1 keeps the five coefficient vectors in registers (2 CTAs per SM);
+// VARIANT 2 keeps them in shared memory and fits 3 CTAs per SM (the kernel is latency-, not issue-bound: 16 warps per
+// SM issued 44 % of the slots at 0.64 of the HBM peak).  Same arithmetic per element as stem_bwd_apply_kernel.
+template <int VARIANT>
+__global__ void __launch_bounds__(256, VARIANT == 2 ? 3 : 2) stem_bwd_apply_rows_kernel(
+    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dyp, const uint8_t* __restrict__ arg,
+    const float* __restrict__ coefA, const float* __restrict__ coefB, const float* __restrict__ coefD,
+    const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ dx, int C,
+    int cg_shift, int H, int W, int Ho, int Wo) {
+  extern __shared__ float scoef[];  // VARIANT 2: [5][C] = A, B, D, scale, shift
+  const int CG = C >> 3;
+  const int a = (int)(blockIdx.x % (unsigned)Ho);
+  const size_t n = blockIdx.x / (unsigned)Ho;
+  const int cg = threadIdx.x & (CG - 1);
+  float A[8], B[8], D[8], sc[8], sh[8];
+  if (VARIANT == 2) {
+    for (int c = threadIdx.x; c < C; c += 256) {
+      scoef[c] = coefA[c];
+      scoef[C + c] = coefB[c];
+      scoef[2 * C + c] = coefD[c];
+      scoef[3 * C + c] = scale[c];
+      scoef[4 * C + c] = shift[c];
+    }
+    __syncthreads();
+  } else {
+    load8f(coefA + cg * 8, A);
+    load8f(coefB + cg * 8, B);
+    load8f(coefD + cg * 8, D);
+    load8f(scale + cg * 8, sc);
+    load8f(shift + cg * 8, sh);
+  }
+  const int items = Wo << cg_shift;
+  for (int j = threadIdx.x; j < items; j += 256) {
+    const int b = j >> cg_shift;
+    StemRaw raw;
+    stem_raw_load(x, dyp, arg, n, a, b, H, W, Ho, Wo, CG, cg, raw);
+    uint32_t dzw[4][4];
+    stem_route(raw, dzw);
+    uint32_t o[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 cA, cB, cD, cS, cH;
+      if (VARIANT == 2) {
+        const float* base = scoef + cg * 8 + 2 * k;
+        cA = *reinterpret_cast<const float2*>(base);
+        cB = *reinterpret_cast<const float2*>(base + C);
+        cD = *reinterpret_cast<const float2*>(base + 2 * C);
+        cS = *reinterpret_cast<const float2*>(base + 3 * C);
+        cH = *reinterpret_cast<const float2*>(base + 4 * C);
+      } else {
+        cA = make_float2(A[2 * k], A[2 * k + 1]);
+        cB = make_float2(B[2 * k], B[2 * k + 1]);
+        cD = make_float2(D[2 * k], D[2 * k + 1]);
+        cS = make_float2(sc[2 * k], sc[2 * k + 1]);
+        cH = make_float2(sh[2 * k], sh[2 * k + 1]);
+      }
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        const uint32_t xw = word_of(raw.vx[px], k);
+        const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw));
+        float2 fz = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dzw[px][k]));
+        if (fmaf(fx.x, cS.x, cH.x) <= 0.f) fz.x = 0.f;  // ReLU gate of the pre-pool activation
+        if (fmaf(fx.y, cS.y, cH.y) <= 0.f) fz.y = 0.f;
+        const __nv_bfloat162 v = __floats2bfloat162_rn(fmaf(cA.x, fz.x, fmaf(cB.x, fx.x, cD.x)),
+                                                       fmaf(cA.y, fz.y, fmaf(cB.y, fx.y, cD.y)));
+        o[px][k] = *reinterpret_cast<const uint32_t*>(&v);
+      }
+    }
+    uint4* dxb = reinterpret_cast<uint4*>(dx) + ((n * H + 2 * a) * W + 2 * b) * CG + cg;
+#pragma unroll
+    for (int px = 0; px < 4; ++px)
+      if (raw.ok[px]) dxb[(px >> 1) * (W * CG) + (px & 1) * CG] = make_uint4(o[px][0], o[px][1], o[px][2], o[px][3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // global average pool  [N][P][C] bf16 -> [N][C] fp32   and its backward (broadcast / P)
 // ------------------------------------------------------------------------------------------
@@ -991,6 +1211,11 @@ static int stream_grid(size_t total_vec, K kernel, int vec_per_thread = 1) {
   const size_t cap = (size_t)num_sms() * occ;
   size_t b = (total_vec + (size_t)256 * vec_per_thread - 1) / ((size_t)256 * vec_per_thread);
   return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+static bool bn_fast_enabled() {
+  const char* e = getenv("ECGMM_BN_FAST");
+  return !(e && e[0] == '0');
 }
 
 static int check_c(int C, const char* who) {
@@ -1068,6 +1293,25 @@ extern "C" int ecgmm_bn_apply(const ecgmm_bf16* x_, const float* scale, const fl
   bf16* y = reinterpret_cast<bf16*>(y_);
   cudaStream_t st = (cudaStream_t)stream;
   const int CG = C >> 3;
+  // ECGMM_BN_FAST=0: the generic kernels everywhere
+  if (!se && CG <= 256 && (CG & (CG - 1)) == 0 && bn_fast_enabled()) {
+    const uint4* x4 = reinterpret_cast<const uint4*>(x);
+    const uint4* r4 = reinterpret_cast<const uint4*>(res);
+    uint4* y4 = reinterpret_cast<uint4*>(y);
+#define ECGMM_APPLY_FAST(RES_, RELU_)                                                                          \
+  bn_apply_fast_kernel<RES_, RELU_><<<stream_grid(total, bn_apply_fast_kernel<RES_, RELU_>, 2), 256, 0, st>>>( \
+      x4, scale, shift, r4, y4, mask_out, CG, total)
+    if (res && relu)
+      ECGMM_APPLY_FAST(true, true);
+    else if (res)
+      ECGMM_APPLY_FAST(true, false);
+    else if (relu)
+      ECGMM_APPLY_FAST(false, true);
+    else
+      ECGMM_APPLY_FAST(false, false);
+#undef ECGMM_APPLY_FAST
+    return check_launch("bn_apply_fast_kernel");
+  }
 #define ECGMM_APPLY(SE_, RES_, RELU_)                                                                 \
   bn_apply_kernel<SE_, RES_, RELU_><<<stream_grid(total, bn_apply_kernel<SE_, RES_, RELU_>), 256, 0, st>>>( \
       x, scale, shift, se, res, y, mask_out, CG, vps, total)
@@ -1097,9 +1341,14 @@ extern "C" int ecgmm_bn_relu_maxpool(const ecgmm_bf16* x, const float* scale, co
     const int tiles_w = (Wo + kPoolTOW - 1) / kPoolTOW, tiles_h = (Ho + kPoolTOH - 1) / kPoolTOH;
     const long long blocks = (long long)N * tiles_h * tiles_w;
     ECGMM_CHECK(blocks <= 0x7fffffffLL, ECGMM_ERR_SHAPE, "bn_relu_maxpool: extent");
-    bn_relu_maxpool_tiled_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const bf16*>(x), scale, shift, reinterpret_cast<bf16*>(y), argmax, H, W, Ho, Wo, tiles_w,
-        tiles_h);
+    if (getenv("ECGMM_POOL_TILED_V1") || (long long)H * W * 8 > 0x7fffffffLL)  // v2 indexes a sample with 32 bits
+      bn_relu_maxpool_tiled_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const bf16*>(x), scale, shift, reinterpret_cast<bf16*>(y), argmax, H, W, Ho, Wo, tiles_w,
+          tiles_h);
+    else
+      bn_relu_maxpool_tiled_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const bf16*>(x), scale, shift, reinterpret_cast<bf16*>(y), argmax, H, W, Ho, Wo, tiles_w,
+          tiles_h);
     return check_launch("bn_relu_maxpool_tiled_kernel");
   }
   bn_relu_maxpool_kernel<<<stream_grid(total, bn_relu_maxpool_kernel), 256, 0, (cudaStream_t)stream>>>(
@@ -1192,8 +1441,43 @@ extern "C" int ecgmm_bn_bwd_apply(const ecgmm_bf16* x, const ecgmm_bf16* dy, con
     ECGMM_CHECK(!dz_out, ECGMM_ERR_ARG, "bn_bwd_apply: mode 2 does not produce dz_out");
     ECGMM_CHECK(256 % (C >> 3) == 0, ECGMM_ERR_SHAPE, "bn_bwd_apply: mode 2 needs C = 8 * a power of two <= 2048 (got %d)", C);
     const size_t tb = (size_t)N * Ho * Wo * (C >> 3);
-    stem_bwd_apply_kernel<<<stream_grid(tb, stem_bwd_apply_kernel), 256, 0, st>>>(xb, dyb, argmax, coefA, coefB, coefD, scale, shift, dxb,
-                                                           C >> 3, tb, H, W, Ho, Wo);
+    // ECGMM_STEM_BWD_APPLY = 0: the grid-stride kernel; 1: one CTA per pooled row, coefficients in registers;
+    // 2 (default): one CTA per pooled row, coefficients in shared memory
+    const char* ev = getenv("ECGMM_STEM_BWD_APPLY");
+    const int variant = ev ? atoi(ev) : 2;
+    const long long rows = (long long)N * Ho;
+    if (variant == 0 || rows > 0x7fffffffLL) {
+      stem_bwd_apply_kernel<<<stream_grid(tb, stem_bwd_apply_kernel), 256, 0, st>>>(
+          xb, dyb, argmax, coefA, coefB, coefD, scale, shift, dxb, C >> 3, tb, H, W, Ho, Wo);
+    } else {
+      int cg_shift = 0;
+      while ((1 << cg_shift) < (C >> 3)) ++cg_shift;
+      if (variant == 1)
+        stem_bwd_apply_rows_kernel<1><<<(unsigned)rows, 256, 0, st>>>(xb, dyb, argmax, coefA, coefB, coefD, scale,
+                                                                      shift, dxb, C, cg_shift, H, W, Ho, Wo);
+      else
+        stem_bwd_apply_rows_kernel<2><<<(unsigned)rows, 256, (size_t)5 * C * sizeof(float), st>>>(
+            xb, dyb, argmax, coefA, coefB, coefD, scale, shift, dxb, C, cg_shift, H, W, Ho, Wo);
+    }
+  } else if (!se && (mode == 0 || mode == 3) && (C >> 3) <= 256 && ((C >> 3) & ((C >> 3) - 1)) == 0 &&
+             bn_fast_enabled()) {
+    const uint4* x4 = reinterpret_cast<const uint4*>(x);
+    const uint4* d4 = reinterpret_cast<const uint4*>(dy);
+    uint4* dx4 = reinterpret_cast<uint4*>(dx);
+    uint4* dz4 = reinterpret_cast<uint4*>(dz_out);
+#define ECGMM_BWD_FAST(MASK_, DZ_)                                                                                 \
+  bn_bwd_apply_fast_kernel<MASK_, DZ_><<<stream_grid(total, bn_bwd_apply_fast_kernel<MASK_, DZ_>, 2), 256, 0, st>>>( \
+      x4, d4, argmax, coefA, coefB, coefD, dx4, dz4, C >> 3, total)
+    if (mode == 3 && dz_out)
+      ECGMM_BWD_FAST(true, true);
+    else if (mode == 3)
+      ECGMM_BWD_FAST(true, false);
+    else if (dz_out)
+      ECGMM_BWD_FAST(false, true);
+    else
+      ECGMM_BWD_FAST(false, false);
+#undef ECGMM_BWD_FAST
+    return check_launch("bn_bwd_apply_fast_kernel");
   } else if (mode == 3 && se)
     ECGMM_BWD(3, true);
   else if (mode == 3)

@@ -33,6 +33,24 @@ __device__ __forceinline__ uint4 ld_stream(const void* p) {
   return v;
 }
 
+// ReLU bit mask of an 8-channel vector (bit j = channel j, as bn_apply writes it) applied to the four packed bf16
+// words of a gradient vector: one multiply puts bit 2k on the sign of byte 1 and bit 2k+1 on the sign of byte 3 (the
+// two shifted copies of the 8-bit mask do not overlap), prmt.b32's sign-replicate selectors (nibble 8 + i; __byte_perm
+// only honours three bits per nibble) widen them to 16-bit lane masks.  3 instructions per 2 channels; a masked lane
+// becomes +0.0, the value `dz = 0.f` packs to.
+__device__ __forceinline__ uint32_t relu_lane_mask(uint32_t m8, int k) {
+  const uint32_t t = m8 * ((1u << (15 - 2 * k)) + (1u << (30 - 2 * k)));
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(t), "r"(0u), "r"(0xBB99u));
+  return d;
+}
+__device__ __forceinline__ void relu_mask_words(uint32_t m8, uint4& v) {
+  v.x &= relu_lane_mask(m8, 0);
+  v.y &= relu_lane_mask(m8, 1);
+  v.z &= relu_lane_mask(m8, 2);
+  v.w &= relu_lane_mask(m8, 3);
+}
+
 __device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
   const float4 a = reinterpret_cast<const float4*>(p)[0];
   const float4 b = reinterpret_cast<const float4*>(p)[1];

@@ -531,7 +531,67 @@ def test_tiled_stem_maxpool_is_bit_identical(N, H, W, monkeypatch):
     gamma[5] = -0.6
     beta = (0.2 * torch.randn(64, generator=g)).to(DEV)
     st = ops.bn_train_stats(x, gamma, beta, None, None, None, 1e-5, 0.1)
-    y1, a1 = ops.bn_relu_maxpool(x, st)
+    y1, a1 = ops.bn_relu_maxpool(x, st)  # default: branch-free scan over a flipped-domain tile
+    monkeypatch.setenv("ECGMM_POOL_TILED_V1", "1")
+    y2, a2 = ops.bn_relu_maxpool(x, st)  # first tiled version (bounds tests in the scan)
     monkeypatch.setenv("ECGMM_POOL_LEGACY", "1")
     y0, a0 = ops.bn_relu_maxpool(x, st)
     assert torch.equal(y0, y1) and torch.equal(a0, a1)
+    assert torch.equal(y0, y2) and torch.equal(a0, a2)
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 125, 1250), (3, 33, 70), (2, 9, 35), (1, 40, 33), (5, 1, 75)])
+def test_stem_bwd_apply_variants_are_bit_identical(N, H, W, monkeypatch):
+    """stem_bwd_apply_rows_kernel<1|2> (one CTA per pooled row; coefficients in registers / shared memory) against the
+    grid-stride kernel: same arithmetic per element, so dx must be identical, odd heights / widths included."""
+    from ecgmm import ops
+
+    g = gen(f"stembwd{N}{H}{W}")
+    x = nhwc((torch.randn(N, 64, H, W, generator=g) * 1.5).to(DEV).to(BF))
+    gamma = (1 + 0.3 * torch.randn(64, generator=g)).to(DEV)
+    gamma[9] = -0.4
+    beta = (0.2 * torch.randn(64, generator=g)).to(DEV)
+    st = ops.bn_train_stats(x, gamma, beta, None, None, None, 1e-5, 0.1)
+    y, arg = ops.bn_relu_maxpool(x, st)
+    dyp = torch.randn(y.shape, generator=g).to(DEV).to(BF)
+    outs = []
+    for v in ("0", "1", "2"):
+        monkeypatch.setenv("ECGMM_STEM_BWD_APPLY", v)
+        dg, db = torch.empty(64, device=DEV), torch.empty(64, device=DEV)
+        dx, _ = ops.bn_backward(x, dyp, st, gamma, argmax=arg, dgamma=dg, dbeta=db, pooled=y, beta=beta)
+        outs.append((dx, dg, db))
+    for o in outs[1:]:
+        assert all(torch.equal(p, q) for p, q in zip(o, outs[0]))
+
+
+@pytest.mark.parametrize("N,H,W,C", [(3, 63, 625, 64), (2, 7, 13, 64), (5, 1, 310, 128), (4, 8, 79, 512), (3, 5, 9, 2048)])
+def test_bn_fast_paths_are_bit_identical(N, H, W, C, monkeypatch):
+    """bn_apply_fast_kernel / bn_bwd_apply_fast_kernel (coefficients in registers, ReLU bit mask applied to the packed
+    gradient words) against the generic kernels (ECGMM_BN_FAST=0): same arithmetic per element -> identical bits."""
+    from ecgmm import ops
+
+    g = gen(f"bnfast{N}{H}{W}{C}")
+    x = nhwc((torch.randn(N, C, H, W, generator=g) * 1.3 + 0.2).to(DEV).to(BF))
+    res = nhwc(torch.randn(N, C, H, W, generator=g).to(DEV).to(BF))
+    dy = nhwc(torch.randn(N, C, H, W, generator=g).to(DEV).to(BF))
+    dy.view(-1)[::7] = -0.0  # negative zeros must survive the packed masking as they survive unpack -> pack
+    gamma = (1 + 0.3 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(C, generator=g)).to(DEV)
+    st = ops.bn_train_stats(x, gamma, beta, None, None, None, 1e-5, 0.1)
+    outs = []
+    for sw in ("0", "1"):
+        monkeypatch.setenv("ECGMM_BN_FAST", sw)
+        o = []
+        for kw in (dict(relu=True, want_mask=True), dict(res=res, relu=True, want_mask=True), dict(res=res, relu=False),
+                   dict(relu=False)):
+            y, m = ops.bn_apply(x, st, **kw)
+            o += [y] + ([m] if m is not None else [])
+        mask = o[3]  # of the residual + ReLU variant
+        for kw in (dict(mask=mask, want_dz=True), dict(mask=mask), dict(want_dz=True), dict()):
+            dg, db = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+            dx, dz = ops.bn_backward(x, dy, st, gamma, dgamma=dg, dbeta=db, **kw)
+            o += [dx, dg, db] + ([dz] if dz is not None else [])
+        outs.append(o)
+    assert len(outs[0]) == len(outs[1])
+    for k, (p, q) in enumerate(zip(*outs)):
+        assert torch.equal(p.view(torch.int16) if p.dtype == BF else p, q.view(torch.int16) if q.dtype == BF else q), k
