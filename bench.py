@@ -444,7 +444,7 @@ def run_ours(args):
         kname = {"conv_wgrad": "wgrad_halo_kernel<128,T> / <64> + igemm_tn_kernel + their split-K folds (conv weight-gradient)",
                  "conv_fwd": "igemm_nt_pair_kernel + igemm_nt_stack_kernel + igemm_nt_kernel (conv forward)",
                  "conv_dgrad": "igemm_nt_pair_kernel + igemm_nt_stack_kernel + igemm_nt_kernel (conv data-gradient)",
-                 "bn_bwd_apply": "bn_bwd_apply_kernel + stem_bwd_apply_kernel (BatchNorm backward, dx)"}.get(dom, dom)
+                 "bn_bwd_apply": "bn_bwd_apply_fast_kernel / bn_bwd_apply_kernel + stem_bwd_apply_rows_kernel (BatchNorm backward, dx)"}.get(dom, dom)
         # DRAM bytes of this class from the committed `ncu --set full` capture of one training step at per-GPU batch 64
         # (profiles/r02_traffic.json, tools/ncu_traffic_r02.sh), scaled to this run's per-GPU batch, per call of the class
         traffic, traffic_src = None, None

@@ -242,6 +242,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
 // thread keeps its channel group and scale / shift live in registers (the generic kernel pays a 64-bit modulo and four
 // 16-byte coefficient loads per vector: ~140 instructions per 16 bytes, which at the power-capped clock is as much of
 // a limit as the HBM), two vectors per trip.  Same arithmetic per element.
+// (Measured and not kept, profiles/r02gg_ab128.txt: the coefficients in shared memory under a 48-register cap for 5 CTAs
+// per SM - the compiler spills, the residual variant is 1.8x slower; four vectors per trip at 3 CTAs per SM - slower too.)
 template <bool RES, bool RELU>
 __global__ void __launch_bounds__(256) bn_apply_fast_kernel(const uint4* __restrict__ x,
                                                              const float* __restrict__ scale,
@@ -577,13 +579,17 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
     for (; p + (U - 1) * rows < pb; p += U * rows) {
       uint4 vx[U], vd[U], vy[U];
       uint32_t vm[U];
+      if (MODE == 3) {  // the mask bytes first: the first thing the arithmetic below waits for (ncu: 35 % of the stall
+                        // samples sat on their consumer when they were issued behind the 16-byte loads)
+#pragma unroll
+        for (int u = 0; u < U; ++u) vm[u] = arg[sbase + (size_t)(p + u * rows) * CG];
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const size_t i = sbase + (size_t)(p + u * rows) * CG;
         vx[u] = ld_stream(reinterpret_cast<const uint4*>(x) + i);
         vd[u] = ld_stream(reinterpret_cast<const uint4*>(dy) + i);
         if (MODE == 1) vy[u] = ld_stream(reinterpret_cast<const uint4*>(y) + i);
-        if (MODE == 3) vm[u] = arg[i];
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -826,9 +832,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(
     for (int u = 0; u < U; ++u) {
       const size_t k = i + u * stride;
       if (k < total_vec) {
+        if (MASK) vm[u] = mask[k];
         vx[u] = ld_stream(x + k);
         vd[u] = ld_stream(dy + k);
-        if (MASK) vm[u] = mask[k];
       }
     }
 #pragma unroll
@@ -1213,6 +1219,7 @@ static int stream_grid(size_t total_vec, K kernel, int vec_per_thread = 1) {
   return (int)(b < cap ? (b ? b : 1) : cap);
 }
 
+// ECGMM_BN_FAST=0: the generic BatchNorm apply / backward-apply kernels everywhere
 static bool bn_fast_enabled() {
   const char* e = getenv("ECGMM_BN_FAST");
   return !(e && e[0] == '0');

@@ -592,6 +592,8 @@ def test_bn_fast_paths_are_bit_identical(N, H, W, C, monkeypatch):
             dx, dz = ops.bn_backward(x, dy, st, gamma, dgamma=dg, dbeta=db, **kw)
             o += [dx, dg, db] + ([dz] if dz is not None else [])
         outs.append(o)
-    assert len(outs[0]) == len(outs[1])
-    for k, (p, q) in enumerate(zip(*outs)):
-        assert torch.equal(p.view(torch.int16) if p.dtype == BF else p, q.view(torch.int16) if q.dtype == BF else q), k
+    bits = lambda t: t.view(torch.int16) if t.dtype == BF else t  # noqa: E731  (compare -0.0 / +0.0 as bit patterns)
+    for v, o in enumerate(outs[1:], 1):
+        assert len(o) == len(outs[0])
+        for k, (p, q) in enumerate(zip(outs[0], o)):
+            assert torch.equal(bits(p), bits(q)), (v, k)

@@ -7,6 +7,8 @@ Variants are selected per call through the library's environment switches:
     ECGMM_POOL_LEGACY / ECGMM_POOL_TILED_V1     bn_relu_maxpool: per-output kernel / tiled v1 / tiled branch-free (default)
     ECGMM_STEM_BWD_APPLY=0|1|2                  stem_bwd_apply: grid-stride / CTA per pooled row (regs) / (smem, default)
     ECGMM_BN_FAST=0                             bn_apply / bn_bwd_apply: generic kernels / register-resident coefficients (default)
+(profiles/r02gg_ab128.txt also holds two variants that were measured and removed: coefficients in shared memory with a
+register cap for 5 CTAs per SM, and four vectors per trip.)
 """
 import argparse
 import json
@@ -122,7 +124,7 @@ def main():
         g2, b2 = torch.randn(c, device=dev), torch.randn(c, device=dev)
         s2 = ops.bn_train_stats(xx, g2, b2, None, None, None, 1e-5, 0.1)
         res, keep = {}, {}
-        for tag, env in (("generic", dict(ECGMM_BN_FAST="0")), ("fast", {})):
+        for tag, env in (("generic", dict(ECGMM_BN_FAST="0")), ("fast", dict(ECGMM_BN_FAST="1"))):
             with Env(ECGMM_BN_FAST=None):
                 with Env(**env):
                     y1, m1 = ops.bn_apply(xx, s2, relu=True, want_mask=True)

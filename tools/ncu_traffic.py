@@ -75,7 +75,8 @@ def main():
     total = sum(x["us"] for x in ls)
     result = {"source": f"{os.path.basename(path)}: ncu --profile-from-start off --metrics (time, dram__bytes_read.sum, "
                         "dram__bytes_write.sum, tensor pipe %, dram %) --clock-control none over every launch of the third "
-                        "training step of tools/one_step.py at per-GPU batch 64 (tools/ncu_traffic_r02.sh), classified by "
+                        "training step of tools/one_step.py at per-GPU batch 64 (tools/ncu_traffic_r02.sh; the shipping build: "
+                        "tools/r02_call_gg.sh), classified by "
                         "tools/ncu_traffic.py", "per_gpu_batch": 64, "classes": {}}
     print(f"# {path}: {len(ls)} launches of one training step at batch 64, {total:.0f} us of device time "
           "(cold-cache, serialised under ncu: compare shares)")
