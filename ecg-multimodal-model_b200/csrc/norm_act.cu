@@ -297,6 +297,77 @@ __global__ void __launch_bounds__(256) bn_apply_fast_kernel(const uint4* __restr
   }
 }
 
+// The same kernel with its loads staged through a thread-private cp.async ring (vec.cuh): ncu showed the register
+// version waiting on the long scoreboard at 48 % occupancy with 25-40 % of the issue slots used - the bytes a thread
+// can have in flight are bounded by the registers that receive them, and every warp alternates "wait for the trip's
+// loads" and "compute".  Here a thread keeps kAsyncStages - 1 future vectors in flight in shared memory (3 CTAs x 256
+// threads x 7 x 16-32 bytes per SM) while it computes on the oldest one.  Same arithmetic per element, same order.
+constexpr int kAsyncStages = 8;
+
+template <bool RES, bool RELU>
+__global__ void __launch_bounds__(256, 3) bn_apply_async_kernel(const uint4* __restrict__ x,
+                                                                 const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift,
+                                                                 const uint4* __restrict__ res,
+                                                                 uint4* __restrict__ y,
+                                                                 uint8_t* __restrict__ mask_out, int CG,
+                                                                 size_t total_vec) {
+  constexpr int S = kAsyncStages, T = RES ? 2 : 1;
+  extern __shared__ uint4 ring[];  // [S][T][256]
+  const size_t stride = (size_t)gridDim.x * 256;
+  const size_t i0 = blockIdx.x * (size_t)256 + threadIdx.x;
+  const int cg = (int)(i0 & (size_t)(CG - 1));
+  float sc[8], sh[8];
+  load8f(scale + cg * 8, sc);
+  load8f(shift + cg * 8, sh);
+  uint4* slot0 = ring + threadIdx.x;
+#pragma unroll
+  for (int s = 0; s < S - 1; ++s) {  // prologue: the first S - 1 vectors of this thread
+    const size_t k = i0 + s * stride;
+    if (k < total_vec) {
+      cp_async16(slot0 + (s * T) * 256, x + k);
+      if (RES) cp_async16(slot0 + (s * T + 1) * 256, res + k);
+    }
+    cp_async_commit();
+  }
+  for (size_t base = i0; base < total_vec; base += S * stride) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const size_t k = base + s * stride;
+      if (k >= total_vec) break;
+      const size_t kn = k + (S - 1) * stride;  // goes into the slot that was consumed one iteration ago
+      const int sn = (s + S - 1) % S;
+      if (kn < total_vec) {
+        cp_async16(slot0 + (sn * T) * 256, x + kn);
+        if (RES) cp_async16(slot0 + (sn * T + 1) * 256, res + kn);
+      }
+      cp_async_commit();
+      cp_async_wait<S - 1>();  // all but the S - 1 newest groups have landed: vector k is in its slot
+      float f[8];
+      unpack8(slot0[(s * T) * 256], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (RES) {
+        float r[8];
+        unpack8(slot0[(s * T + 1) * 256], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += r[j];
+      }
+      if (RELU) {
+        if (mask_out) {
+          uint32_t m = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m |= (f[j] > 0.f ? 1u : 0u) << j;
+          mask_out[k] = (uint8_t)m;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      y[k] = pack8(f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // stem: y = maxpool3x3/s2/p1(relu(x*scale + shift)), arg = position of the maximum inside the
 // window (first maximum in row-major window order, torch's tie rule), 0..8
@@ -670,6 +741,96 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
   }
 }
 
+// bn_bwd_reduce_kernel<0 | 3> with x and dy staged through the thread-private cp.async ring (bn_apply_async_kernel): a
+// thread walks its pixels p = pa + r, pa + r + rows, ... one vector at a time with kRedStages - 1 copies in flight, and
+// accumulates in exactly the order of the register kernel (bit-identical partial rows).
+constexpr int kRedStages = 6;
+
+template <int MODE>
+__global__ void __launch_bounds__(kRedThreads, 3) bn_bwd_reduce_async_kernel(
+    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ arg,
+    const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ p1, float* __restrict__ p2,
+    int P, int C, int rows_per_split) {
+  static_assert(MODE == 0 || MODE == 3, "register kernel for the other modes");
+  constexpr int S = kRedStages;
+  extern __shared__ uint4 ring[];  // [S][2][256] uint4, then the [2][rows][C] float fold area
+  float* sred = reinterpret_cast<float*>(ring + S * 2 * kRedThreads);
+  const int CG = C >> 3;
+  const int rows = kRedThreads / CG;
+  const int cg = threadIdx.x % CG, r = threadIdx.x / CG;
+  const int n = blockIdx.y, split = blockIdx.x;
+  const int pa = split * rows_per_split;
+  const int pb = min(P, pa + rows_per_split);
+  float mu[8], is[8], s[8], q[8];
+  load8f(mean + cg * 8, mu);
+  load8f(invstd + cg * 8, is);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  const uint4* xv4 = reinterpret_cast<const uint4*>(x) + (size_t)n * P * CG + cg;
+  const uint4* dv4 = reinterpret_cast<const uint4*>(dy) + (size_t)n * P * CG + cg;
+  const uint8_t* mk = arg + (size_t)n * P * CG + cg;
+  uint4* slot0 = ring + threadIdx.x;
+  uint32_t mreg[S];
+#pragma unroll
+  for (int t = 0; t < S; ++t) mreg[t] = 0;
+  const int p0 = pa + r;
+#pragma unroll
+  for (int t = 0; t < S - 1; ++t) {
+    const int p = p0 + t * rows;
+    if (p < pb) {
+      if (MODE == 3) mreg[t] = mk[(size_t)p * CG];
+      cp_async16(slot0 + (2 * t) * kRedThreads, xv4 + (size_t)p * CG);
+      cp_async16(slot0 + (2 * t + 1) * kRedThreads, dv4 + (size_t)p * CG);
+    }
+    cp_async_commit();
+  }
+  for (int base = p0; base < pb; base += S * rows) {
+#pragma unroll
+    for (int t = 0; t < S; ++t) {
+      const int p = base + t * rows;
+      if (p >= pb) break;
+      const int pn = p + (S - 1) * rows;
+      const int tn = (t + S - 1) % S;
+      if (pn < pb) {
+        if (MODE == 3) mreg[tn] = mk[(size_t)pn * CG];
+        cp_async16(slot0 + (2 * tn) * kRedThreads, xv4 + (size_t)pn * CG);
+        cp_async16(slot0 + (2 * tn + 1) * kRedThreads, dv4 + (size_t)pn * CG);
+      }
+      cp_async_commit();
+      cp_async_wait<S - 1>();
+      const uint4 vx = slot0[(2 * t) * kRedThreads];
+      uint4 vd = slot0[(2 * t + 1) * kRedThreads];
+      if (MODE == 3) relu_mask_words(mreg[t], vd);
+      float xv[8], dz[8];
+      unpack8(vx, xv);
+      unpack8(vd, dz);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += dz[j];
+        q[j] = fmaf(dz[j], (xv[j] - mu[j]) * is[j], q[j]);
+      }
+    }
+  }
+  float* ss = sred;
+  float* sq = sred + rows * C;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ss[r * C + cg * 8 + j] = s[j];
+    sq[r * C + cg * 8 + j] = q[j];
+  }
+  __syncthreads();
+  const size_t orow = ((size_t)n * gridDim.x + split) * C;
+  for (int c = threadIdx.x; c < C; c += kRedThreads) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < rows; ++i) {
+      a += ss[i * C + c];
+      b += sq[i * C + c];
+    }
+    p1[orow + c] = a;
+    p2[orow + c] = b;
+  }
+}
+
 // Fold the backward partials.  With du = dz*se[n][c] + q[n][c] (SE blocks; se = 1, q = 0
 // otherwise) the BatchNorm backward is   dx = A*se*dz + B*x + D + A*q   with per-channel
 //   A = gamma*invstd,  B = -gamma*invstd^2*m2,  D = -A*m1 + gamma*invstd^2*mean*m2,
@@ -846,6 +1007,64 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(
       float xv[8], dz[8], o[8];
       unpack8(vx[u], xv);
       unpack8(vd[u], dz);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dz[j], fmaf(B[j], xv[j], D[j]));
+      dx[k] = pack8(o);
+    }
+  }
+}
+
+// bn_bwd_apply_fast_kernel with x and dy staged through the thread-private cp.async ring (see bn_apply_async_kernel);
+// the mask bytes (too small for cp.async) ride in a register ring, loaded S - 1 vectors ahead as well.
+template <bool MASK, bool DZ>
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply_async_kernel(
+    const uint4* __restrict__ x, const uint4* __restrict__ dy, const uint8_t* __restrict__ mask,
+    const float* __restrict__ coefA, const float* __restrict__ coefB, const float* __restrict__ coefD,
+    uint4* __restrict__ dx, uint4* __restrict__ dz_out, int CG, size_t total_vec) {
+  constexpr int S = kAsyncStages;
+  extern __shared__ uint4 ring[];  // [S][2][256]
+  const size_t stride = (size_t)gridDim.x * 256;
+  const size_t i0 = blockIdx.x * (size_t)256 + threadIdx.x;
+  const int cg = (int)(i0 & (size_t)(CG - 1));
+  float A[8], B[8], D[8];
+  load8f(coefA + cg * 8, A);
+  load8f(coefB + cg * 8, B);
+  load8f(coefD + cg * 8, D);
+  uint4* slot0 = ring + threadIdx.x;
+  uint32_t mreg[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) mreg[s] = 0;
+#pragma unroll
+  for (int s = 0; s < S - 1; ++s) {
+    const size_t k = i0 + s * stride;
+    if (k < total_vec) {
+      if (MASK) mreg[s] = mask[k];
+      cp_async16(slot0 + (2 * s) * 256, x + k);
+      cp_async16(slot0 + (2 * s + 1) * 256, dy + k);
+    }
+    cp_async_commit();
+  }
+  for (size_t base = i0; base < total_vec; base += S * stride) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const size_t k = base + s * stride;
+      if (k >= total_vec) break;
+      const size_t kn = k + (S - 1) * stride;
+      const int sn = (s + S - 1) % S;
+      if (kn < total_vec) {
+        if (MASK) mreg[sn] = mask[kn];
+        cp_async16(slot0 + (2 * sn) * 256, x + kn);
+        cp_async16(slot0 + (2 * sn + 1) * 256, dy + kn);
+      }
+      cp_async_commit();
+      cp_async_wait<S - 1>();
+      const uint4 vx = slot0[(2 * s) * 256];
+      uint4 vd = slot0[(2 * s + 1) * 256];
+      if (MASK) relu_mask_words(mreg[s], vd);
+      if (DZ) dz_out[k] = vd;
+      float xv[8], dz[8], o[8];
+      unpack8(vx, xv);
+      unpack8(vd, dz);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], dz[j], fmaf(B[j], xv[j], D[j]));
       dx[k] = pack8(o);
@@ -1219,6 +1438,22 @@ static int stream_grid(size_t total_vec, K kernel, int vec_per_thread = 1) {
   return (int)(b < cap ? (b ? b : 1) : cap);
 }
 
+// ECGMM_BN_ASYNC=0: the register versions of the BatchNorm fast paths (no cp.async ring)
+static bool bn_async_enabled() {
+  const char* e = getenv("ECGMM_BN_ASYNC");
+  return !(e && e[0] == '0');
+}
+
+// Persistent grid of a kernel that needs `bytes` of dynamic shared memory per CTA: opt in above 48 KB once, then
+// SMs x resident CTAs (no partially filled last wave, as stream_grid does for the register kernels).
+template <typename K>
+static int async_grid_cap(K kernel, size_t bytes) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, bytes) != cudaSuccess || occ < 1) occ = 1;
+  return num_sms() * occ;
+}
+
 // ECGMM_BN_FAST=0: the generic BatchNorm apply / backward-apply kernels everywhere
 static bool bn_fast_enabled() {
   const char* e = getenv("ECGMM_BN_FAST");
@@ -1305,9 +1540,19 @@ extern "C" int ecgmm_bn_apply(const ecgmm_bf16* x_, const float* scale, const fl
     const uint4* x4 = reinterpret_cast<const uint4*>(x);
     const uint4* r4 = reinterpret_cast<const uint4*>(res);
     uint4* y4 = reinterpret_cast<uint4*>(y);
-#define ECGMM_APPLY_FAST(RES_, RELU_)                                                                          \
-  bn_apply_fast_kernel<RES_, RELU_><<<stream_grid(total, bn_apply_fast_kernel<RES_, RELU_>, 2), 256, 0, st>>>( \
-      x4, scale, shift, r4, y4, mask_out, CG, total)
+#define ECGMM_APPLY_FAST(RES_, RELU_)                                                                            \
+  do {                                                                                                           \
+    if (bn_async_enabled()) {                                                                                    \
+      constexpr size_t kBytes = (size_t)kAsyncStages * ((RES_) ? 2 : 1) * 256 * sizeof(uint4);                   \
+      static const int cap = async_grid_cap(bn_apply_async_kernel<RES_, RELU_>, kBytes);                         \
+      const size_t want = (total + 255) / 256;                                                                   \
+      bn_apply_async_kernel<RES_, RELU_><<<(unsigned)(want < (size_t)cap ? want : (size_t)cap), 256, kBytes, st>>>( \
+          x4, scale, shift, r4, y4, mask_out, CG, total);                                                        \
+    } else {                                                                                                     \
+      bn_apply_fast_kernel<RES_, RELU_><<<stream_grid(total, bn_apply_fast_kernel<RES_, RELU_>, 2), 256, 0, st>>>( \
+          x4, scale, shift, r4, y4, mask_out, CG, total);                                                        \
+    }                                                                                                            \
+  } while (0)
     if (res && relu)
       ECGMM_APPLY_FAST(true, true);
     else if (res)
@@ -1387,6 +1632,21 @@ extern "C" int ecgmm_bn_bwd_reduce(const ecgmm_bf16* x, const ecgmm_bf16* dy, co
   const bf16* dyb = reinterpret_cast<const bf16*>(dy);
   const bf16* yb = reinterpret_cast<const bf16*>(y);
   const int rps = rows_per_split(P, split);
+  if ((mode == 0 || mode == 3) && bn_async_enabled()) {
+    const size_t bytes = (size_t)kRedStages * 2 * kRedThreads * sizeof(uint4) + smem;
+    if (mode == 0) {
+      static const int once = (cudaFuncSetAttribute(bn_bwd_reduce_async_kernel<0>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024), 0);
+      (void)once;
+      bn_bwd_reduce_async_kernel<0><<<grid, kRedThreads, bytes, st>>>(xb, dyb, argmax, mean, invstd, p1, p2, P, C, rps);
+    } else {
+      static const int once = (cudaFuncSetAttribute(bn_bwd_reduce_async_kernel<3>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024), 0);
+      (void)once;
+      bn_bwd_reduce_async_kernel<3><<<grid, kRedThreads, bytes, st>>>(xb, dyb, argmax, mean, invstd, p1, p2, P, C, rps);
+    }
+    return check_launch("bn_bwd_reduce_async_kernel");
+  }
   if (mode == 0)
     bn_bwd_reduce_kernel<0><<<grid, kRedThreads, smem, st>>>(xb, dyb, yb, argmax, mean, invstd, scale, shift, p1, p2,
                                                              P, C, rps, H, W, Ho, Wo);
@@ -1472,9 +1732,21 @@ extern "C" int ecgmm_bn_bwd_apply(const ecgmm_bf16* x, const ecgmm_bf16* dy, con
     const uint4* d4 = reinterpret_cast<const uint4*>(dy);
     uint4* dx4 = reinterpret_cast<uint4*>(dx);
     uint4* dz4 = reinterpret_cast<uint4*>(dz_out);
-#define ECGMM_BWD_FAST(MASK_, DZ_)                                                                                 \
-  bn_bwd_apply_fast_kernel<MASK_, DZ_><<<stream_grid(total, bn_bwd_apply_fast_kernel<MASK_, DZ_>, 2), 256, 0, st>>>( \
-      x4, d4, argmax, coefA, coefB, coefD, dx4, dz4, C >> 3, total)
+#define ECGMM_BWD_FAST(MASK_, DZ_)                                                                               \
+  do {                                                                                                           \
+    if (bn_async_enabled()) {                                                                                    \
+      constexpr size_t kBytes = (size_t)kAsyncStages * 2 * 256 * sizeof(uint4);                                  \
+      static const int cap = async_grid_cap(bn_bwd_apply_async_kernel<MASK_, DZ_>, kBytes);                      \
+      const size_t want = (total + 255) / 256;                                                                   \
+      bn_bwd_apply_async_kernel<MASK_, DZ_>                                                                      \
+          <<<(unsigned)(want < (size_t)cap ? want : (size_t)cap), 256, kBytes, st>>>(                            \
+              x4, d4, argmax, coefA, coefB, coefD, dx4, dz4, C >> 3, total);                                     \
+    } else {                                                                                                     \
+      bn_bwd_apply_fast_kernel<MASK_, DZ_>                                                                       \
+          <<<stream_grid(total, bn_bwd_apply_fast_kernel<MASK_, DZ_>, 2), 256, 0, st>>>(                         \
+              x4, d4, argmax, coefA, coefB, coefD, dx4, dz4, C >> 3, total);                                     \
+    }                                                                                                            \
+  } while (0)
     if (mode == 3 && dz_out)
       ECGMM_BWD_FAST(true, true);
     else if (mode == 3)

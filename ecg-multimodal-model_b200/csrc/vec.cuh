@@ -51,6 +51,21 @@ __device__ __forceinline__ void relu_mask_words(uint32_t m8, uint4& v) {
   v.w &= relu_lane_mask(m8, 3);
 }
 
+// Ampere-style asynchronous 16-byte copies global -> shared (LDGSTS, L2-only caching).  Used thread-privately by the
+// streaming BatchNorm kernels: a thread copies its own future vectors into its own slots of a shared-memory ring and
+// reads back only those, so cp.async.wait_group is all the synchronisation there is (no barrier, nothing to hang on);
+// the bytes in flight live in shared memory instead of registers.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
   const float4 a = reinterpret_cast<const float4*>(p)[0];
   const float4 b = reinterpret_cast<const float4*>(p)[1];

@@ -564,10 +564,13 @@ def test_stem_bwd_apply_variants_are_bit_identical(N, H, W, monkeypatch):
         assert all(torch.equal(p, q) for p, q in zip(o, outs[0]))
 
 
-@pytest.mark.parametrize("N,H,W,C", [(3, 63, 625, 64), (2, 7, 13, 64), (5, 1, 310, 128), (4, 8, 79, 512), (3, 5, 9, 2048)])
+@pytest.mark.parametrize("N,H,W,C", [(3, 63, 625, 64), (2, 7, 13, 64), (5, 1, 310, 128), (4, 8, 79, 512), (3, 5, 9, 2048),
+                                     (1, 125, 1250, 64), (70, 16, 157, 256), (2, 1, 1, 64)])
 def test_bn_fast_paths_are_bit_identical(N, H, W, C, monkeypatch):
-    """bn_apply_fast_kernel / bn_bwd_apply_fast_kernel (coefficients in registers, ReLU bit mask applied to the packed
-    gradient words) against the generic kernels (ECGMM_BN_FAST=0): same arithmetic per element -> identical bits."""
+    """The BatchNorm fast paths against the generic kernels: (ECGMM_BN_FAST, ECGMM_BN_ASYNC) = (0, 0) generic apply /
+    backward-apply and register reduction; (1, 0) coefficients in registers, ReLU bit mask applied to the packed gradient
+    words; (1, 1) the default: the same arithmetic with the loads staged through a thread-private cp.async ring, in the
+    reduction too.  Same arithmetic per element, same summation order -> identical bits."""
     from ecgmm import ops
 
     g = gen(f"bnfast{N}{H}{W}{C}")
@@ -579,8 +582,9 @@ def test_bn_fast_paths_are_bit_identical(N, H, W, C, monkeypatch):
     beta = (0.2 * torch.randn(C, generator=g)).to(DEV)
     st = ops.bn_train_stats(x, gamma, beta, None, None, None, 1e-5, 0.1)
     outs = []
-    for sw in ("0", "1"):
-        monkeypatch.setenv("ECGMM_BN_FAST", sw)
+    for fast, asyn in (("0", "0"), ("1", "0"), ("1", "1")):
+        monkeypatch.setenv("ECGMM_BN_FAST", fast)
+        monkeypatch.setenv("ECGMM_BN_ASYNC", asyn)
         o = []
         for kw in (dict(relu=True, want_mask=True), dict(res=res, relu=True, want_mask=True), dict(res=res, relu=False),
                    dict(relu=False)):

@@ -7,6 +7,7 @@ Variants are selected per call through the library's environment switches:
     ECGMM_POOL_LEGACY / ECGMM_POOL_TILED_V1     bn_relu_maxpool: per-output kernel / tiled v1 / tiled branch-free (default)
     ECGMM_STEM_BWD_APPLY=0|1|2                  stem_bwd_apply: grid-stride / CTA per pooled row (regs) / (smem, default)
     ECGMM_BN_FAST=0                             bn_apply / bn_bwd_apply: generic kernels / register-resident coefficients (default)
+    ECGMM_BN_ASYNC=0                            ... and bn_bwd_reduce: loads into registers / through a cp.async ring (default)
 (profiles/r02gg_ab128.txt also holds two variants that were measured and removed: coefficients in shared memory with a
 register cap for 5 CTAs per SM, and four vectors per trip.)
 """
@@ -63,6 +64,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--only-bn", action="store_true", help="skip the stem sections")
     a = ap.parse_args()
     lib.require_device()
     dev = "cuda"
@@ -71,49 +73,51 @@ def main():
     flush = torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device=dev)
     rep = {"batch": N, "shape": [H, W, C]}
 
-    x = torch.randn(N, H, W, C, device=dev).to(torch.bfloat16)
-    gamma = (torch.randn(C, device=dev) * 0.5 + 0.2)  # both signs: the flipped-domain scan is exercised
-    beta = torch.randn(C, device=dev) * 0.1
-    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
     nb = torch.zeros((), dtype=torch.int64, device=dev)
-    st = ops.bn_train_stats(x, gamma, beta, rm, rv, nb, 1e-5, 0.1)
+    if not a.only_bn:
+        x = torch.randn(N, H, W, C, device=dev).to(torch.bfloat16)
+        gamma = (torch.randn(C, device=dev) * 0.5 + 0.2)  # both signs: the flipped-domain scan is exercised
+        beta = torch.randn(C, device=dev) * 0.1
+        rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+        nb = torch.zeros((), dtype=torch.int64, device=dev)
+        st = ops.bn_train_stats(x, gamma, beta, rm, rv, nb, 1e-5, 0.1)
 
-    # ---- stem max-pool forward
-    pool = {}
-    outs = {}
-    for name, env in (("per_output", dict(ECGMM_POOL_LEGACY="1")), ("tiled_v1", dict(ECGMM_POOL_TILED_V1="1")),
-                      ("tiled_branchfree", {})):
-        with Env(ECGMM_POOL_LEGACY=None, ECGMM_POOL_TILED_V1=None):
-            with Env(**env):
-                outs[name] = ops.bn_relu_maxpool(x, st)
-                pool[name] = timed(lambda: ops.bn_relu_maxpool(x, st), a.iters, flush)
-    ref = outs["per_output"]
-    pool["bit_equal"] = all(torch.equal(o[0], ref[0]) and torch.equal(o[1], ref[1]) for o in outs.values())
-    nbytes = 2.0 * x.numel() + 3.0 * ref[0].numel()
-    pool["GBs"] = {k: nbytes / (v * 1e-3) / 1e9 for k, v in pool.items() if k != "bit_equal"}
-    rep["bn_relu_maxpool_ms"] = pool
-    y, arg = ref
+        # ---- stem max-pool forward
+        pool = {}
+        outs = {}
+        for name, env in (("per_output", dict(ECGMM_POOL_LEGACY="1")), ("tiled_v1", dict(ECGMM_POOL_TILED_V1="1")),
+                          ("tiled_branchfree", {})):
+            with Env(ECGMM_POOL_LEGACY=None, ECGMM_POOL_TILED_V1=None):
+                with Env(**env):
+                    outs[name] = ops.bn_relu_maxpool(x, st)
+                    pool[name] = timed(lambda: ops.bn_relu_maxpool(x, st), a.iters, flush)
+        ref = outs["per_output"]
+        pool["bit_equal"] = all(torch.equal(o[0], ref[0]) and torch.equal(o[1], ref[1]) for o in outs.values())
+        nbytes = 2.0 * x.numel() + 3.0 * ref[0].numel()
+        pool["GBs"] = {k: nbytes / (v * 1e-3) / 1e9 for k, v in pool.items() if k != "bit_equal"}
+        rep["bn_relu_maxpool_ms"] = pool
+        y, arg = ref
 
-    # ---- stem backward apply (+ the pooled-domain reduction and both finalize kernels in front of it)
-    dy = torch.randn_like(y)
-    dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
-    bwd, douts = {}, {}
-    for v in ("0", "1", "2"):
-        with Env(ECGMM_STEM_BWD_APPLY=v):
-            f = lambda: ops.bn_backward(x, dy, st, gamma, argmax=arg, pooled=y, beta=beta, dgamma=dg, dbeta=db)  # noqa: E731
-            douts[v] = f()[0]
-            ops.PROFILE = []
-            for _ in range(a.iters):
-                flush.add_(1.0)
-                f()
-            torch.cuda.synchronize()
-            ts = sorted(e0.elapsed_time(e1) for k, _, e0, e1, _ in ops.PROFILE if k.startswith("bn_bwd_apply"))
-            ops.PROFILE = None
-            bwd[v] = ts[len(ts) // 2]
-    bwd["bit_equal"] = all(torch.equal(douts[v], douts["0"]) for v in douts)
-    nbytes = 4.0 * x.numel() + 3.0 * dy.numel()
-    bwd["GBs"] = {k: nbytes / (v * 1e-3) / 1e9 for k, v in bwd.items() if k != "bit_equal"}
-    rep["stem_bwd_apply_ms"] = bwd
+        # ---- stem backward apply (+ the pooled-domain reduction and both finalize kernels in front of it)
+        dy = torch.randn_like(y)
+        dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+        bwd, douts = {}, {}
+        for v in ("0", "1", "2"):
+            with Env(ECGMM_STEM_BWD_APPLY=v):
+                f = lambda: ops.bn_backward(x, dy, st, gamma, argmax=arg, pooled=y, beta=beta, dgamma=dg, dbeta=db)  # noqa: E731
+                douts[v] = f()[0]
+                ops.PROFILE = []
+                for _ in range(a.iters):
+                    flush.add_(1.0)
+                    f()
+                torch.cuda.synchronize()
+                ts = sorted(e0.elapsed_time(e1) for k, _, e0, e1, _ in ops.PROFILE if k.startswith("bn_bwd_apply"))
+                ops.PROFILE = None
+                bwd[v] = ts[len(ts) // 2]
+        bwd["bit_equal"] = all(torch.equal(douts[v], douts["0"]) for v in douts)
+        nbytes = 4.0 * x.numel() + 3.0 * dy.numel()
+        bwd["GBs"] = {k: nbytes / (v * 1e-3) / 1e9 for k, v in bwd.items() if k != "bit_equal"}
+        rep["stem_bwd_apply_ms"] = bwd
 
     # ---- BatchNorm apply / backward apply / backward reduce: generic kernels (ECGMM_BN_FAST=0) against the fast paths
     bn = {}
@@ -124,8 +128,9 @@ def main():
         g2, b2 = torch.randn(c, device=dev), torch.randn(c, device=dev)
         s2 = ops.bn_train_stats(xx, g2, b2, None, None, None, 1e-5, 0.1)
         res, keep = {}, {}
-        for tag, env in (("generic", dict(ECGMM_BN_FAST="0")), ("fast", dict(ECGMM_BN_FAST="1"))):
-            with Env(ECGMM_BN_FAST=None):
+        for tag, env in (("generic", dict(ECGMM_BN_FAST="0", ECGMM_BN_ASYNC="0")), ("fast", dict(ECGMM_BN_ASYNC="0")),
+                         ("async", {})):
+            with Env(ECGMM_BN_FAST=None, ECGMM_BN_ASYNC=None):
                 with Env(**env):
                     y1, m1 = ops.bn_apply(xx, s2, relu=True, want_mask=True)
                     y2, m2 = ops.bn_apply(xx, s2, res=rr, relu=True, want_mask=True)
@@ -147,7 +152,7 @@ def main():
                             ts = sorted(e0.elapsed_time(e1) for k, _, e0, e1, _ in ops.PROFILE if k.startswith(pref))
                             res[f"{tag}_{kind}_{pref[7:]}"] = ts[len(ts) // 2]
                         ops.PROFILE = None
-        res["bit_equal"] = all(torch.equal(p, q) for p, q in zip(keep["generic"], keep["fast"]))
+        res["bit_equal"] = all(torch.equal(p, q) for t in ("fast", "async") for p, q in zip(keep["generic"], keep[t]))
         bn[f"C{c}"] = res
     rep["bn_ms"] = bn
     print(json.dumps(rep))
