@@ -297,77 +297,6 @@ __global__ void __launch_bounds__(256) bn_apply_fast_kernel(const uint4* __restr
   }
 }
 
-// The same kernel with its loads staged through a thread-private cp.async ring (vec.cuh): ncu showed the register
-// version waiting on the long scoreboard at 48 % occupancy with 25-40 % of the issue slots used - the bytes a thread
-// can have in flight are bounded by the registers that receive them, and every warp alternates "wait for the trip's
-// loads" and "compute".  Here a thread keeps kAsyncStages - 1 future vectors in flight in shared memory (3 CTAs x 256
-// threads x 7 x 16-32 bytes per SM) while it computes on the oldest one.  Same arithmetic per element, same order.
-constexpr int kAsyncStages = 8;
-
-template <bool RES, bool RELU>
-__global__ void __launch_bounds__(256, 3) bn_apply_async_kernel(const uint4* __restrict__ x,
-                                                                 const float* __restrict__ scale,
-                                                                 const float* __restrict__ shift,
-                                                                 const uint4* __restrict__ res,
-                                                                 uint4* __restrict__ y,
-                                                                 uint8_t* __restrict__ mask_out, int CG,
-                                                                 size_t total_vec) {
-  constexpr int S = kAsyncStages, T = RES ? 2 : 1;
-  extern __shared__ uint4 ring[];  // [S][T][256]
-  const size_t stride = (size_t)gridDim.x * 256;
-  const size_t i0 = blockIdx.x * (size_t)256 + threadIdx.x;
-  const int cg = (int)(i0 & (size_t)(CG - 1));
-  float sc[8], sh[8];
-  load8f(scale + cg * 8, sc);
-  load8f(shift + cg * 8, sh);
-  uint4* slot0 = ring + threadIdx.x;
-#pragma unroll
-  for (int s = 0; s < S - 1; ++s) {  // prologue: the first S - 1 vectors of this thread
-    const size_t k = i0 + s * stride;
-    if (k < total_vec) {
-      cp_async16(slot0 + (s * T) * 256, x + k);
-      if (RES) cp_async16(slot0 + (s * T + 1) * 256, res + k);
-    }
-    cp_async_commit();
-  }
-  for (size_t base = i0; base < total_vec; base += S * stride) {
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const size_t k = base + s * stride;
-      if (k >= total_vec) break;
-      const size_t kn = k + (S - 1) * stride;  // goes into the slot that was consumed one iteration ago
-      const int sn = (s + S - 1) % S;
-      if (kn < total_vec) {
-        cp_async16(slot0 + (sn * T) * 256, x + kn);
-        if (RES) cp_async16(slot0 + (sn * T + 1) * 256, res + kn);
-      }
-      cp_async_commit();
-      cp_async_wait<S - 1>();  // all but the S - 1 newest groups have landed: vector k is in its slot
-      float f[8];
-      unpack8(slot0[(s * T) * 256], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
-      if (RES) {
-        float r[8];
-        unpack8(slot0[(s * T + 1) * 256], r);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] += r[j];
-      }
-      if (RELU) {
-        if (mask_out) {
-          uint32_t m = 0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) m |= (f[j] > 0.f ? 1u : 0u) << j;
-          mask_out[k] = (uint8_t)m;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-      }
-      y[k] = pack8(f);
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // stem: y = maxpool3x3/s2/p1(relu(x*scale + shift)), arg = position of the maximum inside the
 // window (first maximum in row-major window order, torch's tie rule), 0..8
@@ -741,7 +670,7 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(
   }
 }
 
-// bn_bwd_reduce_kernel<0 | 3> with x and dy staged through the thread-private cp.async ring (bn_apply_async_kernel): a
+// bn_bwd_reduce_kernel<0 | 3> with x and dy staged through the thread-private cp.async ring (bn_bwd_apply_async_kernel): a
 // thread walks its pixels p = pa + r, pa + r + rows, ... one vector at a time with kRedStages - 1 copies in flight, and
 // accumulates in exactly the order of the register kernel (bit-identical partial rows).
 constexpr int kRedStages = 6;
@@ -1014,8 +943,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(
   }
 }
 
-// bn_bwd_apply_fast_kernel with x and dy staged through the thread-private cp.async ring (see bn_apply_async_kernel);
-// the mask bytes (too small for cp.async) ride in a register ring, loaded S - 1 vectors ahead as well.
+// bn_bwd_apply_fast_kernel with x and dy staged through a thread-private cp.async ring (vec.cuh).  ncu showed the
+// register version waiting on the long scoreboard at 48 % occupancy with 25 % of the issue slots used: the bytes a
+// thread can have in flight are bounded by the registers that receive them, and every warp alternates "wait for the
+// trip's loads" and "compute".  Here a thread keeps kAsyncStages - 1 future vectors in flight in shared memory (3 CTAs x
+// 256 threads x 7 x 32 bytes = 172 KB per SM) while it computes on the oldest one; the mask bytes (too small for
+// cp.async) ride in a register ring, loaded S - 1 vectors ahead as well.  Same arithmetic per element.  Measured
+// (profiles/r02ii_*): backward-apply -1 ... -12 %, the reduction below -4 ... -16 % (1.00 of the measured HBM peak at
+// batch 512); the forward apply kernel built the same way was 3-8 % SLOWER than its register version and was dropped.
+constexpr int kAsyncStages = 8;
+
 template <bool MASK, bool DZ>
 __global__ void __launch_bounds__(256, 3) bn_bwd_apply_async_kernel(
     const uint4* __restrict__ x, const uint4* __restrict__ dy, const uint8_t* __restrict__ mask,
@@ -1438,7 +1375,7 @@ static int stream_grid(size_t total_vec, K kernel, int vec_per_thread = 1) {
   return (int)(b < cap ? (b ? b : 1) : cap);
 }
 
-// ECGMM_BN_ASYNC=0: the register versions of the BatchNorm fast paths (no cp.async ring)
+// ECGMM_BN_ASYNC=0: the register versions of the BatchNorm backward-apply / backward-reduce kernels (no cp.async ring)
 static bool bn_async_enabled() {
   const char* e = getenv("ECGMM_BN_ASYNC");
   return !(e && e[0] == '0');
@@ -1540,19 +1477,9 @@ extern "C" int ecgmm_bn_apply(const ecgmm_bf16* x_, const float* scale, const fl
     const uint4* x4 = reinterpret_cast<const uint4*>(x);
     const uint4* r4 = reinterpret_cast<const uint4*>(res);
     uint4* y4 = reinterpret_cast<uint4*>(y);
-#define ECGMM_APPLY_FAST(RES_, RELU_)                                                                            \
-  do {                                                                                                           \
-    if (bn_async_enabled()) {                                                                                    \
-      constexpr size_t kBytes = (size_t)kAsyncStages * ((RES_) ? 2 : 1) * 256 * sizeof(uint4);                   \
-      static const int cap = async_grid_cap(bn_apply_async_kernel<RES_, RELU_>, kBytes);                         \
-      const size_t want = (total + 255) / 256;                                                                   \
-      bn_apply_async_kernel<RES_, RELU_><<<(unsigned)(want < (size_t)cap ? want : (size_t)cap), 256, kBytes, st>>>( \
-          x4, scale, shift, r4, y4, mask_out, CG, total);                                                        \
-    } else {                                                                                                     \
-      bn_apply_fast_kernel<RES_, RELU_><<<stream_grid(total, bn_apply_fast_kernel<RES_, RELU_>, 2), 256, 0, st>>>( \
-          x4, scale, shift, r4, y4, mask_out, CG, total);                                                        \
-    }                                                                                                            \
-  } while (0)
+#define ECGMM_APPLY_FAST(RES_, RELU_)                                                                          \
+  bn_apply_fast_kernel<RES_, RELU_><<<stream_grid(total, bn_apply_fast_kernel<RES_, RELU_>, 2), 256, 0, st>>>( \
+      x4, scale, shift, r4, y4, mask_out, CG, total)
     if (res && relu)
       ECGMM_APPLY_FAST(true, true);
     else if (res)

@@ -569,8 +569,8 @@ def test_stem_bwd_apply_variants_are_bit_identical(N, H, W, monkeypatch):
 def test_bn_fast_paths_are_bit_identical(N, H, W, C, monkeypatch):
     """The BatchNorm fast paths against the generic kernels: (ECGMM_BN_FAST, ECGMM_BN_ASYNC) = (0, 0) generic apply /
     backward-apply and register reduction; (1, 0) coefficients in registers, ReLU bit mask applied to the packed gradient
-    words; (1, 1) the default: the same arithmetic with the loads staged through a thread-private cp.async ring, in the
-    reduction too.  Same arithmetic per element, same summation order -> identical bits."""
+    words; (1, 1) the default: backward-apply and backward-reduce with their loads staged through a thread-private
+    cp.async ring.  Same arithmetic per element, same summation order -> identical bits."""
     from ecgmm import ops
 
     g = gen(f"bnfast{N}{H}{W}{C}")

@@ -7,7 +7,7 @@ Variants are selected per call through the library's environment switches:
     ECGMM_POOL_LEGACY / ECGMM_POOL_TILED_V1     bn_relu_maxpool: per-output kernel / tiled v1 / tiled branch-free (default)
     ECGMM_STEM_BWD_APPLY=0|1|2                  stem_bwd_apply: grid-stride / CTA per pooled row (regs) / (smem, default)
     ECGMM_BN_FAST=0                             bn_apply / bn_bwd_apply: generic kernels / register-resident coefficients (default)
-    ECGMM_BN_ASYNC=0                            ... and bn_bwd_reduce: loads into registers / through a cp.async ring (default)
+    ECGMM_BN_ASYNC=0                            bn_bwd_apply / bn_bwd_reduce: loads into registers / through a cp.async ring (default)
 (profiles/r02gg_ab128.txt also holds two variants that were measured and removed: coefficients in shared memory with a
 register cap for 5 CTAs per SM, and four vectors per trip.)
 """
