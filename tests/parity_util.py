@@ -17,6 +17,13 @@ Tolerances (bf16 activations / fp32 accumulation against an fp32 reference; stat
             to its fp32 operator at bf16-ulp level, and whole residual blocks at 3 %.
             Tensors whose reference norm is below GRAD_FLOOR * (largest gradient norm), e.g. Conv1d
             biases (true gradient 0 because BatchNorm follows), only need ||g|| below that floor.
+            Additionally every gradient is compared with the STORAGE-MATCHED oracle (fp32 arithmetic, bf16 rounding at
+            exactly the tensors the product stores as bf16: storage_matched_oracle below) and the worst relative error /
+            cosine are REPORTED (smoke prints them; measured on a B200 at B=4, 64x160: worst rel 0.38, worst cosine
+            0.929, both on layer1.0.bn2.weight).  ECGMM_MATCHED_REL / ECGMM_MATCHED_COS turn that report into an
+            assertion for bisecting (tools/grad_parity_probe.py); they are off by default because even matched rounding
+            points leave the fp32 summation order inside a convolution free, which is enough to flip ReLU decisions
+            (finding 5).
   BN running statistics: max|a-b| <= STAT_TOL * max(1, max|b|)
   Adam step: new parameters equal torch.optim.Adam applied to the SAME gradients to ADAM_ABS
 """
@@ -39,7 +46,7 @@ GRAD_REL = 5e-2
 GRAD_NOISE_X = 3.0
 GRAD_MEDIAN_X = 1.5
 GRAD_FLOOR = 1e-4
-MATCHED_REL = float(os.environ.get("ECGMM_MATCHED_REL", "1e9"))   # calibrated on hardware, see module docstring
+MATCHED_REL = float(os.environ.get("ECGMM_MATCHED_REL", "1e9"))   # report-only by default, see module docstring
 MATCHED_COS = float(os.environ.get("ECGMM_MATCHED_COS", "-1"))
 STAT_TOL = 2e-2
 ADAM_ABS = 2e-6
