@@ -1,11 +1,13 @@
-"""CPU restatements of two bit-level constructions in csrc/ (the compiled kernels are checked bit for bit against their
+"""CPU restatements of three small constructions in csrc/ (the compiled kernels are checked bit for bit against their
 plain siblings on the GPU: test_kernels_gpu.py::test_bn_fast_paths_are_bit_identical / test_tiled_stem_maxpool_is_bit_identical;
 these tests pin the ARITHMETIC the constructions rely on, for every input, without a device).
 
 * vec.cuh relu_lane_mask: ReLU bit mask (bit j = channel j of an 8-channel vector) -> 16-bit lane masks of the four
   packed bf16 words with one multiply and one prmt.b32 in sign-replicate mode;
 * norm_act.cu bn_relu_maxpool_tiled_kernel<true>: the max-pool scan runs on sign-flipped bf16 words with -inf (0xFF80)
-  outside the image, strict > keeps the first maximum."""
+  outside the image, strict > keeps the first maximum;
+* norm_act.cu bn_bwd_apply_async_kernel / bn_bwd_reduce_async_kernel: the slot / commit-group bookkeeping of the
+  thread-private cp.async ring, for any number of vectors per thread."""
 import numpy as np
 
 
@@ -76,3 +78,58 @@ def test_flipped_domain_scan_equals_first_maximum_of_the_affine_map():
             want_t = int(np.argmax(a))  # first maximum
             assert abs(got - max(a[want_t], 0.0)) < 1e-6
             assert idx == want_t  # same tap as torch's tie rule (+0.0 and -0.0 tie in both orders)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The thread-private cp.async ring of bn_bwd_apply_async_kernel / bn_bwd_reduce_async_kernel (norm_act.cu): one thread's
+# bookkeeping, restated.  Vector v of the thread travels in commit group v; iteration v issues the copy of vector
+# v + S - 1 into slot (v + S - 1) % S, commits, waits until at most S - 1 groups are pending and consumes slot v % S.
+def _ring_thread(n_vectors, S, land_early):
+    """Simulates the loop for a thread that owns n_vectors vectors.  land_early: copies land the moment they are issued
+    (catches a slot overwritten before it was consumed); otherwise they land only when wait_group forces them (catches
+    a slot consumed before its copy was guaranteed).  Returns the consumed vector ids in order."""
+    slots = [None] * S              # what is VISIBLE in shared memory
+    pending = []                    # committed groups not yet known complete: lists of (slot, vector)
+    consumed, live = [], set()      # live: vectors copied (or in flight) and not yet consumed
+
+    def issue(group, slot, v):
+        assert all(x != slot for g in pending for x, _ in g), "slot has a copy in flight"
+        assert slots[slot] is None or slots[slot] not in live, "overwrites a vector that was not consumed yet"
+        live.add(v)
+        if land_early:
+            slots[slot] = v
+            group.append((slot, None))
+        else:
+            group.append((slot, v))
+
+    def wait(max_pending):
+        while len(pending) > max_pending:
+            for slot, v in pending.pop(0):
+                if v is not None:
+                    slots[slot] = v
+
+    for s in range(S - 1):          # prologue
+        g = []
+        if s < n_vectors:
+            issue(g, s, s)
+        pending.append(g)
+    v = 0
+    while v < n_vectors:            # the kernel's two nested loops, flattened
+        g = []
+        if v + S - 1 < n_vectors:
+            issue(g, (v + S - 1) % S, v + S - 1)
+        pending.append(g)
+        wait(S - 1)
+        assert slots[v % S] == v, (v, slots)
+        consumed.append(v)
+        live.discard(v)
+        v += 1
+    assert not live
+    return consumed
+
+
+def test_cp_async_ring_bookkeeping():
+    for S in (2, 3, 6, 8):
+        for n in list(range(0, 3 * S + 2)) + [57, 123]:
+            for early in (False, True):
+                assert _ring_thread(n, S, early) == list(range(n)), (S, n, early)
